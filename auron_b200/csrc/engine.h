@@ -1,0 +1,89 @@
+// engine.h -- host runtime: operators (the mirror of DataFusion's ExecutionPlan / RecordBatchStream
+// surface used by datafusion-ext-plans), the task runtime (auron/src/rt.rs NativeExecutionRuntime) and
+// the planner (auron-planner/src/planner.rs PhysicalPlanner::create_plan).
+#pragma once
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+
+#include "arrow_bridge.h"
+#include "common.h"
+#include "expr.h"
+#include "kernels.h"
+
+struct auron_callbacks;   // include/auron_b200.h
+
+namespace auron {
+
+struct Task;
+
+struct MetricSet {
+    std::vector<std::pair<std::string, int64_t>> values;
+    void add(const std::string& name, int64_t v) {
+        for (auto& kv : values)
+            if (kv.first == name) {
+                kv.second += v;
+                return;
+            }
+        values.emplace_back(name, v);
+    }
+};
+
+// A batch plus an optional pending row selection (a filter whose gather has not been materialised)
+struct SelBatch {
+    BatchPtr batch;
+    Buf sel;          // int32 row indices into batch, or nullptr = all rows
+    int64_t n = 0;    // selected row count
+};
+
+// ExecutionPlan + RecordBatchStream in one object: execute() == first next()
+struct Operator {
+    std::string name;
+    Schema out_schema;
+    std::vector<std::unique_ptr<Operator>> children;
+    MetricSet metrics;
+    virtual ~Operator() = default;
+    virtual BatchPtr next(Task& t) = 0;          // nullptr at end of stream
+    virtual SelBatch next_sel(Task& t) {         // default: no pending selection
+        SelBatch s;
+        s.batch = next(t);
+        s.n = s.batch ? s.batch->num_rows : 0;
+        return s;
+    }
+};
+using OperatorPtr = std::unique_ptr<Operator>;
+
+struct Task {
+    Ctx ctx;
+    const auron_callbacks* cb = nullptr;
+    uint32_t stage_id = 0, partition_id = 0;
+    uint64_t task_id = 0;
+    OperatorPtr root;
+    std::string error;
+    bool cancelled = false;
+    bool is_running();
+    explicit Task(int device) : ctx(device) {}
+};
+
+// process-wide registry of device-resident inputs (bench "value" leg; also build-side caches keyed by
+// broadcast id like broadcast_join_exec.rs:579-625)
+void put_device_resource(const std::string& id, std::vector<BatchPtr> batches, const Schema& schema);
+bool get_device_resource(const std::string& id, std::vector<BatchPtr>* batches, Schema* schema);
+void drop_device_resource(const std::string& id);
+
+// planner: TaskDefinition bytes -> Task (operator tree)
+std::unique_ptr<Task> create_task(const uint8_t* task_def, size_t len, const auron_callbacks* cb, int device);
+
+Literal decode_scalar_ipc(const uint8_t* bytes, size_t n);
+
+// operators implemented outside engine.cc
+OperatorPtr make_parquet_scan(Task& t, const uint8_t* node, size_t n);
+OperatorPtr make_shuffle_writer(Task& t, OperatorPtr input, const uint8_t* node, size_t n);
+
+// expression decode (shared by planner + scan pruning)
+ExprPtr decode_expr(const uint8_t* b, size_t n);
+Schema decode_schema(const uint8_t* b, size_t n);
+DType decode_arrow_type(const uint8_t* b, size_t n);
+
+}  // namespace auron

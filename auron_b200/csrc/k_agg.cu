@@ -1,0 +1,654 @@
+// k_agg.cu -- hash aggregation on device (rows A1-A4 of SURVEY.md section 8a).
+//
+// Replaces AggHashMap::upsert_records (datafusion-ext-plans/src/agg/agg_hash_map.rs:77-136) and the
+// Agg::partial_update / partial_merge accumulators (agg/sum.rs:98-157, count.rs:89-157, maxmin.rs:100-296,
+// first.rs, acc.rs:233-395) with ONE fused kernel per chunk: each thread finds-or-inserts its row's key
+// in an open-addressed table in HBM (linear probing, power-of-two capacity, atomicCAS claim) and then
+// scatter-updates every accumulator with native atomics.  A row selection vector (the output of a
+// preceding filter) can be consumed directly so Filter -> HashAggregate never materialises filtered rows.
+//
+// Two key paths:
+//   FAST    one key column of <= 8 bytes (ints, dates, floats by bits, decimal precision <= 18): the slot
+//           stores the 64-bit key itself.  NULL and the EMPTY sentinel value get two dedicated slots.
+//   GENERAL any other key set (multi-column, utf8, wide decimal): the slot stores a representative row
+//           index of the chunk; candidate rows are verified with rowkey_equal (NULL == NULL as the
+//           reference's row-format grouping keys, agg_ctx.rs:233-245).
+// Group output order is unspecified, as in the reference (agg_table.rs:177-205).
+//
+// Roofline: HBM-bound stream over (key + argument) bytes; the table and accumulators are scratch.
+// Algorithmic bytes per row for GROUP BY int64 / SUM(int64) / COUNT = 8 + 8 (+1/8 per validity) = 16 B.
+#include "kernels.h"
+#include "rowkeys.cuh"
+
+namespace auron {
+
+#define LAUNCH_CHECK(ctx)            \
+    do {                             \
+        CUDA_OK(cudaGetLastError()); \
+        launch_count(ctx);           \
+    } while (0)
+
+constexpr int kMaxAccs = 16;
+constexpr uint64_t EMPTY_KEY = 0x8A5C3F1E9D7B2461ull;   // sentinel; a real key with this value uses slot `cap`
+
+struct AccDesc {
+    int32_t kind;
+    int32_t in_type;   // TypeId of the input column
+    const void* in;
+    const uint8_t* in_valid;
+    const uint8_t* extra_valid[3];
+    int32_t n_extra;
+    int32_t in_is_dec64;   // decimal input with precision <= 18 (MIN/MAX use the low word)
+    unsigned long long* acc_lo;
+    unsigned long long* acc_hi;
+    uint8_t* acc_valid;
+};
+struct AccArgs {
+    AccDesc a[kMaxAccs];
+    int32_t n;
+};
+
+struct AccVal {
+    uint64_t lo;
+    int64_t hi;
+};
+
+// order-preserving map of a double onto int64 (IEEE total order)
+__device__ __forceinline__ int64_t f64_to_ordered(double d) {
+    int64_t b = __double_as_longlong(d);
+    return b < 0 ? (b ^ 0x7fffffffffffffffll) : b;
+}
+__device__ __forceinline__ double ordered_to_f64(int64_t o) {
+    int64_t b = o < 0 ? (o ^ 0x7fffffffffffffffll) : o;
+    return __longlong_as_double(b);
+}
+
+__device__ __forceinline__ int64_t load_int(const void* p, int32_t type, int64_t row) {
+    switch (type) {
+        case T_INT8: return ((const int8_t*)p)[row];
+        case T_INT16: return ((const int16_t*)p)[row];
+        case T_INT32: case T_DATE32: return ((const int32_t*)p)[row];
+        case T_DECIMAL128: return (int64_t)((const uint64_t*)p)[row * 2];
+        default: return ((const int64_t*)p)[row];
+    }
+}
+__device__ __forceinline__ double load_f64(const void* p, int32_t type, int64_t row) {
+    if (type == T_FLOAT32) return (double)((const float*)p)[row];
+    if (type == T_FLOAT64) return ((const double*)p)[row];
+    return (double)load_int(p, type, row);
+}
+
+// contribution of one row; returns false when the row contributes nothing (NULL argument)
+__device__ __forceinline__ bool acc_load(const AccDesc& d, int64_t row, int64_t pos, AccVal& v) {
+    bool ok = valid_at(d.in_valid, row);
+    switch (d.kind) {
+        case ACC_SUM_I64: case ACC_ADD_I64:
+            if (!ok) return false;
+            v.lo = (uint64_t)load_int(d.in, d.in_type, row);
+            return true;
+        case ACC_SUM_F64:
+            if (!ok) return false;
+            v.lo = (uint64_t)__double_as_longlong(load_f64(d.in, d.in_type, row));
+            return true;
+        case ACC_SUM_DEC: {
+            if (!ok) return false;
+            ulonglong2 t = ((const ulonglong2*)d.in)[row];
+            v.lo = t.x;
+            v.hi = (int64_t)t.y;
+            return true;
+        }
+        case ACC_COUNT:
+            for (int e = 0; e < d.n_extra; e++) ok = ok && valid_at(d.extra_valid[e], row);
+            if (!ok) return false;
+            v.lo = 1;
+            return true;
+        case ACC_MIN: case ACC_MAX:
+            if (!ok) return false;
+            if (d.in_type == T_FLOAT32 || d.in_type == T_FLOAT64) v.lo = (uint64_t)f64_to_ordered(load_f64(d.in, d.in_type, row));
+            else if (d.in_type == T_BOOL) v.lo = bit_get((const uint8_t*)d.in, row);
+            else v.lo = (uint64_t)load_int(d.in, d.in_type, row);
+            return true;
+        case ACC_FIRST:
+            // merge mode: extra_valid[0] holds the partial's is_set bits (first.rs:50 acc = [value, is_set])
+            if (d.n_extra > 0 && !bit_get(d.extra_valid[0], row)) return false;
+            v.lo = (uint64_t)pos;
+            return true;
+        case ACC_FIRST_IGNORES_NULL:
+            if (!ok) return false;
+            v.lo = (uint64_t)pos;
+            return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ void acc_apply(const AccDesc& d, int64_t slot, const AccVal& v) {
+    switch (d.kind) {
+        case ACC_SUM_I64: case ACC_ADD_I64: case ACC_COUNT:
+            atomicAdd(&d.acc_lo[slot], (unsigned long long)v.lo);   // wrapping, as sum.rs:115
+            break;
+        case ACC_SUM_F64:
+            atomicAdd((double*)&d.acc_lo[slot], __longlong_as_double((int64_t)v.lo));
+            break;
+        case ACC_SUM_DEC: {
+            unsigned long long old = atomicAdd(&d.acc_lo[slot], (unsigned long long)v.lo);
+            unsigned long long carry = (old + v.lo) < old ? 1ull : 0ull;
+            atomicAdd(&d.acc_hi[slot], (unsigned long long)v.hi + carry);
+            break;
+        }
+        case ACC_MIN: case ACC_FIRST: case ACC_FIRST_IGNORES_NULL:
+            atomicMin((long long*)&d.acc_lo[slot], (long long)v.lo);
+            break;
+        case ACC_MAX:
+            atomicMax((long long*)&d.acc_lo[slot], (long long)v.lo);
+            break;
+    }
+    if (d.acc_valid) d.acc_valid[slot] = 1;   // idempotent byte store, no atomic needed
+}
+
+// -------------------------------------------------------------------------------- FAST path
+struct FastKey {
+    const void* data;
+    const uint8_t* validity;
+    int32_t type;
+};
+__device__ __forceinline__ uint64_t load_key64(const FastKey& k, int64_t row) {
+    switch (k.type) {
+        case T_INT8: return (uint64_t)(int64_t)((const int8_t*)k.data)[row];
+        case T_INT16: return (uint64_t)(int64_t)((const int16_t*)k.data)[row];
+        case T_INT32: case T_DATE32: return (uint64_t)(int64_t)((const int32_t*)k.data)[row];
+        case T_FLOAT32: return (uint64_t)((const uint32_t*)k.data)[row];
+        case T_DECIMAL128: return ((const uint64_t*)k.data)[row * 2];
+        default: return ((const uint64_t*)k.data)[row];
+    }
+}
+
+constexpr int kMaxProbe = 128;
+
+__global__ void __launch_bounds__(256) agg_fast_kernel(FastKey key, unsigned long long* __restrict__ table, int64_t cap, AccArgs accs,
+                                                       const int32_t* __restrict__ sel, int64_t n, int32_t* __restrict__ flags) {
+    // flags[0] overflow, flags[1] sentinel-key slot used, flags[2] null slot used
+    int64_t stride = (int64_t)gridDim.x * 256;
+    uint64_t mask = (uint64_t)cap - 1;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+        int64_t row = sel ? (int64_t)sel[i] : i;
+        int64_t slot = -1;
+        if (key.validity && !bit_get(key.validity, row)) {
+            slot = cap + 1;
+            flags[2] = 1;
+        } else {
+            uint64_t k = load_key64(key, row);
+            if (k == EMPTY_KEY) {
+                slot = cap;
+                flags[1] = 1;
+            } else {
+                uint64_t h = mix64(k) & mask;
+                for (int p = 0; p < kMaxProbe; p++) {
+                    unsigned long long cur = table[h];
+                    if (cur == k) { slot = (int64_t)h; break; }
+                    if (cur == EMPTY_KEY) {
+                        unsigned long long old = atomicCAS(&table[h], (unsigned long long)EMPTY_KEY, (unsigned long long)k);
+                        if (old == EMPTY_KEY || old == k) { slot = (int64_t)h; break; }
+                    }
+                    h = (h + 1) & mask;
+                }
+                if (slot < 0) {
+                    flags[0] = 1;
+                    continue;
+                }
+            }
+        }
+        for (int a = 0; a < accs.n; a++) {
+            AccVal v;
+            if (acc_load(accs.a[a], row, i, v)) acc_apply(accs.a[a], slot, v);
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------- GENERAL path
+__global__ void __launch_bounds__(256) agg_general_kernel(RowKeys keys, int32_t* __restrict__ slots, int64_t cap, AccArgs accs,
+                                                          const int32_t* __restrict__ sel, int64_t n, int32_t* __restrict__ flags) {
+    int64_t stride = (int64_t)gridDim.x * 256;
+    uint64_t mask = (uint64_t)cap - 1;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+        int64_t row = sel ? (int64_t)sel[i] : i;
+        uint64_t h = rowkey_hash(keys, row) & mask;
+        int64_t slot = -1;
+        for (int p = 0; p < kMaxProbe; p++) {
+            int32_t cur = slots[h];
+            if (cur < 0) {
+                int32_t old = atomicCAS(&slots[h], -1, (int32_t)row);
+                if (old < 0) { slot = (int64_t)h; break; }
+                cur = old;
+            }
+            if (cur == (int32_t)row || rowkey_equal(keys, cur, keys, row)) { slot = (int64_t)h; break; }
+            h = (h + 1) & mask;
+        }
+        if (slot < 0) {
+            flags[0] = 1;
+            continue;
+        }
+        for (int a = 0; a < accs.n; a++) {
+            AccVal v;
+            if (acc_load(accs.a[a], row, i, v)) acc_apply(accs.a[a], slot, v);
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------- no-key path
+__device__ __forceinline__ void acc_combine(int kind, AccVal& a, bool& av, const AccVal& b, bool bv) {
+    if (!bv) return;
+    if (!av) { a = b; av = true; return; }
+    switch (kind) {
+        case ACC_SUM_I64: case ACC_ADD_I64: case ACC_COUNT: a.lo += b.lo; break;
+        case ACC_SUM_F64: a.lo = (uint64_t)__double_as_longlong(__longlong_as_double((int64_t)a.lo) + __longlong_as_double((int64_t)b.lo)); break;
+        case ACC_SUM_DEC: {
+            i128 r = i128_add({a.lo, a.hi}, {b.lo, b.hi});
+            a.lo = r.lo; a.hi = r.hi;
+            break;
+        }
+        case ACC_MIN: case ACC_FIRST: case ACC_FIRST_IGNORES_NULL: if ((int64_t)b.lo < (int64_t)a.lo) a.lo = b.lo; break;
+        case ACC_MAX: if ((int64_t)b.lo > (int64_t)a.lo) a.lo = b.lo; break;
+    }
+}
+__global__ void __launch_bounds__(256) agg_global_kernel(AccArgs accs, const int32_t* __restrict__ sel, int64_t n) {
+    int64_t stride = (int64_t)gridDim.x * 256;
+    for (int a = 0; a < accs.n; a++) {
+        const AccDesc& d = accs.a[a];
+        AccVal acc = {0, 0};
+        bool av = false;
+        for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+            int64_t row = sel ? (int64_t)sel[i] : i;
+            AccVal v = {0, 0};
+            bool ok = acc_load(d, row, i, v);
+            acc_combine(d.kind, acc, av, v, ok);
+        }
+        for (int off = 16; off; off >>= 1) {
+            AccVal o;
+            o.lo = __shfl_down_sync(FULL_MASK, acc.lo, off);
+            o.hi = __shfl_down_sync(FULL_MASK, acc.hi, off);
+            bool ov = __shfl_down_sync(FULL_MASK, (int)av, off);
+            acc_combine(d.kind, acc, av, o, ov);
+        }
+        if (lane_id() == 0 && av) acc_apply(d, 0, acc);
+    }
+}
+
+// -------------------------------------------------------------------------------- emit
+__global__ void occupied_mask_fast_kernel(const unsigned long long* __restrict__ table, int64_t cap, const int32_t* __restrict__ flags,
+                                          uint32_t* __restrict__ mask) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool occ = false;
+    if (s < cap) occ = table[s] != EMPTY_KEY;
+    else if (s == cap) occ = flags[1] != 0;
+    else if (s == cap + 1) occ = flags[2] != 0;
+    uint32_t w = __ballot_sync(FULL_MASK, occ);
+    if (lane_id() == 0 && s < cap + 2) mask[s >> 5] = w;
+}
+__global__ void occupied_mask_general_kernel(const int32_t* __restrict__ slots, int64_t cap, uint32_t* __restrict__ mask) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool occ = s < cap && slots[s] >= 0;
+    uint32_t w = __ballot_sync(FULL_MASK, occ);
+    if (lane_id() == 0 && s < cap) mask[s >> 5] = w;
+}
+__global__ void gather_i32_kernel(const int32_t* __restrict__ in, const int32_t* __restrict__ idx, int64_t n, int32_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[idx[i]];
+}
+__global__ void __launch_bounds__(256) emit_fast_keys_kernel(const unsigned long long* __restrict__ table, int64_t cap,
+                                                             const int32_t* __restrict__ slot_ids, int64_t g, int32_t type, void* __restrict__ out,
+                                                             uint32_t* __restrict__ out_valid) {
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    bool ok = false;
+    if (i < g) {
+        int64_t s = slot_ids[i];
+        uint64_t k = s < cap ? table[s] : (s == cap ? EMPTY_KEY : 0ull);
+        ok = s != cap + 1;
+        switch (type) {
+            case T_INT8: ((int8_t*)out)[i] = (int8_t)k; break;
+            case T_INT16: ((int16_t*)out)[i] = (int16_t)k; break;
+            case T_INT32: case T_DATE32: case T_FLOAT32: ((uint32_t*)out)[i] = (uint32_t)k; break;
+            case T_DECIMAL128: ((uint64_t*)out)[2 * i] = k; ((int64_t*)out)[2 * i + 1] = ((int64_t)k) < 0 ? -1ll : 0ll; break;
+            default: ((uint64_t*)out)[i] = k; break;
+        }
+    }
+    if (out_valid) {
+        uint32_t w = __ballot_sync(FULL_MASK, ok);
+        if (lane_id() == 0 && i < g) out_valid[i >> 5] = w;
+    }
+}
+// accumulator array -> typed output column.  slot_ids == nullptr: identity (no-key path, one row)
+__global__ void __launch_bounds__(256) emit_acc_kernel(AccDesc d, const int32_t* __restrict__ slot_ids, int64_t g, int32_t out_type,
+                                                       void* __restrict__ out, uint32_t* __restrict__ out_valid) {
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    bool ok = false;
+    if (i < g) {
+        int64_t s = slot_ids ? (int64_t)slot_ids[i] : i;
+        ok = d.acc_valid ? d.acc_valid[s] != 0 : true;
+        uint64_t lo = d.acc_lo[s];
+        switch (d.kind) {
+            case ACC_SUM_DEC:
+                ((uint64_t*)out)[2 * i] = ok ? lo : 0;
+                ((uint64_t*)out)[2 * i + 1] = ok ? d.acc_hi[s] : 0;
+                break;
+            case ACC_SUM_F64:
+                if (out_type == T_FLOAT32) ((float*)out)[i] = ok ? (float)__longlong_as_double((int64_t)lo) : 0.f;
+                else ((uint64_t*)out)[i] = ok ? lo : 0;
+                break;
+            case ACC_MIN: case ACC_MAX: {
+                if (!ok) lo = 0;
+                switch (out_type) {
+                    case T_BOOL: break;  // handled by the bool variant below (never reached)
+                    case T_INT8: ((int8_t*)out)[i] = (int8_t)lo; break;
+                    case T_INT16: ((int16_t*)out)[i] = (int16_t)lo; break;
+                    case T_INT32: case T_DATE32: ((int32_t*)out)[i] = (int32_t)lo; break;
+                    case T_FLOAT32: ((float*)out)[i] = ok ? (float)ordered_to_f64((int64_t)lo) : 0.f; break;
+                    case T_FLOAT64: ((double*)out)[i] = ok ? ordered_to_f64((int64_t)lo) : 0.0; break;
+                    case T_DECIMAL128: ((uint64_t*)out)[2 * i] = lo; ((int64_t*)out)[2 * i + 1] = ((int64_t)lo) < 0 ? -1ll : 0ll; break;
+                    default: ((uint64_t*)out)[i] = lo; break;
+                }
+                break;
+            }
+            case ACC_FIRST: case ACC_FIRST_IGNORES_NULL:
+                ((int32_t*)out)[i] = ok ? (int32_t)lo : -1;   // position; gathered by the host wrapper
+                break;
+            default:
+                ((uint64_t*)out)[i] = lo;
+        }
+    }
+    if (out_valid) {
+        uint32_t w = __ballot_sync(FULL_MASK, ok);
+        if (lane_id() == 0 && i < g) out_valid[i >> 5] = w;
+    }
+}
+__global__ void sel_compose_kernel(const int32_t* __restrict__ pos, const int32_t* __restrict__ sel, int64_t n, int32_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = pos[i] < 0 ? -1 : (sel ? sel[pos[i]] : pos[i]);
+}
+__global__ void nonneg_mask_kernel(const int32_t* __restrict__ pos, int64_t n, uint32_t* __restrict__ bits) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool ok = i < n && pos[i] >= 0;
+    uint32_t w = __ballot_sync(FULL_MASK, ok);
+    if (lane_id() == 0 && i < n) bits[i >> 5] = w;
+}
+
+// -------------------------------------------------------------------------------- host side
+static int64_t next_pow2(int64_t v) {
+    int64_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+static bool fast_key_ok(const std::vector<ColumnPtr>& keys) {
+    if (keys.size() != 1) return false;
+    const DType& t = keys[0]->type;
+    if (t.id == T_DECIMAL128) return t.precision <= 18;
+    return t.width() >= 1 && t.width() <= 8;
+}
+
+struct AccBuffers {
+    std::vector<Buf> lo, hi, valid;
+};
+static AccArgs prepare_accs(Ctx& ctx, const std::vector<AccSpec>& specs, int64_t slots, AccBuffers& bufs) {
+    AURON_CHECK((int)specs.size() <= kMaxAccs, "too many aggregate accumulators in one AggExec");
+    AccArgs args;
+    args.n = (int)specs.size();
+    for (int i = 0; i < args.n; i++) {
+        const AccSpec& s = specs[i];
+        AccDesc& d = args.a[i];
+        memset(&d, 0, sizeof(d));
+        d.kind = s.kind;
+        if (s.input) {
+            d.in = s.input->data ? s.input->data->ptr : nullptr;
+            d.in_valid = s.input->vbits();
+            d.in_type = s.input->type.id;
+            d.in_is_dec64 = s.input->type.id == T_DECIMAL128 && s.input->type.precision <= 18;
+        } else {
+            d.in_type = T_NULL;
+        }
+        AURON_CHECK(s.extra.size() <= 3, "COUNT with more than 4 arguments");
+        d.n_extra = 0;
+        if (s.kind == ACC_COUNT)
+            for (auto& e : s.extra) d.extra_valid[d.n_extra++] = e->vbits();
+        if (s.kind == ACC_FIRST && !s.extra.empty()) {
+            AURON_CHECK(s.extra[0]->type.id == T_BOOL, "FIRST merge needs the is_set boolean column");
+            d.extra_valid[d.n_extra++] = P<uint8_t>(s.extra[0]->data);
+        }
+        if ((s.kind == ACC_MIN || s.kind == ACC_MAX) && s.input) {
+            const DType& t = s.input->type;
+            bool ok = t.is_intlike() || t.is_float() || t.id == T_BOOL || (t.id == T_DECIMAL128 && t.precision <= 18);
+            AURON_CHECK(ok, "MIN/MAX over " + t.str() + " is not supported on device yet");
+        }
+        Buf lo;
+        lo = dalloc(ctx, (size_t)slots * 8);
+        bufs.lo.push_back(lo);
+        d.acc_lo = P<unsigned long long>(lo);
+        if (s.kind == ACC_SUM_DEC) {
+            Buf hi = dalloc_zero(ctx, (size_t)slots * 8);
+            bufs.hi.push_back(hi);
+            d.acc_hi = P<unsigned long long>(hi);
+        } else bufs.hi.push_back(nullptr);
+        if (s.kind == ACC_COUNT || s.kind == ACC_ADD_I64) {
+            bufs.valid.push_back(nullptr);
+        } else {
+            Buf v = dalloc_zero(ctx, (size_t)slots);
+            bufs.valid.push_back(v);
+            d.acc_valid = P<uint8_t>(v);
+        }
+    }
+    return args;
+}
+__global__ void fill_u64_kernel(unsigned long long* p, int64_t n, unsigned long long v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+static void fill_u64(Ctx& ctx, void* p, int64_t n, unsigned long long v) {
+    if (n <= 0) return;
+    fill_u64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx.stream>>>((unsigned long long*)p, n, v);
+    LAUNCH_CHECK(ctx);
+}
+static void init_accs(Ctx& ctx, const std::vector<AccSpec>& specs, AccArgs& args, int64_t slots) {
+    for (int i = 0; i < args.n; i++) {
+        unsigned long long init = 0;
+        switch (specs[i].kind) {
+            case ACC_MIN: case ACC_FIRST: case ACC_FIRST_IGNORES_NULL: init = 0x7fffffffffffffffull; break;
+            case ACC_MAX: init = 0x8000000000000000ull; break;
+            default: init = 0;
+        }
+        if (init == 0) CUDA_OK(cudaMemsetAsync(args.a[i].acc_lo, 0, (size_t)slots * 8, ctx.stream));
+        else fill_u64(ctx, args.a[i].acc_lo, slots, init);
+    }
+}
+
+static unsigned agg_grid(Ctx& ctx, int64_t n) {
+    int64_t blocks = (n + 255) / 256;
+    return (unsigned)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)ctx.sm_count * 8));
+}
+
+// accumulator arrays -> output columns (FIRST yields value column + is_set bool column)
+static void emit_accs(Ctx& ctx, const std::vector<AccSpec>& specs, const AccArgs& args, const int32_t* slot_ids, int64_t g,
+                      const int32_t* sel, std::vector<ColumnPtr>& out) {
+    unsigned blocks = (unsigned)((g + 255) / 256);
+    for (int i = 0; i < args.n; i++) {
+        const AccSpec& s = specs[i];
+        const AccDesc& d = args.a[i];
+        if (s.kind == ACC_FIRST || s.kind == ACC_FIRST_IGNORES_NULL) {
+            Buf pos = dalloc(ctx, (size_t)std::max<int64_t>(g, 1) * 4);
+            Buf rows = dalloc(ctx, (size_t)std::max<int64_t>(g, 1) * 4);
+            auto isset = make_column(ctx, DType(T_BOOL), g, false);
+            if (g) {
+                emit_acc_kernel<<<blocks, 256, 0, ctx.stream>>>(d, slot_ids, g, T_INT32, pos->ptr, nullptr);
+                LAUNCH_CHECK(ctx);
+                sel_compose_kernel<<<blocks, 256, 0, ctx.stream>>>(P<int32_t>(pos), sel, g, P<int32_t>(rows));
+                LAUNCH_CHECK(ctx);
+                nonneg_mask_kernel<<<blocks, 256, 0, ctx.stream>>>(P<int32_t>(pos), g, P<uint32_t>(isset->data));
+                LAUNCH_CHECK(ctx);
+            }
+            out.push_back(take(ctx, s.gather_from ? *s.gather_from : *s.input, P<int32_t>(rows), g, true));
+            if (s.kind == ACC_FIRST) out.push_back(isset);
+            continue;
+        }
+        bool nullable = d.acc_valid != nullptr;
+        if (s.out_type.id == T_BOOL) {   // MIN/MAX over bool: emit as int8 then it is tiny; convert through take of a 2-entry table
+            fail("MIN/MAX(bool) output not supported yet");
+        }
+        auto col = make_column(ctx, s.out_type, g, nullable);
+        if (g) {
+            emit_acc_kernel<<<blocks, 256, 0, ctx.stream>>>(d, slot_ids, g, s.out_type.id, col->data->ptr, P<uint32_t>(col->validity));
+            LAUNCH_CHECK(ctx);
+        }
+        out.push_back(col);
+    }
+}
+
+GroupedResult hash_aggregate(Ctx& ctx, const std::vector<ColumnPtr>& keys, const std::vector<AccSpec>& accs, const int32_t* sel,
+                             int64_t n_rows) {
+    AURON_CHECK(!keys.empty(), "hash_aggregate needs at least one key (use global_aggregate)");
+    AURON_CHECK(n_rows < (int64_t)INT32_MAX, "chunk too large");
+    GroupedResult res;
+    bool fast = fast_key_ok(keys);
+    // capacity: start at 1 Mi slots (covers <= ~500k groups), fall back to 2 x rows on overflow
+    int64_t cap = std::min<int64_t>(next_pow2(std::max<int64_t>(2 * n_rows, 1024)), 1 << 20);
+    for (int attempt = 0;; attempt++) {
+        int64_t slots = cap + 2;
+        AccBuffers bufs;
+        AccArgs args = prepare_accs(ctx, accs, slots, bufs);
+        init_accs(ctx, accs, args, slots);
+        Buf flags = dalloc_zero(ctx, 16);
+        Buf table;
+        if (fast) {
+            table = dalloc(ctx, (size_t)cap * 8);
+            fill_u64(ctx, table->ptr, cap, EMPTY_KEY);
+            FastKey k{keys[0]->data->ptr, keys[0]->vbits(), (int32_t)keys[0]->type.id};
+            if (n_rows) {
+                agg_fast_kernel<<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(k, P<unsigned long long>(table), cap, args, sel, n_rows, P<int32_t>(flags));
+                LAUNCH_CHECK(ctx);
+            }
+        } else {
+            table = dalloc_fill(ctx, (size_t)cap * 4, 0xff);
+            RowKeys rk = make_row_keys(keys);
+            if (n_rows) {
+                agg_general_kernel<<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(rk, P<int32_t>(table), cap, args, sel, n_rows, P<int32_t>(flags));
+                LAUNCH_CHECK(ctx);
+            }
+        }
+        int32_t hflags[4];
+        to_host(ctx, hflags, flags->ptr, 16);
+        if (hflags[0]) {   // table too small: retry with the worst-case capacity
+            AURON_CHECK(attempt == 0, "hash table overflow after resize");
+            cap = next_pow2(std::max<int64_t>(2 * n_rows, 1024));
+            continue;
+        }
+        // dense group ids = occupied slots in slot order
+        int64_t mask_slots = fast ? slots : cap;
+        Buf occ = dalloc(ctx, bitmap_alloc_bytes(mask_slots));
+        unsigned mblocks = (unsigned)((mask_slots + 255) / 256);
+        if (fast) occupied_mask_fast_kernel<<<mblocks, 256, 0, ctx.stream>>>(P<unsigned long long>(table), cap, P<int32_t>(flags), P<uint32_t>(occ));
+        else occupied_mask_general_kernel<<<mblocks, 256, 0, ctx.stream>>>(P<int32_t>(table), cap, P<uint32_t>(occ));
+        LAUNCH_CHECK(ctx);
+        int64_t g = 0;
+        Buf slot_ids = mask_to_indices(ctx, P<uint32_t>(occ), mask_slots, &g);
+        res.num_groups = g;
+        res.keys = std::make_shared<Batch>();
+        res.keys->num_rows = g;
+        unsigned gblocks = (unsigned)((g + 255) / 256);
+        if (fast) {
+            auto kc = make_column(ctx, keys[0]->type, g, keys[0]->may_have_nulls());
+            if (g) {
+                emit_fast_keys_kernel<<<gblocks, 256, 0, ctx.stream>>>(P<unsigned long long>(table), cap, P<int32_t>(slot_ids), g, keys[0]->type.id,
+                                                                       kc->data->ptr, P<uint32_t>(kc->validity));
+                LAUNCH_CHECK(ctx);
+            }
+            res.keys->cols.push_back(kc);
+        } else {
+            Buf rep = dalloc(ctx, (size_t)std::max<int64_t>(g, 1) * 4);
+            if (g) {
+                gather_i32_kernel<<<gblocks, 256, 0, ctx.stream>>>(P<int32_t>(table), P<int32_t>(slot_ids), g, P<int32_t>(rep));
+                LAUNCH_CHECK(ctx);
+            }
+            for (auto& k : keys) res.keys->cols.push_back(take(ctx, *k, P<int32_t>(rep), g, false));
+        }
+        emit_accs(ctx, accs, args, P<int32_t>(slot_ids), g, sel, res.accs);
+        return res;
+    }
+}
+
+std::vector<ColumnPtr> global_aggregate(Ctx& ctx, const std::vector<AccSpec>& accs, const int32_t* sel, int64_t n_rows) {
+    AccBuffers bufs;
+    AccArgs args = prepare_accs(ctx, accs, 1, bufs);
+    init_accs(ctx, accs, args, 1);
+    if (n_rows) {
+        agg_global_kernel<<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(args, sel, n_rows);
+        LAUNCH_CHECK(ctx);
+    }
+    std::vector<ColumnPtr> out;
+    emit_accs(ctx, accs, args, nullptr, 1, sel, out);
+    return out;
+}
+
+RowKeys make_row_keys(const std::vector<ColumnPtr>& cols) {
+    AURON_CHECK((int)cols.size() <= kMaxKeyCols, "too many key columns");
+    RowKeys rk;
+    memset(&rk, 0, sizeof(rk));
+    rk.ncols = (int)cols.size();
+    for (int i = 0; i < rk.ncols; i++) {
+        rk.c[i].data = cols[i]->data ? cols[i]->data->ptr : nullptr;
+        rk.c[i].validity = cols[i]->vbits();
+        rk.c[i].offsets = P<int32_t>(cols[i]->offsets);
+        rk.c[i].type = cols[i]->type.id;
+        rk.c[i].width = cols[i]->type.width();
+    }
+    return rk;
+}
+
+}  // namespace auron
+
+namespace auron {
+// AVG final merge (datafusion-ext-plans/src/agg/avg.rs:151-179): non-decimal = f64(sum) / f64(count);
+// decimal = sum.checked_div_euclid(count) on the unscaled i128 at the same scale; count 0 or NULL sum => NULL.
+__global__ void __launch_bounds__(256) avg_finalize_kernel(const void* __restrict__ sum, const uint8_t* __restrict__ sum_valid, int32_t sum_type,
+                                                           const int64_t* __restrict__ cnt, const uint8_t* __restrict__ cnt_valid, int64_t n,
+                                                           int32_t out_type, void* __restrict__ out, uint32_t* __restrict__ out_valid) {
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    bool ok = false;
+    if (i < n) {
+        int64_t c = valid_at(cnt_valid, i) ? cnt[i] : 0;
+        ok = valid_at(sum_valid, i) && c != 0;
+        if (sum_type == T_DECIMAL128) {
+            i128 q = {0, 0};
+            if (ok) {
+                ulonglong2 s = ((const ulonglong2*)sum)[i];
+                i128 v = {s.x, (int64_t)s.y};
+                bool neg = i128_is_neg(v);
+                i128 a = neg ? i128_neg(v) : v;
+                uint64_t rem;
+                q = u128_divmod_u64(a, (uint64_t)c, &rem);   // c > 0 (a count)
+                if (neg) {
+                    q = i128_neg(q);
+                    if (rem != 0) q = i128_sub(q, {1, 0});   // euclid: remainder stays non-negative
+                }
+            }
+            ((uint64_t*)out)[2 * i] = q.lo;
+            ((int64_t*)out)[2 * i + 1] = q.hi;
+        } else {
+            double s = ok ? (sum_type == T_FLOAT64 ? ((const double*)sum)[i] : (double)((const int64_t*)sum)[i]) : 0.0;
+            double r = ok ? s / (double)c : 0.0;
+            if (out_type == T_FLOAT32) ((float*)out)[i] = (float)r;
+            else ((double*)out)[i] = r;
+        }
+    }
+    uint32_t w = __ballot_sync(FULL_MASK, ok);
+    if (lane_id() == 0 && i < n) out_valid[i >> 5] = w;
+}
+ColumnPtr avg_finalize(Ctx& ctx, const Column& sum, const Column& cnt, const DType& out_type) {
+    AURON_CHECK(cnt.type.id == T_INT64, "AVG count accumulator must be int64");
+    AURON_CHECK(sum.type.id == T_DECIMAL128 || sum.type.id == T_FLOAT64 || sum.type.id == T_INT64, "AVG sum accumulator type " + sum.type.str());
+    AURON_CHECK(out_type.id == T_DECIMAL128 ? sum.type.id == T_DECIMAL128 : out_type.is_float(), "AVG result type " + out_type.str());
+    int64_t n = sum.len;
+    auto out = make_column(ctx, out_type, n, true);
+    if (n) {
+        avg_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx.stream>>>(sum.data->ptr, sum.vbits(), sum.type.id, P<int64_t>(cnt.data), cnt.vbits(), n,
+                                                                                 out_type.id, out->data->ptr, P<uint32_t>(out->validity));
+        LAUNCH_CHECK(ctx);
+    }
+    return out;
+}
+}  // namespace auron

@@ -1,0 +1,129 @@
+// k_hash.cu -- Spark-compatible murmur3 / xxhash64 over Arrow columns and the shuffle partition id
+// (row S3 of SURVEY.md section 8a).  Replaces create_murmur3_hashes / create_xxhash64_hashes
+// (datafusion-ext-commons/src/spark_hash.rs:28-224) and evaluate_partition_ids
+// (datafusion-ext-plans/src/shuffle/mod.rs:163-188).
+//
+// HBM-bound: algorithmic bytes per row = sum of key value widths (+1/8 B validity) in, 4 B (ids) out.
+// One fused kernel walks all key columns of a row in registers (the reference makes one pass per
+// column over a hash buffer); fixed-width columns are read with coalesced per-thread loads in a
+// grid-stride loop; utf8 rows are hashed one thread per row (neighbouring rows share cache lines).
+#include "device_utils.cuh"
+#include "kernels.h"
+
+namespace auron {
+
+struct HashCol {
+    const void* data;
+    const uint8_t* validity;
+    const int32_t* offsets;
+    int32_t type;
+};
+constexpr int kMaxHashCols = 16;
+struct HashArgs {
+    HashCol c[kMaxHashCols];
+    int32_t ncols;
+};
+
+template <int KIND>
+__device__ __forceinline__ uint64_t hash_one(const HashCol& col, int64_t row, uint64_t h) {
+    if (col.validity && !bit_get(col.validity, row)) return h;  // NULL leaves the running hash (spark_hash.rs:78-84)
+    switch (col.type) {
+        case T_BOOL: {  // bool -> u32 1/0 (:131-158)
+            uint32_t v = bit_get((const uint8_t*)col.data, row) ? 1u : 0u;
+            return KIND == 0 ? (uint64_t)murmur3_u32(v, (uint32_t)h) : xxhash64_u32(v, h);
+        }
+        case T_INT8: {  // i8/i16 are widened to i32 (:160-165)
+            uint32_t v = (uint32_t)(int32_t)((const int8_t*)col.data)[row];
+            return KIND == 0 ? (uint64_t)murmur3_u32(v, (uint32_t)h) : xxhash64_u32(v, h);
+        }
+        case T_INT16: {
+            uint32_t v = (uint32_t)(int32_t)((const int16_t*)col.data)[row];
+            return KIND == 0 ? (uint64_t)murmur3_u32(v, (uint32_t)h) : xxhash64_u32(v, h);
+        }
+        case T_INT32: case T_DATE32: case T_FLOAT32: {
+            uint32_t v = ((const uint32_t*)col.data)[row];
+            return KIND == 0 ? (uint64_t)murmur3_u32(v, (uint32_t)h) : xxhash64_u32(v, h);
+        }
+        case T_INT64: case T_DATE64: case T_TIMESTAMP: case T_FLOAT64: {
+            uint64_t v = ((const uint64_t*)col.data)[row];
+            return KIND == 0 ? (uint64_t)murmur3_u64(v, (uint32_t)h) : xxhash64_u64(v, h);
+        }
+        case T_DECIMAL128: {  // 16 LE bytes (:110-129)
+            ulonglong2 v = ((const ulonglong2*)col.data)[row];
+            return KIND == 0 ? (uint64_t)murmur3_u128(v.x, v.y, (uint32_t)h) : xxhash64_u128(v.x, v.y, h);
+        }
+        case T_UTF8: case T_BINARY: {
+            int32_t b = col.offsets[row], e = col.offsets[row + 1];
+            const uint8_t* p = (const uint8_t*)col.data + b;
+            return KIND == 0 ? (uint64_t)murmur3_bytes(p, e - b, (uint32_t)h) : xxhash64_bytes(p, e - b, h);
+        }
+        default: return h;
+    }
+}
+
+// OUT_MODE 0: raw hash (int32 for murmur3, int64 for xxhash64); 1: pmod partition id (murmur3 only)
+template <int KIND, int OUT_MODE>
+__global__ void __launch_bounds__(256) hash_rows_kernel(HashArgs a, int64_t n, uint64_t seed, int32_t num_parts, void* __restrict__ out) {
+    int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x; row < n; row += stride) {
+        uint64_t h = seed;
+        for (int c = 0; c < a.ncols; c++) h = hash_one<KIND>(a.c[c], row, h);
+        if (KIND == 0) {
+            int32_t hv = (int32_t)(uint32_t)h;
+            if (OUT_MODE == 1) {
+                int32_t r = hv % num_parts;   // rem_euclid (shuffle/mod.rs:178-188)
+                if (r < 0) r += num_parts;
+                hv = r;
+            }
+            ((int32_t*)out)[row] = hv;
+        } else {
+            ((int64_t*)out)[row] = (int64_t)h;
+        }
+    }
+}
+
+static HashArgs make_args(const std::vector<ColumnPtr>& cols) {
+    AURON_CHECK((int)cols.size() <= kMaxHashCols, "too many hash columns");
+    HashArgs a;
+    a.ncols = (int)cols.size();
+    for (int i = 0; i < a.ncols; i++) {
+        a.c[i].data = cols[i]->data ? cols[i]->data->ptr : nullptr;
+        a.c[i].validity = cols[i]->vbits();
+        a.c[i].offsets = P<int32_t>(cols[i]->offsets);
+        a.c[i].type = cols[i]->type.id;
+        if (cols[i]->type.id == T_NULL) a.c[i].type = T_NULL;
+    }
+    return a;
+}
+
+static unsigned grid_for(Ctx& ctx, int64_t n) {
+    int64_t blocks = (n + 255) / 256;
+    int64_t cap = (int64_t)ctx.sm_count * 16;   // 16 x 256-thread CTAs per SM = 2 full waves of resident warps
+    return (unsigned)std::max<int64_t>(1, std::min(blocks, cap));
+}
+
+Buf hash_columns(Ctx& ctx, const std::vector<ColumnPtr>& cols, int64_t n, int kind, int64_t seed) {
+    HashArgs a = make_args(cols);
+    Buf out = dalloc(ctx, (size_t)std::max<int64_t>(n, 1) * (kind == 0 ? 4 : 8));
+    if (n == 0) return out;
+    if (kind == 0)
+        hash_rows_kernel<0, 0><<<grid_for(ctx, n), 256, 0, ctx.stream>>>(a, n, (uint64_t)(uint32_t)(int32_t)seed, 1, out->ptr);
+    else
+        hash_rows_kernel<1, 0><<<grid_for(ctx, n), 256, 0, ctx.stream>>>(a, n, (uint64_t)seed, 1, out->ptr);
+    CUDA_OK(cudaGetLastError());
+    launch_count(ctx);
+    return out;
+}
+
+Buf murmur3_partition_ids(Ctx& ctx, const std::vector<ColumnPtr>& cols, int64_t n, int32_t num_parts, int32_t seed) {
+    AURON_CHECK(num_parts > 0, "num_parts must be positive");
+    HashArgs a = make_args(cols);
+    Buf out = dalloc(ctx, (size_t)std::max<int64_t>(n, 1) * 4);
+    if (n == 0) return out;
+    hash_rows_kernel<0, 1><<<grid_for(ctx, n), 256, 0, ctx.stream>>>(a, n, (uint64_t)(uint32_t)seed, num_parts, out->ptr);
+    CUDA_OK(cudaGetLastError());
+    launch_count(ctx);
+    return out;
+}
+
+}  // namespace auron

@@ -1,0 +1,122 @@
+// kernels.h -- host-callable API of the kernel layer (one entry per device algorithm).
+// All functions enqueue work on ctx.stream; those that return host-side counts synchronise.
+#pragma once
+#include "common.h"
+
+namespace auron {
+
+// ----------------------------------------------------------------------------- k_basic.cu
+void launch_count(Ctx& ctx, int n = 1);
+// exclusive prefix sums; in == out allowed.  If total != nullptr the grand total is written there (device).
+void exclusive_scan_i32(Ctx& ctx, const int32_t* in, int32_t* out, int64_t n, int32_t* total_dev);
+void exclusive_scan_i64(Ctx& ctx, const int64_t* in, int64_t* out, int64_t n, int64_t* total_dev);
+// number of set bits among the first n bits (synchronises)
+int64_t count_set_bits(Ctx& ctx, const uint8_t* bitmap, int64_t n);
+// bitmap -> ascending row indices of set bits; returns count (synchronises)
+Buf mask_to_indices(Ctx& ctx, const uint32_t* mask_words, int64_t n_rows, int64_t* count_out);
+// dst bitmap (pre-zeroed) |= src bits [src_off, src_off+n) placed at dst_off
+void copy_bits(Ctx& ctx, uint8_t* dst, int64_t dst_off, const uint8_t* src, int64_t src_off, int64_t n);
+void fill_iota_i32(Ctx& ctx, int32_t* out, int64_t n, int32_t start);
+// out[i] = a[i] & b[i] over whole words; either may be nullptr (treated as all ones); returns nullptr if both null
+Buf and_bitmaps(Ctx& ctx, const uint8_t* a, const uint8_t* b, int64_t n_bits);
+Buf not_bitmap(Ctx& ctx, const uint8_t* a, int64_t n_bits);
+
+// gather: out[i] = in[idx[i]]; idx[i] < 0 yields NULL (outer joins).  idx == nullptr => identity copy.
+ColumnPtr take(Ctx& ctx, const Column& in, const int32_t* idx, int64_t n_out, bool idx_may_be_negative);
+BatchPtr take_batch(Ctx& ctx, const Batch& in, const int32_t* idx, int64_t n_out, bool idx_may_be_negative);
+ColumnPtr concat_columns(Ctx& ctx, const std::vector<ColumnPtr>& cols);
+BatchPtr concat_batches(Ctx& ctx, const std::vector<BatchPtr>& batches);
+ColumnPtr slice_column(Ctx& ctx, const Column& in, int64_t off, int64_t len);
+BatchPtr slice_batch(Ctx& ctx, const Batch& in, int64_t off, int64_t len);
+
+// ----------------------------------------------------------------------------- k_hash.cu
+// Spark-compatible chained column hashing (spark_hash.rs:28-57). kind 0 murmur3 -> int32 out, 1 xxhash64 -> int64 out
+Buf hash_columns(Ctx& ctx, const std::vector<ColumnPtr>& cols, int64_t n, int kind, int64_t seed);
+// pmod(murmur3(cols, seed 42), num_parts)  (shuffle/mod.rs:163-188) -> int32[n]
+Buf murmur3_partition_ids(Ctx& ctx, const std::vector<ColumnPtr>& cols, int64_t n, int32_t num_parts, int32_t seed = 42);
+
+// ----------------------------------------------------------------------------- k_rowkeys.cu
+// Row-key view over key columns for hash aggregation / joins (general path)
+struct KeyColDesc {
+    const void* data;
+    const uint8_t* validity;
+    const int32_t* offsets;
+    int32_t type;   // TypeId
+    int32_t width;  // bytes (0 => bool bitmap / varlen)
+};
+constexpr int kMaxKeyCols = 8;
+struct RowKeys {
+    KeyColDesc c[kMaxKeyCols];
+    int32_t ncols;
+};
+RowKeys make_row_keys(const std::vector<ColumnPtr>& cols);
+
+// ----------------------------------------------------------------------------- k_agg.cu
+enum AccKind : int32_t {
+    ACC_SUM_I64 = 0,   // in: int64-extended ints (i8..i64) -> acc int64
+    ACC_SUM_F64 = 1,   // in: f32/f64 -> acc f64
+    ACC_SUM_DEC = 2,   // in: decimal128 -> acc decimal128 (wrapping i128)
+    ACC_COUNT = 3,     // +1 when all args valid (up to 4 arg validities) ; acc int64
+    ACC_ADD_I64 = 4,   // merge of COUNT: acc += value
+    ACC_MIN = 5,       // by input type
+    ACC_MAX = 6,
+    ACC_FIRST = 7,     // value of the smallest row index (+ is_set)
+    ACC_FIRST_IGNORES_NULL = 8,
+};
+struct AccSpec {
+    AccKind kind;
+    ColumnPtr input;                  // may be null for COUNT(*) style (no args)
+    std::vector<ColumnPtr> extra;     // extra args for COUNT(a,b,..) validity; FIRST merge: is_set column
+    DType out_type;                   // accumulator column type
+    ColumnPtr gather_from;            // FIRST merge: column the winning position is gathered from (default: input)
+};
+struct GroupedResult {
+    BatchPtr keys;                    // distinct key columns (dense groups)
+    std::vector<ColumnPtr> accs;      // one column per AccSpec (FIRST adds a second bool column after it)
+    int64_t num_groups = 0;
+};
+// Hash-aggregate one device-resident batch.  sel (optional) = row selection (filter fused into the aggregate).
+GroupedResult hash_aggregate(Ctx& ctx, const std::vector<ColumnPtr>& keys, const std::vector<AccSpec>& accs,
+                             const int32_t* sel, int64_t n_rows);
+// no grouping keys: one output row
+std::vector<ColumnPtr> global_aggregate(Ctx& ctx, const std::vector<AccSpec>& accs, const int32_t* sel, int64_t n_rows);
+// AVG final merge (agg/avg.rs:151-179)
+ColumnPtr avg_finalize(Ctx& ctx, const Column& sum, const Column& cnt, const DType& out_type);
+
+// ----------------------------------------------------------------------------- k_join.cu
+struct JoinTable;   // opaque device hash table over build keys
+std::shared_ptr<JoinTable> join_build(Ctx& ctx, const std::vector<ColumnPtr>& build_keys, int64_t n_build);
+bool join_table_has_null_key(const JoinTable& t);
+struct JoinPairs {
+    Buf probe_idx, build_idx;   // int32 each; -1 = no partner (outer)
+    int64_t count = 0;
+};
+// inner pairs (+ unmatched probe rows as (i,-1) when probe_outer).  matched_build (bitmap over build rows,
+// pre-zeroed, may be null) receives matched flags.  probe_matched_out (optional) = bitmap over probe rows.
+JoinPairs join_probe(Ctx& ctx, const JoinTable& t, const std::vector<ColumnPtr>& probe_keys, int64_t n_probe, bool probe_outer,
+                     uint32_t* matched_build, Buf* probe_matched_out);
+
+// ----------------------------------------------------------------------------- k_sort.cu
+struct SortKeySpec {
+    ColumnPtr col;
+    bool asc = true;
+    bool nulls_first = true;
+};
+// returns permutation (int32 row indices) that orders rows by keys (stable)
+Buf sort_indices(Ctx& ctx, const std::vector<SortKeySpec>& keys, int64_t n_rows);
+// stable LSD radix sort of (u64 key, i32 value) pairs, in place over ping-pong buffers; bits [begin_bit, end_bit)
+void radix_sort_pairs_u64(Ctx& ctx, Buf& keys, Buf& vals, int64_t n, int begin_bit, int end_bit);
+// stable counting partition of rows by partition id: returns row order + offsets[num_parts+1] (device int64)
+void partition_rows(Ctx& ctx, const int32_t* part_ids, int64_t n, int32_t num_parts, Buf* rows_out, Buf* offsets_out);
+
+// ----------------------------------------------------------------------------- k_serde.cu
+// Auron compacted batch format (batch_serde.rs:68-147): serialize rows [row_begin,row_end) of each partition
+// segment into one device byte buffer; returns per-partition byte offsets (host) and the device buffer.
+struct SerializedParts {
+    Buf bytes;
+    std::vector<int64_t> part_offsets;   // num_parts+1 (uncompressed payload offsets)
+};
+SerializedParts serialize_partitions(Ctx& ctx, const Batch& sorted_batch, const std::vector<int64_t>& row_offsets);
+BatchPtr deserialize_batch(Ctx& ctx, const Schema& schema, const uint8_t* host_bytes, int64_t nbytes, int64_t* consumed);
+
+}  // namespace auron

@@ -1,0 +1,703 @@
+// operators.cc -- operator implementations (see operators.h for the reference files they mirror).
+// Every operator works on large device-resident chunks; the 10,000-row batch size of the reference
+// (datafusion-ext-commons/src/lib.rs:72-75) only survives as the JVM-facing default and is not part of
+// the result contract.
+#include "operators.h"
+
+#include <algorithm>
+#include <mutex>
+
+#include "../../include/auron_b200.h"
+
+namespace auron {
+
+bool Task::is_running() {
+    if (cancelled) return false;
+    if (cb && cb->is_task_running) return cb->is_task_running(cb->user) != 0;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------ resources
+struct DevResource {
+    std::vector<BatchPtr> batches;
+    Schema schema;
+};
+static std::mutex g_res_mu;
+static std::map<std::string, DevResource> g_resources;
+void put_device_resource(const std::string& id, std::vector<BatchPtr> batches, const Schema& schema) {
+    std::lock_guard<std::mutex> l(g_res_mu);
+    auto& r = g_resources[id];
+    r.schema = schema;
+    for (auto& b : batches) r.batches.push_back(b);
+}
+bool get_device_resource(const std::string& id, std::vector<BatchPtr>* batches, Schema* schema) {
+    std::lock_guard<std::mutex> l(g_res_mu);
+    auto it = g_resources.find(id);
+    if (it == g_resources.end()) return false;
+    if (batches) *batches = it->second.batches;
+    if (schema) *schema = it->second.schema;
+    return true;
+}
+void drop_device_resource(const std::string& id) {
+    std::lock_guard<std::mutex> l(g_res_mu);
+    g_resources.erase(id);
+}
+
+BatchPtr materialize(Task& t, const SelBatch& s) {
+    if (!s.batch) return nullptr;
+    if (!s.sel) return s.batch;
+    return take_batch(t.ctx, *s.batch, P<int32_t>(s.sel), s.n, false);
+}
+
+ColumnPtr eval_to_column(Task& t, const ExprPtr& e, const Schema& schema, const Batch& b) {
+    int idx;
+    if (is_plain_column(*e, schema, &idx)) return b.cols[idx];
+    VmProgram p = compile_projection({e}, schema);
+    return eval_projection(t.ctx, p, b, nullptr, b.num_rows)[0];
+}
+
+// ------------------------------------------------------------------------------------------ FFIReaderExec
+FFIReaderExec::FFIReaderExec(const Schema& schema, const std::string& id) : resource_id(id) {
+    name = "FFIReaderExec";
+    out_schema = schema;
+    Schema rs;
+    if (get_device_resource(id, &dev_batches, &rs)) {
+        is_device = true;
+        AURON_CHECK(rs.fields.size() == schema.fields.size(), "device resource schema mismatch for " + id);
+    }
+}
+BatchPtr FFIReaderExec::next(Task& t) {
+    if (done) return nullptr;
+    if (is_device) {
+        if (dev_pos >= dev_batches.size()) {
+            done = true;
+            return nullptr;
+        }
+        auto b = dev_batches[dev_pos++];
+        metrics.add("output_rows", b->num_rows);
+        return b;
+    }
+    AURON_CHECK(t.cb && t.cb->export_next_batch, "FFIReaderExec needs the export_next_batch callback");
+    std::vector<BatchPtr> got;
+    int64_t rows = 0;
+    while (rows < t.ctx.gpu_chunk_rows) {
+        ArrowArray arr;
+        memset(&arr, 0, sizeof(arr));
+        int rc = t.cb->export_next_batch(t.cb->user, resource_id.c_str(), &arr);
+        if (rc < 0) fail("export_next_batch failed for resource " + resource_id);
+        if (rc == 0) {
+            done = true;
+            break;
+        }
+        BatchPtr b;
+        try {
+            b = import_batch(t.ctx, &arr, out_schema);
+        } catch (...) {
+            if (arr.release) arr.release(&arr);
+            throw;
+        }
+        if (arr.release) arr.release(&arr);   // engine owns the exported array (ffi_reader_exec.rs:182-251)
+        rows += b->num_rows;
+        if (b->num_rows) got.push_back(b);
+    }
+    if (got.empty()) return nullptr;
+    metrics.add("output_rows", rows);
+    return concat_batches(t.ctx, got);
+}
+
+// ------------------------------------------------------------------------------------------ FilterExec
+FilterExec::FilterExec(OperatorPtr input, std::vector<ExprPtr> preds) : predicates(std::move(preds)) {
+    name = "FilterExec";
+    out_schema = input->out_schema;
+    children.push_back(std::move(input));
+    prog = compile_predicate(predicates, out_schema);
+}
+SelBatch FilterExec::next_sel(Task& t) {
+    SelBatch out;
+    BatchPtr b = children[0]->next(t);
+    if (!b) return out;
+    out.batch = b;
+    Buf mask = eval_predicate(t.ctx, prog, *b, b->num_rows);
+    int64_t cnt = 0;
+    Buf idx = mask_to_indices(t.ctx, P<uint32_t>(mask), b->num_rows, &cnt);
+    out.n = cnt;
+    if (cnt != b->num_rows) out.sel = idx;
+    metrics.add("output_rows", cnt);
+    return out;
+}
+BatchPtr FilterExec::next(Task& t) {
+    SelBatch s = next_sel(t);
+    return materialize(t, s);
+}
+
+// ------------------------------------------------------------------------------------------ ProjectExec
+ProjectExec::ProjectExec(OperatorPtr input, std::vector<ExprPtr> ex, std::vector<std::string> names, std::vector<DType> types)
+    : exprs(std::move(ex)) {
+    name = "ProjectExec";
+    const Schema& in = input->out_schema;
+    std::vector<ExprPtr> computed;
+    for (size_t i = 0; i < exprs.size(); i++) {
+        DType actual = infer_type(*exprs[i], in);
+        DType declared = i < types.size() && types[i].id != T_NULL ? types[i] : actual;
+        if (actual != declared) {   // planner.rs:145-149 wraps a TryCastExpr when the declared type differs
+            auto c = std::make_shared<Expr>();
+            c->kind = E_TRY_CAST;
+            c->type = declared;
+            c->children.push_back(exprs[i]);
+            exprs[i] = c;
+        }
+        int idx = -1;
+        if (is_plain_column(*exprs[i], in, &idx)) {
+            plain_col.push_back(idx);
+            prog_slot.push_back(-1);
+        } else {
+            plain_col.push_back(-1);
+            prog_slot.push_back((int)computed.size());
+            computed.push_back(exprs[i]);
+        }
+        Field f;
+        f.name = i < names.size() ? names[i] : ("c" + std::to_string(i));
+        f.type = declared;
+        out_schema.fields.push_back(f);
+    }
+    if (!computed.empty()) {
+        prog = compile_projection(computed, in);
+        has_prog = true;
+    }
+    children.push_back(std::move(input));
+}
+BatchPtr ProjectExec::next(Task& t) {
+    SelBatch s = children[0]->next_sel(t);
+    if (!s.batch) return nullptr;
+    auto out = std::make_shared<Batch>();
+    out->num_rows = s.n;
+    std::vector<ColumnPtr> computed;
+    if (has_prog) computed = eval_projection(t.ctx, prog, *s.batch, P<int32_t>(s.sel), s.n);
+    for (size_t i = 0; i < exprs.size(); i++) {
+        if (plain_col[i] >= 0) {
+            const ColumnPtr& c = s.batch->cols[plain_col[i]];
+            out->cols.push_back(s.sel ? take(t.ctx, *c, P<int32_t>(s.sel), s.n, false) : c);
+        } else {
+            out->cols.push_back(computed[prog_slot[i]]);
+        }
+    }
+    metrics.add("output_rows", s.n);
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------ AggExec
+static bool load_compatible(const DType& child, const DType& acc) {
+    if (child == acc) return true;
+    if (acc.id == T_INT64 && child.is_integer()) return true;
+    if (acc.id == T_FLOAT64 && (child.is_integer() || child.is_float())) return true;
+    if (acc.id == T_DECIMAL128 && child.id == T_DECIMAL128 && child.scale == acc.scale) return true;
+    return false;
+}
+
+AggExec::AggExec(OperatorPtr input, std::vector<ExprPtr> ge, std::vector<std::string> gn, std::vector<AggExprSpec> ag)
+    : group_exprs(std::move(ge)), group_names(std::move(gn)), aggs(std::move(ag)) {
+    name = "AggExec";
+    const Schema& in = input->out_schema;
+    bool any_final = false, any_nonfinal = false;
+    for (auto& a : aggs) {
+        if (a.mode == MODE_FINAL) any_final = true;
+        else any_nonfinal = true;
+    }
+    AURON_CHECK(!(any_final && any_nonfinal), "final aggregates may not be mixed with partial ones (agg_ctx.rs:111)");
+    is_final = any_final;
+    // accumulator layouts (acc_array_data_types of agg/sum.rs, count.rs, avg.rs:52, maxmin.rs, first.rs:50)
+    input_acc_cols = 0;
+    for (auto& a : aggs) {
+        switch (a.fn) {
+            case AGG_SUM: a.acc_types = {a.return_type}; break;
+            case AGG_COUNT: a.acc_types = {DType(T_INT64)}; break;
+            case AGG_AVG: a.acc_types = {a.return_type, DType(T_INT64)}; break;
+            case AGG_MIN: case AGG_MAX: case AGG_FIRST: case AGG_FIRST_IGNORES_NULL: a.acc_types.clear(); break;
+            default: fail("aggregate function " + std::to_string(a.fn) + " is not native on device (collect/bloom/UDAF are out of scope)");
+        }
+        if (a.mode != MODE_PARTIAL) input_acc_cols += (a.fn == AGG_FIRST) ? 2 : (a.acc_types.empty() ? 1 : (int)a.acc_types.size());
+    }
+    // value types for MIN/MAX/FIRST: child type in partial mode, the trailing acc column type in merge modes
+    int acc_pos = (int)in.fields.size() - input_acc_cols;
+    AURON_CHECK(acc_pos >= 0, "aggregate input has fewer columns than accumulator arrays");
+    for (auto& a : aggs) {
+        bool value_typed = a.fn == AGG_MIN || a.fn == AGG_MAX || a.fn == AGG_FIRST || a.fn == AGG_FIRST_IGNORES_NULL;
+        if (value_typed) {
+            if (a.mode == MODE_PARTIAL) a.value_type = infer_type(*a.children[0], in);
+            else a.value_type = in.fields[acc_pos].type;
+            a.acc_types = {a.value_type};
+            if (a.fn == AGG_FIRST) a.acc_types.push_back(DType(T_BOOL));
+        }
+        if (a.mode != MODE_PARTIAL) acc_pos += (int)a.acc_types.size();
+    }
+    // lowered input expressions: group keys, then the args of every partial-mode aggregate
+    for (auto& g : group_exprs) lowered.push_back(g);
+    for (auto& a : aggs) {
+        if (a.mode != MODE_PARTIAL) continue;
+        for (size_t k = 0; k < a.children.size(); k++) {
+            ExprPtr e = a.children[k];
+            if (k == 0 && (a.fn == AGG_SUM || a.fn == AGG_AVG)) {   // agg.rs:191-198 TryCast(child, return_type)
+                DType ct = infer_type(*e, in);
+                if (!load_compatible(ct, a.return_type)) {
+                    auto c = std::make_shared<Expr>();
+                    c->kind = E_TRY_CAST;
+                    c->type = a.return_type;
+                    c->children.push_back(e);
+                    e = c;
+                }
+            }
+            lowered.push_back(e);
+        }
+    }
+    for (auto& e : lowered) {
+        int idx = -1;
+        if (is_plain_column(*e, in, &idx)) lowered_plain.push_back(idx);
+        else {
+            lowered_plain.push_back(-1);
+            all_plain = false;
+        }
+    }
+    if (!all_plain) lowered_prog = compile_projection(lowered, in);
+    // output schema (agg_ctx.rs:127-150)
+    for (size_t i = 0; i < group_exprs.size(); i++) {
+        Field f;
+        f.name = i < group_names.size() ? group_names[i] : "";
+        f.type = infer_type(*group_exprs[i], in);
+        out_schema.fields.push_back(f);
+    }
+    for (auto& a : aggs) {
+        if (is_final) {
+            Field f;
+            f.name = a.name;
+            f.type = (a.fn == AGG_COUNT) ? DType(T_INT64) : (a.fn == AGG_SUM || a.fn == AGG_AVG) ? a.return_type : a.value_type;
+            out_schema.fields.push_back(f);
+        } else {
+            for (auto& at : a.acc_types) {
+                Field f;
+                f.name = "";
+                f.type = at;
+                out_schema.fields.push_back(f);
+            }
+        }
+    }
+    n_acc_cols = 0;
+    for (auto& a : aggs) n_acc_cols += (int)a.acc_types.size();
+    children.push_back(std::move(input));
+}
+
+static AccKind sum_kind(const DType& acc) {
+    if (acc.id == T_DECIMAL128) return ACC_SUM_DEC;
+    if (acc.id == T_FLOAT64 || acc.id == T_FLOAT32) return ACC_SUM_F64;
+    return ACC_SUM_I64;
+}
+
+// build accumulator specs.  `merge_cols` != nullptr: every aggregate merges from these acc columns.
+static std::vector<AccSpec> build_specs(const std::vector<AggExprSpec>& aggs, const std::vector<ColumnPtr>& partial_args,
+                                        const std::vector<ColumnPtr>* merge_cols, bool force_merge) {
+    std::vector<AccSpec> specs;
+    size_t pa = 0, mc = 0;
+    for (auto& a : aggs) {
+        bool merge = force_merge || a.mode != MODE_PARTIAL;
+        if (!merge) {
+            size_t nargs = a.children.size();
+            std::vector<ColumnPtr> args(partial_args.begin() + pa, partial_args.begin() + pa + nargs);
+            pa += nargs;
+            switch (a.fn) {
+                case AGG_SUM: specs.push_back({sum_kind(a.acc_types[0]), args[0], {}, a.acc_types[0], nullptr}); break;
+                case AGG_COUNT: {
+                    AccSpec s{ACC_COUNT, args.empty() ? nullptr : args[0], {}, DType(T_INT64), nullptr};
+                    for (size_t k = 1; k < args.size(); k++) s.extra.push_back(args[k]);
+                    specs.push_back(s);
+                    break;
+                }
+                case AGG_AVG:
+                    specs.push_back({sum_kind(a.acc_types[0]), args[0], {}, a.acc_types[0], nullptr});
+                    specs.push_back({ACC_COUNT, args[0], {}, DType(T_INT64), nullptr});
+                    break;
+                case AGG_MIN: specs.push_back({ACC_MIN, args[0], {}, a.value_type, nullptr}); break;
+                case AGG_MAX: specs.push_back({ACC_MAX, args[0], {}, a.value_type, nullptr}); break;
+                case AGG_FIRST: specs.push_back({ACC_FIRST, args[0], {}, a.value_type, nullptr}); break;
+                case AGG_FIRST_IGNORES_NULL: specs.push_back({ACC_FIRST_IGNORES_NULL, args[0], {}, a.value_type, nullptr}); break;
+            }
+        } else {
+            const std::vector<ColumnPtr>& m = *merge_cols;
+            switch (a.fn) {
+                case AGG_SUM: specs.push_back({sum_kind(a.acc_types[0]), m[mc], {}, a.acc_types[0], nullptr}); mc += 1; break;
+                case AGG_COUNT: specs.push_back({ACC_ADD_I64, m[mc], {}, DType(T_INT64), nullptr}); mc += 1; break;
+                case AGG_AVG:
+                    specs.push_back({sum_kind(a.acc_types[0]), m[mc], {}, a.acc_types[0], nullptr});
+                    specs.push_back({ACC_ADD_I64, m[mc + 1], {}, DType(T_INT64), nullptr});
+                    mc += 2;
+                    break;
+                case AGG_MIN: specs.push_back({ACC_MIN, m[mc], {}, a.value_type, nullptr}); mc += 1; break;
+                case AGG_MAX: specs.push_back({ACC_MAX, m[mc], {}, a.value_type, nullptr}); mc += 1; break;
+                case AGG_FIRST: specs.push_back({ACC_FIRST, m[mc], {m[mc + 1]}, a.value_type, nullptr}); mc += 2; break;
+                case AGG_FIRST_IGNORES_NULL: specs.push_back({ACC_FIRST_IGNORES_NULL, m[mc], {}, a.value_type, nullptr}); mc += 1; break;
+            }
+        }
+    }
+    return specs;
+}
+
+static BatchPtr run_agg(Task& t, const std::vector<ColumnPtr>& keys, const std::vector<AccSpec>& specs, const int32_t* sel, int64_t n) {
+    auto out = std::make_shared<Batch>();
+    if (keys.empty()) {
+        auto accs = global_aggregate(t.ctx, specs, sel, n);
+        out->num_rows = 1;
+        out->cols = accs;
+    } else {
+        GroupedResult r = hash_aggregate(t.ctx, keys, specs, sel, n);
+        out->num_rows = r.num_groups;
+        out->cols = r.keys->cols;
+        for (auto& c : r.accs) out->cols.push_back(c);
+    }
+    return out;
+}
+
+BatchPtr AggExec::aggregate_chunk(Task& t, const SelBatch& s) {
+    const Batch& in = *s.batch;
+    const int32_t* sel = P<int32_t>(s.sel);
+    int64_t n = s.n;
+    std::vector<ColumnPtr> lowered_cols;
+    bool any_merge = false;
+    for (auto& a : aggs) any_merge |= a.mode != MODE_PARTIAL;
+    BatchPtr dense_holder;
+    const Batch* src = &in;
+    if (all_plain) {
+        for (int idx : lowered_plain) lowered_cols.push_back(in.cols[idx]);
+    } else {
+        lowered_cols = eval_projection(t.ctx, lowered_prog, in, sel, n);
+        if (sel && any_merge) {   // merge inputs must line up with the dense lowered columns
+            dense_holder = take_batch(t.ctx, in, sel, n, false);
+            src = dense_holder.get();
+        }
+        sel = nullptr;
+    }
+    std::vector<ColumnPtr> keys(lowered_cols.begin(), lowered_cols.begin() + group_exprs.size());
+    std::vector<ColumnPtr> pargs(lowered_cols.begin() + group_exprs.size(), lowered_cols.end());
+    std::vector<ColumnPtr> merge_cols;
+    if (any_merge) {
+        int start = (int)src->cols.size() - input_acc_cols;
+        for (int i = start; i < (int)src->cols.size(); i++) merge_cols.push_back(src->cols[i]);
+    }
+    auto specs = build_specs(aggs, pargs, &merge_cols, false);
+    return run_agg(t, keys, specs, sel, n);
+}
+
+BatchPtr AggExec::merge_partials(Task& t, const BatchPtr& all) {
+    size_t g = group_exprs.size();
+    std::vector<ColumnPtr> keys(all->cols.begin(), all->cols.begin() + g);
+    std::vector<ColumnPtr> merge_cols(all->cols.begin() + g, all->cols.end());
+    auto specs = build_specs(aggs, {}, &merge_cols, true);
+    return run_agg(t, keys, specs, nullptr, all->num_rows);
+}
+
+BatchPtr AggExec::finalize(Task& t, const BatchPtr& merged) {
+    if (!is_final) return merged;
+    auto out = std::make_shared<Batch>();
+    out->num_rows = merged->num_rows;
+    size_t g = group_exprs.size(), pos = g;
+    for (size_t i = 0; i < g; i++) out->cols.push_back(merged->cols[i]);
+    for (auto& a : aggs) {
+        switch (a.fn) {
+            case AGG_AVG:
+                out->cols.push_back(avg_finalize(t.ctx, *merged->cols[pos], *merged->cols[pos + 1], a.return_type));
+                pos += 2;
+                break;
+            case AGG_FIRST:
+                out->cols.push_back(merged->cols[pos]);
+                pos += 2;
+                break;
+            default:
+                out->cols.push_back(merged->cols[pos]);
+                pos += 1;
+        }
+    }
+    return out;
+}
+
+BatchPtr AggExec::next(Task& t) {
+    if (output_done) return nullptr;
+    bool saw_input = false;
+    while (!input_done) {
+        AURON_CHECK(t.is_running(), "task killed");
+        SelBatch s = children[0]->next_sel(t);
+        if (!s.batch) {
+            input_done = true;
+            break;
+        }
+        saw_input = true;
+        if (s.n == 0 && !group_exprs.empty()) continue;
+        BatchPtr p = aggregate_chunk(t, s);
+        partials.push_back(p);
+        partial_rows += p->num_rows;
+        // keep the partial list bounded: re-merge when it outgrows one chunk
+        if (partials.size() > 1 && partial_rows > t.ctx.gpu_chunk_rows) {
+            BatchPtr m = merge_partials(t, concat_batches(t.ctx, partials));
+            partials.clear();
+            partials.push_back(m);
+            partial_rows = m->num_rows;
+        }
+    }
+    (void)saw_input;
+    output_done = true;
+    if (partials.empty()) {
+        if (!group_exprs.empty()) return nullptr;
+        // no grouping, no input: one row of empty accumulators (agg_exec.rs:280-323)
+        SelBatch empty;
+        auto eb = std::make_shared<Batch>();
+        const Schema& in = children[0]->out_schema;
+        for (auto& f : in.fields) eb->cols.push_back(f.type.is_varlen() ? make_column(t.ctx, f.type, 0, false) : make_column(t.ctx, f.type, 0, false));
+        empty.batch = eb;
+        empty.n = 0;
+        partials.push_back(aggregate_chunk(t, empty));
+    }
+    BatchPtr merged = partials.size() == 1 ? partials[0] : merge_partials(t, concat_batches(t.ctx, partials));
+    partials.clear();
+    BatchPtr out = finalize(t, merged);
+    metrics.add("output_rows", out->num_rows);
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------ HashJoinExec
+HashJoinExec::HashJoinExec(OperatorPtr left, OperatorPtr right, std::vector<ExprPtr> lk, std::vector<ExprPtr> rk, int jt, int bs, const Schema& schema)
+    : left_keys(std::move(lk)), right_keys(std::move(rk)), join_type(jt), build_side(bs) {
+    name = "HashJoinExec";
+    out_schema = schema;
+    if (out_schema.fields.empty()) {   // derive: [left cols..., right cols...] (full_join.rs:137-140)
+        for (auto& f : left->out_schema.fields) out_schema.fields.push_back(f);
+        if (jt == JOIN_EXISTENCE) {
+            Field f;
+            f.name = "exists";
+            f.type = DType(T_BOOL);
+            out_schema.fields.push_back(f);
+        } else if (jt != JOIN_SEMI && jt != JOIN_ANTI) {
+            for (auto& f : right->out_schema.fields) out_schema.fields.push_back(f);
+        }
+    }
+    children.push_back(std::move(left));
+    children.push_back(std::move(right));
+}
+
+static std::vector<ColumnPtr> eval_keys(Task& t, const std::vector<ExprPtr>& keys, const Schema& schema, const Batch& b) {
+    std::vector<ColumnPtr> out;
+    for (auto& k : keys) out.push_back(eval_to_column(t, k, schema, b));
+    return out;
+}
+
+void HashJoinExec::build(Task& t) {
+    std::vector<BatchPtr> bs;
+    Operator& bc = build_child();
+    while (BatchPtr b = bc.next(t)) {
+        AURON_CHECK(t.is_running(), "task killed");
+        if (b->num_rows) bs.push_back(b);
+    }
+    if (bs.empty()) {
+        build_batch = std::make_shared<Batch>();
+        for (auto& f : bc.out_schema.fields) build_batch->cols.push_back(make_column(t.ctx, f.type, 0, false));
+    } else build_batch = concat_batches(t.ctx, bs);
+    const auto& keys = build_side == SIDE_LEFT ? left_keys : right_keys;
+    build_key_cols = eval_keys(t, keys, bc.out_schema, *build_batch);
+    table = join_build(t.ctx, build_key_cols, build_batch->num_rows);
+    matched_build = dalloc_zero(t.ctx, bitmap_alloc_bytes(build_batch->num_rows) + 4);
+    built = true;
+    metrics.add("build_rows", build_batch->num_rows);
+}
+
+static BatchPtr null_batch(Task& t, const Schema& s, int64_t n) {
+    auto b = std::make_shared<Batch>();
+    b->num_rows = n;
+    for (auto& f : s.fields) {
+        if (f.type.is_varlen()) {
+            auto c = make_column(t.ctx, f.type, n, true);
+            c->null_count = n;
+            CUDA_OK(cudaMemsetAsync(c->offsets->ptr, 0, (size_t)(n + 1) * 4, t.ctx.stream));
+            b->cols.push_back(c);
+        } else b->cols.push_back(make_null_column(t.ctx, f.type, n));
+    }
+    return b;
+}
+static ColumnPtr bool_column_from_bits(Buf bits, int64_t n) {
+    auto c = std::make_shared<Column>();
+    c->type = DType(T_BOOL);
+    c->len = n;
+    c->data = bits;
+    return c;
+}
+
+BatchPtr HashJoinExec::probe_chunk(Task& t, const BatchPtr& probe) {
+    bool probe_is_left = build_side == SIDE_RIGHT;
+    Operator& pc = probe_child();
+    const auto& keys = probe_is_left ? left_keys : right_keys;
+    auto pkeys = eval_keys(t, keys, pc.out_schema, *probe);
+    int64_t n = probe->num_rows;
+    bool probe_outer = (join_type == JOIN_FULL) || (join_type == JOIN_LEFT && probe_is_left) || (join_type == JOIN_RIGHT && !probe_is_left);
+    bool semi_like = join_type == JOIN_SEMI || join_type == JOIN_ANTI || join_type == JOIN_EXISTENCE;
+    if (semi_like) {
+        Buf pm;
+        join_probe(t.ctx, *table, pkeys, n, false, P<uint32_t>(matched_build), &pm);
+        if (!probe_is_left) return nullptr;   // the build (left) side is emitted in finish()
+        if (join_type == JOIN_EXISTENCE) {    // semi_join.rs:251-287: all probe rows + exists column
+            auto out = std::make_shared<Batch>(*probe);
+            out->cols.push_back(bool_column_from_bits(pm, n));
+            return out;
+        }
+        Buf mask = pm;
+        if (join_type == JOIN_ANTI) {
+            if (null_aware_anti) {   // semi_join.rs:191-210: NOT IN drops everything when the build side has a NULL key
+                if (join_table_has_null_key(*table)) return nullptr;
+                Buf nn = not_bitmap(t.ctx, P<uint8_t>(pm), n);
+                const uint8_t* kv = pkeys[0]->vbits();
+                mask = kv ? and_bitmaps(t.ctx, P<uint8_t>(nn), kv, n) : nn;
+            } else mask = not_bitmap(t.ctx, P<uint8_t>(pm), n);
+        }
+        int64_t cnt = 0;
+        Buf idx = mask_to_indices(t.ctx, P<uint32_t>(mask), n, &cnt);
+        if (cnt == 0) return nullptr;
+        return take_batch(t.ctx, *probe, P<int32_t>(idx), cnt, false);
+    }
+    bool need_matched = (join_type == JOIN_FULL) || (join_type == JOIN_LEFT && !probe_is_left) || (join_type == JOIN_RIGHT && probe_is_left);
+    JoinPairs pairs = join_probe(t.ctx, *table, pkeys, n, probe_outer, need_matched ? P<uint32_t>(matched_build) : nullptr, nullptr);
+    if (pairs.count == 0) return nullptr;
+    BatchPtr pcols = take_batch(t.ctx, *probe, P<int32_t>(pairs.probe_idx), pairs.count, false);
+    BatchPtr bcols = take_batch(t.ctx, *build_batch, P<int32_t>(pairs.build_idx), pairs.count, probe_outer);
+    auto out = std::make_shared<Batch>();
+    out->num_rows = pairs.count;
+    const BatchPtr& l = probe_is_left ? pcols : bcols;
+    const BatchPtr& r = probe_is_left ? bcols : pcols;
+    for (auto& c : l->cols) out->cols.push_back(c);
+    for (auto& c : r->cols) out->cols.push_back(c);
+    return out;
+}
+
+BatchPtr HashJoinExec::finish(Task& t) {
+    bool probe_is_left = build_side == SIDE_RIGHT;
+    int64_t nb = build_batch->num_rows;
+    bool build_outer = (join_type == JOIN_FULL) || (join_type == JOIN_LEFT && !probe_is_left) || (join_type == JOIN_RIGHT && probe_is_left);
+    bool semi_like = join_type == JOIN_SEMI || join_type == JOIN_ANTI || join_type == JOIN_EXISTENCE;
+    if (semi_like) {
+        if (probe_is_left || nb == 0) return nullptr;
+        if (join_type == JOIN_EXISTENCE) {
+            auto out = std::make_shared<Batch>(*build_batch);
+            out->cols.push_back(bool_column_from_bits(matched_build, nb));
+            return out;
+        }
+        Buf mask = join_type == JOIN_SEMI ? matched_build : not_bitmap(t.ctx, P<uint8_t>(matched_build), nb);
+        int64_t cnt = 0;
+        Buf idx = mask_to_indices(t.ctx, P<uint32_t>(mask), nb, &cnt);
+        if (cnt == 0) return nullptr;
+        return take_batch(t.ctx, *build_batch, P<int32_t>(idx), cnt, false);
+    }
+    if (!build_outer || nb == 0) return nullptr;
+    // unmatched build rows (incl. NULL-key rows, join_hash_map.rs:103,331-338) with NULLs on the probe side
+    Buf mask = not_bitmap(t.ctx, P<uint8_t>(matched_build), nb);
+    int64_t cnt = 0;
+    Buf idx = mask_to_indices(t.ctx, P<uint32_t>(mask), nb, &cnt);
+    if (cnt == 0) return nullptr;
+    BatchPtr bcols = take_batch(t.ctx, *build_batch, P<int32_t>(idx), cnt, false);
+    BatchPtr pnull = null_batch(t, probe_child().out_schema, cnt);
+    auto out = std::make_shared<Batch>();
+    out->num_rows = cnt;
+    const BatchPtr& l = probe_is_left ? pnull : bcols;
+    const BatchPtr& r = probe_is_left ? bcols : pnull;
+    for (auto& c : l->cols) out->cols.push_back(c);
+    for (auto& c : r->cols) out->cols.push_back(c);
+    return out;
+}
+
+BatchPtr HashJoinExec::next(Task& t) {
+    if (finished) return nullptr;
+    if (!built) build(t);
+    while (!probe_done) {
+        AURON_CHECK(t.is_running(), "task killed");
+        BatchPtr p = probe_child().next(t);
+        if (!p) {
+            probe_done = true;
+            break;
+        }
+        if (p->num_rows == 0) continue;
+        BatchPtr out = probe_chunk(t, p);
+        if (out && out->num_rows) {
+            metrics.add("output_rows", out->num_rows);
+            return out;
+        }
+    }
+    finished = true;
+    BatchPtr out = finish(t);
+    if (out) metrics.add("output_rows", out->num_rows);
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------ SortExec
+SortExec::SortExec(OperatorPtr input, std::vector<SortExprSpec> k, int64_t lim, int64_t off) : keys(std::move(k)), limit(lim), offset(off) {
+    name = "SortExec";
+    out_schema = input->out_schema;
+    children.push_back(std::move(input));
+}
+BatchPtr SortExec::next(Task& t) {
+    if (done) return nullptr;
+    done = true;
+    std::vector<BatchPtr> all;
+    while (BatchPtr b = children[0]->next(t)) {
+        AURON_CHECK(t.is_running(), "task killed");
+        if (b->num_rows) all.push_back(b);
+    }
+    if (all.empty()) return nullptr;
+    BatchPtr in = concat_batches(t.ctx, all);
+    all.clear();
+    std::vector<SortKeySpec> specs;
+    for (auto& k : keys) specs.push_back({eval_to_column(t, k.expr, out_schema, *in), k.asc, k.nulls_first});
+    Buf perm = sort_indices(t.ctx, specs, in->num_rows);
+    // fetch limit: keep sorted rows [offset, limit)  (sort_exec.rs:663,720-722,964)
+    int64_t n = in->num_rows, begin = std::min<int64_t>(offset, n), end = limit >= 0 ? std::min<int64_t>(limit, n) : n;
+    if (end <= begin) return nullptr;
+    BatchPtr out = take_batch(t.ctx, *in, P<int32_t>(perm) + begin, end - begin, false);
+    metrics.add("output_rows", out->num_rows);
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------ misc
+LimitExec::LimitExec(OperatorPtr input, int64_t lim, int64_t off) : limit(lim), offset(off) {
+    name = "LimitExec";
+    out_schema = input->out_schema;
+    children.push_back(std::move(input));
+}
+BatchPtr LimitExec::next(Task& t) {
+    // rows [offset, limit) of the stream; stop pulling once satisfied (limit_exec.rs:132-180)
+    while (seen < limit) {
+        BatchPtr b = children[0]->next(t);
+        if (!b) return nullptr;
+        int64_t lo = std::max<int64_t>(offset - seen, 0), hi = std::min<int64_t>(b->num_rows, limit - seen);
+        seen += b->num_rows;
+        if (hi <= lo) continue;
+        if (lo == 0 && hi == b->num_rows) return b;
+        return slice_batch(t.ctx, *b, lo, hi - lo);
+    }
+    return nullptr;
+}
+RenameColumnsExec::RenameColumnsExec(OperatorPtr input, const std::vector<std::string>& names) {
+    name = "RenameColumnsExec";
+    out_schema = input->out_schema;
+    for (size_t i = 0; i < names.size() && i < out_schema.fields.size(); i++) out_schema.fields[i].name = names[i];
+    children.push_back(std::move(input));
+}
+PassThroughExec::PassThroughExec(OperatorPtr input, const std::string& nm) {
+    name = nm;
+    out_schema = input->out_schema;
+    children.push_back(std::move(input));
+}
+UnionExec::UnionExec(std::vector<OperatorPtr> inputs, const Schema& schema) {
+    name = "UnionExec";
+    out_schema = schema;
+    for (auto& i : inputs) children.push_back(std::move(i));
+}
+BatchPtr UnionExec::next(Task& t) {
+    while (cur < children.size()) {
+        BatchPtr b = children[cur]->next(t);
+        if (b) return b;
+        cur++;
+    }
+    return nullptr;
+}
+
+}  // namespace auron

@@ -1,0 +1,145 @@
+// operators.h -- operator classes (mirror of datafusion-ext-plans/src/*_exec.rs)
+#pragma once
+#include "engine.h"
+
+namespace auron {
+
+// proto enums (auron.proto)
+enum AggFn { AGG_MIN = 0, AGG_MAX = 1, AGG_SUM = 2, AGG_AVG = 3, AGG_COUNT = 4, AGG_FIRST = 7, AGG_FIRST_IGNORES_NULL = 8 };
+enum AggModeE { MODE_PARTIAL = 0, MODE_PARTIAL_MERGE = 1, MODE_FINAL = 2 };
+enum JoinTypeE { JOIN_INNER = 0, JOIN_LEFT = 1, JOIN_RIGHT = 2, JOIN_FULL = 3, JOIN_SEMI = 4, JOIN_ANTI = 5, JOIN_EXISTENCE = 6 };
+enum JoinSideE { SIDE_LEFT = 0, SIDE_RIGHT = 1 };
+
+// ffi_reader_exec.rs: batches exported by the JVM (or HBM-resident batches registered under the id)
+struct FFIReaderExec : Operator {
+    std::string resource_id;
+    bool is_device = false, done = false;
+    std::vector<BatchPtr> dev_batches;
+    size_t dev_pos = 0;
+    FFIReaderExec(const Schema& schema, const std::string& id);
+    BatchPtr next(Task& t) override;
+};
+
+// filter_exec.rs:128-224
+struct FilterExec : Operator {
+    std::vector<ExprPtr> predicates;
+    VmProgram prog;
+    FilterExec(OperatorPtr input, std::vector<ExprPtr> preds);
+    BatchPtr next(Task& t) override;
+    SelBatch next_sel(Task& t) override;
+};
+
+// project_exec.rs:135-232 (fuses with a FilterExec child through next_sel)
+struct ProjectExec : Operator {
+    std::vector<ExprPtr> exprs;
+    std::vector<int> plain_col;       // >= 0: bare column index, -1: computed
+    std::vector<int> prog_slot;       // index into the VM program outputs for computed exprs
+    VmProgram prog;
+    bool has_prog = false;
+    ProjectExec(OperatorPtr input, std::vector<ExprPtr> exprs, std::vector<std::string> names, std::vector<DType> types);
+    BatchPtr next(Task& t) override;
+};
+
+struct AggExprSpec {
+    int fn = AGG_SUM;
+    int mode = MODE_PARTIAL;
+    std::vector<ExprPtr> children;
+    DType return_type;
+    std::string name;
+    // derived
+    std::vector<DType> acc_types;
+    DType value_type;   // type of the aggregated values (MIN/MAX/FIRST)
+};
+
+// agg_exec.rs:141-323 + agg/*.rs
+struct AggExec : Operator {
+    std::vector<ExprPtr> group_exprs;
+    std::vector<std::string> group_names;
+    std::vector<AggExprSpec> aggs;
+    bool is_final = false;
+    bool input_done = false, output_done = false;
+    std::vector<BatchPtr> partials;   // [group cols..., acc cols...]
+    int64_t partial_rows = 0;
+    // lowered input expressions (group keys + partial-mode agg args), evaluated through the VM when not plain
+    std::vector<ExprPtr> lowered;
+    std::vector<int> lowered_plain;
+    bool all_plain = true;
+    VmProgram lowered_prog;
+    int n_acc_cols = 0, input_acc_cols = 0;
+    AggExec(OperatorPtr input, std::vector<ExprPtr> group_exprs, std::vector<std::string> group_names, std::vector<AggExprSpec> aggs);
+    BatchPtr next(Task& t) override;
+
+   private:
+    BatchPtr aggregate_chunk(Task& t, const SelBatch& s);
+    BatchPtr merge_partials(Task& t, const BatchPtr& all);
+    BatchPtr finalize(Task& t, const BatchPtr& merged);
+};
+
+// broadcast_join_exec.rs / sort_merge_join_exec.rs (hash build + probe for every join flavour)
+struct HashJoinExec : Operator {
+    std::vector<ExprPtr> left_keys, right_keys;
+    int join_type = JOIN_INNER;
+    int build_side = SIDE_RIGHT;
+    bool null_aware_anti = false;
+    std::string cache_id;
+    // state
+    bool built = false, probe_done = false, finished = false;
+    BatchPtr build_batch;
+    std::vector<ColumnPtr> build_key_cols;
+    std::shared_ptr<JoinTable> table;
+    Buf matched_build;
+    HashJoinExec(OperatorPtr left, OperatorPtr right, std::vector<ExprPtr> lk, std::vector<ExprPtr> rk, int join_type, int build_side, const Schema& schema);
+    BatchPtr next(Task& t) override;
+
+   private:
+    void build(Task& t);
+    BatchPtr probe_chunk(Task& t, const BatchPtr& probe);
+    BatchPtr finish(Task& t);
+    Operator& build_child() { return *children[build_side == SIDE_LEFT ? 0 : 1]; }
+    Operator& probe_child() { return *children[build_side == SIDE_LEFT ? 1 : 0]; }
+};
+
+struct SortExprSpec {
+    ExprPtr expr;
+    bool asc = true, nulls_first = true;
+};
+// sort_exec.rs:197-290,637-768
+struct SortExec : Operator {
+    std::vector<SortExprSpec> keys;
+    int64_t limit = -1, offset = 0;
+    bool done = false;
+    SortExec(OperatorPtr input, std::vector<SortExprSpec> keys, int64_t limit, int64_t offset);
+    BatchPtr next(Task& t) override;
+};
+
+// limit_exec.rs:132-180
+struct LimitExec : Operator {
+    int64_t limit, offset, seen = 0, emitted = 0;
+    LimitExec(OperatorPtr input, int64_t limit, int64_t offset);
+    BatchPtr next(Task& t) override;
+};
+
+struct RenameColumnsExec : Operator {
+    RenameColumnsExec(OperatorPtr input, const std::vector<std::string>& names);
+    BatchPtr next(Task& t) override { return children[0]->next(t); }
+};
+struct EmptyPartitionsExec : Operator {
+    explicit EmptyPartitionsExec(const Schema& s) { name = "EmptyPartitionsExec"; out_schema = s; }
+    BatchPtr next(Task&) override { return nullptr; }
+};
+struct PassThroughExec : Operator {   // CoalesceBatches / BroadcastJoinBuildHashMap / Debug: batch shape is not part of the contract
+    PassThroughExec(OperatorPtr input, const std::string& nm);
+    BatchPtr next(Task& t) override { return children[0]->next(t); }
+};
+// union_exec.rs:118-160
+struct UnionExec : Operator {
+    size_t cur = 0;
+    UnionExec(std::vector<OperatorPtr> inputs, const Schema& schema);
+    BatchPtr next(Task& t) override;
+};
+
+// helpers shared with scan / shuffle
+ColumnPtr eval_to_column(Task& t, const ExprPtr& e, const Schema& schema, const Batch& b);
+BatchPtr materialize(Task& t, const SelBatch& s);
+
+}  // namespace auron

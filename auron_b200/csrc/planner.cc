@@ -1,0 +1,804 @@
+// planner.cc -- protobuf TaskDefinition -> operator tree.  Mirror of PhysicalPlanner::create_plan
+// (auron-planner/src/planner.rs:120-842), try_parse_physical_expr (:844-1053) and the ArrowType / Schema /
+// ScalarValue conversions (auron-planner/src/lib.rs).  Field numbers are those of
+// auron-planner/proto/auron.proto; the wire format is decoded by hand (pb.h).
+#include "operators.h"
+#include "pb.h"
+
+namespace auron {
+
+// ------------------------------------------------------------------------------------------ types
+DType decode_arrow_type(const uint8_t* b, size_t n) {
+    PbReader r(b, n);
+    uint32_t f, w;
+    DType t(T_NULL);
+    while (r.next(&f, &w)) {
+        const uint8_t* sb = nullptr;
+        size_t sn = 0;
+        uint64_t v = 0;
+        if (w == 2) r.bytes_view(&sb, &sn);
+        else if (w == 0) v = r.varint();
+        else r.skip(w);
+        switch (f) {   // auron.proto:915-951
+            case 1: t = DType(T_NULL); break;
+            case 2: t = DType(T_BOOL); break;
+            case 4: t = DType(T_INT8); break;
+            case 6: t = DType(T_INT16); break;
+            case 8: t = DType(T_INT32); break;
+            case 10: t = DType(T_INT64); break;
+            case 12: t = DType(T_FLOAT32); break;
+            case 13: t = DType(T_FLOAT64); break;
+            case 14: case 32: t = DType(T_UTF8); break;
+            case 15: case 31: t = DType(T_BINARY); break;
+            case 17: t = DType(T_DATE32); break;
+            case 18: t = DType(T_DATE64); break;
+            case 20: {   // Timestamp{time_unit=1, timezone=2}
+                t = DType(T_TIMESTAMP);
+                t.unit = 0;
+                PbReader tr(sb, sn);
+                uint32_t tf, tw;
+                while (tr.next(&tf, &tw)) {
+                    if (tf == 1 && tw == 0) t.unit = (int)tr.varint();
+                    else if (tf == 2 && tw == 2) t.tz = tr.bytes();
+                    else tr.skip(tw);
+                }
+                break;
+            }
+            case 24: {   // Decimal{whole=1 (precision), fractional=2 (scale)}
+                int p = 0, s = 0;
+                PbReader dr(sb, sn);
+                uint32_t df, dw;
+                while (dr.next(&df, &dw)) {
+                    if (df == 1 && dw == 0) p = (int)dr.varint();
+                    else if (df == 2 && dw == 0) s = (int)(int64_t)dr.varint();
+                    else dr.skip(dw);
+                }
+                t = DType::decimal(p, s);
+                break;
+            }
+            case 3: case 5: case 7: case 9: fail("unsigned integer columns are not supported on device");
+            default: fail("unsupported ArrowType tag " + std::to_string(f) + " (nested / interval types are out of scope)");
+        }
+        (void)v;
+    }
+    return t;
+}
+
+static Field decode_field(const uint8_t* b, size_t n) {
+    PbReader r(b, n);
+    uint32_t f, w;
+    Field out;
+    out.nullable = false;
+    while (r.next(&f, &w)) {
+        if (f == 1 && w == 2) out.name = r.bytes();
+        else if (f == 2 && w == 2) {
+            const uint8_t* sb;
+            size_t sn;
+            r.bytes_view(&sb, &sn);
+            out.type = decode_arrow_type(sb, sn);
+        } else if (f == 3 && w == 0) out.nullable = r.varint() != 0;
+        else r.skip(w);
+    }
+    return out;
+}
+Schema decode_schema(const uint8_t* b, size_t n) {
+    PbReader r(b, n);
+    uint32_t f, w;
+    Schema s;
+    while (r.next(&f, &w)) {
+        if (f == 1 && w == 2) {
+            const uint8_t* sb;
+            size_t sn;
+            r.bytes_view(&sb, &sn);
+            s.fields.push_back(decode_field(sb, sn));
+        } else r.skip(w);
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------ literals
+// Arrow IPC stream: schema message + one record batch with one row / one column (NativeConverters.scala:413-428)
+static bool next_ipc_message(const uint8_t*& p, const uint8_t* end, const uint8_t** meta, uint32_t* meta_len, const uint8_t** body, int64_t* body_len) {
+    if (end - p < 4) return false;
+    uint32_t first;
+    memcpy(&first, p, 4);
+    if (first == 0xFFFFFFFFu) {
+        p += 4;
+        if (end - p < 4) return false;
+        memcpy(&first, p, 4);
+    }
+    p += 4;
+    if (first == 0) return false;   // end-of-stream marker
+    AURON_CHECK((size_t)(end - p) >= first, "Arrow IPC: truncated message");
+    *meta = p;
+    *meta_len = first;
+    p += first;
+    FbTable msg;
+    msg.base = *meta;
+    msg.size = first;
+    msg.tbl = *meta + FbTable::rd<uint32_t>(*meta);
+    *body_len = msg.scalar<int64_t>(3, 0);
+    *body = p;
+    AURON_CHECK(end - p >= *body_len, "Arrow IPC: truncated body");
+    p += *body_len;
+    return true;
+}
+
+Literal decode_scalar_ipc(const uint8_t* bytes, size_t n) {
+    const uint8_t* p = bytes;
+    const uint8_t* end = bytes + n;
+    const uint8_t *meta, *body;
+    uint32_t meta_len;
+    int64_t body_len;
+    Literal lit;
+    AURON_CHECK(next_ipc_message(p, end, &meta, &meta_len, &body, &body_len), "ScalarValue: missing schema message");
+    FbTable msg;
+    msg.base = meta;
+    msg.size = meta_len;
+    msg.tbl = meta + FbTable::rd<uint32_t>(meta);
+    AURON_CHECK(msg.scalar<uint8_t>(1, 0) == 1, "ScalarValue: first IPC message is not a Schema");
+    FbTable schema = msg.table(2);
+    uint32_t nfields;
+    const uint8_t* fields = schema.vec(1, &nfields);
+    AURON_CHECK(nfields == 1, "ScalarValue: expected exactly one field");
+    FbTable field = schema.vec_table(fields, 0);
+    uint8_t tt = field.scalar<uint8_t>(2, 0);
+    FbTable ty = field.table(3);
+    switch (tt) {   // org.apache.arrow.flatbuf.Type
+        case 1: lit.type = DType(T_NULL); break;
+        case 2: {
+            int bw = ty.ok() ? ty.scalar<int32_t>(0, 0) : 0;
+            bool sg = ty.ok() ? ty.scalar<uint8_t>(1, 0) != 0 : true;
+            AURON_CHECK(sg, "unsigned literal");
+            lit.type = DType(bw == 8 ? T_INT8 : bw == 16 ? T_INT16 : bw == 32 ? T_INT32 : T_INT64);
+            break;
+        }
+        case 3: {
+            int prec = ty.ok() ? ty.scalar<int16_t>(0, 0) : 0;
+            AURON_CHECK(prec == 1 || prec == 2, "half-float literal");
+            lit.type = DType(prec == 1 ? T_FLOAT32 : T_FLOAT64);
+            break;
+        }
+        case 4: lit.type = DType(T_BINARY); break;
+        case 5: lit.type = DType(T_UTF8); break;
+        case 6: lit.type = DType(T_BOOL); break;
+        case 7: lit.type = DType::decimal(ty.ok() ? ty.scalar<int32_t>(0, 0) : 0, ty.ok() ? ty.scalar<int32_t>(1, 0) : 0); break;
+        case 8: lit.type = DType((ty.ok() ? ty.scalar<int16_t>(0, 1) : 1) == 0 ? T_DATE32 : T_DATE64); break;
+        case 10: {
+            lit.type = DType(T_TIMESTAMP);
+            lit.type.unit = ty.ok() ? ty.scalar<int16_t>(0, 0) : 0;
+            if (ty.ok()) lit.type.tz = ty.str(1);
+            break;
+        }
+        default: fail("ScalarValue: unsupported literal type tag " + std::to_string(tt));
+    }
+    if (!next_ipc_message(p, end, &meta, &meta_len, &body, &body_len)) {
+        lit.is_null = true;
+        return lit;
+    }
+    msg.base = meta;
+    msg.size = meta_len;
+    msg.tbl = meta + FbTable::rd<uint32_t>(meta);
+    AURON_CHECK(msg.scalar<uint8_t>(1, 0) == 3, "ScalarValue: second IPC message is not a RecordBatch");
+    FbTable rb = msg.table(2);
+    int64_t length = rb.scalar<int64_t>(0, 0);
+    uint32_t nnodes, nbufs;
+    const uint8_t* nodes = rb.vec(1, &nnodes);
+    const uint8_t* bufs = rb.vec(2, &nbufs);
+    AURON_CHECK(rb.field_off(3) == 0, "ScalarValue: compressed IPC bodies are not supported");
+    if (length == 0 || lit.type.id == T_NULL) {
+        lit.is_null = true;
+        return lit;
+    }
+    int64_t null_count = nnodes ? FbTable::rd<int64_t>(nodes + 8) : 0;
+    auto buf = [&](uint32_t i, int64_t* len) -> const uint8_t* {
+        AURON_CHECK(i < nbufs, "ScalarValue: missing buffer");
+        int64_t off = FbTable::rd<int64_t>(bufs + 16 * i);
+        *len = FbTable::rd<int64_t>(bufs + 16 * i + 8);
+        return body + off;
+    };
+    int64_t vlen;
+    const uint8_t* validity = buf(0, &vlen);
+    if (null_count > 0 || (vlen > 0 && !(validity[0] & 1))) {
+        lit.is_null = true;
+        return lit;
+    }
+    lit.is_null = false;
+    int64_t dlen;
+    switch (lit.type.id) {
+        case T_BOOL: lit.i = buf(1, &dlen)[0] & 1; break;
+        case T_INT8: lit.i = (int8_t)buf(1, &dlen)[0]; break;
+        case T_INT16: lit.i = FbTable::rd<int16_t>(buf(1, &dlen)); break;
+        case T_INT32: case T_DATE32: lit.i = FbTable::rd<int32_t>(buf(1, &dlen)); break;
+        case T_INT64: case T_DATE64: case T_TIMESTAMP: lit.i = FbTable::rd<int64_t>(buf(1, &dlen)); break;
+        case T_FLOAT32: lit.d = FbTable::rd<float>(buf(1, &dlen)); break;
+        case T_FLOAT64: lit.d = FbTable::rd<double>(buf(1, &dlen)); break;
+        case T_DECIMAL128: {
+            const uint8_t* d = buf(1, &dlen);
+            lit.lo = FbTable::rd<uint64_t>(d);
+            lit.hi = FbTable::rd<int64_t>(d + 8);
+            break;
+        }
+        case T_UTF8: case T_BINARY: {
+            const uint8_t* offs = buf(1, &dlen);
+            int32_t b0 = FbTable::rd<int32_t>(offs), b1 = FbTable::rd<int32_t>(offs + 4);
+            int64_t l2;
+            const uint8_t* data = buf(2, &l2);
+            lit.s.assign((const char*)data + b0, (size_t)(b1 - b0));
+            break;
+        }
+        default: fail("ScalarValue: unsupported literal type");
+    }
+    return lit;
+}
+
+// ------------------------------------------------------------------------------------------ expressions
+static const char* scalar_fn_name(int fun) {   // auron.proto ScalarFunction :213-292
+    switch (fun) {
+        case 0: return "Abs"; case 1: return "Acos"; case 2: return "Asin"; case 3: return "Atan"; case 5: return "Ceil";
+        case 6: return "Cos"; case 8: return "Exp"; case 9: return "Floor"; case 10: return "Ln"; case 11: return "Log";
+        case 12: return "Log10"; case 13: return "Log2"; case 14: return "Round"; case 15: return "Signum"; case 16: return "Sin";
+        case 17: return "Sqrt"; case 18: return "Tan"; case 19: return "Trunc"; case 20: return "NullIf"; case 23: return "Btrim";
+        case 24: return "CharacterLength"; case 26: return "Concat"; case 28: return "DatePart"; case 33: return "Lower";
+        case 34: return "Ltrim"; case 37: return "OctetLength"; case 45: return "Rtrim"; case 51: return "StartsWith";
+        case 53: return "Substr"; case 61: return "Trim"; case 62: return "Upper"; case 63: return "Coalesce"; case 64: return "Expm1";
+        case 67: return "Power"; case 69: return "IsNaN"; case 82: return "Nvl";
+        default: return nullptr;
+    }
+}
+
+static ExprPtr decode_expr_required(const uint8_t* b, size_t n) {
+    ExprPtr e = decode_expr(b, n);
+    AURON_CHECK(e != nullptr, "Unexpected empty physical expression");
+    return e;
+}
+
+ExprPtr decode_expr(const uint8_t* b, size_t n) {
+    PbReader r(b, n);
+    uint32_t f, w;
+    ExprPtr out;
+    while (r.next(&f, &w)) {
+        if (w != 2) {
+            r.skip(w);
+            continue;
+        }
+        const uint8_t* sb;
+        size_t sn;
+        r.bytes_view(&sb, &sn);
+        auto e = std::make_shared<Expr>();
+        PbReader s(sb, sn);
+        uint32_t sf, sw;
+        auto child = [&](PbReader& rr) {
+            const uint8_t* cb;
+            size_t cn;
+            rr.bytes_view(&cb, &cn);
+            return decode_expr_required(cb, cn);
+        };
+        switch (f) {
+            case 1:   // PhysicalColumn{name=1,index=2}: resolved by NAME (planner.rs:855)
+                e->kind = E_COLUMN;
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) e->name = s.bytes();
+                    else s.skip(sw);
+                }
+                break;
+            case 2:   // ScalarValue{ipc_bytes=1}
+                e->kind = E_LITERAL;
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) {
+                        const uint8_t* ib;
+                        size_t in;
+                        s.bytes_view(&ib, &in);
+                        e->lit = decode_scalar_ipc(ib, in);
+                    } else s.skip(sw);
+                }
+                break;
+            case 3:   // BoundReference{index=1,data_type=2,nullable=3}
+                e->kind = E_COLUMN;
+                e->index = 0;
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 0) e->index = (int)s.varint();
+                    else s.skip(sw);
+                }
+                break;
+            case 4:   // PhysicalBinaryExprNode{l=1,r=2,op=3}
+                e->kind = E_BINARY;
+                e->children.resize(2);
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) e->children[0] = child(s);
+                    else if (sf == 2 && sw == 2) e->children[1] = child(s);
+                    else if (sf == 3 && sw == 2) e->op = s.bytes();
+                    else s.skip(sw);
+                }
+                AURON_CHECK(e->children[0] && e->children[1], "binary expression missing operand");
+                break;
+            case 5: fail("Cannot convert aggregate expr node to physical expression");
+            case 11: fail("Cannot convert sort expr node to physical expression");
+            case 6: case 7: case 8: case 12:
+                e->kind = f == 6 ? E_IS_NULL : f == 7 ? E_IS_NOT_NULL : f == 8 ? E_NOT : E_NEGATIVE;
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) e->children.push_back(child(s));
+                    else s.skip(sw);
+                }
+                break;
+            case 9: {   // PhysicalCaseNode{expr=1, when_then_expr=2{when=1,then=2}, else_expr=3}
+                e->kind = E_CASE;
+                ExprPtr base, els;
+                std::vector<ExprPtr> wt;
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) base = child(s);
+                    else if (sf == 2 && sw == 2) {
+                        const uint8_t* wb;
+                        size_t wn;
+                        s.bytes_view(&wb, &wn);
+                        PbReader wr(wb, wn);
+                        uint32_t wf, ww;
+                        ExprPtr we, te;
+                        while (wr.next(&wf, &ww)) {
+                            if (wf == 1 && ww == 2) we = child(wr);
+                            else if (wf == 2 && ww == 2) te = child(wr);
+                            else wr.skip(ww);
+                        }
+                        AURON_CHECK(we && te, "CASE branch missing when/then");
+                        wt.push_back(we);
+                        wt.push_back(te);
+                    } else if (sf == 3 && sw == 2) els = child(s);
+                    else s.skip(sw);
+                }
+                if (base) {
+                    e->has_case_expr = true;
+                    e->children.push_back(base);
+                }
+                for (auto& x : wt) e->children.push_back(x);
+                if (els) {
+                    e->has_else = true;
+                    e->children.push_back(els);
+                }
+                break;
+            }
+            case 10: case 15:   // Cast / TryCast {expr=1, arrow_type=2}
+                e->kind = f == 10 ? E_CAST : E_TRY_CAST;
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) e->children.push_back(child(s));
+                    else if (sf == 2 && sw == 2) {
+                        const uint8_t* tb;
+                        size_t tn;
+                        s.bytes_view(&tb, &tn);
+                        e->type = decode_arrow_type(tb, tn);
+                    } else s.skip(sw);
+                }
+                break;
+            case 13:   // InList{expr=1, list=2, negated=3}
+                e->kind = E_IN_LIST;
+                e->children.resize(1);
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) e->children[0] = child(s);
+                    else if (sf == 2 && sw == 2) e->children.push_back(child(s));
+                    else if (sf == 3 && sw == 0) e->negated = s.varint() != 0;
+                    else s.skip(sw);
+                }
+                break;
+            case 14: {   // ScalarFunction{name=1, fun=2, args=3, return_type=4}
+                e->kind = E_SCALAR_FN;
+                int fun = 0;
+                std::string nm;
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) nm = s.bytes();
+                    else if (sf == 2 && sw == 0) fun = (int)s.varint();
+                    else if (sf == 3 && sw == 2) e->children.push_back(child(s));
+                    else if (sf == 4 && sw == 2) {
+                        const uint8_t* tb;
+                        size_t tn;
+                        s.bytes_view(&tb, &tn);
+                        e->type = decode_arrow_type(tb, tn);
+                    } else s.skip(sw);
+                }
+                if (fun == 10000) e->name = nm;   // AuronExtFunctions: name selects the function (planner.rs:944-960)
+                else {
+                    const char* k = scalar_fn_name(fun);
+                    if (!k) fail("scalar function #" + std::to_string(fun) + " is not native on device");
+                    e->name = k;
+                }
+                break;
+            }
+            case 20:   // Like{negated=1, case_insensitive=2, expr=3, pattern=4}
+                e->kind = E_LIKE;
+                e->children.resize(2);
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 0) e->negated = s.varint() != 0;
+                    else if (sf == 2 && sw == 0) e->case_insensitive = s.varint() != 0;
+                    else if (sf == 3 && sw == 2) e->children[0] = child(s);
+                    else if (sf == 4 && sw == 2) e->children[1] = child(s);
+                    else s.skip(sw);
+                }
+                break;
+            case 3000: case 3001:
+                e->kind = f == 3000 ? E_SC_AND : E_SC_OR;
+                e->children.resize(2);
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) e->children[0] = child(s);
+                    else if (sf == 2 && sw == 2) e->children[1] = child(s);
+                    else s.skip(sw);
+                }
+                break;
+            case 20000: case 20001: case 20002:
+                e->kind = f == 20000 ? E_STARTS_WITH : f == 20001 ? E_ENDS_WITH : E_CONTAINS;
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) e->children.push_back(child(s));
+                    else if (sf == 2 && sw == 2) e->lit.s = s.bytes();
+                    else s.skip(sw);
+                }
+                break;
+            default:
+                fail("physical expression kind #" + std::to_string(f) + " is not native on device (JVM-callback / nested-type expressions are out of scope)");
+        }
+        out = e;
+    }
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------ plan nodes
+static OperatorPtr decode_plan(Task& t, const uint8_t* b, size_t n);
+
+static OperatorPtr plan_field(Task& t, PbReader& r) {
+    const uint8_t* sb;
+    size_t sn;
+    r.bytes_view(&sb, &sn);
+    return decode_plan(t, sb, sn);
+}
+static ExprPtr expr_field(PbReader& r) {
+    const uint8_t* sb;
+    size_t sn;
+    r.bytes_view(&sb, &sn);
+    return decode_expr_required(sb, sn);
+}
+static Schema schema_field(PbReader& r) {
+    const uint8_t* sb;
+    size_t sn;
+    r.bytes_view(&sb, &sn);
+    return decode_schema(sb, sn);
+}
+
+static void decode_join_on(PbReader& r, std::vector<ExprPtr>* l, std::vector<ExprPtr>* rr) {
+    const uint8_t* sb;
+    size_t sn;
+    r.bytes_view(&sb, &sn);
+    PbReader s(sb, sn);
+    uint32_t f, w;
+    ExprPtr le, re;
+    while (s.next(&f, &w)) {
+        if (f == 1 && w == 2) le = expr_field(s);
+        else if (f == 2 && w == 2) re = expr_field(s);
+        else s.skip(w);
+    }
+    AURON_CHECK(le && re, "JoinOn needs both sides");
+    l->push_back(le);
+    rr->push_back(re);
+}
+
+static SortExprSpec decode_sort_expr(const uint8_t* b, size_t n) {
+    // PhysicalExprNode{sort=11{expr=1, asc=2, nulls_first=3}}
+    PbReader r(b, n);
+    uint32_t f, w;
+    SortExprSpec out;
+    out.asc = false;
+    out.nulls_first = false;
+    bool found = false;
+    while (r.next(&f, &w)) {
+        if (f == 11 && w == 2) {
+            const uint8_t* sb;
+            size_t sn;
+            r.bytes_view(&sb, &sn);
+            PbReader s(sb, sn);
+            uint32_t sf, sw;
+            while (s.next(&sf, &sw)) {
+                if (sf == 1 && sw == 2) out.expr = expr_field(s);
+                else if (sf == 2 && sw == 0) out.asc = s.varint() != 0;
+                else if (sf == 3 && sw == 0) out.nulls_first = s.varint() != 0;
+                else s.skip(sw);
+            }
+            found = true;
+        } else r.skip(w);
+    }
+    AURON_CHECK(found && out.expr, "sort expression expected");
+    return out;
+}
+
+static OperatorPtr decode_agg(Task& t, const uint8_t* b, size_t n) {
+    PbReader r(b, n);
+    uint32_t f, w;
+    OperatorPtr input;
+    std::vector<ExprPtr> groups;
+    std::vector<std::string> gnames, anames;
+    std::vector<int> modes;
+    std::vector<AggExprSpec> aggs;
+    while (r.next(&f, &w)) {
+        if (f == 1 && w == 2) input = plan_field(t, r);
+        else if (f == 3 && w == 2) groups.push_back(expr_field(r));
+        else if (f == 4 && w == 2) {   // PhysicalExprNode{agg_expr=5{agg_function=1, children=3, return_type=4}}
+            const uint8_t* sb;
+            size_t sn;
+            r.bytes_view(&sb, &sn);
+            PbReader e(sb, sn);
+            uint32_t ef, ew;
+            AggExprSpec spec;
+            bool found = false;
+            while (e.next(&ef, &ew)) {
+                if (ef == 5 && ew == 2) {
+                    const uint8_t* ab;
+                    size_t an;
+                    e.bytes_view(&ab, &an);
+                    PbReader a(ab, an);
+                    uint32_t af, aw;
+                    spec.fn = 0;
+                    while (a.next(&af, &aw)) {
+                        if (af == 1 && aw == 0) spec.fn = (int)a.varint();
+                        else if (af == 3 && aw == 2) spec.children.push_back(expr_field(a));
+                        else if (af == 4 && aw == 2) {
+                            const uint8_t* tb;
+                            size_t tn;
+                            a.bytes_view(&tb, &tn);
+                            spec.return_type = decode_arrow_type(tb, tn);
+                        } else a.skip(aw);
+                    }
+                    found = true;
+                } else e.skip(ew);
+            }
+            AURON_CHECK(found, "Invalid aggregate expression for AggExec");
+            aggs.push_back(spec);
+        } else if (f == 5 && w == 0) modes.push_back((int)r.varint());
+        else if (f == 5 && w == 2) {   // packed repeated enum
+            const uint8_t* sb;
+            size_t sn;
+            r.bytes_view(&sb, &sn);
+            PbReader p(sb, sn);
+            while (!p.done()) modes.push_back((int)p.varint());
+        } else if (f == 6 && w == 2) gnames.push_back(r.bytes());
+        else if (f == 7 && w == 2) anames.push_back(r.bytes());
+        else r.skip(w);
+    }
+    AURON_CHECK(input, "AggExecNode without input");
+    for (size_t i = 0; i < aggs.size(); i++) {
+        aggs[i].mode = i < modes.size() ? modes[i] : MODE_PARTIAL;
+        aggs[i].name = i < anames.size() ? anames[i] : "";
+    }
+    return OperatorPtr(new AggExec(std::move(input), groups, gnames, aggs));
+}
+
+static OperatorPtr decode_join(Task& t, const uint8_t* b, size_t n, int kind /*0 hash, 1 smj, 2 broadcast*/) {
+    PbReader r(b, n);
+    uint32_t f, w;
+    Schema schema;
+    OperatorPtr left, right;
+    std::vector<ExprPtr> lk, rk;
+    int jt = JOIN_INNER, side = SIDE_RIGHT;
+    bool null_aware = false;
+    std::string cache_id;
+    while (r.next(&f, &w)) {
+        if (f == 1 && w == 2) schema = schema_field(r);
+        else if (f == 2 && w == 2) left = plan_field(t, r);
+        else if (f == 3 && w == 2) right = plan_field(t, r);
+        else if (f == 4 && w == 2) decode_join_on(r, &lk, &rk);
+        else if (kind == 1 && f == 6 && w == 0) jt = (int)r.varint();
+        else if (kind != 1 && f == 5 && w == 0) jt = (int)r.varint();
+        else if (kind != 1 && f == 6 && w == 0) side = (int)r.varint();
+        else if (kind == 2 && f == 7 && w == 2) cache_id = r.bytes();
+        else if (kind == 2 && f == 8 && w == 0) null_aware = r.varint() != 0;
+        else r.skip(w);
+    }
+    AURON_CHECK(left && right, "join without both inputs");
+    if (kind == 1) side = (jt == JOIN_RIGHT) ? SIDE_LEFT : SIDE_RIGHT;   // SMJ: stream the preserved side, keep its order
+    auto* j = new HashJoinExec(std::move(left), std::move(right), lk, rk, jt, side, schema);
+    j->null_aware_anti = null_aware;
+    j->cache_id = cache_id;
+    if (kind == 1) j->name = "SortMergeJoinExec";
+    if (kind == 2) j->name = "BroadcastJoinExec";
+    return OperatorPtr(j);
+}
+
+static OperatorPtr decode_plan(Task& t, const uint8_t* b, size_t n) {
+    PbReader r(b, n);
+    uint32_t f, w;
+    OperatorPtr out;
+    while (r.next(&f, &w)) {
+        if (w != 2) {
+            r.skip(w);
+            continue;
+        }
+        const uint8_t* sb;
+        size_t sn;
+        r.bytes_view(&sb, &sn);
+        PbReader s(sb, sn);
+        uint32_t sf, sw;
+        switch (f) {   // PhysicalPlanNode oneof (auron.proto:27-56)
+            case 8: {   // FilterExecNode{input=1, expr=2}  (planner.rs:156-164)
+                OperatorPtr input;
+                std::vector<ExprPtr> preds;
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) input = plan_field(t, s);
+                    else if (sf == 2 && sw == 2) preds.push_back(expr_field(s));
+                    else s.skip(sw);
+                }
+                AURON_CHECK(input && !preds.empty(), "FilterExecNode needs input and predicates");
+                out.reset(new FilterExec(std::move(input), preds));
+                break;
+            }
+            case 6: {   // ProjectionExecNode{input=1, expr=2, expr_name=3, data_type=4}  (planner.rs:130-155)
+                OperatorPtr input;
+                std::vector<ExprPtr> exprs;
+                std::vector<std::string> names;
+                std::vector<DType> types;
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) input = plan_field(t, s);
+                    else if (sf == 2 && sw == 2) exprs.push_back(expr_field(s));
+                    else if (sf == 3 && sw == 2) names.push_back(s.bytes());
+                    else if (sf == 4 && sw == 2) {
+                        const uint8_t* tb;
+                        size_t tn;
+                        s.bytes_view(&tb, &tn);
+                        types.push_back(decode_arrow_type(tb, tn));
+                    } else s.skip(sw);
+                }
+                AURON_CHECK(input, "ProjectionExecNode without input");
+                out.reset(new ProjectExec(std::move(input), exprs, names, types));
+                break;
+            }
+            case 16: out = decode_agg(t, sb, sn); break;
+            case 11: out = decode_join(t, sb, sn, 0); break;
+            case 10: out = decode_join(t, sb, sn, 1); break;
+            case 13: out = decode_join(t, sb, sn, 2); break;
+            case 7: {   // SortExecNode{input=1, expr=2, fetch_limit=3{limit=1, offset=2}}  (planner.rs:355-369)
+                OperatorPtr input;
+                std::vector<SortExprSpec> keys;
+                int64_t limit = -1, offset = 0;
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) input = plan_field(t, s);
+                    else if (sf == 2 && sw == 2) {
+                        const uint8_t* eb;
+                        size_t en;
+                        s.bytes_view(&eb, &en);
+                        keys.push_back(decode_sort_expr(eb, en));
+                    } else if (sf == 3 && sw == 2) {
+                        const uint8_t* lb;
+                        size_t ln;
+                        s.bytes_view(&lb, &ln);
+                        PbReader l(lb, ln);
+                        uint32_t lf, lw;
+                        limit = 0;
+                        while (l.next(&lf, &lw)) {
+                            if (lf == 1 && lw == 0) limit = (int64_t)l.varint();
+                            else if (lf == 2 && lw == 0) offset = (int64_t)l.varint();
+                            else l.skip(lw);
+                        }
+                    } else s.skip(sw);
+                }
+                AURON_CHECK(input, "SortExecNode without input");
+                out.reset(new SortExec(std::move(input), keys, limit, offset));
+                break;
+            }
+            case 17: {   // LimitExecNode{input=1, limit=2, offset=3}
+                OperatorPtr input;
+                int64_t limit = 0, offset = 0;
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) input = plan_field(t, s);
+                    else if (sf == 2 && sw == 0) limit = (int64_t)s.varint();
+                    else if (sf == 3 && sw == 0) offset = (int64_t)s.varint();
+                    else s.skip(sw);
+                }
+                AURON_CHECK(input, "LimitExecNode without input");
+                out.reset(new LimitExec(std::move(input), limit, offset));
+                break;
+            }
+            case 18: {   // FFIReaderExecNode{num_partitions=1, schema=2, export_iter_provider_resource_id=3}  (planner.rs:570-577)
+                Schema schema;
+                std::string id;
+                while (s.next(&sf, &sw)) {
+                    if (sf == 2 && sw == 2) schema = schema_field(s);
+                    else if (sf == 3 && sw == 2) id = s.bytes();
+                    else s.skip(sw);
+                }
+                out.reset(new FFIReaderExec(schema, id));
+                break;
+            }
+            case 14: {   // RenameColumnsExecNode{input=1, renamed_column_names=2}
+                OperatorPtr input;
+                std::vector<std::string> names;
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) input = plan_field(t, s);
+                    else if (sf == 2 && sw == 2) names.push_back(s.bytes());
+                    else s.skip(sw);
+                }
+                AURON_CHECK(input, "RenameColumnsExecNode without input");
+                out.reset(new RenameColumnsExec(std::move(input), names));
+                break;
+            }
+            case 15: {   // EmptyPartitionsExecNode{schema=1}
+                Schema schema;
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) schema = schema_field(s);
+                    else s.skip(sw);
+                }
+                out.reset(new EmptyPartitionsExec(schema));
+                break;
+            }
+            case 19: case 12: case 1: {   // CoalesceBatches / BroadcastJoinBuildHashMap / Debug: input = 1
+                OperatorPtr input;
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) input = plan_field(t, s);
+                    else s.skip(sw);
+                }
+                AURON_CHECK(input, "plan node without input");
+                out.reset(new PassThroughExec(std::move(input), f == 19 ? "CoalesceBatchesExec" : f == 12 ? "BroadcastJoinBuildHashMapExec" : "DebugExec"));
+                break;
+            }
+            case 9: {   // UnionExecNode{input=1{input=1, partition=2}, schema=2, num_partitions=3, cur_partition=4}
+                std::vector<OperatorPtr> inputs;
+                Schema schema;
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) {
+                        const uint8_t* ub;
+                        size_t un;
+                        s.bytes_view(&ub, &un);
+                        PbReader u(ub, un);
+                        uint32_t uf, uw;
+                        while (u.next(&uf, &uw)) {
+                            if (uf == 1 && uw == 2) inputs.push_back(plan_field(t, u));
+                            else u.skip(uw);
+                        }
+                    } else if (sf == 2 && sw == 2) schema = schema_field(s);
+                    else s.skip(sw);
+                }
+                if (schema.fields.empty() && !inputs.empty()) schema = inputs[0]->out_schema;
+                out.reset(new UnionExec(std::move(inputs), schema));
+                break;
+            }
+            case 5: out = make_parquet_scan(t, sb, sn); break;
+            case 2: {   // ShuffleWriterExecNode{input=1, ...}
+                OperatorPtr input;
+                PbReader s2(sb, sn);
+                while (s2.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) input = plan_field(t, s2);
+                    else s2.skip(sw);
+                }
+                AURON_CHECK(input, "ShuffleWriterExecNode without input");
+                out = make_shuffle_writer(t, std::move(input), sb, sn);
+                break;
+            }
+            default:
+                fail("plan node #" + std::to_string(f) + " is not native in auron_b200 (see DESIGN.md scope)");
+        }
+    }
+    AURON_CHECK(out != nullptr, "empty PhysicalPlanNode");
+    return out;
+}
+
+std::unique_ptr<Task> create_task(const uint8_t* task_def, size_t len, const auron_callbacks* cb, int device) {
+    auto t = std::make_unique<Task>(device);
+    t->cb = cb;
+    PbReader r(task_def, len);
+    uint32_t f, w;
+    while (r.next(&f, &w)) {
+        if (f == 1 && w == 2) {   // PartitionId{stage_id=2, partition_id=4, task_id=5}
+            const uint8_t* sb;
+            size_t sn;
+            r.bytes_view(&sb, &sn);
+            PbReader s(sb, sn);
+            uint32_t sf, sw;
+            while (s.next(&sf, &sw)) {
+                if (sf == 2 && sw == 0) t->stage_id = (uint32_t)s.varint();
+                else if (sf == 4 && sw == 0) t->partition_id = (uint32_t)s.varint();
+                else if (sf == 5 && sw == 0) t->task_id = s.varint();
+                else s.skip(sw);
+            }
+        } else if (f == 2 && w == 2) {
+            const uint8_t* sb;
+            size_t sn;
+            r.bytes_view(&sb, &sn);
+            t->root = decode_plan(*t, sb, sn);
+        } else r.skip(w);
+    }
+    AURON_CHECK(t->root != nullptr, "TaskDefinition without a plan");
+    return t;
+}
+
+}  // namespace auron

@@ -1,0 +1,238 @@
+"""ctypes binding of libauron_b200.so -- the host side that plays the role of Auron's JVM glue
+(auron-core/src/main/java/org/apache/auron/jni/AuronCallNativeWrapper.java:78-192): ship a protobuf
+TaskDefinition down, pull Arrow batches back through the Arrow C Data Interface, feed FFI-reader
+inputs through the export_next_batch upcall.
+
+There is NO CPU fallback: if the CUDA library is missing or no device is present every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Iterable
+
+import pyarrow as pa
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libauron_b200.so")
+
+
+class ArrowSchemaC(C.Structure):
+    _fields_ = [("format", C.c_char_p), ("name", C.c_char_p), ("metadata", C.c_char_p), ("flags", C.c_int64), ("n_children", C.c_int64),
+                ("children", C.c_void_p), ("dictionary", C.c_void_p), ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
+class ArrowArrayC(C.Structure):
+    _fields_ = [("length", C.c_int64), ("null_count", C.c_int64), ("offset", C.c_int64), ("n_buffers", C.c_int64), ("n_children", C.c_int64),
+                ("buffers", C.c_void_p), ("children", C.c_void_p), ("dictionary", C.c_void_p), ("release", C.c_void_p), ("private_data", C.c_void_p)]
+
+
+_EXPORT_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p, C.c_void_p)
+_READ_CB = C.CFUNCTYPE(C.c_int64, C.c_void_p, C.c_char_p, C.c_char_p, C.c_int64, C.c_void_p, C.c_int64)
+_RUNNING_CB = C.CFUNCTYPE(C.c_int, C.c_void_p)
+_METRIC_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int64)
+
+
+class Callbacks(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("export_next_batch", _EXPORT_CB), ("read_fully", _READ_CB), ("is_task_running", _RUNNING_CB)]
+
+
+class AuronError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise AuronError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` first")
+        L = C.CDLL(LIB_PATH)
+        L.auron_b200_call_native.restype = C.c_void_p
+        L.auron_b200_call_native.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_int]
+        L.auron_b200_schema.argtypes = [C.c_void_p, C.c_void_p]
+        L.auron_b200_next_batch.argtypes = [C.c_void_p, C.c_void_p]
+        L.auron_b200_finalize_native.argtypes = [C.c_void_p]
+        L.auron_b200_finalize_native.restype = None
+        L.auron_b200_last_error.restype = C.c_char_p
+        L.auron_b200_metrics.argtypes = [C.c_void_p, _METRIC_CB, C.c_void_p]
+        L.auron_b200_put_device_batch.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.auron_b200_drop_device_resource.argtypes = [C.c_char_p]
+        L.auron_b200_drop_device_resource.restype = None
+        L.auron_b200_k_hash.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+        L.auron_b200_k_partition_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int]
+        L.auron_b200_kernel_launches.restype = C.c_int64
+        L.auron_b200_time_kernel.restype = C.c_double
+        L.auron_b200_time_kernel.argtypes = [C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int]
+        _lib = L
+    return _lib
+
+
+EXPORTED_SYMBOLS = [
+    "auron_b200_call_native", "auron_b200_schema", "auron_b200_next_batch", "auron_b200_finalize_native", "auron_b200_on_exit",
+    "auron_b200_last_error", "auron_b200_metrics", "auron_b200_put_device_batch", "auron_b200_drop_device_resource", "auron_b200_k_hash",
+    "auron_b200_k_partition_ids", "auron_b200_kernel_launches", "auron_b200_time_kernel",
+]
+
+
+def _err() -> str:
+    return (lib().auron_b200_last_error() or b"").decode(errors="replace")
+
+
+def _export_batch(batch: pa.RecordBatch):
+    arr, sch = ArrowArrayC(), ArrowSchemaC()
+    batch._export_to_c(C.addressof(arr), C.addressof(sch))
+    return arr, sch
+
+
+def _release(struct):
+    if struct.release:
+        C.CFUNCTYPE(None, C.c_void_p)(struct.release)(C.addressof(struct))
+
+
+def kernel_launches() -> int:
+    return lib().auron_b200_kernel_launches()
+
+
+class Task:
+    """One native task: callNative -> nextBatch* -> finalizeNative (JniBridge.java:49-55)."""
+
+    def __init__(self, task_definition: bytes, inputs: dict[str, Iterable[pa.RecordBatch]] | None = None, device: int = 0,
+                 read_fully=None):
+        self._inputs = {k: iter(v) for k, v in (inputs or {}).items()}
+        self._cb_error: BaseException | None = None
+
+        def _export_next(user, rid, out_ptr):
+            try:
+                it = self._inputs.get(rid.decode())
+                if it is None:
+                    return -1
+                batch = next(it, None)
+                if batch is None:
+                    return 0
+                batch._export_to_c(out_ptr)
+                return 1
+            except BaseException as e:  # noqa: BLE001 - must not unwind through C
+                self._cb_error = e
+                return -1
+
+        def _read(user, fsid, path, pos, buf, length):
+            try:
+                if read_fully is not None:
+                    data = read_fully(fsid.decode(), path.decode(), pos, length)
+                else:
+                    with open(path.decode(), "rb") as f:
+                        f.seek(pos)
+                        data = f.read(length)
+                C.memmove(buf, data, len(data))
+                return len(data)
+            except BaseException as e:  # noqa: BLE001
+                self._cb_error = e
+                return -1
+
+        self._cbs = Callbacks(None, _EXPORT_CB(_export_next), _READ_CB(_read) if read_fully is not None else _READ_CB(0), _RUNNING_CB(0))
+        self._handle = lib().auron_b200_call_native(task_definition, len(task_definition), C.addressof(self._cbs), device)
+        if not self._handle:
+            raise AuronError(_err())
+        sch = ArrowSchemaC()
+        if lib().auron_b200_schema(self._handle, C.addressof(sch)) != 0:
+            raise AuronError(_err())
+        self.schema = pa.Schema._import_from_c(C.addressof(sch))
+
+    def next_batch(self) -> pa.RecordBatch | None:
+        arr = ArrowArrayC()
+        rc = lib().auron_b200_next_batch(self._handle, C.addressof(arr))
+        if rc < 0:
+            if self._cb_error is not None:
+                raise self._cb_error
+            raise AuronError(_err())
+        if rc == 0:
+            return None
+        return pa.RecordBatch._import_from_c(C.addressof(arr), self.schema)
+
+    def __iter__(self):
+        while True:
+            b = self.next_batch()
+            if b is None:
+                return
+            yield b
+
+    def metrics(self) -> list[tuple[int, str, str, int]]:
+        out = []
+
+        def cb(user, depth, op, name, value):
+            out.append((depth, op.decode(), name.decode(), value))
+
+        lib().auron_b200_metrics(self._handle, _METRIC_CB(cb), None)
+        return out
+
+    def close(self):
+        if self._handle:
+            lib().auron_b200_finalize_native(self._handle)
+            self._handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def run_task(task_definition: bytes, inputs: dict[str, Iterable[pa.RecordBatch]] | None = None, device: int = 0, read_fully=None) -> pa.Table:
+    """Execute a TaskDefinition and collect its output stream."""
+    with Task(task_definition, inputs, device, read_fully) as t:
+        batches = list(t)
+        return pa.Table.from_batches(batches, schema=t.schema)
+
+
+def put_device_batch(resource_id: str, batch: pa.RecordBatch, device: int = 0):
+    arr, sch = _export_batch(batch)
+    try:
+        if lib().auron_b200_put_device_batch(resource_id.encode(), C.addressof(arr), C.addressof(sch), device) != 0:
+            raise AuronError(_err())
+    finally:
+        _release(arr)
+        _release(sch)
+
+
+def drop_device_resource(resource_id: str):
+    lib().auron_b200_drop_device_resource(resource_id.encode())
+
+
+def _kernel_one_column(fn, batch: pa.RecordBatch, cols: list[int], *mid_args, device: int = 0) -> pa.Array:
+    arr, sch = _export_batch(batch)
+    oa, os_ = ArrowArrayC(), ArrowSchemaC()
+    idx = (C.c_int32 * len(cols))(*cols)
+    try:
+        rc = fn(C.addressof(arr), C.addressof(sch), idx, len(cols), *mid_args, C.addressof(oa), C.addressof(os_), device)
+        if rc != 0:
+            raise AuronError(_err())
+    finally:
+        _release(arr)
+        _release(sch)
+    schema = pa.Schema._import_from_c(C.addressof(os_))
+    return pa.RecordBatch._import_from_c(C.addressof(oa), schema).column(0)
+
+
+def k_hash(batch: pa.RecordBatch, cols: list[int], kind: str = "murmur3", seed: int = 42, device: int = 0) -> pa.Array:
+    return _kernel_one_column(lib().auron_b200_k_hash, batch, cols, 0 if kind == "murmur3" else 1, seed, device=device)
+
+
+def k_partition_ids(batch: pa.RecordBatch, cols: list[int], num_partitions: int, device: int = 0) -> pa.Array:
+    return _kernel_one_column(lib().auron_b200_k_partition_ids, batch, cols, num_partitions, device=device)
+
+
+def time_kernel(kernel: str, resource_id: str, iters: int = 10, arg0: int = 0, device: int = 0) -> float:
+    ms = lib().auron_b200_time_kernel(kernel.encode(), resource_id.encode(), iters, arg0, device)
+    if ms < 0:
+        raise AuronError(_err())
+    return ms

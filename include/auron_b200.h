@@ -1,0 +1,95 @@
+/*
+ * auron_b200.h -- C ABI of libauron_b200.so, the B200-native drop-in for Apache Auron's native engine
+ * (the Rust cdylib `libauron`).  Plain pointers and sizes only; batches cross the boundary through the
+ * Arrow C Data Interface exactly as in the reference.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to apache/auron):
+ *
+ *   auron_b200_call_native      <- Java_org_apache_auron_jni_JniBridge_callNative
+ *                                  native-engine/auron/src/exec.rs:42-118 (+ rt.rs:75-248 start)
+ *   auron_b200_schema           <- AuronCallNativeWrapper.importSchema upcall, rt.rs:167-170
+ *   auron_b200_next_batch       <- Java_..._JniBridge_nextBatch, exec.rs:122-129 (+ rt.rs:250-280,
+ *                                  importBatch upcall :258-262)
+ *   auron_b200_finalize_native  <- Java_..._JniBridge_finalizeNative, exec.rs:133-140 (rt.rs:282-306)
+ *   auron_b200_on_exit          <- Java_..._JniBridge_onExit, exec.rs:144-149
+ *   auron_b200_metrics          <- update_metrics walk, native-engine/auron/src/metrics.rs:22-58
+ *   auron_callbacks             <- the JNI upcalls the engine makes on the hot path
+ *                                  (native-engine/auron-jni-bridge/src/jni_bridge.rs:607-777,1485-1525)
+ *
+ * The JNI symbols themselves (same names/signatures as exec.rs) are exported by jni_face.cc on top of
+ * these functions; see INTEGRATION.md.
+ */
+#ifndef AURON_B200_H
+#define AURON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+struct ArrowSchema;
+struct ArrowArray;
+
+/* Upcalls (all optional except export_next_batch when the plan has an FFIReaderExec). */
+typedef struct auron_callbacks {
+    void* user;
+    /* AuronArrowFFIExporter.exportNextBatch(long ptr) (ffi_reader_exec.rs:182-251): fill *out (an empty
+     * ArrowArray owned by the engine, which will call out->release) with the next batch of the exporter
+     * registered under resource_id.  Returns 1 = batch produced, 0 = end of input, <0 = error. */
+    int (*export_next_batch)(void* user, const char* resource_id, struct ArrowArray* out);
+    /* FSDataInputWrapper.readFully(pos, buf) through JniBridge.openFileAsDataInputWrapper
+     * (scan/internal_file_reader.rs:64-68, parquet_exec.rs:294-397).  Returns bytes read or <0.
+     * NULL => the engine reads `path` from the local file system. */
+    int64_t (*read_fully)(void* user, const char* fs_resource_id, const char* path, int64_t pos, void* buf, int64_t len);
+    /* JniBridge.isTaskRunning() (auron-jni-bridge/src/lib.rs:35-50).  NULL => always running. */
+    int (*is_task_running)(void* user);
+} auron_callbacks;
+
+typedef struct auron_task auron_task;
+
+/* Decode a protobuf TaskDefinition (auron.proto:790-795), build the operator tree and start the task on
+ * CUDA device `device`.  Returns NULL on failure (see auron_b200_last_error). */
+auron_task* auron_b200_call_native(const uint8_t* task_definition, size_t len, const auron_callbacks* callbacks, int device);
+/* Output schema of the task's root operator.  Caller releases *out.  0 = ok, <0 = error. */
+int auron_b200_schema(auron_task* task, struct ArrowSchema* out);
+/* Next output batch (a struct array, one child per column; move semantics, caller calls out->release).
+ * 1 = batch delivered, 0 = end of stream, <0 = error. */
+int auron_b200_next_batch(auron_task* task, struct ArrowArray* out);
+/* Cancel outstanding work, free the task.  Safe before the stream is exhausted (rt.rs:282-298). */
+void auron_b200_finalize_native(auron_task* task);
+void auron_b200_on_exit(void);
+/* Thread-local message of the last failing call on this thread. */
+const char* auron_b200_last_error(void);
+
+/* Walk the operator tree depth-first (same order as the JVM MetricNode tree) reporting (name, value). */
+typedef void (*auron_metric_fn)(void* user, int depth, const char* operator_name, const char* metric_name, int64_t value);
+int auron_b200_metrics(auron_task* task, auron_metric_fn fn, void* user);
+
+/* ---- device-resident inputs (no counterpart in the reference: HBM residency for the GPU engine) ----
+ * Copies `batch` to HBM and appends it to the resource `resource_id`; an FFIReaderExec whose
+ * export_iter_provider_resource_id equals resource_id then streams the resident batches without any
+ * host transfer.  The batch is NOT released by the call. */
+int auron_b200_put_device_batch(const char* resource_id, const struct ArrowArray* batch, const struct ArrowSchema* schema, int device);
+void auron_b200_drop_device_resource(const char* resource_id);
+
+/* ---- kernel-level entry points (one per device algorithm; used by tests, ncu captures, bench) ----
+ * Inputs/outputs are host Arrow struct arrays; columns named by index. */
+/* create_murmur3_hashes / create_xxhash64_hashes (datafusion-ext-commons/src/spark_hash.rs:28-57):
+ * kind 0 = murmur3 -> int32 column, 1 = xxhash64 -> int64 column. */
+int auron_b200_k_hash(const struct ArrowArray* batch, const struct ArrowSchema* schema, const int32_t* cols, int32_t ncols, int32_t kind,
+                      int64_t seed, struct ArrowArray* out, struct ArrowSchema* out_schema, int device);
+/* evaluate_partition_ids (datafusion-ext-plans/src/shuffle/mod.rs:163-188) -> int32 column */
+int auron_b200_k_partition_ids(const struct ArrowArray* batch, const struct ArrowSchema* schema, const int32_t* cols, int32_t ncols,
+                               int32_t num_partitions, struct ArrowArray* out, struct ArrowSchema* out_schema, int device);
+/* number of kernels this library has launched in the calling process (bench.py "gpu_launches") */
+int64_t auron_b200_kernel_launches(void);
+/* micro-benchmark hook: runs `iters` launches of a named kernel over device-resident resource data and
+ * returns the average milliseconds per launch measured with CUDA events on the launching stream. */
+double auron_b200_time_kernel(const char* kernel, const char* resource_id, int32_t iters, int32_t arg0, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AURON_B200_H */

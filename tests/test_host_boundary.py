@@ -1,0 +1,107 @@
+"""CPU-only checks of the boundary: the C-ABI library loads and exports every symbol declared in
+include/auron_b200.h, the plan encoder produces well-formed protobuf, and the product refuses to run
+without a CUDA device (no CPU fallback)."""
+import os
+import re
+
+import pyarrow as pa
+import pytest
+
+from auron_b200 import proto as P
+from auron_b200 import runtime
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "auron_b200.h")).read()
+    return sorted(set(re.findall(r"\b(auron_b200_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = runtime.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 13
+    for sym in declared:
+        assert hasattr(L, sym), f"{sym} declared in include/auron_b200.h but not exported"
+    assert set(runtime.EXPORTED_SYMBOLS) <= set(declared)
+
+
+def test_jni_symbols_exported():
+    # same names as native-engine/auron/src/exec.rs:42,122,133,144
+    import ctypes
+    L = ctypes.CDLL(runtime.LIB_PATH)
+    for s in ("callNative", "nextBatch", "finalizeNative", "onExit"):
+        assert hasattr(L, f"Java_org_apache_auron_jni_JniBridge_{s}")
+
+
+def _parse(buf: bytes):
+    """tiny generic proto reader: [(field, wire, value)]"""
+    out, i = [], 0
+
+    def varint():
+        nonlocal i
+        v = s = 0
+        while True:
+            b = buf[i]
+            i += 1
+            v |= (b & 0x7F) << s
+            if not b & 0x80:
+                return v
+            s += 7
+
+    while i < len(buf):
+        t = varint()
+        f, w = t >> 3, t & 7
+        if w == 0:
+            out.append((f, w, varint()))
+        elif w == 2:
+            n = varint()
+            out.append((f, w, buf[i:i + n]))
+            i += n
+        else:
+            raise AssertionError("unexpected wire type")
+    return out
+
+
+def test_plan_encoding_roundtrip():
+    s = pa.schema([("a", pa.int64()), ("s", pa.string()), ("d", pa.decimal128(7, 2))])
+    plan = P.filter_(P.ffi_reader(s, "rid"), [P.binary("Gt", P.col("a"), P.lit(5, pa.int64()))])
+    td = P.task_definition(plan, stage_id=3, partition_id=4, task_id=5)
+    top = _parse(td)
+    assert [f for f, _, _ in top] == [1, 2]
+    assert _parse(top[0][2]) == [(2, 0, 3), (4, 0, 4), (5, 0, 5)]       # PartitionId{stage_id=2, partition_id=4, task_id=5}
+    node = _parse(top[1][2])
+    assert node[0][0] == 8                                               # PhysicalPlanNode.filter
+    flt = _parse(node[0][2])
+    assert [f for f, _, _ in flt] == [1, 2]
+    ffi = _parse(_parse(flt[0][2])[0][2])
+    assert ffi[2] == (3, 2, b"rid")
+    fields = [_parse(x[2]) for x in _parse(ffi[1][2])]
+    assert [f[0][2] for f in fields] == [b"a", b"s", b"d"]
+    assert _parse(fields[2][1][2])[0][0] == 24                           # ArrowType.DECIMAL
+    # literal = Arrow IPC stream (schema + 1-row batch)
+    expr = _parse(flt[1][2])
+    assert expr[0][0] == 4
+    lit = _parse(_parse(expr[0][2])[1][2])
+    ipc = _parse(lit[0][2])[0][2]
+    assert pa.ipc.open_stream(ipc).read_all().column(0).to_pylist() == [5]
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    t = pa.table({"a": pa.array([1, 2, 3], type=pa.int64())})
+    with pytest.raises(runtime.AuronError):
+        runtime.run_task(P.task_definition(P.ffi_reader(t.schema, "t")), {"t": t.to_batches()})
+    with pytest.raises(runtime.AuronError):
+        runtime.k_partition_ids(t.to_batches()[0], [0], 8)
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "auron_b200")):
+        for f in files:
+            if f.endswith((".py", ".cc", ".cu", ".h", ".cuh")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in src and "auron_oracle" not in src, f
