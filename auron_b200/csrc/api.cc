@@ -135,6 +135,19 @@ void auron_b200_drop_device_resource(const char* resource_id) {
     } catch (...) {
     }
 }
+int auron_b200_put_device_file(const char* path, const uint8_t* bytes, size_t len, int device) {
+    API_GUARD_BEGIN
+    CUDA_OK(cudaSetDevice(device));
+    put_device_file(path, bytes, len, device);
+    return 0;
+    API_GUARD_END(-1)
+}
+void auron_b200_drop_device_file(const char* path) {
+    try {
+        drop_device_file(path);
+    } catch (...) {
+    }
+}
 
 // ---- kernel-level entry points
 static int one_column_out(Ctx& ctx, Buf data, int64_t n, const DType& t, const char* name, struct ArrowArray* out, struct ArrowSchema* out_schema) {

@@ -72,6 +72,10 @@ void put_device_resource(const std::string& id, std::vector<BatchPtr> batches, c
 bool get_device_resource(const std::string& id, std::vector<BatchPtr>* batches, Schema* schema);
 void drop_device_resource(const std::string& id);
 
+// Parquet files whose bytes are resident in HBM (scan decodes page payloads in place)
+void put_device_file(const std::string& path, const uint8_t* bytes, size_t len, int device);
+void drop_device_file(const std::string& path);
+
 // planner: TaskDefinition bytes -> Task (operator tree)
 std::unique_ptr<Task> create_task(const uint8_t* task_def, size_t len, const auron_callbacks* cb, int device);
 

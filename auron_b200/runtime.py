@@ -62,6 +62,9 @@ def lib():
         L.auron_b200_put_device_batch.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_int]
         L.auron_b200_drop_device_resource.argtypes = [C.c_char_p]
         L.auron_b200_drop_device_resource.restype = None
+        L.auron_b200_put_device_file.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int]
+        L.auron_b200_drop_device_file.argtypes = [C.c_char_p]
+        L.auron_b200_drop_device_file.restype = None
         L.auron_b200_k_hash.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
         L.auron_b200_k_partition_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int]
         L.auron_b200_kernel_launches.restype = C.c_int64
@@ -74,6 +77,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "auron_b200_call_native", "auron_b200_schema", "auron_b200_next_batch", "auron_b200_finalize_native", "auron_b200_on_exit",
     "auron_b200_last_error", "auron_b200_metrics", "auron_b200_put_device_batch", "auron_b200_drop_device_resource", "auron_b200_k_hash",
+    "auron_b200_put_device_file", "auron_b200_drop_device_file",
     "auron_b200_k_partition_ids", "auron_b200_kernel_launches", "auron_b200_time_kernel",
 ]
 
@@ -206,6 +210,18 @@ def put_device_batch(resource_id: str, batch: pa.RecordBatch, device: int = 0):
 
 def drop_device_resource(resource_id: str):
     lib().auron_b200_drop_device_resource(resource_id.encode())
+
+
+def put_device_file(path: str, data, device: int = 0):
+    """Make a Parquet file image resident in HBM under `path` (data: any bytes-like object)."""
+    import numpy as np
+    arr = np.frombuffer(data, dtype=np.uint8)
+    if lib().auron_b200_put_device_file(path.encode(), arr.ctypes.data, arr.nbytes, device) != 0:
+        raise AuronError(_err())
+
+
+def drop_device_file(path: str):
+    lib().auron_b200_drop_device_file(path.encode())
 
 
 def _kernel_one_column(fn, batch: pa.RecordBatch, cols: list[int], *mid_args, device: int = 0) -> pa.Array:

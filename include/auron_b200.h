@@ -73,6 +73,10 @@ int auron_b200_metrics(auron_task* task, auron_metric_fn fn, void* user);
  * host transfer.  The batch is NOT released by the call. */
 int auron_b200_put_device_batch(const char* resource_id, const struct ArrowArray* batch, const struct ArrowSchema* schema, int device);
 void auron_b200_drop_device_resource(const char* resource_id);
+/* Same idea for Parquet: copies a whole file image to HBM under `path`; a ParquetScanExec whose
+ * PartitionedFile.path equals `path` then decodes page payloads in place (no host transfer, no IO). */
+int auron_b200_put_device_file(const char* path, const uint8_t* bytes, size_t len, int device);
+void auron_b200_drop_device_file(const char* path);
 
 /* ---- kernel-level entry points (one per device algorithm; used by tests, ncu captures, bench) ----
  * Inputs/outputs are host Arrow struct arrays; columns named by index. */

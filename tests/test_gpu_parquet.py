@@ -1,0 +1,132 @@
+"""ParquetScanExec parity (row P1): the device decode of RLE / bit-packed hybrid levels and dictionary indices,
+PLAIN values and byte arrays must reproduce what Arrow C++'s reader (the oracle for the third-party `parquet`
+crate) returns for the same files."""
+import decimal
+import os
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.compute as pc
+import pyarrow.parquet as pq
+import pytest
+
+import oracle
+from auron_b200 import proto as P
+from auron_b200 import runtime
+from helpers import assert_same_rows, run
+
+pytestmark = pytest.mark.gpu
+
+
+def _table(n, seed, nulls=0.04):
+    rng = np.random.default_rng(seed)
+
+    def m():
+        return rng.random(n) < nulls if nulls else None
+
+    words = ["", "a", "store", "sales", "天地玄黄", "x" * 40, "b200"]
+    return pa.table({
+        "sk": pa.array(rng.integers(1, 2000, n), type=pa.int32(), mask=m()),           # dictionary friendly
+        "big": pa.array(rng.integers(-2**62, 2**62, n), type=pa.int64(), mask=m()),     # high cardinality -> PLAIN fallback
+        "q": pa.array(rng.integers(1, 100, n), type=pa.int32()),                        # no nulls
+        "price": pa.array([None if x else decimal.Decimal(int(v)) / 100 for x, v in zip(rng.random(n) < nulls, rng.integers(0, 99999, n))],
+                          type=pa.decimal128(7, 2)),
+        "f": pa.array(rng.standard_normal(n).astype(np.float32), mask=m()),
+        "d": pa.array(rng.standard_normal(n), mask=m()),
+        "flag": pa.array(rng.random(n) < 0.3, mask=m()),
+        "s": pa.array([words[int(i)] for i in rng.integers(0, len(words), n)], mask=m()),
+        "u": pa.array([f"unique-{i}-{int(x)}" for i, x in enumerate(rng.integers(0, 10**9, n))], mask=m()),  # PLAIN strings
+        "dt": pa.array(rng.integers(10000, 20000, n).astype(np.int32), type=pa.date32(), mask=m()),
+    })
+
+
+def _scan(path, schema, proj=None):
+    plan = P.parquet_scan(schema, [(path, os.path.getsize(path))], proj if proj is not None else list(range(len(schema))))
+    return run(plan, {})
+
+
+@pytest.mark.parametrize("compression", ["NONE", "SNAPPY", "ZSTD"])
+@pytest.mark.parametrize("version,dict_", [("1.0", True), ("2.0", True), ("1.0", False)])
+def test_scan_matches_arrow_reader(tmp_path, compression, version, dict_):
+    t = _table(50_000, seed=7)
+    path = str(tmp_path / "t.parquet")
+    pq.write_table(t, path, compression=compression, use_dictionary=dict_, data_page_version=version, row_group_size=17_001, data_page_size=8 * 1024,
+                   store_decimal_as_integer=True)
+    got = _scan(path, t.schema)
+    exp = pq.read_table(path)
+    assert got.num_rows == exp.num_rows
+    for name in t.column_names:
+        assert got[name].to_pylist() == exp[name].to_pylist(), name       # scans preserve file order
+
+
+def test_scan_flba_decimal_required_columns_and_projection(tmp_path):
+    t = _table(20_000, seed=9, nulls=0)
+    path = str(tmp_path / "r.parquet")
+    # default pyarrow: decimal as FIXED_LEN_BYTE_ARRAY; non-nullable schema -> REQUIRED columns (max_def = 0)
+    schema = pa.schema([pa.field(f.name, f.type, nullable=False) for f in t.schema])
+    pq.write_table(t.cast(schema), path, compression="NONE", row_group_size=6_000)
+    got = _scan(path, t.schema, proj=[3, 0, 7])
+    exp = pq.read_table(path, columns=["price", "sk", "s"])
+    assert got.schema.names == ["price", "sk", "s"]
+    for name in got.schema.names:
+        assert got[name].to_pylist() == exp[name].to_pylist(), name
+
+
+def test_scan_schema_adaptation(tmp_path):
+    # scan/mod.rs:56-160: case-insensitive match, missing column -> NULL, INT32 -> int64 / decimal128 widening
+    t = pa.table({"A": pa.array([1, None, 3], type=pa.int32()), "p": pa.array([150, 275, None], type=pa.int32())})
+    path = str(tmp_path / "a.parquet")
+    pq.write_table(t, path)
+    want = pa.schema([("a", pa.int64()), ("p", pa.decimal128(7, 2)), ("missing", pa.string())])
+    got = _scan(path, want)
+    assert got["a"].to_pylist() == [1, None, 3]
+    assert got["p"].to_pylist() == [decimal.Decimal("1.50"), decimal.Decimal("2.75"), None]
+    assert got["missing"].to_pylist() == [None, None, None]
+
+
+def test_scan_file_ranges_partition_row_groups(tmp_path):
+    t = _table(30_000, seed=11).select(["sk", "q"])
+    path = str(tmp_path / "g.parquet")
+    pq.write_table(t, path, row_group_size=5_000)
+    size = os.path.getsize(path)
+    md = pq.ParquetFile(path).metadata
+    starts = [md.row_group(i).column(0).dictionary_page_offset or md.row_group(i).column(0).data_page_offset for i in range(md.num_row_groups)]
+    mid = starts[3]
+    a = run(P.parquet_scan(t.schema, [(path, size)], [0, 1], ranges=[(0, mid)]), {})
+    b = run(P.parquet_scan(t.schema, [(path, size)], [0, 1], ranges=[(mid, size)]), {})
+    assert a.num_rows == 15_000 and b.num_rows == 15_000
+    assert pa.concat_tables([a, b])["sk"].to_pylist() == t["sk"].to_pylist()
+
+
+def test_scan_filter_aggregate_config2_small(tmp_path):
+    # BASELINE config 2 at test size: ParquetScan -> Filter -> HashAggregate(GROUP BY int64, SUM/COUNT), host file and HBM-resident file
+    rng = np.random.default_rng(13)
+    n = 400_000
+    t = pa.table({"ss_item_sk": pa.array(rng.integers(1, 20_000, n), type=pa.int32()),
+                  "ss_quantity": pa.array(rng.integers(1, 101, n), type=pa.int32(), mask=rng.random(n) < 0.03),
+                  "ss_sold_date_sk": pa.array(rng.integers(2450816, 2452642, n), type=pa.int32(), mask=rng.random(n) < 0.04)})
+    path = str(tmp_path / "store_sales.parquet")
+    pq.write_table(t, path, compression="NONE", row_group_size=150_000, data_page_size=64 * 1024)
+
+    def plan(p):
+        scan = P.parquet_scan(t.schema, [(p, os.path.getsize(path))], [0, 1, 2])
+        flt = P.filter_(scan, [P.binary("GtEq", P.col("ss_sold_date_sk"), P.lit(2451000, pa.int32())),
+                               P.binary("Lt", P.col("ss_sold_date_sk"), P.lit(2452000, pa.int32()))])
+        return P.agg(flt, [P.try_cast(P.col("ss_item_sk"), pa.int64())], ["k"],
+                     [P.agg_expr("SUM", [P.col("ss_quantity")], pa.int64()), P.agg_expr("COUNT", [P.col("ss_quantity")], pa.int64())],
+                     ["s", "c"], ["PARTIAL", "PARTIAL"])
+
+    d = t["ss_sold_date_sk"].combine_chunks()
+    pred = np.asarray(pc.and_kleene(pc.greater_equal(d, 2451000), pc.less(d, 2452000)).fill_null(False))
+    exp = oracle.agg_sum_count_i64(t["ss_item_sk"].combine_chunks().cast(pa.int64()), t["ss_quantity"].combine_chunks().cast(pa.int64()), pred)
+    got = run(plan(path), {})
+    assert_same_rows(got, exp)
+    # same query with the file image resident in HBM
+    with open(path, "rb") as f:
+        data = f.read()
+    runtime.put_device_file("hbm://store_sales", data)
+    try:
+        got2 = run(plan("hbm://store_sales"), {})
+    finally:
+        runtime.drop_device_file("hbm://store_sales")
+    assert_same_rows(got2, exp)
