@@ -2,6 +2,7 @@
 // point converts engine errors to a return code + thread-local message, the way the reference converts
 // Rust errors/panics into a Java exception and a false/0 return (auron/src/lib.rs:30-82, rt.rs:205-236).
 #include <atomic>
+#include <chrono>
 #include <cstring>
 
 #include "../../include/auron_b200.h"
@@ -12,6 +13,7 @@ using namespace auron;
 struct auron_task {
     std::unique_ptr<Task> task;
     bool finished = false;
+    int64_t compute_ns = 0, export_ns = 0;   // host wall time inside next_batch: operator tree vs D2H export
 };
 
 static thread_local std::string g_last_error;
@@ -65,16 +67,20 @@ int auron_b200_next_batch(auron_task* task, struct ArrowArray* out) {
     CUDA_OK(cudaSetDevice(t.ctx.device));
     int64_t before = t.ctx.kernel_launches;
     BatchPtr b;
+    auto t0 = std::chrono::steady_clock::now();
     // WrappedSender::send drops empty batches (execution_context.rs:715-738)
     do {
         b = t.root->next(t);
     } while (b && b->num_rows == 0);
+    auto t1 = std::chrono::steady_clock::now();
+    task->compute_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
     g_launches += t.ctx.kernel_launches - before;
     if (!b) {
         task->finished = true;
         return 0;
     }
     export_batch(t.ctx, *b, t.root->out_schema, out);
+    task->export_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t1).count();
     return 1;
     API_GUARD_END(-1)
 }
@@ -103,6 +109,14 @@ int auron_b200_metrics(auron_task* task, auron_metric_fn fn, void* user) {
     API_GUARD_BEGIN
     AURON_CHECK(task && task->task && task->task->root, "null task");
     walk_metrics(*task->task->root, 0, fn, user);
+    // device-time totals of the named launch sites (AURON_PROFILE=1), reported under a pseudo operator
+    for (auto& k : task->task->ctx.prof_summary()) {
+        fn(user, -1, "__kernels__", (k.name + ".device_us").c_str(), (int64_t)(k.ms * 1000.0));
+        fn(user, -1, "__kernels__", (k.name + ".launches").c_str(), k.launches);
+    }
+    fn(user, -1, "__kernels__", "total_launches", task->task->ctx.kernel_launches);
+    fn(user, -1, "__task__", "compute_ns", task->compute_ns);
+    fn(user, -1, "__task__", "export_ns", task->export_ns);
     return 0;
     API_GUARD_END(-1)
 }

@@ -117,12 +117,47 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     int64_t batch_size = 10000;             // auron.batchSize (datafusion-ext-commons/src/lib.rs:72-75)
-    int64_t gpu_chunk_rows = 16 << 20;      // device-side accumulation target (SURVEY hard part 2)
+    int64_t gpu_chunk_rows = 64 << 20;      // device-side accumulation target (SURVEY hard part 2); AURON_GPU_CHUNK_ROWS overrides
     int64_t kernel_launches = 0;            // number of our kernels launched on this ctx
     explicit Ctx(int dev = 0);
     ~Ctx();
     Ctx(const Ctx&) = delete;
     void sync() { CUDA_OK(cudaStreamSynchronize(stream)); }
+
+    // Optional per-kernel device timing (AURON_PROFILE=1): CUDA events recorded on this stream around named
+    // launch sites; bench.py reads the totals through auron_b200_metrics ("__kernels__" pseudo operator).
+    struct ProfEntry {
+        const char* name;
+        cudaEvent_t e0, e1;
+    };
+    bool profile = false;
+    std::vector<ProfEntry> prof;
+    struct ProfTotal {
+        std::string name;
+        double ms = 0;
+        int64_t launches = 0;
+    };
+    std::vector<ProfTotal> prof_summary();   // synchronises; drains the event list
+};
+
+struct ProfScope {
+    Ctx& ctx;
+    bool on;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const char* name;
+    ProfScope(Ctx& c, const char* n) : ctx(c), on(c.profile), name(n) {
+        if (on) {
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+            cudaEventRecord(e0, ctx.stream);
+        }
+    }
+    ~ProfScope() {
+        if (on) {
+            cudaEventRecord(e1, ctx.stream);
+            ctx.prof.push_back({name, e0, e1});
+        }
+    }
 };
 
 struct DevMem {

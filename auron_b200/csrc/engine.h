@@ -2,6 +2,7 @@
 // surface used by datafusion-ext-plans), the task runtime (auron/src/rt.rs NativeExecutionRuntime) and
 // the planner (auron-planner/src/planner.rs PhysicalPlanner::create_plan).
 #pragma once
+#include <chrono>
 #include <functional>
 #include <map>
 #include <memory>
@@ -28,6 +29,15 @@ struct MetricSet {
             }
         values.emplace_back(name, v);
     }
+};
+
+// inclusive wall-clock timer feeding a metric (the reference's elapsed_compute / *_time metrics, execution_context.rs:136-144)
+struct OpTimer {
+    MetricSet& m;
+    const char* name;
+    std::chrono::steady_clock::time_point t0;
+    OpTimer(MetricSet& ms, const char* n) : m(ms), name(n), t0(std::chrono::steady_clock::now()) {}
+    ~OpTimer() { m.add(name, std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count()); }
 };
 
 // A batch plus an optional pending row selection (a filter whose gather has not been materialised)

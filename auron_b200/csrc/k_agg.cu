@@ -500,7 +500,7 @@ static void emit_accs(Ctx& ctx, const std::vector<AccSpec>& specs, const AccArgs
 }
 
 GroupedResult hash_aggregate(Ctx& ctx, const std::vector<ColumnPtr>& keys, const std::vector<AccSpec>& accs, const int32_t* sel,
-                             int64_t n_rows) {
+                             int64_t n_rows, const DType* fast_key_out) {
     AURON_CHECK(!keys.empty(), "hash_aggregate needs at least one key (use global_aggregate)");
     AURON_CHECK(n_rows < (int64_t)INT32_MAX, "chunk too large");
     GroupedResult res;
@@ -519,6 +519,7 @@ GroupedResult hash_aggregate(Ctx& ctx, const std::vector<ColumnPtr>& keys, const
             fill_u64(ctx, table->ptr, cap, EMPTY_KEY);
             FastKey k{keys[0]->data->ptr, keys[0]->vbits(), (int32_t)keys[0]->type.id};
             if (n_rows) {
+                ProfScope ps(ctx, "agg_update");
                 agg_fast_kernel<<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(k, P<unsigned long long>(table), cap, args, sel, n_rows, P<int32_t>(flags));
                 LAUNCH_CHECK(ctx);
             }
@@ -526,6 +527,7 @@ GroupedResult hash_aggregate(Ctx& ctx, const std::vector<ColumnPtr>& keys, const
             table = dalloc_fill(ctx, (size_t)cap * 4, 0xff);
             RowKeys rk = make_row_keys(keys);
             if (n_rows) {
+                ProfScope ps(ctx, "agg_update");
                 agg_general_kernel<<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(rk, P<int32_t>(table), cap, args, sel, n_rows, P<int32_t>(flags));
                 LAUNCH_CHECK(ctx);
             }
@@ -551,9 +553,14 @@ GroupedResult hash_aggregate(Ctx& ctx, const std::vector<ColumnPtr>& keys, const
         res.keys->num_rows = g;
         unsigned gblocks = (unsigned)((g + 255) / 256);
         if (fast) {
-            auto kc = make_column(ctx, keys[0]->type, g, keys[0]->may_have_nulls());
+            DType kt = keys[0]->type;
+            if (fast_key_out) {
+                AURON_CHECK(kt.is_integer() && fast_key_out->is_integer() && kt.width() <= fast_key_out->width(), "bad widened key type");
+                kt = *fast_key_out;
+            }
+            auto kc = make_column(ctx, kt, g, keys[0]->may_have_nulls());
             if (g) {
-                emit_fast_keys_kernel<<<gblocks, 256, 0, ctx.stream>>>(P<unsigned long long>(table), cap, P<int32_t>(slot_ids), g, keys[0]->type.id,
+                emit_fast_keys_kernel<<<gblocks, 256, 0, ctx.stream>>>(P<unsigned long long>(table), cap, P<int32_t>(slot_ids), g, kt.id,
                                                                        kc->data->ptr, P<uint32_t>(kc->validity));
                 LAUNCH_CHECK(ctx);
             }

@@ -36,6 +36,7 @@ Ctx::Ctx(int dev) : device(dev) {
     cudaDeviceProp prop;
     CUDA_OK(cudaGetDeviceProperties(&prop, dev));
     sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("AURON_PROFILE")) profile = atoi(e) != 0;
     if (const char* e = getenv("AURON_GPU_CHUNK_ROWS")) {   // device-side accumulation target (tests shrink it to force merges)
         long long v = atoll(e);
         if (v > 0) gpu_chunk_rows = v;
@@ -50,7 +51,32 @@ Ctx::Ctx(int dev) : device(dev) {
         }
     });
 }
+std::vector<Ctx::ProfTotal> Ctx::prof_summary() {
+    std::vector<ProfTotal> out;
+    if (prof.empty()) return out;
+    cudaStreamSynchronize(stream);
+    for (auto& e : prof) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e.e0, e.e1);
+        cudaEventDestroy(e.e0);
+        cudaEventDestroy(e.e1);
+        bool found = false;
+        for (auto& t : out)
+            if (t.name == e.name) {
+                t.ms += ms;
+                t.launches++;
+                found = true;
+            }
+        if (!found) out.push_back({e.name, ms, 1});
+    }
+    prof.clear();
+    return out;
+}
 Ctx::~Ctx() {
+    for (auto& e : prof) {
+        cudaEventDestroy(e.e0);
+        cudaEventDestroy(e.e1);
+    }
     if (stream) {
         cudaStreamSynchronize(stream);
         cudaStreamDestroy(stream);
@@ -282,6 +308,7 @@ Buf mask_to_indices(Ctx& ctx, const uint32_t* mask_words, int64_t n_rows, int64_
     }
     int64_t n_words = (n_rows + 31) / 32;
     int64_t nblocks = (n_words + 255) / 256;
+    ProfScope ps(ctx, "mask_to_indices");
     Buf counts = dalloc(ctx, (nblocks + 1) * 4);
     mask_popc_kernel<<<(unsigned)nblocks, 256, 0, ctx.stream>>>(mask_words, n_words, n_rows, P<int32_t>(counts));
     LAUNCH_CHECK(ctx);
@@ -434,6 +461,7 @@ struct alignas(16) u128_t {
 };
 
 ColumnPtr take(Ctx& ctx, const Column& in, const int32_t* idx, int64_t n_out, bool idx_may_be_negative) {
+    ProfScope ps(ctx, "take");
     auto out = std::make_shared<Column>();
     out->type = in.type;
     out->len = n_out;

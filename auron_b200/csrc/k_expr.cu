@@ -998,8 +998,154 @@ __global__ void __launch_bounds__(VM_THREADS) vm_kernel(VmParams p) {
 #undef SETV
 }
 
+// ------------------------------------------------------------------------------------------ conjunctive compare fast path
+// The overwhelmingly common filter shape (TPC-DS: BETWEEN, =, <, IS NOT NULL on fixed-width columns) is a conjunction of
+// `column <op> literal` terms.  Those skip the interpreter: every thread loads each referenced column once into
+// registers, evaluates the terms and the warp ballots the keep-bits into the selection bitmap -- one coalesced pass
+// over the referenced columns, nothing else.  Semantics are those of the VM ops (NULL => row dropped).
+constexpr int SP_MAX_TERMS = 8, SP_MAX_COLS = 4;
+struct SimpleTerm {
+    int32_t col;     // slot into SimplePredArgs::data
+    int32_t op;      // OP_EQ..OP_GE, OP_ISNULL, OP_ISNOTNULL
+    int64_t c_lo, c_hi;
+};
+struct SimplePredArgs {
+    const void* data[SP_MAX_COLS];
+    const uint8_t* valid[SP_MAX_COLS];
+    int32_t vt[SP_MAX_COLS];
+    SimpleTerm t[SP_MAX_TERMS];
+    int32_t n_terms, n_cols;
+};
+__global__ void __launch_bounds__(256) simple_predicate_kernel(SimplePredArgs a, int64_t n, uint32_t* __restrict__ out) {
+    int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t base = (int64_t)blockIdx.x * 256; base < n; base += stride) {
+        int64_t i = base + threadIdx.x;
+        bool active = i < n;
+        uint64_t lo[SP_MAX_COLS];
+        int64_t hi[SP_MAX_COLS];
+        bool ok[SP_MAX_COLS];
+#pragma unroll
+        for (int c = 0; c < SP_MAX_COLS; c++) {
+            lo[c] = 0;
+            hi[c] = 0;
+            ok[c] = false;
+            if (c < a.n_cols && active) {
+                ok[c] = valid_at(a.valid[c], i);
+                const void* d = a.data[c];
+                switch (a.vt[c]) {
+                    case VT_BOOL: lo[c] = bit_get((const uint8_t*)d, i); break;
+                    case VT_I8: lo[c] = (uint64_t)(int64_t)((const int8_t*)d)[i]; break;
+                    case VT_I16: lo[c] = (uint64_t)(int64_t)((const int16_t*)d)[i]; break;
+                    case VT_I32: lo[c] = (uint64_t)(int64_t)((const int32_t*)d)[i]; break;
+                    case VT_F32: lo[c] = (uint64_t)(int64_t)f32_total(((const float*)d)[i]); break;
+                    case VT_F64: lo[c] = (uint64_t)f64_total(((const double*)d)[i]); break;
+                    case VT_DEC: {
+                        ulonglong2 q = ((const ulonglong2*)d)[i];
+                        lo[c] = q.x;
+                        hi[c] = (int64_t)q.y;
+                        break;
+                    }
+                    default: lo[c] = ((const uint64_t*)d)[i]; break;
+                }
+            }
+        }
+        bool keep = active;
+        for (int k = 0; k < a.n_terms; k++) {
+            const SimpleTerm t = a.t[k];
+            uint64_t x = 0;
+            int64_t xh = 0;
+            bool v = false;
+            int vt = 0;
+#pragma unroll
+            for (int c = 0; c < SP_MAX_COLS; c++)
+                if (c == t.col) {
+                    x = lo[c];
+                    xh = hi[c];
+                    v = ok[c];
+                    vt = a.vt[c];
+                }
+            if (t.op == OP_ISNULL) { keep = keep && !v; continue; }
+            if (t.op == OP_ISNOTNULL) { keep = keep && v; continue; }
+            int cmp;
+            if (vt == VT_DEC) cmp = i128_cmp({x, xh}, {(uint64_t)t.c_lo, t.c_hi});
+            else cmp = (int64_t)x < t.c_lo ? -1 : ((int64_t)x > t.c_lo ? 1 : 0);
+            bool r = false;
+            switch (t.op) {
+                case OP_EQ: r = cmp == 0; break;
+                case OP_NE: r = cmp != 0; break;
+                case OP_LT: r = cmp < 0; break;
+                case OP_LE: r = cmp <= 0; break;
+                case OP_GT: r = cmp > 0; break;
+                case OP_GE: r = cmp >= 0; break;
+            }
+            keep = keep && v && r;
+        }
+        uint32_t wbits = __ballot_sync(FULL_MASK, keep);
+        if ((threadIdx.x & 31) == 0 && active) out[i >> 5] = wbits;
+    }
+}
+
+// When every term is an ordering comparison the conjunction folds (on the host) into one closed interval per column in the
+// order-preserving int64 domain, and the kernel is a handful of instructions per row: 4 independent coalesced loads per
+// thread (128 rows per warp iteration), one validity word per 32 rows, two compares, a ballot.
+struct IntervalArgs {
+    const void* data[SP_MAX_COLS];
+    const uint32_t* valid[SP_MAX_COLS];
+    int32_t vt[SP_MAX_COLS];
+    int64_t lo[SP_MAX_COLS], hi[SP_MAX_COLS];
+    int32_t n_cols;
+};
+__device__ __forceinline__ int64_t ordered_load(const void* d, int vt, int64_t i) {
+    switch (vt) {
+        case VT_BOOL: return bit_get((const uint8_t*)d, i);
+        case VT_I8: return ((const int8_t*)d)[i];
+        case VT_I16: return ((const int16_t*)d)[i];
+        case VT_I32: return ((const int32_t*)d)[i];
+        case VT_F32: return f32_total(((const float*)d)[i]);
+        case VT_F64: return f64_total(((const double*)d)[i]);
+        default: return ((const int64_t*)d)[i];
+    }
+}
+template <int NCOLS>
+__global__ void __launch_bounds__(256) interval_predicate_kernel(IntervalArgs a, int64_t n, uint32_t* __restrict__ out) {
+    const unsigned lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * 256) >> 5;
+    for (int64_t base = warp * 128; base < n; base += nwarps * 128) {
+        bool keep[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) keep[k] = base + 32 * k + lane < n;
+#pragma unroll
+        for (int c = 0; c < NCOLS; c++) {
+            int64_t x[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int64_t row = base + 32 * k + lane;
+                x[k] = row < n ? ordered_load(a.data[c], a.vt[c], row) : 0;
+            }
+            const int64_t lo = a.lo[c], hi = a.hi[c];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                bool v = true;
+                if (a.valid[c] && base + 32 * k < n) v = (a.valid[c][(base >> 5) + k] >> lane) & 1u;
+                keep[k] = keep[k] && v && x[k] >= lo && x[k] <= hi;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t w = __ballot_sync(FULL_MASK, keep[k]);
+            if (lane == 0 && base + 32 * k < n) out[(base >> 5) + k] = w;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ compiler (host)
 struct VmProgramImpl {
+    // interval form of the fast path (one closed interval per column); empty => not foldable
+    std::vector<int64_t> iv_lo, iv_hi;
+    // conjunctive-compare fast path (empty => use the interpreter)
+    std::vector<SimpleTerm> simple_terms;
+    std::vector<int> simple_cols;   // schema column per slot
+    std::vector<int> simple_vt;
     std::vector<Instr> code;
     std::vector<ConstEntry> consts;
     std::string pool;
@@ -1530,10 +1676,102 @@ VmProgram compile_projection(const std::vector<ExprPtr>& exprs, const Schema& in
     }
     return p;
 }
+static int64_t host_f64_total(double d) {
+    int64_t b;
+    memcpy(&b, &d, 8);
+    return b < 0 ? (b ^ 0x7fffffffffffffffll) : b;
+}
+static int64_t host_f32_total(float f) {
+    int32_t b;
+    memcpy(&b, &f, 4);
+    return (int64_t)(b < 0 ? (b ^ 0x7fffffff) : b);
+}
+// conjunction of `column <cmp> literal` / IS [NOT] NULL terms over fixed-width columns?
+static bool try_compile_simple(const std::vector<ExprPtr>& conjuncts, const Schema& input, VmProgramImpl& im) {
+    std::vector<SimpleTerm> terms;
+    std::vector<int> cols, vts;
+    auto slot_of = [&](int col, int vt) {
+        for (size_t i = 0; i < cols.size(); i++)
+            if (cols[i] == col) return (int)i;
+        cols.push_back(col);
+        vts.push_back(vt);
+        return (int)cols.size() - 1;
+    };
+    for (auto& e : conjuncts) {
+        SimpleTerm t{};
+        int idx;
+        if ((e->kind == E_IS_NULL || e->kind == E_IS_NOT_NULL) && is_plain_column(*e->children[0], input, &idx)) {
+            const DType& ct = input.fields[idx].type;
+            if (ct.is_varlen() || ct.id == T_NULL) return false;
+            t.col = slot_of(idx, vt_of(ct));
+            t.op = e->kind == E_IS_NULL ? OP_ISNULL : OP_ISNOTNULL;
+            terms.push_back(t);
+            continue;
+        }
+        if (e->kind != E_BINARY) return false;
+        int op = e->op == "Eq" ? OP_EQ : e->op == "NotEq" ? OP_NE : e->op == "Lt" ? OP_LT : e->op == "LtEq" ? OP_LE : e->op == "Gt" ? OP_GT : e->op == "GtEq" ? OP_GE : -1;
+        if (op < 0) return false;
+        const Expr* ce = e->children[0].get();
+        const Expr* le = e->children[1].get();
+        if (ce->kind == E_LITERAL && le->kind == E_COLUMN) {   // literal <op> column: mirror the operator
+            std::swap(ce, le);
+            op = op == OP_LT ? OP_GT : op == OP_LE ? OP_GE : op == OP_GT ? OP_LT : op == OP_GE ? OP_LE : op;
+        }
+        if (ce->kind != E_COLUMN || le->kind != E_LITERAL || le->lit.is_null) return false;
+        idx = resolve_col(*ce, input);
+        const DType& ct = input.fields[idx].type;
+        const DType& lt = le->lit.type;
+        if (ct.is_varlen() || ct.id == T_NULL) return false;
+        int vt = vt_of(ct);
+        if (ct.id == T_DECIMAL128) {
+            if (!(lt == ct)) return false;
+            t.c_lo = (int64_t)le->lit.lo;
+            t.c_hi = le->lit.hi;
+        } else if (ct.is_float()) {
+            if (!(lt == ct)) return false;
+            t.c_lo = ct.id == T_FLOAT32 ? host_f32_total((float)le->lit.d) : host_f64_total(le->lit.d);
+        } else {
+            if (vt_of(lt) > VT_I64 || lt.is_float() || lt.id == T_DECIMAL128 || (lt.id == T_BOOL) != (ct.id == T_BOOL)) return false;
+            t.c_lo = le->lit.i;
+        }
+        t.col = slot_of(idx, vt);
+        t.op = op;
+        terms.push_back(t);
+    }
+    if (terms.empty() || terms.size() > (size_t)SP_MAX_TERMS || cols.size() > (size_t)SP_MAX_COLS) return false;
+    im.simple_terms = terms;
+    im.simple_cols = cols;
+    im.simple_vt = vts;
+    // fold into one closed interval per column when every term is an ordering comparison on a non-decimal column
+    std::vector<int64_t> lo(cols.size(), INT64_MIN), hi(cols.size(), INT64_MAX);
+    bool foldable = true;
+    for (auto& t : terms) {
+        if (vts[t.col] == VT_DEC || t.op == OP_NE || t.op == OP_ISNULL) {
+            foldable = false;
+            break;
+        }
+        int64_t c = t.c_lo;
+        switch (t.op) {
+            case OP_EQ: lo[t.col] = std::max(lo[t.col], c); hi[t.col] = std::min(hi[t.col], c); break;
+            case OP_LT: if (c == INT64_MIN) { lo[t.col] = 1; hi[t.col] = 0; } else hi[t.col] = std::min(hi[t.col], c - 1); break;
+            case OP_LE: hi[t.col] = std::min(hi[t.col], c); break;
+            case OP_GT: if (c == INT64_MAX) { lo[t.col] = 1; hi[t.col] = 0; } else lo[t.col] = std::max(lo[t.col], c + 1); break;
+            case OP_GE: lo[t.col] = std::max(lo[t.col], c); break;
+            default: break;   // IS NOT NULL: validity is required by every interval anyway
+        }
+    }
+    if (foldable) {
+        im.iv_lo = lo;
+        im.iv_hi = hi;
+    }
+    return true;
+}
+
 VmProgram compile_predicate(const std::vector<ExprPtr>& conjuncts, const Schema& input) {
     VmProgram p;
     p.impl = std::make_shared<VmProgramImpl>();
     p.is_predicate = true;
+    if (!getenv("AURON_DISABLE_SIMPLE_PREDICATE") && try_compile_simple(conjuncts, input, *p.impl)) return p;
     Compiler c(input, *p.impl);
     AURON_CHECK(!conjuncts.empty(), "empty predicate");
     Compiler::Val acc = c.gen(*conjuncts[0]);
@@ -1577,6 +1815,7 @@ static void launch_vm(Ctx& ctx, const VmProgramImpl& im, const VmParams& p) {
     int64_t blocks = (p.n + VM_THREADS - 1) / VM_THREADS;
     int per_sm = im.need_hi ? 3 : 6;
     unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)ctx.sm_count * per_sm));
+    ProfScope ps(ctx, "expr_vm");
     if (im.need_hi) vm_kernel<true><<<grid, VM_THREADS, smem, ctx.stream>>>(p);
     else vm_kernel<false><<<grid, VM_THREADS, smem, ctx.stream>>>(p);
     LAUNCH_CHECK(ctx);
@@ -1653,6 +1892,49 @@ Buf eval_predicate(Ctx& ctx, const VmProgram& prog, const Batch& in, int64_t n_r
     VmProgramImpl& im = *prog.impl;
     Buf mask = dalloc(ctx, bitmap_alloc_bytes(n_rows));
     if (n_rows == 0) return mask;
+    if (!im.iv_lo.empty()) {
+        IntervalArgs a;
+        memset(&a, 0, sizeof(a));
+        a.n_cols = (int)im.simple_cols.size();
+        for (int c = 0; c < a.n_cols; c++) {
+            const Column& col = *in.cols[im.simple_cols[c]];
+            a.data[c] = col.data ? col.data->ptr : nullptr;
+            a.valid[c] = (const uint32_t*)col.vbits();
+            a.vt[c] = im.simple_vt[c];
+            a.lo[c] = im.iv_lo[c];
+            a.hi[c] = im.iv_hi[c];
+        }
+        int64_t warps = (n_rows + 127) / 128;
+        unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((warps + 7) / 8, (int64_t)ctx.sm_count * 8));
+        ProfScope ps(ctx, "simple_predicate");
+        switch (a.n_cols) {
+            case 1: interval_predicate_kernel<1><<<grid, 256, 0, ctx.stream>>>(a, n_rows, P<uint32_t>(mask)); break;
+            case 2: interval_predicate_kernel<2><<<grid, 256, 0, ctx.stream>>>(a, n_rows, P<uint32_t>(mask)); break;
+            case 3: interval_predicate_kernel<3><<<grid, 256, 0, ctx.stream>>>(a, n_rows, P<uint32_t>(mask)); break;
+            default: interval_predicate_kernel<4><<<grid, 256, 0, ctx.stream>>>(a, n_rows, P<uint32_t>(mask)); break;
+        }
+        LAUNCH_CHECK(ctx);
+        return mask;
+    }
+    if (!im.simple_terms.empty()) {
+        SimplePredArgs a;
+        memset(&a, 0, sizeof(a));
+        a.n_cols = (int)im.simple_cols.size();
+        a.n_terms = (int)im.simple_terms.size();
+        for (int c = 0; c < a.n_cols; c++) {
+            const Column& col = *in.cols[im.simple_cols[c]];
+            a.data[c] = col.data ? col.data->ptr : nullptr;
+            a.valid[c] = col.vbits();
+            a.vt[c] = im.simple_vt[c];
+        }
+        for (int k = 0; k < a.n_terms; k++) a.t[k] = im.simple_terms[k];
+        int64_t blocks = (n_rows + 255) / 256;
+        unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)ctx.sm_count * 16));
+        ProfScope ps(ctx, "simple_predicate");
+        simple_predicate_kernel<<<grid, 256, 0, ctx.stream>>>(a, n_rows, P<uint32_t>(mask));
+        LAUNCH_CHECK(ctx);
+        return mask;
+    }
     upload(ctx, im);
     VmParams p;
     bind_inputs(im, in, p);

@@ -120,6 +120,7 @@ Buf murmur3_partition_ids(Ctx& ctx, const std::vector<ColumnPtr>& cols, int64_t 
     HashArgs a = make_args(cols);
     Buf out = dalloc(ctx, (size_t)std::max<int64_t>(n, 1) * 4);
     if (n == 0) return out;
+    ProfScope ps(ctx, "murmur3_partition_ids");
     hash_rows_kernel<0, 1><<<grid_for(ctx, n), 256, 0, ctx.stream>>>(a, n, (uint64_t)(uint32_t)seed, num_parts, out->ptr);
     CUDA_OK(cudaGetLastError());
     launch_count(ctx);

@@ -167,9 +167,151 @@ __device__ __forceinline__ void store_zero(const PqColumnArgs& a, int64_t row) {
 }
 
 constexpr int PQ_WARPS = 4;
+constexpr int PQ_TILE = 1024;   // rows per decode tile (one warp)
 
-__global__ void __launch_bounds__(PQ_WARPS * 32) pq_decode_pages_kernel(PqColumnArgs a) {
-    int page_id = blockIdx.x * PQ_WARPS + (threadIdx.x >> 5);
+// checkpoint of a hybrid stream (offsets relative to the stream's first byte)
+struct HybridCk {
+    int32_t p_off, run_remaining, bp_base_off, bp_consumed;
+    uint32_t rle_value;
+    int32_t is_rle;
+};
+struct PqTile {
+    int32_t page, row0, n, pad;
+    int64_t v0;   // non-null values of the page before this tile
+    HybridCk def, idx;
+};
+__device__ __forceinline__ HybridCk hybrid_save(const Hybrid& h, const uint8_t* base) {
+    HybridCk c;
+    c.p_off = (int32_t)(h.p - base);
+    c.run_remaining = h.run_remaining;
+    c.bp_base_off = (int32_t)(h.bp_base - base);
+    c.bp_consumed = h.bp_consumed;
+    c.rle_value = h.rle_value;
+    c.is_rle = h.is_rle ? 1 : 0;
+    return c;
+}
+__device__ __forceinline__ void hybrid_restore(Hybrid& h, const HybridCk& c, const uint8_t* base, const uint8_t* end, int bw) {
+    h.p = base + c.p_off;
+    h.end = end;
+    h.bw = bw;
+    h.run_remaining = c.run_remaining;
+    h.is_rle = c.is_rle != 0;
+    h.rle_value = c.rle_value;
+    h.bp_base = base + c.bp_base_off;
+    h.bp_consumed = c.bp_consumed;
+}
+// advance a stream by n values without materialising them (header walk only)
+__device__ __forceinline__ void hybrid_skip(Hybrid& h, int n) {
+    while (n > 0) {
+        if (h.run_remaining == 0) h.next_run();
+        int t = min(n, h.run_remaining);
+        h.run_remaining -= t;
+        if (!h.is_rle) h.bp_consumed += t;
+        n -= t;
+    }
+}
+// number of ones among the next m values of a bit-width-1 stream (m <= 1024); warp-cooperative, advances the stream
+__device__ __forceinline__ int hybrid_count_ones(Hybrid& h, int m, unsigned lane) {
+    int cnt = 0;
+    while (m > 0) {
+        if (h.run_remaining == 0) h.next_run();
+        int t = min(m, h.run_remaining);
+        if (h.is_rle) cnt += (h.rle_value & 1) ? t : 0;
+        else {
+            int64_t s = (int64_t)h.bp_consumed + 32 * (int64_t)lane;   // this lane's first bit
+            int mine = min(32, t - 32 * (int)lane);
+            int c = 0;
+            if (mine > 0) {
+                const uint8_t* q = h.bp_base + (s >> 3);
+                uint64_t w = 0;
+#pragma unroll
+                for (int i = 0; i < 5; i++) w |= (uint64_t)q[i] << (8 * i);
+                uint32_t bits = (uint32_t)(w >> (s & 7));
+                if (mine < 32) bits &= (1u << mine) - 1u;
+                c = __popc(bits);
+            }
+#pragma unroll
+            for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(FULL_MASK, c, d);
+            cnt += c;
+            h.bp_consumed += t;
+        }
+        h.run_remaining -= t;
+        m -= t;
+    }
+    return cnt;
+}
+
+struct PqLaunch {
+    PqColumnArgs a;
+    const int32_t* tile_base;   // [n_pages + 1]
+    PqTile* tiles;
+    uint32_t* tile_valid;       // [n_tiles][32] tile-local validity words written by the scout (nullable columns)
+};
+
+// Definition levels of one tile -> 32 validity words (lane L returns word L, bit i of the tile = row 32L+i).
+// Writers emit very short level runs (a NULL every ~30 rows splits the stream into ~60 runs per 1024 rows), so a
+// warp-wide step per run wastes 31 lanes.  Instead lane 0 walks up to 32 run headers (the only serial part) and drops
+// a descriptor per run into shared memory; then every lane materialises one run into the tile bitmap in parallel.
+// `def` is only meaningful in lane 0 afterwards.
+__device__ __forceinline__ uint32_t extract_bits(const uint8_t* base, int64_t bitpos, int bw);
+struct DefRun {
+    int32_t dst, t;       // first tile-local row, row count
+    int32_t srcbit;       // bit offset from the stream base (bit-packed runs)
+    int32_t kind;         // 0 bit-packed, 1 RLE ones, 2 RLE zeros
+};
+__device__ __forceinline__ uint32_t def_tile_words(Hybrid& def, const uint8_t* def_base, int m, unsigned lane, uint32_t* bm /*[32] smem*/,
+                                                   DefRun* runs /*[32] smem*/) {
+    bm[lane] = 0;
+    int filled = 0;
+    __syncwarp();
+    while (filled < m) {
+        int nr = 0;
+        if (lane == 0) {
+            int f = filled;
+            while (nr < 32 && f < m) {
+                if (def.run_remaining == 0) def.next_run();
+                int t = min(m - f, def.run_remaining);
+                DefRun r;
+                r.dst = f;
+                r.t = t;
+                r.kind = def.is_rle ? ((def.rle_value & 1) ? 1 : 2) : 0;
+                r.srcbit = def.is_rle ? 0 : (int32_t)((def.bp_base - def_base) * 8 + def.bp_consumed);
+                runs[nr++] = r;
+                def.run_remaining -= t;
+                if (!def.is_rle) def.bp_consumed += t;
+                f += t;
+            }
+            filled = f;
+        }
+        nr = __shfl_sync(FULL_MASK, nr, 0);
+        filled = __shfl_sync(FULL_MASK, filled, 0);
+        __syncwarp();
+        if ((int)lane < nr) {
+            DefRun r = runs[lane];
+            if (r.kind != 2) {
+                int done = 0;
+                while (done < r.t) {   // at most 32 bits per step, aligned to the destination word
+                    int d = r.dst + done;
+                    int take = min(r.t - done, 32 - (d & 31));
+                    uint32_t bits = r.kind == 1 ? 0xffffffffu : extract_bits(def_base, (int64_t)r.srcbit + done, 32);
+                    if (take < 32) bits &= (1u << take) - 1u;
+                    if (bits) atomicOr(&bm[d >> 5], bits << (d & 31));
+                    done += take;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    return bm[lane];
+}
+
+// pass 1: one warp per page walks the run headers and checkpoints both streams every PQ_TILE rows
+__global__ void __launch_bounds__(PQ_WARPS * 32) pq_scout_kernel(PqLaunch L) {
+    __shared__ uint32_t s_bm[PQ_WARPS][32];
+    __shared__ DefRun s_runs[PQ_WARPS][32];
+    const PqColumnArgs& a = L.a;
+    const int wid = threadIdx.x >> 5;
+    int page_id = blockIdx.x * PQ_WARPS + wid;
     if (page_id >= a.n_pages) return;
     const unsigned lane = lane_id();
     const PqPage pg = a.pages[page_id];
@@ -177,19 +319,77 @@ __global__ void __launch_bounds__(PQ_WARPS * 32) pq_decode_pages_kernel(PqColumn
     const bool has_def = a.max_def > 0 && pg.def_len > 0;
     if (has_def) def.init(pg.def_ptr, pg.def_ptr + pg.def_len, 1);
     const bool dict = pg.encoding == 2 || pg.encoding == 8;
+    const bool bool_rle = a.phys_type == 0 && pg.encoding == 3;
+    const uint8_t* vals = pg.val_ptr;
+    const uint8_t* idx_base = vals;
+    if (dict) {
+        idx_base = vals + 1;
+        idx.init(idx_base, vals + pg.val_len, pg.val_len > 0 ? vals[0] : 0);
+    } else if (bool_rle) {
+        idx_base = vals + 4;
+        idx.init(idx_base, vals + pg.val_len, 1);
+    } else idx.init(vals, vals, 0);
+    const int rows = pg.num_values;
+    int64_t v0 = 0;
+    const uint8_t* pf_idx = idx_base;
+    int tile = L.tile_base[page_id];
+    for (int r = 0; r < rows; r += PQ_TILE, tile++) {
+        int m = min(PQ_TILE, rows - r);
+        if (lane == 0) {
+            PqTile t;
+            t.page = page_id;
+            t.row0 = r;
+            t.n = m;
+            t.pad = 0;
+            t.v0 = v0;
+            t.def = has_def ? hybrid_save(def, pg.def_ptr) : HybridCk{0, 0, 0, 0, 0, 1};
+            t.idx = (dict || bool_rle) ? hybrid_save(idx, idx_base) : HybridCk{0, 0, 0, 0, 0, 1};
+            L.tiles[tile] = t;
+        }
+        // the header walk is a pointer chase: pull the next 8 KB of both streams into L1 ahead of it (32 lines per shot)
+        if (dict || bool_rle) {
+            const uint8_t* send = vals + pg.val_len;
+            while (pf_idx < idx.p + 8192 && pf_idx < send) {
+                const uint8_t* q = pf_idx + 128 * lane;
+                if (q < send) asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+                pf_idx += 4096;
+            }
+        }
+        int nvalid = m;
+        if (has_def) {
+            uint32_t w = def_tile_words(def, pg.def_ptr, m, lane, s_bm[wid], s_runs[wid]);
+            L.tile_valid[(int64_t)tile * 32 + lane] = w;
+            int c = __popc(w);
+#pragma unroll
+            for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(FULL_MASK, c, d);
+            nvalid = c;
+        } else if (a.max_def > 0 && pg.all_null) nvalid = 0;
+        if (dict || bool_rle) hybrid_skip(idx, nvalid);
+        v0 += nvalid;
+    }
+}
+
+// pass 2: one warp per tile
+__global__ void __launch_bounds__(PQ_WARPS * 32) pq_decode_tiles_kernel(PqLaunch L, int n_tiles) {
+    const PqColumnArgs& a = L.a;
+    int tile_id = blockIdx.x * PQ_WARPS + (threadIdx.x >> 5);
+    if (tile_id >= n_tiles) return;
+    const unsigned lane = lane_id();
+    const PqTile tl = L.tiles[tile_id];
+    const PqPage pg = a.pages[tl.page];
+    Hybrid def, idx;
+    const bool has_def = a.max_def > 0 && pg.def_len > 0;
+    if (has_def) hybrid_restore(def, tl.def, pg.def_ptr, pg.def_ptr + pg.def_len, 1);
+    const bool dict = pg.encoding == 2 || pg.encoding == 8;
     const uint8_t* vals = pg.val_ptr;
     const bool bool_rle = a.phys_type == 0 && pg.encoding == 3;   // RLE booleans (data page v2 writers): u32 length + hybrid, bit width 1
-    if (dict) {
-        int bw = pg.val_len > 0 ? vals[0] : 0;
-        idx.init(vals + 1, vals + pg.val_len, bw);
-    } else if (bool_rle) {
-        idx.init(vals + 4, vals + pg.val_len, 1);
-    }
+    if (dict) hybrid_restore(idx, tl.idx, vals + 1, vals + pg.val_len, pg.val_len > 0 ? vals[0] : 0);
+    else if (bool_rle) hybrid_restore(idx, tl.idx, vals + 4, vals + pg.val_len, 1);
     const PqDict dd = dict ? a.dicts[pg.dict_id] : PqDict{nullptr, 0, 0};
     const int w = a.phys_width;
-    int done = 0;
-    int64_t value_base = 0;
-    const int rows = pg.num_values;
+    int done = tl.row0;
+    int64_t value_base = tl.v0;
+    const int rows = tl.row0 + tl.n;
     while (done < rows) {
         int64_t out_row = (int64_t)pg.row_start + done;
         int m = min(rows - done, 32 - (int)(out_row & 31));
@@ -243,10 +443,140 @@ __global__ void __launch_bounds__(PQ_WARPS * 32) pq_decode_pages_kernel(PqColumn
     }
 }
 
-void pq_decode_pages(Ctx& ctx, const PqColumnArgs& a) {
+// 64-bit window starting at an arbitrary bit position (two aligned 32-bit pairs + funnel shifts)
+__device__ __forceinline__ uint32_t extract_bits(const uint8_t* base, int64_t bitpos, int bw) {
+    const uint8_t* q = base + (bitpos >> 3);
+    uintptr_t a = (uintptr_t)q;
+    const uint32_t* wp = (const uint32_t*)(a & ~(uintptr_t)3);
+    unsigned sh = (unsigned)(a & 3) * 8 + (unsigned)(bitpos & 7);   // 0..31
+    uint32_t v = __funnelshift_r(wp[0], wp[1], sh);   // bits [sh, sh + 32) of the aligned 64-bit pair: enough for any bw <= 32
+    return bw == 32 ? v : (v & ((1u << bw) - 1u));
+}
+
+// pass 2 (fast path): one warp per tile, three phases --
+//   1. the tile's definition levels become 32 validity words (one per lane) straight from the hybrid runs,
+//      a warp scan of their popcounts gives every word its rank base;
+//   2. the tile's dictionary indices are unpacked into shared memory, lanes striding over each run;
+//   3. 32 rows per iteration: rank = base + popc(lower lanes), dictionary / PLAIN load, typed store.
+// Booleans keep the generic kernel above.
+__global__ void __launch_bounds__(PQ_WARPS * 32) pq_decode_tiles_fast_kernel(PqLaunch L, int n_tiles) {
+    __shared__ uint32_t s_vals[PQ_WARPS][PQ_TILE];
+    __shared__ uint32_t s_w[PQ_WARPS][33];
+    const PqColumnArgs& a = L.a;
+    const int wid = threadIdx.x >> 5;
+    int tile_id = blockIdx.x * PQ_WARPS + wid;
+    if (tile_id >= n_tiles) return;
+    const unsigned lane = lane_id();
+    const PqTile tl = L.tiles[tile_id];
+    const PqPage pg = a.pages[tl.page];
+    const int n = tl.n;
+    const bool has_def = a.max_def > 0 && pg.def_len > 0;
+    const bool dict = pg.encoding == 2 || pg.encoding == 8;
+    const uint8_t* vals = pg.val_ptr;
+    // ---- 1. validity words
+    uint32_t w = 0;
+    if (has_def) {
+        w = L.tile_valid[(int64_t)tile_id * 32 + lane];   // decoded once, by the scout
+    } else if (!(a.max_def > 0 && pg.all_null)) {
+        int cnt = n - 32 * (int)lane;
+        w = cnt >= 32 ? 0xffffffffu : (cnt > 0 ? (1u << cnt) - 1u : 0u);
+    }
+    int pc = __popc(w), inc = pc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(FULL_MASK, inc, d);
+        if ((int)lane >= d) inc += t;
+    }
+    const int prefix = inc - pc;
+    const int nv = __shfl_sync(FULL_MASK, inc, 31);
+    // ---- 2. dictionary indices of the tile's non-null values
+    if (dict) {
+        Hybrid idx;
+        const int bw = pg.val_len > 0 ? vals[0] : 0;
+        hybrid_restore(idx, tl.idx, vals + 1, vals + pg.val_len, bw);
+        int pos = 0;
+        while (pos < nv) {
+            if (idx.run_remaining == 0) idx.next_run();
+            int t = min(nv - pos, idx.run_remaining);
+            if (idx.is_rle) {
+                for (int k = lane; k < t; k += 32) s_vals[wid][pos + k] = idx.rle_value;
+            } else {
+                for (int k = lane; k < t; k += 32) s_vals[wid][pos + k] = extract_bits(idx.bp_base, (int64_t)(idx.bp_consumed + k) * bw, bw);
+            }
+            pos += t;
+            idx.run_remaining -= t;
+            if (!idx.is_rle) idx.bp_consumed += t;
+        }
+    }
+    s_w[wid][lane] = w;
+    if (lane == 0) s_w[wid][32] = 0;
+    __syncwarp();
+    // ---- 3. rows
+    const PqDict dd = dict ? a.dicts[pg.dict_id] : PqDict{nullptr, 0, 0};
+    const int width = a.phys_width;
+    const int64_t out0 = (int64_t)pg.row_start + tl.row0;
+    for (int j = 0; j * 32 < n; j++) {
+        int i = 32 * j + (int)lane;
+        bool active = i < n;
+        uint32_t wj = s_w[wid][j];
+        int pj = __shfl_sync(FULL_MASK, prefix, j);
+        bool valid = active && ((wj >> lane) & 1u);
+        int rank = pj + __popc(wj & lanemask_lt());
+        int64_t row = out0 + i;
+        if (!active) continue;
+        if (a.mode == PQ_MODE_INDEX) {
+            uint32_t di = dict ? s_vals[wid][rank] : 0;
+            if (di >= (uint32_t)dd.num_values) di = 0;
+            a.out_idx[row] = valid ? (dict ? dd.value_base + (int32_t)di : pg.plain_value_base + (int32_t)(tl.v0 + rank)) : -1;
+        } else if (valid) {
+            const uint8_t* src;
+            if (dict) {
+                uint32_t di = s_vals[wid][rank];
+                if (di >= (uint32_t)dd.num_values) di = 0;   // corrupt index guard
+                src = dd.data + (int64_t)di * width;
+            } else src = vals + (tl.v0 + rank) * width;
+            store_converted(a, src, row);
+        } else {
+            store_zero(a, row);
+        }
+    }
+    // ---- 4. validity words of the output (tile rows are not 32-aligned in general)
+    if (a.out_valid) {
+        const int sh = (int)(out0 & 31);
+        const int64_t q0 = out0 >> 5;
+        const int nwords = (sh + n + 31) / 32;
+        for (int q = lane; q < nwords; q += 32) {
+            uint32_t cur = q < 32 ? s_w[wid][q] : 0u, prev = q > 0 ? s_w[wid][q - 1] : 0u;
+            uint32_t bits = sh ? ((cur << sh) | (prev >> (32 - sh))) : cur;
+            bool full = (q > 0 || sh == 0) && ((q + 1) * 32 <= sh + n);
+            if (full) a.out_valid[q0 + q] = bits;
+            else if (bits) atomicOr(&a.out_valid[q0 + q], bits);
+        }
+    }
+}
+
+void pq_decode_pages(Ctx& ctx, const PqColumnArgs& a, const std::vector<PqPage>& host_pages) {
     if (a.n_pages == 0) return;
-    pq_decode_pages_kernel<<<(a.n_pages + PQ_WARPS - 1) / PQ_WARPS, PQ_WARPS * 32, 0, ctx.stream>>>(a);
-    LAUNCH_CHECK(ctx);
+    std::vector<int32_t> tb(host_pages.size() + 1, 0);
+    for (size_t i = 0; i < host_pages.size(); i++) tb[i + 1] = tb[i] + (host_pages[i].num_values + PQ_TILE - 1) / PQ_TILE;
+    int n_tiles = tb.back();
+    if (n_tiles == 0) return;
+    Buf dtb = to_device(ctx, tb.data(), tb.size() * 4);
+    Buf tiles = dalloc(ctx, (size_t)n_tiles * sizeof(PqTile));
+    Buf tvalid = dalloc(ctx, a.max_def > 0 ? (size_t)n_tiles * 128 : 4);
+    PqLaunch L{a, P<int32_t>(dtb), P<PqTile>(tiles), P<uint32_t>(tvalid)};
+    {
+        ProfScope ps(ctx, "pq_scout");
+        pq_scout_kernel<<<(a.n_pages + PQ_WARPS - 1) / PQ_WARPS, PQ_WARPS * 32, 0, ctx.stream>>>(L);
+        LAUNCH_CHECK(ctx);
+    }
+    {
+        ProfScope ps(ctx, "pq_decode_pages");
+        if (a.phys_type == 0) pq_decode_tiles_kernel<<<(n_tiles + PQ_WARPS - 1) / PQ_WARPS, PQ_WARPS * 32, 0, ctx.stream>>>(L, n_tiles);
+        else pq_decode_tiles_fast_kernel<<<(n_tiles + PQ_WARPS - 1) / PQ_WARPS, PQ_WARPS * 32, 0, ctx.stream>>>(L, n_tiles);
+        LAUNCH_CHECK(ctx);
+    }
+    ctx.sync();   // tb (host) is read by an async copy
 }
 
 // ---- PLAIN BYTE_ARRAY sections (dictionary pages and non-dictionary data pages): one thread walks one section

@@ -76,8 +76,9 @@ struct GroupedResult {
     int64_t num_groups = 0;
 };
 // Hash-aggregate one device-resident batch.  sel (optional) = row selection (filter fused into the aggregate).
+// fast_key_out (optional, single fixed-width integer key only): emit the group key in this wider integer type.
 GroupedResult hash_aggregate(Ctx& ctx, const std::vector<ColumnPtr>& keys, const std::vector<AccSpec>& accs,
-                             const int32_t* sel, int64_t n_rows);
+                             const int32_t* sel, int64_t n_rows, const DType* fast_key_out = nullptr);
 // no grouping keys: one output row
 std::vector<ColumnPtr> global_aggregate(Ctx& ctx, const std::vector<AccSpec>& accs, const int32_t* sel, int64_t n_rows);
 // AVG final merge (agg/avg.rs:151-179)

@@ -116,6 +116,7 @@ SelBatch FilterExec::next_sel(Task& t) {
     SelBatch out;
     BatchPtr b = children[0]->next(t);
     if (!b) return out;
+    OpTimer timer(metrics, "elapsed_ns");
     out.batch = b;
     Buf mask = eval_predicate(t.ctx, prog, *b, b->num_rows);
     int64_t cnt = 0;
@@ -232,6 +233,20 @@ AggExec::AggExec(OperatorPtr input, std::vector<ExprPtr> ge, std::vector<std::st
     }
     // lowered input expressions: group keys, then the args of every partial-mode aggregate
     for (auto& g : group_exprs) lowered.push_back(g);
+    // GROUP BY cast(int column AS wider int): the widening is injective, so group on the source column (fast 64-bit key
+    // path sign-extends it anyway) and emit the key in the wider type -- saves materialising the cast for every input row.
+    if (group_exprs.size() == 1 && (group_exprs[0]->kind == E_CAST || group_exprs[0]->kind == E_TRY_CAST)) {
+        int idx;
+        const Expr& ce = *group_exprs[0];
+        if (is_plain_column(*ce.children[0], in, &idx)) {
+            const DType& from = in.fields[idx].type;
+            if (from.is_integer() && ce.type.is_integer() && from.width() <= ce.type.width()) {
+                lowered[0] = ce.children[0];
+                widened_key_type = ce.type;
+                has_widened_key = true;
+            }
+        }
+    }
     for (auto& a : aggs) {
         if (a.mode != MODE_PARTIAL) continue;
         for (size_t k = 0; k < a.children.size(); k++) {
@@ -339,14 +354,15 @@ static std::vector<AccSpec> build_specs(const std::vector<AggExprSpec>& aggs, co
     return specs;
 }
 
-static BatchPtr run_agg(Task& t, const std::vector<ColumnPtr>& keys, const std::vector<AccSpec>& specs, const int32_t* sel, int64_t n) {
+static BatchPtr run_agg(Task& t, const std::vector<ColumnPtr>& keys, const std::vector<AccSpec>& specs, const int32_t* sel, int64_t n,
+                        const DType* key_out = nullptr) {
     auto out = std::make_shared<Batch>();
     if (keys.empty()) {
         auto accs = global_aggregate(t.ctx, specs, sel, n);
         out->num_rows = 1;
         out->cols = accs;
     } else {
-        GroupedResult r = hash_aggregate(t.ctx, keys, specs, sel, n);
+        GroupedResult r = hash_aggregate(t.ctx, keys, specs, sel, n, key_out);
         out->num_rows = r.num_groups;
         out->cols = r.keys->cols;
         for (auto& c : r.accs) out->cols.push_back(c);
@@ -381,7 +397,7 @@ BatchPtr AggExec::aggregate_chunk(Task& t, const SelBatch& s) {
         for (int i = start; i < (int)src->cols.size(); i++) merge_cols.push_back(src->cols[i]);
     }
     auto specs = build_specs(aggs, pargs, &merge_cols, false);
-    return run_agg(t, keys, specs, sel, n);
+    return run_agg(t, keys, specs, sel, n, has_widened_key ? &widened_key_type : nullptr);
 }
 
 BatchPtr AggExec::merge_partials(Task& t, const BatchPtr& all) {
@@ -428,6 +444,7 @@ BatchPtr AggExec::next(Task& t) {
         }
         saw_input = true;
         if (s.n == 0 && !group_exprs.empty()) continue;
+        OpTimer timer(metrics, "hashing_ns");
         BatchPtr p = aggregate_chunk(t, s);
         partials.push_back(p);
         partial_rows += p->num_rows;

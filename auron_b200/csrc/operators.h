@@ -66,6 +66,8 @@ struct AggExec : Operator {
     bool all_plain = true;
     VmProgram lowered_prog;
     int n_acc_cols = 0, input_acc_cols = 0;
+    bool has_widened_key = false;   // single GROUP BY cast(int col AS wider int): grouped on the source column
+    DType widened_key_type;
     AggExec(OperatorPtr input, std::vector<ExprPtr> group_exprs, std::vector<std::string> group_names, std::vector<AggExprSpec> aggs);
     BatchPtr next(Task& t) override;
 

@@ -40,7 +40,7 @@ struct PqByteSection {
     int32_t value_base;
 };
 
-void pq_decode_pages(Ctx& ctx, const PqColumnArgs& a);
+void pq_decode_pages(Ctx& ctx, const PqColumnArgs& a, const std::vector<PqPage>& host_pages);
 ColumnPtr pq_build_value_table(Ctx& ctx, const std::vector<PqByteSection>& secs, int64_t total_values, const DType& type);
 
 }  // namespace auron

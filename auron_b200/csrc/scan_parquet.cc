@@ -386,16 +386,34 @@ struct ParquetScanExec : Operator {
         AURON_CHECK(ok, "cannot read parquet column " + el.name + " (physical type " + std::to_string(el.type) + ") as " + t.str());
     }
 
-    BatchPtr decode_row_groups(Task& t, const std::vector<size_t>& rgs) {
-        const PqFileSpec& f = files[file_pos];
-        int64_t n_rows = 0;
-        for (size_t g : rgs) n_rows += meta.row_groups[g].num_rows;
+    // per projected column: descriptors accumulated over the row groups (possibly of several files) of one batch
+    struct ColState {
+        int leaf = -1;   // index into `leaves`, -1 = column missing in the file(s)
+        pq::SchemaElement el;
+        bool is_string = false;
+        ChunkPages cp;
+    };
+    // layout signature of the current file for the projected columns; a batch never mixes different layouts
+    std::string signature() const {
+        std::string s;
+        for (int pj : projection) {
+            int li = find_leaf(table_schema.fields[pj].name);
+            if (li < 0) s += "-;";
+            else s += std::to_string(leaves[li].leaf_index) + ":" + std::to_string(leaves[li].el.type) + ":" + std::to_string(leaves[li].el.repetition) + ":" +
+                      std::to_string(leaves[li].el.type_length) + ";";
+        }
+        return s;
+    }
+
+    BatchPtr build_batch(Task& t, std::vector<ColState>& cols, int64_t n_rows) {
         AURON_CHECK(n_rows < (int64_t)INT32_MAX, "parquet batch too large");
         auto out = std::make_shared<Batch>();
         out->num_rows = n_rows;
-        for (int pj : projection) {
-            const Field& fld = table_schema.fields[pj];
-            int li = find_leaf(fld.name);
+        for (size_t ci = 0; ci < projection.size(); ci++) {
+            const Field& fld = table_schema.fields[projection[ci]];
+            ColState& cs = cols[ci];
+            ChunkPages& cp = cs.cp;
+            int li = cs.leaf;
             if (li < 0) {   // missing column -> NULL (scan/mod.rs:84-100)
                 if (fld.type.is_varlen()) {
                     auto c = make_column(t.ctx, fld.type, n_rows, true);
@@ -405,17 +423,8 @@ struct ParquetScanExec : Operator {
                 } else out->cols.push_back(make_null_column(t.ctx, fld.type, n_rows));
                 continue;
             }
-            const pq::SchemaElement& el = leaves[li].el;
-            check_types(el, fld.type);
-            const bool is_string = el.type == pq::PT_BYTE_ARRAY;
-            ChunkPages cp;
-            int64_t row = 0;
-            for (size_t g : rgs) {
-                const auto& rg = meta.row_groups[g];
-                AURON_CHECK((size_t)leaves[li].leaf_index < rg.columns.size(), "row group misses a column chunk");
-                walk_chunk(t, f, rg.columns[leaves[li].leaf_index], el, is_string, row, cp);
-                row += rg.num_rows;
-            }
+            const pq::SchemaElement& el = cs.el;
+            const bool is_string = cs.is_string;
             const int max_def = el.repetition == 1 ? 1 : 0;
             PqColumnArgs a;
             memset(&a, 0, sizeof(a));
@@ -440,7 +449,7 @@ struct ParquetScanExec : Operator {
                 a.mode = PQ_MODE_INDEX;
                 a.out_idx = P<int32_t>(idx);
                 a.out_valid = nullptr;
-                pq_decode_pages(t.ctx, a);
+                pq_decode_pages(t.ctx, a, cp.pages);
                 col = take(t.ctx, *table, P<int32_t>(idx), n_rows, max_def > 0);
             } else {
                 col = std::make_shared<Column>();
@@ -450,7 +459,7 @@ struct ParquetScanExec : Operator {
                 else col->data = dalloc(t.ctx, (size_t)n_rows * fld.type.width());
                 a.out = col->data->ptr;
                 a.mode = PQ_MODE_VALUES;
-                pq_decode_pages(t.ctx, a);
+                pq_decode_pages(t.ctx, a, cp.pages);
                 if (validity) {
                     col->validity = validity;
                     col->null_count = -1;
@@ -463,25 +472,52 @@ struct ParquetScanExec : Operator {
     }
 
     BatchPtr next(Task& t) override {
+        OpTimer timer(metrics, "elapsed_ns");
+        std::vector<ColState> cols;
+        std::string batch_sig;
+        int64_t rows = 0;
+        bool started = false;
         for (;;) {
-            if (file_pos >= files.size()) return nullptr;
+            if (file_pos >= files.size()) break;
             if (!file_open) open_file(t);
             if (rg_pos >= row_groups.size()) {
                 file_open = false;
                 file_pos++;
                 continue;
             }
-            std::vector<size_t> rgs;
-            int64_t rows = 0;
-            while (rg_pos < row_groups.size() && (rgs.empty() || rows + meta.row_groups[row_groups[rg_pos]].num_rows <= t.ctx.gpu_chunk_rows)) {
-                rows += meta.row_groups[row_groups[rg_pos]].num_rows;
-                rgs.push_back(row_groups[rg_pos++]);
-            }
+            const auto& rg = meta.row_groups[row_groups[rg_pos]];
+            std::string sig = signature();
+            if (started && (sig != batch_sig || rows + rg.num_rows > t.ctx.gpu_chunk_rows)) break;
             AURON_CHECK(t.is_running(), "task killed");
-            BatchPtr b = decode_row_groups(t, rgs);
-            metrics.add("output_rows", b->num_rows);
-            return b;
+            if (!started) {
+                started = true;
+                batch_sig = sig;
+                cols.assign(projection.size(), ColState());
+                for (size_t ci = 0; ci < projection.size(); ci++) {
+                    const Field& fld = table_schema.fields[projection[ci]];
+                    int li = find_leaf(fld.name);
+                    cols[ci].leaf = li;
+                    if (li < 0) continue;
+                    cols[ci].el = leaves[li].el;
+                    check_types(cols[ci].el, fld.type);
+                    cols[ci].is_string = cols[ci].el.type == pq::PT_BYTE_ARRAY;
+                }
+            }
+            for (size_t ci = 0; ci < projection.size(); ci++) {
+                ColState& cs = cols[ci];
+                if (cs.leaf < 0) continue;
+                int leaf_index = leaves[find_leaf(table_schema.fields[projection[ci]].name)].leaf_index;
+                AURON_CHECK((size_t)leaf_index < rg.columns.size(), "row group misses a column chunk");
+                walk_chunk(t, files[file_pos], rg.columns[leaf_index], cs.el, cs.is_string, rows, cs.cp);
+            }
+            rows += rg.num_rows;
+            rg_pos++;
         }
+        if (!started) return nullptr;
+        OpTimer timer2(metrics, "decode_ns");
+        BatchPtr b = build_batch(t, cols, rows);
+        metrics.add("output_rows", b->num_rows);
+        return b;
     }
 };
 

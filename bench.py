@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json config[1]: ParquetScan -> Filter -> HashAggregate (GROUP BY int64, SUM/COUNT) over a
+synthetic TPC-DS SF100 `store_sales` (287,997,024 rows), one step = one pass of the whole plan.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1 via torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                     (CPU arm: Arrow C++ scan/filter + the oracle's C aggregate)
+
+`value`  : rows/s with the Parquet file images already resident in HBM (decode -> filter -> aggregate on device).
+`e2e`    : rows/s through the C ABI with the files in HOST memory (page cache): pread -> pinned staging -> H2D of
+           the encoded column chunks -> decode -> filter -> aggregate -> D2H of the result, every step.
+`roofline`: dominant kernel of the timed steps, algorithmic bytes / device time from CUDA events recorded on the
+           launching stream inside the library (AURON_PROFILE=1), against MEASURED_PEAKS.json hbm_gbs.
+The oracle is used only by the cpu_baseline / --impl reference legs (as the timed CPU arm), never by the product path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.compute as pc
+import pyarrow.parquet as pq
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SF100_ROWS = 287_997_024
+ROWS_PER_FILE = 16_000_000
+DATE_LO, DATE_HI = 2450816, 2452642          # ss_sold_date_sk window (~5 years)
+FILTER_LO, FILTER_HI = 2451000, 2452000      # WHERE ss_sold_date_sk >= lo AND < hi
+N_ITEMS = 204_000                            # item cardinality at SF100
+SCHEMA = pa.schema([("ss_item_sk", pa.int32()), ("ss_quantity", pa.int32()), ("ss_sold_date_sk", pa.int32())])
+
+
+def gen_file(path: str, rows: int, seed: int):
+    rng = np.random.default_rng(seed)
+    t = pa.table({
+        "ss_item_sk": pa.array(rng.integers(1, N_ITEMS + 1, rows, dtype=np.int32)),
+        "ss_quantity": pa.array(rng.integers(1, 101, rows, dtype=np.int32), mask=rng.random(rows) < 0.03),
+        "ss_sold_date_sk": pa.array(rng.integers(DATE_LO, DATE_HI, rows, dtype=np.int32), mask=rng.random(rows) < 0.04),
+    }, schema=SCHEMA)
+    pq.write_table(t, path, compression="NONE", use_dictionary=True, row_group_size=8_000_000, data_page_size=1 << 20)
+
+
+def gen_dataset(directory: str, total_rows: int) -> list[tuple[str, int]]:
+    os.makedirs(directory, exist_ok=True)
+    specs, left, i = [], total_rows, 0
+    while left > 0:
+        r = min(ROWS_PER_FILE, left)
+        specs.append((os.path.join(directory, f"store_sales_{i:03d}.parquet"), r, 42 + i))
+        left -= r
+        i += 1
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        list(ex.map(lambda s: gen_file(*s) if not os.path.exists(s[0]) else None, specs))
+    return [(p, r) for p, r, _ in specs]
+
+
+def build_plan(P, files: list[str], sizes: list[int]) -> bytes:
+    scan = P.parquet_scan(SCHEMA, list(zip(files, sizes)), [0, 1, 2])
+    flt = P.filter_(scan, [P.binary("GtEq", P.col("ss_sold_date_sk"), P.lit(FILTER_LO, pa.int32())),
+                           P.binary("Lt", P.col("ss_sold_date_sk"), P.lit(FILTER_HI, pa.int32()))])
+    agg = P.agg(flt, [P.try_cast(P.col("ss_item_sk"), pa.int64())], ["ss_item_sk"],
+                [P.agg_expr("SUM", [P.col("ss_quantity")], pa.int64()), P.agg_expr("COUNT", [P.col("ss_quantity")], pa.int64())],
+                ["sum_qty", "cnt_qty"], ["PARTIAL", "PARTIAL"])
+    return P.task_definition(agg)
+
+
+class ClockSampler:
+    """nvidia-smi clocks during the timed region (profiling recipe)"""
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_pipeline(files: list[str]) -> tuple[int, float]:
+    """The CPU arm: Arrow C++ Parquet reader + filter (stand-in for the parquet crate / arrow-rs kernels the reference
+    delegates to) feeding the oracle's C hash aggregate (port of agg_hash_map.rs / sum.rs / count.rs), all host threads."""
+    import oracle
+    rows = 0
+    t0 = time.perf_counter()
+    for f in files:
+        t = pq.read_table(f, columns=["ss_item_sk", "ss_quantity", "ss_sold_date_sk"], use_threads=True)
+        d = t["ss_sold_date_sk"]
+        mask = pc.and_kleene(pc.greater_equal(d, FILTER_LO), pc.less(d, FILTER_HI))
+        ft = t.filter(mask)
+        oracle.agg_sum_count_i64(ft["ss_item_sk"].combine_chunks().cast(pa.int64()), ft["ss_quantity"].combine_chunks().cast(pa.int64()))
+        rows += t.num_rows
+    return rows, time.perf_counter() - t0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="auron")
+    ap.add_argument("--rows", type=int, default=SF100_ROWS)
+    ap.add_argument("--data-dir", default=os.path.join(tempfile.gettempdir(), "auron_b200_bench"))
+    ap.add_argument("--skip-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    config = {"workload": "BASELINE configs[1]: ParquetScan->Filter->HashAggregate(GROUP BY int64 ss_item_sk, SUM/COUNT ss_quantity), "
+                          "synthetic TPC-DS SF100 store_sales", "rows": args.rows, "groups": N_ITEMS, "filter_selectivity": "~0.53",
+              "parquet": "3 INT32 columns, RLE_DICTIONARY + PLAIN fallback pages, 8M-row row groups, UNCOMPRESSED pages",
+              "l2_policy": "inputs (>=1.4 GB encoded, 3.4 GB decoded per step) are far larger than the 126 MB L2",
+              "parallelism": f"dp{args.gpus}: table partitions sharded per GPU, no data-path collective"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        files = gen_dataset(args.data_dir, args.rows)
+        sample = [f for f, _ in files[:2]]
+        for _ in range(args.warmup):
+            cpu_pipeline(sample[:1])
+        rows, secs = 0, 0.0
+        for _ in range(args.steps):
+            r, s = cpu_pipeline(sample)
+            rows += r
+            secs += s
+        v = rows / secs
+        print(json.dumps({"impl": "reference", "metric": "rows_per_sec", "value": v, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1000 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": v, "unit": "rows/s", "cores": cores, "kind": "port",
+                                           "sample": f"{len(sample)} of {len(files)} files ({sum(r for _, r in files[:2])} rows) per step"},
+                          "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    from auron_b200 import proto as P
+    from auron_b200 import runtime
+
+    if rank == 0:
+        files = gen_dataset(args.data_dir, args.rows)
+    if world > 1:
+        dist.barrier()
+    files = gen_dataset(args.data_dir, args.rows)       # no-op when the files exist
+    paths = [f for f, _ in files]
+    sizes = [os.path.getsize(f) for f in paths]
+    total_rows = sum(r for _, r in files)
+    h2d_bytes = 0
+    for f in paths:
+        md = pq.ParquetFile(f).metadata
+        for g in range(md.num_row_groups):
+            for c in range(md.num_columns):
+                h2d_bytes += md.row_group(g).column(c).total_compressed_size
+
+    os.environ["AURON_PROFILE"] = "1"
+
+    def barrier_sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_steps(plan: bytes, steps: int, collect: bool):
+        kern, launches, out_bytes = {}, 0, 0
+        barrier_sync()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            with runtime.Task(plan, device=local_rank) as task:
+                out = pa.Table.from_batches(list(task), schema=task.schema)
+                out_bytes = out.nbytes
+                if collect:
+                    for depth, op, name, v in task.metrics():
+                        if op == "__kernels__":
+                            kern[name] = kern.get(name, 0) + v
+                        elif os.environ.get("AURON_BENCH_VERBOSE"):
+                            print(f"[metric] {op}.{name} = {v}", file=sys.stderr)
+        barrier_sync()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        return dt, kern, out_bytes, out
+
+    # ---- value: file images resident in HBM
+    hbm_paths = [f"hbm://{os.path.basename(p)}@{local_rank}" for p in paths]
+    for p, hp in zip(paths, hbm_paths):
+        with open(p, "rb") as fh:
+            runtime.put_device_file(hp, fh.read(), device=local_rank)
+    plan_hbm = build_plan(P, hbm_paths, sizes)
+    run_steps(plan_hbm, args.warmup, False)
+    with ClockSampler(local_rank) as cs:
+        dt, kern, out_bytes, out = run_steps(plan_hbm, args.steps, True)
+    clocks = cs.summary()
+    value = world * total_rows * args.steps / dt
+    for hp in hbm_paths:
+        runtime.drop_device_file(hp)
+
+    # ---- e2e: files in host memory, H2D inside the timed region
+    e2e = None
+    if not args.skip_e2e:
+        plan_host = build_plan(P, paths, sizes)
+        run_steps(plan_host, 1, False)
+        dte, _, out_bytes_e, _ = run_steps(plan_host, args.steps, False)
+        e2e = {"value": world * total_rows * args.steps / dte, "unit": "rows/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": out_bytes_e,
+               "ms_per_step": 1000 * dte / args.steps}
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel (device time from CUDA events on the launching stream)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    names = sorted({k.rsplit(".", 1)[0] for k in kern if k.endswith(".device_us")}, key=lambda n: -kern[n + ".device_us"])
+    # partial-mode output = [group, sum acc, count acc] (accumulator fields are unnamed, agg_ctx.rs:127-150)
+    sel_rows = int(out.column(2).to_numpy().sum() / 0.97) if out.num_rows else 0        # filtered rows reaching the aggregate (approx)
+    decoded_bytes = total_rows * 12 + 2 * total_rows // 8                               # 3 x int32 out + 2 validity bitmaps
+    alg = {   # algorithmic bytes per step for each launch site (DESIGN.md "Kernels and rooflines")
+        "pq_decode_pages": h2d_bytes + decoded_bytes,
+        "expr_vm": None,
+        "agg_update": None,
+        "take": None,
+    }
+    roofs = []
+    for n in names:
+        us = kern[n + ".device_us"] / args.steps
+        roofs.append({"kernel": n, "device_ms_per_step": us / 1000.0, "launches_per_step": kern[n + ".launches"] / args.steps,
+                      "share_of_step": (us / 1e6) / (dt / args.steps)})
+    dom = names[0] if names else None
+    dom_us = kern[dom + ".device_us"] / args.steps if dom else None
+    dom_bytes = alg.get(dom) if dom else None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": (dom_bytes / (dom_us * 1e-6) / 1e9) if dom_bytes and dom_us else None, "peak": peak,
+                "unit": "GB/s", "frac": (dom_bytes / (dom_us * 1e-6) / 1e9 / peak) if dom_bytes and dom_us else None, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_step": dom_bytes, "kernels": roofs}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
+    cpu = None
+    if world == 1:
+        sample = paths[:2]
+        cpu_pipeline(sample[:1])
+        r, s = cpu_pipeline(sample)
+        cpu = {"value": r / s, "unit": "rows/s", "cores": cores, "kind": "port",
+               "sample": f"{len(sample)} of {len(paths)} files ({r} rows): Arrow C++ scan+filter, oracle C hash aggregate"}
+
+    line = {"metric": "rows_per_sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+            "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
+            "gpu_launches": int(kern.get("total_launches", 0)), "roofline": roofline, "cpu_baseline": cpu,
+            "result_groups": out.num_rows, "selected_rows_est": sel_rows}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

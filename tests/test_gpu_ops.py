@@ -110,6 +110,48 @@ def test_filter_project_config1():
     assert got.column(1).to_pylist() == exp.column(1).to_pylist()
 
 
+def test_conjunctive_compare_fast_paths_match_vm_and_arrow():
+    # column-vs-literal conjunctions take the interval / simple-term kernels; they must agree with the interpreter and Arrow
+    import os
+    rng = np.random.default_rng(77)
+    n = 70_001
+    t = pa.table({"i": pa.array(rng.integers(-50, 50, n), type=pa.int32(), mask=rng.random(n) < 0.05),
+                  "l": pa.array(rng.integers(-2**62, 2**62, n), type=pa.int64(), mask=rng.random(n) < 0.05),
+                  "f": pa.array(np.where(rng.random(n) < 0.02, np.nan, rng.standard_normal(n)), mask=rng.random(n) < 0.05),
+                  "d": pa.array([None if x else decimal.Decimal(int(v)) / 100 for x, v in zip(rng.random(n) < 0.05, rng.integers(-5000, 5000, n))], type=pa.decimal128(7, 2)),
+                  "b": pa.array(rng.random(n) < 0.5, mask=rng.random(n) < 0.05),
+                  "row": pa.array(np.arange(n), type=pa.int64())})
+    I, Lc, F, D, B = P.col("i"), P.col("l"), P.col("f"), P.col("d"), P.col("b")
+    li = lambda v: P.lit(v, pa.int32())
+    cases = [
+        ([P.binary("GtEq", I, li(-10)), P.binary("Lt", I, li(20))], pc.and_kleene(pc.greater_equal(t["i"], -10), pc.less(t["i"], 20))),
+        ([P.binary("Gt", li(5), I)], pc.less(t["i"], 5)),                                       # literal on the left
+        ([P.binary("Eq", I, li(7)), P.is_not_null(Lc)], pc.and_kleene(pc.equal(t["i"], 7), pc.is_valid(t["l"]))),
+        ([P.binary("NotEq", I, li(0)), P.binary("LtEq", Lc, P.lit(0, pa.int64()))], pc.and_kleene(pc.not_equal(t["i"], 0), pc.less_equal(t["l"], 0))),
+        ([P.is_null(I), P.binary("Gt", Lc, P.lit(-2**61, pa.int64()))], pc.and_kleene(pc.is_null(t["i"]), pc.greater(t["l"], -2**61))),
+        ([P.binary("Lt", Lc, P.lit(-2**63, pa.int64()))], pc.less(t["l"], -2**63)),             # empty interval
+        ([P.binary("Gt", F, P.lit(0.25, pa.float64())), P.binary("Eq", B, P.lit(True, pa.bool_()))], None),   # NaN > x under totalOrder
+        ([P.binary("GtEq", D, P.lit(decimal.Decimal("-1.50"), pa.decimal128(7, 2))), P.binary("Lt", D, P.lit(decimal.Decimal("12.34"), pa.decimal128(7, 2)))],
+         pc.and_kleene(pc.greater_equal(t["d"], decimal.Decimal("-1.50")), pc.less(t["d"], decimal.Decimal("12.34")))),
+    ]
+    for preds, arrow_mask in cases:
+        plan = P.filter_(P.ffi_reader(t.schema, "t"), preds)
+        fast = run(plan, {"t": t})["row"].to_pylist()
+        os.environ["AURON_DISABLE_SIMPLE_PREDICATE"] = "1"
+        try:
+            vm = run(plan, {"t": t})["row"].to_pylist()
+        finally:
+            os.environ.pop("AURON_DISABLE_SIMPLE_PREDICATE", None)
+        assert fast == vm
+        if arrow_mask is not None:
+            assert fast == t.filter(arrow_mask)["row"].to_pylist()
+        else:
+            f = t["f"].to_pylist()
+            b = t["b"].to_pylist()
+            exp = [i for i in range(n) if f[i] is not None and b[i] and (math.isnan(f[i]) or f[i] > 0.25)]
+            assert fast == exp
+
+
 def _eval(t: pa.Table, exprs, names, types):
     plan = P.projection(P.ffi_reader(t.schema, "t"), exprs, names, types)
     return run(plan, {"t": t})
