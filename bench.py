@@ -75,40 +75,50 @@ def build_plan(P, files: list[str], sizes: list[int]) -> bytes:
 
 
 class ClockSampler:
-    """nvidia-smi clocks during the timed region (profiling recipe)"""
+    """SM clock + throttle reasons sampled DURING the timed region (profiling recipe), through NVML in a background thread
+    (the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints, without a subprocess per sample)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+    def __init__(self, gpu_index: int, period_s: float = 0.02):
+        self.sm, self.mx, self.reasons, self.idx, self.period = [], None, set(), gpu_index, period_s
+        self._stop = threading.Event()
+        self._thr = None
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.idx}", "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap",
-                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].isdigit() else self.idx
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        for bit, name in self.REASONS.items():
+                            if mask & bit:
+                                self.reasons.add(name)
+                    except Exception:
+                        pass
+                    self._stop.wait(self.period)
+
+            self._thr = threading.Thread(target=loop, daemon=True)
+            self._thr.start()
         except Exception:
-            self.proc = None
+            self._thr = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
     def __exit__(self, *a):
-        if self.proc:
-            self.proc.terminate()
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=1)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
 
 
 def cpu_pipeline(files: list[str]) -> tuple[int, float]:
@@ -130,7 +140,7 @@ def cpu_pipeline(files: list[str]) -> tuple[int, float]:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="auron")
     ap.add_argument("--rows", type=int, default=SF100_ROWS)
