@@ -3,15 +3,21 @@
 // FSDataInputWrapper.readFully) and AuronSchemaAdapter (scan/mod.rs:56-160: case-insensitive column match,
 // missing columns -> NULL, INT32/INT64 decimals widened by value copy).
 //
-// Host work: footer + page headers (Thrift), row-group selection by file range, optional host
-// decompression of SNAPPY / ZSTD / LZ4_RAW pages.  Everything per value happens in k_parquet.cu.  When the
-// file bytes are already resident in HBM (auron_b200_put_device_file) page payloads are decoded in place.
+// Host work per device batch (up to AURON_GPU_CHUNK_ROWS rows, possibly spanning files):
+//   1. plan   : footers (Thrift), row-group selection by file range, list of column chunks
+//   2. fetch  : HBM-resident file images are used in place; host files are pread by a thread pool into one pinned
+//               staging buffer and uploaded with a single async copy
+//   3. parse  : page headers of every chunk (Thrift) in parallel on host threads -> page / dictionary descriptors;
+//               SNAPPY / ZSTD / LZ4_RAW pages are decompressed here (UNCOMPRESSED pages are decoded in place)
+//   4. decode : k_parquet.cu, one scout + one decode launch per column
 #include <dlfcn.h>
 #include <fcntl.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
+#include <thread>
 
 #include "../../include/auron_b200.h"
 #include "operators.h"
@@ -74,6 +80,37 @@ static void host_decompress(int codec, const uint8_t* in, size_t in_len, uint8_t
     }
 }
 
+// run fn(i) for i in [0, n) on up to `threads` host threads; the first exception is rethrown
+template <typename F>
+static void parallel_for(size_t n, unsigned threads, F fn) {
+    if (n == 0) return;
+    threads = (unsigned)std::max<size_t>(1, std::min<size_t>(threads, n));
+    if (threads == 1) {
+        for (size_t i = 0; i < n; i++) fn(i);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    std::mutex mu;
+    std::string err;
+    auto work = [&]() {
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= n) return;
+            try {
+                fn(i);
+            } catch (const std::exception& e) {
+                std::lock_guard<std::mutex> l(mu);
+                if (err.empty()) err = e.what();
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < threads; t++) th.emplace_back(work);
+    work();
+    for (auto& x : th) x.join();
+    if (!err.empty()) fail(err);
+}
+
 // ------------------------------------------------------------------------------------------ operator
 struct PqFileSpec {
     std::string path;
@@ -90,94 +127,128 @@ struct ParquetScanExec : Operator {
     std::vector<int> projection;
     std::string fs_id;
     size_t file_pos = 0;
-    // current file state
-    bool file_open = false;
-    std::shared_ptr<DeviceFile> dev_file;
-    int fd = -1;
-    pq::FileMeta meta;
-    std::vector<LeafColumn> leaves;
-    std::vector<size_t> row_groups;   // selected row groups of the current file
+
+    // state of one opened file; kept alive for the batch that references it
+    struct FileState {
+        PqFileSpec spec;
+        std::shared_ptr<DeviceFile> dev_file;
+        int fd = -1;
+        pq::FileMeta meta;
+        std::vector<LeafColumn> leaves;
+        std::vector<size_t> row_groups;   // selected row groups
+        ~FileState() {
+            if (fd >= 0) close(fd);
+        }
+    };
+    std::shared_ptr<FileState> cur;   // currently open file
     size_t rg_pos = 0;
     void* pinned = nullptr;
     size_t pinned_cap = 0;
+    unsigned host_threads = 16;
 
     ~ParquetScanExec() override {
-        if (fd >= 0) close(fd);
-        if (pinned) cudaFreeHost(pinned);
+        if (pinned) pinned_pool().put(pinned, pinned_cap);
     }
-    void read_at(Task& t, const PqFileSpec& f, int64_t pos, void* dst, int64_t len) {
-        if (dev_file) {
-            AURON_CHECK(pos >= 0 && (size_t)(pos + len) <= dev_file->host.size(), "parquet read out of range");
-            memcpy(dst, dev_file->host.data() + pos, (size_t)len);
+
+    void read_at(Task& t, FileState& f, int64_t pos, void* dst, int64_t len) {
+        if (f.dev_file) {
+            AURON_CHECK(pos >= 0 && (size_t)(pos + len) <= f.dev_file->host.size(), "parquet read out of range");
+            memcpy(dst, f.dev_file->host.data() + pos, (size_t)len);
             return;
         }
         if (t.cb && t.cb->read_fully) {   // FSDataInputWrapper.readFully (internal_file_reader.rs:64-68)
-            int64_t got = t.cb->read_fully(t.cb->user, fs_id.c_str(), f.path.c_str(), pos, dst, len);
-            AURON_CHECK(got == len, "read_fully failed for " + f.path);
+            int64_t got = t.cb->read_fully(t.cb->user, fs_id.c_str(), f.spec.path.c_str(), pos, dst, len);
+            AURON_CHECK(got == len, "read_fully failed for " + f.spec.path);
             return;
         }
-        if (fd < 0) {
-            fd = open(f.path.c_str(), O_RDONLY);
-            AURON_CHECK(fd >= 0, "cannot open " + f.path);
+        if (f.fd < 0) {
+            f.fd = open(f.spec.path.c_str(), O_RDONLY);
+            AURON_CHECK(f.fd >= 0, "cannot open " + f.spec.path);
         }
         int64_t done = 0;
         while (done < len) {
-            ssize_t r = pread(fd, (uint8_t*)dst + done, (size_t)(len - done), pos + done);
-            AURON_CHECK(r > 0, "short read on " + f.path);
+            ssize_t r = pread(f.fd, (uint8_t*)dst + done, (size_t)(len - done), pos + done);
+            AURON_CHECK(r > 0, "short read on " + f.spec.path);
             done += r;
         }
     }
+    // pinned staging comes from a process-wide pool: cudaHostAlloc costs ~0.4 s per GB, far more than the copy it feeds
+    struct PinnedPool {
+        std::mutex mu;
+        std::vector<std::pair<void*, size_t>> free_list;
+        void* get(size_t n, size_t* cap) {
+            std::lock_guard<std::mutex> l(mu);
+            size_t best = SIZE_MAX;
+            for (size_t i = 0; i < free_list.size(); i++)
+                if (free_list[i].second >= n && (best == SIZE_MAX || free_list[i].second < free_list[best].second)) best = i;
+            if (best != SIZE_MAX) {
+                auto e = free_list[best];
+                free_list.erase(free_list.begin() + best);
+                *cap = e.second;
+                return e.first;
+            }
+            for (auto& e : free_list) cudaFreeHost(e.first);   // too small: replace rather than accumulate
+            free_list.clear();
+            void* p = nullptr;
+            size_t c = std::max<size_t>(n + n / 8, 64 << 20);
+            CUDA_OK(cudaHostAlloc(&p, c, cudaHostAllocDefault));
+            *cap = c;
+            return p;
+        }
+        void put(void* p, size_t cap) {
+            std::lock_guard<std::mutex> l(mu);
+            free_list.emplace_back(p, cap);
+        }
+    };
+    static PinnedPool& pinned_pool() {
+        static PinnedPool pool;
+        return pool;
+    }
     void* staging(size_t n) {
         if (n > pinned_cap) {
-            if (pinned) cudaFreeHost(pinned);
-            pinned_cap = std::max<size_t>(n, 64 << 20);
-            CUDA_OK(cudaHostAlloc(&pinned, pinned_cap, cudaHostAllocDefault));
+            if (pinned) pinned_pool().put(pinned, pinned_cap);
+            pinned = pinned_pool().get(n, &pinned_cap);
         }
         return pinned;
     }
     void open_file(Task& t) {
-        const PqFileSpec& f = files[file_pos];
-        if (fd >= 0) {
-            close(fd);
-            fd = -1;
-        }
-        dev_file = find_device_file(f.path);
-        int64_t size = dev_file ? (int64_t)dev_file->host.size() : f.size;
-        AURON_CHECK(size >= 12, "not a parquet file: " + f.path);
+        auto fs = std::make_shared<FileState>();
+        fs->spec = files[file_pos];
+        fs->dev_file = find_device_file(fs->spec.path);
+        int64_t size = fs->dev_file ? (int64_t)fs->dev_file->host.size() : fs->spec.size;
+        AURON_CHECK(size >= 12, "not a parquet file: " + fs->spec.path);
         uint8_t tail[8];
-        read_at(t, f, size - 8, tail, 8);
-        AURON_CHECK(memcmp(tail + 4, "PAR1", 4) == 0, "missing PAR1 magic in " + f.path);
+        read_at(t, *fs, size - 8, tail, 8);
+        AURON_CHECK(memcmp(tail + 4, "PAR1", 4) == 0, "missing PAR1 magic in " + fs->spec.path);
         uint32_t flen;
         memcpy(&flen, tail, 4);
         AURON_CHECK((int64_t)flen + 8 <= size, "corrupt parquet footer length");
         std::vector<uint8_t> footer(flen);
-        read_at(t, f, size - 8 - flen, footer.data(), flen);
-        meta = pq::parse_file_meta(footer.data(), footer.size());
-        leaves.clear();
-        AURON_CHECK(!meta.schema.empty(), "empty parquet schema");
+        read_at(t, *fs, size - 8 - flen, footer.data(), flen);
+        fs->meta = pq::parse_file_meta(footer.data(), footer.size());
+        AURON_CHECK(!fs->meta.schema.empty(), "empty parquet schema");
         int leaf = 0;
-        for (size_t i = 1; i < meta.schema.size(); i++) {
-            const auto& el = meta.schema[i];
+        for (size_t i = 1; i < fs->meta.schema.size(); i++) {
+            const auto& el = fs->meta.schema[i];
             AURON_CHECK(el.num_children == 0, "nested parquet columns are out of scope (" + el.name + ")");
             AURON_CHECK(el.repetition != 2, "repeated parquet columns are out of scope (" + el.name + ")");
-            leaves.push_back({leaf++, el});
+            fs->leaves.push_back({leaf++, el});
         }
-        row_groups.clear();
-        for (size_t g = 0; g < meta.row_groups.size(); g++) {
-            const auto& rg = meta.row_groups[g];
+        for (size_t g = 0; g < fs->meta.row_groups.size(); g++) {
+            const auto& rg = fs->meta.row_groups[g];
             if (rg.columns.empty()) continue;
             int64_t start = rg.columns[0].start_offset();
-            if (f.range_start >= 0 && !(start >= f.range_start && start < f.range_end)) continue;
-            row_groups.push_back(g);
+            if (fs->spec.range_start >= 0 && !(start >= fs->spec.range_start && start < fs->spec.range_end)) continue;
+            fs->row_groups.push_back(g);
         }
         rg_pos = 0;
-        file_open = true;
+        cur = fs;
     }
-    int find_leaf(const std::string& name) const {
-        for (size_t i = 0; i < leaves.size(); i++)
-            if (leaves[i].el.name == name) return (int)i;
-        for (size_t i = 0; i < leaves.size(); i++) {   // case-insensitive (scan/mod.rs:56-100)
-            const std::string& n = leaves[i].el.name;
+    static int find_leaf(const FileState& f, const std::string& name) {
+        for (size_t i = 0; i < f.leaves.size(); i++)
+            if (f.leaves[i].el.name == name) return (int)i;
+        for (size_t i = 0; i < f.leaves.size(); i++) {   // case-insensitive (scan/mod.rs:56-100)
+            const std::string& n = f.leaves[i].el.name;
             if (n.size() != name.size()) continue;
             bool eq = true;
             for (size_t k = 0; k < n.size(); k++) eq = eq && tolower(n[k]) == tolower(name[k]);
@@ -185,152 +256,54 @@ struct ParquetScanExec : Operator {
         }
         return -1;
     }
+    // layout signature of a file for the projected columns; a batch never mixes different layouts
+    std::string signature(const FileState& f) const {
+        std::string s;
+        for (int pj : projection) {
+            int li = find_leaf(f, table_schema.fields[pj].name);
+            if (li < 0) s += "-;";
+            else s += std::to_string(f.leaves[li].leaf_index) + ":" + std::to_string(f.leaves[li].el.type) + ":" + std::to_string(f.leaves[li].el.repetition) +
+                      ":" + std::to_string(f.leaves[li].el.type_length) + ";";
+        }
+        return s;
+    }
 
+    // descriptors of one column chunk (local numbering; rebased when merged into the column's lists)
     struct ChunkPages {
         std::vector<PqPage> pages;
         std::vector<PqDict> dicts;
         std::vector<PqByteSection> secs;
-        std::vector<Buf> keep;
         int64_t value_table_size = 0;
-    };
-
-    // walk the pages of one column chunk, appending page / dictionary descriptors
-    void walk_chunk(Task& t, const PqFileSpec& f, const pq::ColumnMeta& cm, const pq::SchemaElement& el, bool is_string, int64_t row_start, ChunkPages& out) {
-        int64_t start = cm.start_offset(), len = cm.total_compressed;
-        const uint8_t* host;
-        const uint8_t* dev;
-        if (dev_file) {
-            host = dev_file->host.data() + start;
-            dev = P<uint8_t>(dev_file->dev) + start;
-        } else {
-            uint8_t* st = (uint8_t*)staging((size_t)len + 64);
-            read_at(t, f, start, st, len);
-            Buf d = dalloc(t.ctx, (size_t)len + 64);
-            CUDA_OK(cudaMemcpyAsync(d->ptr, st, (size_t)len, cudaMemcpyHostToDevice, t.ctx.stream));
-            t.ctx.sync();   // the pinned staging buffer is reused by the next chunk
-            out.keep.push_back(d);
-            host = st;
-            dev = P<uint8_t>(d);
-        }
-        const int max_def = el.repetition == 1 ? 1 : 0;
-        const bool compressed = cm.codec != pq::CODEC_UNCOMPRESSED;
-        // compressed chunks: decompress page payloads into one host buffer, upload once
+        // compressed chunks: page payloads decompressed here, pointers patched after the upload
         std::vector<uint8_t> unc;
         struct Fix {
-            size_t page;   // index into out.pages, or SIZE_MAX for a dictionary
-            size_t dict;
-            size_t sec;
-            int64_t off;   // offset of the page payload in `unc`
+            size_t page;   // index into pages, or SIZE_MAX for a dictionary
+            size_t dict, sec;
+            int64_t off;
         };
         std::vector<Fix> fixes;
-        int64_t pos = 0, values_seen = 0, rows = row_start;
-        int cur_dict = -1;
-        while (pos < len && values_seen < cm.num_values) {
-            pq::PageHeader h = pq::parse_page_header(host + pos, (size_t)(len - pos));
-            const uint8_t* payload_h = host + pos + h.header_len;
-            const uint8_t* payload_d = dev + pos + h.header_len;
-            AURON_CHECK(pos + h.header_len + h.compressed_size <= len, "parquet page overruns its column chunk");
-            pos += h.header_len + h.compressed_size;
-            if (h.type == pq::PAGE_INDEX) continue;
-            int64_t unc_off = -1;
-            int32_t lvl_bytes = h.type == pq::PAGE_DATA_V2 ? h.def_bytes + h.rep_bytes : 0;
-            if (compressed && !(h.type == pq::PAGE_DATA_V2 && !h.v2_compressed)) {
-                unc_off = (int64_t)unc.size();
-                unc.resize(unc.size() + (size_t)h.uncompressed_size + 8);
-                if (lvl_bytes) memcpy(unc.data() + unc_off, payload_h, (size_t)lvl_bytes);   // v2 levels are never compressed
-                host_decompress(cm.codec, payload_h + lvl_bytes, (size_t)(h.compressed_size - lvl_bytes), unc.data() + unc_off + lvl_bytes,
-                                (size_t)(h.uncompressed_size - lvl_bytes));
-                payload_h = nullptr;   // re-pointed after the upload
-            }
-            auto hp = [&](int64_t o) -> const uint8_t* { return unc_off >= 0 ? unc.data() + unc_off + o : payload_h + o; };
-            if (h.type == pq::PAGE_DICTIONARY) {
-                AURON_CHECK(h.encoding == pq::ENC_PLAIN || h.encoding == pq::ENC_PLAIN_DICTIONARY, "unsupported dictionary page encoding");
-                PqDict d{payload_d, h.num_values, (int32_t)out.value_table_size};
-                cur_dict = (int)out.dicts.size();
-                out.dicts.push_back(d);
-                size_t sec_idx = SIZE_MAX;
-                if (is_string) {
-                    sec_idx = out.secs.size();
-                    out.secs.push_back({payload_d, h.uncompressed_size, h.num_values, (int32_t)out.value_table_size});
-                    out.value_table_size += h.num_values;
-                }
-                if (unc_off >= 0) fixes.push_back({SIZE_MAX, (size_t)cur_dict, sec_idx, unc_off});
-                continue;
-            }
-            AURON_CHECK(h.type == pq::PAGE_DATA || h.type == pq::PAGE_DATA_V2, "unknown parquet page type");
-            PqPage pg;
-            memset(&pg, 0, sizeof(pg));
-            pg.num_values = h.num_values;
-            pg.row_start = (int32_t)rows;
-            pg.encoding = h.encoding;
-            pg.dict_id = cur_dict;
-            AURON_CHECK(h.encoding == pq::ENC_PLAIN || ((h.encoding == pq::ENC_RLE_DICTIONARY || h.encoding == pq::ENC_PLAIN_DICTIONARY) && cur_dict >= 0) ||
-                            (h.encoding == pq::ENC_RLE && el.type == pq::PT_BOOLEAN),
-                        "parquet encoding " + std::to_string(h.encoding) + " is not supported on device (PLAIN / RLE_DICTIONARY are)");
-            int64_t o = 0, total = h.uncompressed_size;
-            if (h.type == pq::PAGE_DATA) {
-                if (max_def > 0) {
-                    AURON_CHECK(h.def_encoding == pq::ENC_RLE, "only RLE definition levels are supported");
-                    uint32_t dl;
-                    memcpy(&dl, hp(0), 4);
-                    pg.def_ptr = (const uint8_t*)(intptr_t)4;   // offsets now, pointers after the base is known
-                    pg.def_len = (int32_t)dl;
-                    o = 4 + dl;
-                }
-            } else {
-                o = h.rep_bytes;
-                if (max_def > 0 && h.def_bytes > 0) {
-                    pg.def_ptr = (const uint8_t*)(intptr_t)o;
-                    pg.def_len = h.def_bytes;
-                }
-                if (max_def > 0 && h.def_bytes == 0 && h.num_nulls == h.num_values) pg.all_null = 1;
-                o += h.def_bytes;
-            }
-            AURON_CHECK(o <= total, "corrupt parquet page levels");
-            int64_t val_off = o;
-            pg.val_len = (int32_t)(total - o);
-            const uint8_t* base_d = unc_off >= 0 ? nullptr : payload_d;
-            if (base_d) {
-                pg.def_ptr = pg.def_len ? base_d + (intptr_t)pg.def_ptr : nullptr;
-                pg.val_ptr = base_d + val_off;
-            } else {
-                pg.val_ptr = (const uint8_t*)(intptr_t)val_off;
-            }
-            size_t sec_idx = SIZE_MAX;
-            if (is_string && h.encoding == pq::ENC_PLAIN) {
-                // number of non-null values is only known on device; sections carry the page's value count upper bound
-                // => PLAIN string pages need their exact non-null count: v2 gives it, v1 requires the def levels.
-                int32_t nn = h.type == pq::PAGE_DATA_V2 ? h.num_values - h.num_nulls : count_non_null_v1(hp(0), max_def, h.num_values);
-                pg.plain_value_base = (int32_t)out.value_table_size;
-                sec_idx = out.secs.size();
-                out.secs.push_back({base_d ? pg.val_ptr : nullptr, pg.val_len, nn, (int32_t)out.value_table_size});
-                out.value_table_size += nn;
-            }
-            if (unc_off >= 0) fixes.push_back({out.pages.size(), 0, sec_idx, unc_off});
-            out.pages.push_back(pg);
-            rows += h.num_values;
-            values_seen += h.num_values;
-        }
-        if (!unc.empty()) {
-            Buf d = to_device(t.ctx, unc.data(), unc.size());
-            t.ctx.sync();
-            out.keep.push_back(d);
-            const uint8_t* base = P<uint8_t>(d);
-            for (auto& fx : fixes) {
-                if (fx.page == SIZE_MAX) {
-                    out.dicts[fx.dict].data = base + fx.off;
-                    if (fx.sec != SIZE_MAX) out.secs[fx.sec].ptr = base + fx.off;
-                } else {
-                    PqPage& pg = out.pages[fx.page];
-                    if (pg.def_len) pg.def_ptr = base + fx.off + (intptr_t)pg.def_ptr;
-                    else pg.def_ptr = nullptr;
-                    intptr_t vo = (intptr_t)pg.val_ptr;
-                    pg.val_ptr = base + fx.off + vo;
-                    if (fx.sec != SIZE_MAX) out.secs[fx.sec].ptr = pg.val_ptr;
-                }
-            }
-        }
-    }
+    };
+    struct ChunkTask {
+        std::shared_ptr<FileState> file;
+        const pq::ColumnMeta* cm = nullptr;
+        int col = 0;               // index into projection
+        int64_t row_start = 0;
+        const uint8_t* host = nullptr;
+        const uint8_t* dev = nullptr;
+        int64_t stage_off = -1;    // offset in the pinned staging buffer (host files)
+        ChunkPages out;
+    };
+    struct ColState {
+        int leaf = -1;   // index into leaves, -1 = missing
+        pq::SchemaElement el;
+        bool is_string = false;
+        std::vector<PqPage> pages;
+        std::vector<PqDict> dicts;
+        std::vector<PqByteSection> secs;
+        int64_t value_table_size = 0;
+        std::vector<Buf> keep;
+    };
+
     // host-side count of non-null values of a v1 page (needed only for PLAIN string pages)
     static int32_t count_non_null_v1(const uint8_t* payload, int max_def, int32_t num_values) {
         if (max_def == 0) return num_values;
@@ -363,6 +336,104 @@ struct ParquetScanExec : Operator {
         return nn;
     }
 
+    // pure CPU: walk the pages of one column chunk (thread-safe, no CUDA calls)
+    static void parse_chunk(ChunkTask& ct, const pq::SchemaElement& el, bool is_string) {
+        const pq::ColumnMeta& cm = *ct.cm;
+        ChunkPages& out = ct.out;
+        const uint8_t* host = ct.host;
+        const uint8_t* dev = ct.dev;
+        const int64_t len = cm.total_compressed;
+        const int max_def = el.repetition == 1 ? 1 : 0;
+        const bool compressed = cm.codec != pq::CODEC_UNCOMPRESSED;
+        int64_t pos = 0, values_seen = 0, rows = ct.row_start;
+        int cur_dict = -1;
+        while (pos < len && values_seen < cm.num_values) {
+            pq::PageHeader h = pq::parse_page_header(host + pos, (size_t)(len - pos));
+            const uint8_t* payload_h = host + pos + h.header_len;
+            const uint8_t* payload_d = dev + pos + h.header_len;
+            AURON_CHECK(pos + h.header_len + h.compressed_size <= len, "parquet page overruns its column chunk");
+            pos += h.header_len + h.compressed_size;
+            if (h.type == pq::PAGE_INDEX) continue;
+            int64_t unc_off = -1;
+            int32_t lvl_bytes = h.type == pq::PAGE_DATA_V2 ? h.def_bytes + h.rep_bytes : 0;
+            if (compressed && !(h.type == pq::PAGE_DATA_V2 && !h.v2_compressed)) {
+                unc_off = (int64_t)out.unc.size();
+                out.unc.resize(out.unc.size() + (size_t)h.uncompressed_size + 8);
+                if (lvl_bytes) memcpy(out.unc.data() + unc_off, payload_h, (size_t)lvl_bytes);   // v2 levels are never compressed
+                host_decompress(cm.codec, payload_h + lvl_bytes, (size_t)(h.compressed_size - lvl_bytes), out.unc.data() + unc_off + lvl_bytes,
+                                (size_t)(h.uncompressed_size - lvl_bytes));
+                payload_h = nullptr;
+            }
+            auto hp = [&](int64_t o) -> const uint8_t* { return unc_off >= 0 ? out.unc.data() + unc_off + o : payload_h + o; };
+            if (h.type == pq::PAGE_DICTIONARY) {
+                AURON_CHECK(h.encoding == pq::ENC_PLAIN || h.encoding == pq::ENC_PLAIN_DICTIONARY, "unsupported dictionary page encoding");
+                PqDict d{payload_d, h.num_values, (int32_t)out.value_table_size};
+                cur_dict = (int)out.dicts.size();
+                out.dicts.push_back(d);
+                size_t sec_idx = SIZE_MAX;
+                if (is_string) {
+                    sec_idx = out.secs.size();
+                    out.secs.push_back({payload_d, h.uncompressed_size, h.num_values, (int32_t)out.value_table_size});
+                    out.value_table_size += h.num_values;
+                }
+                if (unc_off >= 0) out.fixes.push_back({SIZE_MAX, (size_t)cur_dict, sec_idx, unc_off});
+                continue;
+            }
+            AURON_CHECK(h.type == pq::PAGE_DATA || h.type == pq::PAGE_DATA_V2, "unknown parquet page type");
+            PqPage pg;
+            memset(&pg, 0, sizeof(pg));
+            pg.num_values = h.num_values;
+            pg.row_start = (int32_t)rows;
+            pg.encoding = h.encoding;
+            pg.dict_id = cur_dict;
+            AURON_CHECK(h.encoding == pq::ENC_PLAIN || ((h.encoding == pq::ENC_RLE_DICTIONARY || h.encoding == pq::ENC_PLAIN_DICTIONARY) && cur_dict >= 0) ||
+                            (h.encoding == pq::ENC_RLE && el.type == pq::PT_BOOLEAN),
+                        "parquet encoding " + std::to_string(h.encoding) + " is not supported on device (PLAIN / RLE_DICTIONARY are)");
+            int64_t o = 0, total = h.uncompressed_size;
+            if (h.type == pq::PAGE_DATA) {
+                if (max_def > 0) {
+                    AURON_CHECK(h.def_encoding == pq::ENC_RLE, "only RLE definition levels are supported");
+                    uint32_t dl;
+                    memcpy(&dl, hp(0), 4);
+                    pg.def_ptr = (const uint8_t*)(intptr_t)4;   // offsets now, pointers once the base is known
+                    pg.def_len = (int32_t)dl;
+                    o = 4 + dl;
+                }
+            } else {
+                o = h.rep_bytes;
+                if (max_def > 0 && h.def_bytes > 0) {
+                    pg.def_ptr = (const uint8_t*)(intptr_t)o;
+                    pg.def_len = h.def_bytes;
+                }
+                if (max_def > 0 && h.def_bytes == 0 && h.num_nulls == h.num_values) pg.all_null = 1;
+                o += h.def_bytes;
+            }
+            AURON_CHECK(o <= total, "corrupt parquet page levels");
+            int64_t val_off = o;
+            pg.val_len = (int32_t)(total - o);
+            const uint8_t* base_d = unc_off >= 0 ? nullptr : payload_d;
+            if (base_d) {
+                pg.def_ptr = pg.def_len ? base_d + (intptr_t)pg.def_ptr : nullptr;
+                pg.val_ptr = base_d + val_off;
+            } else {
+                pg.val_ptr = (const uint8_t*)(intptr_t)val_off;
+            }
+            size_t sec_idx = SIZE_MAX;
+            if (is_string && h.encoding == pq::ENC_PLAIN) {
+                // PLAIN string pages need their exact non-null count: v2 gives it, v1 requires the def levels
+                int32_t nn = h.type == pq::PAGE_DATA_V2 ? h.num_values - h.num_nulls : count_non_null_v1(hp(0), max_def, h.num_values);
+                pg.plain_value_base = (int32_t)out.value_table_size;
+                sec_idx = out.secs.size();
+                out.secs.push_back({base_d ? pg.val_ptr : nullptr, pg.val_len, nn, (int32_t)out.value_table_size});
+                out.value_table_size += nn;
+            }
+            if (unc_off >= 0) out.fixes.push_back({out.pages.size(), 0, sec_idx, unc_off});
+            out.pages.push_back(pg);
+            rows += h.num_values;
+            values_seen += h.num_values;
+        }
+    }
+
     static int phys_width(int phys, int type_length) {
         switch (phys) {
             case pq::PT_INT32: case pq::PT_FLOAT: return 4;
@@ -386,25 +457,6 @@ struct ParquetScanExec : Operator {
         AURON_CHECK(ok, "cannot read parquet column " + el.name + " (physical type " + std::to_string(el.type) + ") as " + t.str());
     }
 
-    // per projected column: descriptors accumulated over the row groups (possibly of several files) of one batch
-    struct ColState {
-        int leaf = -1;   // index into `leaves`, -1 = column missing in the file(s)
-        pq::SchemaElement el;
-        bool is_string = false;
-        ChunkPages cp;
-    };
-    // layout signature of the current file for the projected columns; a batch never mixes different layouts
-    std::string signature() const {
-        std::string s;
-        for (int pj : projection) {
-            int li = find_leaf(table_schema.fields[pj].name);
-            if (li < 0) s += "-;";
-            else s += std::to_string(leaves[li].leaf_index) + ":" + std::to_string(leaves[li].el.type) + ":" + std::to_string(leaves[li].el.repetition) + ":" +
-                      std::to_string(leaves[li].el.type_length) + ";";
-        }
-        return s;
-    }
-
     BatchPtr build_batch(Task& t, std::vector<ColState>& cols, int64_t n_rows) {
         AURON_CHECK(n_rows < (int64_t)INT32_MAX, "parquet batch too large");
         auto out = std::make_shared<Batch>();
@@ -412,9 +464,7 @@ struct ParquetScanExec : Operator {
         for (size_t ci = 0; ci < projection.size(); ci++) {
             const Field& fld = table_schema.fields[projection[ci]];
             ColState& cs = cols[ci];
-            ChunkPages& cp = cs.cp;
-            int li = cs.leaf;
-            if (li < 0) {   // missing column -> NULL (scan/mod.rs:84-100)
+            if (cs.leaf < 0) {   // missing column -> NULL (scan/mod.rs:84-100)
                 if (fld.type.is_varlen()) {
                     auto c = make_column(t.ctx, fld.type, n_rows, true);
                     c->null_count = n_rows;
@@ -428,11 +478,11 @@ struct ParquetScanExec : Operator {
             const int max_def = el.repetition == 1 ? 1 : 0;
             PqColumnArgs a;
             memset(&a, 0, sizeof(a));
-            Buf dpages = to_device(t.ctx, cp.pages.data(), cp.pages.size() * sizeof(PqPage));
-            Buf ddicts = to_device(t.ctx, cp.dicts.empty() ? (const void*)"" : (const void*)cp.dicts.data(), cp.dicts.size() * sizeof(PqDict));
+            Buf dpages = to_device(t.ctx, cs.pages.data(), cs.pages.size() * sizeof(PqPage));
+            Buf ddicts = to_device(t.ctx, cs.dicts.empty() ? (const void*)"" : (const void*)cs.dicts.data(), cs.dicts.size() * sizeof(PqDict));
             a.pages = P<PqPage>(dpages);
             a.dicts = P<PqDict>(ddicts);
-            a.n_pages = (int)cp.pages.size();
+            a.n_pages = (int)cs.pages.size();
             a.phys_type = el.type;
             a.type_length = el.type_length;
             a.phys_width = phys_width(el.type, el.type_length);
@@ -444,12 +494,12 @@ struct ParquetScanExec : Operator {
             a.out_valid = P<uint32_t>(validity);
             ColumnPtr col;
             if (is_string) {
-                ColumnPtr table = pq_build_value_table(t.ctx, cp.secs, cp.value_table_size, fld.type);
+                ColumnPtr table = pq_build_value_table(t.ctx, cs.secs, cs.value_table_size, fld.type);
                 Buf idx = dalloc(t.ctx, (size_t)std::max<int64_t>(n_rows, 1) * 4);
                 a.mode = PQ_MODE_INDEX;
                 a.out_idx = P<int32_t>(idx);
                 a.out_valid = nullptr;
-                pq_decode_pages(t.ctx, a, cp.pages);
+                pq_decode_pages(t.ctx, a, cs.pages);
                 col = take(t.ctx, *table, P<int32_t>(idx), n_rows, max_def > 0);
             } else {
                 col = std::make_shared<Column>();
@@ -459,34 +509,36 @@ struct ParquetScanExec : Operator {
                 else col->data = dalloc(t.ctx, (size_t)n_rows * fld.type.width());
                 a.out = col->data->ptr;
                 a.mode = PQ_MODE_VALUES;
-                pq_decode_pages(t.ctx, a, cp.pages);
+                pq_decode_pages(t.ctx, a, cs.pages);
                 if (validity) {
                     col->validity = validity;
                     col->null_count = -1;
                 }
             }
-            t.ctx.sync();   // descriptor vectors (host) were uploaded asynchronously
             out->cols.push_back(col);
         }
+        t.ctx.sync();   // descriptor vectors (host) were uploaded asynchronously; chunk buffers die with `cols`
         return out;
     }
 
     BatchPtr next(Task& t) override {
         OpTimer timer(metrics, "elapsed_ns");
+        // ---- 1. plan the batch
         std::vector<ColState> cols;
+        std::vector<ChunkTask> tasks;
         std::string batch_sig;
         int64_t rows = 0;
         bool started = false;
         for (;;) {
             if (file_pos >= files.size()) break;
-            if (!file_open) open_file(t);
-            if (rg_pos >= row_groups.size()) {
-                file_open = false;
+            if (!cur) open_file(t);
+            if (rg_pos >= cur->row_groups.size()) {
+                cur.reset();
                 file_pos++;
                 continue;
             }
-            const auto& rg = meta.row_groups[row_groups[rg_pos]];
-            std::string sig = signature();
+            const auto& rg = cur->meta.row_groups[cur->row_groups[rg_pos]];
+            std::string sig = signature(*cur);
             if (started && (sig != batch_sig || rows + rg.num_rows > t.ctx.gpu_chunk_rows)) break;
             AURON_CHECK(t.is_running(), "task killed");
             if (!started) {
@@ -495,25 +547,130 @@ struct ParquetScanExec : Operator {
                 cols.assign(projection.size(), ColState());
                 for (size_t ci = 0; ci < projection.size(); ci++) {
                     const Field& fld = table_schema.fields[projection[ci]];
-                    int li = find_leaf(fld.name);
+                    int li = find_leaf(*cur, fld.name);
                     cols[ci].leaf = li;
                     if (li < 0) continue;
-                    cols[ci].el = leaves[li].el;
+                    cols[ci].el = cur->leaves[li].el;
                     check_types(cols[ci].el, fld.type);
                     cols[ci].is_string = cols[ci].el.type == pq::PT_BYTE_ARRAY;
                 }
             }
             for (size_t ci = 0; ci < projection.size(); ci++) {
-                ColState& cs = cols[ci];
-                if (cs.leaf < 0) continue;
-                int leaf_index = leaves[find_leaf(table_schema.fields[projection[ci]].name)].leaf_index;
+                if (cols[ci].leaf < 0) continue;
+                int leaf_index = cur->leaves[find_leaf(*cur, table_schema.fields[projection[ci]].name)].leaf_index;
                 AURON_CHECK((size_t)leaf_index < rg.columns.size(), "row group misses a column chunk");
-                walk_chunk(t, files[file_pos], rg.columns[leaf_index], cs.el, cs.is_string, rows, cs.cp);
+                ChunkTask ct;
+                ct.file = cur;
+                ct.cm = &rg.columns[leaf_index];
+                ct.col = (int)ci;
+                ct.row_start = rows;
+                tasks.push_back(std::move(ct));
             }
             rows += rg.num_rows;
             rg_pos++;
         }
         if (!started) return nullptr;
+        // ---- 2. fetch
+        {
+            OpTimer tf(metrics, "fetch_ns");
+            int64_t stage_bytes = 0;
+            for (auto& ct : tasks) {
+                int64_t start = ct.cm->start_offset(), len = ct.cm->total_compressed;
+                if (ct.file->dev_file) {
+                    AURON_CHECK(start >= 0 && (size_t)(start + len) <= ct.file->dev_file->host.size(), "column chunk outside the file image");
+                    ct.host = ct.file->dev_file->host.data() + start;
+                    ct.dev = P<uint8_t>(ct.file->dev_file->dev) + start;
+                } else {
+                    ct.stage_off = stage_bytes;
+                    stage_bytes += (len + 63) & ~(int64_t)63;
+                }
+            }
+            if (stage_bytes > 0) {
+                uint8_t* st = (uint8_t*)staging((size_t)stage_bytes + 64);
+                bool via_callback = t.cb && t.cb->read_fully;
+                Buf d = dalloc(t.ctx, (size_t)stage_bytes + 64);
+                const int device = t.ctx.device;
+                cudaStream_t stream = t.ctx.stream;
+                // callbacks re-enter the host runtime (JVM / Python): keep those reads on this thread.  Each chunk is
+                // uploaded as soon as its read completes, so page-cache reads and H2D copies overlap.
+                parallel_for(tasks.size(), via_callback ? 1 : host_threads, [&](size_t i) {
+                    ChunkTask& ct = tasks[i];
+                    if (ct.stage_off < 0) return;
+                    int64_t start = ct.cm->start_offset(), len = ct.cm->total_compressed;
+                    if (via_callback) {
+                        read_at(t, *ct.file, start, st + ct.stage_off, len);
+                    } else {
+                        cudaSetDevice(device);
+                        int fd = open(ct.file->spec.path.c_str(), O_RDONLY);   // own descriptor per worker read
+                        AURON_CHECK(fd >= 0, "cannot open " + ct.file->spec.path);
+                        int64_t done = 0;
+                        while (done < len) {
+                            ssize_t r = pread(fd, st + ct.stage_off + done, (size_t)(len - done), start + done);
+                            if (r <= 0) {
+                                close(fd);
+                                fail("short read on " + ct.file->spec.path);
+                            }
+                            done += r;
+                        }
+                        close(fd);
+                    }
+                    cudaError_t e = cudaMemcpyAsync(P<uint8_t>(d) + ct.stage_off, st + ct.stage_off, (size_t)len, cudaMemcpyHostToDevice, stream);
+                    if (e != cudaSuccess) fail(std::string("H2D copy failed: ") + cudaGetErrorString(e));
+                });
+                metrics.add("h2d_bytes", stage_bytes);
+                for (auto& ct : tasks)
+                    if (ct.stage_off >= 0) {
+                        ct.host = st + ct.stage_off;
+                        ct.dev = P<uint8_t>(d) + ct.stage_off;
+                        cols[ct.col].keep.push_back(d);
+                    }
+            }
+        }
+        // ---- 3. parse page headers in parallel (overlaps the H2D copy above)
+        {
+            OpTimer tp(metrics, "parse_ns");
+            parallel_for(tasks.size(), host_threads, [&](size_t i) { parse_chunk(tasks[i], cols[tasks[i].col].el, cols[tasks[i].col].is_string); });
+            // ordered merge, rebasing dictionary ids / value-table positions; compressed chunks upload their payloads first
+            for (auto& ct : tasks) {
+                ColState& cs = cols[ct.col];
+                ChunkPages& cp = ct.out;
+                if (!cp.unc.empty()) {
+                    Buf d = to_device(t.ctx, cp.unc.data(), cp.unc.size());
+                    t.ctx.sync();
+                    cs.keep.push_back(d);
+                    const uint8_t* base = P<uint8_t>(d);
+                    for (auto& fx : cp.fixes) {
+                        if (fx.page == SIZE_MAX) {
+                            cp.dicts[fx.dict].data = base + fx.off;
+                            if (fx.sec != SIZE_MAX) cp.secs[fx.sec].ptr = base + fx.off;
+                        } else {
+                            PqPage& pg = cp.pages[fx.page];
+                            pg.def_ptr = pg.def_len ? base + fx.off + (intptr_t)pg.def_ptr : nullptr;
+                            intptr_t vo = (intptr_t)pg.val_ptr;
+                            pg.val_ptr = base + fx.off + vo;
+                            if (fx.sec != SIZE_MAX) cp.secs[fx.sec].ptr = pg.val_ptr;
+                        }
+                    }
+                }
+                int dict_base = (int)cs.dicts.size();
+                int32_t vbase = (int32_t)cs.value_table_size;
+                for (auto d : cp.dicts) {
+                    d.value_base += vbase;
+                    cs.dicts.push_back(d);
+                }
+                for (auto s : cp.secs) {
+                    s.value_base += vbase;
+                    cs.secs.push_back(s);
+                }
+                for (auto pg : cp.pages) {
+                    if (pg.dict_id >= 0) pg.dict_id += dict_base;
+                    pg.plain_value_base += vbase;
+                    cs.pages.push_back(pg);
+                }
+                cs.value_table_size += cp.value_table_size;
+            }
+        }
+        // ---- 4. decode
         OpTimer timer2(metrics, "decode_ns");
         BatchPtr b = build_batch(t, cols, rows);
         metrics.add("output_rows", b->num_rows);
@@ -524,6 +681,7 @@ struct ParquetScanExec : Operator {
 OperatorPtr make_parquet_scan(Task& t, const uint8_t* node, size_t n) {
     auto op = std::make_unique<ParquetScanExec>();
     op->name = "ParquetExec";
+    op->host_threads = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
     PbReader r(node, n);
     uint32_t f, w;
     while (r.next(&f, &w)) {
