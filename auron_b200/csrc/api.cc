@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "../../include/auron_b200.h"
+#include "exchange.h"
 #include "operators.h"
 
 using namespace auron;
@@ -159,6 +160,26 @@ int auron_b200_put_device_file(const char* path, const uint8_t* bytes, size_t le
 void auron_b200_drop_device_file(const char* path) {
     try {
         drop_device_file(path);
+    } catch (...) {
+    }
+}
+
+// ---- NCCL exchange plumbing
+int auron_b200_nccl_unique_id(uint8_t out_id[128]) {
+    API_GUARD_BEGIN
+    nccl_get_unique_id(out_id);
+    return 0;
+    API_GUARD_END(-1)
+}
+int auron_b200_nccl_init(const uint8_t id[128], int rank, int world, int device) {
+    API_GUARD_BEGIN
+    nccl_init(id, rank, world, device);
+    return 0;
+    API_GUARD_END(-1)
+}
+void auron_b200_nccl_finalize(void) {
+    try {
+        nccl_finalize();
     } catch (...) {
     }
 }

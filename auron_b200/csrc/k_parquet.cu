@@ -462,6 +462,7 @@ __device__ __forceinline__ uint32_t extract_bits(const uint8_t* base, int64_t bi
 __global__ void __launch_bounds__(PQ_WARPS * 32) pq_decode_tiles_fast_kernel(PqLaunch L, int n_tiles) {
     __shared__ uint32_t s_vals[PQ_WARPS][PQ_TILE];
     __shared__ uint32_t s_w[PQ_WARPS][33];
+    __shared__ int32_t s_pref[PQ_WARPS][32];
     const PqColumnArgs& a = L.a;
     const int wid = threadIdx.x >> 5;
     int tile_id = blockIdx.x * PQ_WARPS + wid;
@@ -515,6 +516,36 @@ __global__ void __launch_bounds__(PQ_WARPS * 32) pq_decode_tiles_fast_kernel(PqL
     const PqDict dd = dict ? a.dicts[pg.dict_id] : PqDict{nullptr, 0, 0};
     const int width = a.phys_width;
     const int64_t out0 = (int64_t)pg.row_start + tl.row0;
+    s_pref[wid][lane] = prefix;
+    __syncwarp();
+    // specialised inner loops for the common fixed-width cases: no per-row type switches, rank base from shared memory
+    const bool same4 = a.mode == PQ_MODE_VALUES && width == 4 && a.out_width == 4 && (a.phys_type == 1 || a.phys_type == 4);
+    const bool same8 = a.mode == PQ_MODE_VALUES && width == 8 && a.out_width == 8 && (a.phys_type == 2 || a.phys_type == 5);
+    const bool widen = a.mode == PQ_MODE_VALUES && a.phys_type == 1 && (a.out_type == T_INT64 || a.out_type == T_TIMESTAMP || a.out_type == T_DATE64);
+    if (same4 || same8 || widen) {
+        const uint32_t ndict = (uint32_t)dd.num_values;
+#pragma unroll 2
+        for (int j = 0; j * 32 < n; j++) {
+            const int i = 32 * j + (int)lane;
+            const uint32_t wj = s_w[wid][j];
+            const int rank = s_pref[wid][j] + __popc(wj & lanemask_lt());
+            const bool valid = (wj >> lane) & 1u;
+            if (i < n) {
+                const int64_t row = out0 + i;
+                const uint8_t* src = nullptr;
+                if (valid) {
+                    if (dict) {
+                        uint32_t di = s_vals[wid][rank];
+                        di = di < ndict ? di : 0;
+                        src = dd.data + (int64_t)di * width;
+                    } else src = vals + (tl.v0 + rank) * width;
+                }
+                if (same4) ((uint32_t*)a.out)[row] = valid ? ld_u32_unaligned(src) : 0u;
+                else if (same8) ((uint64_t*)a.out)[row] = valid ? ld_u64_unaligned(src) : 0ull;
+                else ((int64_t*)a.out)[row] = valid ? (int64_t)(int32_t)ld_u32_unaligned(src) : 0ll;
+            }
+        }
+    } else
     for (int j = 0; j * 32 < n; j++) {
         int i = 32 * j + (int)lane;
         bool active = i < n;

@@ -17,6 +17,7 @@
 #include <mutex>
 #include <thread>
 
+#include "exchange.h"
 #include "operators.h"
 #include "pb.h"
 
@@ -167,9 +168,45 @@ struct ShuffleWriterExec : Operator {
         metrics.add("output_rows", rows_so_far);
     }
 
+    // in-box repartition: output_data_file = "nccl://<name>" turns the writer into an exchange whose output stream is
+    // the set of rows this rank owns after the all-to-all (so the next stage can be chained in the same task plan)
+    BatchPtr exchange(Task& t) {
+        std::vector<BatchPtr> all;
+        while (BatchPtr b = children[0]->next(t)) {
+            AURON_CHECK(t.is_running(), "task killed");
+            if (b->num_rows) all.push_back(b);
+        }
+        BatchPtr in;
+        if (all.empty()) {
+            in = std::make_shared<Batch>();
+            for (auto& f : out_schema.fields) in->cols.push_back(make_column(t.ctx, f.type, 0, false));
+        } else in = concat_batches(t.ctx, all);
+        all.clear();
+        int64_t n = in->num_rows;
+        AURON_CHECK(kind == 2, "the NCCL exchange implements hash repartitioning");
+        std::vector<ColumnPtr> keys;
+        for (auto& e : hash_exprs) keys.push_back(eval_to_column(t, e, children[0]->out_schema, *in));
+        Buf pids = murmur3_partition_ids(t.ctx, keys, n, (int32_t)num_parts, 42);
+        Buf rows, offs;
+        partition_rows(t.ctx, P<int32_t>(pids), n, (int32_t)num_parts, &rows, &offs);
+        std::vector<int64_t> row_off(num_parts + 1, 0);
+        to_host(t.ctx, row_off.data(), offs->ptr, (size_t)(num_parts + 1) * 8);
+        BatchPtr sorted = take_batch(t.ctx, *in, P<int32_t>(rows), n, false);
+        int64_t sent = 0;
+        BatchPtr out;
+        {
+            OpTimer timer(metrics, "exchange_ns");
+            out = nccl_exchange(t.ctx, *sorted, row_off, num_parts, &sent);
+        }
+        metrics.add("data_size", sent);
+        metrics.add("output_rows", out->num_rows);
+        return out;
+    }
+
     BatchPtr next(Task& t) override {
         if (done) return nullptr;
         done = true;
+        if (data_file.rfind("nccl://", 0) == 0) return exchange(t);
         while (BatchPtr b = children[0]->next(t)) {
             AURON_CHECK(t.is_running(), "task killed");
             if (b->num_rows == 0) continue;

@@ -77,7 +77,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "auron_b200_call_native", "auron_b200_schema", "auron_b200_next_batch", "auron_b200_finalize_native", "auron_b200_on_exit",
     "auron_b200_last_error", "auron_b200_metrics", "auron_b200_put_device_batch", "auron_b200_drop_device_resource", "auron_b200_k_hash",
-    "auron_b200_put_device_file", "auron_b200_drop_device_file",
+    "auron_b200_put_device_file", "auron_b200_drop_device_file", "auron_b200_nccl_unique_id", "auron_b200_nccl_init", "auron_b200_nccl_finalize",
     "auron_b200_k_partition_ids", "auron_b200_kernel_launches", "auron_b200_time_kernel",
 ]
 
@@ -222,6 +222,29 @@ def put_device_file(path: str, data, device: int = 0):
 
 def drop_device_file(path: str):
     lib().auron_b200_drop_device_file(path.encode())
+
+
+def nccl_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    if lib().auron_b200_nccl_unique_id(buf) != 0:
+        raise AuronError(_err())
+    return bytes(buf)
+
+
+def nccl_init(unique_id: bytes, rank: int, world: int, device: int):
+    """Join the engine's NCCL communicator (one process per GPU).  The id comes from rank 0's nccl_unique_id()."""
+    buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+    if lib().auron_b200_nccl_init(buf, rank, world, device) != 0:
+        raise AuronError(_err())
+
+
+def nccl_finalize():
+    lib().auron_b200_nccl_finalize()
+
+
+def owner_of_partition(p: int, world: int, num_parts: int) -> int:
+    """rank that owns shuffle partition p after the in-box exchange (exchange.cu: contiguous blocks)"""
+    return p * world // num_parts
 
 
 def _kernel_one_column(fn, batch: pa.RecordBatch, cols: list[int], *mid_args, device: int = 0) -> pa.Array:

@@ -220,12 +220,13 @@ def main():
             with runtime.Task(plan, device=local_rank) as task:
                 out = pa.Table.from_batches(list(task), schema=task.schema)
                 out_bytes = out.nbytes
-                if collect:
+                if collect or os.environ.get("AURON_BENCH_VERBOSE"):
                     for depth, op, name, v in task.metrics():
                         if op == "__kernels__":
-                            kern[name] = kern.get(name, 0) + v
+                            if collect:
+                                kern[name] = kern.get(name, 0) + v
                         elif os.environ.get("AURON_BENCH_VERBOSE"):
-                            print(f"[metric] {op}.{name} = {v}", file=sys.stderr)
+                            print(f"[metric{'' if collect else ' e2e'}] {op}.{name} = {v}", file=sys.stderr)
         barrier_sync()
         dt = time.perf_counter() - t0
         if world > 1:

@@ -78,6 +78,15 @@ void auron_b200_drop_device_resource(const char* resource_id);
 int auron_b200_put_device_file(const char* path, const uint8_t* bytes, size_t len, int device);
 void auron_b200_drop_device_file(const char* path);
 
+/* ---- in-box repartition over NVLink (no counterpart in the reference, which shuffles through Spark's block manager:
+ * datafusion-ext-plans/src/shuffle/ and ipc_reader_exec.rs).  One process per GPU; rank 0 creates the id, the host
+ * runtime distributes it, every rank calls init once.  A ShuffleWriterExecNode whose output_data_file is
+ * "nccl://<name>" then performs hash partitioning + all-to-all-v and streams out the rows of the partitions this rank
+ * owns (partition p -> rank p * world / partition_count). */
+int auron_b200_nccl_unique_id(uint8_t out_id[128]);
+int auron_b200_nccl_init(const uint8_t id[128], int rank, int world, int device);
+void auron_b200_nccl_finalize(void);
+
 /* ---- kernel-level entry points (one per device algorithm; used by tests, ncu captures, bench) ----
  * Inputs/outputs are host Arrow struct arrays; columns named by index. */
 /* create_murmur3_hashes / create_xxhash64_hashes (datafusion-ext-commons/src/spark_hash.rs:28-57):
