@@ -167,39 +167,175 @@ constexpr int kMaxProbe = 128;
 __global__ void __launch_bounds__(256) agg_fast_kernel(FastKey key, unsigned long long* __restrict__ table, int64_t cap, AccArgs accs,
                                                        const int32_t* __restrict__ sel, int64_t n, int32_t* __restrict__ flags) {
     // flags[0] overflow, flags[1] sentinel-key slot used, flags[2] null slot used
-    int64_t stride = (int64_t)gridDim.x * 256;
-    uint64_t mask = (uint64_t)cap - 1;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
-        int64_t row = sel ? (int64_t)sel[i] : i;
-        int64_t slot = -1;
-        if (key.validity && !bit_get(key.validity, row)) {
-            slot = cap + 1;
-            flags[2] = 1;
-        } else {
-            uint64_t k = load_key64(key, row);
-            if (k == EMPTY_KEY) {
-                slot = cap;
+    // The per-row chain selection -> key -> table slot -> accumulators is a sequence of dependent, mostly random loads;
+    // four rows per thread are kept in flight (all selection loads, then all key loads, then all first probes) so the
+    // memory system sees 4x the requests per warp.
+    constexpr int U = 1;   // measured on B200 (SF100 bench): U = 1 -> 3.2 ms, 2 -> 4.5 ms, 4 -> 4.3 ms: the kernel is bound by L2 atomic
+                           // throughput, extra rows in flight only cost occupancy (registers)
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    const uint64_t mask = (uint64_t)cap - 1;
+    for (int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x; i0 < n; i0 += U * stride) {
+        int64_t row[U], slot[U];
+        uint64_t k[U], h[U];
+        unsigned long long cur[U];
+        bool act[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            int64_t i = i0 + u * stride;
+            act[u] = i < n;
+            row[u] = act[u] ? (sel ? (int64_t)sel[i] : i) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            slot[u] = -1;
+            k[u] = 0;
+            if (act[u]) {
+                if (key.validity && !bit_get(key.validity, row[u])) slot[u] = cap + 1;
+                else k[u] = load_key64(key, row[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            h[u] = mix64(k[u]) & mask;
+            cur[u] = (act[u] && slot[u] < 0 && k[u] != EMPTY_KEY) ? table[h[u]] : EMPTY_KEY;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (!act[u]) continue;
+            if (slot[u] == cap + 1) {
+                flags[2] = 1;
+            } else if (k[u] == EMPTY_KEY) {
+                slot[u] = cap;
                 flags[1] = 1;
             } else {
-                uint64_t h = mix64(k) & mask;
+                uint64_t hh = h[u];
+                unsigned long long c = cur[u];
                 for (int p = 0; p < kMaxProbe; p++) {
-                    unsigned long long cur = table[h];
-                    if (cur == k) { slot = (int64_t)h; break; }
-                    if (cur == EMPTY_KEY) {
-                        unsigned long long old = atomicCAS(&table[h], (unsigned long long)EMPTY_KEY, (unsigned long long)k);
-                        if (old == EMPTY_KEY || old == k) { slot = (int64_t)h; break; }
+                    if (c == k[u]) { slot[u] = (int64_t)hh; break; }
+                    if (c == EMPTY_KEY) {
+                        unsigned long long old = atomicCAS(&table[hh], (unsigned long long)EMPTY_KEY, (unsigned long long)k[u]);
+                        if (old == EMPTY_KEY || old == k[u]) { slot[u] = (int64_t)hh; break; }
                     }
-                    h = (h + 1) & mask;
+                    hh = (hh + 1) & mask;
+                    c = table[hh];
                 }
-                if (slot < 0) {
+                if (slot[u] < 0) {
                     flags[0] = 1;
-                    continue;
+                    act[u] = false;
                 }
             }
         }
         for (int a = 0; a < accs.n; a++) {
-            AccVal v;
-            if (acc_load(accs.a[a], row, i, v)) acc_apply(accs.a[a], slot, v);
+            const AccDesc& d = accs.a[a];
+            AccVal v[U];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                v[u] = {0, 0};
+                ok[u] = act[u] && acc_load(d, row[u], i0 + u * stride, v[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+                if (ok[u]) acc_apply(d, slot[u], v[u]);
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------- FAST path, low cardinality
+// With a few hundred groups every row of the plain kernel hits the same handful of L2 atomics.  This variant keeps a
+// per-CTA hash table + accumulators in shared memory (2048 slots), aggregates the CTA's rows there with shared-memory
+// atomics and merges each occupied slot into the global table once at the end.  Rows that do not fit (table full after
+// a few probes), NULL keys and the sentinel key take the global path directly, so the result is exact for any input;
+// the host picks this variant when a sample of the chunk shows <= 1024 distinct keys.
+constexpr int SM_SLOTS = 2048, SM_PROBE = 16, SM_MAX_ACCS = 4;
+__device__ __forceinline__ int64_t global_slot_fast(unsigned long long* table, uint64_t mask, uint64_t k, int32_t* flags) {
+    uint64_t h = mix64(k) & mask;
+    for (int p = 0; p < kMaxProbe; p++) {
+        unsigned long long cur = table[h];
+        if (cur == k) return (int64_t)h;
+        if (cur == EMPTY_KEY) {
+            unsigned long long old = atomicCAS(&table[h], (unsigned long long)EMPTY_KEY, (unsigned long long)k);
+            if (old == EMPTY_KEY || old == k) return (int64_t)h;
+        }
+        h = (h + 1) & mask;
+    }
+    flags[0] = 1;
+    return -1;
+}
+__global__ void __launch_bounds__(256) agg_fast_smem_kernel(FastKey key, unsigned long long* __restrict__ table, int64_t cap, AccArgs accs,
+                                                            const int32_t* __restrict__ sel, int64_t n, int32_t* __restrict__ flags) {
+    extern __shared__ __align__(16) unsigned long long sm[];
+    unsigned long long* s_keys = sm;                                   // [SM_SLOTS]
+    unsigned long long* s_acc = sm + SM_SLOTS;                         // [n_accs][SM_SLOTS]
+    uint8_t* s_valid = (uint8_t*)(s_acc + (size_t)accs.n * SM_SLOTS);  // [n_accs][SM_SLOTS]
+    for (int i = threadIdx.x; i < SM_SLOTS; i += 256) s_keys[i] = EMPTY_KEY;
+    for (int a = 0; a < accs.n; a++) {
+        unsigned long long init = 0;
+        int kd = accs.a[a].kind;
+        if (kd == ACC_MIN) init = 0x7fffffffffffffffull;
+        else if (kd == ACC_MAX) init = 0x8000000000000000ull;
+        for (int i = threadIdx.x; i < SM_SLOTS; i += 256) {
+            s_acc[(size_t)a * SM_SLOTS + i] = init;
+            s_valid[(size_t)a * SM_SLOTS + i] = 0;
+        }
+    }
+    __syncthreads();
+    const uint64_t gmask = (uint64_t)cap - 1;
+    // contiguous slab of rows per CTA
+    const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t lo = (int64_t)blockIdx.x * per, hi = min(n, lo + per);
+    for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
+        int64_t row = sel ? (int64_t)sel[i] : i;
+        bool knull = key.validity && !bit_get(key.validity, row);
+        uint64_t k = knull ? 0 : load_key64(key, row);
+        int sslot = -1;
+        if (!knull && k != EMPTY_KEY) {
+            uint32_t h = (uint32_t)mix64(k) & (SM_SLOTS - 1);
+            for (int p = 0; p < SM_PROBE; p++) {
+                unsigned long long cur = s_keys[h];
+                if (cur == k) { sslot = (int)h; break; }
+                if (cur == EMPTY_KEY) {
+                    unsigned long long old = atomicCAS(&s_keys[h], (unsigned long long)EMPTY_KEY, (unsigned long long)k);
+                    if (old == EMPTY_KEY || old == k) { sslot = (int)h; break; }
+                }
+                h = (h + 1) & (SM_SLOTS - 1);
+            }
+        }
+        if (sslot >= 0) {
+            for (int a = 0; a < accs.n; a++) {
+                AccDesc d = accs.a[a];
+                AccVal v;
+                if (!acc_load(d, row, i, v)) continue;
+                d.acc_lo = s_acc + (size_t)a * SM_SLOTS;
+                d.acc_valid = d.acc_valid ? s_valid + (size_t)a * SM_SLOTS : nullptr;
+                acc_apply(d, sslot, v);
+            }
+        } else {   // global path: NULL / sentinel key, or the shared table is full
+            int64_t slot;
+            if (knull) { slot = cap + 1; flags[2] = 1; }
+            else if (k == EMPTY_KEY) { slot = cap; flags[1] = 1; }
+            else slot = global_slot_fast(table, gmask, k, flags);
+            if (slot < 0) continue;
+            for (int a = 0; a < accs.n; a++) {
+                AccVal v;
+                if (acc_load(accs.a[a], row, i, v)) acc_apply(accs.a[a], slot, v);
+            }
+        }
+    }
+    __syncthreads();
+    // merge the CTA's groups into the global table
+    for (int s = threadIdx.x; s < SM_SLOTS; s += 256) {
+        unsigned long long k = s_keys[s];
+        if (k == EMPTY_KEY) continue;
+        int64_t slot = global_slot_fast(table, gmask, k, flags);
+        if (slot < 0) continue;
+        for (int a = 0; a < accs.n; a++) {
+            const AccDesc& d = accs.a[a];
+            if (d.acc_valid && !s_valid[(size_t)a * SM_SLOTS + s]) continue;
+            AccVal v{s_acc[(size_t)a * SM_SLOTS + s], 0};
+            AccDesc m = d;
+            if (m.kind == ACC_COUNT) m.kind = ACC_ADD_I64;   // partial counts add up
+            acc_apply(m, slot, v);
         }
     }
 }
@@ -518,7 +654,32 @@ GroupedResult hash_aggregate(Ctx& ctx, const std::vector<ColumnPtr>& keys, const
             table = dalloc(ctx, (size_t)cap * 8);
             fill_u64(ctx, table->ptr, cap, EMPTY_KEY);
             FastKey k{keys[0]->data->ptr, keys[0]->vbits(), (int32_t)keys[0]->type.id};
-            if (n_rows) {
+            // low-cardinality variant?  decided from a sample of the chunk (exact either way, see agg_fast_smem_kernel)
+            bool use_smem = false;
+            // Measured on B200 (64M rows, 400 groups, SUM+COUNT): shared-memory variant 5.0 ms vs plain L2 atomics 2.5 ms -- 64-bit
+            // shared atomics at 2 CTAs/SM lose to the L2 atomic units, so the variant is opt-in (AURON_ENABLE_SMEM_AGG=1) until it is
+            // reworked (32-bit partial sums, more CTAs per SM).
+            if (attempt == 0 && n_rows >= (1 << 20) && !accs.empty() && (int)accs.size() <= SM_MAX_ACCS && getenv("AURON_ENABLE_SMEM_AGG")) {
+                bool kinds_ok = true;
+                for (auto& s : accs)
+                    kinds_ok = kinds_ok && (s.kind == ACC_SUM_I64 || s.kind == ACC_SUM_F64 || s.kind == ACC_ADD_I64 || s.kind == ACC_COUNT || s.kind == ACC_MIN ||
+                                            s.kind == ACC_MAX);
+                if (kinds_ok) {
+                    GroupedResult sample = hash_aggregate(ctx, keys, {}, sel, std::min<int64_t>(n_rows, 1 << 18));
+                    use_smem = sample.num_groups <= 1024;
+                }
+            }
+            if (n_rows && use_smem) {
+                static bool attr = false;
+                size_t smem = (size_t)SM_SLOTS * 8 * (1 + accs.size()) + (size_t)SM_SLOTS * accs.size();
+                if (!attr) {
+                    CUDA_OK(cudaFuncSetAttribute(agg_fast_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SLOTS * 8 * (1 + SM_MAX_ACCS) + SM_SLOTS * SM_MAX_ACCS));
+                    attr = true;
+                }
+                ProfScope ps(ctx, "agg_update");
+                agg_fast_smem_kernel<<<ctx.sm_count * 2, 256, smem, ctx.stream>>>(k, P<unsigned long long>(table), cap, args, sel, n_rows, P<int32_t>(flags));
+                LAUNCH_CHECK(ctx);
+            } else if (n_rows) {
                 ProfScope ps(ctx, "agg_update");
                 agg_fast_kernel<<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(k, P<unsigned long long>(table), cap, args, sel, n_rows, P<int32_t>(flags));
                 LAUNCH_CHECK(ctx);

@@ -248,6 +248,142 @@ struct PqLaunch {
     uint32_t* tile_valid;       // [n_tiles][32] tile-local validity words written by the scout (nullable columns)
 };
 
+// ---- parallel parse of a bit-width-1 hybrid stream (definition levels) -------------------------------------------
+// Level streams are chains of tiny runs (a NULL every ~30 rows gives ~60 runs per 1024 rows); walking them serially
+// costs a dependent chain per run.  Instead the stream is treated as a finite-state transducer over 1 KiB windows:
+//   1. lane L owns bytes [32L, 32L+32) of the window and computes, for EVERY entry offset o in its block, where a
+//      parse entering at o leaves the block (dynamic programming from o = 31 down: exit[o] = next(o) >= 32 ? next(o)
+//      : exit[next(o)]) -- no knowledge of the true entry point needed;
+//   2. lane 0 chains the 32 tables from the window's known entry position: 32 lookups give every lane its real entry;
+//   3. lanes count the rows of their own runs, a warp scan turns the counts into row bases;
+//   4. lanes emit their runs' bits into the page bitmap concurrently (atomicOr on partial words).
+__device__ __forceinline__ uint32_t extract_bits(const uint8_t* base, int64_t bitpos, int bw);
+struct LvlHdr {
+    int hl;        // header bytes
+    int payload;   // payload bytes
+    int rows;      // values in the run
+    int kind;      // 0 bit-packed, 1 RLE ones, 2 RLE zeros
+};
+__device__ __forceinline__ LvlHdr lvl_parse(const uint8_t* base, int p, int len) {
+    LvlHdr r;
+    uint32_t h = base[p];
+    int hl = 1;
+    if (h & 0x80) {
+        h &= 0x7f;
+        int sh = 7;
+        while (p + hl < len) {
+            uint32_t b = base[p + hl];
+            hl++;
+            h |= (b & 0x7f) << sh;
+            sh += 7;
+            if (!(b & 0x80) || sh > 28) break;
+        }
+    }
+    r.hl = hl;
+    if (h & 1) {
+        r.kind = 0;
+        r.payload = (int)(h >> 1);
+        r.rows = (int)(h >> 1) * 8;
+    } else {
+        r.payload = 1;
+        r.rows = (int)(h >> 1);
+        r.kind = (p + hl < len && (base[p + hl] & 1)) ? 1 : 2;
+    }
+    return r;
+}
+// set bits [r, r+t) of a zero-initialised bitmap
+__device__ __forceinline__ void bm_set_range(uint32_t* bm, int64_t r, int64_t t) {
+    while (t > 0) {
+        int sh = (int)(r & 31);
+        int take = (int)min((int64_t)(32 - sh), t);
+        uint32_t bits = take == 32 ? 0xffffffffu : (((1u << take) - 1u) << sh);
+        if (take == 32) bm[r >> 5] = bits;
+        else atomicOr(&bm[r >> 5], bits);
+        r += take;
+        t -= take;
+    }
+}
+// copy t bits starting at byte `src` (bit 0) to bitmap position r
+__device__ __forceinline__ void bm_copy_bits(uint32_t* bm, int64_t r, const uint8_t* src, int64_t t) {
+    int64_t done = 0;
+    while (done < t) {
+        int sh = (int)((r + done) & 31);
+        int take = (int)min((int64_t)(32 - sh), t - done);
+        uint32_t bits = extract_bits(src, done, 32);
+        if (take < 32) bits &= (1u << take) - 1u;
+        if (bits) atomicOr(&bm[(r + done) >> 5], bits << sh);
+        done += take;
+    }
+}
+constexpr int LVL_WIN = 1024;
+__device__ inline void lvl_page_bits(const uint8_t* base, int len, int64_t rows, unsigned lane, uint32_t* bm, int (*exitT)[33], int* s_entry) {
+    int64_t row_base = 0;
+    int pos = 0;   // absolute byte offset of the next run header
+    while (pos < len && row_base < rows) {
+        const int win = pos;
+        const int b0 = win + 32 * (int)lane;
+        // 1. exit table of this lane's block (relative to the block start; >= 32 means "left the block")
+        for (int o = 31; o >= 0; o--) {
+            int p = b0 + o, nx;
+            if (p >= len) nx = 32;
+            else {
+                LvlHdr h = lvl_parse(base, p, len);
+                nx = o + h.hl + h.payload;
+            }
+            exitT[lane][o] = nx >= 32 ? nx : exitT[lane][nx];
+        }
+        __syncwarp();
+        // 2. chain
+        if (lane == 0) {
+            int rel = 0;
+            for (int L = 0; L < 32; L++) {
+                if (rel >= 32 * L && rel < 32 * (L + 1)) {
+                    s_entry[L] = rel - 32 * L;
+                    rel = 32 * L + exitT[L][rel - 32 * L];
+                } else s_entry[L] = -1;
+            }
+            s_entry[32] = rel;
+        }
+        __syncwarp();
+        // 3. rows of my runs
+        const int e = s_entry[lane];
+        int64_t cnt = 0;
+        if (e >= 0) {
+            int o = e;
+            while (o < 32 && b0 + o < len) {
+                LvlHdr h = lvl_parse(base, b0 + o, len);
+                cnt += h.rows;
+                o += h.hl + h.payload;
+            }
+        }
+        int64_t inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int64_t t = __shfl_up_sync(FULL_MASK, inc, d);
+            if ((int)lane >= d) inc += t;
+        }
+        const int64_t total = __shfl_sync(FULL_MASK, inc, 31);
+        // 4. emit
+        if (e >= 0) {
+            int o = e;
+            int64_t r = row_base + inc - cnt;
+            while (o < 32 && b0 + o < len && r < rows) {
+                LvlHdr h = lvl_parse(base, b0 + o, len);
+                int64_t t = min((int64_t)h.rows, rows - r);
+                if (h.kind == 1) bm_set_range(bm, r, t);
+                else if (h.kind == 0) bm_copy_bits(bm, r, base + b0 + o + h.hl, t);
+                r += h.rows;
+                o += h.hl + h.payload;
+            }
+        }
+        row_base += total;
+        pos = win + s_entry[32];
+        __syncwarp();
+    }
+    __threadfence();
+    __syncwarp();
+}
+
 // Definition levels of one tile -> 32 validity words (lane L returns word L, bit i of the tile = row 32L+i).
 // Writers emit very short level runs (a NULL every ~30 rows splits the stream into ~60 runs per 1024 rows), so a
 // warp-wide step per run wastes 31 lanes.  Instead lane 0 walks up to 32 run headers (the only serial part) and drops
@@ -307,8 +443,8 @@ __device__ __forceinline__ uint32_t def_tile_words(Hybrid& def, const uint8_t* d
 
 // pass 1: one warp per page walks the run headers and checkpoints both streams every PQ_TILE rows
 __global__ void __launch_bounds__(PQ_WARPS * 32) pq_scout_kernel(PqLaunch L) {
-    __shared__ uint32_t s_bm[PQ_WARPS][32];
-    __shared__ DefRun s_runs[PQ_WARPS][32];
+    __shared__ int s_exit[PQ_WARPS][32][33];
+    __shared__ int s_entry[PQ_WARPS][33];
     const PqColumnArgs& a = L.a;
     const int wid = threadIdx.x >> 5;
     int page_id = blockIdx.x * PQ_WARPS + wid;
@@ -333,6 +469,7 @@ __global__ void __launch_bounds__(PQ_WARPS * 32) pq_scout_kernel(PqLaunch L) {
     int64_t v0 = 0;
     const uint8_t* pf_idx = idx_base;
     int tile = L.tile_base[page_id];
+    if (has_def) lvl_page_bits(pg.def_ptr, pg.def_len, rows, lane, L.tile_valid + (int64_t)tile * 32, s_exit[wid], s_entry[wid]);
     for (int r = 0; r < rows; r += PQ_TILE, tile++) {
         int m = min(PQ_TILE, rows - r);
         if (lane == 0) {
@@ -357,8 +494,7 @@ __global__ void __launch_bounds__(PQ_WARPS * 32) pq_scout_kernel(PqLaunch L) {
         }
         int nvalid = m;
         if (has_def) {
-            uint32_t w = def_tile_words(def, pg.def_ptr, m, lane, s_bm[wid], s_runs[wid]);
-            L.tile_valid[(int64_t)tile * 32 + lane] = w;
+            uint32_t w = L.tile_valid[(int64_t)tile * 32 + lane];   // written by lvl_page_bits above
             int c = __popc(w);
 #pragma unroll
             for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(FULL_MASK, c, d);
@@ -395,9 +531,9 @@ __global__ void __launch_bounds__(PQ_WARPS * 32) pq_decode_tiles_kernel(PqLaunch
         int m = min(rows - done, 32 - (int)(out_row & 31));
         bool active = (int)lane < m;
         bool valid = active;
-        if (has_def) {
-            uint32_t d = def.read_batch(m, lane);
-            valid = active && d == (uint32_t)a.max_def;
+        if (has_def) {   // the scout already turned the definition levels into tile-local validity words
+            int il = done - tl.row0 + (int)lane;
+            valid = active && ((L.tile_valid[(int64_t)tile_id * 32 + (il >> 5)] >> (il & 31)) & 1u);
         } else if (a.max_def > 0 && pg.all_null) valid = false;
         uint32_t mask = __ballot_sync(FULL_MASK, valid);
         int rank = __popc(mask & lanemask_lt());
@@ -502,7 +638,17 @@ __global__ void __launch_bounds__(PQ_WARPS * 32) pq_decode_tiles_fast_kernel(PqL
             if (idx.is_rle) {
                 for (int k = lane; k < t; k += 32) s_vals[wid][pos + k] = idx.rle_value;
             } else {
-                for (int k = lane; k < t; k += 32) s_vals[wid][pos + k] = extract_bits(idx.bp_base, (int64_t)(idx.bp_consumed + k) * bw, bw);
+                for (int k0 = lane; k0 < t; k0 += 128) {   // 4 independent unpacks in flight per lane
+                    uint32_t v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        int k = k0 + 32 * u;
+                        v[u] = k < t ? extract_bits(idx.bp_base, (int64_t)(idx.bp_consumed + k) * bw, bw) : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (k0 + 32 * u < t) s_vals[wid][pos + k0 + 32 * u] = v[u];
+                }
             }
             pos += t;
             idx.run_remaining -= t;
@@ -524,25 +670,43 @@ __global__ void __launch_bounds__(PQ_WARPS * 32) pq_decode_tiles_fast_kernel(PqL
     const bool widen = a.mode == PQ_MODE_VALUES && a.phys_type == 1 && (a.out_type == T_INT64 || a.out_type == T_TIMESTAMP || a.out_type == T_DATE64);
     if (same4 || same8 || widen) {
         const uint32_t ndict = (uint32_t)dd.num_values;
-#pragma unroll 2
-        for (int j = 0; j * 32 < n; j++) {
-            const int i = 32 * j + (int)lane;
-            const uint32_t wj = s_w[wid][j];
-            const int rank = s_pref[wid][j] + __popc(wj & lanemask_lt());
-            const bool valid = (wj >> lane) & 1u;
-            if (i < n) {
-                const int64_t row = out0 + i;
-                const uint8_t* src = nullptr;
-                if (valid) {
+        const unsigned lt = lanemask_lt();
+        // 4 row-groups (128 rows) per iteration: the four gathers are issued back to back before any store
+        for (int j0 = 0; j0 * 32 < n; j0 += 4) {
+            const uint8_t* src[4];
+            bool valid[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = j0 + u;
+                const uint32_t wj = j < 32 ? s_w[wid][j] : 0u;
+                const int rank = (j < 32 ? s_pref[wid][j] : 0) + __popc(wj & lt);
+                valid[u] = ((wj >> lane) & 1u) && (32 * j + (int)lane < n);
+                src[u] = vals;
+                if (valid[u]) {
                     if (dict) {
                         uint32_t di = s_vals[wid][rank];
                         di = di < ndict ? di : 0;
-                        src = dd.data + (int64_t)di * width;
-                    } else src = vals + (tl.v0 + rank) * width;
+                        src[u] = dd.data + (int64_t)di * width;
+                    } else src[u] = vals + (tl.v0 + rank) * width;
                 }
-                if (same4) ((uint32_t*)a.out)[row] = valid ? ld_u32_unaligned(src) : 0u;
-                else if (same8) ((uint64_t*)a.out)[row] = valid ? ld_u64_unaligned(src) : 0ull;
-                else ((int64_t*)a.out)[row] = valid ? (int64_t)(int32_t)ld_u32_unaligned(src) : 0ll;
+            }
+            if (same8) {
+                uint64_t v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = valid[u] ? ld_u64_unaligned(src[u]) : 0ull;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (32 * (j0 + u) + (int)lane < n) ((uint64_t*)a.out)[out0 + 32 * (j0 + u) + lane] = v[u];
+            } else {
+                uint32_t v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = valid[u] ? ld_u32_unaligned(src[u]) : 0u;
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (32 * (j0 + u) + (int)lane < n) {
+                        if (same4) ((uint32_t*)a.out)[out0 + 32 * (j0 + u) + lane] = v[u];
+                        else ((int64_t*)a.out)[out0 + 32 * (j0 + u) + lane] = (int64_t)(int32_t)v[u];
+                    }
             }
         }
     } else
@@ -594,7 +758,7 @@ void pq_decode_pages(Ctx& ctx, const PqColumnArgs& a, const std::vector<PqPage>&
     if (n_tiles == 0) return;
     Buf dtb = to_device(ctx, tb.data(), tb.size() * 4);
     Buf tiles = dalloc(ctx, (size_t)n_tiles * sizeof(PqTile));
-    Buf tvalid = dalloc(ctx, a.max_def > 0 ? (size_t)n_tiles * 128 : 4);
+    Buf tvalid = dalloc_zero(ctx, a.max_def > 0 ? (size_t)n_tiles * 128 : 4);   // zeroed: the scout ORs level bits into it
     PqLaunch L{a, P<int32_t>(dtb), P<PqTile>(tiles), P<uint32_t>(tvalid)};
     {
         ProfScope ps(ctx, "pq_scout");

@@ -342,6 +342,31 @@ def test_agg_fuzz_sum_count_vs_oracle(n, card, chunk):
     assert_same_rows(got, exp)
 
 
+@pytest.mark.parametrize("card", [7, 400, 5000])
+def test_agg_low_cardinality_shared_memory_variant(card):
+    # few groups => the per-CTA shared-memory pre-aggregation variant; 5000 groups overflow its 2048 slots for some CTAs only
+    # when the sample says "low" -- every path must give the exact result
+    rng = np.random.default_rng(card)
+    n = 2_500_000
+    k = np.where(rng.random(n) < 0.5, rng.integers(0, min(card, 300), n), rng.integers(0, card, n))   # skewed: hot keys
+    if card == 5000:
+        k[: 1 << 18] = rng.integers(0, 100, 1 << 18)    # the sampled prefix looks low-cardinality, the tail is not
+    t = pa.table({"k": pa.array(k, type=pa.int32(), mask=rng.random(n) < 0.01), "v": pa.array(rng.integers(-10**6, 10**6, n), type=pa.int64(), mask=rng.random(n) < 0.03),
+                  "f": pa.array(rng.standard_normal(n), mask=rng.random(n) < 0.03)})
+    plan = P.agg(P.ffi_reader(t.schema, "t"), [P.col("k")], ["k"],
+                 [P.agg_expr("SUM", [P.col("v")], pa.int64()), P.agg_expr("COUNT", [P.col("v")], pa.int64()), P.agg_expr("MIN", [P.col("v")], pa.int64()),
+                  P.agg_expr("MAX", [P.col("f")], pa.float64())], ["s", "c", "mn", "mx"], ["PARTIAL"] * 4)
+    import os
+    g = t.group_by("k").aggregate([("v", "sum"), ("v", "count"), ("v", "min"), ("f", "max")])
+    exp = pa.table({"k": g["k"], "s": g["v_sum"], "c": g["v_count"], "mn": g["v_min"], "mx": g["f_max"]})
+    assert_same_rows(run(plan, {"t": t}), exp)                      # default: L2-atomic kernel
+    os.environ["AURON_ENABLE_SMEM_AGG"] = "1"
+    try:
+        assert_same_rows(run(plan, {"t": t}), exp)                  # opt-in shared-memory variant
+    finally:
+        os.environ.pop("AURON_ENABLE_SMEM_AGG", None)
+
+
 def test_agg_filter_fusion_and_expressions():
     rng = np.random.default_rng(9)
     n = 100_000
