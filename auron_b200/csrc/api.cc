@@ -163,6 +163,19 @@ void auron_b200_drop_device_file(const char* path) {
     } catch (...) {
     }
 }
+int auron_b200_put_host_file(const char* path, const uint8_t* bytes, size_t len) {
+    API_GUARD_BEGIN
+    AURON_CHECK(path && bytes, "put_host_file: null argument");
+    put_host_file(path, bytes, len);
+    return 0;
+    API_GUARD_END(-1)
+}
+void auron_b200_drop_host_file(const char* path) {
+    try {
+        drop_host_file(path);
+    } catch (...) {
+    }
+}
 
 // ---- NCCL exchange plumbing
 int auron_b200_nccl_unique_id(uint8_t out_id[128]) {

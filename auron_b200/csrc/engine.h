@@ -85,6 +85,8 @@ void drop_device_resource(const std::string& id);
 // Parquet files whose bytes are resident in HBM (scan decodes page payloads in place)
 void put_device_file(const std::string& path, const uint8_t* bytes, size_t len, int device);
 void drop_device_file(const std::string& path);
+void put_host_file(const std::string& path, const uint8_t* bytes, size_t len);
+void drop_host_file(const std::string& path);
 
 // planner: TaskDefinition bytes -> Task (operator tree)
 std::unique_ptr<Task> create_task(const uint8_t* task_def, size_t len, const auron_callbacks* cb, int device);

@@ -55,6 +55,28 @@ static std::shared_ptr<DeviceFile> find_device_file(const std::string& path) {
     return it == g_dev_files.end() ? nullptr : it->second;
 }
 
+// host-resident file images (caller-owned, ideally pinned): the scan uploads column chunks straight from them, no pread
+struct HostFile {
+    const uint8_t* ptr;
+    size_t len;
+};
+static std::map<std::string, HostFile> g_host_files;
+void put_host_file(const std::string& path, const uint8_t* bytes, size_t len) {
+    std::lock_guard<std::mutex> l(g_file_mu);
+    g_host_files[path] = HostFile{bytes, len};
+}
+void drop_host_file(const std::string& path) {
+    std::lock_guard<std::mutex> l(g_file_mu);
+    g_host_files.erase(path);
+}
+static bool find_host_file(const std::string& path, HostFile* out) {
+    std::lock_guard<std::mutex> l(g_file_mu);
+    auto it = g_host_files.find(path);
+    if (it == g_host_files.end()) return false;
+    *out = it->second;
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------ codecs (system libs, no headers in the image)
 typedef size_t (*zstd_decompress_fn)(void*, size_t, const void*, size_t);
 typedef unsigned (*zstd_iserror_fn)(size_t);
@@ -132,6 +154,7 @@ struct ParquetScanExec : Operator {
     struct FileState {
         PqFileSpec spec;
         std::shared_ptr<DeviceFile> dev_file;
+        HostFile host_file{nullptr, 0};   // registered host image (optional)
         int fd = -1;
         pq::FileMeta meta;
         std::vector<LeafColumn> leaves;
@@ -146,14 +169,15 @@ struct ParquetScanExec : Operator {
     size_t pinned_cap = 0;
     unsigned host_threads = 16;
 
-    ~ParquetScanExec() override {
-        if (pinned) pinned_pool().put(pinned, pinned_cap);
-    }
-
     void read_at(Task& t, FileState& f, int64_t pos, void* dst, int64_t len) {
         if (f.dev_file) {
             AURON_CHECK(pos >= 0 && (size_t)(pos + len) <= f.dev_file->host.size(), "parquet read out of range");
             memcpy(dst, f.dev_file->host.data() + pos, (size_t)len);
+            return;
+        }
+        if (f.host_file.ptr) {
+            AURON_CHECK(pos >= 0 && (size_t)(pos + len) <= f.host_file.len, "parquet read out of range");
+            memcpy(dst, f.host_file.ptr + pos, (size_t)len);
             return;
         }
         if (t.cb && t.cb->read_fully) {   // FSDataInputWrapper.readFully (internal_file_reader.rs:64-68)
@@ -215,7 +239,8 @@ struct ParquetScanExec : Operator {
         auto fs = std::make_shared<FileState>();
         fs->spec = files[file_pos];
         fs->dev_file = find_device_file(fs->spec.path);
-        int64_t size = fs->dev_file ? (int64_t)fs->dev_file->host.size() : fs->spec.size;
+        if (!fs->dev_file) find_host_file(fs->spec.path, &fs->host_file);
+        int64_t size = fs->dev_file ? (int64_t)fs->dev_file->host.size() : (fs->host_file.ptr ? (int64_t)fs->host_file.len : fs->spec.size);
         AURON_CHECK(size >= 12, "not a parquet file: " + fs->spec.path);
         uint8_t tail[8];
         read_at(t, *fs, size - 8, tail, 8);
@@ -290,7 +315,8 @@ struct ParquetScanExec : Operator {
         int64_t row_start = 0;
         const uint8_t* host = nullptr;
         const uint8_t* dev = nullptr;
-        int64_t stage_off = -1;    // offset in the pinned staging buffer (host files)
+        int64_t stage_off = -1;    // offset in the pinned staging buffer (files that must be pread)
+        int64_t dev_off = -1;      // offset in the batch's device buffer (every chunk that is uploaded)
         ChunkPages out;
     };
     struct ColState {
@@ -521,13 +547,37 @@ struct ParquetScanExec : Operator {
         return out;
     }
 
-    BatchPtr next(Task& t) override {
-        OpTimer timer(metrics, "elapsed_ns");
-        // ---- 1. plan the batch
+    // ---- batch pipeline: plan (main thread) -> fetch + parse (background thread, copy stream) -> merge + decode (main thread).
+    // While the GPU decodes batch k and the downstream operators consume it, batch k+1 is already being read, uploaded
+    // and parsed, so the PCIe transfer of the e2e path hides behind compute.
+    struct Prepared {
         std::vector<ColState> cols;
         std::vector<ChunkTask> tasks;
+        int64_t rows = 0, stage_bytes = 0, dev_bytes = 0;
+        void* pinned = nullptr;
+        size_t pinned_cap = 0;
+        Buf dev;
+        cudaEvent_t alloc_ready = nullptr, copied = nullptr;
+        std::thread th;
+        std::string err;
+        int64_t fetch_ns = 0, parse_ns = 0;
+    };
+    std::unique_ptr<Prepared> pending;
+    cudaStream_t copy_stream = nullptr;
+
+    void release(Prepared& p) {
+        if (p.th.joinable()) p.th.join();
+        if (p.pinned) pinned_pool().put(p.pinned, p.pinned_cap);
+        p.pinned = nullptr;
+        if (p.alloc_ready) cudaEventDestroy(p.alloc_ready);
+        if (p.copied) cudaEventDestroy(p.copied);
+        p.alloc_ready = p.copied = nullptr;
+    }
+
+    std::unique_ptr<Prepared> plan_batch(Task& t) {
+        auto pp = std::make_unique<Prepared>();
+        Prepared& p = *pp;
         std::string batch_sig;
-        int64_t rows = 0;
         bool started = false;
         for (;;) {
             if (file_pos >= files.size()) break;
@@ -539,73 +589,96 @@ struct ParquetScanExec : Operator {
             }
             const auto& rg = cur->meta.row_groups[cur->row_groups[rg_pos]];
             std::string sig = signature(*cur);
-            if (started && (sig != batch_sig || rows + rg.num_rows > t.ctx.gpu_chunk_rows)) break;
+            if (started && (sig != batch_sig || p.rows + rg.num_rows > t.ctx.gpu_chunk_rows)) break;
             AURON_CHECK(t.is_running(), "task killed");
             if (!started) {
                 started = true;
                 batch_sig = sig;
-                cols.assign(projection.size(), ColState());
+                p.cols.assign(projection.size(), ColState());
                 for (size_t ci = 0; ci < projection.size(); ci++) {
                     const Field& fld = table_schema.fields[projection[ci]];
                     int li = find_leaf(*cur, fld.name);
-                    cols[ci].leaf = li;
+                    p.cols[ci].leaf = li;
                     if (li < 0) continue;
-                    cols[ci].el = cur->leaves[li].el;
-                    check_types(cols[ci].el, fld.type);
-                    cols[ci].is_string = cols[ci].el.type == pq::PT_BYTE_ARRAY;
+                    p.cols[ci].el = cur->leaves[li].el;
+                    check_types(p.cols[ci].el, fld.type);
+                    p.cols[ci].is_string = p.cols[ci].el.type == pq::PT_BYTE_ARRAY;
                 }
             }
             for (size_t ci = 0; ci < projection.size(); ci++) {
-                if (cols[ci].leaf < 0) continue;
+                if (p.cols[ci].leaf < 0) continue;
                 int leaf_index = cur->leaves[find_leaf(*cur, table_schema.fields[projection[ci]].name)].leaf_index;
                 AURON_CHECK((size_t)leaf_index < rg.columns.size(), "row group misses a column chunk");
                 ChunkTask ct;
                 ct.file = cur;
                 ct.cm = &rg.columns[leaf_index];
                 ct.col = (int)ci;
-                ct.row_start = rows;
-                tasks.push_back(std::move(ct));
+                ct.row_start = p.rows;
+                p.tasks.push_back(std::move(ct));
             }
-            rows += rg.num_rows;
+            p.rows += rg.num_rows;
             rg_pos++;
         }
         if (!started) return nullptr;
-        // ---- 2. fetch
-        {
-            OpTimer tf(metrics, "fetch_ns");
-            int64_t stage_bytes = 0;
-            for (auto& ct : tasks) {
-                int64_t start = ct.cm->start_offset(), len = ct.cm->total_compressed;
-                if (ct.file->dev_file) {
-                    AURON_CHECK(start >= 0 && (size_t)(start + len) <= ct.file->dev_file->host.size(), "column chunk outside the file image");
-                    ct.host = ct.file->dev_file->host.data() + start;
-                    ct.dev = P<uint8_t>(ct.file->dev_file->dev) + start;
+        // chunk placement: HBM-resident images in place, host files into one pinned staging buffer + one device buffer
+        for (auto& ct : p.tasks) {
+            int64_t start = ct.cm->start_offset(), len = ct.cm->total_compressed;
+            if (ct.file->dev_file) {
+                AURON_CHECK(start >= 0 && (size_t)(start + len) <= ct.file->dev_file->host.size(), "column chunk outside the file image");
+                ct.host = ct.file->dev_file->host.data() + start;
+                ct.dev = P<uint8_t>(ct.file->dev_file->dev) + start;
+            } else {
+                ct.dev_off = p.dev_bytes;
+                p.dev_bytes += (len + 63) & ~(int64_t)63;
+                if (ct.file->host_file.ptr) {
+                    AURON_CHECK(start >= 0 && (size_t)(start + len) <= ct.file->host_file.len, "column chunk outside the host image");
+                    ct.host = ct.file->host_file.ptr + start;
                 } else {
-                    ct.stage_off = stage_bytes;
-                    stage_bytes += (len + 63) & ~(int64_t)63;
+                    ct.stage_off = p.stage_bytes;
+                    p.stage_bytes += (len + 63) & ~(int64_t)63;
                 }
             }
-            if (stage_bytes > 0) {
-                uint8_t* st = (uint8_t*)staging((size_t)stage_bytes + 64);
-                bool via_callback = t.cb && t.cb->read_fully;
-                Buf d = dalloc(t.ctx, (size_t)stage_bytes + 64);
-                const int device = t.ctx.device;
-                cudaStream_t stream = t.ctx.stream;
-                // callbacks re-enter the host runtime (JVM / Python): keep those reads on this thread.  Each chunk is
-                // uploaded as soon as its read completes, so page-cache reads and H2D copies overlap.
-                parallel_for(tasks.size(), via_callback ? 1 : host_threads, [&](size_t i) {
-                    ChunkTask& ct = tasks[i];
-                    if (ct.stage_off < 0) return;
-                    int64_t start = ct.cm->start_offset(), len = ct.cm->total_compressed;
+        }
+        if (p.dev_bytes > 0) {
+            if (p.stage_bytes > 0) p.pinned = pinned_pool().get((size_t)p.stage_bytes + 64, &p.pinned_cap);
+            p.dev = dalloc(t.ctx, (size_t)p.dev_bytes + 64);
+            CUDA_OK(cudaEventCreateWithFlags(&p.alloc_ready, cudaEventDisableTiming));
+            CUDA_OK(cudaEventCreateWithFlags(&p.copied, cudaEventDisableTiming));
+            CUDA_OK(cudaEventRecord(p.alloc_ready, t.ctx.stream));
+            if (!copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+            for (auto& ct : p.tasks)
+                if (ct.dev_off >= 0) {
+                    if (ct.stage_off >= 0) ct.host = (uint8_t*)p.pinned + ct.stage_off;
+                    ct.dev = P<uint8_t>(p.dev) + ct.dev_off;
+                    p.cols[ct.col].keep.push_back(p.dev);
+                }
+        }
+        return pp;
+    }
+
+    // steps 2 + 3; runs on a background thread unless reads go through a host callback
+    void fetch_and_parse(Task& t, Prepared& p) {
+        auto t0 = std::chrono::steady_clock::now();
+        const bool via_callback = t.cb && t.cb->read_fully;
+        if (p.dev_bytes > 0) {
+            const int device = t.ctx.device;
+            cudaSetDevice(device);
+            CUDA_OK(cudaStreamWaitEvent(copy_stream, p.alloc_ready, 0));
+            cudaStream_t cs = copy_stream;
+            parallel_for(p.tasks.size(), via_callback ? 1 : host_threads, [&](size_t i) {
+                ChunkTask& ct = p.tasks[i];
+                if (ct.dev_off < 0) return;
+                int64_t start = ct.cm->start_offset(), len = ct.cm->total_compressed;
+                uint8_t* dst = const_cast<uint8_t*>(ct.host);
+                if (ct.stage_off >= 0) {   // not resident anywhere: read into the pinned staging buffer first
                     if (via_callback) {
-                        read_at(t, *ct.file, start, st + ct.stage_off, len);
+                        read_at(t, *ct.file, start, dst, len);
                     } else {
-                        cudaSetDevice(device);
                         int fd = open(ct.file->spec.path.c_str(), O_RDONLY);   // own descriptor per worker read
                         AURON_CHECK(fd >= 0, "cannot open " + ct.file->spec.path);
                         int64_t done = 0;
                         while (done < len) {
-                            ssize_t r = pread(fd, st + ct.stage_off + done, (size_t)(len - done), start + done);
+                            ssize_t r = pread(fd, dst + done, (size_t)(len - done), start + done);
                             if (r <= 0) {
                                 close(fd);
                                 fail("short read on " + ct.file->spec.path);
@@ -614,65 +687,114 @@ struct ParquetScanExec : Operator {
                         }
                         close(fd);
                     }
-                    cudaError_t e = cudaMemcpyAsync(P<uint8_t>(d) + ct.stage_off, st + ct.stage_off, (size_t)len, cudaMemcpyHostToDevice, stream);
-                    if (e != cudaSuccess) fail(std::string("H2D copy failed: ") + cudaGetErrorString(e));
-                });
-                metrics.add("h2d_bytes", stage_bytes);
-                for (auto& ct : tasks)
-                    if (ct.stage_off >= 0) {
-                        ct.host = st + ct.stage_off;
-                        ct.dev = P<uint8_t>(d) + ct.stage_off;
-                        cols[ct.col].keep.push_back(d);
-                    }
-            }
+                }
+                // upload each chunk as soon as its bytes are in host memory: reads and H2D copies overlap
+                cudaSetDevice(device);
+                cudaError_t e = cudaMemcpyAsync(const_cast<uint8_t*>(ct.dev), ct.host, (size_t)len, cudaMemcpyHostToDevice, cs);
+                if (e != cudaSuccess) fail(std::string("H2D copy failed: ") + cudaGetErrorString(e));
+            });
+            CUDA_OK(cudaEventRecord(p.copied, copy_stream));
         }
-        // ---- 3. parse page headers in parallel (overlaps the H2D copy above)
+        auto t1 = std::chrono::steady_clock::now();
+        parallel_for(p.tasks.size(), host_threads, [&](size_t i) { parse_chunk(p.tasks[i], p.cols[p.tasks[i].col].el, p.cols[p.tasks[i].col].is_string); });
+        auto t2 = std::chrono::steady_clock::now();
+        p.fetch_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
+        p.parse_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(t2 - t1).count();
+    }
+    void start(Task& t, Prepared& p) {
+        const bool via_callback = t.cb && t.cb->read_fully;
+        if (via_callback || getenv("AURON_SCAN_NO_PREFETCH")) {   // callbacks re-enter the host runtime: stay on the task thread
+            fetch_and_parse(t, p);
+            return;
+        }
+        p.th = std::thread([this, &t, &p] {
+            try {
+                fetch_and_parse(t, p);
+            } catch (const std::exception& e) {
+                p.err = e.what();
+            } catch (...) {
+                p.err = "unknown failure in the scan prefetch thread";
+            }
+        });
+    }
+
+    ~ParquetScanExec() override {
+        if (pending) release(*pending);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+    }
+
+    BatchPtr next(Task& t) override {
+        OpTimer timer(metrics, "elapsed_ns");
+        if (!pending) {
+            pending = plan_batch(t);
+            if (!pending) return nullptr;
+            start(t, *pending);
+        }
+        std::unique_ptr<Prepared> ready = std::move(pending);
         {
-            OpTimer tp(metrics, "parse_ns");
-            parallel_for(tasks.size(), host_threads, [&](size_t i) { parse_chunk(tasks[i], cols[tasks[i].col].el, cols[tasks[i].col].is_string); });
-            // ordered merge, rebasing dictionary ids / value-table positions; compressed chunks upload their payloads first
-            for (auto& ct : tasks) {
-                ColState& cs = cols[ct.col];
-                ChunkPages& cp = ct.out;
-                if (!cp.unc.empty()) {
-                    Buf d = to_device(t.ctx, cp.unc.data(), cp.unc.size());
-                    t.ctx.sync();
-                    cs.keep.push_back(d);
-                    const uint8_t* base = P<uint8_t>(d);
-                    for (auto& fx : cp.fixes) {
-                        if (fx.page == SIZE_MAX) {
-                            cp.dicts[fx.dict].data = base + fx.off;
-                            if (fx.sec != SIZE_MAX) cp.secs[fx.sec].ptr = base + fx.off;
-                        } else {
-                            PqPage& pg = cp.pages[fx.page];
-                            pg.def_ptr = pg.def_len ? base + fx.off + (intptr_t)pg.def_ptr : nullptr;
-                            intptr_t vo = (intptr_t)pg.val_ptr;
-                            pg.val_ptr = base + fx.off + vo;
-                            if (fx.sec != SIZE_MAX) cp.secs[fx.sec].ptr = pg.val_ptr;
-                        }
+            OpTimer tw(metrics, "wait_fetch_ns");
+            if (ready->th.joinable()) ready->th.join();
+        }
+        if (!ready->err.empty()) {
+            std::string e = ready->err;
+            release(*ready);
+            fail(e);
+        }
+        metrics.add("fetch_ns", ready->fetch_ns);
+        metrics.add("parse_ns", ready->parse_ns);
+        if (ready->dev_bytes) {
+            metrics.add("h2d_bytes", ready->dev_bytes);
+            CUDA_OK(cudaStreamWaitEvent(t.ctx.stream, ready->copied, 0));
+        }
+        // kick off the next batch before decoding this one
+        pending = plan_batch(t);
+        if (pending) start(t, *pending);
+        Prepared& p = *ready;
+        // ordered merge, rebasing dictionary ids / value-table positions; compressed chunks upload their payloads first
+        for (auto& ct : p.tasks) {
+            ColState& cs = p.cols[ct.col];
+            ChunkPages& cp = ct.out;
+            if (!cp.unc.empty()) {
+                Buf d = to_device(t.ctx, cp.unc.data(), cp.unc.size());
+                t.ctx.sync();
+                cs.keep.push_back(d);
+                const uint8_t* base = P<uint8_t>(d);
+                for (auto& fx : cp.fixes) {
+                    if (fx.page == SIZE_MAX) {
+                        cp.dicts[fx.dict].data = base + fx.off;
+                        if (fx.sec != SIZE_MAX) cp.secs[fx.sec].ptr = base + fx.off;
+                    } else {
+                        PqPage& pg = cp.pages[fx.page];
+                        pg.def_ptr = pg.def_len ? base + fx.off + (intptr_t)pg.def_ptr : nullptr;
+                        intptr_t vo = (intptr_t)pg.val_ptr;
+                        pg.val_ptr = base + fx.off + vo;
+                        if (fx.sec != SIZE_MAX) cp.secs[fx.sec].ptr = pg.val_ptr;
                     }
                 }
-                int dict_base = (int)cs.dicts.size();
-                int32_t vbase = (int32_t)cs.value_table_size;
-                for (auto d : cp.dicts) {
-                    d.value_base += vbase;
-                    cs.dicts.push_back(d);
-                }
-                for (auto s : cp.secs) {
-                    s.value_base += vbase;
-                    cs.secs.push_back(s);
-                }
-                for (auto pg : cp.pages) {
-                    if (pg.dict_id >= 0) pg.dict_id += dict_base;
-                    pg.plain_value_base += vbase;
-                    cs.pages.push_back(pg);
-                }
-                cs.value_table_size += cp.value_table_size;
             }
+            int dict_base = (int)cs.dicts.size();
+            int32_t vbase = (int32_t)cs.value_table_size;
+            for (auto d : cp.dicts) {
+                d.value_base += vbase;
+                cs.dicts.push_back(d);
+            }
+            for (auto s : cp.secs) {
+                s.value_base += vbase;
+                cs.secs.push_back(s);
+            }
+            for (auto pg : cp.pages) {
+                if (pg.dict_id >= 0) pg.dict_id += dict_base;
+                pg.plain_value_base += vbase;
+                cs.pages.push_back(pg);
+            }
+            cs.value_table_size += cp.value_table_size;
         }
-        // ---- 4. decode
-        OpTimer timer2(metrics, "decode_ns");
-        BatchPtr b = build_batch(t, cols, rows);
+        BatchPtr b;
+        {
+            OpTimer timer2(metrics, "decode_ns");
+            b = build_batch(t, p.cols, p.rows);
+        }
+        release(p);
         metrics.add("output_rows", b->num_rows);
         return b;
     }

@@ -65,6 +65,9 @@ def lib():
         L.auron_b200_put_device_file.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int]
         L.auron_b200_drop_device_file.argtypes = [C.c_char_p]
         L.auron_b200_drop_device_file.restype = None
+        L.auron_b200_put_host_file.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t]
+        L.auron_b200_drop_host_file.argtypes = [C.c_char_p]
+        L.auron_b200_drop_host_file.restype = None
         L.auron_b200_k_hash.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
         L.auron_b200_k_partition_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int]
         L.auron_b200_kernel_launches.restype = C.c_int64
@@ -77,7 +80,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "auron_b200_call_native", "auron_b200_schema", "auron_b200_next_batch", "auron_b200_finalize_native", "auron_b200_on_exit",
     "auron_b200_last_error", "auron_b200_metrics", "auron_b200_put_device_batch", "auron_b200_drop_device_resource", "auron_b200_k_hash",
-    "auron_b200_put_device_file", "auron_b200_drop_device_file", "auron_b200_nccl_unique_id", "auron_b200_nccl_init", "auron_b200_nccl_finalize",
+    "auron_b200_put_device_file", "auron_b200_drop_device_file", "auron_b200_put_host_file", "auron_b200_drop_host_file", "auron_b200_nccl_unique_id", "auron_b200_nccl_init", "auron_b200_nccl_finalize",
     "auron_b200_k_partition_ids", "auron_b200_kernel_launches", "auron_b200_time_kernel",
 ]
 
@@ -218,6 +221,29 @@ def put_device_file(path: str, data, device: int = 0):
     arr = np.frombuffer(data, dtype=np.uint8)
     if lib().auron_b200_put_device_file(path.encode(), arr.ctypes.data, arr.nbytes, device) != 0:
         raise AuronError(_err())
+
+
+_host_files = {}
+
+
+def put_host_file(path: str, buf):
+    """Register a host-resident image of `path` (a uint8 torch tensor — pin it for full PCIe rate — or a numpy array).
+    The buffer is kept alive until drop_host_file."""
+    if hasattr(buf, "data_ptr"):
+        ptr, n = buf.data_ptr(), buf.numel() * buf.element_size()
+    else:
+        import numpy as np
+
+        buf = np.ascontiguousarray(np.frombuffer(buf, dtype=np.uint8)) if not isinstance(buf, np.ndarray) else buf
+        ptr, n = buf.ctypes.data, buf.nbytes
+    if lib().auron_b200_put_host_file(path.encode(), ptr, n) != 0:
+        raise AuronError(_err())
+    _host_files[path] = buf
+
+
+def drop_host_file(path: str):
+    lib().auron_b200_drop_host_file(path.encode())
+    _host_files.pop(path, None)
 
 
 def drop_device_file(path: str):

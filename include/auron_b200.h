@@ -77,6 +77,12 @@ void auron_b200_drop_device_resource(const char* resource_id);
  * PartitionedFile.path equals `path` then decodes page payloads in place (no host transfer, no IO). */
 int auron_b200_put_device_file(const char* path, const uint8_t* bytes, size_t len, int device);
 void auron_b200_drop_device_file(const char* path);
+/* Host-resident file image (the JVM side already holds the file in a direct / pinned buffer, e.g. a cached block):
+ * the scan uploads the projected column chunks straight from `bytes` (cudaMemcpyAsync per chunk, no read_fully /
+ * pread round trip).  `bytes` stays owned by the caller and must outlive every task that scans `path`; pinned
+ * memory gives full PCIe rate, pageable memory works but is staged by the driver. */
+int auron_b200_put_host_file(const char* path, const uint8_t* bytes, size_t len);
+void auron_b200_drop_host_file(const char* path);
 
 /* ---- in-box repartition over NVLink (no counterpart in the reference, which shuffles through Spark's block manager:
  * datafusion-ext-plans/src/shuffle/ and ipc_reader_exec.rs).  One process per GPU; rank 0 creates the id, the host
