@@ -122,7 +122,12 @@ struct Ctx {
     explicit Ctx(int dev = 0);
     ~Ctx();
     Ctx(const Ctx&) = delete;
-    void sync() { CUDA_OK(cudaStreamSynchronize(stream)); }
+    void sync();   // cudaStreamSynchronize + recycles the staged-upload arena
+    // Small host->device uploads (descriptor tables, page lists) do not go through the copy engine: they are staged
+    // in this pinned, device-mapped arena and moved by a tiny kernel on the task stream.  A copy-engine transfer
+    // would queue FIFO behind bulk H2D traffic of the scan's prefetch stream (measured: +4..14 ms per batch).
+    uint8_t* stage_host = nullptr;
+    size_t stage_cap = 0, stage_off = 0;
 
     // Optional per-kernel device timing (AURON_PROFILE=1): CUDA events recorded on this stream around named
     // launch sites; bench.py reads the totals through auron_b200_metrics ("__kernels__" pseudo operator).
@@ -172,6 +177,7 @@ Buf dalloc(Ctx& ctx, size_t bytes);                  // uninitialised, padded (+
 Buf dalloc_zero(Ctx& ctx, size_t bytes);
 Buf dalloc_fill(Ctx& ctx, size_t bytes, int byte);   // memset
 Buf to_device(Ctx& ctx, const void* host, size_t bytes);
+void upload_small(Ctx& ctx, void* dev, const void* host, size_t bytes);   // 16-byte aligned `dev`, <= 4 MB: staged + kernel, else copy engine
 void to_host(Ctx& ctx, void* host, const void* dev, size_t bytes);   // synchronises
 template <typename T>
 inline T* P(const Buf& b) { return b ? static_cast<T*>(b->ptr) : nullptr; }

@@ -2,6 +2,9 @@
 // (take), concat.  These are the HBM-bound building blocks every operator composes; the gather is
 // the device counterpart of datafusion-ext-commons/src/arrow/selection.rs:32-304 (take/interleave)
 // and arrow-select filter (cached_exprs_evaluator.rs:131).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "device_utils.cuh"
@@ -33,9 +36,7 @@ std::string DType::str() const {
 Ctx::Ctx(int dev) : device(dev) {
     CUDA_OK(cudaSetDevice(dev));
     CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    cudaDeviceProp prop;
-    CUDA_OK(cudaGetDeviceProperties(&prop, dev));
-    sm_count = prop.multiProcessorCount;
+    CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     if (const char* e = getenv("AURON_PROFILE")) profile = atoi(e) != 0;
     if (const char* e = getenv("AURON_GPU_CHUNK_ROWS")) {   // device-side accumulation target (tests shrink it to force merges)
         long long v = atoll(e);
@@ -72,6 +73,19 @@ std::vector<Ctx::ProfTotal> Ctx::prof_summary() {
     prof.clear();
     return out;
 }
+static void stage_arena_put(uint8_t* p);
+static const bool g_stall_log = getenv("AURON_STALL_LOG") != nullptr;   // report host-side stalls of allocator / sync calls
+void Ctx::sync() {
+    if (g_stall_log) {
+        auto t0 = std::chrono::steady_clock::now();
+        CUDA_OK(cudaStreamSynchronize(stream));
+        double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > 40.0) fprintf(stderr, "[stall] stream sync took %.1f ms\n", ms);
+    } else {
+        CUDA_OK(cudaStreamSynchronize(stream));
+    }
+    stage_off = 0;   // every staged upload kernel has run
+}
 Ctx::~Ctx() {
     for (auto& e : prof) {
         cudaEventDestroy(e.e0);
@@ -81,16 +95,33 @@ Ctx::~Ctx() {
         cudaStreamSynchronize(stream);
         cudaStreamDestroy(stream);
     }
+    if (stage_host) stage_arena_put(stage_host);
 }
 
 DevMem::~DevMem() {
-    if (ptr) cudaFreeAsync(ptr, stream);
+    if (!ptr) return;
+    if (g_stall_log) {
+        auto t0 = std::chrono::steady_clock::now();
+        cudaFreeAsync(ptr, stream);
+        double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > 2.0) fprintf(stderr, "[stall] cudaFreeAsync(%zu) took %.1f ms\n", bytes, ms);
+        return;
+    }
+    cudaFreeAsync(ptr, stream);
 }
 
+// AURON_STALL_LOG=1: report allocator calls that take longer than 2 ms on the host (pool growth shows up here)
 Buf dalloc(Ctx& ctx, size_t bytes) {
     auto m = std::make_shared<DevMem>();
     m->bytes = bytes;
     m->stream = ctx.stream;
+    if (g_stall_log) {
+        auto t0 = std::chrono::steady_clock::now();
+        CUDA_OK(cudaMallocAsync(&m->ptr, bytes + 64, ctx.stream));
+        double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > 2.0) fprintf(stderr, "[stall] cudaMallocAsync(%zu) took %.1f ms\n", bytes, ms);
+        return m;
+    }
     CUDA_OK(cudaMallocAsync(&m->ptr, bytes + 64, ctx.stream));
     return m;
 }
@@ -100,9 +131,54 @@ Buf dalloc_fill(Ctx& ctx, size_t bytes, int byte) {
     return b;
 }
 Buf dalloc_zero(Ctx& ctx, size_t bytes) { return dalloc_fill(ctx, bytes, 0); }
+// ---- staged small uploads (see Ctx::stage_host)
+static const size_t kStageArena = 16u << 20, kStageMax = 4u << 20;
+static std::mutex g_stage_mu;
+static std::vector<uint8_t*> g_stage_free;
+static uint8_t* stage_arena_get() {
+    {
+        std::lock_guard<std::mutex> l(g_stage_mu);
+        if (!g_stage_free.empty()) {
+            uint8_t* p = g_stage_free.back();
+            g_stage_free.pop_back();
+            return p;
+        }
+    }
+    void* p = nullptr;
+    CUDA_OK(cudaHostAlloc(&p, kStageArena, cudaHostAllocMapped | cudaHostAllocPortable));
+    return (uint8_t*)p;
+}
+static void stage_arena_put(uint8_t* p) {
+    std::lock_guard<std::mutex> l(g_stage_mu);
+    g_stage_free.push_back(p);
+}
+__global__ void staged_upload_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n16) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+void upload_small(Ctx& ctx, void* dev, const void* host, size_t bytes) {
+    if (bytes == 0) return;
+    size_t padded = (bytes + 15) & ~(size_t)15;
+    if (padded > kStageMax || ((uintptr_t)dev & 15)) {   // bulk or oddly placed: plain copy-engine transfer
+        CUDA_OK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx.stream));
+        return;
+    }
+    if (!ctx.stage_host) {
+        ctx.stage_host = stage_arena_get();
+        ctx.stage_cap = kStageArena;
+        ctx.stage_off = 0;
+    }
+    if (ctx.stage_off + padded > ctx.stage_cap) ctx.sync();
+    uint8_t* st = ctx.stage_host + ctx.stage_off;
+    memcpy(st, host, bytes);
+    ctx.stage_off += padded;
+    size_t n16 = padded / 16;
+    int blocks = (int)std::min<size_t>((n16 + 255) / 256, (size_t)ctx.sm_count * 4);
+    staged_upload_kernel<<<blocks, 256, 0, ctx.stream>>>((uint4*)dev, (const uint4*)st, n16);
+    CUDA_OK(cudaGetLastError());
+}
 Buf to_device(Ctx& ctx, const void* host, size_t bytes) {
-    Buf b = dalloc(ctx, bytes);
-    if (bytes) CUDA_OK(cudaMemcpyAsync(b->ptr, host, bytes, cudaMemcpyHostToDevice, ctx.stream));
+    Buf b = dalloc(ctx, bytes);   // allocations are padded by 64 B, so the 16-byte rounding of the staged copy stays inside
+    upload_small(ctx, b->ptr, host, bytes);
     return b;
 }
 void to_host(Ctx& ctx, void* host, const void* dev, size_t bytes) {

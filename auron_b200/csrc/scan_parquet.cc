@@ -16,6 +16,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <thread>
 
@@ -547,9 +549,10 @@ struct ParquetScanExec : Operator {
         return out;
     }
 
-    // ---- batch pipeline: plan (main thread) -> fetch + parse (background thread, copy stream) -> merge + decode (main thread).
-    // While the GPU decodes batch k and the downstream operators consume it, batch k+1 is already being read, uploaded
-    // and parsed, so the PCIe transfer of the e2e path hides behind compute.
+    // ---- batch pipeline: a producer thread plans, reads, uploads (copy stream) and parses up to `prefetch_depth`
+    // batches ahead; the task thread merges + decodes them on the task stream.  While the GPU decodes batch k and the
+    // downstream operators consume it, later batches are already crossing PCIe, so the e2e transfer hides behind
+    // compute and the copy engine never waits for the task thread.
     struct Prepared {
         std::vector<ColState> cols;
         std::vector<ChunkTask> tasks;
@@ -557,21 +560,32 @@ struct ParquetScanExec : Operator {
         void* pinned = nullptr;
         size_t pinned_cap = 0;
         Buf dev;
-        cudaEvent_t alloc_ready = nullptr, copied = nullptr;
-        std::thread th;
-        std::string err;
+        cudaEvent_t copied = nullptr, copy_begin = nullptr;
         int64_t fetch_ns = 0, parse_ns = 0;
     };
-    std::unique_ptr<Prepared> pending;
     cudaStream_t copy_stream = nullptr;
+    int prefetch_depth = 3;
+    std::thread producer;
+    std::mutex qmu;
+    std::condition_variable qcv;
+    std::deque<std::unique_ptr<Prepared>> ready_q;
+    bool producer_started = false, producer_done = false, stop_producer = false;
+    std::string producer_err;
+    // AURON_SCAN_TIMELINE=1 (with AURON_PROFILE=1): device-side timeline of every batch, printed when the scan ends
+    struct TimelineRow {
+        float copy0, copy1, dec0, dec1;
+        int64_t rows;
+    };
+    std::vector<TimelineRow> timeline;
+    cudaEvent_t tl_base = nullptr;
+    bool want_timeline = getenv("AURON_SCAN_TIMELINE") != nullptr;
 
     void release(Prepared& p) {
-        if (p.th.joinable()) p.th.join();
         if (p.pinned) pinned_pool().put(p.pinned, p.pinned_cap);
         p.pinned = nullptr;
-        if (p.alloc_ready) cudaEventDestroy(p.alloc_ready);
         if (p.copied) cudaEventDestroy(p.copied);
-        p.alloc_ready = p.copied = nullptr;
+        if (p.copy_begin) cudaEventDestroy(p.copy_begin);
+        p.copied = p.copy_begin = nullptr;
     }
 
     std::unique_ptr<Prepared> plan_batch(Task& t) {
@@ -590,7 +604,6 @@ struct ParquetScanExec : Operator {
             const auto& rg = cur->meta.row_groups[cur->row_groups[rg_pos]];
             std::string sig = signature(*cur);
             if (started && (sig != batch_sig || p.rows + rg.num_rows > t.ctx.gpu_chunk_rows)) break;
-            AURON_CHECK(t.is_running(), "task killed");
             if (!started) {
                 started = true;
                 batch_sig = sig;
@@ -641,11 +654,14 @@ struct ParquetScanExec : Operator {
         }
         if (p.dev_bytes > 0) {
             if (p.stage_bytes > 0) p.pinned = pinned_pool().get((size_t)p.stage_bytes + 64, &p.pinned_cap);
-            p.dev = dalloc(t.ctx, (size_t)p.dev_bytes + 64);
-            CUDA_OK(cudaEventCreateWithFlags(&p.alloc_ready, cudaEventDisableTiming));
-            CUDA_OK(cudaEventCreateWithFlags(&p.copied, cudaEventDisableTiming));
-            CUDA_OK(cudaEventRecord(p.alloc_ready, t.ctx.stream));
+            // allocated in copy-stream order (the uploads follow on that stream), freed in task-stream order after decode
             if (!copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+            p.dev = std::make_shared<DevMem>();
+            p.dev->bytes = (size_t)p.dev_bytes + 64;
+            p.dev->stream = t.ctx.stream;
+            CUDA_OK(cudaMallocAsync(&p.dev->ptr, p.dev->bytes + 64, copy_stream));
+            CUDA_OK(cudaEventCreateWithFlags(&p.copied, t.ctx.profile ? cudaEventDefault : cudaEventDisableTiming));
+            if (t.ctx.profile) CUDA_OK(cudaEventCreate(&p.copy_begin));
             for (auto& ct : p.tasks)
                 if (ct.dev_off >= 0) {
                     if (ct.stage_off >= 0) ct.host = (uint8_t*)p.pinned + ct.stage_off;
@@ -656,41 +672,56 @@ struct ParquetScanExec : Operator {
         return pp;
     }
 
-    // steps 2 + 3; runs on a background thread unless reads go through a host callback
+    // read + upload + parse one planned batch
     void fetch_and_parse(Task& t, Prepared& p) {
         auto t0 = std::chrono::steady_clock::now();
         const bool via_callback = t.cb && t.cb->read_fully;
         if (p.dev_bytes > 0) {
             const int device = t.ctx.device;
             cudaSetDevice(device);
-            CUDA_OK(cudaStreamWaitEvent(copy_stream, p.alloc_ready, 0));
             cudaStream_t cs = copy_stream;
-            parallel_for(p.tasks.size(), via_callback ? 1 : host_threads, [&](size_t i) {
-                ChunkTask& ct = p.tasks[i];
-                if (ct.dev_off < 0) return;
-                int64_t start = ct.cm->start_offset(), len = ct.cm->total_compressed;
-                uint8_t* dst = const_cast<uint8_t*>(ct.host);
-                if (ct.stage_off >= 0) {   // not resident anywhere: read into the pinned staging buffer first
-                    if (via_callback) {
-                        read_at(t, *ct.file, start, dst, len);
-                    } else {
-                        int fd = open(ct.file->spec.path.c_str(), O_RDONLY);   // own descriptor per worker read
-                        AURON_CHECK(fd >= 0, "cannot open " + ct.file->spec.path);
-                        int64_t done = 0;
-                        while (done < len) {
-                            ssize_t r = pread(fd, dst + done, (size_t)(len - done), start + done);
-                            if (r <= 0) {
-                                close(fd);
-                                fail("short read on " + ct.file->spec.path);
-                            }
-                            done += r;
-                        }
-                        close(fd);
-                    }
+            if (p.copy_begin) CUDA_OK(cudaEventRecord(p.copy_begin, cs));
+            // chunks that already sit in a host image need no worker: issue their uploads right away, in order
+            for (auto& ct : p.tasks)
+                if (ct.dev_off >= 0 && ct.stage_off < 0)
+                    CUDA_OK(cudaMemcpyAsync(const_cast<uint8_t*>(ct.dev), ct.host, (size_t)ct.cm->total_compressed, cudaMemcpyHostToDevice, cs));
+            // everything else is read in 4 MB slices by the worker pool (a batch may hold fewer column chunks than
+            // workers); each slice is uploaded as soon as its bytes are in the pinned staging buffer
+            struct Slice {
+                ChunkTask* ct;
+                int64_t off, len;
+            };
+            std::vector<Slice> slices;
+            const int64_t kSlice = via_callback ? INT64_MAX : (4 << 20);
+            if (p.stage_bytes > 0)
+                for (auto& ct : p.tasks) {
+                    if (ct.dev_off < 0 || ct.stage_off < 0) continue;
+                    for (int64_t o = 0; o < ct.cm->total_compressed; o += std::min(kSlice, ct.cm->total_compressed - o))
+                        slices.push_back(Slice{&ct, o, std::min(kSlice, ct.cm->total_compressed - o)});
                 }
-                // upload each chunk as soon as its bytes are in host memory: reads and H2D copies overlap
+            parallel_for(slices.size(), via_callback ? 1 : host_threads, [&](size_t i) {
+                const Slice& sl = slices[i];
+                ChunkTask& ct = *sl.ct;
+                int64_t start = ct.cm->start_offset() + sl.off, len = sl.len;
+                uint8_t* dst = const_cast<uint8_t*>(ct.host) + sl.off;
+                if (via_callback) {
+                    read_at(t, *ct.file, start, dst, len);
+                } else {
+                    int fd = open(ct.file->spec.path.c_str(), O_RDONLY);   // own descriptor per worker read
+                    AURON_CHECK(fd >= 0, "cannot open " + ct.file->spec.path);
+                    int64_t done = 0;
+                    while (done < len) {
+                        ssize_t r = pread(fd, dst + done, (size_t)(len - done), start + done);
+                        if (r <= 0) {
+                            close(fd);
+                            fail("short read on " + ct.file->spec.path);
+                        }
+                        done += r;
+                    }
+                    close(fd);
+                }
                 cudaSetDevice(device);
-                cudaError_t e = cudaMemcpyAsync(const_cast<uint8_t*>(ct.dev), ct.host, (size_t)len, cudaMemcpyHostToDevice, cs);
+                cudaError_t e = cudaMemcpyAsync(const_cast<uint8_t*>(ct.dev) + sl.off, dst, (size_t)len, cudaMemcpyHostToDevice, cs);
                 if (e != cudaSuccess) fail(std::string("H2D copy failed: ") + cudaGetErrorString(e));
             });
             CUDA_OK(cudaEventRecord(p.copied, copy_stream));
@@ -701,54 +732,129 @@ struct ParquetScanExec : Operator {
         p.fetch_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count();
         p.parse_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(t2 - t1).count();
     }
-    void start(Task& t, Prepared& p) {
-        const bool via_callback = t.cb && t.cb->read_fully;
-        if (via_callback || getenv("AURON_SCAN_NO_PREFETCH")) {   // callbacks re-enter the host runtime: stay on the task thread
-            fetch_and_parse(t, p);
-            return;
-        }
-        p.th = std::thread([this, &t, &p] {
-            try {
-                fetch_and_parse(t, p);
-            } catch (const std::exception& e) {
-                p.err = e.what();
-            } catch (...) {
-                p.err = "unknown failure in the scan prefetch thread";
+    void producer_loop(Task& t) {
+        try {
+            CUDA_OK(cudaSetDevice(t.ctx.device));
+            for (;;) {
+                {
+                    std::unique_lock<std::mutex> l(qmu);
+                    qcv.wait(l, [&] { return stop_producer || (int)ready_q.size() < prefetch_depth; });
+                    if (stop_producer) break;
+                }
+                auto p = plan_batch(t);
+                if (!p) break;
+                try {
+                    fetch_and_parse(t, *p);
+                } catch (...) {
+                    release(*p);
+                    throw;
+                }
+                std::lock_guard<std::mutex> l(qmu);
+                ready_q.push_back(std::move(p));
+                qcv.notify_all();
             }
-        });
+        } catch (const std::exception& e) {
+            std::lock_guard<std::mutex> l(qmu);
+            producer_err = e.what();
+        } catch (...) {
+            std::lock_guard<std::mutex> l(qmu);
+            producer_err = "unknown failure in the scan prefetch thread";
+        }
+        std::lock_guard<std::mutex> l(qmu);
+        producer_done = true;
+        qcv.notify_all();
+    }
+    void stop() {
+        if (producer.joinable()) {
+            {
+                std::lock_guard<std::mutex> l(qmu);
+                stop_producer = true;
+                qcv.notify_all();
+            }
+            producer.join();
+        }
+        for (auto& p : ready_q) release(*p);
+        ready_q.clear();
     }
 
     ~ParquetScanExec() override {
-        if (pending) release(*pending);
-        if (copy_stream) cudaStreamDestroy(copy_stream);
+        stop();
+        if (copy_stream) {
+            cudaStreamSynchronize(copy_stream);
+            cudaStreamDestroy(copy_stream);
+        }
+    }
+
+    // next planned + fetched + parsed batch, or nullptr at the end of the scan
+    std::unique_ptr<Prepared> take_ready(Task& t) {
+        const bool via_callback = t.cb && t.cb->read_fully;
+        if (via_callback || prefetch_depth <= 0) {   // callbacks re-enter the host runtime: stay on the task thread
+            auto p = plan_batch(t);
+            if (p) {
+                try {
+                    fetch_and_parse(t, *p);
+                } catch (...) {
+                    release(*p);
+                    throw;
+                }
+            }
+            return p;
+        }
+        if (!producer_started) {
+            producer_started = true;
+            producer = std::thread([this, &t] { producer_loop(t); });
+        }
+        std::unique_lock<std::mutex> l(qmu);
+        qcv.wait(l, [&] { return !ready_q.empty() || producer_done; });
+        if (ready_q.empty()) {
+            if (!producer_err.empty()) fail(producer_err);
+            return nullptr;
+        }
+        auto p = std::move(ready_q.front());
+        ready_q.pop_front();
+        qcv.notify_all();
+        return p;
     }
 
     BatchPtr next(Task& t) override {
         OpTimer timer(metrics, "elapsed_ns");
-        if (!pending) {
-            pending = plan_batch(t);
-            if (!pending) return nullptr;
-            start(t, *pending);
-        }
-        std::unique_ptr<Prepared> ready = std::move(pending);
+        AURON_CHECK(t.is_running(), "task killed");
+        std::unique_ptr<Prepared> ready;
         {
             OpTimer tw(metrics, "wait_fetch_ns");
-            if (ready->th.joinable()) ready->th.join();
+            ready = take_ready(t);
         }
-        if (!ready->err.empty()) {
-            std::string e = ready->err;
-            release(*ready);
-            fail(e);
+        if (!ready) {
+            if (want_timeline && !timeline.empty()) {
+                for (size_t i = 0; i < timeline.size(); i++)
+                    fprintf(stderr, "[scan timeline] batch %zu rows=%lld  copy %.2f..%.2f ms  decode %.2f..%.2f ms\n", i, (long long)timeline[i].rows,
+                            timeline[i].copy0, timeline[i].copy1, timeline[i].dec0, timeline[i].dec1);
+                timeline.clear();
+            }
+            return nullptr;
         }
+        const bool tl = want_timeline && t.ctx.profile;
+        cudaEvent_t dec0 = nullptr, dec1 = nullptr;
+        if (tl && !tl_base) {
+            CUDA_OK(cudaEventCreate(&tl_base));
+            CUDA_OK(cudaEventRecord(tl_base, t.ctx.stream));
+        }
+        struct Releaser {
+            ParquetScanExec* op;
+            Prepared* p;
+            ~Releaser() { op->release(*p); }
+        } releaser{this, ready.get()};
         metrics.add("fetch_ns", ready->fetch_ns);
         metrics.add("parse_ns", ready->parse_ns);
         if (ready->dev_bytes) {
             metrics.add("h2d_bytes", ready->dev_bytes);
             CUDA_OK(cudaStreamWaitEvent(t.ctx.stream, ready->copied, 0));
         }
-        // kick off the next batch before decoding this one
-        pending = plan_batch(t);
-        if (pending) start(t, *pending);
+        if (tl) {
+            CUDA_OK(cudaEventCreate(&dec0));
+            CUDA_OK(cudaEventCreate(&dec1));
+            CUDA_OK(cudaEventRecord(dec0, t.ctx.stream));
+        }
         Prepared& p = *ready;
         // ordered merge, rebasing dictionary ids / value-table positions; compressed chunks upload their payloads first
         for (auto& ct : p.tasks) {
@@ -794,7 +900,26 @@ struct ParquetScanExec : Operator {
             OpTimer timer2(metrics, "decode_ns");
             b = build_batch(t, p.cols, p.rows);
         }
-        release(p);
+        if (p.copy_begin && p.copied) {
+            float ms = 0;
+            CUDA_OK(cudaEventSynchronize(p.copied));
+            CUDA_OK(cudaEventElapsedTime(&ms, p.copy_begin, p.copied));
+            metrics.add("h2d_device_us", (int64_t)(ms * 1000));
+        }
+        if (tl) {
+            CUDA_OK(cudaEventRecord(dec1, t.ctx.stream));
+            CUDA_OK(cudaEventSynchronize(dec1));
+            TimelineRow r{0, 0, 0, 0, p.rows};
+            if (p.copy_begin && p.copied) {
+                cudaEventElapsedTime(&r.copy0, tl_base, p.copy_begin);
+                cudaEventElapsedTime(&r.copy1, tl_base, p.copied);
+            }
+            cudaEventElapsedTime(&r.dec0, tl_base, dec0);
+            cudaEventElapsedTime(&r.dec1, tl_base, dec1);
+            timeline.push_back(r);
+            cudaEventDestroy(dec0);
+            cudaEventDestroy(dec1);
+        }
         metrics.add("output_rows", b->num_rows);
         return b;
     }
@@ -804,6 +929,8 @@ OperatorPtr make_parquet_scan(Task& t, const uint8_t* node, size_t n) {
     auto op = std::make_unique<ParquetScanExec>();
     op->name = "ParquetExec";
     op->host_threads = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    if (const char* e = getenv("AURON_SCAN_PREFETCH_DEPTH")) op->prefetch_depth = atoi(e);
+    if (getenv("AURON_SCAN_NO_PREFETCH")) op->prefetch_depth = 0;
     PbReader r(node, n);
     uint32_t f, w;
     while (r.next(&f, &w)) {

@@ -130,3 +130,19 @@ def test_scan_filter_aggregate_config2_small(tmp_path):
     finally:
         runtime.drop_device_file("hbm://store_sales")
     assert_same_rows(got2, exp)
+    # and with the file image handed over as a (pinned) host buffer, small device chunks so the prefetch pipeline runs
+    import torch
+
+    buf = torch.frombuffer(bytearray(data), dtype=torch.uint8).pin_memory()
+    runtime.put_host_file("pinned://store_sales", buf)
+    old = os.environ.get("AURON_GPU_CHUNK_ROWS")
+    os.environ["AURON_GPU_CHUNK_ROWS"] = "100000"
+    try:
+        got3 = run(plan("pinned://store_sales"), {})
+    finally:
+        runtime.drop_host_file("pinned://store_sales")
+        if old is None:
+            del os.environ["AURON_GPU_CHUNK_ROWS"]
+        else:
+            os.environ["AURON_GPU_CHUNK_ROWS"] = old
+    assert_same_rows(got3, exp)
