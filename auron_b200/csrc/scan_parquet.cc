@@ -18,6 +18,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <deque>
+#include <exception>
 #include <mutex>
 #include <thread>
 
@@ -226,6 +227,52 @@ struct ParquetScanExec : Operator {
             free_list.emplace_back(p, cap);
         }
     };
+    // Device-side landing buffers for encoded column chunks.  Plain cudaMalloc blocks recycled across batches and
+    // tasks: a stream-ordered allocation made by the producer thread on the copy stream contends with the task
+    // thread's own cudaMallocAsync calls inside the driver (measured: 115 KB allocations stalling for 5..155 ms).
+    struct DevStagePool {
+        std::mutex mu;
+        struct Blk {
+            void* p;
+            size_t cap;
+            int device;
+        };
+        std::vector<Blk> free_list;
+        void* get(size_t n, int device, size_t* cap) {
+            {
+                std::lock_guard<std::mutex> l(mu);
+                size_t best = SIZE_MAX;
+                for (size_t i = 0; i < free_list.size(); i++)
+                    if (free_list[i].device == device && free_list[i].cap >= n && (best == SIZE_MAX || free_list[i].cap < free_list[best].cap)) best = i;
+                if (best != SIZE_MAX) {
+                    Blk e = free_list[best];
+                    free_list.erase(free_list.begin() + best);
+                    *cap = e.cap;
+                    return e.p;
+                }
+            }
+            void* p = nullptr;
+            size_t c = std::max<size_t>(n + n / 8, 64 << 20);
+            CUDA_OK(cudaMalloc(&p, c));
+            *cap = c;
+            return p;
+        }
+        void put(void* p, size_t cap, int device) {
+            std::lock_guard<std::mutex> l(mu);
+            free_list.push_back(Blk{p, cap, device});
+            while (free_list.size() > 8) {   // keep the cache bounded: drop the smallest block
+                size_t worst = 0;
+                for (size_t i = 1; i < free_list.size(); i++)
+                    if (free_list[i].cap < free_list[worst].cap) worst = i;
+                cudaFree(free_list[worst].p);
+                free_list.erase(free_list.begin() + worst);
+            }
+        }
+    };
+    static DevStagePool& dev_stage_pool() {
+        static DevStagePool pool;
+        return pool;
+    }
     static PinnedPool& pinned_pool() {
         static PinnedPool pool;
         return pool;
@@ -559,7 +606,9 @@ struct ParquetScanExec : Operator {
         int64_t rows = 0, stage_bytes = 0, dev_bytes = 0;
         void* pinned = nullptr;
         size_t pinned_cap = 0;
-        Buf dev;
+        void* dev = nullptr;   // from dev_stage_pool()
+        size_t dev_cap = 0;
+        int device = 0;
         cudaEvent_t copied = nullptr, copy_begin = nullptr;
         int64_t fetch_ns = 0, parse_ns = 0;
     };
@@ -583,6 +632,13 @@ struct ParquetScanExec : Operator {
     void release(Prepared& p) {
         if (p.pinned) pinned_pool().put(p.pinned, p.pinned_cap);
         p.pinned = nullptr;
+        if (p.dev) {
+            // every reader of the landing buffer has finished on the normal path (build_batch ends with a stream sync);
+            // on error paths make sure the uploads themselves are done before the block is recycled
+            if (p.copied) cudaEventSynchronize(p.copied);
+            dev_stage_pool().put(p.dev, p.dev_cap, p.device);
+            p.dev = nullptr;
+        }
         if (p.copied) cudaEventDestroy(p.copied);
         if (p.copy_begin) cudaEventDestroy(p.copy_begin);
         p.copied = p.copy_begin = nullptr;
@@ -654,19 +710,15 @@ struct ParquetScanExec : Operator {
         }
         if (p.dev_bytes > 0) {
             if (p.stage_bytes > 0) p.pinned = pinned_pool().get((size_t)p.stage_bytes + 64, &p.pinned_cap);
-            // allocated in copy-stream order (the uploads follow on that stream), freed in task-stream order after decode
             if (!copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-            p.dev = std::make_shared<DevMem>();
-            p.dev->bytes = (size_t)p.dev_bytes + 64;
-            p.dev->stream = t.ctx.stream;
-            CUDA_OK(cudaMallocAsync(&p.dev->ptr, p.dev->bytes + 64, copy_stream));
+            p.device = t.ctx.device;
+            p.dev = dev_stage_pool().get((size_t)p.dev_bytes + 128, p.device, &p.dev_cap);
             CUDA_OK(cudaEventCreateWithFlags(&p.copied, t.ctx.profile ? cudaEventDefault : cudaEventDisableTiming));
             if (t.ctx.profile) CUDA_OK(cudaEventCreate(&p.copy_begin));
             for (auto& ct : p.tasks)
                 if (ct.dev_off >= 0) {
                     if (ct.stage_off >= 0) ct.host = (uint8_t*)p.pinned + ct.stage_off;
-                    ct.dev = P<uint8_t>(p.dev) + ct.dev_off;
-                    p.cols[ct.col].keep.push_back(p.dev);
+                    ct.dev = (const uint8_t*)p.dev + ct.dev_off;
                 }
         }
         return pp;
@@ -842,8 +894,13 @@ struct ParquetScanExec : Operator {
         struct Releaser {
             ParquetScanExec* op;
             Prepared* p;
-            ~Releaser() { op->release(*p); }
-        } releaser{this, ready.get()};
+            cudaStream_t st;
+            int exc;
+            ~Releaser() {
+                if (std::uncaught_exceptions() > exc) cudaStreamSynchronize(st);   // decode kernels may still read the landing buffer
+                op->release(*p);
+            }
+        } releaser{this, ready.get(), t.ctx.stream, std::uncaught_exceptions()};
         metrics.add("fetch_ns", ready->fetch_ns);
         metrics.add("parse_ns", ready->parse_ns);
         if (ready->dev_bytes) {
@@ -929,6 +986,7 @@ OperatorPtr make_parquet_scan(Task& t, const uint8_t* node, size_t n) {
     auto op = std::make_unique<ParquetScanExec>();
     op->name = "ParquetExec";
     op->host_threads = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    if (const char* e = getenv("AURON_SCAN_THREADS")) op->host_threads = (unsigned)std::max(1, atoi(e));
     if (const char* e = getenv("AURON_SCAN_PREFETCH_DEPTH")) op->prefetch_depth = atoi(e);
     if (getenv("AURON_SCAN_NO_PREFETCH")) op->prefetch_depth = 0;
     PbReader r(node, n);
