@@ -43,9 +43,13 @@ struct OpTimer {
 // A batch plus an optional pending row selection (a filter whose gather has not been materialised)
 struct SelBatch {
     BatchPtr batch;
-    Buf sel;          // int32 row indices into batch, or nullptr = all rows
-    int64_t n = 0;    // selected row count
+    Buf sel;          // int32 row indices into batch (materialised selection), or nullptr
+    Buf mask;         // pending selection as a bit mask over the batch rows (bits past num_rows are zero), or nullptr;
+                      // consumers that can skip rows themselves (hash aggregate) use it directly, others call ensure_sel()
+    int64_t n = 0;    // selected row count (== batch rows when neither sel nor mask is set)
 };
+struct Task;
+const int32_t* ensure_sel(Task& t, SelBatch& s);   // materialise mask -> indices if needed; nullptr = all rows
 
 // ExecutionPlan + RecordBatchStream in one object: execute() == first next()
 struct Operator {

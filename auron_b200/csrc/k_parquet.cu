@@ -315,7 +315,6 @@ __device__ __forceinline__ void bm_copy_bits(uint32_t* bm, int64_t r, const uint
         done += take;
     }
 }
-constexpr int LVL_WIN = 1024;
 __device__ inline void lvl_page_bits(const uint8_t* base, int len, int64_t rows, unsigned lane, uint32_t* bm, int (*exitT)[33], int* s_entry) {
     int64_t row_base = 0;
     int pos = 0;   // absolute byte offset of the next run header
@@ -638,16 +637,28 @@ __global__ void __launch_bounds__(PQ_WARPS * 32) pq_decode_tiles_fast_kernel(PqL
             if (idx.is_rle) {
                 for (int k = lane; k < t; k += 32) s_vals[wid][pos + k] = idx.rle_value;
             } else {
-                for (int k0 = lane; k0 < t; k0 += 128) {   // 4 independent unpacks in flight per lane
+                // lane L unpacks values L, L+32, ...: 32 values are exactly `bw` 32-bit words, so the word pointer
+                // advances by bw per step and the sub-word shift is a per-lane constant of the run
+                const int64_t bit0 = (int64_t)(idx.bp_consumed + (int)lane) * bw;
+                const uintptr_t qa = (uintptr_t)(idx.bp_base + (bit0 >> 3));
+                const uint32_t* wp = (const uint32_t*)(qa & ~(uintptr_t)3);
+                const unsigned sh = (unsigned)(qa & 3) * 8 + (unsigned)(bit0 & 7);
+                const uint32_t vmask = bw >= 32 ? 0xffffffffu : ((1u << bw) - 1u);
+                uint32_t* dst = &s_vals[wid][pos + (int)lane];
+                int k = lane;
+                for (; k + 96 < t; k += 128) {   // 4 independent unpacks in flight per lane
                     uint32_t v[4];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        int k = k0 + 32 * u;
-                        v[u] = k < t ? extract_bits(idx.bp_base, (int64_t)(idx.bp_consumed + k) * bw, bw) : 0u;
-                    }
+                    for (int u = 0; u < 4; u++) v[u] = __funnelshift_r(wp[u * bw], wp[u * bw + 1], sh) & vmask;
 #pragma unroll
-                    for (int u = 0; u < 4; u++)
-                        if (k0 + 32 * u < t) s_vals[wid][pos + k0 + 32 * u] = v[u];
+                    for (int u = 0; u < 4; u++) dst[32 * u] = v[u];
+                    wp += 4 * bw;
+                    dst += 128;
+                }
+                for (; k < t; k += 32) {
+                    *dst = __funnelshift_r(wp[0], wp[1], sh) & vmask;
+                    wp += bw;
+                    dst += 32;
                 }
             }
             pos += t;
@@ -668,46 +679,77 @@ __global__ void __launch_bounds__(PQ_WARPS * 32) pq_decode_tiles_fast_kernel(PqL
     const bool same4 = a.mode == PQ_MODE_VALUES && width == 4 && a.out_width == 4 && (a.phys_type == 1 || a.phys_type == 4);
     const bool same8 = a.mode == PQ_MODE_VALUES && width == 8 && a.out_width == 8 && (a.phys_type == 2 || a.phys_type == 5);
     const bool widen = a.mode == PQ_MODE_VALUES && a.phys_type == 1 && (a.out_type == T_INT64 || a.out_type == T_TIMESTAMP || a.out_type == T_DATE64);
-    if (same4 || same8 || widen) {
+    if (same4 || widen) {
+        // value r (dictionary index, or PLAIN ordinal within the tile) is the 32-bit word at base + 4r; the base is
+        // not 4-byte aligned in general (page payloads sit at arbitrary file offsets): one uniform funnel shift
         const uint32_t ndict = (uint32_t)dd.num_values;
         const unsigned lt = lanemask_lt();
+        const uintptr_t ba = (uintptr_t)(dict ? dd.data : vals + tl.v0 * 4);
+        const uint32_t* bw32 = (const uint32_t*)(ba & ~(uintptr_t)3);
+        const unsigned bsh = (unsigned)(ba & 3) * 8;
+        uint32_t* out32 = (uint32_t*)a.out + out0 + lane;
+        int64_t* out64 = (int64_t*)a.out + out0 + lane;
+        const int nfull = n - (int)lane;   // row 32j + lane exists iff 32j < nfull
         // 4 row-groups (128 rows) per iteration: the four gathers are issued back to back before any store
+        for (int j0 = 0; j0 * 32 < n; j0 += 4) {
+            uint32_t e[4], v[4];
+            bool valid[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = j0 + u;   // < 32 (n <= 1024)
+                const uint32_t wj = s_w[wid][j];
+                const int rank = s_pref[wid][j] + __popc(wj & lt);
+                valid[u] = (wj >> lane) & 1u;   // validity words carry no bits past the tile's rows
+                e[u] = 0;
+                if (valid[u]) {
+                    e[u] = (uint32_t)rank;
+                    if (dict) {
+                        const uint32_t di = s_vals[wid][rank];
+                        e[u] = di < ndict ? di : 0;   // corrupt index guard
+                    }
+                }
+            }
+            if (bsh == 0) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = valid[u] ? bw32[e[u]] : 0u;
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = valid[u] ? __funnelshift_r(bw32[e[u]], bw32[e[u] + 1], bsh) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (32 * (j0 + u) < nfull) {
+                    if (same4) out32[32 * (j0 + u)] = v[u];
+                    else out64[32 * (j0 + u)] = (int64_t)(int32_t)v[u];
+                }
+        }
+    } else if (same8) {
+        const uint32_t ndict = (uint32_t)dd.num_values;
+        const unsigned lt = lanemask_lt();
         for (int j0 = 0; j0 * 32 < n; j0 += 4) {
             const uint8_t* src[4];
             bool valid[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const int j = j0 + u;
-                const uint32_t wj = j < 32 ? s_w[wid][j] : 0u;
-                const int rank = (j < 32 ? s_pref[wid][j] : 0) + __popc(wj & lt);
-                valid[u] = ((wj >> lane) & 1u) && (32 * j + (int)lane < n);
+                const uint32_t wj = s_w[wid][j];
+                const int rank = s_pref[wid][j] + __popc(wj & lt);
+                valid[u] = (wj >> lane) & 1u;
                 src[u] = vals;
                 if (valid[u]) {
                     if (dict) {
                         uint32_t di = s_vals[wid][rank];
                         di = di < ndict ? di : 0;
-                        src[u] = dd.data + (int64_t)di * width;
-                    } else src[u] = vals + (tl.v0 + rank) * width;
+                        src[u] = dd.data + (int64_t)di * 8;
+                    } else src[u] = vals + (tl.v0 + rank) * 8;
                 }
             }
-            if (same8) {
-                uint64_t v[4];
+            uint64_t v[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) v[u] = valid[u] ? ld_u64_unaligned(src[u]) : 0ull;
+            for (int u = 0; u < 4; u++) v[u] = valid[u] ? ld_u64_unaligned(src[u]) : 0ull;
 #pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if (32 * (j0 + u) + (int)lane < n) ((uint64_t*)a.out)[out0 + 32 * (j0 + u) + lane] = v[u];
-            } else {
-                uint32_t v[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) v[u] = valid[u] ? ld_u32_unaligned(src[u]) : 0u;
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if (32 * (j0 + u) + (int)lane < n) {
-                        if (same4) ((uint32_t*)a.out)[out0 + 32 * (j0 + u) + lane] = v[u];
-                        else ((int64_t*)a.out)[out0 + 32 * (j0 + u) + lane] = (int64_t)(int32_t)v[u];
-                    }
-            }
+            for (int u = 0; u < 4; u++)
+                if (32 * (j0 + u) + (int)lane < n) ((uint64_t*)a.out)[out0 + 32 * (j0 + u) + lane] = v[u];
         }
     } else
     for (int j = 0; j * 32 < n; j++) {
@@ -771,7 +813,7 @@ void pq_decode_pages(Ctx& ctx, const PqColumnArgs& a, const std::vector<PqPage>&
         else pq_decode_tiles_fast_kernel<<<(n_tiles + PQ_WARPS - 1) / PQ_WARPS, PQ_WARPS * 32, 0, ctx.stream>>>(L, n_tiles);
         LAUNCH_CHECK(ctx);
     }
-    ctx.sync();   // tb (host) is read by an async copy
+    // no sync: to_device stages `tb` before returning (pinned arena copy, or the driver's pageable-copy staging)
 }
 
 // ---- PLAIN BYTE_ARRAY sections (dictionary pages and non-dictionary data pages): one thread walks one section

@@ -78,9 +78,11 @@ struct GroupedResult {
 // Hash-aggregate one device-resident batch.  sel (optional) = row selection (filter fused into the aggregate).
 // fast_key_out (optional, single fixed-width integer key only): emit the group key in this wider integer type.
 GroupedResult hash_aggregate(Ctx& ctx, const std::vector<ColumnPtr>& keys, const std::vector<AccSpec>& accs,
-                             const int32_t* sel, int64_t n_rows, const DType* fast_key_out = nullptr);
+                             const int32_t* sel, int64_t n_rows, const DType* fast_key_out = nullptr,
+                             const uint32_t* selmask = nullptr, int64_t n_selected = -1);   // selmask: pending filter bit mask (see k_agg.cu)
 // no grouping keys: one output row
-std::vector<ColumnPtr> global_aggregate(Ctx& ctx, const std::vector<AccSpec>& accs, const int32_t* sel, int64_t n_rows);
+std::vector<ColumnPtr> global_aggregate(Ctx& ctx, const std::vector<AccSpec>& accs, const int32_t* sel, int64_t n_rows,
+                                        const uint32_t* selmask = nullptr);
 // AVG final merge (agg/avg.rs:151-179)
 ColumnPtr avg_finalize(Ctx& ctx, const Column& sum, const Column& cnt, const DType& out_type);
 

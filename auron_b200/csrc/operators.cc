@@ -43,10 +43,20 @@ void drop_device_resource(const std::string& id) {
     g_resources.erase(id);
 }
 
-BatchPtr materialize(Task& t, const SelBatch& s) {
+const int32_t* ensure_sel(Task& t, SelBatch& s) {
+    if (!s.sel && s.mask && s.batch) {
+        int64_t cnt = 0;
+        s.sel = mask_to_indices(t.ctx, P<uint32_t>(s.mask), s.batch->num_rows, &cnt);
+        s.n = cnt;
+        s.mask.reset();
+    }
+    return P<int32_t>(s.sel);
+}
+BatchPtr materialize(Task& t, SelBatch& s) {
     if (!s.batch) return nullptr;
-    if (!s.sel) return s.batch;
-    return take_batch(t.ctx, *s.batch, P<int32_t>(s.sel), s.n, false);
+    const int32_t* sel = ensure_sel(t, s);
+    if (!sel) return s.batch;
+    return take_batch(t.ctx, *s.batch, sel, s.n, false);
 }
 
 ColumnPtr eval_to_column(Task& t, const ExprPtr& e, const Schema& schema, const Batch& b) {
@@ -118,11 +128,11 @@ SelBatch FilterExec::next_sel(Task& t) {
     if (!b) return out;
     OpTimer timer(metrics, "elapsed_ns");
     out.batch = b;
+    // the selection stays a bit mask until a consumer needs row indices (ensure_sel): Filter -> HashAggregate never does
     Buf mask = eval_predicate(t.ctx, prog, *b, b->num_rows);
-    int64_t cnt = 0;
-    Buf idx = mask_to_indices(t.ctx, P<uint32_t>(mask), b->num_rows, &cnt);
+    int64_t cnt = count_set_bits(t.ctx, (const uint8_t*)mask->ptr, b->num_rows);
     out.n = cnt;
-    if (cnt != b->num_rows) out.sel = idx;
+    if (cnt != b->num_rows) out.mask = mask;
     metrics.add("output_rows", cnt);
     return out;
 }
@@ -170,6 +180,7 @@ ProjectExec::ProjectExec(OperatorPtr input, std::vector<ExprPtr> ex, std::vector
 BatchPtr ProjectExec::next(Task& t) {
     SelBatch s = children[0]->next_sel(t);
     if (!s.batch) return nullptr;
+    ensure_sel(t, s);
     auto out = std::make_shared<Batch>();
     out->num_rows = s.n;
     std::vector<ColumnPtr> computed;
@@ -355,14 +366,14 @@ static std::vector<AccSpec> build_specs(const std::vector<AggExprSpec>& aggs, co
 }
 
 static BatchPtr run_agg(Task& t, const std::vector<ColumnPtr>& keys, const std::vector<AccSpec>& specs, const int32_t* sel, int64_t n,
-                        const DType* key_out = nullptr) {
+                        const DType* key_out = nullptr, const uint32_t* selmask = nullptr, int64_t n_selected = -1) {
     auto out = std::make_shared<Batch>();
     if (keys.empty()) {
-        auto accs = global_aggregate(t.ctx, specs, sel, n);
+        auto accs = global_aggregate(t.ctx, specs, sel, n, selmask);
         out->num_rows = 1;
         out->cols = accs;
     } else {
-        GroupedResult r = hash_aggregate(t.ctx, keys, specs, sel, n, key_out);
+        GroupedResult r = hash_aggregate(t.ctx, keys, specs, sel, n, key_out, selmask, n_selected);
         out->num_rows = r.num_groups;
         out->cols = r.keys->cols;
         for (auto& c : r.accs) out->cols.push_back(c);
@@ -370,10 +381,13 @@ static BatchPtr run_agg(Task& t, const std::vector<ColumnPtr>& keys, const std::
     return out;
 }
 
-BatchPtr AggExec::aggregate_chunk(Task& t, const SelBatch& s) {
+BatchPtr AggExec::aggregate_chunk(Task& t, SelBatch& s) {
     const Batch& in = *s.batch;
-    const int32_t* sel = P<int32_t>(s.sel);
-    int64_t n = s.n;
+    // plain column arguments: the kernels read the filter's bit mask directly; computed arguments need row indices
+    const uint32_t* selmask = (all_plain && !s.sel) ? P<uint32_t>(s.mask) : nullptr;
+    const int64_t n_selected = s.n;
+    const int32_t* sel = selmask ? nullptr : ensure_sel(t, s);
+    int64_t n = selmask ? in.num_rows : s.n;
     std::vector<ColumnPtr> lowered_cols;
     bool any_merge = false;
     for (auto& a : aggs) any_merge |= a.mode != MODE_PARTIAL;
@@ -397,7 +411,7 @@ BatchPtr AggExec::aggregate_chunk(Task& t, const SelBatch& s) {
         for (int i = start; i < (int)src->cols.size(); i++) merge_cols.push_back(src->cols[i]);
     }
     auto specs = build_specs(aggs, pargs, &merge_cols, false);
-    return run_agg(t, keys, specs, sel, n, has_widened_key ? &widened_key_type : nullptr);
+    return run_agg(t, keys, specs, sel, n, has_widened_key ? &widened_key_type : nullptr, selmask, n_selected);
 }
 
 BatchPtr AggExec::merge_partials(Task& t, const BatchPtr& all) {

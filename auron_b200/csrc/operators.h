@@ -72,7 +72,7 @@ struct AggExec : Operator {
     BatchPtr next(Task& t) override;
 
    private:
-    BatchPtr aggregate_chunk(Task& t, const SelBatch& s);
+    BatchPtr aggregate_chunk(Task& t, SelBatch& s);
     BatchPtr merge_partials(Task& t, const BatchPtr& all);
     BatchPtr finalize(Task& t, const BatchPtr& merged);
 };
@@ -142,6 +142,6 @@ struct UnionExec : Operator {
 
 // helpers shared with scan / shuffle
 ColumnPtr eval_to_column(Task& t, const ExprPtr& e, const Schema& schema, const Batch& b);
-BatchPtr materialize(Task& t, const SelBatch& s);
+BatchPtr materialize(Task& t, SelBatch& s);
 
 }  // namespace auron

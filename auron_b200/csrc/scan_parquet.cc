@@ -19,6 +19,7 @@
 #include <condition_variable>
 #include <deque>
 #include <exception>
+#include <functional>
 #include <mutex>
 #include <thread>
 
@@ -105,6 +106,67 @@ static void host_decompress(int codec, const uint8_t* in, size_t in_len, uint8_t
     }
 }
 
+// Persistent host worker pool (process-wide).  Spawning 32 std::threads per parallel_for cost ~0.6 ms per scan batch,
+// more than the page-header parsing they were spawned for.
+class WorkerPool {
+  public:
+    struct Job {
+        std::function<void()> work;
+        int outstanding = 0;   // tickets handed to the pool and not yet finished (guarded by pool mutex)
+    };
+    static WorkerPool& get() {
+        static WorkerPool* pool = new WorkerPool();   // leaked on purpose: workers may outlive static destruction
+        return *pool;
+    }
+    // run job.work() on up to `extra` pool workers in addition to the caller; returns when all of them are done
+    void run(Job& job, unsigned extra) {
+        extra = std::min<unsigned>(extra, (unsigned)workers_.size());
+        {
+            std::lock_guard<std::mutex> l(mu_);
+            job.outstanding = (int)extra;
+            for (unsigned i = 0; i < extra; i++) tickets_.push_back(&job);
+        }
+        if (extra == 1) cv_.notify_one();
+        else if (extra > 1) cv_.notify_all();
+        job.work();
+        std::unique_lock<std::mutex> l(mu_);
+        for (auto it = tickets_.begin(); it != tickets_.end();) {   // tickets nobody picked up yet are not needed any more
+            if (*it == &job) {
+                it = tickets_.erase(it);
+                job.outstanding--;
+            } else ++it;
+        }
+        done_cv_.wait(l, [&] { return job.outstanding == 0; });
+    }
+
+  private:
+    WorkerPool() {
+        unsigned n = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+        for (unsigned i = 0; i < n; i++) {
+            workers_.emplace_back([this] { loop(); });
+            workers_.back().detach();
+        }
+    }
+    void loop() {
+        for (;;) {
+            Job* j;
+            {
+                std::unique_lock<std::mutex> l(mu_);
+                cv_.wait(l, [&] { return !tickets_.empty(); });
+                j = tickets_.front();
+                tickets_.pop_front();
+            }
+            j->work();
+            std::lock_guard<std::mutex> l(mu_);
+            if (--j->outstanding == 0) done_cv_.notify_all();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    std::deque<Job*> tickets_;
+    std::vector<std::thread> workers_;
+};
+
 // run fn(i) for i in [0, n) on up to `threads` host threads; the first exception is rethrown
 template <typename F>
 static void parallel_for(size_t n, unsigned threads, F fn) {
@@ -117,7 +179,8 @@ static void parallel_for(size_t n, unsigned threads, F fn) {
     std::atomic<size_t> next{0};
     std::mutex mu;
     std::string err;
-    auto work = [&]() {
+    WorkerPool::Job job;
+    job.work = [&]() {
         for (;;) {
             size_t i = next.fetch_add(1);
             if (i >= n) return;
@@ -126,13 +189,13 @@ static void parallel_for(size_t n, unsigned threads, F fn) {
             } catch (const std::exception& e) {
                 std::lock_guard<std::mutex> l(mu);
                 if (err.empty()) err = e.what();
+            } catch (...) {
+                std::lock_guard<std::mutex> l(mu);
+                if (err.empty()) err = "unknown failure in a scan worker";
             }
         }
     };
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < threads; t++) th.emplace_back(work);
-    work();
-    for (auto& x : th) x.join();
+    WorkerPool::get().run(job, threads - 1);
     if (!err.empty()) fail(err);
 }
 

@@ -130,6 +130,9 @@ def test_conjunctive_compare_fast_paths_match_vm_and_arrow():
         ([P.binary("NotEq", I, li(0)), P.binary("LtEq", Lc, P.lit(0, pa.int64()))], pc.and_kleene(pc.not_equal(t["i"], 0), pc.less_equal(t["l"], 0))),
         ([P.is_null(I), P.binary("Gt", Lc, P.lit(-2**61, pa.int64()))], pc.and_kleene(pc.is_null(t["i"]), pc.greater(t["l"], -2**61))),
         ([P.binary("Lt", Lc, P.lit(-2**63, pa.int64()))], pc.less(t["l"], -2**63)),             # empty interval
+        ([P.binary("GtEq", Lc, P.lit(-2**61, pa.int64())), P.binary("Lt", P.col("row"), P.lit(60_000, pa.int64()))],     # two int64 columns (vector kernel)
+         pc.and_kleene(pc.greater_equal(t["l"], -2**61), pc.less(t["row"], 60_000))),
+        ([P.binary("Gt", I, P.lit(2**31 - 1, pa.int32()))], pc.greater(t["i"], 2**31 - 1)),     # empty after clamping to the int32 domain
         ([P.binary("Gt", F, P.lit(0.25, pa.float64())), P.binary("Eq", B, P.lit(True, pa.bool_()))], None),   # NaN > x under totalOrder
         ([P.binary("GtEq", D, P.lit(decimal.Decimal("-1.50"), pa.decimal128(7, 2))), P.binary("Lt", D, P.lit(decimal.Decimal("12.34"), pa.decimal128(7, 2)))],
          pc.and_kleene(pc.greater_equal(t["d"], decimal.Decimal("-1.50")), pc.less(t["d"], decimal.Decimal("12.34")))),
@@ -387,6 +390,43 @@ def test_agg_filter_fusion_and_expressions():
         [("v2", "sum"), ("v", "count"), ("v", "min"), ("v", "max"), ("v", "mean")])
     exp = pa.table({"k": g["k"], "s": g["v2_sum"], "c": g["v_count"], "mn": g["v_min"], "mx": g["v_max"], "avg": g["v_mean"]})
     assert_same_rows(got, exp, float_tol=1e-9)
+
+
+def test_agg_consumes_filter_mask_on_every_kernel_path():
+    # Filter -> HashAggregate with plain column arguments: the aggregate reads the filter's bit mask directly (no index vector).
+    # Covers the 64-bit fast-key kernel, the general (string + int) row-key kernel, the no-grouping kernel and FIRST positions.
+    rng = np.random.default_rng(33)
+    n = 123_457
+    words = ["x", "yy", "zzz", None]
+    t = pa.table({"k": pa.array(rng.integers(0, 50, n), type=pa.int64(), mask=rng.random(n) < 0.03),
+                  "s": pa.array([words[int(i)] for i in rng.integers(0, 4, n)]),
+                  "v": pa.array(rng.integers(-100, 100, n), type=pa.int64(), mask=rng.random(n) < 0.1),
+                  "f": pa.array(rng.integers(0, 10, n), type=pa.int32()),
+                  "pos": pa.array(np.arange(n), type=pa.int64())})
+    pred = [P.binary("GtEq", P.col("f"), P.lit(3, pa.int32()))]
+    ft = t.filter(pc.greater_equal(t["f"], 3))
+    aggs = [P.agg_expr("SUM", [P.col("v")], pa.int64()), P.agg_expr("COUNT", [P.col("v")], pa.int64()), P.agg_expr("MIN", [P.col("pos")], pa.int64())]
+    finals = [P.agg_expr(f, [P.lit(None, pa.null())], pa.int64()) for f in ("SUM", "COUNT", "MIN")]
+    for keys in (["k"], ["s", "k"], []):
+        flt = P.filter_(P.ffi_reader(t.schema, "t"), pred)
+        part = P.agg(flt, [P.col(k) for k in keys], keys, aggs, ["s_v", "c_v", "first_pos"], ["PARTIAL"] * 3)
+        final = P.agg(part, [P.col(k) for k in keys], keys, finals, ["s_v", "c_v", "first_pos"], ["FINAL"] * 3)
+        got = run(final, {"t": t}, chunk=40_000)
+        if keys:
+            g = ft.group_by(keys, use_threads=False).aggregate([("v", "sum"), ("v", "count"), ("pos", "min")])
+            exp = pa.table({**{k: g[k] for k in keys}, "s_v": g["v_sum"], "c_v": g["v_count"], "first_pos": g["pos_min"]})
+        else:
+            exp = pa.table({"s_v": pa.array([pc.sum(ft["v"]).as_py()], type=pa.int64()), "c_v": pa.array([pc.count(ft["v"]).as_py()], type=pa.int64()),
+                            "first_pos": pa.array([pc.min(ft["pos"]).as_py()], type=pa.int64())})
+        assert_same_rows(got, exp)
+    # FIRST keeps the first selected row of each group in input order
+    flt = P.filter_(P.ffi_reader(t.schema, "t"), pred)
+    got = run(P.agg(flt, [P.col("k")], ["k"], [P.agg_expr("FIRST", [P.col("pos")], pa.int64())], ["fp"], ["PARTIAL"]), {"t": t})
+    first = {}
+    for k, pos in zip(ft["k"].to_pylist(), ft["pos"].to_pylist()):
+        first.setdefault(k, pos)
+    got_map = dict(zip(got.column(0).to_pylist(), got.column(1).to_pylist()))
+    assert got_map == first
 
 
 def test_agg_string_and_multi_keys_decimal_sum():
