@@ -44,6 +44,9 @@ struct AccDesc {
     uint8_t* acc_valid;
     int32_t lo_stride;      // u64 words between consecutive slots (1 = SoA arrays, W = slot records interleaved with the key)
     int32_t valid_stride;   // bytes between consecutive slots' valid flags
+    // SUM/MIN/MAX(x) next to COUNT(x) over the same column: the group's accumulator is valid iff that count is non-zero,
+    // so the per-row valid-flag store (one more random L2 access per row) is dropped and validity is read from the count.
+    const unsigned long long* valid_cnt;
 };
 struct AccArgs {
     AccDesc a[kMaxAccs];
@@ -241,6 +244,160 @@ __global__ void __launch_bounds__(256) agg_fast_kernel(FastKey key, unsigned lon
             agg_fast_row(key, table, tw, cap, mask, accs, row, row, flags);
         }
         __syncwarp();
+    }
+}
+
+// -------------------------------------------------------------------------------- DIRECT path
+// One integer key whose value range in the chunk is small (TPC-DS surrogate keys: item_sk in [1, 204000]): the slot is
+// key - min, so the per-row table probe (a random 8-byte load, plus CAS on insert) disappears and a row costs only its
+// accumulator atomics.  The range comes from a min/max pass over the key column; slot `range` is the NULL group.  A group
+// exists if some accumulator shows it (COUNT != 0 or a valid flag) or, for rows that contribute to no such accumulator, the
+// `seen` byte written for exactly those rows.
+struct DirectTable {
+    long long kmin;
+    int64_t range;
+    uint8_t* seen;
+};
+__global__ void __launch_bounds__(256) key_minmax_kernel(FastKey key, int64_t n, long long* __restrict__ out) {
+    long long mn = 0x7fffffffffffffffll, mx = (long long)0x8000000000000000ull;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+        if (key.validity && !bit_get(key.validity, i)) continue;
+        long long k = (long long)load_key64(key, i);
+        mn = min(mn, k);
+        mx = max(mx, k);
+    }
+    for (int d = 16; d; d >>= 1) {
+        mn = min(mn, __shfl_down_sync(FULL_MASK, mn, d));
+        mx = max(mx, __shfl_down_sync(FULL_MASK, mx, d));
+    }
+    if (lane_id() == 0 && mn <= mx) {
+        atomicMin(&out[0], mn);
+        atomicMax(&out[1], mx);
+    }
+}
+// same reduction for int32 / int64 keys: 4 consecutive rows per lane from 128-bit loads, one validity nibble per lane
+template <typename T>
+__global__ void __launch_bounds__(256) key_minmax_vec_kernel(const T* __restrict__ data, const uint32_t* __restrict__ valid, int64_t n,
+                                                             long long* __restrict__ out) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned sub = (lane & 7) * 4;
+    const int64_t warp = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * 256) >> 5;
+    long long mn = 0x7fffffffffffffffll, mx = (long long)0x8000000000000000ull;
+    for (int64_t base = warp * 128; base < n; base += nwarps * 128) {
+        if (base + 128 <= n) {
+            T x[4];
+            if (sizeof(T) == 4) {
+                const int4 v = ((const int4*)(data + base))[lane];
+                x[0] = (T)v.x, x[1] = (T)v.y, x[2] = (T)v.z, x[3] = (T)v.w;
+            } else {
+                const longlong2* q = (const longlong2*)(data + base) + 2 * lane;
+                const longlong2 v0 = q[0], v1 = q[1];
+                x[0] = (T)v0.x, x[1] = (T)v0.y, x[2] = (T)v1.x, x[3] = (T)v1.y;
+            }
+            const uint32_t m = valid ? (valid[(base >> 5) + (lane >> 3)] >> sub) & 0xFu : 0xFu;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if ((m >> k) & 1u) {
+                    mn = min(mn, (long long)x[k]);
+                    mx = max(mx, (long long)x[k]);
+                }
+        } else {
+            for (int k = 0; k < 4; k++) {
+                const int64_t row = base + 4 * lane + k;
+                if (row < n && (!valid || ((valid[row >> 5] >> (row & 31)) & 1u))) {
+                    mn = min(mn, (long long)data[row]);
+                    mx = max(mx, (long long)data[row]);
+                }
+            }
+        }
+    }
+    for (int d = 16; d; d >>= 1) {
+        mn = min(mn, __shfl_down_sync(FULL_MASK, mn, d));
+        mx = max(mx, __shfl_down_sync(FULL_MASK, mx, d));
+    }
+    if (lane == 0 && mn <= mx) {
+        atomicMin(&out[0], mn);
+        atomicMax(&out[1], mx);
+    }
+}
+__device__ __forceinline__ void agg_direct_row(const FastKey& key, const DirectTable& t, const AccArgs& accs, int64_t row, int64_t dense) {
+    int64_t slot = t.range;
+    if (!key.validity || bit_get(key.validity, row)) slot = (int64_t)((long long)load_key64(key, row) - t.kmin);
+    bool marked = false;
+    for (int a = 0; a < accs.n; a++) {
+        const AccDesc& d = accs.a[a];
+        AccVal v = {0, 0};
+        if (acc_load(d, row, dense, v)) {
+            acc_apply(d, slot, v);
+            marked = marked || (((d.kind == ACC_COUNT || d.kind == ACC_ADD_I64) && v.lo != 0) || d.acc_valid != nullptr);
+        }
+    }
+    if (!marked) t.seen[slot] = 1;
+}
+__global__ void __launch_bounds__(256) agg_direct_kernel(FastKey key, DirectTable t, AccArgs accs, const int32_t* __restrict__ sel, int64_t n,
+                                                         const uint32_t* __restrict__ selmask) {
+    if (!selmask) {
+        const int64_t stride = (int64_t)gridDim.x * 256;
+        for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) agg_direct_row(key, t, accs, sel ? (int64_t)sel[i] : i, i);
+        return;
+    }
+    // pending filter mask: warp-local compaction of each 128-row window (see agg_fast_kernel)
+    __shared__ int32_t s_rows[8][128];
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const int64_t n_words = (n + 31) >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * 8 + wid, nwarps = (int64_t)gridDim.x * 8;
+    for (int64_t w0 = warp * 4; w0 < n_words; w0 += nwarps * 4) {
+        uint32_t mw = (lane < 4 && w0 + lane < n_words) ? selmask[w0 + lane] : 0u;
+        if (w0 + lane == n_words - 1 && (n & 31)) mw &= (1u << (n & 31)) - 1u;
+        int pos = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t wq = __shfl_sync(FULL_MASK, mw, q);
+            if ((wq >> lane) & 1u) s_rows[wid][pos + __popc(wq & lt)] = (int32_t)((w0 + q) * 32 + lane);
+            pos += __popc(wq);
+        }
+        __syncwarp();
+        for (int j = lane; j < pos; j += 32) {
+            const int64_t row = s_rows[wid][j];
+            agg_direct_row(key, t, accs, row, row);
+        }
+        __syncwarp();
+    }
+}
+__global__ void __launch_bounds__(256) occupied_mask_direct_kernel(DirectTable t, AccArgs accs, uint32_t* __restrict__ mask) {
+    const int64_t s = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    bool occ = false;
+    if (s <= t.range) {
+        occ = t.seen[s] != 0;
+        for (int a = 0; a < accs.n && !occ; a++) {
+            const AccDesc& d = accs.a[a];
+            if (d.kind == ACC_COUNT || d.kind == ACC_ADD_I64) occ = d.acc_lo[s] != 0;
+            else if (d.acc_valid) occ = d.acc_valid[s] != 0;
+        }
+    }
+    uint32_t w = __ballot_sync(FULL_MASK, occ);
+    if (lane_id() == 0 && s <= t.range) mask[s >> 5] = w;
+}
+__global__ void __launch_bounds__(256) emit_direct_keys_kernel(DirectTable t, const int32_t* __restrict__ slot_ids, int64_t g, int32_t type,
+                                                               void* __restrict__ out, uint32_t* __restrict__ out_valid) {
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    bool valid = false;
+    if (i < g) {
+        const int64_t s = slot_ids[i];
+        valid = s < t.range;
+        const long long k = valid ? t.kmin + s : 0;
+        switch (type) {
+            case T_INT8: ((int8_t*)out)[i] = (int8_t)k; break;
+            case T_INT16: ((int16_t*)out)[i] = (int16_t)k; break;
+            case T_INT32: case T_DATE32: ((int32_t*)out)[i] = (int32_t)k; break;
+            default: ((long long*)out)[i] = k; break;
+        }
+    }
+    if (out_valid) {
+        uint32_t w = __ballot_sync(FULL_MASK, valid);
+        if (lane_id() == 0 && i < g) out_valid[i >> 5] = w;
     }
 }
 
@@ -467,7 +624,7 @@ __global__ void __launch_bounds__(256) emit_acc_kernel(AccDesc d, const int32_t*
     bool ok = false;
     if (i < g) {
         int64_t s = slot_ids ? (int64_t)slot_ids[i] : i;
-        ok = d.acc_valid ? d.acc_valid[s * d.valid_stride] != 0 : true;
+        ok = d.valid_cnt ? d.valid_cnt[s] != 0 : (d.acc_valid ? d.acc_valid[s * d.valid_stride] != 0 : true);
         uint64_t lo = d.acc_lo[s * d.lo_stride];
         switch (d.kind) {
             case ACC_SUM_DEC:
@@ -629,6 +786,19 @@ static AccArgs prepare_accs(Ctx& ctx, const std::vector<AccSpec>& specs, int64_t
             d.acc_valid = P<uint8_t>(v);
         }
     }
+    // pair SUM / MIN / MAX (x) with a COUNT(x) over the very same column (AVG lowers to exactly this pair)
+    if (!rec_base && !getenv("AURON_DISABLE_AGG_VALID_FROM_COUNT") && !getenv("AURON_ENABLE_SMEM_AGG"))
+        for (int i = 0; i < args.n; i++) {
+            const AccSpec& s = specs[i];
+            bool value_acc = s.kind == ACC_SUM_I64 || s.kind == ACC_SUM_F64 || s.kind == ACC_SUM_DEC || s.kind == ACC_MIN || s.kind == ACC_MAX;
+            if (!value_acc || !s.input) continue;
+            for (int j = 0; j < args.n; j++)
+                if (specs[j].kind == ACC_COUNT && specs[j].input && specs[j].input.get() == s.input.get() && specs[j].extra.empty()) {
+                    args.a[i].valid_cnt = args.a[j].acc_lo;
+                    args.a[i].acc_valid = nullptr;   // the buffer stays allocated (zeroed) but is neither written nor read
+                    break;
+                }
+        }
     return args;
 }
 __global__ void fill_u64_kernel(unsigned long long* p, int64_t n, unsigned long long v) {
@@ -681,7 +851,7 @@ static void emit_accs(Ctx& ctx, const std::vector<AccSpec>& specs, const AccArgs
             if (s.kind == ACC_FIRST) out.push_back(isset);
             continue;
         }
-        bool nullable = d.acc_valid != nullptr;
+        bool nullable = d.acc_valid != nullptr || d.valid_cnt != nullptr;
         if (s.out_type.id == T_BOOL) {   // MIN/MAX over bool: emit as int8 then it is tiny; convert through take of a 2-entry table
             fail("MIN/MAX(bool) output not supported yet");
         }
@@ -704,6 +874,65 @@ GroupedResult hash_aggregate(Ctx& ctx, const std::vector<ColumnPtr>& keys, const
     AURON_CHECK(n_rows < (int64_t)INT32_MAX, "chunk too large");
     GroupedResult res;
     bool fast = fast_key_ok(keys);
+    // ---- DIRECT path: one integer key with a small value range in this chunk
+    const TypeId kt0 = keys[0]->type.id;
+    const bool int_key = fast && (kt0 == T_INT8 || kt0 == T_INT16 || kt0 == T_INT32 || kt0 == T_INT64 || kt0 == T_DATE32);
+    if (int_key && (n_in >= (1 << 15) || getenv("AURON_FORCE_DIRECT_AGG")) && !getenv("AURON_DISABLE_DIRECT_AGG") && !getenv("AURON_AGG_INTERLEAVE") && !getenv("AURON_ENABLE_SMEM_AGG")) {
+        FastKey k{keys[0]->data->ptr, keys[0]->vbits(), (int32_t)kt0};
+        const long long init[2] = {0x7fffffffffffffffll, (long long)0x8000000000000000ull};
+        Buf mm = to_device(ctx, init, 16);
+        {
+            ProfScope ps(ctx, "agg_key_range");
+            const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n_rows + 1023) / 1024, (int64_t)ctx.sm_count * 8));
+            const uint32_t* kv = (const uint32_t*)keys[0]->vbits();
+            if (kt0 == T_INT32 || kt0 == T_DATE32) key_minmax_vec_kernel<int32_t><<<grid, 256, 0, ctx.stream>>>((const int32_t*)k.data, kv, n_rows, P<long long>(mm));
+            else if (kt0 == T_INT64) key_minmax_vec_kernel<long long><<<grid, 256, 0, ctx.stream>>>((const long long*)k.data, kv, n_rows, P<long long>(mm));
+            else key_minmax_kernel<<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(k, n_rows, P<long long>(mm));
+            LAUNCH_CHECK(ctx);
+        }
+        long long h[2];
+        to_host(ctx, h, mm->ptr, 16);
+        const bool any = h[0] <= h[1];
+        const unsigned long long span = any ? (unsigned long long)h[1] - (unsigned long long)h[0] : 0ull;
+        if (span < (1ull << 22)) {
+            DirectTable dt;
+            dt.kmin = any ? h[0] : 0;
+            dt.range = any ? (int64_t)span + 1 : 0;
+            const int64_t slots = dt.range + 1;   // + the NULL group
+            AccBuffers bufs;
+            AccArgs args = prepare_accs(ctx, accs, slots, bufs);
+            init_accs(ctx, accs, args, slots);
+            Buf seen = dalloc_zero(ctx, (size_t)slots);
+            dt.seen = P<uint8_t>(seen);
+            {
+                ProfScope ps(ctx, "agg_update");
+                agg_direct_kernel<<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(k, dt, args, sel, n_rows, selmask);
+                LAUNCH_CHECK(ctx);
+            }
+            Buf occ = dalloc(ctx, bitmap_alloc_bytes(slots));
+            occupied_mask_direct_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, ctx.stream>>>(dt, args, P<uint32_t>(occ));
+            LAUNCH_CHECK(ctx);
+            int64_t g = 0;
+            Buf slot_ids = mask_to_indices(ctx, P<uint32_t>(occ), slots, &g);
+            res.num_groups = g;
+            res.keys = std::make_shared<Batch>();
+            res.keys->num_rows = g;
+            DType kt = keys[0]->type;
+            if (fast_key_out) {
+                AURON_CHECK(kt.is_integer() && fast_key_out->is_integer() && kt.width() <= fast_key_out->width(), "bad widened key type");
+                kt = *fast_key_out;
+            }
+            auto kc = make_column(ctx, kt, g, keys[0]->may_have_nulls());
+            if (g) {
+                emit_direct_keys_kernel<<<(unsigned)((g + 255) / 256), 256, 0, ctx.stream>>>(dt, P<int32_t>(slot_ids), g, kt.id, kc->data->ptr,
+                                                                                             P<uint32_t>(kc->validity));
+                LAUNCH_CHECK(ctx);
+            }
+            res.keys->cols.push_back(kc);
+            emit_accs(ctx, accs, args, P<int32_t>(slot_ids), g, sel, res.accs);
+            return res;
+        }
+    }
     // capacity: start at 1 Mi slots (covers <= ~500k groups), fall back to 2 x rows on overflow
     int64_t cap = std::min<int64_t>(next_pow2(std::max<int64_t>(2 * n_in, 1024)), 1 << 20);
     for (int attempt = 0;; attempt++) {

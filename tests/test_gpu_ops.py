@@ -324,11 +324,13 @@ def test_agg_golden_partial_then_final():
     assert part.num_columns == 8 and [f.type for f in part.schema][1:] == [pa.int64(), pa.float64(), pa.int64(), pa.int32(), pa.int32(), pa.int64(), pa.int32()]
 
 
-@pytest.mark.parametrize("n,card,chunk", [(1000, 7, None), (300_000, 2000, 50_000), (300_000, 250_000, 100_000)])
-def test_agg_fuzz_sum_count_vs_oracle(n, card, chunk):
-    # fuzz test of agg_exec.rs:716-843: SUM/COUNT vs a hash map, nullable keys and values, multi-chunk merge
+@pytest.mark.parametrize("n,card,chunk,scale", [(1000, 7, None, 1), (300_000, 2000, 50_000, 1), (300_000, 250_000, 100_000, 1),
+                                                (300_000, 2000, 50_000, 10**12)])
+def test_agg_fuzz_sum_count_vs_oracle(n, card, chunk, scale):
+    # fuzz test of agg_exec.rs:716-843: SUM/COUNT vs a hash map, nullable keys and values, multi-chunk merge.
+    # scale = 1: dense integer keys (direct-address path for the large cases); scale = 10^12: sparse keys (hash table path)
     rng = np.random.default_rng(n + card)
-    t = pa.table({"k": pa.array(rng.integers(-card // 2, card // 2, n), type=pa.int64(), mask=rng.random(n) < 0.01),
+    t = pa.table({"k": pa.array(rng.integers(-card // 2, card // 2, n) * scale, type=pa.int64(), mask=rng.random(n) < 0.01),
                   "v": pa.array(rng.integers(-10**6, 10**6, n), type=pa.int64(), mask=rng.random(n) < 0.03)})
     plan = P.agg(P.ffi_reader(t.schema, "t"), [P.col("k")], ["k"],
                  [P.agg_expr("SUM", [P.col("v")], pa.int64()), P.agg_expr("COUNT", [P.col("v")], pa.int64())], ["s", "c"], ["PARTIAL", "PARTIAL"])
@@ -392,7 +394,14 @@ def test_agg_filter_fusion_and_expressions():
     assert_same_rows(got, exp, float_tol=1e-9)
 
 
-def test_agg_consumes_filter_mask_on_every_kernel_path():
+@pytest.mark.parametrize("direct", ["default", "force", "off"])
+def test_agg_consumes_filter_mask_on_every_kernel_path(direct, monkeypatch):
+    # single integer keys normally take the direct-address path (slot = key - min); "off" keeps them on the hash table
+    if direct == "force":
+        monkeypatch.setenv("AURON_FORCE_DIRECT_AGG", "1")
+    elif direct == "off":
+        monkeypatch.setenv("AURON_DISABLE_DIRECT_AGG", "1")
+        monkeypatch.setenv("AURON_DISABLE_AGG_VALID_FROM_COUNT", "1")
     # Filter -> HashAggregate with plain column arguments: the aggregate reads the filter's bit mask directly (no index vector).
     # Covers the 64-bit fast-key kernel, the general (string + int) row-key kernel, the no-grouping kernel and FIRST positions.
     rng = np.random.default_rng(33)
