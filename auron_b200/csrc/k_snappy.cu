@@ -1,0 +1,247 @@
+// k_snappy.cu -- Parquet page decompression on device (row P1 of SURVEY.md section 8a: the `parquet` crate decompresses
+// every page with the `snap` crate on a CPU core before decoding it; call site parquet_exec.rs:175-197).
+//
+// Spark writes SNAPPY pages by default.  A page is an independent Snappy raw block (no framing): a varint with the
+// uncompressed length, then a sequence of elements -- literals (copy the next L bytes of the input) and back references
+// (copy L bytes that start `offset` bytes before the current output position).  Elements are inherently serial, so the
+// unit of parallelism is the page: ONE WARP PER PAGE.  All 32 lanes read the same tag bytes (uniform, broadcast loads, no
+// divergence) and then move the element's bytes cooperatively:
+//   * literals: 16-byte vectors at the destination's alignment, the source re-aligned with funnel shifts (512 B per
+//     warp instruction); short references byte-wise;
+//   * overlapping references (offset < length, i.e. a repeated pattern): byte i of the run is out[pos - offset + i % offset],
+//     every source byte is already written, so all lanes proceed in parallel as well.
+// Dictionary-encoded, bit-packed index pages are close to incompressible: their Snappy form is a handful of 64 KB literals
+// and the kernel runs at copy speed; highly repetitive pages are bound by the per-element tag latency instead.
+//
+// Roofline: HBM-bound copy, algorithmic bytes = compressed bytes in + uncompressed bytes out.
+#include "kernels.h"
+#include "parquet_dev.h"
+
+namespace auron {
+
+#define LAUNCH_CHECK(ctx)            \
+    do {                             \
+        CUDA_OK(cudaGetLastError()); \
+        launch_count(ctx);           \
+    } while (0)
+
+// 16 bytes of the byte stream that starts `sb` (0..15) bytes into the aligned vector pair (a, b)
+__device__ __forceinline__ uint4 shift16(const uint4& a, const uint4& b, unsigned sb) {
+    const unsigned bs = (sb & 3) * 8;
+    uint4 r;
+    switch (sb >> 2) {   // uniform across the warp
+        case 0: r.x = __funnelshift_r(a.x, a.y, bs), r.y = __funnelshift_r(a.y, a.z, bs), r.z = __funnelshift_r(a.z, a.w, bs), r.w = __funnelshift_r(a.w, b.x, bs); break;
+        case 1: r.x = __funnelshift_r(a.y, a.z, bs), r.y = __funnelshift_r(a.z, a.w, bs), r.z = __funnelshift_r(a.w, b.x, bs), r.w = __funnelshift_r(b.x, b.y, bs); break;
+        case 2: r.x = __funnelshift_r(a.z, a.w, bs), r.y = __funnelshift_r(a.w, b.x, bs), r.z = __funnelshift_r(b.x, b.y, bs), r.w = __funnelshift_r(b.y, b.z, bs); break;
+        default: r.x = __funnelshift_r(a.w, b.x, bs), r.y = __funnelshift_r(b.x, b.y, bs), r.z = __funnelshift_r(b.y, b.z, bs), r.w = __funnelshift_r(b.z, b.w, bs); break;
+    }
+    return r;
+}
+// dst[0, len) = src[0, len); no overlap; any alignment.  Bulk: 16-byte stores at the destination's alignment, the source
+// re-aligned from two 16-byte loads (512 B per warp instruction, two vectors in flight per lane).
+__device__ __forceinline__ void warp_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int64_t len, unsigned lane) {
+    if (len < 256) {
+        for (int64_t i = lane; i < len; i += 32) dst[i] = src[i];
+        return;
+    }
+    const int head = (int)((16 - ((uintptr_t)dst & 15)) & 15);
+    if ((int)lane < head) dst[lane] = src[lane];
+    dst += head;
+    src += head;
+    len -= head;
+    int64_t nv = len >> 4;                       // whole 16-byte vectors
+    const uintptr_t sa = (uintptr_t)src;
+    const uint4* sv = (const uint4*)(sa & ~(uintptr_t)15);
+    const unsigned sb = (unsigned)(sa & 15);
+    uint4* dv = (uint4*)dst;
+    if (sb == 0) {
+        int64_t j = lane;
+        for (; j + 32 < nv; j += 64) {
+            const uint4 a = sv[j], b = sv[j + 32];
+            dv[j] = a;
+            dv[j + 32] = b;
+        }
+        for (; j < nv; j += 32) dv[j] = sv[j];
+    } else {
+        // the last vector would read 16 bytes past the source's aligned end: leave it to the byte tail
+        nv -= 1;
+        int64_t j = lane;
+        for (; j + 32 < nv; j += 64) {
+            const uint4 a0 = sv[j], a1 = sv[j + 1], b0 = sv[j + 32], b1 = sv[j + 33];
+            dv[j] = shift16(a0, a1, sb);
+            dv[j + 32] = shift16(b0, b1, sb);
+        }
+        for (; j < nv; j += 32) dv[j] = shift16(sv[j], sv[j + 1], sb);
+    }
+    for (int64_t i = (nv << 4) + lane; i < len; i += 32) dst[i] = src[i];
+}
+
+// status: 0 ok, else 1 + index of the first failing job
+//
+// Back references read bytes this warp wrote a few elements earlier.  Through global memory that is a store followed by a
+// dependent load of the same line (an L2 round trip per element: measured 1.35 ms for the 87k level prefixes of the SF100
+// bench, ~400 short elements each).  So every short element is ALSO written into a per-warp shared-memory ring holding the
+// last SN_RING output bytes, and references that fall inside the ring are served from it; long literals bypass the ring
+// (ring_from marks the first output position the ring is valid from).
+constexpr int SN_RING = 4096;
+__global__ void __launch_bounds__(128, 12) pq_decompress_kernel(const PqDecompJob* __restrict__ jobs, int n_jobs, int32_t* __restrict__ status,
+                                                            PqDecompResult* __restrict__ results) {
+    __shared__ uint8_t s_ring[4][SN_RING];
+    const int job = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (job >= n_jobs) return;
+    const unsigned lane = threadIdx.x & 31;
+    uint8_t* ring = s_ring[threadIdx.x >> 5];
+    const PqDecompJob jb = jobs[job];
+    if (lane == 0) results[job] = PqDecompResult{nullptr, -1, 0};
+    const uint8_t* __restrict__ src = jb.src;
+    uint8_t* dst = jb.dst;
+    if (jb.kind == 0) {   // stored bytes (v2 level sections)
+        warp_copy(dst, src, jb.dst_len, lane);
+        return;
+    }
+    const int n_in = jb.src_len, n_out = jb.dst_len;
+    int ip = 0, op = 0, ring_from = 0;
+    bool bad = false;
+    // preamble: uncompressed length
+    {
+        uint32_t v = 0;
+        int shift = 0;
+        for (;;) {
+            if (ip >= n_in || shift > 28) { bad = true; break; }
+            uint8_t b = src[ip++];
+            v |= (uint32_t)(b & 0x7f) << shift;
+            if (!(b & 0x80)) break;
+            shift += 7;
+        }
+        if ((int)v != n_out) bad = true;
+    }
+    while (!bad && ip < n_in) {
+        const uint32_t tag = src[ip++];
+        const uint32_t kind = tag & 3;
+        if (kind == 0) {
+            int len = (int)(tag >> 2) + 1;
+            if (len > 60) {
+                const int nb = len - 60;
+                if (ip + nb > n_in) { bad = true; break; }
+                uint32_t v = 0;
+                for (int k = 0; k < nb; k++) v |= (uint32_t)src[ip + k] << (8 * k);
+                ip += nb;
+                if (v >= 0x7fffffffu) { bad = true; break; }
+                len = (int)v + 1;
+            }
+            if (len > n_in - ip || len > n_out - op) { bad = true; break; }
+            if (len <= 256) {   // short literal: global + ring
+                for (int i = lane; i < len; i += 32) {
+                    const uint8_t c = src[ip + i];
+                    dst[op + i] = c;
+                    ring[(op + i) & (SN_RING - 1)] = c;
+                }
+                ip += len;
+                op += len;
+                __syncwarp();
+                continue;
+            }
+            // Nullable v1 data page whose stream ends with one literal that contains the whole value section (bit-packed
+            // dictionary indices do not compress; the level bytes in front of them do): copy only the level bytes that
+            // spill into this literal and let the page read its values in place from the compressed buffer.
+            if (jb.v1_levels && ip + len == n_in && op + len == n_out && op >= 4) {
+                __syncwarp();
+                const int64_t val_off = 4 + (int64_t)((uint32_t)dst[0] | ((uint32_t)dst[1] << 8) | ((uint32_t)dst[2] << 16) | ((uint32_t)dst[3] << 24));
+                const int64_t keep = val_off - op;
+                if (keep >= 0 && len - keep >= 256) {
+                    warp_copy(dst + op, src + ip, keep, lane);
+                    if (lane == 0) results[job] = PqDecompResult{src + ip + keep, (int32_t)val_off, 0};
+                    ip += len;
+                    op += len;
+                    break;
+                }
+            }
+            warp_copy(dst + op, src + ip, len, lane);
+            ip += len;
+            op += len;
+            ring_from = op;   // the ring does not hold this literal
+            __syncwarp();
+        } else {
+            int len, off;
+            if (kind == 1) {
+                if (ip + 1 > n_in) { bad = true; break; }
+                len = 4 + (int)((tag >> 2) & 7);
+                off = (int)(((tag >> 5) << 8) | src[ip]);
+                ip += 1;
+            } else if (kind == 2) {
+                if (ip + 2 > n_in) { bad = true; break; }
+                len = (int)(tag >> 2) + 1;
+                off = (int)((uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8));
+                ip += 2;
+            } else {
+                if (ip + 4 > n_in) { bad = true; break; }
+                len = (int)(tag >> 2) + 1;
+                const uint32_t o4 = (uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8) | ((uint32_t)src[ip + 2] << 16) | ((uint32_t)src[ip + 3] << 24);
+                if (o4 > 0x7fffffffu) { bad = true; break; }
+                off = (int)o4;
+                ip += 4;
+            }
+            if (off <= 0 || off > op || len > n_out - op) { bad = true; break; }
+            const int from = op - off;
+            // len <= 64: at most two bytes per lane; byte i of the run is out[from + i % off] (i % off == i when off >= len)
+            if (from >= ring_from && off <= SN_RING - 64) {
+                for (int i = lane; i < len; i += 32) {
+                    const int k = off >= len ? i : (int)((unsigned)i % (unsigned)off);
+                    const uint8_t c = ring[(from + k) & (SN_RING - 1)];
+                    dst[op + i] = c;
+                    ring[(op + i) & (SN_RING - 1)] = c;   // distinct from every source slot: off + len <= SN_RING
+                }
+            } else {
+                for (int i = lane; i < len; i += 32) {
+                    const int k = off >= len ? i : (int)((unsigned)i % (unsigned)off);
+                    const uint8_t c = dst[from + k];
+                    dst[op + i] = c;
+                    ring[(op + i) & (SN_RING - 1)] = c;
+                }
+            }
+            op += len;
+            __syncwarp();
+        }
+    }
+    if (!bad && op != n_out) bad = true;
+    if (bad && lane == 0) atomicCAS(status, 0, job + 1);
+}
+
+// v1 data pages keep [u32 length][definition levels][values] inside the compressed body: once the body is in HBM the
+// page descriptor's level / value sections are derived from that length word.
+__global__ void pq_fix_v1_pages_kernel(PqPage* __restrict__ pages, int n, const PqDecompResult* __restrict__ results) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PqPage pg = pages[i];
+    if (pg.def_len != -1) return;
+    const uint8_t* body = pg.def_ptr - 4;   // def_ptr was set to body + 4
+    uint32_t dl = (uint32_t)body[0] | ((uint32_t)body[1] << 8) | ((uint32_t)body[2] << 16) | ((uint32_t)body[3] << 24);
+    const int32_t total = pg.val_len;   // whole uncompressed body
+    if ((int64_t)dl + 4 > total) dl = (uint32_t)(total - 4);   // corrupt length: clamp, the decode kernels stay in bounds
+    pg.def_len = (int32_t)dl;
+    pg.val_ptr = body + 4 + dl;
+    pg.val_len = total - 4 - (int32_t)dl;
+    if (results && pg.job >= 0 && results[pg.job].tail_start == (int32_t)(4 + dl)) pg.val_ptr = results[pg.job].tail_src;   // values were left in place
+    if (dl == 0) pg.def_ptr = nullptr;
+    pages[i] = pg;
+}
+
+PqDecompOut pq_decompress(Ctx& ctx, const std::vector<PqDecompJob>& jobs) {
+    PqDecompOut out;
+    out.status = dalloc_zero(ctx, 4);
+    if (jobs.empty()) return out;
+    out.results = dalloc(ctx, jobs.size() * sizeof(PqDecompResult));
+    Buf dj = to_device(ctx, jobs.data(), jobs.size() * sizeof(PqDecompJob));
+    ProfScope ps(ctx, "pq_decompress");
+    pq_decompress_kernel<<<(unsigned)((jobs.size() + 3) / 4), 128, 0, ctx.stream>>>(P<PqDecompJob>(dj), (int)jobs.size(), P<int32_t>(out.status),
+                                                                                       P<PqDecompResult>(out.results));
+    LAUNCH_CHECK(ctx);
+    return out;
+}
+void pq_fix_v1_pages(Ctx& ctx, PqPage* pages, int n, const PqDecompResult* results) {
+    if (n <= 0) return;
+    pq_fix_v1_pages_kernel<<<(n + 255) / 256, 256, 0, ctx.stream>>>(pages, n, results);
+    LAUNCH_CHECK(ctx);
+}
+
+}  // namespace auron

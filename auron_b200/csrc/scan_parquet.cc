@@ -419,6 +419,11 @@ struct ParquetScanExec : Operator {
             int64_t off;
         };
         std::vector<Fix> fixes;
+        // SNAPPY pages of fixed-width columns are decompressed on the device: jobs with dst as an OFFSET into a scratch
+        // buffer of gpu_unc_bytes that the task thread allocates; `fixes` then patch the descriptors with the scratch base
+        std::vector<PqDecompJob> jobs;
+        int64_t gpu_unc_bytes = 0;
+        bool has_v1_inline = false;
     };
     struct ChunkTask {
         std::shared_ptr<FileState> file;
@@ -440,6 +445,7 @@ struct ParquetScanExec : Operator {
         std::vector<PqByteSection> secs;
         int64_t value_table_size = 0;
         std::vector<Buf> keep;
+        bool has_v1_inline = false;   // some v1 pages still need their level / value sections split on the device
     };
 
     // host-side count of non-null values of a v1 page (needed only for PLAIN string pages)
@@ -474,6 +480,35 @@ struct ParquetScanExec : Operator {
         return nn;
     }
 
+    // `p[0, n)` is a Snappy block of `unc` bytes made of exactly one literal element: returns the offset of the literal's
+    // bytes (> 0), else 0
+    static int64_t snappy_single_literal(const uint8_t* p, int64_t n, int64_t unc) {
+        int64_t i = 0;
+        uint64_t v = 0;
+        for (int shift = 0; shift <= 28; shift += 7) {
+            if (i >= n) return 0;
+            uint8_t b = p[i++];
+            v |= (uint64_t)(b & 0x7f) << shift;
+            if (!(b & 0x80)) break;
+            if (shift == 28) return 0;
+        }
+        if ((int64_t)v != unc || i >= n || unc <= 0) return 0;
+        const uint8_t tag = p[i++];
+        if (tag & 3) return 0;
+        int64_t len = (tag >> 2) + 1;
+        if (len > 60) {
+            const int nb = (int)len - 60;
+            if (i + nb > n) return 0;
+            uint32_t w = 0;
+            for (int k = 0; k < nb; k++) w |= (uint32_t)p[i + k] << (8 * k);
+            i += nb;
+            len = (int64_t)w + 1;
+        }
+        return (len == unc && i + len == n) ? i : 0;
+    }
+    static bool gpu_snappy() {
+        return getenv("AURON_HOST_SNAPPY") == nullptr;   // AURON_HOST_SNAPPY=1: decompress on the host cores instead
+    }
     // pure CPU: walk the pages of one column chunk (thread-safe, no CUDA calls)
     static void parse_chunk(ChunkTask& ct, const pq::SchemaElement& el, bool is_string) {
         const pq::ColumnMeta& cm = *ct.cm;
@@ -483,6 +518,7 @@ struct ParquetScanExec : Operator {
         const int64_t len = cm.total_compressed;
         const int max_def = el.repetition == 1 ? 1 : 0;
         const bool compressed = cm.codec != pq::CODEC_UNCOMPRESSED;
+        const bool dev_snappy = cm.codec == pq::CODEC_SNAPPY && !is_string && gpu_snappy();
         int64_t pos = 0, values_seen = 0, rows = ct.row_start;
         int cur_dict = -1;
         while (pos < len && values_seen < cm.num_values) {
@@ -494,7 +530,33 @@ struct ParquetScanExec : Operator {
             if (h.type == pq::PAGE_INDEX) continue;
             int64_t unc_off = -1;
             int32_t lvl_bytes = h.type == pq::PAGE_DATA_V2 ? h.def_bytes + h.rep_bytes : 0;
-            if (compressed && !(h.type == pq::PAGE_DATA_V2 && !h.v2_compressed)) {
+            const bool page_compressed = compressed && !(h.type == pq::PAGE_DATA_V2 && !h.v2_compressed);
+            // Where the page body ends up: in place (uncompressed, or "stored" below), decompressed on the device (Snappy pages
+            // of fixed-width columns; string pages may need their levels on the host), or decompressed on the host.
+            bool on_device = false;
+            int64_t gap = 0;   // stored v2 page with level sections: Snappy framing bytes between the levels and the values
+            if (page_compressed && dev_snappy) {
+                AURON_CHECK(h.uncompressed_size >= lvl_bytes && h.compressed_size >= lvl_bytes, "corrupt parquet page sizes");
+                // Incompressible pages (bit-packed dictionary indices of random keys) are one Snappy literal: preamble, literal
+                // tag, raw body.  The body is then already in HBM inside the chunk, a few bytes further on: no job, no copy.
+                const int64_t lit = snappy_single_literal(payload_h + lvl_bytes, h.compressed_size - lvl_bytes, h.uncompressed_size - lvl_bytes);
+                if (lit > 0 && lvl_bytes == 0) {
+                    payload_h += lit;
+                    payload_d += lit;
+                } else if (lit > 0) {
+                    gap = lit;
+                } else {
+                    on_device = true;
+                }
+            }
+            if (on_device) {
+                unc_off = out.gpu_unc_bytes;
+                out.gpu_unc_bytes += ((int64_t)h.uncompressed_size + 8 + 15) & ~(int64_t)15;
+                if (lvl_bytes) out.jobs.push_back(PqDecompJob{payload_d, (uint8_t*)(intptr_t)unc_off, lvl_bytes, lvl_bytes, 0, 0});   // v2 levels are stored
+                out.jobs.push_back(PqDecompJob{payload_d + lvl_bytes, (uint8_t*)(intptr_t)(unc_off + lvl_bytes), h.compressed_size - lvl_bytes,
+                                               h.uncompressed_size - lvl_bytes, 1, 0});
+                payload_h = nullptr;
+            } else if (page_compressed && !dev_snappy) {
                 unc_off = (int64_t)out.unc.size();
                 out.unc.resize(out.unc.size() + (size_t)h.uncompressed_size + 8);
                 if (lvl_bytes) memcpy(out.unc.data() + unc_off, payload_h, (size_t)lvl_bytes);   // v2 levels are never compressed
@@ -520,6 +582,7 @@ struct ParquetScanExec : Operator {
             AURON_CHECK(h.type == pq::PAGE_DATA || h.type == pq::PAGE_DATA_V2, "unknown parquet page type");
             PqPage pg;
             memset(&pg, 0, sizeof(pg));
+            pg.job = -1;
             pg.num_values = h.num_values;
             pg.row_start = (int32_t)rows;
             pg.encoding = h.encoding;
@@ -531,11 +594,20 @@ struct ParquetScanExec : Operator {
             if (h.type == pq::PAGE_DATA) {
                 if (max_def > 0) {
                     AURON_CHECK(h.def_encoding == pq::ENC_RLE, "only RLE definition levels are supported");
-                    uint32_t dl;
-                    memcpy(&dl, hp(0), 4);
                     pg.def_ptr = (const uint8_t*)(intptr_t)4;   // offsets now, pointers once the base is known
-                    pg.def_len = (int32_t)dl;
-                    o = 4 + dl;
+                    if (on_device) {
+                        // the length word is inside the compressed body: pq_fix_v1_pages splits the sections on the device
+                        AURON_CHECK(total >= 4, "corrupt parquet page");
+                        pg.def_len = -1;
+                        pg.job = (int32_t)out.jobs.size() - 1;   // the Snappy job pushed for this page above
+                        out.jobs.back().v1_levels = 1;
+                        out.has_v1_inline = true;
+                    } else {
+                        uint32_t dl;
+                        memcpy(&dl, hp(0), 4);
+                        pg.def_len = (int32_t)dl;
+                        o = 4 + dl;
+                    }
                 }
             } else {
                 o = h.rep_bytes;
@@ -547,11 +619,11 @@ struct ParquetScanExec : Operator {
                 o += h.def_bytes;
             }
             AURON_CHECK(o <= total, "corrupt parquet page levels");
-            int64_t val_off = o;
-            pg.val_len = (int32_t)(total - o);
+            int64_t val_off = o + gap;
+            pg.val_len = (int32_t)(total - o);   // v1 inline: the whole body until the device splits it
             const uint8_t* base_d = unc_off >= 0 ? nullptr : payload_d;
             if (base_d) {
-                pg.def_ptr = pg.def_len ? base_d + (intptr_t)pg.def_ptr : nullptr;
+                pg.def_ptr = pg.def_len ? base_d + (intptr_t)pg.def_ptr : nullptr;   // (def_len -1 never reaches here: on_device => no base yet)
                 pg.val_ptr = base_d + val_off;
             } else {
                 pg.val_ptr = (const uint8_t*)(intptr_t)val_off;
@@ -595,6 +667,7 @@ struct ParquetScanExec : Operator {
         AURON_CHECK(ok, "cannot read parquet column " + el.name + " (physical type " + std::to_string(el.type) + ") as " + t.str());
     }
 
+    const PqDecompResult* decomp_results = nullptr;   // results of the current batch's decompression launch (device)
     BatchPtr build_batch(Task& t, std::vector<ColState>& cols, int64_t n_rows) {
         AURON_CHECK(n_rows < (int64_t)INT32_MAX, "parquet batch too large");
         auto out = std::make_shared<Batch>();
@@ -618,6 +691,7 @@ struct ParquetScanExec : Operator {
             memset(&a, 0, sizeof(a));
             Buf dpages = to_device(t.ctx, cs.pages.data(), cs.pages.size() * sizeof(PqPage));
             Buf ddicts = to_device(t.ctx, cs.dicts.empty() ? (const void*)"" : (const void*)cs.dicts.data(), cs.dicts.size() * sizeof(PqDict));
+            if (cs.has_v1_inline) pq_fix_v1_pages(t.ctx, P<PqPage>(dpages), (int)cs.pages.size(), decomp_results);
             a.pages = P<PqPage>(dpages);
             a.dicts = P<PqDict>(ddicts);
             a.n_pages = (int)cs.pages.size();
@@ -977,12 +1051,26 @@ struct ParquetScanExec : Operator {
         }
         Prepared& p = *ready;
         // ordered merge, rebasing dictionary ids / value-table positions; compressed chunks upload their payloads first
+        std::vector<PqDecompJob> decomp_jobs;
         for (auto& ct : p.tasks) {
             ColState& cs = p.cols[ct.col];
             ChunkPages& cp = ct.out;
-            if (!cp.unc.empty()) {
-                Buf d = to_device(t.ctx, cp.unc.data(), cp.unc.size());
-                t.ctx.sync();
+            if (!cp.unc.empty() || cp.gpu_unc_bytes > 0) {
+                Buf d;
+                if (cp.gpu_unc_bytes > 0) {   // decompressed by pq_decompress below, straight from the chunk bytes in HBM
+                    d = dalloc(t.ctx, (size_t)cp.gpu_unc_bytes + 64);
+                    const int32_t job_base = (int32_t)decomp_jobs.size();
+                    for (auto& pg : cp.pages)
+                        if (pg.job >= 0) pg.job += job_base;
+                    for (auto jb : cp.jobs) {
+                        jb.dst = P<uint8_t>(d) + (intptr_t)jb.dst;
+                        decomp_jobs.push_back(jb);
+                    }
+                    cs.has_v1_inline = cs.has_v1_inline || cp.has_v1_inline;
+                } else {
+                    d = to_device(t.ctx, cp.unc.data(), cp.unc.size());
+                    t.ctx.sync();
+                }
                 cs.keep.push_back(d);
                 const uint8_t* base = P<uint8_t>(d);
                 for (auto& fx : cp.fixes) {
@@ -1018,7 +1106,16 @@ struct ParquetScanExec : Operator {
         BatchPtr b;
         {
             OpTimer timer2(metrics, "decode_ns");
-            b = build_batch(t, p.cols, p.rows);
+            PqDecompOut dec = pq_decompress(t.ctx, decomp_jobs);
+            Buf status = dec.status;
+            decomp_results = P<PqDecompResult>(dec.results);
+            b = build_batch(t, p.cols, p.rows);   // ends with a stream sync
+            decomp_results = nullptr;
+            if (!decomp_jobs.empty()) {
+                int32_t st = 0;
+                to_host(t.ctx, &st, status->ptr, 4);
+                AURON_CHECK(st == 0, "corrupt Snappy page in the parquet file (decompression job " + std::to_string(st - 1) + ")");
+            }
         }
         if (p.copy_begin && p.copied) {
             float ms = 0;

@@ -39,6 +39,7 @@ ROWS_PER_FILE = 16_000_000
 DATE_LO, DATE_HI = 2450816, 2452642          # ss_sold_date_sk window (~5 years)
 FILTER_LO, FILTER_HI = 2451000, 2452000      # WHERE ss_sold_date_sk >= lo AND < hi
 N_ITEMS = 204_000                            # item cardinality at SF100
+CODEC = os.environ.get("AURON_BENCH_CODEC", "SNAPPY")   # page compression of the synthetic files (SNAPPY = Spark default; NONE = uncompressed)
 SCHEMA = pa.schema([("ss_item_sk", pa.int32()), ("ss_quantity", pa.int32()), ("ss_sold_date_sk", pa.int32())])
 
 
@@ -49,7 +50,8 @@ def gen_file(path: str, rows: int, seed: int):
         "ss_quantity": pa.array(rng.integers(1, 101, rows, dtype=np.int32), mask=rng.random(rows) < 0.03),
         "ss_sold_date_sk": pa.array(rng.integers(DATE_LO, DATE_HI, rows, dtype=np.int32), mask=rng.random(rows) < 0.04),
     }, schema=SCHEMA)
-    pq.write_table(t, path, compression="NONE", use_dictionary=True, row_group_size=8_000_000, data_page_size=1 << 20)
+    # Spark's writer defaults: SNAPPY pages, dictionary encoding, ~128 MB row groups (8M rows x 3 projected columns)
+    pq.write_table(t, path, compression=CODEC, use_dictionary=True, row_group_size=8_000_000, data_page_size=1 << 20)
 
 
 def gen_dataset(directory: str, total_rows: int) -> list[tuple[str, int]]:
@@ -57,7 +59,7 @@ def gen_dataset(directory: str, total_rows: int) -> list[tuple[str, int]]:
     specs, left, i = [], total_rows, 0
     while left > 0:
         r = min(ROWS_PER_FILE, left)
-        specs.append((os.path.join(directory, f"store_sales_{i:03d}.parquet"), r, 42 + i))
+        specs.append((os.path.join(directory, f"store_sales_{CODEC.lower()}_{i:03d}.parquet"), r, 42 + i))
         left -= r
         i += 1
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
@@ -155,7 +157,8 @@ def main():
     cores = os.cpu_count() or 1
     config = {"workload": "BASELINE configs[1]: ParquetScan->Filter->HashAggregate(GROUP BY int64 ss_item_sk, SUM/COUNT ss_quantity), "
                           "synthetic TPC-DS SF100 store_sales", "rows": args.rows, "groups": N_ITEMS, "filter_selectivity": "~0.53",
-              "parquet": "3 INT32 columns, RLE_DICTIONARY + PLAIN fallback pages, 8M-row row groups, UNCOMPRESSED pages",
+              "parquet": f"3 INT32 columns, RLE_DICTIONARY + PLAIN fallback pages, 8M-row (~128 MB) row groups, {CODEC} pages "
+                         "(decompressed on the GPU)",
               "l2_policy": "inputs (>=1.4 GB encoded, 3.4 GB decoded per step) are far larger than the 126 MB L2",
               "parallelism": f"dp{args.gpus}: table partitions sharded per GPU, no data-path collective"}
 
@@ -196,12 +199,13 @@ def main():
     paths = [f for f, _ in files]
     sizes = [os.path.getsize(f) for f in paths]
     total_rows = sum(r for _, r in files)
-    h2d_bytes = 0
+    h2d_bytes = unc_bytes = 0      # column-chunk bytes as stored (what crosses PCIe) / after page decompression
     for f in paths:
         md = pq.ParquetFile(f).metadata
         for g in range(md.num_row_groups):
             for c in range(md.num_columns):
                 h2d_bytes += md.row_group(g).column(c).total_compressed_size
+                unc_bytes += md.row_group(g).column(c).total_uncompressed_size
 
     os.environ["AURON_PROFILE"] = "1"
     # device chunk = the whole SF100 partition set of this GPU (3.4 GB decoded; HBM is 180 GB)
@@ -300,17 +304,23 @@ def main():
     # partial-mode output = [group, sum acc, count acc] (accumulator fields are unnamed, agg_ctx.rs:127-150)
     sel_rows = int(out.column(2).to_numpy().sum() / 0.97) if out.num_rows else 0        # filtered rows reaching the aggregate (approx)
     decoded_bytes = total_rows * 12 + 2 * total_rows // 8                               # 3 x int32 out + 2 validity bitmaps
-    alg = {   # algorithmic bytes per step for each launch site (DESIGN.md "Kernels and rooflines")
-        "pq_decode_pages": h2d_bytes + decoded_bytes,
-        "expr_vm": None,
-        "agg_update": None,
-        "take": None,
+    alg = {   # algorithmic bytes per step for each launch site (inputs once + outputs once)
+        "pq_decompress": (h2d_bytes + unc_bytes) if CODEC != "NONE" else None,
+        "pq_decode_pages": unc_bytes + decoded_bytes,
+        "simple_predicate": total_rows * 4 + 2 * (total_rows // 8),                 # date column + its validity in, mask out
+        "agg_key_range": total_rows * 4 + total_rows // 8,                            # key column + validity
+        "agg_update": total_rows // 8 + sel_rows * (4 + 4) + sel_rows // 8,          # mask + selected (key, value) + value validity
     }
     roofs = []
     for n in names:
         us = kern[n + ".device_us"] / args.steps
-        roofs.append({"kernel": n, "device_ms_per_step": us / 1000.0, "launches_per_step": kern[n + ".launches"] / args.steps,
-                      "share_of_step": (us / 1e6) / (dt / args.steps)})
+        r = {"kernel": n, "device_ms_per_step": us / 1000.0, "launches_per_step": kern[n + ".launches"] / args.steps,
+             "share_of_step": (us / 1e6) / (dt / args.steps)}
+        if alg.get(n) and us > 0:
+            r["algorithmic_bytes_per_step"] = alg[n]
+            r["achieved_gbs"] = alg[n] / (us * 1e-6) / 1e9
+            r["frac_of_peak"] = r["achieved_gbs"] / peak
+        roofs.append(r)
     dom = names[0] if names else None
     dom_us = kern[dom + ".device_us"] / args.steps if dom else None
     dom_bytes = alg.get(dom) if dom else None

@@ -146,3 +146,45 @@ def test_scan_filter_aggregate_config2_small(tmp_path):
         else:
             os.environ["AURON_GPU_CHUNK_ROWS"] = old
     assert_same_rows(got3, exp)
+
+
+@pytest.mark.parametrize("version", ["1.0", "2.0"])
+@pytest.mark.parametrize("dict_", [True, False])
+def test_scan_snappy_pages_decompressed_on_device(tmp_path, version, dict_, monkeypatch):
+    # compressible fixed-width columns: long runs, short periodic patterns (overlapping back references), sorted keys,
+    # next to an incompressible column (a single literal per 64 KB block); v1 pages carry their level length inside the body
+    rng = np.random.default_rng(5)
+    n = 200_003
+    t = pa.table({
+        "runs": pa.array(np.repeat(rng.integers(0, 50, n // 1000 + 1), 1000)[:n].astype(np.int32), mask=rng.random(n) < 0.02),
+        "period": pa.array((np.arange(n) % 7).astype(np.int64) * 1_000_003),
+        "sorted": pa.array(np.sort(rng.integers(0, 10**6, n)).astype(np.int64), mask=rng.random(n) < 0.3),
+        "noise": pa.array(rng.integers(-2**31, 2**31 - 1, n).astype(np.int32), mask=rng.random(n) < 0.05),
+        "f": pa.array(np.round(rng.standard_normal(n), 1)),
+        "flag": pa.array((np.arange(n) // 100) % 2 == 0, mask=rng.random(n) < 0.01),
+        "allnull": pa.array([None] * n, type=pa.int32()),
+    })
+    path = str(tmp_path / "c.parquet")
+    pq.write_table(t, path, compression="SNAPPY", use_dictionary=dict_, data_page_version=version, row_group_size=70_000, data_page_size=32 * 1024)
+    exp = pq.read_table(path)
+    got = _scan(path, t.schema)
+    monkeypatch.setenv("AURON_HOST_SNAPPY", "1")
+    got_host = _scan(path, t.schema)
+    for name in t.column_names:
+        assert got[name].to_pylist() == exp[name].to_pylist(), name
+        assert got_host[name].to_pylist() == exp[name].to_pylist(), name
+
+
+def test_scan_reports_corrupt_snappy_page(tmp_path):
+    n = 20_000
+    t = pa.table({"a": pa.array(np.arange(n, dtype=np.int64) % 13)})
+    path = str(tmp_path / "bad.parquet")
+    pq.write_table(t, path, compression="SNAPPY", use_dictionary=False)
+    md = pq.ParquetFile(path).metadata.row_group(0).column(0)
+    raw = bytearray(open(path, "rb").read())
+    off = md.data_page_offset + 40          # inside the first page body: turn literals into impossible back references
+    for i in range(off, off + 64):
+        raw[i] = 0xFF
+    open(path, "wb").write(bytes(raw))
+    with pytest.raises(runtime.AuronError):
+        _scan(path, t.schema)

@@ -58,6 +58,9 @@ for mode, pl in (("pinned", pins), ("files", paths), ("hbm", hbm)):
             task.__exit__(None, None, None)
             t3 = time.perf_counter()
             ms = 1000 * (t3 - t0)
+            if os.environ.get("PROBE_DUMP") and it == int(os.environ.get("PROBE_STEPS", "8")) - 1:
+                for depth, op, name, v in m:
+                    print(f"    {'  ' * depth}{op}.{name} = {v}")
             scan = {name: v for _, op, name, v in m if op == "ParquetExec"}
             keys = ("elapsed_ns", "fetch_ns", "wait_fetch_ns", "parse_ns", "decode_ns")
             print(f"  step {it}: {ms:7.1f} ms  " + "  ".join(f"{k[:-3]}={scan.get(k, 0) / 1e6:.1f}ms" for k in keys)
