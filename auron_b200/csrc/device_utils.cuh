@@ -228,4 +228,57 @@ __device__ inline i128 u128_divmod_u64(i128 a, uint64_t d, uint64_t* rem) {
     return {qlo, (int64_t)qhi};
 }
 
+// ---- warp-cooperative byte copy (page decompression, shuffle block assembly)
+// 16 bytes of the byte stream that starts `sb` (0..15) bytes into the aligned vector pair (a, b)
+__device__ __forceinline__ uint4 shift16(const uint4& a, const uint4& b, unsigned sb) {
+    const unsigned bs = (sb & 3) * 8;
+    uint4 r;
+    switch (sb >> 2) {   // uniform across the warp
+        case 0: r.x = __funnelshift_r(a.x, a.y, bs), r.y = __funnelshift_r(a.y, a.z, bs), r.z = __funnelshift_r(a.z, a.w, bs), r.w = __funnelshift_r(a.w, b.x, bs); break;
+        case 1: r.x = __funnelshift_r(a.y, a.z, bs), r.y = __funnelshift_r(a.z, a.w, bs), r.z = __funnelshift_r(a.w, b.x, bs), r.w = __funnelshift_r(b.x, b.y, bs); break;
+        case 2: r.x = __funnelshift_r(a.z, a.w, bs), r.y = __funnelshift_r(a.w, b.x, bs), r.z = __funnelshift_r(b.x, b.y, bs), r.w = __funnelshift_r(b.y, b.z, bs); break;
+        default: r.x = __funnelshift_r(a.w, b.x, bs), r.y = __funnelshift_r(b.x, b.y, bs), r.z = __funnelshift_r(b.y, b.z, bs), r.w = __funnelshift_r(b.z, b.w, bs); break;
+    }
+    return r;
+}
+// dst[0, len) = src[0, len); no overlap; any alignment.  Bulk: 16-byte stores at the destination's alignment, the source
+// re-aligned from two 16-byte loads (512 B per warp instruction, two vectors in flight per lane).
+__device__ __forceinline__ void warp_copy(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int64_t len, unsigned lane) {
+    if (len < 256) {
+        for (int64_t i = lane; i < len; i += 32) dst[i] = src[i];
+        return;
+    }
+    const int head = (int)((16 - ((uintptr_t)dst & 15)) & 15);
+    if ((int)lane < head) dst[lane] = src[lane];
+    dst += head;
+    src += head;
+    len -= head;
+    int64_t nv = len >> 4;                       // whole 16-byte vectors
+    const uintptr_t sa = (uintptr_t)src;
+    const uint4* sv = (const uint4*)(sa & ~(uintptr_t)15);
+    const unsigned sb = (unsigned)(sa & 15);
+    uint4* dv = (uint4*)dst;
+    if (sb == 0) {
+        int64_t j = lane;
+        for (; j + 32 < nv; j += 64) {
+            const uint4 a = sv[j], b = sv[j + 32];
+            dv[j] = a;
+            dv[j + 32] = b;
+        }
+        for (; j < nv; j += 32) dv[j] = sv[j];
+    } else {
+        // the last vector would read 16 bytes past the source's aligned end: leave it to the byte tail
+        nv -= 1;
+        int64_t j = lane;
+        for (; j + 32 < nv; j += 64) {
+            const uint4 a0 = sv[j], a1 = sv[j + 1], b0 = sv[j + 32], b1 = sv[j + 33];
+            dv[j] = shift16(a0, a1, sb);
+            dv[j + 32] = shift16(b0, b1, sb);
+        }
+        for (; j < nv; j += 32) dv[j] = shift16(sv[j], sv[j + 1], sb);
+    }
+    for (int64_t i = (nv << 4) + lane; i < len; i += 32) dst[i] = src[i];
+}
+
+
 }  // namespace auron

@@ -120,6 +120,27 @@ struct SerializedParts {
     std::vector<int64_t> part_offsets;   // num_parts+1 (uncompressed payload offsets)
 };
 SerializedParts serialize_partitions(Ctx& ctx, const Batch& sorted_batch, const std::vector<int64_t>& row_offsets);
+// LZ4-frame compression on device (k_lz4.cu): one warp per <= 64 KB block, then assembly of the partition streams
+struct Lz4Block {
+    const uint8_t* src;   // raw bytes of the block
+    uint8_t* dst;         // scratch slot of lz4_block_bound(len) bytes
+    int32_t len;
+    int32_t pad;
+};
+struct Lz4Place {
+    const uint8_t* src;   // compressed bytes (scratch) or the raw bytes when the block is stored
+    uint8_t* dst;         // position of the block's 4-byte size word in the output image
+    int32_t len;          // data bytes that follow the size word
+    uint32_t size_word;   // len, high bit set for a stored block
+    uint32_t flags;       // 1 = first block of its stream (writes u32 stream length + 7-byte frame header at dst-11), 2 = last (end mark)
+    uint32_t stream_len;  // frame bytes of the stream (flag 1)
+    uint8_t header[8];    // frame header (flag 1)
+};
+constexpr int kLz4BlockBytes = 64 * 1024;
+inline int64_t lz4_block_bound(int64_t n) { return n + n / 255 + 32; }
+void lz4_compress_blocks(Ctx& ctx, const Lz4Block* dev_blocks, int n_blocks, int32_t* dev_sizes);
+void lz4_assemble(Ctx& ctx, const Lz4Place* dev_places, int n);
+
 BatchPtr deserialize_batch(Ctx& ctx, const Schema& schema, const uint8_t* host_bytes, int64_t nbytes, int64_t* consumed);
 
 }  // namespace auron

@@ -26,6 +26,7 @@
 #include "../../include/auron_b200.h"
 #include "operators.h"
 #include "parquet_dev.h"
+#include "host_pool.h"
 #include "parquet_meta.h"
 #include "pb.h"
 
@@ -106,99 +107,6 @@ static void host_decompress(int codec, const uint8_t* in, size_t in_len, uint8_t
     }
 }
 
-// Persistent host worker pool (process-wide).  Spawning 32 std::threads per parallel_for cost ~0.6 ms per scan batch,
-// more than the page-header parsing they were spawned for.
-class WorkerPool {
-  public:
-    struct Job {
-        std::function<void()> work;
-        int outstanding = 0;   // tickets handed to the pool and not yet finished (guarded by pool mutex)
-    };
-    static WorkerPool& get() {
-        static WorkerPool* pool = new WorkerPool();   // leaked on purpose: workers may outlive static destruction
-        return *pool;
-    }
-    // run job.work() on up to `extra` pool workers in addition to the caller; returns when all of them are done
-    void run(Job& job, unsigned extra) {
-        extra = std::min<unsigned>(extra, (unsigned)workers_.size());
-        {
-            std::lock_guard<std::mutex> l(mu_);
-            job.outstanding = (int)extra;
-            for (unsigned i = 0; i < extra; i++) tickets_.push_back(&job);
-        }
-        if (extra == 1) cv_.notify_one();
-        else if (extra > 1) cv_.notify_all();
-        job.work();
-        std::unique_lock<std::mutex> l(mu_);
-        for (auto it = tickets_.begin(); it != tickets_.end();) {   // tickets nobody picked up yet are not needed any more
-            if (*it == &job) {
-                it = tickets_.erase(it);
-                job.outstanding--;
-            } else ++it;
-        }
-        done_cv_.wait(l, [&] { return job.outstanding == 0; });
-    }
-
-  private:
-    WorkerPool() {
-        unsigned n = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
-        for (unsigned i = 0; i < n; i++) {
-            workers_.emplace_back([this] { loop(); });
-            workers_.back().detach();
-        }
-    }
-    void loop() {
-        for (;;) {
-            Job* j;
-            {
-                std::unique_lock<std::mutex> l(mu_);
-                cv_.wait(l, [&] { return !tickets_.empty(); });
-                j = tickets_.front();
-                tickets_.pop_front();
-            }
-            j->work();
-            std::lock_guard<std::mutex> l(mu_);
-            if (--j->outstanding == 0) done_cv_.notify_all();
-        }
-    }
-    std::mutex mu_;
-    std::condition_variable cv_, done_cv_;
-    std::deque<Job*> tickets_;
-    std::vector<std::thread> workers_;
-};
-
-// run fn(i) for i in [0, n) on up to `threads` host threads; the first exception is rethrown
-template <typename F>
-static void parallel_for(size_t n, unsigned threads, F fn) {
-    if (n == 0) return;
-    threads = (unsigned)std::max<size_t>(1, std::min<size_t>(threads, n));
-    if (threads == 1) {
-        for (size_t i = 0; i < n; i++) fn(i);
-        return;
-    }
-    std::atomic<size_t> next{0};
-    std::mutex mu;
-    std::string err;
-    WorkerPool::Job job;
-    job.work = [&]() {
-        for (;;) {
-            size_t i = next.fetch_add(1);
-            if (i >= n) return;
-            try {
-                fn(i);
-            } catch (const std::exception& e) {
-                std::lock_guard<std::mutex> l(mu);
-                if (err.empty()) err = e.what();
-            } catch (...) {
-                std::lock_guard<std::mutex> l(mu);
-                if (err.empty()) err = "unknown failure in a scan worker";
-            }
-        }
-    };
-    WorkerPool::get().run(job, threads - 1);
-    if (!err.empty()) fail(err);
-}
-
 // ------------------------------------------------------------------------------------------ operator
 struct PqFileSpec {
     std::string path;
@@ -262,34 +170,6 @@ struct ParquetScanExec : Operator {
             done += r;
         }
     }
-    // pinned staging comes from a process-wide pool: cudaHostAlloc costs ~0.4 s per GB, far more than the copy it feeds
-    struct PinnedPool {
-        std::mutex mu;
-        std::vector<std::pair<void*, size_t>> free_list;
-        void* get(size_t n, size_t* cap) {
-            std::lock_guard<std::mutex> l(mu);
-            size_t best = SIZE_MAX;
-            for (size_t i = 0; i < free_list.size(); i++)
-                if (free_list[i].second >= n && (best == SIZE_MAX || free_list[i].second < free_list[best].second)) best = i;
-            if (best != SIZE_MAX) {
-                auto e = free_list[best];
-                free_list.erase(free_list.begin() + best);
-                *cap = e.second;
-                return e.first;
-            }
-            for (auto& e : free_list) cudaFreeHost(e.first);   // too small: replace rather than accumulate
-            free_list.clear();
-            void* p = nullptr;
-            size_t c = std::max<size_t>(n + n / 8, 64 << 20);
-            CUDA_OK(cudaHostAlloc(&p, c, cudaHostAllocDefault));
-            *cap = c;
-            return p;
-        }
-        void put(void* p, size_t cap) {
-            std::lock_guard<std::mutex> l(mu);
-            free_list.emplace_back(p, cap);
-        }
-    };
     // Device-side landing buffers for encoded column chunks.  Plain cudaMalloc blocks recycled across batches and
     // tasks: a stream-ordered allocation made by the producer thread on the copy stream contends with the task
     // thread's own cudaMallocAsync calls inside the driver (measured: 115 KB allocations stalling for 5..155 ms).
@@ -334,10 +214,6 @@ struct ParquetScanExec : Operator {
     };
     static DevStagePool& dev_stage_pool() {
         static DevStagePool pool;
-        return pool;
-    }
-    static PinnedPool& pinned_pool() {
-        static PinnedPool pool;
         return pool;
     }
     void* staging(size_t n) {

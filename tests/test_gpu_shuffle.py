@@ -55,9 +55,14 @@ def _table(n, seed):
     })
 
 
-@pytest.mark.parametrize("codec", ["lz4", "zstd"])
-@pytest.mark.parametrize("n,nparts,chunk_rows", [(1000, 4, None), (100_000, 200, None), (100_000, 13, 30_000)])
-def test_hash_partition_shuffle_write(tmp_path, codec, n, nparts, chunk_rows):
+@pytest.mark.parametrize("codec", ["lz4", "zstd", "lz4-host"])
+@pytest.mark.parametrize("n,nparts,chunk_rows", [(1000, 4, None), (100_000, 200, None), (100_000, 13, 30_000), (200_000, 3, None)])
+def test_hash_partition_shuffle_write(tmp_path, codec, n, nparts, chunk_rows, monkeypatch):
+    # "lz4" frames are produced on the GPU (64 KB independent blocks; the 3-partition case has ~40 blocks per stream),
+    # "lz4-host" by liblz4 on the host cores, "zstd" by libzstd on the host cores
+    if codec == "lz4-host":
+        monkeypatch.setenv("AURON_HOST_LZ4", "1")
+        codec = "lz4"
     t = _table(n, seed=n + nparts)
     data, index = str(tmp_path / "shuffle.data"), str(tmp_path / "shuffle.index")
     plan = P.shuffle_writer(P.ffi_reader(t.schema, "t"), P.hash_repartition([P.col("k"), P.col("s")], nparts), data, index)
