@@ -115,6 +115,20 @@ Buf hash_columns(Ctx& ctx, const std::vector<ColumnPtr>& cols, int64_t n, int ki
     return out;
 }
 
+// RoundRobinPartitioning: row i of the chunk goes to (i + start) % num_parts (evaluate_robin_partition_ids, shuffle/mod.rs:190-202)
+__global__ void round_robin_ids_kernel(int32_t* __restrict__ out, int64_t n, int64_t start, int32_t num_parts) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int32_t)((i + start) % num_parts);
+}
+Buf round_robin_partition_ids(Ctx& ctx, int64_t n, int64_t start, int32_t num_parts) {
+    Buf out = dalloc(ctx, (size_t)std::max<int64_t>(n, 1) * 4);
+    if (n > 0) {
+        round_robin_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx.stream>>>(P<int32_t>(out), n, start, num_parts);
+        CUDA_OK(cudaGetLastError());
+        launch_count(ctx);
+    }
+    return out;
+}
 Buf murmur3_partition_ids(Ctx& ctx, const std::vector<ColumnPtr>& cols, int64_t n, int32_t num_parts, int32_t seed) {
     AURON_CHECK(num_parts > 0, "num_parts must be positive");
     HashArgs a = make_args(cols);

@@ -214,8 +214,13 @@ struct ShuffleWriterExec : Operator {
                 std::vector<ColumnPtr> keys;
                 for (auto& e : hash_exprs) keys.push_back(eval_to_column(t, e, children[0]->out_schema, *in));
                 pids = murmur3_partition_ids(ctx, keys, n, (int32_t)num_parts, 42);
+            } else if (kind == 3) {
+                // sort_batches_by_partition_id (buffered_data.rs:291-312): the first row of a flush starts at
+                // (partition_id * 1000193 + rows written so far) % N
+                int64_t start = (int64_t)(((uint64_t)t.partition_id * 1000193ull + (uint64_t)rows_so_far) % (uint64_t)num_parts);
+                pids = round_robin_partition_ids(ctx, n, start, (int32_t)num_parts);
             } else {
-                fail("round-robin / range repartitioning on device is not built yet (hash and single are)");
+                fail("range repartitioning on device is not built yet (hash, round-robin and single are)");
             }
             Buf rows, offs;
             partition_rows(ctx, P<int32_t>(pids), n, (int32_t)num_parts, &rows, &offs);

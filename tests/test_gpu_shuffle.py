@@ -98,3 +98,24 @@ def test_single_partition_and_empty_input(tmp_path):
     run(P.shuffle_writer(P.ffi_reader(t.schema, "t"), P.hash_repartition([P.col("k")], 8), data, index), {"t": t.slice(0, 0)})
     assert os.path.getsize(data) == 0
     assert struct.unpack("<9q", open(index, "rb").read()) == (0,) * 9     # zero rows => all-zero index (buffered_data.rs:124-126)
+
+
+@pytest.mark.parametrize("partition_id,chunk_rows", [(0, None), (7, 20_000)])
+def test_round_robin_shuffle_write(tmp_path, partition_id, chunk_rows):
+    # evaluate_robin_partition_ids (shuffle/mod.rs:190-202) with the start offset of buffered_data.rs:291-312:
+    # row i of the task goes to (partition_id * 1000193 + i) % N
+    n, nparts = 50_001, 7
+    t = _table(n, seed=99)
+    data, index = str(tmp_path / "rr.data"), str(tmp_path / "rr.index")
+    plan = P.shuffle_writer(P.ffi_reader(t.schema, "t"), P.round_robin_repartition(nparts), data, index)
+    td = P.task_definition(plan, stage_id=1, partition_id=partition_id, task_id=3)
+    if chunk_rows:
+        os.environ["AURON_GPU_CHUNK_ROWS"] = str(chunk_rows)
+    try:
+        runtime.run_task(td, {"t": batches(t, chunk_rows)})
+    finally:
+        os.environ.pop("AURON_GPU_CHUNK_ROWS", None)
+    parts, offsets = read_shuffle_files(data, index, t.schema)
+    pid = (partition_id * 1000193 + np.arange(n)) % nparts
+    for p in range(nparts):
+        assert_same_rows(parts[p], t.filter(pa.array(pid == p)))
