@@ -51,7 +51,7 @@ enum Op : uint16_t {
     OP_DATEPART, OP_NULLIFZERO, OP_ISNAN, OP_NORMNAN, OP_CHECK_OVERFLOW, OP_MAKE_DECIMAL, OP_UNSCALED,
     OP_MATH1, OP_POW, OP_HASH,
     OP_BITAND, OP_BITOR, OP_BITXOR, OP_SHL, OP_SHR,
-    OP_OUT, OP_OUT_PRED,
+    OP_OUT, OP_OUT_PRED, OP_FMT_OUT,
 };
 enum DatePart : int { DP_YEAR = 0, DP_MONTH, DP_DAY, DP_DOW, DP_QUARTER, DP_WEEK, DP_DOY };
 enum Math1 : int { M_SQRT = 0, M_EXP, M_LN, M_LOG10, M_LOG2, M_SIN, M_COS, M_TAN, M_ASIN, M_ACOS, M_ATAN, M_CEIL, M_FLOOR, M_SIGNUM, M_TRUNC, M_EXPM1 };
@@ -505,6 +505,73 @@ __device__ inline bool vm_cast(const VmParams& p, int st, int dt, int sscale, in
 }
 
 // ------------------------------------------------------------------------------------------ the VM kernel
+// ---- CAST(x AS STRING) of a projection output (TryCastExpr -> arrow cast; bool: cast.rs:104-112, decimal: cast.rs:660-690):
+// format `kind` value into buf (>= 24 bytes), returns the length.  kind: 0 bool, 1 integer, 2 date32, 3 decimal (scale)
+enum FmtKind : int { FMT_BOOL = 0, FMT_INT = 1, FMT_DATE = 2, FMT_DEC = 3 };
+__device__ inline int fmt_u64(uint64_t v, char* end) {   // writes digits backwards, returns count
+    int n = 0;
+    do {
+        *--end = (char)('0' + (int)(v % 10));
+        v /= 10;
+        n++;
+    } while (v);
+    return n;
+}
+__device__ inline int fmt_value(int kind, int scale, uint64_t lo, char* buf) {
+    char tmp[24];
+    char* end = tmp + 24;
+    int n = 0;
+    if (kind == FMT_BOOL) {
+        const char* t = lo ? "true" : "false";
+        n = lo ? 4 : 5;
+        for (int i = 0; i < n; i++) buf[i] = t[i];
+        return n;
+    }
+    if (kind == FMT_DATE) {
+        int64_t y;
+        unsigned m, d;
+        civil_from_days((int64_t)(int32_t)lo, &y, &m, &d);
+        int k = 0;
+        if (y < 0) {
+            buf[k++] = '-';
+            y = -y;
+        }
+        int yd = fmt_u64((uint64_t)y, end);
+        for (int i = yd; i < 4; i++) buf[k++] = '0';
+        for (int i = 0; i < yd; i++) buf[k++] = (end - yd)[i];
+        buf[k++] = '-';
+        buf[k++] = (char)('0' + m / 10);
+        buf[k++] = (char)('0' + m % 10);
+        buf[k++] = '-';
+        buf[k++] = (char)('0' + d / 10);
+        buf[k++] = (char)('0' + d % 10);
+        return k;
+    }
+    const int64_t sv = (int64_t)lo;
+    const bool neg = sv < 0;
+    const uint64_t mag = neg ? (uint64_t)0 - (uint64_t)sv : (uint64_t)sv;
+    n = fmt_u64(mag, end);
+    const char* digits = end - n;
+    int k = 0;
+    if (neg) buf[k++] = '-';
+    if (kind == FMT_INT || scale <= 0) {
+        for (int i = 0; i < n; i++) buf[k++] = digits[i];
+        return k;
+    }
+    // decimal: integer part (at least "0"), '.', `scale` fractional digits
+    if (n > scale) {
+        for (int i = 0; i < n - scale; i++) buf[k++] = digits[i];
+        buf[k++] = '.';
+        for (int i = n - scale; i < n; i++) buf[k++] = digits[i];
+    } else {
+        buf[k++] = '0';
+        buf[k++] = '.';
+        for (int i = n; i < scale; i++) buf[k++] = '0';
+        for (int i = 0; i < n; i++) buf[k++] = digits[i];
+    }
+    return k;
+}
+
 template <bool HI>
 __global__ void __launch_bounds__(VM_THREADS) vm_kernel(VmParams p) {
     extern __shared__ __align__(16) uint64_t vm_smem[];
@@ -980,6 +1047,21 @@ __global__ void __launch_bounds__(VM_THREADS) vm_kernel(VmParams p) {
                         }
                         uint32_t w = __ballot_sync(FULL_MASK, v);
                         if ((tid & 31) == 0 && active) p.out_valid[o][i >> 5] = w;
+                    }
+                    break;
+                }
+                case OP_FMT_OUT: {   // CAST(value AS STRING) straight into a utf8 output column (both passes format the value)
+                    const int o = ins.aux;
+                    bool v = active && VALID(ins.a);
+                    char buf[44];
+                    int len = v ? fmt_value((ins.aux2 >> 8) & 0xff, ins.aux2 & 0xff, RLO(ins.a), buf) : 0;
+                    if (p.mode == 0) {
+                        if (active) p.out_lens[o][i] = len;
+                        uint32_t w = __ballot_sync(FULL_MASK, v);
+                        if ((tid & 31) == 0 && active) p.out_valid[o][i >> 5] = w;
+                    } else if (v) {
+                        uint8_t* d = (uint8_t*)p.out_data[o] + p.out_off[o][i];
+                        for (int k = 0; k < len; k++) d[k] = (uint8_t)buf[k];
                     }
                     break;
                 }
@@ -1732,6 +1814,25 @@ VmProgram compile_projection(const std::vector<ExprPtr>& exprs, const Schema& in
     Compiler c(input, *p.impl);
     AURON_CHECK(exprs.size() <= VM_MAX_COLS, "too many projection expressions for one program");
     for (size_t i = 0; i < exprs.size(); i++) {
+        const Expr& ex = *exprs[i];
+        if ((ex.kind == E_CAST || ex.kind == E_TRY_CAST) && ex.type.id == T_UTF8) {
+            DType st = infer_type(*ex.children[0], input);
+            int kind = -1, scale = 0;
+            if (st.id == T_BOOL) kind = FMT_BOOL;
+            else if (st.is_integer()) kind = FMT_INT;
+            else if (st.id == T_DATE32) kind = FMT_DATE;
+            else if (st.id == T_DECIMAL128 && st.precision <= 18 && st.scale >= 0 && st.scale <= 18) kind = FMT_DEC, scale = st.scale;
+            if (kind >= 0) {   // formatted directly into the output column; a string CAST nested inside another expression is not built
+                Compiler::Val v = c.gen(*ex.children[0]);
+                c.note_type(v.type);
+                c.note_type(ex.type);
+                c.emit(OP_FMT_OUT, 0, v.reg, 0, 0, vt_of(v.type), 0, (int)i, (kind << 8) | scale);
+                c.release(v.reg);
+                p.out_types.push_back(ex.type);
+                p.impl->out_vt.push_back(VT_STR);
+                continue;
+            }
+        }
         Compiler::Val v = c.gen(*exprs[i]);
         DType t = v.type;
         if (t.id == T_NULL) fail("projection of an untyped NULL");

@@ -259,6 +259,7 @@ __global__ void jfill_u64(unsigned long long* p, int64_t n, unsigned long long v
 }
 
 std::shared_ptr<JoinTable> join_build(Ctx& ctx, const std::vector<ColumnPtr>& build_keys, int64_t n_build) {
+    ProfScope ps_fn(ctx, "join_build");
     AURON_CHECK(n_build < (1ll << 30), "join build side must be < 2^30 rows (join_hash_map.rs:100-103)");
     auto t = std::make_shared<JoinTable>();
     t->fast = jfast_ok(build_keys);
@@ -313,6 +314,7 @@ std::shared_ptr<JoinTable> join_build(Ctx& ctx, const std::vector<ColumnPtr>& bu
 
 JoinPairs join_probe(Ctx& ctx, const JoinTable& t, const std::vector<ColumnPtr>& probe_keys, int64_t n_probe, bool probe_outer,
                      uint32_t* matched_build, Buf* probe_matched_out) {
+    ProfScope ps_fn(ctx, "join_probe");
     JoinPairs out;
     AURON_CHECK(n_probe < (int64_t)INT32_MAX, "probe chunk too large");
     AURON_CHECK(probe_keys.size() == t.keys.size(), "join key arity mismatch");

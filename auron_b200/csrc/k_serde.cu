@@ -105,6 +105,7 @@ static int put_varint(uint64_t v, uint8_t* out) {   // io/mod.rs:61-69
 }
 
 SerializedParts serialize_partitions(Ctx& ctx, const Batch& b, const std::vector<int64_t>& row_offsets) {
+    ProfScope ps_fn(ctx, "serde_write");
     const int num_parts = (int)row_offsets.size() - 1;
     const int ncols = (int)b.cols.size();
     SerializedParts res;

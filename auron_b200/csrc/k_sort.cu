@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint64_t* 
 constexpr size_t RS_SMEM = RS_TILE * 12 + RS_WARPS * 256 * 4 + 256 * 4 + 256 * 4;
 
 void radix_sort_pairs_u64(Ctx& ctx, Buf& keys, Buf& vals, int64_t n, int begin_bit, int end_bit) {
+    ProfScope ps_fn(ctx, "radix_sort");
     if (n <= 1) return;
     AURON_CHECK(n < (int64_t)INT32_MAX, "sort chunk too large");
     static bool attr_set = false;
@@ -353,6 +354,7 @@ __global__ void __launch_bounds__(256) pid_hist_kernel(const int32_t* __restrict
 }
 
 void partition_rows(Ctx& ctx, const int32_t* part_ids, int64_t n, int32_t num_parts, Buf* rows_out, Buf* offsets_out) {
+    ProfScope ps_fn(ctx, "partition_rows");
     Buf counts = dalloc_zero(ctx, (size_t)(num_parts + 1) * 8);
     Buf rows = dalloc(ctx, (size_t)std::max<int64_t>(n, 1) * 4);
     fill_iota_i32(ctx, P<int32_t>(rows), n, 0);

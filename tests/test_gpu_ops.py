@@ -242,6 +242,33 @@ def test_casts_golden():
     assert got["f"].to_pylist() == [None, 123.456, -0.005, 99999.995, -7.5]
 
 
+def test_casts_to_string_golden_and_vs_arrow():
+    # cast.rs:536-552 (bool -> "true"/"false"), cast.rs:660-690 (decimal -> plain string with `scale` fraction digits); integers and
+    # dates go through arrow's cast in the reference: compared with Arrow C++ here
+    b = pa.table({"b": pa.array([None, True, False])})
+    assert _eval(b, [P.try_cast(P.col("b"), pa.string())], ["s"], [pa.string()])["s"].to_pylist() == [None, "true", "false"]
+    d = pa.table({"d": pa.array([None, decimal.Decimal("123.000000"), decimal.Decimal("-987.654321"), decimal.Decimal("0.000005"), decimal.Decimal("-0.500000"),
+                                 decimal.Decimal("999999999999.999999")], type=pa.decimal128(18, 6)),
+                  "z": pa.array([None, decimal.Decimal(7), decimal.Decimal(-12345), decimal.Decimal(0), decimal.Decimal(10), decimal.Decimal(-1)], type=pa.decimal128(9, 0))})
+    got = _eval(d, [P.try_cast(P.col("d"), pa.string()), P.try_cast(P.col("z"), pa.string())], ["s", "t"], [pa.string(), pa.string()])
+    assert got["s"].to_pylist() == [None, "123.000000", "-987.654321", "0.000005", "-0.500000", "999999999999.999999"]
+    assert got["t"].to_pylist() == [None, "7", "-12345", "0", "10", "-1"]
+    rng = np.random.default_rng(4)
+    n = 20_000
+    t = pa.table({"i8": pa.array(rng.integers(-128, 128, n), type=pa.int8(), mask=rng.random(n) < 0.05),
+                  "i32": pa.array(rng.integers(-2**31, 2**31, n), type=pa.int32(), mask=rng.random(n) < 0.05),
+                  "i64": pa.array(np.concatenate([[-2**63, 2**63 - 1, 0, -1], rng.integers(-2**62, 2**62, n - 4)]), type=pa.int64()),
+                  "dt": pa.array(rng.integers(-200_000, 200_000, n).astype(np.int32), type=pa.date32(), mask=rng.random(n) < 0.05)})
+    got = _eval(t, [P.try_cast(P.col(c), pa.string()) for c in t.column_names] + [P.try_cast(P.binary("Plus", P.col("i32"), P.col("i32")), pa.string())],
+                t.column_names + ["sum"], [pa.string()] * 5)
+    for c in ("i8", "i32", "i64"):
+        assert got[c].to_pylist() == t[c].cast(pa.string()).to_pylist(), c
+    exp_dt = [None if v is None else (f"{v.year:04d}-{v.month:02d}-{v.day:02d}") for v in t["dt"].to_pylist()]
+    assert got["dt"].to_pylist() == exp_dt
+    exp_sum = [None if v is None else str((int(v) * 2 + 2**31) % 2**32 - 2**31) for v in t["i32"].to_pylist()]
+    assert got["sum"].to_pylist() == exp_sum                                    # wrapping int32 addition, then formatted
+
+
 def test_string_predicates_golden():
     # datafusion-ext-exprs/src/string_starts_with.rs:137-165, string_ends_with.rs:137-168, string_contains.rs:136-168
     s1 = pa.table({"s": pa.array([None, "rabaok", "rraara", "s_skdo[]ra.,?';,{}\ra", " raefuwidn"])})

@@ -34,7 +34,11 @@ def put(resource, table):
         runtime.put_device_batch(resource, b)
 
 
-def run(plan, label, rows, steps=4, consume=True):
+PEAK = 6575.1   # GB/s, MEASURED_PEAKS.json hbm_gbs of this pool's B200s
+
+
+def run(plan, label, rows, steps=4, alg=None):
+    """alg: {launch site: algorithmic bytes per pass} (inputs once + outputs once)"""
     td = P.task_definition(plan)
     best = None
     for it in range(steps):
@@ -54,7 +58,11 @@ def run(plan, label, rows, steps=4, consume=True):
         if op == "__kernels__" and name.endswith(".device_us"):
             kern[name[:-10]] = v
     for k, v in sorted(kern.items(), key=lambda kv: -kv[1]):
-        print(f"     {k:28s} {v / 1000:9.3f} ms")
+        extra = ""
+        if alg and alg.get(k) and v > 0:
+            gbs = alg[k] / (v * 1e-6) / 1e9
+            extra = f"   {alg[k] / 1e9:7.2f} GB algorithmic -> {gbs:7.0f} GB/s = {100 * gbs / PEAK:4.1f} % of {PEAK:.0f}"
+        print(f"     {k:28s} {v / 1000:9.3f} ms{extra}")
     for _, op, name, v in m:
         if op != "__kernels__" and name.endswith("_ns") and v > 2e5:
             print(f"     [{op}.{name} = {v / 1e6:.2f} ms]")
@@ -75,7 +83,11 @@ if "join" in which:
                     [(P.col("d_date_sk"), P.col("ss_sold_date_sk"))], "INNER", "LEFT")
     plan = P.agg(j, [], [], [P.agg_expr("SUM", [P.col("ss_quantity")], pa.int64()), P.agg_expr("SUM", [P.col("d_year")], pa.int64()),
                              P.agg_expr("COUNT", [P.col("ss_item_sk")], pa.int64())], ["q", "y", "c"], ["PARTIAL"] * 3)
-    run(plan, f"cfg3 HashJoin build=date_dim(73,049) probe={N} rows + global SUM/COUNT of the joined rows", N)
+    matched = int(N * 0.96)
+    run(plan, f"cfg3 HashJoin build=date_dim(73,049) probe={N} rows + global SUM/COUNT of the joined rows", N,
+        alg={"join_probe": N * 4 + N // 8 + matched * 8,           # probe keys + validity in, (probe row, build row) pairs out
+             "take": matched * 2 * 20,                              # 5 int32 output columns gathered: row bytes in + out
+             "join_build": 73049 * 4 * 2})
     runtime.drop_device_resource("ss_join")
     runtime.drop_device_resource("dd_join")
 
@@ -99,11 +111,15 @@ if "sort" in which or "shuffle" in which:
         run(plan, f"cfg4 SortExec ORDER BY ss_item_sk LIMIT 1000 over {N} rows x 28 B (top-k path)", N)
         plan = P.agg(P.sort(P.ffi_reader(t4.schema, "t4"), [P.sort_expr(P.col("ss_item_sk"))]), [], [],
                      [P.agg_expr("COUNT", [P.col("ss_item_sk")], pa.int64())], ["c"], ["PARTIAL"])
-        run(plan, f"cfg4 SortExec full ORDER BY ss_item_sk over {N} rows x 28 B (+ COUNT so that only one row leaves the GPU)", N)
+        run(plan, f"cfg4 SortExec full ORDER BY ss_item_sk over {N} rows x 28 B (+ COUNT so that only one row leaves the GPU)", N,
+            alg={"radix_sort": 3 * 2 * 12 * N,                      # 18-bit key: 3 executed 8-bit passes x (u64 word + i32 row) read + write
+                 "take": 2 * 28 * N})
     if "shuffle" in which:
         d = "/dev/shm/auron_ops_shuffle"
         os.makedirs(d, exist_ok=True)
         plan = P.shuffle_writer(P.ffi_reader(t4.schema, "t4"), P.hash_repartition([P.col("ss_item_sk")], 200), f"{d}/s.data", f"{d}/s.index")
-        run(plan, f"cfg4 ShuffleWriterExec hash(ss_item_sk) -> 200 partitions, {N} rows x 28 B, LZ4 blocks written to /dev/shm", N, steps=3)
+        run(plan, f"cfg4 ShuffleWriterExec hash(ss_item_sk) -> 200 partitions, {N} rows x 28 B, LZ4 blocks written to /dev/shm", N, steps=3,
+            alg={"murmur3_partition_ids": 8 * N, "partition_rows": 8 * N, "take": 2 * 28 * N, "serde_write": 2 * 28 * N,
+                 "lz4_compress": 28 * N + os.path.getsize(d + "/s.data") if os.path.exists(d + "/s.data") else 28 * N})
         print(f"     shuffle file: {os.path.getsize(d + '/s.data') / 1e6:.0f} MB")
     runtime.drop_device_resource("t4")
