@@ -96,6 +96,16 @@ void drop_host_file(const std::string& path);
 std::unique_ptr<Task> create_task(const uint8_t* task_def, size_t len, const auron_callbacks* cb, int device);
 
 Literal decode_scalar_ipc(const uint8_t* bytes, size_t n);
+// a flat Arrow array held on the host (the child of a one-row List ScalarValue: range-partition bounds)
+struct HostArray {
+    DType type;
+    int64_t len = 0;
+    std::vector<uint8_t> validity;   // empty = no nulls
+    std::vector<uint8_t> data;       // values (bool: bitmap; utf8/binary: bytes)
+    std::vector<int32_t> offsets;    // utf8/binary
+};
+HostArray decode_list_scalar_ipc(const uint8_t* bytes, size_t n);
+ColumnPtr host_array_to_device(Ctx& ctx, const HostArray& a);
 
 // operators implemented outside engine.cc
 OperatorPtr make_parquet_scan(Task& t, const uint8_t* node, size_t n);

@@ -362,17 +362,38 @@ __device__ inline void lvl_page_bits(const uint8_t* base, int len, int64_t rows,
             if ((int)lane >= d) inc += t;
         }
         const int64_t total = __shfl_sync(FULL_MASK, inc, 31);
-        // 4. emit
+        // 4. emit: short runs by their owner lane; long RLE runs of ones (a page without NULLs is ONE such run of up to 20,000
+        //    rows -- a single lane needed ~600 serial word stores for it) are handed to the whole warp, 32 words per step
+        int64_t long_r[4], long_t[4];
+        int n_long = 0;
         if (e >= 0) {
             int o = e;
             int64_t r = row_base + inc - cnt;
             while (o < 32 && b0 + o < len && r < rows) {
                 LvlHdr h = lvl_parse(base, b0 + o, len);
                 int64_t t = min((int64_t)h.rows, rows - r);
-                if (h.kind == 1) bm_set_range(bm, r, t);
-                else if (h.kind == 0) bm_copy_bits(bm, r, base + b0 + o + h.hl, t);
+                if (h.kind == 1) {
+                    if (t > 128 && n_long < 4) {
+                        long_r[n_long] = r;
+                        long_t[n_long] = t;
+                        n_long++;
+                    } else bm_set_range(bm, r, t);
+                } else if (h.kind == 0) bm_copy_bits(bm, r, base + b0 + o + h.hl, t);
                 r += h.rows;
                 o += h.hl + h.payload;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            unsigned owners = __ballot_sync(FULL_MASK, k < n_long);
+            while (owners) {
+                const int l = __ffs(owners) - 1;
+                owners &= owners - 1;
+                const int64_t r = __shfl_sync(FULL_MASK, long_r[k], l), t = __shfl_sync(FULL_MASK, long_t[k], l);
+                const int64_t w0 = r >> 5, w1 = (r + t - 1) >> 5;   // t > 128: at least three words apart
+                if (lane == 0) atomicOr(&bm[w0], 0xffffffffu << (r & 31));
+                if (lane == 1) atomicOr(&bm[w1], 0xffffffffu >> (31 - ((r + t - 1) & 31)));
+                for (int64_t w = w0 + 1 + lane; w < w1; w += 32) bm[w] = 0xffffffffu;
             }
         }
         row_base += total;

@@ -34,7 +34,7 @@ namespace auron {
 // last SN_RING output bytes, and references that fall inside the ring are served from it; long literals bypass the ring
 // (ring_from marks the first output position the ring is valid from).
 constexpr int SN_RING = 4096;
-__global__ void __launch_bounds__(128, 12) pq_decompress_kernel(const PqDecompJob* __restrict__ jobs, int n_jobs, int32_t* __restrict__ status,
+__global__ void __launch_bounds__(128) pq_decompress_kernel(const PqDecompJob* __restrict__ jobs, int n_jobs, int32_t* __restrict__ status,
                                                             PqDecompResult* __restrict__ results) {
     __shared__ uint8_t s_ring[4][SN_RING];
     const int job = blockIdx.x * 4 + (threadIdx.x >> 5);

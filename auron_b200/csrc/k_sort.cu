@@ -353,6 +353,30 @@ __global__ void __launch_bounds__(256) pid_hist_kernel(const int32_t* __restrict
     }
 }
 
+// range partitioning: perm = stable sort order of [n key rows ++ nb bound rows]; out[key row] = bound rows in front of it
+__global__ void bound_flag_kernel(const int32_t* __restrict__ perm, int64_t total, int32_t n, int32_t* __restrict__ flags) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) flags[i] = perm[i] >= n ? 1 : 0;
+}
+__global__ void bound_rank_scatter_kernel(const int32_t* __restrict__ perm, const int32_t* __restrict__ rank, int64_t total, int32_t n,
+                                          int32_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total && perm[i] < n) out[perm[i]] = rank[i];
+}
+Buf bound_ranks(Ctx& ctx, const int32_t* perm, int64_t n, int64_t nb) {
+    const int64_t total = n + nb;
+    Buf out = dalloc(ctx, (size_t)std::max<int64_t>(n, 1) * 4);
+    if (total == 0) return out;
+    Buf flags = dalloc(ctx, (size_t)total * 4), tot = dalloc(ctx, 4);
+    unsigned blocks = (unsigned)((total + 255) / 256);
+    bound_flag_kernel<<<blocks, 256, 0, ctx.stream>>>(perm, total, (int32_t)n, P<int32_t>(flags));
+    LAUNCH_CHECK(ctx);
+    exclusive_scan_i32(ctx, P<int32_t>(flags), P<int32_t>(flags), total, P<int32_t>(tot));
+    bound_rank_scatter_kernel<<<blocks, 256, 0, ctx.stream>>>(perm, P<int32_t>(flags), total, (int32_t)n, P<int32_t>(out));
+    LAUNCH_CHECK(ctx);
+    return out;
+}
+
 void partition_rows(Ctx& ctx, const int32_t* part_ids, int64_t n, int32_t num_parts, Buf* rows_out, Buf* offsets_out) {
     ProfScope ps_fn(ctx, "partition_rows");
     Buf counts = dalloc_zero(ctx, (size_t)(num_parts + 1) * 8);

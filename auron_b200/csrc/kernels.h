@@ -34,6 +34,7 @@ BatchPtr slice_batch(Ctx& ctx, const Batch& in, int64_t off, int64_t len);
 Buf hash_columns(Ctx& ctx, const std::vector<ColumnPtr>& cols, int64_t n, int kind, int64_t seed);
 // pmod(murmur3(cols, seed 42), num_parts)  (shuffle/mod.rs:163-188) -> int32[n]
 Buf murmur3_partition_ids(Ctx& ctx, const std::vector<ColumnPtr>& cols, int64_t n, int32_t num_parts, int32_t seed = 42);
+Buf bound_ranks(Ctx& ctx, const int32_t* perm, int64_t n, int64_t nb);   // range partitioning (k_sort.cu)
 Buf round_robin_partition_ids(Ctx& ctx, int64_t n, int64_t start, int32_t num_parts);   // (i + start) % num_parts
 
 // ----------------------------------------------------------------------------- k_rowkeys.cu

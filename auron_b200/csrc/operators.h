@@ -105,6 +105,7 @@ struct SortExprSpec {
     ExprPtr expr;
     bool asc = true, nulls_first = true;
 };
+SortExprSpec decode_sort_expr(const uint8_t* b, size_t n);   // PhysicalExprNode{sort} (planner.cc)
 // sort_exec.rs:197-290,637-768
 struct SortExec : Operator {
     std::vector<SortExprSpec> keys;

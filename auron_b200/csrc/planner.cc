@@ -124,6 +124,151 @@ static bool next_ipc_message(const uint8_t*& p, const uint8_t* end, const uint8_
     return true;
 }
 
+// org.apache.arrow.flatbuf.Field -> DType (flat types only)
+static DType fb_field_type(const FbTable& field) {
+    uint8_t tt = field.scalar<uint8_t>(2, 0);
+    FbTable ty = field.table(3);
+    DType t;
+    switch (tt) {   // org.apache.arrow.flatbuf.Type
+        case 1: t = DType(T_NULL); break;
+        case 2: {
+            int bw = ty.ok() ? ty.scalar<int32_t>(0, 0) : 0;
+            bool sg = ty.ok() ? ty.scalar<uint8_t>(1, 0) != 0 : true;
+            AURON_CHECK(sg, "unsigned literal");
+            t = DType(bw == 8 ? T_INT8 : bw == 16 ? T_INT16 : bw == 32 ? T_INT32 : T_INT64);
+            break;
+        }
+        case 3: {
+            int prec = ty.ok() ? ty.scalar<int16_t>(0, 0) : 0;
+            AURON_CHECK(prec == 1 || prec == 2, "half-float literal");
+            t = DType(prec == 1 ? T_FLOAT32 : T_FLOAT64);
+            break;
+        }
+        case 4: t = DType(T_BINARY); break;
+        case 5: t = DType(T_UTF8); break;
+        case 6: t = DType(T_BOOL); break;
+        case 7: t = DType::decimal(ty.ok() ? ty.scalar<int32_t>(0, 0) : 0, ty.ok() ? ty.scalar<int32_t>(1, 0) : 0); break;
+        case 8: t = DType((ty.ok() ? ty.scalar<int16_t>(0, 1) : 1) == 0 ? T_DATE32 : T_DATE64); break;
+        case 10: {
+            t = DType(T_TIMESTAMP);
+            t.unit = ty.ok() ? ty.scalar<int16_t>(0, 0) : 0;
+            if (ty.ok()) t.tz = ty.str(1);
+            break;
+        }
+        default: fail("ScalarValue: unsupported literal type tag " + std::to_string(tt));
+    }
+    return t;
+}
+
+// ScalarValue holding a List<T> with ONE row (range partition bounds, planner.rs:1174-1203): returns the child array
+HostArray decode_list_scalar_ipc(const uint8_t* bytes, size_t n) {
+    const uint8_t* p = bytes;
+    const uint8_t* end = bytes + n;
+    const uint8_t *meta, *body;
+    uint32_t meta_len;
+    int64_t body_len;
+    HostArray out;
+    AURON_CHECK(next_ipc_message(p, end, &meta, &meta_len, &body, &body_len), "list ScalarValue: missing schema message");
+    FbTable msg;
+    msg.base = meta;
+    msg.size = meta_len;
+    msg.tbl = meta + FbTable::rd<uint32_t>(meta);
+    AURON_CHECK(msg.scalar<uint8_t>(1, 0) == 1, "list ScalarValue: first IPC message is not a Schema");
+    FbTable schema = msg.table(2);
+    uint32_t nfields;
+    const uint8_t* fields = schema.vec(1, &nfields);
+    AURON_CHECK(nfields == 1, "list ScalarValue: expected exactly one field");
+    FbTable field = schema.vec_table(fields, 0);
+    uint8_t tt = field.scalar<uint8_t>(2, 0);
+    AURON_CHECK(tt == 12 || tt == 21, "range partition bounds must be List scalars");   // List / LargeList
+    AURON_CHECK(tt == 12, "LargeList bounds are not supported");
+    uint32_t nchildren;
+    const uint8_t* children = field.vec(5, &nchildren);
+    AURON_CHECK(children && nchildren == 1, "list ScalarValue: malformed child field");
+    out.type = fb_field_type(field.vec_table(children, 0));
+    AURON_CHECK(next_ipc_message(p, end, &meta, &meta_len, &body, &body_len), "list ScalarValue: missing record batch");
+    msg.base = meta;
+    msg.size = meta_len;
+    msg.tbl = meta + FbTable::rd<uint32_t>(meta);
+    AURON_CHECK(msg.scalar<uint8_t>(1, 0) == 3, "list ScalarValue: second IPC message is not a RecordBatch");
+    FbTable rb = msg.table(2);
+    uint32_t nnodes, nbufs;
+    const uint8_t* nodes = rb.vec(1, &nnodes);
+    const uint8_t* bufs = rb.vec(2, &nbufs);
+    AURON_CHECK(rb.field_off(3) == 0, "list ScalarValue: compressed IPC bodies are not supported");
+    AURON_CHECK(nnodes == 2 && rb.scalar<int64_t>(0, 0) == 1, "list ScalarValue: expected one list row");
+    auto buf = [&](uint32_t i, int64_t* len) -> const uint8_t* {
+        AURON_CHECK(i < nbufs, "list ScalarValue: missing buffer");
+        int64_t off = FbTable::rd<int64_t>(bufs + 16 * i);
+        *len = FbTable::rd<int64_t>(bufs + 16 * i + 8);
+        AURON_CHECK(off >= 0 && off + *len <= body_len, "list ScalarValue: buffer outside the body");
+        return body + off;
+    };
+    int64_t l;
+    const uint8_t* loffs = buf(1, &l);
+    AURON_CHECK(l >= 8, "list ScalarValue: missing list offsets");
+    const int32_t first = FbTable::rd<int32_t>(loffs), last = FbTable::rd<int32_t>(loffs + 4);
+    const int64_t child_len = FbTable::rd<int64_t>(nodes + 16), child_nulls = FbTable::rd<int64_t>(nodes + 24);
+    AURON_CHECK(first >= 0 && last >= first && last <= child_len, "list ScalarValue: bad list offsets");
+    out.len = last - first;
+    int64_t vl;
+    const uint8_t* cv = buf(2, &vl);
+    if (child_nulls > 0 && vl > 0) {
+        out.validity.assign((size_t)((out.len + 7) / 8), 0);
+        for (int64_t i = 0; i < out.len; i++)
+            if ((cv[(first + i) >> 3] >> ((first + i) & 7)) & 1) out.validity[(size_t)(i >> 3)] |= (uint8_t)(1u << (i & 7));
+    }
+    if (out.type.is_varlen()) {
+        int64_t ol, dl;
+        const uint8_t* co = buf(3, &ol);
+        const uint8_t* cd = buf(4, &dl);
+        AURON_CHECK(ol >= (child_len + 1) * 4, "list ScalarValue: short offsets buffer");
+        const int32_t b0 = FbTable::rd<int32_t>(co + 4 * (size_t)first);
+        out.offsets.resize((size_t)out.len + 1);
+        for (int64_t i = 0; i <= out.len; i++) out.offsets[(size_t)i] = FbTable::rd<int32_t>(co + 4 * (size_t)(first + i)) - b0;
+        AURON_CHECK(b0 >= 0 && b0 + out.offsets.back() <= dl, "list ScalarValue: string data outside the buffer");
+        out.data.assign(cd + b0, cd + b0 + out.offsets.back());
+    } else if (out.type.id == T_BOOL) {
+        int64_t dl;
+        const uint8_t* cd = buf(3, &dl);
+        out.data.assign((size_t)((out.len + 7) / 8), 0);
+        for (int64_t i = 0; i < out.len; i++)
+            if ((cd[(first + i) >> 3] >> ((first + i) & 7)) & 1) out.data[(size_t)(i >> 3)] |= (uint8_t)(1u << (i & 7));
+    } else if (out.type.id != T_NULL) {
+        int64_t dl;
+        const uint8_t* cd = buf(3, &dl);
+        const int w = out.type.width();
+        AURON_CHECK(dl >= (int64_t)last * w, "list ScalarValue: short data buffer");
+        out.data.assign(cd + (size_t)first * w, cd + (size_t)last * w);
+    }
+    return out;
+}
+
+ColumnPtr host_array_to_device(Ctx& ctx, const HostArray& a) {
+    auto c = std::make_shared<Column>();
+    c->type = a.type;
+    c->len = a.len;
+    if (!a.validity.empty()) {
+        std::vector<uint8_t> v((size_t)bitmap_alloc_bytes(a.len), 0);
+        memcpy(v.data(), a.validity.data(), std::min(v.size(), a.validity.size()));
+        c->validity = to_device(ctx, v.data(), v.size());
+        c->null_count = -1;
+    }
+    if (a.type.is_varlen()) {
+        c->offsets = to_device(ctx, a.offsets.data(), a.offsets.size() * 4);
+        c->data = to_device(ctx, a.data.empty() ? (const void*)"" : (const void*)a.data.data(), a.data.size());
+        c->data_bytes = (int64_t)a.data.size();
+    } else if (a.type.id == T_BOOL) {
+        std::vector<uint8_t> v((size_t)bitmap_alloc_bytes(a.len), 0);
+        memcpy(v.data(), a.data.data(), std::min(v.size(), a.data.size()));
+        c->data = to_device(ctx, v.data(), v.size());
+    } else {
+        c->data = to_device(ctx, a.data.empty() ? (const void*)"" : (const void*)a.data.data(), a.data.size());
+    }
+    ctx.sync();
+    return c;
+}
+
 Literal decode_scalar_ipc(const uint8_t* bytes, size_t n) {
     const uint8_t* p = bytes;
     const uint8_t* end = bytes + n;
@@ -142,36 +287,7 @@ Literal decode_scalar_ipc(const uint8_t* bytes, size_t n) {
     const uint8_t* fields = schema.vec(1, &nfields);
     AURON_CHECK(nfields == 1, "ScalarValue: expected exactly one field");
     FbTable field = schema.vec_table(fields, 0);
-    uint8_t tt = field.scalar<uint8_t>(2, 0);
-    FbTable ty = field.table(3);
-    switch (tt) {   // org.apache.arrow.flatbuf.Type
-        case 1: lit.type = DType(T_NULL); break;
-        case 2: {
-            int bw = ty.ok() ? ty.scalar<int32_t>(0, 0) : 0;
-            bool sg = ty.ok() ? ty.scalar<uint8_t>(1, 0) != 0 : true;
-            AURON_CHECK(sg, "unsigned literal");
-            lit.type = DType(bw == 8 ? T_INT8 : bw == 16 ? T_INT16 : bw == 32 ? T_INT32 : T_INT64);
-            break;
-        }
-        case 3: {
-            int prec = ty.ok() ? ty.scalar<int16_t>(0, 0) : 0;
-            AURON_CHECK(prec == 1 || prec == 2, "half-float literal");
-            lit.type = DType(prec == 1 ? T_FLOAT32 : T_FLOAT64);
-            break;
-        }
-        case 4: lit.type = DType(T_BINARY); break;
-        case 5: lit.type = DType(T_UTF8); break;
-        case 6: lit.type = DType(T_BOOL); break;
-        case 7: lit.type = DType::decimal(ty.ok() ? ty.scalar<int32_t>(0, 0) : 0, ty.ok() ? ty.scalar<int32_t>(1, 0) : 0); break;
-        case 8: lit.type = DType((ty.ok() ? ty.scalar<int16_t>(0, 1) : 1) == 0 ? T_DATE32 : T_DATE64); break;
-        case 10: {
-            lit.type = DType(T_TIMESTAMP);
-            lit.type.unit = ty.ok() ? ty.scalar<int16_t>(0, 0) : 0;
-            if (ty.ok()) lit.type.tz = ty.str(1);
-            break;
-        }
-        default: fail("ScalarValue: unsupported literal type tag " + std::to_string(tt));
-    }
+    lit.type = fb_field_type(field);
     if (!next_ipc_message(p, end, &meta, &meta_len, &body, &body_len)) {
         lit.is_null = true;
         return lit;
@@ -476,7 +592,7 @@ static void decode_join_on(PbReader& r, std::vector<ExprPtr>* l, std::vector<Exp
     rr->push_back(re);
 }
 
-static SortExprSpec decode_sort_expr(const uint8_t* b, size_t n) {
+SortExprSpec decode_sort_expr(const uint8_t* b, size_t n) {
     // PhysicalExprNode{sort=11{expr=1, asc=2, nulls_first=3}}
     PbReader r(b, n);
     uint32_t f, w;

@@ -85,8 +85,12 @@ void compress_block(bool zstd, const uint8_t* in, size_t n, std::vector<uint8_t>
 }  // namespace
 
 struct ShuffleWriterExec : Operator {
-    int kind = 1;   // 1 single, 2 hash, 3 round robin
+    int kind = 1;   // 1 single, 2 hash, 3 round robin, 4 range
     std::vector<ExprPtr> hash_exprs;
+    // range partitioning: sort expressions + one bound column per expression (num_parts - 1 rows, ascending in sort order)
+    std::vector<SortExprSpec> range_keys;
+    std::vector<HostArray> range_bounds_host;
+    std::vector<ColumnPtr> range_bounds;
     int64_t num_parts = 1;
     std::string data_file, index_file;
     bool done = false;
@@ -203,6 +207,27 @@ struct ShuffleWriterExec : Operator {
         return out;
     }
 
+    // evaluate_range_partition_ids + get_partition (shuffle/mod.rs:204-262): partition = number of bound rows that sort strictly
+    // before the key row.  On the device: sort [key rows ++ bound rows] once with the stable key sort (bounds last, so a bound
+    // equal to a key stays behind it), then the partition of a key row is the number of bound rows in front of it.
+    Buf range_partition_ids(Task& t, const Batch& in) {
+        Ctx& ctx = t.ctx;
+        const int64_t n = in.num_rows;
+        if (range_bounds.empty())
+            for (auto& h : range_bounds_host) range_bounds.push_back(host_array_to_device(ctx, h));
+        AURON_CHECK(range_bounds.size() == range_keys.size(), "range partitioning: one bound list per sort expression expected");
+        const int64_t nb = range_bounds.empty() ? 0 : range_bounds[0]->len;
+        std::vector<SortKeySpec> specs;
+        for (size_t k = 0; k < range_keys.size(); k++) {
+            ColumnPtr kc = eval_to_column(t, range_keys[k].expr, children[0]->out_schema, in);
+            AURON_CHECK(kc->type == range_bounds[k]->type, "range partitioning: bound type " + range_bounds[k]->type.str() + " != key type " + kc->type.str());
+            AURON_CHECK(range_bounds[k]->len == nb, "range partitioning: ragged bound lists");
+            specs.push_back({concat_columns(ctx, {kc, range_bounds[k]}), range_keys[k].asc, range_keys[k].nulls_first});
+        }
+        Buf perm = sort_indices(ctx, specs, n + nb);
+        return bound_ranks(ctx, P<int32_t>(perm), n, nb);
+    }
+
     void write_chunk(Task& t, const BatchPtr& in) {
         Ctx& ctx = t.ctx;
         int64_t n = in->num_rows;
@@ -220,7 +245,7 @@ struct ShuffleWriterExec : Operator {
                 int64_t start = (int64_t)(((uint64_t)t.partition_id * 1000193ull + (uint64_t)rows_so_far) % (uint64_t)num_parts);
                 pids = round_robin_partition_ids(ctx, n, start, (int32_t)num_parts);
             } else {
-                fail("range repartitioning on device is not built yet (hash, round-robin and single are)");
+                pids = range_partition_ids(t, *in);
             }
             Buf rows, offs;
             partition_rows(ctx, P<int32_t>(pids), n, (int32_t)num_parts, &rows, &offs);
@@ -376,8 +401,41 @@ OperatorPtr make_shuffle_writer(Task& t, OperatorPtr input, const uint8_t* node,
                 PbReader s(sb, sn);
                 uint32_t sf, sw;
                 op->kind = (int)pf;
-                AURON_CHECK(pf >= 1 && pf <= 3, "range repartitioning is not built on device yet");
+                AURON_CHECK(pf >= 1 && pf <= 4, "unknown repartition kind");
                 while (s.next(&sf, &sw)) {
+                    if (pf == 4) {   // PhysicalRangeRepartition{sort_expr = 1 (SortExecNode), partition_count = 2, list_value = 3 (ScalarValue)*}
+                        if (sf == 1 && sw == 2) {
+                            const uint8_t* nb;
+                            size_t nn;
+                            s.bytes_view(&nb, &nn);
+                            PbReader sn(nb, nn);
+                            uint32_t nf, nw;
+                            while (sn.next(&nf, &nw)) {
+                                if (nf == 2 && nw == 2) {
+                                    const uint8_t* eb;
+                                    size_t en;
+                                    sn.bytes_view(&eb, &en);
+                                    op->range_keys.push_back(decode_sort_expr(eb, en));
+                                } else sn.skip(nw);
+                            }
+                        } else if (sf == 2 && sw == 0) op->num_parts = (int64_t)s.varint();
+                        else if (sf == 3 && sw == 2) {
+                            const uint8_t* vb;
+                            size_t vn;
+                            s.bytes_view(&vb, &vn);
+                            PbReader sv(vb, vn);
+                            uint32_t vf, vw;
+                            while (sv.next(&vf, &vw)) {
+                                if (vf == 1 && vw == 2) {
+                                    const uint8_t* ib;
+                                    size_t in_;
+                                    sv.bytes_view(&ib, &in_);
+                                    op->range_bounds_host.push_back(decode_list_scalar_ipc(ib, in_));
+                                } else sv.skip(vw);
+                            }
+                        } else s.skip(sw);
+                        continue;
+                    }
                     if (pf == 2 && sf == 1 && sw == 2) {
                         const uint8_t* eb;
                         size_t en;
@@ -393,6 +451,9 @@ OperatorPtr make_shuffle_writer(Task& t, OperatorPtr input, const uint8_t* node,
     }
     AURON_CHECK(op->num_parts >= 1, "shuffle writer needs at least one output partition");
     if (op->kind == 1) op->num_parts = 1;   // SingleShuffleRepartitioner (single_repartitioner.rs:64-97)
+    if (op->kind == 4 && op->num_parts == 1) op->kind = 1;   // planner.rs:1161-1162
+    if (op->kind == 4)
+        for (auto& h : op->range_bounds_host) AURON_CHECK(h.len == op->num_parts - 1, "range partitioning needs partition_count - 1 bounds");
     if (const char* c = getenv("AURON_IO_COMPRESSION_CODEC")) op->zstd = std::string(c) == "zstd";   // spark.io.compression.codec (lz4 | zstd)
     op->children.push_back(std::move(input));
     (void)t;

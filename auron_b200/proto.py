@@ -287,6 +287,13 @@ def round_robin_repartition(n: int) -> bytes:
     return f_bytes(3, f_varint(1, n))
 
 
+def range_repartition(sort_exprs: list[bytes], n: int, bounds: list[tuple[list, pa.DataType]]) -> bytes:
+    """PhysicalRepartition{range_repartition}: sort expressions (inside a SortExecNode without input), partition count and one
+    List ScalarValue of n - 1 bound values per sort expression (auron.proto:681-685, planner.rs:1160-1210)"""
+    sort_node = b"".join(f_bytes(2, e) for e in sort_exprs)
+    return f_bytes(4, f_bytes(1, sort_node) + f_varint(2, n) + b"".join(f_bytes(3, scalar_value(vals, pa.list_(t))) for vals, t in bounds))
+
+
 def shuffle_writer(inp: bytes, repartition: bytes, data_file: str, index_file: str) -> bytes:
     """PhysicalPlanNode{shuffle_writer} (auron.proto:553-558)"""
     return f_bytes(2, f_bytes(1, inp) + f_bytes(2, repartition) + f_str(3, data_file) + f_str(4, index_file))

@@ -119,3 +119,60 @@ def test_round_robin_shuffle_write(tmp_path, partition_id, chunk_rows):
     pid = (partition_id * 1000193 + np.arange(n)) % nparts
     for p in range(nparts):
         assert_same_rows(parts[p], t.filter(pa.array(pid == p)))
+
+
+@pytest.mark.parametrize("case", ["int_asc", "int_desc_nulls_last", "string_then_int"])
+def test_range_partition_shuffle_write(tmp_path, case):
+    # evaluate_range_partition_ids / get_partition (shuffle/mod.rs:204-262): partition = number of bounds that sort strictly
+    # before the row's key (a key equal to a bound stays in the lower partition); bounds arrive as List ScalarValues
+    n = 40_000
+    rng = np.random.default_rng(17)
+    words = ["", "a", "ab", "b", "zz", "天"]
+    t = pa.table({"k": pa.array(rng.integers(-500, 500, n), type=pa.int32(), mask=rng.random(n) < 0.05),
+                  "s": pa.array([words[int(i)] for i in rng.integers(0, len(words), n)], mask=rng.random(n) < 0.05),
+                  "row": pa.array(np.arange(n), type=pa.int64())})
+    if case == "int_asc":
+        keys, bounds = [("k", True, True)], [([-300, -1, 0, 0, 250], pa.int32())]
+    elif case == "int_desc_nulls_last":
+        keys, bounds = [("k", False, False)], [([400, 100, -100, None], pa.int32())]
+    else:
+        keys, bounds = [("s", True, True), ("k", True, True)], [(["a", "b", "b"], pa.string()), ([0, -10, 10], pa.int32())]
+    nparts = len(bounds[0][0]) + 1
+    data, index = str(tmp_path / "r.data"), str(tmp_path / "r.index")
+    plan = P.shuffle_writer(P.ffi_reader(t.schema, "t"),
+                            P.range_repartition([P.sort_expr(P.col(c), asc, nf) for c, asc, nf in keys], nparts, bounds), data, index)
+    run(plan, {"t": t}, chunk=15_000)
+    parts, offsets = read_shuffle_files(data, index, t.schema)
+
+    def sort_key(vals):          # tuple comparable in the requested order: (null rank, value) per column
+        out = []
+        for v, (_, asc, nf) in zip(vals, keys):
+            if v is None:
+                out.append((0 if nf else 2, 0))
+            else:
+                x = v.encode() if isinstance(v, str) else v
+                out.append((1, x if asc else _Neg(x)))
+        return tuple(out)
+
+    class _Neg:                  # reverses the order of the wrapped value
+        def __init__(self, x):
+            self.x = x
+
+        def __lt__(self, o):
+            return o.x < self.x
+
+        def __eq__(self, o):
+            return o.x == self.x
+
+        def __gt__(self, o):
+            return o.x > self.x
+
+    bkeys = [sort_key([b[0][i] for b in bounds]) for i in range(nparts - 1)]
+    cols = [t[c].to_pylist() for c, _, _ in keys]
+    exp_pid = []
+    for vals in zip(*cols):
+        kk = sort_key(vals)
+        exp_pid.append(sum(1 for b in bkeys if b < kk))
+    exp_pid = np.array(exp_pid)
+    for p in range(nparts):
+        assert sorted(parts[p]["row"].to_pylist()) == np.nonzero(exp_pid == p)[0].tolist(), p
