@@ -290,6 +290,9 @@ def main():
         e2e["page_cache_files"] = {"value": world * total_rows * args.steps / dtf, "ms_per_step": 1000 * dtf / args.steps, "step_ms": spread(),
                                    "input": "parquet files in the OS page cache (pread into pinned staging, then H2D)"}
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     # ---- roofline of the dominant kernel (device time from CUDA events on the launching stream)
@@ -324,8 +327,17 @@ def main():
     dom = names[0] if names else None
     dom_us = kern[dom + ".device_us"] / args.steps if dom else None
     dom_bytes = alg.get(dom) if dom else None
+    # DRAM traffic of the dominant kernel per step, from the committed ncu pass at this workload's full size (profiles/)
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if dom in tj and args.rows == SF100_ROWS and CODEC == "SNAPPY":
+            traffic, traffic_src = tj[dom]["dram_bytes_per_step"], tj[dom]["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": (dom_bytes / (dom_us * 1e-6) / 1e9) if dom_bytes and dom_us else None, "peak": peak,
-                "unit": "GB/s", "frac": (dom_bytes / (dom_us * 1e-6) / 1e9 / peak) if dom_bytes and dom_us else None, "traffic": None,
+                "unit": "GB/s", "frac": (dom_bytes / (dom_us * 1e-6) / 1e9 / peak) if dom_bytes and dom_us else None, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src, "algorithmic_bytes_per_step": dom_bytes, "kernels": roofs}
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
