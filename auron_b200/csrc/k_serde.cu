@@ -288,6 +288,186 @@ SerializedParts serialize_partitions(Ctx& ctx, const Batch& b, const std::vector
     return res;
 }
 
-BatchPtr deserialize_batch(Ctx&, const Schema&, const uint8_t*, int64_t, int64_t*) { fail("deserialize_batch: shuffle read is a 'next' row (SURVEY.md section 8f)"); }
+// ------------------------------------------------------------------------------------------ read side (IpcReaderExec)
+// Inverse of the kernels above (read_batch / read_array, batch_serde.rs:81-101,309-346): the decompressed payload of a
+// shuffle segment is a sequence of batches; the host walks the section layout (it decompressed the bytes, so it has them)
+// and hands one descriptor per (batch, column) to the device, which rebuilds Arrow columns for ALL batches of the chunk
+// at once: byte planes -> values (same warp-per-128-rows scheme, planes read as unaligned 32-bit words), validity / bool
+// bits re-packed at the output row offset, utf8 lengths -> offsets by one scan, payload bytes by cooperative copies.
+__device__ __forceinline__ uint32_t ld32_any(const uint8_t* p) {
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t* w = (const uint32_t*)(a & ~(uintptr_t)3);
+    const unsigned sh = (unsigned)(a & 3) * 8;
+    return sh ? __funnelshift_r(w[0], w[1], sh) : w[0];
+}
+template <int W>
+__global__ void __launch_bounds__(256) deser_fixed_kernel(const uint8_t* __restrict__ payload, const DeserSeg* __restrict__ segs, const int32_t* __restrict__ chunk_base,
+                                                          int n_segs, int total_chunks, uint8_t* __restrict__ out) {
+    const int chunk = (int)(((int64_t)blockIdx.x * 256 + threadIdx.x) >> 5);
+    if (chunk >= total_chunks) return;
+    const unsigned lane = threadIdx.x & 31;
+    int lo = 0, hi = n_segs;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (chunk_base[mid] <= chunk) lo = mid;
+        else hi = mid;
+    }
+    const DeserSeg s = segs[lo];
+    const int64_t j0 = (int64_t)(chunk - chunk_base[lo]) * 128 + 4 * lane;
+    const int mine = (int)max((int64_t)0, min((int64_t)4, s.n - j0));
+    if (mine <= 0) return;
+    constexpr int NW = W >= 4 ? W / 4 : 1;
+    uint32_t P[W];
+#pragma unroll
+    for (int k = 0; k < W; k++) {
+        const uint8_t* q = payload + s.values_off + (int64_t)k * s.n + j0;
+        if (mine == 4) P[k] = ld32_any(q);   // the payload buffer is padded, the funnel's second word stays inside it
+        else {
+            P[k] = 0;
+            for (int t = 0; t < mine; t++) P[k] |= (uint32_t)q[t] << (8 * t);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        if (r >= mine) break;
+        const int64_t row = s.out_row0 + j0 + r;
+        if constexpr (W == 1) out[row] = (uint8_t)(P[0] >> (8 * r));
+        else if constexpr (W == 2) ((uint16_t*)out)[row] = (uint16_t)((P[0] >> (8 * r)) & 0xff) | (uint16_t)(((P[1] >> (8 * r)) & 0xff) << 8);
+        else {
+            uint32_t* d = (uint32_t*)out + row * NW;
+#pragma unroll
+            for (int q = 0; q < NW; q++) d[q] = pack_plane(P[4 * q], P[4 * q + 1], P[4 * q + 2], P[4 * q + 3], r);
+        }
+    }
+}
+// validity sections / bool values: 32 source bits per thread, OR-ed into the zero-initialised output bitmap at the batch's
+// row offset.  bits_off < 0: the batch has no validity section (all rows valid).
+__global__ void __launch_bounds__(256) deser_bits_kernel(const uint8_t* __restrict__ payload, const DeserSeg* __restrict__ segs, const int32_t* __restrict__ word_base,
+                                                         int n_segs, int total_words, int use_values, uint32_t* __restrict__ out) {
+    const int w = blockIdx.x * 256 + threadIdx.x;
+    if (w >= total_words) return;
+    int lo = 0, hi = n_segs;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (word_base[mid] <= w) lo = mid;
+        else hi = mid;
+    }
+    const DeserSeg s = segs[lo];
+    const int64_t j = (int64_t)(w - word_base[lo]) * 32;
+    const int cnt = (int)min((int64_t)32, s.n - j);
+    if (cnt <= 0) return;
+    const int64_t src = use_values ? s.values_off : s.validity_off;
+    uint32_t bits = 0xffffffffu;
+    if (src >= 0) {
+        bits = 0;
+        const uint8_t* q = payload + src + (j >> 3);
+        for (int t = 0; t < (cnt + 7) / 8; t++) bits |= (uint32_t)q[t] << (8 * t);
+    }
+    if (cnt < 32) bits &= (1u << cnt) - 1u;
+    if (!bits) return;
+    const int64_t o = s.out_row0 + j;
+    const int sh = (int)(o & 31);
+    atomicOr(&out[o >> 5], bits << sh);
+    if (sh && (bits >> (32 - sh))) atomicOr(&out[(o >> 5) + 1], bits >> (32 - sh));
+}
+// utf8 / binary: row lengths from the four transposed length planes
+__global__ void __launch_bounds__(256) deser_lengths_kernel(const uint8_t* __restrict__ payload, const DeserSeg* __restrict__ segs, const int32_t* __restrict__ chunk_base,
+                                                            int n_segs, int total_chunks, int32_t* __restrict__ lens) {
+    const int64_t gi = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int chunk = (int)(gi >> 7);   // 128 rows per chunk, one row per thread
+    if (chunk >= total_chunks) return;
+    int lo = 0, hi = n_segs;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (chunk_base[mid] <= chunk) lo = mid;
+        else hi = mid;
+    }
+    const DeserSeg s = segs[lo];
+    const int64_t j = (int64_t)(chunk - chunk_base[lo]) * 128 + (gi & 127);
+    if (j >= s.n) return;
+    const uint8_t* q = payload + s.values_off + j;
+    lens[s.out_row0 + j] = (int32_t)((uint32_t)q[0] | ((uint32_t)q[s.n] << 8) | ((uint32_t)q[2 * s.n] << 16) | ((uint32_t)q[3 * s.n] << 24));
+}
+__global__ void __launch_bounds__(128) deser_bytes_kernel(const uint8_t* __restrict__ payload, const DeserCopy* __restrict__ copies, int n, uint8_t* __restrict__ out) {
+    const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (c >= n) return;
+    const DeserCopy cp = copies[c];
+    warp_copy(out + cp.dst, payload + cp.src, cp.len, threadIdx.x & 31);
+}
+
+ColumnPtr deserialize_column(Ctx& ctx, const DType& type, const uint8_t* dev_payload, const std::vector<DeserSeg>& segs, int64_t total_rows,
+                             const std::vector<DeserCopy>& byte_copies, int64_t total_bytes) {
+    auto col = std::make_shared<Column>();
+    col->type = type;
+    col->len = total_rows;
+    if (type.id == T_NULL) {
+        col->null_count = total_rows;
+        return col;
+    }
+    const int n_segs = (int)segs.size();
+    bool any_nulls = false;
+    std::vector<int32_t> chunk_base((size_t)n_segs + 1, 0), word_base((size_t)n_segs + 1, 0);
+    for (int i = 0; i < n_segs; i++) {
+        any_nulls = any_nulls || segs[(size_t)i].validity_off >= 0;
+        chunk_base[(size_t)i + 1] = chunk_base[(size_t)i] + (int32_t)((segs[(size_t)i].n + 127) / 128);
+        word_base[(size_t)i + 1] = word_base[(size_t)i] + (int32_t)((segs[(size_t)i].n + 31) / 32);
+    }
+    const int total_chunks = chunk_base.back(), total_words = word_base.back();
+    Buf dsegs = to_device(ctx, segs.empty() ? (const void*)"" : (const void*)segs.data(), segs.size() * sizeof(DeserSeg));
+    Buf dchunks = to_device(ctx, chunk_base.data(), chunk_base.size() * 4);
+    Buf dwords = to_device(ctx, word_base.data(), word_base.size() * 4);
+    if (any_nulls && total_rows > 0) {
+        col->validity = dalloc_zero(ctx, bitmap_alloc_bytes(total_rows));
+        col->null_count = -1;
+        deser_bits_kernel<<<(unsigned)((total_words + 255) / 256), 256, 0, ctx.stream>>>(dev_payload, P<DeserSeg>(dsegs), P<int32_t>(dwords), n_segs, total_words, 0,
+                                                                                         P<uint32_t>(col->validity));
+        LAUNCH_CHECK(ctx);
+    }
+    if (total_rows == 0) {
+        if (type.is_varlen()) {
+            col->offsets = dalloc_zero(ctx, 4);
+            col->data = dalloc(ctx, 1);
+        } else col->data = dalloc(ctx, 16);
+        return col;
+    }
+    const unsigned cgrid = (unsigned)(((int64_t)total_chunks * 32 + 255) / 256);
+    if (type.id == T_BOOL) {
+        col->data = dalloc_zero(ctx, bitmap_alloc_bytes(total_rows));
+        deser_bits_kernel<<<(unsigned)((total_words + 255) / 256), 256, 0, ctx.stream>>>(dev_payload, P<DeserSeg>(dsegs), P<int32_t>(dwords), n_segs, total_words, 1,
+                                                                                         P<uint32_t>(col->data));
+        LAUNCH_CHECK(ctx);
+    } else if (type.is_varlen()) {
+        AURON_CHECK(total_bytes < (int64_t)INT32_MAX, "shuffle read: more than 2 GiB of string data in one batch");
+        Buf lens = dalloc(ctx, (size_t)(total_rows + 1) * 4);
+        deser_lengths_kernel<<<(unsigned)(((int64_t)total_chunks * 128 + 255) / 256), 256, 0, ctx.stream>>>(dev_payload, P<DeserSeg>(dsegs), P<int32_t>(dchunks), n_segs,
+                                                                                                          total_chunks, P<int32_t>(lens));
+        LAUNCH_CHECK(ctx);
+        CUDA_OK(cudaMemsetAsync(P<int32_t>(lens) + total_rows, 0, 4, ctx.stream));
+        col->offsets = dalloc(ctx, (size_t)(total_rows + 1) * 4);
+        Buf tot = dalloc(ctx, 4);
+        exclusive_scan_i32(ctx, P<int32_t>(lens), P<int32_t>(col->offsets), total_rows + 1, P<int32_t>(tot));
+        col->data = dalloc(ctx, (size_t)std::max<int64_t>(total_bytes, 1));
+        col->data_bytes = total_bytes;
+        if (!byte_copies.empty()) {
+            Buf dcp = to_device(ctx, byte_copies.data(), byte_copies.size() * sizeof(DeserCopy));
+            deser_bytes_kernel<<<(unsigned)((byte_copies.size() + 3) / 4), 128, 0, ctx.stream>>>(dev_payload, P<DeserCopy>(dcp), (int)byte_copies.size(), P<uint8_t>(col->data));
+            LAUNCH_CHECK(ctx);
+        }
+    } else {
+        const int w = type.width();
+        col->data = dalloc(ctx, (size_t)total_rows * w);
+        uint8_t* o = P<uint8_t>(col->data);
+        switch (w) {
+            case 1: deser_fixed_kernel<1><<<cgrid, 256, 0, ctx.stream>>>(dev_payload, P<DeserSeg>(dsegs), P<int32_t>(dchunks), n_segs, total_chunks, o); break;
+            case 2: deser_fixed_kernel<2><<<cgrid, 256, 0, ctx.stream>>>(dev_payload, P<DeserSeg>(dsegs), P<int32_t>(dchunks), n_segs, total_chunks, o); break;
+            case 4: deser_fixed_kernel<4><<<cgrid, 256, 0, ctx.stream>>>(dev_payload, P<DeserSeg>(dsegs), P<int32_t>(dchunks), n_segs, total_chunks, o); break;
+            case 8: deser_fixed_kernel<8><<<cgrid, 256, 0, ctx.stream>>>(dev_payload, P<DeserSeg>(dsegs), P<int32_t>(dchunks), n_segs, total_chunks, o); break;
+            case 16: deser_fixed_kernel<16><<<cgrid, 256, 0, ctx.stream>>>(dev_payload, P<DeserSeg>(dsegs), P<int32_t>(dchunks), n_segs, total_chunks, o); break;
+            default: fail("shuffle read: unsupported fixed width " + std::to_string(w));
+        }
+        LAUNCH_CHECK(ctx);
+    }
+    return col;
+}
 
 }  // namespace auron

@@ -143,6 +143,17 @@ inline int64_t lz4_block_bound(int64_t n) { return n + n / 255 + 32; }
 void lz4_compress_blocks(Ctx& ctx, const Lz4Block* dev_blocks, int n_blocks, int32_t* dev_sizes);
 void lz4_assemble(Ctx& ctx, const Lz4Place* dev_places, int n);
 
-BatchPtr deserialize_batch(Ctx& ctx, const Schema& schema, const uint8_t* host_bytes, int64_t nbytes, int64_t* consumed);
+// read side (IpcReaderExec): one DeserSeg per batch of the column, offsets into the decompressed payload on the device
+struct DeserSeg {
+    int64_t validity_off;   // -1: no validity section (all rows valid)
+    int64_t values_off;     // fixed: byte planes ; bool: bits ; utf8: four length planes
+    int64_t out_row0;       // first output row of this batch
+    int64_t n;
+};
+struct DeserCopy {          // utf8 payload bytes of one batch (or a piece of it)
+    int64_t src, dst, len;
+};
+ColumnPtr deserialize_column(Ctx& ctx, const DType& type, const uint8_t* dev_payload, const std::vector<DeserSeg>& segs, int64_t total_rows,
+                             const std::vector<DeserCopy>& byte_copies, int64_t total_bytes);
 
 }  // namespace auron

@@ -816,6 +816,17 @@ static OperatorPtr decode_plan(Task& t, const uint8_t* b, size_t n) {
                 out.reset(new FFIReaderExec(schema, id));
                 break;
             }
+            case 3: {   // IpcReaderExecNode{num_partitions=1, schema=2, ipc_provider_resource_id=3}  (planner.rs; auron.proto:636-640)
+                Schema schema;
+                std::string id;
+                while (s.next(&sf, &sw)) {
+                    if (sf == 2 && sw == 2) schema = schema_field(s);
+                    else if (sf == 3 && sw == 2) id = s.bytes();
+                    else s.skip(sw);
+                }
+                out = make_ipc_reader(t, schema, id);
+                break;
+            }
             case 14: {   // RenameColumnsExecNode{input=1, renamed_column_names=2}
                 OperatorPtr input;
                 std::vector<std::string> names;

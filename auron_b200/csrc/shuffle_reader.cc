@@ -1,0 +1,309 @@
+// shuffle_reader.cc -- IpcReaderExec: the read side of Auron's compacted shuffle format.
+//
+// Mirrors datafusion-ext-plans/src/ipc_reader_exec.rs:166-275: the host runtime hands over an iterator of blocks (file
+// segment | in-memory buffer; AuronBlockObject.hasFileSegment / hasByteBuffer), every block is a sequence of
+//     u32_le compressed_len | codec stream                (IpcCompressionReader, ipc_compression.rs:115-176)
+// whose concatenated payload is a sequence of batches in the byte-plane format (read_batch, batch_serde.rs:81-101).
+//
+// Host side (this file): fetch the blocks into pinned memory, decompress the codec streams on the worker pool (LZ4 frame /
+// ZSTD through the system libraries, detected by magic), walk the section layout of every batch (varints, section sizes,
+// string byte totals) and ship payload + descriptors to the GPU.  Device side (k_serde.cu): all batches of the chunk become
+// one Arrow batch -- planes -> values, validity / bool bits re-packed at the row offset, string lengths -> offsets by a
+// scan, string bytes by cooperative copies.  The reference coalesces staged batches up to the batch size
+// (ipc_reader_exec.rs:241-262); here a chunk is 256 MB of compressed blocks.
+#include <dlfcn.h>
+#include <fcntl.h>
+#include <unistd.h>
+
+#include <cstring>
+
+#include "../../include/auron_b200.h"
+#include "host_pool.h"
+#include "operators.h"
+#include "pb.h"
+
+namespace auron {
+
+namespace {
+// ---- codecs (system libraries, no headers in this image)
+struct ZInBuf {
+    const void* src;
+    size_t size, pos;
+};
+struct ZOutBuf {
+    void* dst;
+    size_t size, pos;
+};
+struct DecCodecs {
+    // LZ4F
+    size_t (*lz4_create)(void**, unsigned) = nullptr;
+    size_t (*lz4_free)(void*) = nullptr;
+    size_t (*lz4_decompress)(void*, void*, size_t*, const void*, size_t*, const void*) = nullptr;
+    unsigned (*lz4_iserr)(size_t) = nullptr;
+    // ZSTD
+    void* (*z_create)() = nullptr;
+    size_t (*z_free)(void*) = nullptr;
+    size_t (*z_stream)(void*, ZOutBuf*, ZInBuf*) = nullptr;
+    unsigned (*z_iserr)(size_t) = nullptr;
+};
+const DecCodecs& dec_codecs() {
+    static DecCodecs c = [] {
+        DecCodecs c;
+        if (void* h = dlopen("liblz4.so.1", RTLD_NOW | RTLD_GLOBAL)) {
+            c.lz4_create = (decltype(c.lz4_create))dlsym(h, "LZ4F_createDecompressionContext");
+            c.lz4_free = (decltype(c.lz4_free))dlsym(h, "LZ4F_freeDecompressionContext");
+            c.lz4_decompress = (decltype(c.lz4_decompress))dlsym(h, "LZ4F_decompress");
+            c.lz4_iserr = (decltype(c.lz4_iserr))dlsym(h, "LZ4F_isError");
+        }
+        if (void* h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_GLOBAL)) {
+            c.z_create = (decltype(c.z_create))dlsym(h, "ZSTD_createDStream");
+            c.z_free = (decltype(c.z_free))dlsym(h, "ZSTD_freeDStream");
+            c.z_stream = (decltype(c.z_stream))dlsym(h, "ZSTD_decompressStream");
+            c.z_iserr = (decltype(c.z_iserr))dlsym(h, "ZSTD_isError");
+        }
+        return c;
+    }();
+    return c;
+}
+// one codec stream -> bytes appended to out
+void decompress_stream(const uint8_t* in, size_t n, std::vector<uint8_t>& out) {
+    AURON_CHECK(n >= 4, "shuffle read: truncated codec stream");
+    uint32_t magic;
+    memcpy(&magic, in, 4);
+    const DecCodecs& c = dec_codecs();
+    const size_t kStep = 1 << 20;
+    if (magic == 0x184D2204u) {
+        AURON_CHECK(c.lz4_create && c.lz4_decompress, "liblz4.so.1 not available");
+        void* ctx = nullptr;
+        AURON_CHECK(!c.lz4_iserr(c.lz4_create(&ctx, 100)), "LZ4F context");
+        size_t ip = 0;
+        try {
+            for (;;) {
+                size_t have = out.size();
+                out.resize(have + kStep);
+                size_t dn = kStep, sn = n - ip;
+                size_t r = c.lz4_decompress(ctx, out.data() + have, &dn, in + ip, &sn, nullptr);
+                out.resize(have + dn);
+                AURON_CHECK(!c.lz4_iserr(r), "shuffle read: corrupt LZ4 frame");
+                ip += sn;
+                if (r == 0) break;                                   // frame complete
+                AURON_CHECK(dn > 0 || sn > 0, "shuffle read: truncated LZ4 frame");
+            }
+        } catch (...) {
+            c.lz4_free(ctx);
+            throw;
+        }
+        c.lz4_free(ctx);
+    } else if (magic == 0xFD2FB528u) {
+        AURON_CHECK(c.z_create && c.z_stream, "libzstd.so.1 not available");
+        void* ds = c.z_create();
+        AURON_CHECK(ds, "ZSTD stream");
+        ZInBuf ib{in, n, 0};
+        try {
+            for (;;) {
+                size_t have = out.size();
+                out.resize(have + kStep);
+                ZOutBuf ob{out.data() + have, kStep, 0};
+                const size_t before = ib.pos;
+                size_t r = c.z_stream(ds, &ob, &ib);
+                out.resize(have + ob.pos);
+                AURON_CHECK(!c.z_iserr(r), "shuffle read: corrupt ZSTD stream");
+                if (r == 0) break;                                   // frame complete
+                AURON_CHECK(ob.pos > 0 || ib.pos > before, "shuffle read: truncated ZSTD stream");
+            }
+        } catch (...) {
+            c.z_free(ds);
+            throw;
+        }
+        c.z_free(ds);
+    } else {
+        fail("shuffle read: unknown codec stream (neither an LZ4 frame nor ZSTD)");
+    }
+}
+uint64_t read_varint(const uint8_t* p, int64_t n, int64_t* pos) {   // io/mod.rs:71-84
+    uint64_t v = 0;
+    int shift = 0;
+    for (;;) {
+        AURON_CHECK(*pos < n && shift < 64, "shuffle read: truncated varint");
+        uint8_t b = p[(*pos)++];
+        v |= (uint64_t)(b & 0x7f) << shift;
+        if (!(b & 0x80)) return v;
+        shift += 7;
+    }
+}
+}  // namespace
+
+struct IpcReaderExec : Operator {
+    std::string resource_id;
+    bool done = false;
+    struct Block {
+        std::string path;
+        int64_t offset = 0, length = 0;
+        const uint8_t* data = nullptr;
+        std::vector<uint8_t> copy;   // in-memory blocks are only valid until the next upcall: copied at once
+    };
+
+    bool next_block(Task& t, Block* out) {
+        AURON_CHECK(t.cb && t.cb->next_shuffle_block, "IpcReaderExec needs the next_shuffle_block callback");
+        auron_shuffle_block b;
+        memset(&b, 0, sizeof(b));
+        int r = t.cb->next_shuffle_block(t.cb->user, resource_id.c_str(), &b);
+        AURON_CHECK(r >= 0, "next_shuffle_block failed for resource " + resource_id);
+        if (r == 0) return false;
+        out->path = b.path ? b.path : "";
+        out->offset = b.offset;
+        out->length = b.length;
+        AURON_CHECK(out->length >= 0 && (b.data || !out->path.empty()), "next_shuffle_block returned an empty block descriptor");
+        if (b.data) {
+            out->copy.assign(b.data, b.data + out->length);
+            out->data = out->copy.data();
+        }
+        return true;
+    }
+
+    BatchPtr next(Task& t) override {
+        if (done) return nullptr;
+        OpTimer timer(metrics, "elapsed_ns");
+        const int ncols = (int)out_schema.fields.size();
+        // ---- 1. gather blocks for this chunk
+        std::vector<Block> blocks;
+        int64_t fetched = 0;
+        const int64_t kChunkBytes = 256ll << 20;   // compressed bytes per chunk
+        while (fetched < kChunkBytes) {
+            AURON_CHECK(t.is_running(), "task killed");
+            Block b;
+            if (!next_block(t, &b)) {
+                done = true;
+                break;
+            }
+            if (b.length == 0) continue;
+            fetched += b.length;
+            blocks.push_back(std::move(b));
+        }
+        if (blocks.empty()) return nullptr;
+        // ---- 2. bytes of every block -> host, split into codec streams
+        std::vector<std::vector<uint8_t>> owned(blocks.size());
+        struct Stream {
+            const uint8_t* p;
+            size_t n;
+        };
+        std::vector<Stream> streams;
+        {
+            OpTimer tf(metrics, "fetch_ns");
+            parallel_for(blocks.size(), 16, [&](size_t i) {
+                Block& b = blocks[i];
+                if (b.data) return;
+                owned[i].resize((size_t)b.length);
+                int fd = open(b.path.c_str(), O_RDONLY);
+                AURON_CHECK(fd >= 0, "cannot open shuffle file " + b.path);
+                int64_t got = 0;
+                while (got < b.length) {
+                    ssize_t r = pread(fd, owned[i].data() + got, (size_t)(b.length - got), b.offset + got);
+                    if (r <= 0) {
+                        close(fd);
+                        fail("short read on shuffle file " + b.path);
+                    }
+                    got += r;
+                }
+                close(fd);
+                b.data = owned[i].data();
+            });
+            for (auto& b : blocks) {
+                int64_t pos = 0;
+                while (pos < b.length) {
+                    AURON_CHECK(pos + 4 <= b.length, "shuffle read: truncated block header");
+                    uint32_t len;
+                    memcpy(&len, b.data + pos, 4);
+                    pos += 4;
+                    AURON_CHECK(pos + (int64_t)len <= b.length, "shuffle read: block overruns its segment");
+                    if (len) streams.push_back(Stream{b.data + pos, (size_t)len});
+                    pos += len;
+                }
+            }
+        }
+        // ---- 3. decompress (worker pool), concatenate into one pinned payload
+        std::vector<std::vector<uint8_t>> raw(streams.size());
+        {
+            OpTimer td(metrics, "decompress_ns");
+            parallel_for(streams.size(), 32, [&](size_t i) { decompress_stream(streams[i].p, streams[i].n, raw[i]); });
+        }
+        int64_t total = 0;
+        std::vector<int64_t> raw_off(raw.size() + 1, 0);
+        for (size_t i = 0; i < raw.size(); i++) {
+            raw_off[i] = total;
+            total += (int64_t)raw[i].size();
+        }
+        raw_off[raw.size()] = total;
+        metrics.add("size", total);
+        size_t cap = 0;
+        uint8_t* payload = (uint8_t*)pinned_pool().get((size_t)total + 64, &cap);
+        struct PinnedGuard {
+            uint8_t* p;
+            size_t cap;
+            ~PinnedGuard() { pinned_pool().put(p, cap); }
+        } guard{payload, cap};
+        parallel_for(raw.size(), 16, [&](size_t i) {
+            if (!raw[i].empty()) memcpy(payload + raw_off[i], raw[i].data(), raw[i].size());
+        });
+        raw.clear();
+        owned.clear();
+        // ---- 4. layout walk (batches may continue across stream boundaries: the payload is one byte stream)
+        std::vector<std::vector<DeserSeg>> segs((size_t)ncols);
+        std::vector<std::vector<DeserCopy>> copies((size_t)ncols);
+        std::vector<int64_t> col_bytes((size_t)ncols, 0);
+        int64_t rows = 0, pos = 0;
+        {
+            OpTimer tw(metrics, "layout_ns");
+            while (pos < total) {
+                const int64_t n = (int64_t)read_varint(payload, total, &pos);
+                for (int c = 0; c < ncols; c++) {
+                    const DType& ty = out_schema.fields[(size_t)c].type;
+                    if (ty.id == T_NULL) continue;
+                    DeserSeg s{-1, 0, rows, n};
+                    const uint64_t has_nulls = read_varint(payload, total, &pos);
+                    if (has_nulls) {
+                        s.validity_off = pos;
+                        pos += (n + 7) / 8;
+                    }
+                    s.values_off = pos;
+                    if (ty.id == T_BOOL) pos += (n + 7) / 8;
+                    else if (ty.is_varlen()) {
+                        AURON_CHECK(pos + 4 * n <= total, "shuffle read: truncated length planes");
+                        const uint8_t *p0 = payload + pos, *p1 = p0 + n, *p2 = p1 + n, *p3 = p2 + n;
+                        int64_t sum = 0;
+                        for (int64_t i = 0; i < n; i++) sum += (int64_t)((uint32_t)p0[i] | ((uint32_t)p1[i] << 8) | ((uint32_t)p2[i] << 16) | ((uint32_t)p3[i] << 24));
+                        pos += 4 * n;
+                        for (int64_t o = 0; o < sum; o += 1 << 20)
+                            copies[(size_t)c].push_back(DeserCopy{pos + o, col_bytes[(size_t)c] + o, std::min<int64_t>(1 << 20, sum - o)});
+                        col_bytes[(size_t)c] += sum;
+                        pos += sum;
+                    } else pos += (int64_t)ty.width() * n;
+                    AURON_CHECK(pos <= total, "shuffle read: batch overruns the payload");
+                    segs[(size_t)c].push_back(s);
+                }
+                rows += n;
+                AURON_CHECK(rows < (int64_t)INT32_MAX, "shuffle read: chunk too large");
+            }
+        }
+        // ---- 5. device
+        Buf dpayload = dalloc(t.ctx, (size_t)total + 64);
+        CUDA_OK(cudaMemcpyAsync(dpayload->ptr, payload, (size_t)total, cudaMemcpyHostToDevice, t.ctx.stream));
+        auto out = std::make_shared<Batch>();
+        out->num_rows = rows;
+        for (int c = 0; c < ncols; c++)
+            out->cols.push_back(deserialize_column(t.ctx, out_schema.fields[(size_t)c].type, P<uint8_t>(dpayload), segs[(size_t)c], rows, copies[(size_t)c], col_bytes[(size_t)c]));
+        t.ctx.sync();   // the pinned payload goes back to the pool
+        metrics.add("output_rows", rows);
+        return out;
+    }
+};
+
+OperatorPtr make_ipc_reader(Task&, const Schema& schema, const std::string& resource_id) {
+    auto op = std::make_unique<IpcReaderExec>();
+    op->name = "IpcReaderExec";
+    op->out_schema = schema;
+    op->resource_id = resource_id;
+    return op;
+}
+
+}  // namespace auron

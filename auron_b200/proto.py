@@ -208,6 +208,11 @@ def ffi_reader(s: pa.Schema, resource_id: str, num_partitions: int = 1) -> bytes
     return f_bytes(18, f_varint(1, num_partitions) + f_bytes(2, schema(s)) + f_str(3, resource_id))
 
 
+def ipc_reader(s: pa.Schema, resource_id: str, num_partitions: int = 1) -> bytes:
+    """PhysicalPlanNode{ipc_reader}: shuffle read (auron.proto:636-640)"""
+    return f_bytes(3, f_varint(1, num_partitions) + f_bytes(2, schema(s)) + f_str(3, resource_id))
+
+
 def filter_(inp: bytes, exprs: list[bytes]) -> bytes:
     return f_bytes(8, f_bytes(1, inp) + b"".join(f_bytes(2, e) for e in exprs))
 

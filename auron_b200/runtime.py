@@ -33,8 +33,16 @@ _RUNNING_CB = C.CFUNCTYPE(C.c_int, C.c_void_p)
 _METRIC_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_int64)
 
 
+class ShuffleBlockC(C.Structure):
+    _fields_ = [("path", C.c_char_p), ("offset", C.c_int64), ("length", C.c_int64), ("data", C.c_void_p)]
+
+
+_BLOCK_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p, C.POINTER(ShuffleBlockC))
+
+
 class Callbacks(C.Structure):
-    _fields_ = [("user", C.c_void_p), ("export_next_batch", _EXPORT_CB), ("read_fully", _READ_CB), ("is_task_running", _RUNNING_CB)]
+    _fields_ = [("user", C.c_void_p), ("export_next_batch", _EXPORT_CB), ("read_fully", _READ_CB), ("is_task_running", _RUNNING_CB),
+                ("next_shuffle_block", _BLOCK_CB)]
 
 
 class AuronError(RuntimeError):
@@ -108,9 +116,40 @@ class Task:
     """One native task: callNative -> nextBatch* -> finalizeNative (JniBridge.java:49-55)."""
 
     def __init__(self, task_definition: bytes, inputs: dict[str, Iterable[pa.RecordBatch]] | None = None, device: int = 0,
-                 read_fully=None):
+                 read_fully=None, shuffle_blocks: dict[str, Iterable] | None = None):
+        """shuffle_blocks: resource id -> iterable of blocks for IpcReaderExec; a block is (path, offset, length) for a file
+        segment or a bytes object for an in-memory buffer (AuronBlockObject.hasFileSegment / hasByteBuffer)."""
         self._inputs = {k: iter(v) for k, v in (inputs or {}).items()}
+        self._blocks = {k: iter(v) for k, v in (shuffle_blocks or {}).items()}
+        self._block_keep = None
         self._cb_error: BaseException | None = None
+
+        def _next_block(user, rid, out):
+            try:
+                it = self._blocks.get(rid.decode())
+                if it is None:
+                    return -1
+                blk = next(it, None)
+                if blk is None:
+                    return 0
+                if isinstance(blk, (bytes, bytearray, memoryview)):
+                    buf = C.create_string_buffer(bytes(blk), len(blk))
+                    self._block_keep = buf                       # valid until the next upcall
+                    out[0].path = None
+                    out[0].offset = 0
+                    out[0].length = len(blk)
+                    out[0].data = C.cast(buf, C.c_void_p)
+                else:
+                    path, offset, length = blk
+                    self._block_keep = path.encode()
+                    out[0].path = self._block_keep
+                    out[0].offset = offset
+                    out[0].length = length
+                    out[0].data = None
+                return 1
+            except BaseException as e:  # noqa: BLE001 - must not unwind through C
+                self._cb_error = e
+                return -1
 
         def _export_next(user, rid, out_ptr):
             try:
@@ -140,7 +179,8 @@ class Task:
                 self._cb_error = e
                 return -1
 
-        self._cbs = Callbacks(None, _EXPORT_CB(_export_next), _READ_CB(_read) if read_fully is not None else _READ_CB(0), _RUNNING_CB(0))
+        self._cbs = Callbacks(None, _EXPORT_CB(_export_next), _READ_CB(_read) if read_fully is not None else _READ_CB(0), _RUNNING_CB(0),
+                              _BLOCK_CB(_next_block))
         self._handle = lib().auron_b200_call_native(task_definition, len(task_definition), C.addressof(self._cbs), device)
         if not self._handle:
             raise AuronError(_err())
@@ -194,9 +234,10 @@ class Task:
             pass
 
 
-def run_task(task_definition: bytes, inputs: dict[str, Iterable[pa.RecordBatch]] | None = None, device: int = 0, read_fully=None) -> pa.Table:
+def run_task(task_definition: bytes, inputs: dict[str, Iterable[pa.RecordBatch]] | None = None, device: int = 0, read_fully=None,
+             shuffle_blocks: dict[str, Iterable] | None = None) -> pa.Table:
     """Execute a TaskDefinition and collect its output stream."""
-    with Task(task_definition, inputs, device, read_fully) as t:
+    with Task(task_definition, inputs, device, read_fully, shuffle_blocks) as t:
         batches = list(t)
         return pa.Table.from_batches(batches, schema=t.schema)
 

@@ -32,6 +32,13 @@ extern "C" {
 struct ArrowSchema;
 struct ArrowArray;
 
+typedef struct auron_shuffle_block {
+    const char* path;      /* file segment: path + offset + length */
+    int64_t offset;
+    int64_t length;
+    const uint8_t* data;   /* in-memory block: data + length (path == NULL) */
+} auron_shuffle_block;
+
 /* Upcalls (all optional except export_next_batch when the plan has an FFIReaderExec). */
 typedef struct auron_callbacks {
     void* user;
@@ -45,6 +52,11 @@ typedef struct auron_callbacks {
     int64_t (*read_fully)(void* user, const char* fs_resource_id, const char* path, int64_t pos, void* buf, int64_t len);
     /* JniBridge.isTaskRunning() (auron-jni-bridge/src/lib.rs:35-50).  NULL => always running. */
     int (*is_task_running)(void* user);
+    /* Next shuffle block of the iterator registered under resource_id (IpcReaderExec: the Scala iterator of
+     * AuronBlockObject, ipc_reader_exec.rs:186-207): a file segment (path, offset, length -- hasFileSegment) or an
+     * in-memory buffer (data, length -- hasByteBuffer; must stay valid until the next call).  Returns 1 = block
+     * produced, 0 = end of input, <0 = error.  Only needed when the plan has an IpcReaderExecNode. */
+    int (*next_shuffle_block)(void* user, const char* resource_id, struct auron_shuffle_block* out);
 } auron_callbacks;
 
 typedef struct auron_task auron_task;
