@@ -77,6 +77,35 @@ def build_plan(P, files: list[str], sizes: list[int]) -> bytes:
     return P.task_definition(agg)
 
 
+def bind_to_gpu_numa_node(torch, gpu_index: int):
+    """One process per GPU: run on the cores of the GPU's NUMA node, so that the pinned host buffers (first touch) and the
+    scan's worker threads sit next to the PCIe root the GPU hangs off.  Without it the 8-GPU e2e leg is bound by
+    cross-socket traffic.  Returns the node id or None (single-node boxes, missing sysfs entries)."""
+    try:
+        p = torch.cuda.get_device_properties(gpu_index)
+        if hasattr(p, "pci_bus_id"):
+            bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        else:   # older torch: NVML reports the same bus id string
+            import pynvml
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(gpu_index)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            bdf = bus[-12:].lower()
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(base + "/numa_node").read())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node >= 0 and cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """SM clock + throttle reasons sampled DURING the timed region (profiling recipe), through NVML in a background thread
     (the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints, without a subprocess per sample)."""
@@ -160,7 +189,7 @@ def main():
               "parquet": f"3 INT32 columns, RLE_DICTIONARY + PLAIN fallback pages, 8M-row (~128 MB) row groups, {CODEC} pages "
                          "(decompressed on the GPU)",
               "l2_policy": "inputs (>=1.4 GB encoded, 3.4 GB decoded per step) are far larger than the 126 MB L2",
-              "parallelism": f"dp{args.gpus}: table partitions sharded per GPU, no data-path collective"}
+              "parallelism": f"dp{args.gpus}: table partitions sharded per GPU, no data-path collective; one process per GPU bound to the GPU's NUMA node"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -188,6 +217,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank)    # before any pinned allocation / worker thread exists
+    config["numa_node"] = numa
     from auron_b200 import proto as P
     from auron_b200 import runtime
 
