@@ -213,6 +213,24 @@ def test_ipc_reader_reads_reference_style_blocks(tmp_path, codec):
 
 
 @pytest.mark.parametrize("codec", ["lz4", "zstd"])
+def test_ipc_reader_batches_straddling_blocks(codec):
+    # the reference's reader chains blocks into one byte stream (ipc_compression.rs:131-170), so a batch may in principle end in
+    # the next block: cut the payload at arbitrary byte positions
+    t = _table(20_000, seed=8)
+    payload = b"".join(oracle.serde_write_batch(b) for b in t.to_batches(max_chunksize=3000))
+    seg = b""
+    for o in range(0, len(payload), 10_007):
+        sink = pa.BufferOutputStream()
+        with pa.CompressedOutputStream(sink, codec) as z:
+            z.write(payload[o:o + 10_007])
+        comp = sink.getvalue().to_pybytes()
+        seg += struct.pack("<I", len(comp)) + comp
+    got = runtime.run_task(P.task_definition(P.ipc_reader(t.schema, "in")), shuffle_blocks={"in": [seg]})
+    for name in t.column_names:
+        assert got[name].to_pylist() == t[name].to_pylist(), name
+
+
+@pytest.mark.parametrize("codec", ["lz4", "zstd"])
 def test_shuffle_write_then_read_two_stage_aggregate(tmp_path, codec, monkeypatch):
     # the file-based exchange end to end: stage 1 partial aggregate -> ShuffleWriterExec (hash on the group key), stage 2 per
     # partition IpcReaderExec -> final aggregate; the union of the partitions equals a one-stage aggregate

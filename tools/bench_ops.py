@@ -122,4 +122,25 @@ if "sort" in which or "shuffle" in which:
             alg={"murmur3_partition_ids": 8 * N, "partition_rows": 8 * N, "take": 2 * 28 * N, "serde_write": 2 * 28 * N,
                  "lz4_compress": 28 * N + os.path.getsize(d + "/s.data") if os.path.exists(d + "/s.data") else 28 * N})
         print(f"     shuffle file: {os.path.getsize(d + '/s.data') / 1e6:.0f} MB")
+        # read side: IpcReaderExec over all 200 segments of the file just written (+ COUNT so that one row leaves the GPU)
+        import struct
+        offs = struct.unpack("<201q", open(f"{d}/s.index", "rb").read())
+        blocks = [(f"{d}/s.data", offs[p], offs[p + 1] - offs[p]) for p in range(200)]
+        rplan = P.agg(P.ipc_reader(t4.schema, "shuffle_in"), [], [], [P.agg_expr("COUNT", [P.col("ss_item_sk")], pa.int64()),
+                                                                      P.agg_expr("SUM", [P.col("ss_ticket_number")], pa.int64())], ["c", "s"], ["PARTIAL"] * 2)
+        td = P.task_definition(rplan)
+        best = None
+        for it in range(3):
+            t0 = time.perf_counter()
+            with runtime.Task(td, shuffle_blocks={"shuffle_in": list(blocks)}) as task:
+                out = pa.Table.from_batches(list(task), schema=task.schema)
+                m = task.metrics()
+            dt = time.perf_counter() - t0
+            if best is None or dt < best[0]:
+                best = (dt, out, m)
+        dt, out, m = best
+        print(f"== cfg4 IpcReaderExec (shuffle read) of the same file: {N / dt / 1e6:.0f} Mrows/s ({1000 * dt:.1f} ms, count = {out.column(0).to_pylist()})")
+        for _, op, name, v in m:
+            if op != "__kernels__" and name.endswith("_ns") and v > 2e5:
+                print(f"     [{op}.{name} = {v / 1e6:.2f} ms]")
     runtime.drop_device_resource("t4")
