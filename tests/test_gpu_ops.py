@@ -664,3 +664,34 @@ def test_errors_are_reported_not_thrown():
         run(P.filter_(P.ffi_reader(t.schema, "t"), [P.binary("Gt", P.col("nope"), P.lit(1, pa.int32()))]), {"t": t})
     with pytest.raises(runtime.AuronError):
         runtime.run_task(b"\x12\x03\xff\xff\xff", {})
+
+
+def test_concurrent_tasks_share_the_library():
+    # Spark runs several tasks of an executor concurrently in one process: every native task has its own stream and context,
+    # the process-wide pools (pinned staging, worker threads, staged uploads, device landing buffers) are shared
+    import concurrent.futures
+    rng = np.random.default_rng(1)
+    n = 200_000
+    tables = [pa.table({"k": pa.array(rng.integers(0, 1000, n), type=pa.int32()), "v": pa.array(rng.integers(-50, 50, n), type=pa.int64(),
+                                                                                                 mask=rng.random(n) < 0.1),
+                        "s": pa.array([f"w{int(x)}" for x in rng.integers(0, 50, n)])}) for _ in range(6)]
+
+    def job(i):
+        t = tables[i]
+        flt = P.filter_(P.ffi_reader(t.schema, "t"), [P.binary("GtEq", P.col("k"), P.lit(100 * (i % 3), pa.int32())), P.like(P.col("s"), P.lit("w1%", pa.string()))])
+        plan = P.agg(flt, [P.col("k")], ["k"], [P.agg_expr("SUM", [P.col("v")], pa.int64()), P.agg_expr("COUNT", [P.col("v")], pa.int64())], ["s", "c"], ["PARTIAL"] * 2)
+        out = []
+        for _ in range(3):
+            out.append(run(plan, {"t": t}, chunk=50_000))
+        return out
+
+    with concurrent.futures.ThreadPoolExecutor(max_workers=6) as ex:
+        results = list(ex.map(job, range(6)))
+    for i, outs in enumerate(results):
+        t = tables[i]
+        keep = pc.and_kleene(pc.greater_equal(t["k"], 100 * (i % 3)), pc.starts_with(t["s"], "w1"))
+        ft = t.filter(keep)
+        exp = oracle.agg_sum_count_i64(ft["k"].combine_chunks().cast(pa.int64()), ft["v"].combine_chunks())
+        for got in outs:
+            got = pa.table({"k": got.column(0).cast(pa.int64()), "s": got.column(1), "c": got.column(2)})
+            assert_same_rows(got, exp)
