@@ -47,6 +47,7 @@ struct AccDesc {
     // SUM/MIN/MAX(x) next to COUNT(x) over the same column: the group's accumulator is valid iff that count is non-zero,
     // so the per-row valid-flag store (one more random L2 access per row) is dropped and validity is read from the count.
     const unsigned long long* valid_cnt;
+    const int32_t* in_offsets;   // utf8 / binary input (MIN_STR / MAX_STR compare rows through it)
 };
 struct AccArgs {
     AccDesc a[kMaxAccs];
@@ -122,8 +123,22 @@ __device__ __forceinline__ bool acc_load(const AccDesc& d, int64_t row, int64_t 
             if (!ok) return false;
             v.lo = (uint64_t)pos;
             return true;
+        case ACC_MIN_STR: case ACC_MAX_STR:
+            if (!ok) return false;
+            v.lo = (uint64_t)row;
+            return true;
     }
     return false;
+}
+// byte-wise (unsigned, shorter-prefix-first) order of two rows of a utf8 / binary column: < 0, 0, > 0
+__device__ __forceinline__ int str_row_cmp(const uint8_t* __restrict__ data, const int32_t* __restrict__ offs, int64_t a, int64_t b) {
+    const int32_t a0 = offs[a], la = offs[a + 1] - a0, b0 = offs[b], lb = offs[b + 1] - b0;
+    const int32_t m = la < lb ? la : lb;
+    for (int32_t i = 0; i < m; i++) {
+        const int d = (int)data[a0 + i] - (int)data[b0 + i];
+        if (d) return d;
+    }
+    return la - lb;
 }
 
 __device__ __forceinline__ void acc_apply(const AccDesc& d, int64_t slot, const AccVal& v) {
@@ -146,6 +161,20 @@ __device__ __forceinline__ void acc_apply(const AccDesc& d, int64_t slot, const 
         case ACC_MAX:
             atomicMax((long long*)&d.acc_lo[slot * d.lo_stride], (long long)v.lo);
             break;
+        case ACC_MIN_STR: case ACC_MAX_STR: {   // install this row unless the installed one is already at least as extreme
+            unsigned long long* p = &d.acc_lo[slot * d.lo_stride];
+            unsigned long long cur = *(volatile unsigned long long*)p;
+            for (;;) {
+                if (cur != ~0ull) {
+                    const int c = str_row_cmp((const uint8_t*)d.in, d.in_offsets, (int64_t)v.lo, (int64_t)cur);
+                    if (d.kind == ACC_MIN_STR ? c >= 0 : c <= 0) break;
+                }
+                const unsigned long long old = atomicCAS(p, cur, (unsigned long long)v.lo);
+                if (old == cur) break;
+                cur = old;
+            }
+            break;
+        }
     }
     if (d.acc_valid) d.acc_valid[slot * d.valid_stride] = 1;   // idempotent byte store, no atomic needed
 }
@@ -561,6 +590,10 @@ __global__ void __launch_bounds__(256) agg_global_kernel(AccArgs accs, const int
             int64_t row = sel ? (int64_t)sel[i] : i;
             AccVal v = {0, 0};
             bool ok = acc_load(d, row, i, v);
+            if (d.kind == ACC_MIN_STR || d.kind == ACC_MAX_STR) {   // rows are compared through the column: straight to the slot
+                if (ok) acc_apply(d, 0, v);
+                continue;
+            }
             acc_combine(d.kind, acc, av, v, ok);
         }
         for (int off = 16; off; off >>= 1) {
@@ -652,6 +685,9 @@ __global__ void __launch_bounds__(256) emit_acc_kernel(AccDesc d, const int32_t*
             case ACC_FIRST: case ACC_FIRST_IGNORES_NULL:
                 ((int32_t*)out)[i] = ok ? (int32_t)lo : -1;   // position; gathered by the host wrapper
                 break;
+            case ACC_MIN_STR: case ACC_MAX_STR:
+                ((int32_t*)out)[i] = (int32_t)(int64_t)lo;    // row of the extreme (-1 = none); gathered by the host wrapper
+                break;
             default:
                 ((uint64_t*)out)[i] = lo;
         }
@@ -740,6 +776,7 @@ static AccArgs prepare_accs(Ctx& ctx, const std::vector<AccSpec>& specs, int64_t
             d.in_valid = s.input->vbits();
             d.in_type = s.input->type.id;
             d.in_is_dec64 = s.input->type.id == T_DECIMAL128 && s.input->type.precision <= 18;
+            d.in_offsets = P<int32_t>(s.input->offsets);
         } else {
             d.in_type = T_NULL;
         }
@@ -778,8 +815,8 @@ static AccArgs prepare_accs(Ctx& ctx, const std::vector<AccSpec>& specs, int64_t
             bufs.hi.push_back(hi);
             d.acc_hi = P<unsigned long long>(hi);
         } else bufs.hi.push_back(nullptr);
-        if (s.kind == ACC_COUNT || s.kind == ACC_ADD_I64) {
-            bufs.valid.push_back(nullptr);
+        if (s.kind == ACC_COUNT || s.kind == ACC_ADD_I64 || s.kind == ACC_MIN_STR || s.kind == ACC_MAX_STR) {
+            bufs.valid.push_back(nullptr);   // (string extremes: "no row yet" is the accumulator value -1)
         } else {
             Buf v = dalloc_zero(ctx, (size_t)slots);
             bufs.valid.push_back(v);
@@ -816,6 +853,7 @@ static void init_accs(Ctx& ctx, const std::vector<AccSpec>& specs, AccArgs& args
         switch (specs[i].kind) {
             case ACC_MIN: case ACC_FIRST: case ACC_FIRST_IGNORES_NULL: init = 0x7fffffffffffffffull; break;
             case ACC_MAX: init = 0x8000000000000000ull; break;
+            case ACC_MIN_STR: case ACC_MAX_STR: init = ~0ull; break;
             default: init = 0;
         }
         if (init == 0) CUDA_OK(cudaMemsetAsync(args.a[i].acc_lo, 0, (size_t)slots * 8, ctx.stream));
@@ -849,6 +887,15 @@ static void emit_accs(Ctx& ctx, const std::vector<AccSpec>& specs, const AccArgs
             }
             out.push_back(take(ctx, s.gather_from ? *s.gather_from : *s.input, P<int32_t>(rows), g, true));
             if (s.kind == ACC_FIRST) out.push_back(isset);
+            continue;
+        }
+        if (s.kind == ACC_MIN_STR || s.kind == ACC_MAX_STR) {
+            Buf rows = dalloc(ctx, (size_t)std::max<int64_t>(g, 1) * 4);
+            if (g) {
+                emit_acc_kernel<<<blocks, 256, 0, ctx.stream>>>(d, slot_ids, g, T_INT32, rows->ptr, nullptr);
+                LAUNCH_CHECK(ctx);
+            }
+            out.push_back(take(ctx, *s.input, P<int32_t>(rows), g, true));
             continue;
         }
         bool nullable = d.acc_valid != nullptr || d.valid_cnt != nullptr;

@@ -64,6 +64,8 @@ enum AccKind : int32_t {
     ACC_MAX = 6,
     ACC_FIRST = 7,     // value of the smallest row index (+ is_set)
     ACC_FIRST_IGNORES_NULL = 8,
+    ACC_MIN_STR = 9,   // utf8 / binary input: the accumulator holds the ROW of the current extreme (byte-wise order), -1 = none
+    ACC_MAX_STR = 10,
 };
 struct AccSpec {
     AccKind kind;

@@ -340,8 +340,8 @@ static std::vector<AccSpec> build_specs(const std::vector<AggExprSpec>& aggs, co
                     specs.push_back({sum_kind(a.acc_types[0]), args[0], {}, a.acc_types[0], nullptr});
                     specs.push_back({ACC_COUNT, args[0], {}, DType(T_INT64), nullptr});
                     break;
-                case AGG_MIN: specs.push_back({ACC_MIN, args[0], {}, a.value_type, nullptr}); break;
-                case AGG_MAX: specs.push_back({ACC_MAX, args[0], {}, a.value_type, nullptr}); break;
+                case AGG_MIN: specs.push_back({args[0]->type.is_varlen() ? ACC_MIN_STR : ACC_MIN, args[0], {}, a.value_type, nullptr}); break;
+                case AGG_MAX: specs.push_back({args[0]->type.is_varlen() ? ACC_MAX_STR : ACC_MAX, args[0], {}, a.value_type, nullptr}); break;
                 case AGG_FIRST: specs.push_back({ACC_FIRST, args[0], {}, a.value_type, nullptr}); break;
                 case AGG_FIRST_IGNORES_NULL: specs.push_back({ACC_FIRST_IGNORES_NULL, args[0], {}, a.value_type, nullptr}); break;
             }
@@ -355,8 +355,8 @@ static std::vector<AccSpec> build_specs(const std::vector<AggExprSpec>& aggs, co
                     specs.push_back({ACC_ADD_I64, m[mc + 1], {}, DType(T_INT64), nullptr});
                     mc += 2;
                     break;
-                case AGG_MIN: specs.push_back({ACC_MIN, m[mc], {}, a.value_type, nullptr}); mc += 1; break;
-                case AGG_MAX: specs.push_back({ACC_MAX, m[mc], {}, a.value_type, nullptr}); mc += 1; break;
+                case AGG_MIN: specs.push_back({m[mc]->type.is_varlen() ? ACC_MIN_STR : ACC_MIN, m[mc], {}, a.value_type, nullptr}); mc += 1; break;
+                case AGG_MAX: specs.push_back({m[mc]->type.is_varlen() ? ACC_MAX_STR : ACC_MAX, m[mc], {}, a.value_type, nullptr}); mc += 1; break;
                 case AGG_FIRST: specs.push_back({ACC_FIRST, m[mc], {m[mc + 1]}, a.value_type, nullptr}); mc += 2; break;
                 case AGG_FIRST_IGNORES_NULL: specs.push_back({ACC_FIRST_IGNORES_NULL, m[mc], {}, a.value_type, nullptr}); mc += 1; break;
             }

@@ -695,3 +695,44 @@ def test_concurrent_tasks_share_the_library():
         for got in outs:
             got = pa.table({"k": got.column(0).cast(pa.int64()), "s": got.column(1), "c": got.column(2)})
             assert_same_rows(got, exp)
+
+
+@pytest.mark.parametrize("keys", [["k"], ["k", "g"], []])
+def test_agg_min_max_on_strings(keys):
+    # AggMaxMin over utf8 (maxmin.rs:100-296): byte-wise order, NULLs ignored, all-NULL groups give NULL; partial -> final merge
+    rng = np.random.default_rng(12)
+    n = 60_000
+    words = ["", "a", "ab", "abc", "b", "zz", "z", "天地", "天", "Ab", "~"]
+    t = pa.table({"k": pa.array(rng.integers(0, 300, n), type=pa.int32(), mask=rng.random(n) < 0.02),
+                  "g": pa.array([["x", "y", None][int(i)] for i in rng.integers(0, 3, n)]),
+                  "s": pa.array([words[int(i)] + str(int(j)) for i, j in zip(rng.integers(0, len(words), n), rng.integers(0, 50, n))], mask=rng.random(n) < 0.3),
+                  "f": pa.array(rng.integers(0, 10, n), type=pa.int32())})
+    # group 299 only has NULL strings
+    s = t["s"].to_pylist()
+    k = t["k"].to_pylist()
+    s = [None if kk == 299 else v for kk, v in zip(k, s)]
+    t = t.set_column(2, "s", pa.array(s, type=pa.string()))
+    flt = P.filter_(P.ffi_reader(t.schema, "t"), [P.binary("Lt", P.col("f"), P.lit(7, pa.int32()))])
+    part = P.agg(flt, [P.col(c) for c in keys], keys, [P.agg_expr("MIN", [P.col("s")], pa.string()), P.agg_expr("MAX", [P.col("s")], pa.string())],
+                 ["mn", "mx"], ["PARTIAL"] * 2)
+    final = P.agg(part, [P.col(c) for c in keys], keys, [P.agg_expr("MIN", [P.lit(None, pa.null())], pa.string()), P.agg_expr("MAX", [P.lit(None, pa.null())], pa.string())],
+                  ["mn", "mx"], ["FINAL"] * 2)
+    got = run(final, {"t": t}, chunk=17_000)
+    acc = {}
+    cols = [t[c].to_pylist() for c in keys]
+    for i, (v, f) in enumerate(zip(s, t["f"].to_pylist())):
+        if f >= 7:
+            continue
+        key = tuple(c[i] for c in cols)
+        a = acc.setdefault(key, [None, None])
+        if v is not None:
+            b = v.encode()
+            if a[0] is None or b < a[0]:
+                a[0] = b
+            if a[1] is None or b > a[1]:
+                a[1] = b
+    if not keys and not acc:
+        acc[()] = [None, None]
+    exp_rows = sorted([key + (None if a[0] is None else a[0].decode(), None if a[1] is None else a[1].decode()) for key, a in acc.items()], key=repr)
+    got_rows = sorted(zip(*[c.to_pylist() for c in got.columns]), key=repr)
+    assert got_rows == exp_rows
