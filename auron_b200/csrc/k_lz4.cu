@@ -72,7 +72,10 @@ __global__ void __launch_bounds__(128) lz4_compress_blocks_kernel(const Lz4Block
         }
         __syncwarp();
         if (valid) ht[h] = (uint16_t)q;   // candidates were read before any lane of this step published its position
-        const bool hit = valid && cand < q && lz_load4(src + cand) == seq;
+        // A candidate must agree on 8 bytes, not LZ4's minimum of 4: byte planes with a few distinct values (the third byte
+        // of a 204k-valued key) match everywhere for 4-8 bytes, and a warp spends ~400 cycles per sequence -- measured 17.3 ms
+        // per 1.8 GB with the 4-byte rule against 10.5 ms with this one, for a file that is 0.8 % larger (638 -> 643 MB).
+        const bool hit = valid && cand < q && lz_load4(src + cand) == seq && lz_load4(src + cand + 4) == lz_load4(src + q + 4);
         const unsigned ball = __ballot_sync(0xffffffffu, hit);
         if (ball == 0) {
             ip += 32;
