@@ -194,6 +194,10 @@ struct Column {
     Buf data;      // values; bool => bitmap; utf8/binary => bytes
     Buf offsets;   // int32[len+1] for utf8/binary
     int64_t data_bytes = 0;  // utf8/binary: number of payload bytes (== offsets[len])
+    // optional bounds of the non-null values of an integer column (a superset is fine): set by the Parquet scan from the
+    // column-chunk statistics, used by the aggregate's direct-address path instead of a min/max pass over the keys
+    bool has_range = false;
+    int64_t range_min = 0, range_max = 0;
 
     const uint8_t* vbits() const { return validity ? static_cast<const uint8_t*>(validity->ptr) : nullptr; }
     bool may_have_nulls() const { return validity != nullptr; }

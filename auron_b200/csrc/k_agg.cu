@@ -141,6 +141,10 @@ __device__ __forceinline__ int str_row_cmp(const uint8_t* __restrict__ data, con
     return la - lb;
 }
 
+// STR: the kernel instance handles string extremes (MIN_STR / MAX_STR).  Compiled into every instance, the CAS loop below
+// cost the SUM / COUNT path of agg_direct_kernel 50 % (2.0 -> 3.1 ms on the SF100 bench), so plans without string extremes
+// run instances that do not contain it.
+template <bool STR = false>
 __device__ __forceinline__ void acc_apply(const AccDesc& d, int64_t slot, const AccVal& v) {
     switch (d.kind) {
         case ACC_SUM_I64: case ACC_ADD_I64: case ACC_COUNT:
@@ -161,20 +165,21 @@ __device__ __forceinline__ void acc_apply(const AccDesc& d, int64_t slot, const 
         case ACC_MAX:
             atomicMax((long long*)&d.acc_lo[slot * d.lo_stride], (long long)v.lo);
             break;
-        case ACC_MIN_STR: case ACC_MAX_STR: {   // install this row unless the installed one is already at least as extreme
-            unsigned long long* p = &d.acc_lo[slot * d.lo_stride];
-            unsigned long long cur = *(volatile unsigned long long*)p;
-            for (;;) {
-                if (cur != ~0ull) {
-                    const int c = str_row_cmp((const uint8_t*)d.in, d.in_offsets, (int64_t)v.lo, (int64_t)cur);
-                    if (d.kind == ACC_MIN_STR ? c >= 0 : c <= 0) break;
+        case ACC_MIN_STR: case ACC_MAX_STR:
+            if constexpr (STR) {   // install this row unless the installed one is already at least as extreme
+                unsigned long long* p = &d.acc_lo[slot * d.lo_stride];
+                unsigned long long cur = *(volatile unsigned long long*)p;
+                for (;;) {
+                    if (cur != ~0ull) {
+                        const int c = str_row_cmp((const uint8_t*)d.in, d.in_offsets, (int64_t)v.lo, (int64_t)cur);
+                        if (d.kind == ACC_MIN_STR ? c >= 0 : c <= 0) break;
+                    }
+                    const unsigned long long old = atomicCAS(p, cur, (unsigned long long)v.lo);
+                    if (old == cur) break;
+                    cur = old;
                 }
-                const unsigned long long old = atomicCAS(p, cur, (unsigned long long)v.lo);
-                if (old == cur) break;
-                cur = old;
             }
             break;
-        }
     }
     if (d.acc_valid) d.acc_valid[slot * d.valid_stride] = 1;   // idempotent byte store, no atomic needed
 }
@@ -199,6 +204,7 @@ __device__ __forceinline__ uint64_t load_key64(const FastKey& k, int64_t row) {
 constexpr int kMaxProbe = 128;
 
 // one input row: key -> table slot (find or insert) -> accumulators
+template <bool STR>
 __device__ __forceinline__ void agg_fast_row(const FastKey& key, unsigned long long* __restrict__ table, int tw, int64_t cap, uint64_t mask,
                                              const AccArgs& accs, int64_t row, int64_t dense, int32_t* __restrict__ flags) {
     // flags[0] overflow, flags[1] sentinel-key slot used, flags[2] null slot used
@@ -232,7 +238,7 @@ __device__ __forceinline__ void agg_fast_row(const FastKey& key, unsigned long l
     for (int a = 0; a < accs.n; a++) {
         const AccDesc& d = accs.a[a];
         AccVal v = {0, 0};
-        if (acc_load(d, row, dense, v)) acc_apply(d, slot, v);
+        if (acc_load(d, row, dense, v)) acc_apply<STR>(d, slot, v);
     }
 }
 // The per-row chain selection -> key -> table slot -> accumulators is a sequence of dependent, mostly random accesses; the
@@ -241,6 +247,7 @@ __device__ __forceinline__ void agg_fast_row(const FastKey& key, unsigned long l
 // With a pending filter mask (selmask) every warp first compacts the selected rows of a 128-row window into shared memory
 // and then processes them 32 at a time: running the row body under the raw mask (55 % of the lanes active) measured
 // 4.4 ms instead of 3.2 ms, because requests in flight scale with the active lanes.
+template <bool STR>
 __global__ void __launch_bounds__(256) agg_fast_kernel(FastKey key, unsigned long long* __restrict__ table, int tw, int64_t cap, AccArgs accs,
                                                        const int32_t* __restrict__ sel, int64_t n, int32_t* __restrict__ flags,
                                                        const uint32_t* __restrict__ selmask) {
@@ -248,7 +255,7 @@ __global__ void __launch_bounds__(256) agg_fast_kernel(FastKey key, unsigned lon
     if (!selmask) {
         const int64_t stride = (int64_t)gridDim.x * 256;
         for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride)
-            agg_fast_row(key, table, tw, cap, mask, accs, sel ? (int64_t)sel[i] : i, i, flags);
+            agg_fast_row<STR>(key, table, tw, cap, mask, accs, sel ? (int64_t)sel[i] : i, i, flags);
         return;
     }
     __shared__ int32_t s_rows[8][128];
@@ -270,7 +277,7 @@ __global__ void __launch_bounds__(256) agg_fast_kernel(FastKey key, unsigned lon
         __syncwarp();
         for (int j = lane; j < pos; j += 32) {
             const int64_t row = s_rows[wid][j];
-            agg_fast_row(key, table, tw, cap, mask, accs, row, row, flags);
+            agg_fast_row<STR>(key, table, tw, cap, mask, accs, row, row, flags);
         }
         __syncwarp();
     }
@@ -286,6 +293,7 @@ struct DirectTable {
     long long kmin;
     int64_t range;
     uint8_t* seen;
+    int32_t* oor;   // set when a key falls outside [kmin, kmin + range): the bounds came from file statistics and were wrong
 };
 __global__ void __launch_bounds__(256) key_minmax_kernel(FastKey key, int64_t n, long long* __restrict__ out) {
     long long mn = 0x7fffffffffffffffll, mx = (long long)0x8000000000000000ull;
@@ -350,25 +358,33 @@ __global__ void __launch_bounds__(256) key_minmax_vec_kernel(const T* __restrict
         atomicMax(&out[1], mx);
     }
 }
+template <bool STR>
 __device__ __forceinline__ void agg_direct_row(const FastKey& key, const DirectTable& t, const AccArgs& accs, int64_t row, int64_t dense) {
     int64_t slot = t.range;
-    if (!key.validity || bit_get(key.validity, row)) slot = (int64_t)((long long)load_key64(key, row) - t.kmin);
+    if (!key.validity || bit_get(key.validity, row)) {
+        slot = (int64_t)((long long)load_key64(key, row) - t.kmin);
+        if ((uint64_t)slot >= (uint64_t)t.range) {   // never with bounds computed from the data; the flagged result is discarded
+            *t.oor = 1;
+            slot = t.range;
+        }
+    }
     bool marked = false;
     for (int a = 0; a < accs.n; a++) {
         const AccDesc& d = accs.a[a];
         AccVal v = {0, 0};
         if (acc_load(d, row, dense, v)) {
-            acc_apply(d, slot, v);
+            acc_apply<STR>(d, slot, v);
             marked = marked || (((d.kind == ACC_COUNT || d.kind == ACC_ADD_I64) && v.lo != 0) || d.acc_valid != nullptr);
         }
     }
     if (!marked) t.seen[slot] = 1;
 }
+template <bool STR>
 __global__ void __launch_bounds__(256) agg_direct_kernel(FastKey key, DirectTable t, AccArgs accs, const int32_t* __restrict__ sel, int64_t n,
                                                          const uint32_t* __restrict__ selmask) {
     if (!selmask) {
         const int64_t stride = (int64_t)gridDim.x * 256;
-        for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) agg_direct_row(key, t, accs, sel ? (int64_t)sel[i] : i, i);
+        for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) agg_direct_row<STR>(key, t, accs, sel ? (int64_t)sel[i] : i, i);
         return;
     }
     // pending filter mask: warp-local compaction of each 128-row window (see agg_fast_kernel)
@@ -390,7 +406,7 @@ __global__ void __launch_bounds__(256) agg_direct_kernel(FastKey key, DirectTabl
         __syncwarp();
         for (int j = lane; j < pos; j += 32) {
             const int64_t row = s_rows[wid][j];
-            agg_direct_row(key, t, accs, row, row);
+            agg_direct_row<STR>(key, t, accs, row, row);
         }
         __syncwarp();
     }
@@ -533,6 +549,7 @@ __global__ void __launch_bounds__(256) agg_fast_smem_kernel(FastKey key, unsigne
 }
 
 // -------------------------------------------------------------------------------- GENERAL path
+template <bool STR>
 __global__ void __launch_bounds__(256) agg_general_kernel(RowKeys keys, int32_t* __restrict__ slots, int64_t cap, AccArgs accs,
                                                           const int32_t* __restrict__ sel, int64_t n, int32_t* __restrict__ flags, const uint32_t* __restrict__ selmask) {
     int64_t stride = (int64_t)gridDim.x * 256;
@@ -558,7 +575,7 @@ __global__ void __launch_bounds__(256) agg_general_kernel(RowKeys keys, int32_t*
         }
         for (int a = 0; a < accs.n; a++) {
             AccVal v;
-            if (acc_load(accs.a[a], row, i, v)) acc_apply(accs.a[a], slot, v);
+            if (acc_load(accs.a[a], row, i, v)) acc_apply<STR>(accs.a[a], slot, v);
         }
     }
 }
@@ -579,6 +596,7 @@ __device__ __forceinline__ void acc_combine(int kind, AccVal& a, bool& av, const
         case ACC_MAX: if ((int64_t)b.lo > (int64_t)a.lo) a.lo = b.lo; break;
     }
 }
+template <bool STR>
 __global__ void __launch_bounds__(256) agg_global_kernel(AccArgs accs, const int32_t* __restrict__ sel, int64_t n, const uint32_t* __restrict__ selmask) {
     int64_t stride = (int64_t)gridDim.x * 256;
     for (int a = 0; a < accs.n; a++) {
@@ -591,7 +609,7 @@ __global__ void __launch_bounds__(256) agg_global_kernel(AccArgs accs, const int
             AccVal v = {0, 0};
             bool ok = acc_load(d, row, i, v);
             if (d.kind == ACC_MIN_STR || d.kind == ACC_MAX_STR) {   // rows are compared through the column: straight to the slot
-                if (ok) acc_apply(d, 0, v);
+                if (ok) acc_apply<STR>(d, 0, v);
                 continue;
             }
             acc_combine(d.kind, acc, av, v, ok);
@@ -603,7 +621,7 @@ __global__ void __launch_bounds__(256) agg_global_kernel(AccArgs accs, const int
             bool ov = __shfl_down_sync(FULL_MASK, (int)av, off);
             acc_combine(d.kind, acc, av, o, ov);
         }
-        if (lane_id() == 0 && av) acc_apply(d, 0, acc);
+        if (lane_id() == 0 && av) acc_apply<STR>(d, 0, acc);
     }
 }
 
@@ -917,6 +935,8 @@ GroupedResult hash_aggregate(Ctx& ctx, const std::vector<ColumnPtr>& keys, const
     // kernels then skip unselected rows themselves and no index vector is ever materialised.  Mutually exclusive with sel.
     AURON_CHECK(!(sel && selmask), "hash_aggregate: both an index selection and a mask selection");
     const int64_t n_in = selmask && n_selected >= 0 ? n_selected : n_rows;   // rows that reach the table
+    bool has_str = false;   // string extremes need the kernel instances that carry their CAS loop
+    for (auto& sp : accs) has_str = has_str || sp.kind == ACC_MIN_STR || sp.kind == ACC_MAX_STR;
     AURON_CHECK(!keys.empty(), "hash_aggregate needs at least one key (use global_aggregate)");
     AURON_CHECK(n_rows < (int64_t)INT32_MAX, "chunk too large");
     GroupedResult res;
@@ -926,19 +946,25 @@ GroupedResult hash_aggregate(Ctx& ctx, const std::vector<ColumnPtr>& keys, const
     const bool int_key = fast && (kt0 == T_INT8 || kt0 == T_INT16 || kt0 == T_INT32 || kt0 == T_INT64 || kt0 == T_DATE32);
     if (int_key && (n_in >= (1 << 15) || getenv("AURON_FORCE_DIRECT_AGG")) && !getenv("AURON_DISABLE_DIRECT_AGG") && !getenv("AURON_AGG_INTERLEAVE") && !getenv("AURON_ENABLE_SMEM_AGG")) {
         FastKey k{keys[0]->data->ptr, keys[0]->vbits(), (int32_t)kt0};
-        const long long init[2] = {0x7fffffffffffffffll, (long long)0x8000000000000000ull};
-        Buf mm = to_device(ctx, init, 16);
-        {
-            ProfScope ps(ctx, "agg_key_range");
-            const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n_rows + 1023) / 1024, (int64_t)ctx.sm_count * 8));
-            const uint32_t* kv = (const uint32_t*)keys[0]->vbits();
-            if (kt0 == T_INT32 || kt0 == T_DATE32) key_minmax_vec_kernel<int32_t><<<grid, 256, 0, ctx.stream>>>((const int32_t*)k.data, kv, n_rows, P<long long>(mm));
-            else if (kt0 == T_INT64) key_minmax_vec_kernel<long long><<<grid, 256, 0, ctx.stream>>>((const long long*)k.data, kv, n_rows, P<long long>(mm));
-            else key_minmax_kernel<<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(k, n_rows, P<long long>(mm));
-            LAUNCH_CHECK(ctx);
-        }
         long long h[2];
-        to_host(ctx, h, mm->ptr, 16);
+        if (keys[0]->has_range) {   // bounds from the scan's column statistics: no pass over the keys
+            h[0] = keys[0]->range_min;
+            h[1] = keys[0]->range_max;
+        } else {
+            const long long init[2] = {0x7fffffffffffffffll, (long long)0x8000000000000000ull};
+            Buf mm = to_device(ctx, init, 16);
+            {
+                ProfScope ps(ctx, "agg_key_range");
+                const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n_rows + 1023) / 1024, (int64_t)ctx.sm_count * 8));
+                const uint32_t* kv = (const uint32_t*)keys[0]->vbits();
+                if (kt0 == T_INT32 || kt0 == T_DATE32) key_minmax_vec_kernel<int32_t><<<grid, 256, 0, ctx.stream>>>((const int32_t*)k.data, kv, n_rows, P<long long>(mm));
+                else if (kt0 == T_INT64) key_minmax_vec_kernel<long long><<<grid, 256, 0, ctx.stream>>>((const long long*)k.data, kv, n_rows, P<long long>(mm));
+                else key_minmax_kernel<<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(k, n_rows, P<long long>(mm));
+                LAUNCH_CHECK(ctx);
+            }
+            to_host(ctx, h, mm->ptr, 16);
+        }
+        if (getenv("AURON_AGG_DEBUG")) fprintf(stderr, "[agg] direct candidate: has_range=%d min=%lld max=%lld rows=%lld\n", (int)keys[0]->has_range, h[0], h[1], (long long)n_in);
         const bool any = h[0] <= h[1];
         const unsigned long long span = any ? (unsigned long long)h[1] - (unsigned long long)h[0] : 0ull;
         if (span < (1ull << 22)) {
@@ -949,13 +975,23 @@ GroupedResult hash_aggregate(Ctx& ctx, const std::vector<ColumnPtr>& keys, const
             AccBuffers bufs;
             AccArgs args = prepare_accs(ctx, accs, slots, bufs);
             init_accs(ctx, accs, args, slots);
-            Buf seen = dalloc_zero(ctx, (size_t)slots);
+            Buf seen = dalloc_zero(ctx, (size_t)slots + 8);
             dt.seen = P<uint8_t>(seen);
+            Buf oor = dalloc_zero(ctx, 4);
+            dt.oor = P<int32_t>(oor);
             {
                 ProfScope ps(ctx, "agg_update");
-                agg_direct_kernel<<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(k, dt, args, sel, n_rows, selmask);
+                if (has_str) agg_direct_kernel<true><<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(k, dt, args, sel, n_rows, selmask);
+                else agg_direct_kernel<false><<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(k, dt, args, sel, n_rows, selmask);
                 LAUNCH_CHECK(ctx);
             }
+            bool trusted = !keys[0]->has_range;
+            if (!trusted) {
+                int32_t bad = 0;
+                to_host(ctx, &bad, oor->ptr, 4);
+                trusted = bad == 0;
+            }
+            if (trusted) {
             Buf occ = dalloc(ctx, bitmap_alloc_bytes(slots));
             occupied_mask_direct_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, ctx.stream>>>(dt, args, P<uint32_t>(occ));
             LAUNCH_CHECK(ctx);
@@ -978,6 +1014,7 @@ GroupedResult hash_aggregate(Ctx& ctx, const std::vector<ColumnPtr>& keys, const
             res.keys->cols.push_back(kc);
             emit_accs(ctx, accs, args, P<int32_t>(slot_ids), g, sel, res.accs);
             return res;
+            }   // else: the file's statistics did not cover the data -> the hash table below starts from scratch
         }
     }
     // capacity: start at 1 Mi slots (covers <= ~500k groups), fall back to 2 x rows on overflow
@@ -1039,7 +1076,8 @@ GroupedResult hash_aggregate(Ctx& ctx, const std::vector<ColumnPtr>& keys, const
                 LAUNCH_CHECK(ctx);
             } else if (n_rows) {
                 ProfScope ps(ctx, "agg_update");
-                agg_fast_kernel<<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(k, P<unsigned long long>(table), tw, cap, args, sel, n_rows, P<int32_t>(flags), selmask);
+                if (has_str) agg_fast_kernel<true><<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(k, P<unsigned long long>(table), tw, cap, args, sel, n_rows, P<int32_t>(flags), selmask);
+                else agg_fast_kernel<false><<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(k, P<unsigned long long>(table), tw, cap, args, sel, n_rows, P<int32_t>(flags), selmask);
                 LAUNCH_CHECK(ctx);
             }
         } else {
@@ -1047,7 +1085,8 @@ GroupedResult hash_aggregate(Ctx& ctx, const std::vector<ColumnPtr>& keys, const
             RowKeys rk = make_row_keys(keys);
             if (n_rows) {
                 ProfScope ps(ctx, "agg_update");
-                agg_general_kernel<<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(rk, P<int32_t>(table), cap, args, sel, n_rows, P<int32_t>(flags), selmask);
+                if (has_str) agg_general_kernel<true><<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(rk, P<int32_t>(table), cap, args, sel, n_rows, P<int32_t>(flags), selmask);
+                else agg_general_kernel<false><<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(rk, P<int32_t>(table), cap, args, sel, n_rows, P<int32_t>(flags), selmask);
                 LAUNCH_CHECK(ctx);
             }
         }
@@ -1102,7 +1141,10 @@ std::vector<ColumnPtr> global_aggregate(Ctx& ctx, const std::vector<AccSpec>& ac
     AccArgs args = prepare_accs(ctx, accs, 1, bufs);
     init_accs(ctx, accs, args, 1);
     if (n_rows) {
-        agg_global_kernel<<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(args, sel, n_rows, selmask);
+        bool has_str = false;
+        for (auto& sp : accs) has_str = has_str || sp.kind == ACC_MIN_STR || sp.kind == ACC_MAX_STR;
+        if (has_str) agg_global_kernel<true><<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(args, sel, n_rows, selmask);
+        else agg_global_kernel<false><<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(args, sel, n_rows, selmask);
         LAUNCH_CHECK(ctx);
     }
     std::vector<ColumnPtr> out;

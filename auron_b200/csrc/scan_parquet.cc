@@ -323,6 +323,9 @@ struct ParquetScanExec : Operator {
         std::vector<Buf> keep;
         bool has_v1_inline = false;   // some v1 pages still need their level / value sections split on the device
         bool needs_decomp = false;    // some pages of this column are produced by the batch's decompression launch
+        // bounds of the non-null values from the column-chunk statistics of every chunk in the batch (INT32 / INT64)
+        bool stat_ok = true;
+        int64_t stat_min = INT64_MAX, stat_max = INT64_MIN;
     };
 
     // host-side count of non-null values of a v1 page (needed only for PLAIN string pages)
@@ -641,6 +644,13 @@ struct ParquetScanExec : Operator {
                 if (validity) {
                     col->validity = validity;
                     col->null_count = -1;
+                }
+                const TypeId ot = fld.type.id;
+                if (cs.stat_ok && cs.stat_min <= cs.stat_max && (ot == T_INT32 || ot == T_INT64 || ot == T_DATE32) && fld.type.width() >= phys_width(el.type, el.type_length) &&
+                    !getenv("AURON_SCAN_NO_STATS")) {
+                    col->has_range = true;
+                    col->range_min = cs.stat_min;
+                    col->range_max = cs.stat_max;
                 }
             }
             out->cols.push_back(col);
@@ -1006,6 +1016,26 @@ struct ParquetScanExec : Operator {
                         pg.val_ptr = base + fx.off + vo;
                         if (fx.sec != SIZE_MAX) cp.secs[fx.sec].ptr = pg.val_ptr;
                     }
+                }
+            }
+            {   // statistics -> value bounds (Statistics.min_value / max_value are PLAIN-encoded: little-endian two's complement)
+                const pq::Statistics& st = ct.cm->stats;
+                const size_t w = cs.el.type == pq::PT_INT32 ? 4 : cs.el.type == pq::PT_INT64 ? 8 : 0;
+                if (w && st.has_min && st.has_max && st.min_value.size() == w && st.max_value.size() == w) {
+                    int64_t mn, mx;
+                    if (w == 4) {
+                        int32_t a, b;
+                        memcpy(&a, st.min_value.data(), 4);
+                        memcpy(&b, st.max_value.data(), 4);
+                        mn = a, mx = b;
+                    } else {
+                        memcpy(&mn, st.min_value.data(), 8);
+                        memcpy(&mx, st.max_value.data(), 8);
+                    }
+                    cs.stat_min = std::min(cs.stat_min, mn);
+                    cs.stat_max = std::max(cs.stat_max, mx);
+                } else if (!(st.has_null_count && st.null_count == ct.cm->num_values)) {
+                    cs.stat_ok = false;   // (an all-NULL chunk has no min / max and constrains nothing)
                 }
             }
             int dict_base = (int)cs.dicts.size();

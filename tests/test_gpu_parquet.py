@@ -188,3 +188,29 @@ def test_scan_reports_corrupt_snappy_page(tmp_path):
     open(path, "wb").write(bytes(raw))
     with pytest.raises(runtime.AuronError):
         _scan(path, t.schema)
+
+
+def test_aggregate_survives_wrong_column_statistics(tmp_path):
+    # the scan hands the chunk statistics (min / max) to the aggregate's direct-address path; a file whose statistics do not
+    # cover its data (buggy writer) must still aggregate correctly (the kernel flags the out-of-range key, the hash table takes over)
+    rng = np.random.default_rng(3)
+    n = 100_000
+    k = rng.integers(1000, 2000, n).astype(np.int32)
+    k[:10] = [1000, 1999] * 5                                  # make sure both bounds occur
+    t = pa.table({"k": pa.array(k), "v": pa.array(rng.integers(0, 100, n), type=pa.int64())})
+    path = str(tmp_path / "stats.parquet")
+    pq.write_table(t, path, compression="NONE", use_dictionary=False)
+    raw = bytearray(open(path, "rb").read())
+    md = pq.ParquetFile(path).metadata
+    footer_len = int.from_bytes(raw[-8:-4], "little")
+    foot = len(raw) - 8 - footer_len
+    patched = raw[:foot] + raw[foot:].replace((1999).to_bytes(4, "little"), (1500).to_bytes(4, "little"))
+    assert patched != raw and len(patched) == len(raw)
+    open(path, "wb").write(bytes(patched))
+    assert pq.ParquetFile(path).metadata.row_group(0).column(0).statistics.max == 1500
+    scan = P.parquet_scan(t.schema, [(path, os.path.getsize(path))], [0, 1])
+    plan = P.agg(scan, [P.col("k")], ["k"], [P.agg_expr("SUM", [P.col("v")], pa.int64()), P.agg_expr("COUNT", [P.col("v")], pa.int64())], ["s", "c"], ["PARTIAL"] * 2)
+    got = run(plan, {})
+    exp = oracle.agg_sum_count_i64(t["k"].combine_chunks().cast(pa.int64()), t["v"].combine_chunks())
+    got = pa.table({"k": got.column(0).cast(pa.int64()), "s": got.column(1), "c": got.column(2)})
+    assert_same_rows(got, exp)
