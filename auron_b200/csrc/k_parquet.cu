@@ -615,7 +615,7 @@ __device__ __forceinline__ uint32_t extract_bits(const uint8_t* base, int64_t bi
 //   2. the tile's dictionary indices are unpacked into shared memory, lanes striding over each run;
 //   3. 32 rows per iteration: rank = base + popc(lower lanes), dictionary / PLAIN load, typed store.
 // Booleans keep the generic kernel above.
-__global__ void __launch_bounds__(PQ_WARPS * 32, 12) pq_decode_tiles_fast_kernel(PqLaunch L, int n_tiles) {
+__global__ void __launch_bounds__(PQ_WARPS * 32) pq_decode_tiles_fast_kernel(PqLaunch L, int n_tiles) {
     __shared__ uint32_t s_vals[PQ_WARPS][PQ_TILE];
     __shared__ uint32_t s_w[PQ_WARPS][33];
     __shared__ int32_t s_pref[PQ_WARPS][32];
