@@ -983,40 +983,39 @@ struct ParquetScanExec : Operator {
         Prepared& p = *ready;
         // ordered merge, rebasing dictionary ids / value-table positions; compressed chunks upload their payloads first
         std::vector<PqDecompJob> decomp_jobs;
-        for (auto& ct : p.tasks) {
+        OpTimer* tmerge = new OpTimer(metrics, "merge_ns");
+        // Phase A (serial, cheap): slot of every chunk in the per-column descriptor arrays, in the batch's scratch buffer for
+        // device-decompressed pages and in the job list; value bounds from the chunk statistics.
+        struct Slot {
+            int64_t unc_off = 0;
+            size_t job_base = 0, page_base = 0, dict_base = 0, sec_base = 0;
+            int32_t vbase = 0;
+            Buf host_unc;   // chunks decompressed on the host: their payload, uploaded below
+        };
+        std::vector<Slot> slots(p.tasks.size());
+        int64_t unc_total = 0;
+        size_t n_jobs = 0;
+        std::vector<size_t> npages(p.cols.size(), 0), ndicts(p.cols.size(), 0), nsecs(p.cols.size(), 0);
+        for (size_t ti = 0; ti < p.tasks.size(); ti++) {
+            ChunkTask& ct = p.tasks[ti];
             ColState& cs = p.cols[ct.col];
             ChunkPages& cp = ct.out;
-            if (!cp.unc.empty() || cp.gpu_unc_bytes > 0) {
-                Buf d;
-                if (cp.gpu_unc_bytes > 0) {   // decompressed by pq_decompress below, straight from the chunk bytes in HBM
-                    d = dalloc(t.ctx, (size_t)cp.gpu_unc_bytes + 64);
-                    const int32_t job_base = (int32_t)decomp_jobs.size();
-                    for (auto& pg : cp.pages)
-                        if (pg.job >= 0) pg.job += job_base;
-                    for (auto jb : cp.jobs) {
-                        jb.dst = P<uint8_t>(d) + (intptr_t)jb.dst;
-                        decomp_jobs.push_back(jb);
-                    }
-                    cs.has_v1_inline = cs.has_v1_inline || cp.has_v1_inline;
-                    cs.needs_decomp = true;
-                } else {
-                    d = to_device(t.ctx, cp.unc.data(), cp.unc.size());
-                    t.ctx.sync();
-                }
-                cs.keep.push_back(d);
-                const uint8_t* base = P<uint8_t>(d);
-                for (auto& fx : cp.fixes) {
-                    if (fx.page == SIZE_MAX) {
-                        cp.dicts[fx.dict].data = base + fx.off;
-                        if (fx.sec != SIZE_MAX) cp.secs[fx.sec].ptr = base + fx.off;
-                    } else {
-                        PqPage& pg = cp.pages[fx.page];
-                        pg.def_ptr = pg.def_len ? base + fx.off + (intptr_t)pg.def_ptr : nullptr;
-                        intptr_t vo = (intptr_t)pg.val_ptr;
-                        pg.val_ptr = base + fx.off + vo;
-                        if (fx.sec != SIZE_MAX) cp.secs[fx.sec].ptr = pg.val_ptr;
-                    }
-                }
+            Slot& sl = slots[ti];
+            sl.unc_off = unc_total;
+            unc_total += (cp.gpu_unc_bytes + 255) & ~(int64_t)255;
+            sl.job_base = n_jobs;
+            n_jobs += cp.jobs.size();
+            sl.page_base = npages[ct.col];
+            sl.dict_base = ndicts[ct.col];
+            sl.sec_base = nsecs[ct.col];
+            sl.vbase = (int32_t)cs.value_table_size;
+            npages[ct.col] += cp.pages.size();
+            ndicts[ct.col] += cp.dicts.size();
+            nsecs[ct.col] += cp.secs.size();
+            cs.value_table_size += cp.value_table_size;
+            if (cp.gpu_unc_bytes > 0) {
+                cs.has_v1_inline = cs.has_v1_inline || cp.has_v1_inline;
+                cs.needs_decomp = true;
             }
             {   // statistics -> value bounds (Statistics.min_value / max_value are PLAIN-encoded: little-endian two's complement)
                 const pq::Statistics& st = ct.cm->stats;
@@ -1038,23 +1037,74 @@ struct ParquetScanExec : Operator {
                     cs.stat_ok = false;   // (an all-NULL chunk has no min / max and constrains nothing)
                 }
             }
-            int dict_base = (int)cs.dicts.size();
-            int32_t vbase = (int32_t)cs.value_table_size;
-            for (auto d : cp.dicts) {
-                d.value_base += vbase;
-                cs.dicts.push_back(d);
+            if (!cp.unc.empty()) {   // host-decompressed payloads (ZSTD / LZ4_RAW pages, string columns) are uploaded here
+                sl.host_unc = to_device(t.ctx, cp.unc.data(), cp.unc.size());
+                cs.keep.push_back(sl.host_unc);
             }
-            for (auto s : cp.secs) {
-                s.value_base += vbase;
-                cs.secs.push_back(s);
-            }
-            for (auto pg : cp.pages) {
-                if (pg.dict_id >= 0) pg.dict_id += dict_base;
-                pg.plain_value_base += vbase;
-                cs.pages.push_back(pg);
-            }
-            cs.value_table_size += cp.value_table_size;
         }
+        Buf unc_scratch;   // one scratch allocation for every device-decompressed page of the batch
+        if (unc_total > 0) {
+            unc_scratch = dalloc(t.ctx, (size_t)unc_total + 256);
+            for (auto& cs : p.cols)
+                if (cs.needs_decomp) cs.keep.push_back(unc_scratch);
+        }
+        decomp_jobs.resize(n_jobs);
+        parallel_for(p.cols.size(), (unsigned)p.cols.size(), [&](size_t c) {   // (value-initialisation = page faults: one thread per column)
+            p.cols[c].pages.resize(npages[c]);
+            p.cols[c].dicts.resize(ndicts[c]);
+            p.cols[c].secs.resize(nsecs[c]);
+        });
+        // Phase B (worker pool): pointer fix-ups and the copy of every chunk's descriptors into its slot, rebased
+        parallel_for(p.tasks.size(), host_threads, [&](size_t ti) {
+            ChunkTask& ct = p.tasks[ti];
+            ColState& cs = p.cols[ct.col];
+            ChunkPages& cp = ct.out;
+            const Slot& sl = slots[ti];
+            if (!cp.unc.empty() || cp.gpu_unc_bytes > 0) {
+                const uint8_t* base;
+                if (cp.gpu_unc_bytes > 0) {   // decompressed by pq_decompress below, straight from the chunk bytes in HBM
+                    uint8_t* cbase = P<uint8_t>(unc_scratch) + sl.unc_off;
+                    base = cbase;
+                    for (auto& pg : cp.pages)
+                        if (pg.job >= 0) pg.job += (int32_t)sl.job_base;
+                    for (size_t j = 0; j < cp.jobs.size(); j++) {
+                        PqDecompJob jb = cp.jobs[j];
+                        jb.dst = cbase + (intptr_t)jb.dst;
+                        decomp_jobs[sl.job_base + j] = jb;
+                    }
+                } else base = P<uint8_t>(sl.host_unc);
+                for (auto& fx : cp.fixes) {
+                    if (fx.page == SIZE_MAX) {
+                        cp.dicts[fx.dict].data = base + fx.off;
+                        if (fx.sec != SIZE_MAX) cp.secs[fx.sec].ptr = base + fx.off;
+                    } else {
+                        PqPage& pg = cp.pages[fx.page];
+                        pg.def_ptr = pg.def_len ? base + fx.off + (intptr_t)pg.def_ptr : nullptr;
+                        intptr_t vo = (intptr_t)pg.val_ptr;
+                        pg.val_ptr = base + fx.off + vo;
+                        if (fx.sec != SIZE_MAX) cp.secs[fx.sec].ptr = pg.val_ptr;
+                    }
+                }
+            }
+            for (size_t i = 0; i < cp.dicts.size(); i++) {
+                PqDict d = cp.dicts[i];
+                d.value_base += sl.vbase;
+                cs.dicts[sl.dict_base + i] = d;
+            }
+            for (size_t i = 0; i < cp.secs.size(); i++) {
+                PqByteSection sc = cp.secs[i];
+                sc.value_base += sl.vbase;
+                cs.secs[sl.sec_base + i] = sc;
+            }
+            PqPage* dst = cs.pages.data() + sl.page_base;
+            for (size_t i = 0; i < cp.pages.size(); i++) {
+                PqPage pg = cp.pages[i];
+                if (pg.dict_id >= 0) pg.dict_id += (int32_t)sl.dict_base;
+                pg.plain_value_base += sl.vbase;
+                dst[i] = pg;
+            }
+        });
+        delete tmerge;
         BatchPtr b;
         {
             OpTimer timer2(metrics, "decode_ns");
