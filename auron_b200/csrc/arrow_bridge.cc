@@ -1,6 +1,10 @@
 // arrow_bridge.cc -- Arrow C Data Interface <-> device columns.
 #include "arrow_bridge.h"
 
+#include <memory>
+
+#include "host_pool.h"
+
 #include <cstdlib>
 
 namespace auron {
@@ -188,8 +192,26 @@ BatchPtr import_batch(Ctx& ctx, const ArrowArray* arr, const Schema& schema) {
 }
 
 // ------------------------------------------------------------------------------------------- export
+// All buffers of an exported batch live in ONE pinned block (D2H at full PCIe rate, one stream sync per batch instead of one
+// pageable copy + sync per buffer); the block goes back to the pinned pool when the last array pointing into it is released
+// (children may be moved out of the struct array and outlive it, so every array holds a reference).
+struct PinnedBlock {
+    void* p = nullptr;
+    size_t cap = 0;
+    size_t used = 0;
+    bool pinned = false;   // small results use plain host memory (a pinned block is at least 64 MB)
+    ~PinnedBlock() {
+        if (p && pinned) pinned_pool().put(p, cap);
+        else free(p);
+    }
+    void* take(size_t n) {
+        void* r = (uint8_t*)p + used;
+        used += (std::max<size_t>(n, 1) + 63) & ~(size_t)63;
+        return r;
+    }
+};
 struct ArrayPriv {
-    std::vector<void*> owned;
+    std::shared_ptr<PinnedBlock> block;
     std::vector<const void*> buffers;
     std::vector<ArrowArray*> children;
 };
@@ -200,15 +222,19 @@ static void release_array(ArrowArray* a) {
         if (c->release) c->release(c);
         delete c;
     }
-    for (void* m : p->owned) free(m);
     delete p;
     a->release = nullptr;
 }
-static void* host_alloc(ArrayPriv* p, size_t n) {
-    void* m = nullptr;
-    if (posix_memalign(&m, 64, std::max<size_t>(n, 64)) != 0) fail("out of host memory");
-    p->owned.push_back(m);
-    return m;
+static void* host_alloc(ArrayPriv* p, size_t n) { return p->block->take(n); }
+static size_t export_bytes(const Column& c) {   // upper bound of what export_column takes from the block
+    auto al = [](size_t n) { return (std::max<size_t>(n, 1) + 63) & ~(size_t)63; };
+    size_t n = (size_t)c.len, t = 0;
+    if (c.type.id == T_NULL) return 0;
+    if (c.validity) t += al(bitmap_alloc_bytes(c.len) + 8);
+    if (c.type.id == T_BOOL) t += al(bitmap_alloc_bytes(c.len) + 8);
+    else if (c.type.width() > 0) t += al(n * (size_t)c.type.width());
+    else if (c.type.is_varlen()) t += al((n + 1) * 4) + al((size_t)c.data_bytes);
+    return t;
 }
 static int64_t count_nulls(const uint8_t* bits, int64_t n) {
     int64_t set = 0;
@@ -218,8 +244,9 @@ static int64_t count_nulls(const uint8_t* bits, int64_t n) {
     return n - set;
 }
 
-static void export_column(Ctx& ctx, const Column& c, ArrowArray* out) {
+static void export_column(Ctx& ctx, const Column& c, ArrowArray* out, const std::shared_ptr<PinnedBlock>& block) {
     auto* p = new ArrayPriv;
+    p->block = block;
     memset(out, 0, sizeof(*out));
     out->length = c.len;
     out->release = release_array;
@@ -255,8 +282,7 @@ static void export_column(Ctx& ctx, const Column& c, ArrowArray* out) {
     } else {
         fail("export: unsupported type " + c.type.str());
     }
-    ctx.sync();
-    out->null_count = hv ? count_nulls(hv, n) : 0;
+    out->null_count = hv ? -1 : 0;   // counted after the batch's single sync
     out->n_buffers = (int64_t)p->buffers.size();
     out->buffers = p->buffers.data();
 }
@@ -272,10 +298,26 @@ void export_batch(Ctx& ctx, const Batch& b, const Schema& schema, ArrowArray* ou
     p->buffers.push_back(nullptr);
     out->n_buffers = 1;
     out->buffers = p->buffers.data();
+    auto block = std::make_shared<PinnedBlock>();
+    size_t total = 64;
+    for (auto& c : b.cols) total += export_bytes(*c);
+    if (total >= (1u << 20)) {
+        block->p = pinned_pool().get(total, &block->cap);
+        block->pinned = true;
+    } else {
+        if (posix_memalign(&block->p, 64, total) != 0) fail("out of host memory");
+        block->cap = total;
+    }
+    p->block = block;
     for (auto& c : b.cols) {
         auto* ch = new ArrowArray;
-        export_column(ctx, *c, ch);
+        export_column(ctx, *c, ch, block);
         p->children.push_back(ch);
+    }
+    ctx.sync();   // one sync for every buffer of the batch
+    for (size_t i = 0; i < b.cols.size(); i++) {
+        ArrowArray* ch = p->children[i];
+        if (ch->null_count < 0) ch->null_count = count_nulls((const uint8_t*)ch->buffers[0], ch->length);
     }
     out->n_children = (int64_t)p->children.size();
     out->children = p->children.data();
