@@ -679,6 +679,8 @@ struct ParquetScanExec : Operator {
     };
     cudaStream_t copy_stream = nullptr;
     int prefetch_depth = 3;
+    int64_t batches_planned = 0;
+    int64_t ramp_rows = getenv("AURON_SCAN_RAMP_ROWS") ? atoll(getenv("AURON_SCAN_RAMP_ROWS")) : 0;
     std::thread producer;
     std::mutex qmu;
     std::condition_variable qcv;
@@ -724,7 +726,9 @@ struct ParquetScanExec : Operator {
             }
             const auto& rg = cur->meta.row_groups[cur->row_groups[rg_pos]];
             std::string sig = signature(*cur);
-            if (started && (sig != batch_sig || p.rows + rg.num_rows > t.ctx.gpu_chunk_rows)) break;
+            // ramp-up: the first batch is small so that the GPU starts while the remaining page headers are still being parsed
+            const int64_t limit = batches_planned == 0 && ramp_rows > 0 ? std::min(ramp_rows, t.ctx.gpu_chunk_rows) : t.ctx.gpu_chunk_rows;
+            if (started && (sig != batch_sig || p.rows + rg.num_rows > limit)) break;
             if (!started) {
                 started = true;
                 batch_sig = sig;
@@ -754,6 +758,7 @@ struct ParquetScanExec : Operator {
             rg_pos++;
         }
         if (!started) return nullptr;
+        batches_planned++;
         // chunk placement: HBM-resident images in place, host files into one pinned staging buffer + one device buffer
         for (auto& ct : p.tasks) {
             int64_t start = ct.cm->start_offset(), len = ct.cm->total_compressed;
