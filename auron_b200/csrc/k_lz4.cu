@@ -149,6 +149,140 @@ __global__ void __launch_bounds__(128) lz4_assemble_kernel(const Lz4Place* __res
     if ((pl.flags & 2) && lane < 4) d[4 + pl.len + lane] = 0;   // end mark
 }
 
+// ------------------------------------------------------------------------------------------ decompression (IpcReaderExec)
+// One warp per LZ4 block of a frame with independent blocks (what this engine's writer and lz4_flex's FrameEncoder produce):
+// the warp walks the sequences -- token, literal length, literals, offset, match length -- with uniform control flow; literals
+// are cooperative vector copies from the compressed block, matches are served from a shared-memory ring of the last 4 KB of
+// output when they are short and near (the common case in the noisy byte planes), else from the output in global memory
+// (long runs of equal bytes in the high planes: pattern copy, byte i = out[pos - offset + i % offset]).
+// out_sizes[b] = decoded bytes, or -1 for a malformed block.
+constexpr int LZD_RING = 4096;
+__global__ void __launch_bounds__(128) lz4_decompress_blocks_kernel(const Lz4DBlock* __restrict__ blocks, int n_blocks, int32_t* __restrict__ out_sizes) {
+    __shared__ uint8_t s_ring[4][LZD_RING];
+    const int b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= n_blocks) return;
+    const unsigned lane = threadIdx.x & 31;
+    uint8_t* ring = s_ring[threadIdx.x >> 5];
+    const Lz4DBlock blk = blocks[b];
+    const uint8_t* __restrict__ src = blk.src;
+    uint8_t* dst = blk.dst;
+    const int n_in = blk.src_len, cap = blk.dst_cap;
+    if (blk.stored) {
+        if (n_in > cap) {
+            if (lane == 0) out_sizes[b] = -1;
+            return;
+        }
+        warp_copy(dst, src, n_in, lane);
+        if (lane == 0) out_sizes[b] = n_in;
+        return;
+    }
+    int ip = 0, op = 0, ring_from = 0;
+    bool bad = false;
+    while (ip < n_in) {
+        const uint32_t token = src[ip++];
+        int litlen = (int)(token >> 4);
+        if (litlen == 15) {
+            for (;;) {
+                if (ip >= n_in) { bad = true; break; }
+                const uint32_t x = src[ip++];
+                litlen += (int)x;
+                if (x != 255) break;
+            }
+            if (bad) break;
+        }
+        if (litlen > n_in - ip || litlen > cap - op) { bad = true; break; }
+        if (litlen > 0) {
+            if (litlen <= 256) {
+                for (int i = lane; i < litlen; i += 32) {
+                    const uint8_t c = src[ip + i];
+                    dst[op + i] = c;
+                    ring[(op + i) & (LZD_RING - 1)] = c;
+                }
+            } else {
+                warp_copy(dst + op, src + ip, litlen, lane);
+                ring_from = op + litlen;   // the ring does not hold this literal
+            }
+            ip += litlen;
+            op += litlen;
+        }
+        if (ip >= n_in) break;   // the last sequence of a block has no match part
+        if (ip + 2 > n_in) { bad = true; break; }
+        const int off = (int)((uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8));
+        ip += 2;
+        int mlen = (int)(token & 15);
+        if (mlen == 15) {
+            for (;;) {
+                if (ip >= n_in) { bad = true; break; }
+                const uint32_t x = src[ip++];
+                mlen += (int)x;
+                if (x != 255) break;
+            }
+            if (bad) break;
+        }
+        mlen += LZ_MINMATCH;
+        if (off == 0 || off > op || mlen > cap - op) { bad = true; break; }
+        __syncwarp();   // the referenced bytes were written by other lanes
+        const int from = op - off;
+        if (mlen <= 256 && from >= ring_from && off <= LZD_RING - 256) {
+            for (int i = lane; i < mlen; i += 32) {
+                const int k = off >= mlen ? i : (int)((unsigned)i % (unsigned)off);
+                const uint8_t c = ring[(from + k) & (LZD_RING - 1)];
+                dst[op + i] = c;
+                ring[(op + i) & (LZD_RING - 1)] = c;   // never a slot that is still to be read: off + mlen <= LZD_RING
+            }
+        } else if (off >= mlen) {
+            warp_copy(dst + op, dst + from, mlen, lane);   // disjoint ranges
+            ring_from = op + mlen;
+        } else {
+            // overlapping run: every output byte depends only on bytes before `op`
+            if (off >= 4 && mlen >= 256) {
+                // period >= 4: replicate 4-byte words; lane handles words w = lane, lane + 32, ... of the run
+                for (int i = lane * 4; i < mlen; i += 128) {
+                    uint32_t v = 0;
+                    const int m4 = min(4, mlen - i);
+                    for (int t = 0; t < m4; t++) v |= (uint32_t)dst[from + (int)((unsigned)(i + t) % (unsigned)off)] << (8 * t);
+                    for (int t = 0; t < m4; t++) dst[op + i + t] = (uint8_t)(v >> (8 * t));
+                }
+            } else if (off < 4 && mlen >= 64) {
+                // tiny period (runs of one byte value dominate the high planes): build the 4-byte pattern word once, store words
+                uint32_t pat = 0;
+                for (int t = 0; t < 4; t++) pat |= (uint32_t)dst[from + (t % off)] << (8 * t);
+                // output byte j (absolute op + j) = pattern byte j % off; rotate the word so that aligned stores line up
+                const int head = (int)((4 - ((uintptr_t)(dst + op) & 3)) & 3);
+                for (int i = lane; i < min(head, mlen); i += 32) dst[op + i] = dst[from + (i % off)];
+                const int body = (mlen - head) >> 2;
+                uint32_t w = 0;
+                for (int t = 0; t < 4; t++) w |= (uint32_t)((pat >> (8 * ((head + t) % off))) & 0xff) << (8 * t);
+                // with off in {1, 2} every word of the body is identical; off == 3 has period 3 words
+                uint32_t* dw = (uint32_t*)(dst + op + head);
+                if (off == 3) {
+                    for (int q = lane; q < body; q += 32) {
+                        uint32_t x = 0;
+                        for (int t = 0; t < 4; t++) x |= (uint32_t)((pat >> (8 * ((head + 4 * q + t) % 3))) & 0xff) << (8 * t);
+                        dw[q] = x;
+                    }
+                } else {
+                    for (int q = lane; q < body; q += 32) dw[q] = w;
+                }
+                for (int i = head + 4 * body + lane; i < mlen; i += 32) dst[op + i] = dst[from + (i % off)];
+            } else {
+                for (int i = lane; i < mlen; i += 32) dst[op + i] = dst[from + (int)((unsigned)i % (unsigned)off)];
+            }
+            ring_from = op + mlen;
+        }
+        op += mlen;
+        __syncwarp();
+    }
+    if (lane == 0) out_sizes[b] = bad ? -1 : op;
+}
+
+void lz4_decompress_blocks(Ctx& ctx, const Lz4DBlock* dev_blocks, int n_blocks, int32_t* dev_sizes) {
+    if (n_blocks <= 0) return;
+    ProfScope ps(ctx, "lz4_decompress");
+    lz4_decompress_blocks_kernel<<<(n_blocks + 3) / 4, 128, 0, ctx.stream>>>(dev_blocks, n_blocks, dev_sizes);
+    LAUNCH_CHECK(ctx);
+}
+
 void lz4_compress_blocks(Ctx& ctx, const Lz4Block* dev_blocks, int n_blocks, int32_t* dev_sizes) {
     if (n_blocks <= 0) return;
     ProfScope ps(ctx, "lz4_compress");

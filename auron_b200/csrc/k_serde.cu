@@ -395,6 +395,83 @@ __global__ void __launch_bounds__(128) deser_bytes_kernel(const uint8_t* __restr
     warp_copy(out + cp.dst, payload + cp.src, cp.len, threadIdx.x & 31);
 }
 
+// Layout walk on the device (used when the payload was decompressed on the GPU and never visits the host): one warp per codec
+// stream parses its batches -- varint row count, per column the has_nulls varint and the section sizes, string byte totals by a
+// warp reduction over the four length planes.  Pass 1 (segs == nullptr) counts batches, pass 2 fills one DeserSeg per (batch,
+// column) with out_row0 = 0 (the host adds the row offsets) and the string byte totals.  flags[stream] != 0: malformed payload
+// or a batch that continues in the next stream (the host-side walk handles that case).
+__global__ void __launch_bounds__(128) deser_layout_kernel(const uint8_t* __restrict__ payload, const LayoutStream* __restrict__ streams, int n_streams,
+                                                           LayoutSchema sch, const int32_t* __restrict__ seg_base, DeserSeg* __restrict__ segs,
+                                                           int64_t* __restrict__ sbytes, int64_t* __restrict__ batch_rows, int32_t* __restrict__ counts,
+                                                           int32_t* __restrict__ flags) {
+    const int si = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (si >= n_streams) return;
+    const unsigned lane = threadIdx.x & 31;
+    const int64_t end = streams[si].end;
+    int64_t pos = streams[si].begin;
+    int nb = 0;
+    bool bad = false;
+    auto varint = [&](uint64_t* v) {
+        uint64_t x = 0;
+        for (int shift = 0; shift < 64; shift += 7) {
+            if (pos >= end) return false;
+            const uint8_t b = payload[pos++];
+            x |= (uint64_t)(b & 0x7f) << shift;
+            if (!(b & 0x80)) {
+                *v = x;
+                return true;
+            }
+        }
+        return false;
+    };
+    while (pos < end && !bad) {
+        uint64_t n64;
+        if (!varint(&n64) || n64 > 0x7fffffffull) { bad = true; break; }
+        const int64_t n = (int64_t)n64;
+        const int64_t slot = segs ? (int64_t)seg_base[si] + nb : 0;
+        if (segs && lane == 0) batch_rows[slot] = n;
+        for (int c = 0; c < sch.ncols && !bad; c++) {
+            const int kind = sch.kind[c];
+            if (kind == 0) continue;
+            uint64_t hn;
+            if (!varint(&hn)) { bad = true; break; }
+            DeserSeg sg{-1, 0, 0, n};
+            if (hn) {
+                sg.validity_off = pos;
+                pos += (n + 7) / 8;
+            }
+            sg.values_off = pos;
+            int64_t sum = 0;
+            if (kind == 1) pos += (n + 7) / 8;
+            else if (kind == 2) pos += (int64_t)sch.width[c] * n;
+            else {
+                if (pos + 4 * n > end) { bad = true; break; }
+                const uint8_t* p0 = payload + pos;
+                for (int64_t i = lane; i < n; i += 32) sum += (int64_t)((uint32_t)p0[i] | ((uint32_t)p0[n + i] << 8) | ((uint32_t)p0[2 * n + i] << 16) | ((uint32_t)p0[3 * n + i] << 24));
+                for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(FULL_MASK, sum, d);
+                pos += 4 * n + sum;
+            }
+            if (pos > end) { bad = true; break; }
+            if (segs && lane == 0) {
+                segs[slot * sch.ncols + c] = sg;
+                sbytes[slot * sch.ncols + c] = sum;
+            }
+        }
+        nb++;
+    }
+    if (lane == 0) {
+        counts[si] = nb;
+        flags[si] = bad ? 1 : 0;
+    }
+}
+void deserialize_layout(Ctx& ctx, const uint8_t* dev_payload, const LayoutStream* dev_streams, int n_streams, const LayoutSchema& sch, const int32_t* dev_seg_base,
+                        DeserSeg* dev_segs, int64_t* dev_sbytes, int64_t* dev_batch_rows, int32_t* dev_counts, int32_t* dev_flags) {
+    if (n_streams <= 0) return;
+    deser_layout_kernel<<<(n_streams + 3) / 4, 128, 0, ctx.stream>>>(dev_payload, dev_streams, n_streams, sch, dev_seg_base, dev_segs, dev_sbytes, dev_batch_rows,
+                                                                     dev_counts, dev_flags);
+    LAUNCH_CHECK(ctx);
+}
+
 ColumnPtr deserialize_column(Ctx& ctx, const DType& type, const uint8_t* dev_payload, const std::vector<DeserSeg>& segs, int64_t total_rows,
                              const std::vector<DeserCopy>& byte_copies, int64_t total_bytes) {
     auto col = std::make_shared<Column>();

@@ -144,6 +144,14 @@ constexpr int kLz4BlockBytes = 64 * 1024;
 inline int64_t lz4_block_bound(int64_t n) { return n + n / 255 + 32; }
 void lz4_compress_blocks(Ctx& ctx, const Lz4Block* dev_blocks, int n_blocks, int32_t* dev_sizes);
 void lz4_assemble(Ctx& ctx, const Lz4Place* dev_places, int n);
+struct Lz4DBlock {          // one block of an LZ4 frame to decode (IpcReaderExec)
+    const uint8_t* src;     // block data (after its 4-byte size word)
+    uint8_t* dst;           // slot of dst_cap bytes in the payload buffer
+    int32_t src_len, dst_cap;
+    int32_t stored;         // 1 = the block is stored uncompressed
+    int32_t pad;
+};
+void lz4_decompress_blocks(Ctx& ctx, const Lz4DBlock* dev_blocks, int n_blocks, int32_t* dev_sizes);   // sizes: decoded bytes, -1 = malformed
 
 // read side (IpcReaderExec): one DeserSeg per batch of the column, offsets into the decompressed payload on the device
 struct DeserSeg {
@@ -155,6 +163,17 @@ struct DeserSeg {
 struct DeserCopy {          // utf8 payload bytes of one batch (or a piece of it)
     int64_t src, dst, len;
 };
+// device-side layout walk (payload decompressed on the GPU)
+struct LayoutStream {
+    int64_t begin, end;     // byte range of one codec stream's payload
+};
+struct LayoutSchema {
+    int32_t ncols;
+    uint8_t kind[64];       // 0 null, 1 bool, 2 fixed width, 3 utf8 / binary
+    uint8_t width[64];
+};
+void deserialize_layout(Ctx& ctx, const uint8_t* dev_payload, const LayoutStream* dev_streams, int n_streams, const LayoutSchema& sch, const int32_t* dev_seg_base,
+                        DeserSeg* dev_segs, int64_t* dev_sbytes, int64_t* dev_batch_rows, int32_t* dev_counts, int32_t* dev_flags);
 ColumnPtr deserialize_column(Ctx& ctx, const DType& type, const uint8_t* dev_payload, const std::vector<DeserSeg>& segs, int64_t total_rows,
                              const std::vector<DeserCopy>& byte_copies, int64_t total_bytes);
 

@@ -250,6 +250,147 @@ struct IpcReaderExec : Operator {
         return true;
     }
 
+    struct StreamRef {
+        const uint8_t* p;
+        size_t n;
+    };
+    // GPU path: every codec stream is an LZ4 frame with independent blocks -> upload the COMPRESSED bytes, decode the blocks,
+    // walk the layout and rebuild the columns on the device; the payload never visits the host.  Returns nullptr when the chunk
+    // does not qualify (ZSTD, linked blocks, dictionaries, blocks that are not filled to the block size, batches that continue
+    // in the next stream): the host path then handles it.
+    BatchPtr try_device_decode(Task& t, const std::vector<StreamRef>& streams, const uint8_t* cbuf, size_t cbuf_bytes) {
+        if (streams.empty() || getenv("AURON_HOST_LZ4_DECODE")) return nullptr;
+        const int ncols = (int)out_schema.fields.size();
+        if (ncols > 64) return nullptr;
+        struct Frame {
+            size_t first;
+            int nblocks;
+            int64_t block_max;
+        };
+        std::vector<Frame> frames;
+        std::vector<Lz4DBlock> blocks;
+        static const int64_t kMax[8] = {0, 0, 0, 0, 64 << 10, 256 << 10, 1 << 20, 4 << 20};
+        for (auto& st : streams) {
+            const uint8_t* in = st.p;
+            const size_t n = st.n;
+            if (n < 11) return nullptr;
+            uint32_t magic;
+            memcpy(&magic, in, 4);
+            if (magic != 0x184D2204u) return nullptr;
+            const uint8_t flg = in[4], bd = in[5];
+            if ((flg >> 6) != 1 || !(flg & 0x20) || (flg & 0x01)) return nullptr;   // version 1, independent blocks, no dictionary
+            const int64_t block_max = kMax[(bd >> 4) & 7];
+            if (!block_max) return nullptr;
+            size_t pos = 6 + ((flg & 0x08) ? 8 : 0) + 1;
+            Frame f{blocks.size(), 0, block_max};
+            for (;;) {
+                if (pos + 4 > n) return nullptr;
+                uint32_t w;
+                memcpy(&w, in + pos, 4);
+                pos += 4;
+                if (w == 0) break;
+                const uint32_t len = w & 0x7fffffffu;
+                if (pos + len + ((flg & 0x10) ? 4 : 0) > n || (int64_t)len > block_max + 64) return nullptr;
+                blocks.push_back(Lz4DBlock{in + pos, nullptr, (int32_t)len, (int32_t)block_max, (w >> 31) ? 1 : 0, 0});
+                pos += len + ((flg & 0x10) ? 4 : 0);
+                f.nblocks++;
+            }
+            frames.push_back(f);
+        }
+        const size_t ns = streams.size();
+        std::vector<int64_t> slot(ns + 1, 0);
+        for (size_t i = 0; i < ns; i++) slot[i + 1] = slot[i] + (((int64_t)frames[i].nblocks * frames[i].block_max + 63) & ~(int64_t)63);
+        if (slot[ns] > (24ll << 30) || blocks.empty()) return nullptr;
+        Ctx& ctx = t.ctx;
+        OpTimer tdev(metrics, "device_ns");
+        Buf dcomp = dalloc(ctx, cbuf_bytes + 64);
+        CUDA_OK(cudaMemcpyAsync(dcomp->ptr, cbuf, cbuf_bytes, cudaMemcpyHostToDevice, ctx.stream));
+        Buf dpayload = dalloc(ctx, (size_t)slot[ns] + 64);
+        for (size_t i = 0; i < ns; i++)
+            for (int j = 0; j < frames[i].nblocks; j++) {
+                Lz4DBlock& b = blocks[frames[i].first + (size_t)j];
+                b.src = P<uint8_t>(dcomp) + (b.src - cbuf);
+                b.dst = P<uint8_t>(dpayload) + slot[i] + (int64_t)j * frames[i].block_max;
+            }
+        Buf dblocks = to_device(ctx, blocks.data(), blocks.size() * sizeof(Lz4DBlock));
+        Buf dsizes = dalloc(ctx, blocks.size() * 4);
+        lz4_decompress_blocks(ctx, P<Lz4DBlock>(dblocks), (int)blocks.size(), P<int32_t>(dsizes));
+        std::vector<int32_t> sizes(blocks.size());
+        to_host(ctx, sizes.data(), dsizes->ptr, sizes.size() * 4);
+        std::vector<LayoutStream> lstreams(ns);
+        int64_t payload_bytes = 0;
+        for (size_t i = 0; i < ns; i++) {
+            int64_t sz = 0;
+            for (int j = 0; j < frames[i].nblocks; j++) {
+                const int32_t bs = sizes[frames[i].first + (size_t)j];
+                AURON_CHECK(bs >= 0, "shuffle read: corrupt LZ4 block");
+                if (j + 1 < frames[i].nblocks && bs != frames[i].block_max) return nullptr;   // a flushed (partial) block in the middle
+                sz += bs;
+            }
+            lstreams[i] = LayoutStream{slot[i], slot[i] + sz};
+            payload_bytes += sz;
+        }
+        // layout: count, then fill
+        LayoutSchema sch;
+        memset(&sch, 0, sizeof(sch));
+        sch.ncols = ncols;
+        for (int c = 0; c < ncols; c++) {
+            const DType& ty = out_schema.fields[(size_t)c].type;
+            sch.kind[c] = ty.id == T_NULL ? 0 : ty.id == T_BOOL ? 1 : ty.is_varlen() ? 3 : 2;
+            sch.width[c] = (uint8_t)(sch.kind[c] == 2 ? ty.width() : 0);
+        }
+        Buf dstreams = to_device(ctx, lstreams.data(), ns * sizeof(LayoutStream));
+        Buf dcounts = dalloc(ctx, ns * 4), dflags = dalloc(ctx, ns * 4);
+        deserialize_layout(ctx, P<uint8_t>(dpayload), P<LayoutStream>(dstreams), (int)ns, sch, nullptr, nullptr, nullptr, nullptr, P<int32_t>(dcounts), P<int32_t>(dflags));
+        std::vector<int32_t> counts(ns), flags(ns);
+        to_host(ctx, counts.data(), dcounts->ptr, ns * 4);
+        to_host(ctx, flags.data(), dflags->ptr, ns * 4);
+        std::vector<int32_t> seg_base(ns + 1, 0);
+        for (size_t i = 0; i < ns; i++) {
+            if (flags[i]) return nullptr;   // malformed, or a batch that continues in the next stream: the host walk decides
+            seg_base[i + 1] = seg_base[i] + counts[i];
+        }
+        const size_t nbatches = (size_t)seg_base[ns];
+        std::vector<DeserSeg> hsegs(nbatches * (size_t)ncols);
+        std::vector<int64_t> hbytes(nbatches * (size_t)ncols), hrows(nbatches);
+        if (nbatches) {
+            Buf dbase = to_device(ctx, seg_base.data(), seg_base.size() * 4);
+            Buf dsegs = dalloc_zero(ctx, hsegs.size() * sizeof(DeserSeg)), dbytes = dalloc_zero(ctx, hbytes.size() * 8), drows = dalloc_zero(ctx, nbatches * 8);
+            deserialize_layout(ctx, P<uint8_t>(dpayload), P<LayoutStream>(dstreams), (int)ns, sch, P<int32_t>(dbase), P<DeserSeg>(dsegs), P<int64_t>(dbytes), P<int64_t>(drows),
+                               P<int32_t>(dcounts), P<int32_t>(dflags));
+            to_host(ctx, hsegs.data(), dsegs->ptr, hsegs.size() * sizeof(DeserSeg));
+            to_host(ctx, hbytes.data(), dbytes->ptr, hbytes.size() * 8);
+            to_host(ctx, hrows.data(), drows->ptr, nbatches * 8);
+        }
+        std::vector<std::vector<DeserSeg>> segs((size_t)ncols);
+        std::vector<std::vector<DeserCopy>> copies((size_t)ncols);
+        std::vector<int64_t> col_bytes((size_t)ncols, 0);
+        int64_t rows = 0;
+        for (size_t bi = 0; bi < nbatches; bi++) {
+            for (int c = 0; c < ncols; c++) {
+                if (sch.kind[c] == 0) continue;
+                DeserSeg sg = hsegs[bi * (size_t)ncols + (size_t)c];
+                sg.out_row0 = rows;
+                segs[(size_t)c].push_back(sg);
+                if (sch.kind[c] == 3) {
+                    const int64_t sum = hbytes[bi * (size_t)ncols + (size_t)c], at = sg.values_off + 4 * sg.n;
+                    for (int64_t o = 0; o < sum; o += 1 << 20) copies[(size_t)c].push_back(DeserCopy{at + o, col_bytes[(size_t)c] + o, std::min<int64_t>(1 << 20, sum - o)});
+                    col_bytes[(size_t)c] += sum;
+                }
+            }
+            rows += hrows[bi];
+            AURON_CHECK(rows < (int64_t)INT32_MAX, "shuffle read: chunk too large");
+        }
+        metrics.add("size", payload_bytes);
+        auto out = std::make_shared<Batch>();
+        out->num_rows = rows;
+        for (int c = 0; c < ncols; c++)
+            out->cols.push_back(deserialize_column(ctx, out_schema.fields[(size_t)c].type, P<uint8_t>(dpayload), segs[(size_t)c], rows, copies[(size_t)c], col_bytes[(size_t)c]));
+        ctx.sync();   // dcomp / dpayload are released when this function returns
+        metrics.add("output_rows", rows);
+        return out;
+    }
+
     BatchPtr next(Task& t) override {
         if (done) return nullptr;
         OpTimer timer(metrics, "elapsed_ns");
@@ -271,10 +412,7 @@ struct IpcReaderExec : Operator {
         }
         if (blocks.empty()) return nullptr;
         // ---- 2. bytes of every block -> one pinned buffer (recycled: no page faults, no frees), split into codec streams
-        struct Stream {
-            const uint8_t* p;
-            size_t n;
-        };
+        using Stream = StreamRef;
         std::vector<Stream> streams;
         std::vector<int64_t> boff(blocks.size() + 1, 0);
         for (size_t i = 0; i < blocks.size(); i++) boff[i + 1] = boff[i] + ((blocks[i].length + 63) & ~(int64_t)63);
@@ -322,6 +460,7 @@ struct IpcReaderExec : Operator {
                 }
             }
         }
+        if (BatchPtr dev = try_device_decode(t, streams, cbuf, (size_t)boff.back())) return dev;
         // ---- 3. decompress on the worker pool, straight into ONE pinned payload buffer: every stream gets a slot sized by
         // its decoded-size bound (LZ4 frames: blocks x block size; ZSTD: the frame's content size); streams that do not
         // announce a size are decoded into vectors first.  (Decoding into fresh vectors and concatenating cost 540 of

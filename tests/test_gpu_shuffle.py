@@ -256,3 +256,26 @@ def test_shuffle_write_then_read_two_stage_aggregate(tmp_path, codec, monkeypatc
     assert_same_rows(got, exp)
     keys = [f.column(0).to_pylist() for f in finals]
     assert sum(len(k) for k in keys) == len(set(x for k in keys for x in k))       # a key lives in exactly one partition
+
+
+@pytest.mark.parametrize("decode", ["device", "host"])
+def test_ipc_reader_round_trip_all_types(tmp_path, decode, monkeypatch):
+    # ShuffleWriterExec's LZ4 frames (independent 64 KB blocks) are decoded on the GPU, layout walk included; AURON_HOST_LZ4_DECODE=1
+    # sends the same bytes through liblz4 and the host-side walk.  Every column type of the format, several chunks per partition.
+    if decode == "host":
+        monkeypatch.setenv("AURON_HOST_LZ4_DECODE", "1")
+    n, nparts = 150_000, 4
+    t = _table(n, seed=31)
+    data, index = str(tmp_path / "rt.data"), str(tmp_path / "rt.index")
+    run(P.shuffle_writer(P.ffi_reader(t.schema, "t"), P.hash_repartition([P.col("k")], nparts), data, index), {"t": t}, chunk=40_000)
+    offsets = struct.unpack(f"<{nparts + 1}q", open(index, "rb").read())
+    pid = oracle.partition_ids([t["k"].combine_chunks()], nparts)
+    td = P.task_definition(P.ipc_reader(t.schema, "in"))
+    for p in range(nparts):
+        got = runtime.run_task(td, shuffle_blocks={"in": [(data, offsets[p], offsets[p + 1] - offsets[p])]})
+        assert_same_rows(got, t.filter(pa.array(pid == p)))
+    # all partitions through one reader, mixed block shapes (file segments and an in-memory copy)
+    raw = open(data, "rb").read()
+    blocks = [(data, offsets[0], offsets[1] - offsets[0]), raw[offsets[1]:offsets[2]], (data, offsets[2], offsets[4] - offsets[2])]
+    got = runtime.run_task(td, shuffle_blocks={"in": blocks})
+    assert_same_rows(got, t)
