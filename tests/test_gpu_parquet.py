@@ -190,24 +190,31 @@ def test_scan_reports_corrupt_snappy_page(tmp_path):
         _scan(path, t.schema)
 
 
-def test_aggregate_survives_wrong_column_statistics(tmp_path):
+@pytest.mark.parametrize("lie", ["key_max", "value_max"])
+def test_aggregate_survives_wrong_column_statistics(tmp_path, lie):
     # the scan hands the chunk statistics (min / max) to the aggregate's direct-address path; a file whose statistics do not
     # cover its data (buggy writer) must still aggregate correctly (the kernel flags the out-of-range key, the hash table takes over)
     rng = np.random.default_rng(3)
     n = 100_000
     k = rng.integers(1000, 2000, n).astype(np.int32)
     k[:10] = [1000, 1999] * 5                                  # make sure both bounds occur
-    t = pa.table({"k": pa.array(k), "v": pa.array(rng.integers(0, 100, n), type=pa.int64())})
+    v = rng.integers(0, 100, n)
+    v[:4] = [0, 99, 99, 0]
+    t = pa.table({"k": pa.array(k), "v": pa.array(v, type=pa.int64())})
     path = str(tmp_path / "stats.parquet")
     pq.write_table(t, path, compression="NONE", use_dictionary=False)
     raw = bytearray(open(path, "rb").read())
     md = pq.ParquetFile(path).metadata
     footer_len = int.from_bytes(raw[-8:-4], "little")
     foot = len(raw) - 8 - footer_len
-    patched = raw[:foot] + raw[foot:].replace((1999).to_bytes(4, "little"), (1500).to_bytes(4, "little"))
+    if lie == "key_max":
+        patched = raw[:foot] + raw[foot:].replace((1999).to_bytes(4, "little"), (1500).to_bytes(4, "little"))
+    else:
+        patched = raw[:foot] + raw[foot:].replace((99).to_bytes(8, "little"), (50).to_bytes(8, "little"))
     assert patched != raw and len(patched) == len(raw)
     open(path, "wb").write(bytes(patched))
-    assert pq.ParquetFile(path).metadata.row_group(0).column(0).statistics.max == 1500
+    st = pq.ParquetFile(path).metadata.row_group(0)
+    assert (st.column(0).statistics.max, st.column(1).statistics.max) == ((1500, 99) if lie == "key_max" else (1999, 50))
     scan = P.parquet_scan(t.schema, [(path, os.path.getsize(path))], [0, 1])
     plan = P.agg(scan, [P.col("k")], ["k"], [P.agg_expr("SUM", [P.col("v")], pa.int64()), P.agg_expr("COUNT", [P.col("v")], pa.int64())], ["s", "c"], ["PARTIAL"] * 2)
     got = run(plan, {})
