@@ -279,3 +279,25 @@ def test_ipc_reader_round_trip_all_types(tmp_path, decode, monkeypatch):
     blocks = [(data, offsets[0], offsets[1] - offsets[0]), raw[offsets[1]:offsets[2]], (data, offsets[2], offsets[4] - offsets[2])]
     got = runtime.run_task(td, shuffle_blocks={"in": blocks})
     assert_same_rows(got, t)
+
+
+def test_partitioning_goldens_from_the_reference(tmp_path):
+    # shuffle/buffered_data.rs:396-542: round-robin(4) starting at 3, range partitioning with one-key bounds [11, 14, 17] and
+    # two-key bounds [(11, 1), (14, 3), (17, 5)] over the same 10-row table; rows inside a partition are unordered (radix sort)
+    t = pa.table({"a": pa.array([19, 18, 17, 16, 15, 14, 13, 12, 11, 10], type=pa.int32()),
+                  "b": pa.array([0, 1, 2, 3, 4, 5, 6, 7, 8, 9], type=pa.int32()),
+                  "c": pa.array([5, 6, 7, 8, 9, 0, 1, 2, 3, 4], type=pa.int32())})
+    data, index = str(tmp_path / "g.data"), str(tmp_path / "g.index")
+
+    def parts_of(repartition, partition_id=0):
+        td = P.task_definition(P.shuffle_writer(P.ffi_reader(t.schema, "t"), repartition, data, index), stage_id=0, partition_id=partition_id, task_id=1)
+        runtime.run_task(td, {"t": t.to_batches()})
+        parts, _ = read_shuffle_files(data, index, t.schema)
+        return [sorted(p["a"].to_pylist()) for p in parts]
+
+    # start = (partition_id * 1000193 + rows so far) % 4 = 3 for partition_id 3 (the reference test passes current_num_rows = 3)
+    assert parts_of(P.round_robin_repartition(4), partition_id=3) == [[10, 14, 18], [13, 17], [12, 16], [11, 15, 19]]
+    asc = lambda c: P.sort_expr(P.col(c), True, True)
+    assert parts_of(P.range_repartition([asc("a")], 4, [([11, 14, 17], pa.int32())])) == [[10, 11], [12, 13, 14], [15, 16, 17], [18, 19]]
+    assert parts_of(P.range_repartition([asc("a"), asc("b")], 4, [([11, 14, 17], pa.int32()), ([1, 3, 5], pa.int32())])) == [
+        [10], [11, 12, 13], [14, 15, 16, 17], [18, 19]]
