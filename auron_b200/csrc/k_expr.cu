@@ -308,6 +308,71 @@ __device__ inline bool str_like(const uint8_t* s, int32_t ls, const uint8_t* p, 
     return pi == lp;
 }
 // Spark to_integer (cast.rs:394-468)
+// utf8 -> decimal128(prec, scale): cast.rs:223-225 (scientific notation is rewritten to a plain decimal string first,
+// cast.rs:328-351) followed by arrow's string -> decimal parser: [+-] digits [. digits] [e[+-]digits]; fraction digits beyond the
+// scale are dropped (no rounding), no surrounding whitespace, anything else or more than `prec` digits -> NULL.
+// Golden vectors: cast.rs:629-658.
+__device__ inline bool str_to_decimal(const uint8_t* s, int32_t len, int prec, int scale, i128* out) {
+    int32_t i = 0;
+    bool neg = false;
+    if (len > 0 && (s[0] == '-' || s[0] == '+')) {
+        neg = s[0] == '-';
+        i = 1;
+    }
+    if (i >= len) return false;
+    // pass 1: structure
+    int32_t dig0 = i, ni = 0, nf = 0, dot = -1, epos = -1;
+    for (; i < len; i++) {
+        const uint8_t c = s[i];
+        if (c >= '0' && c <= '9') {
+            if (dot < 0) ni++;
+            else nf++;
+        } else if (c == '.' && dot < 0) dot = i;
+        else if (c == 'e' || c == 'E') {
+            epos = i;
+            break;
+        } else return false;
+    }
+    if (ni + nf == 0) return false;
+    int64_t E = 0;
+    if (epos >= 0) {
+        int32_t j = epos + 1;
+        bool eneg = false;
+        if (j < len && (s[j] == '-' || s[j] == '+')) {
+            eneg = s[j] == '-';
+            j++;
+        }
+        if (j >= len) return false;
+        for (; j < len; j++) {
+            if (s[j] < '0' || s[j] > '9') return false;
+            E = E * 10 + (s[j] - '0');
+            if (E > 100000) return false;
+        }
+        if (eneg) E = -E;
+    }
+    // value = D x 10^(E - nf), D = all mantissa digits; unscaled result = trunc(D x 10^shift)
+    const int64_t shift = E - nf + scale;
+    int64_t keep = (int64_t)ni + nf + (shift < 0 ? shift : 0);   // mantissa digits that survive the truncation
+    const int32_t dend = epos >= 0 ? epos : len;
+    i128 acc = {0, 0};
+    int sig = 0;   // digits accumulated after the first non-zero one
+    for (int32_t j = dig0; j < dend && keep > 0; j++) {
+        const uint8_t c = s[j];
+        if (c == '.') continue;
+        keep--;
+        if (sig == 0 && c == '0') continue;
+        if (++sig > 38) return false;
+        if (!u128_mul_pow10(acc, 1, &acc)) return false;
+        acc = i128_add(acc, {(uint64_t)(c - '0'), 0});
+    }
+    if (shift > 0 && sig > 0) {
+        if (shift + sig > 38) return false;
+        if (!u128_mul_pow10(acc, (int)shift, &acc)) return false;
+    }
+    if (!dec_fits_precision(acc, prec)) return false;
+    *out = neg ? i128_neg(acc) : acc;
+    return true;
+}
 __device__ inline bool str_to_int(const uint8_t* s, int32_t len, int t, int64_t* out) {
     if (len == 0) return false;
     int bits = t == VT_I8 ? 8 : t == VT_I16 ? 16 : t == VT_I32 ? 32 : 64;
@@ -497,6 +562,13 @@ __device__ inline bool vm_cast(const VmParams& p, int st, int dt, int sscale, in
             }
             if (!str_to_int(s, len, dt, &r)) return false;
             lo = (uint64_t)r;
+            return true;
+        }
+        if (dt == VT_DEC) {
+            i128 r;
+            if (!str_to_decimal(s, len, dprec, dscale, &r)) return false;
+            lo = r.lo;
+            hi = r.hi;
             return true;
         }
         return false;
@@ -1488,7 +1560,7 @@ struct Compiler {
         if (st <= VT_I64 && dt != VT_STR) ok = true;
         if ((st == VT_F32 || st == VT_F64) && dt != VT_STR) ok = true;
         if (st == VT_DEC && dt != VT_STR && dt != VT_BOOL) ok = true;
-        if (st == VT_STR && ((dt >= VT_I8 && dt <= VT_I64 && to.is_integer()) || date_target)) ok = true;
+        if (st == VT_STR && ((dt >= VT_I8 && dt <= VT_I64 && to.is_integer()) || date_target || dt == VT_DEC)) ok = true;
         if (st == VT_STR && dt == VT_STR) return {v.reg, to};
         // same physical representation (date32 <-> int32 etc.) are not native casts in the reference
         if ((v.type.id == T_DATE32 || to.id == T_DATE32 || v.type.id == T_TIMESTAMP || to.id == T_TIMESTAMP || v.type.id == T_DATE64 || to.id == T_DATE64) &&

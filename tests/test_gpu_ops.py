@@ -242,6 +242,25 @@ def test_casts_golden():
     assert got["f"].to_pylist() == [None, 123.456, -0.005, 99999.995, -7.5]
 
 
+def test_cast_string_to_decimal_golden():
+    # datafusion-ext-commons/src/arrow/cast.rs:629-658 (scientific notation is rewritten to plain digits first, :328-351)
+    g = pa.table({"s": pa.array([None, "1e-8", "1.012345678911111111e10", "1.42e-6", "0.00000142", "123.456", "987.654",
+                                 "123456789012345.678901234567890", "-123456789012345.678901234567890"])})
+    got = _eval(g, [P.try_cast(P.col("s"), pa.decimal128(38, 18))], ["d"], [pa.decimal128(38, 18)])
+    with decimal.localcontext() as ctx:
+        ctx.prec = 60                                    # the default 28 digits would round the 33-digit values
+        unscaled = [None if v is None else int(v.scaleb(18)) for v in got["d"].to_pylist()]
+    assert unscaled == [
+        None, 10000000000, 10123456789111111110000000000, 1420000000000, 1420000000000, 123456000000000000000, 987654000000000000000,
+        123456789012345678901234567890000, -123456789012345678901234567890000]
+    # arrow's parser behind it: fraction digits past the scale are dropped, too many digits / malformed input -> NULL, no trimming
+    e = pa.table({"s": pa.array(["987.6549999", "-0.019", "+5", ".5", "1.", "12345.67", "123456.7", "", ".", "-", "1e", "1e+2", "12x", " 1", "0.000000", "1E2"])})
+    got = _eval(e, [P.try_cast(P.col("s"), pa.decimal128(7, 2))], ["d"], [pa.decimal128(7, 2)])
+    D = decimal.Decimal
+    assert got["d"].to_pylist() == [D("987.65"), D("-0.01"), D("5.00"), D("0.50"), D("1.00"), D("12345.67"), None, None, None, None, None, D("100.00"), None, None,
+                                    D("0.00"), D("100.00")]
+
+
 def test_casts_to_string_golden_and_vs_arrow():
     # cast.rs:536-552 (bool -> "true"/"false"), cast.rs:660-690 (decimal -> plain string with `scale` fraction digits); integers and
     # dates go through arrow's cast in the reference: compared with Arrow C++ here
