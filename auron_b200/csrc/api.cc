@@ -122,6 +122,20 @@ int auron_b200_metrics(auron_task* task, auron_metric_fn fn, void* user) {
     API_GUARD_END(-1)
 }
 
+static void walk_metric_nodes(Operator& op, int depth, int child_index, auron_metric_node_fn enter, auron_metric_fn fn, void* user) {
+    enter(user, depth, child_index, op.name.c_str());
+    for (auto& kv : op.metrics.values) fn(user, depth, op.name.c_str(), kv.first.c_str(), kv.second);
+    int i = 0;
+    for (auto& c : op.children) walk_metric_nodes(*c, depth + 1, i++, enter, fn, user);
+}
+int auron_b200_metrics_walk(auron_task* task, auron_metric_node_fn enter, auron_metric_fn fn, void* user) {
+    API_GUARD_BEGIN
+    AURON_CHECK(task && task->task && task->task->root && enter && fn, "null task or callback");
+    walk_metric_nodes(*task->task->root, 0, 0, enter, fn, user);
+    return 0;
+    API_GUARD_END(-1)
+}
+
 // ---- device residency
 static std::map<int, std::unique_ptr<Ctx>>& util_ctxs() {
     static std::map<int, std::unique_ptr<Ctx>> m;

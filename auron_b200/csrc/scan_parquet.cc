@@ -814,14 +814,16 @@ struct ParquetScanExec : Operator {
                 int64_t off, len;
             };
             std::vector<Slice> slices;
-            const int64_t kSlice = via_callback ? INT64_MAX : (4 << 20);
+            // a host runtime that cannot take upcalls from other threads gets one read per chunk on the task thread
+            const bool serial_cb = via_callback && !t.cb->upcalls_from_any_thread;
+            const int64_t kSlice = serial_cb ? INT64_MAX : (4 << 20);
             if (p.stage_bytes > 0)
                 for (auto& ct : p.tasks) {
                     if (ct.dev_off < 0 || ct.stage_off < 0) continue;
                     for (int64_t o = 0; o < ct.cm->total_compressed; o += std::min(kSlice, ct.cm->total_compressed - o))
                         slices.push_back(Slice{&ct, o, std::min(kSlice, ct.cm->total_compressed - o)});
                 }
-            parallel_for(slices.size(), via_callback ? 1 : host_threads, [&](size_t i) {
+            parallel_for(slices.size(), serial_cb ? 1 : host_threads, [&](size_t i) {
                 const Slice& sl = slices[i];
                 ChunkTask& ct = *sl.ct;
                 int64_t start = ct.cm->start_offset() + sl.off, len = sl.len;
@@ -909,8 +911,8 @@ struct ParquetScanExec : Operator {
 
     // next planned + fetched + parsed batch, or nullptr at the end of the scan
     std::unique_ptr<Prepared> take_ready(Task& t) {
-        const bool via_callback = t.cb && t.cb->read_fully;
-        if (via_callback || prefetch_depth <= 0) {   // callbacks re-enter the host runtime: stay on the task thread
+        const bool serial_cb = t.cb && t.cb->read_fully && !t.cb->upcalls_from_any_thread;
+        if (serial_cb || prefetch_depth <= 0) {   // such callbacks re-enter the host runtime: stay on the task thread
             auto p = plan_batch(t);
             if (p) {
                 try {

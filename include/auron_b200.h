@@ -13,6 +13,7 @@
  *   auron_b200_finalize_native  <- Java_..._JniBridge_finalizeNative, exec.rs:133-140 (rt.rs:282-306)
  *   auron_b200_on_exit          <- Java_..._JniBridge_onExit, exec.rs:144-149
  *   auron_b200_metrics          <- update_metrics walk, native-engine/auron/src/metrics.rs:22-58
+ *   auron_b200_metrics_walk     <- update_metric_node (tree-shaped walk), metrics.rs:22-50
  *   auron_callbacks             <- the JNI upcalls the engine makes on the hot path
  *                                  (native-engine/auron-jni-bridge/src/jni_bridge.rs:607-777,1485-1525)
  *
@@ -57,6 +58,11 @@ typedef struct auron_callbacks {
      * in-memory buffer (data, length -- hasByteBuffer; must stay valid until the next call).  Returns 1 = block
      * produced, 0 = end of input, <0 = error.  Only needed when the plan has an IpcReaderExecNode. */
     int (*next_shuffle_block)(void* user, const char* resource_id, struct auron_shuffle_block* out);
+    /* Non-zero: read_fully may be called from the engine's own reader threads, several at a time (the JNI face sets it:
+     * its threads attach to the JVM like the reference's tokio workers do, and FSDataInputWrapper.readFully is
+     * thread-safe).  Zero: every upcall is made on the thread that calls auron_b200_next_batch, one at a time, and the
+     * scan neither prefetches nor splits reads. */
+    int32_t upcalls_from_any_thread;
 } auron_callbacks;
 
 typedef struct auron_task auron_task;
@@ -78,6 +84,11 @@ const char* auron_b200_last_error(void);
 /* Walk the operator tree depth-first (same order as the JVM MetricNode tree) reporting (name, value). */
 typedef void (*auron_metric_fn)(void* user, int depth, const char* operator_name, const char* metric_name, int64_t value);
 int auron_b200_metrics(auron_task* task, auron_metric_fn fn, void* user);
+/* The same walk with the tree shape made explicit, as update_metric_node needs it (metrics.rs:22-50: MetricNode.getChild(i)
+ * per plan child): `enter` is called once per operator before its metrics, with its depth and its index among the
+ * children of its parent; operators without metrics are still entered. */
+typedef void (*auron_metric_node_fn)(void* user, int depth, int child_index, const char* operator_name);
+int auron_b200_metrics_walk(auron_task* task, auron_metric_node_fn enter, auron_metric_fn fn, void* user);
 
 /* ---- device-resident inputs (no counterpart in the reference: HBM residency for the GPU engine) ----
  * Copies `batch` to HBM and appends it to the resource `resource_id`; an FFIReaderExec whose

@@ -538,7 +538,10 @@ L1 = dict(a1=[1, 2, 3], b1=[4, 5, 5], c1=[7, 8, 9])
 R1 = dict(a2=[10, 20, 30], b1=[4, 5, 6], c2=[70, 80, 90])
 
 
-def _join(left: pa.Table, right: pa.Table, on, jt, impl):
+def _join(left, right, on, jt, impl, chunk=None):
+    """left/right: a table, or a list of tables that arrive as separate input batches (build_table_from_batches, test.rs:68-78)"""
+    lparts, rparts = (left if isinstance(left, list) else [left]), (right if isinstance(right, list) else [right])
+    left, right = lparts[0], rparts[0]
     lsrc, rsrc = P.ffi_reader(left.schema, "l"), P.ffi_reader(right.schema, "r")
     names = [f"l_{n}" for n in left.column_names]
     if jt in ("SEMI", "ANTI"):
@@ -555,7 +558,8 @@ def _join(left: pa.Table, right: pa.Table, on, jt, impl):
         plan = P.broadcast_join(s, lsrc, rsrc, onp, jt, "LEFT" if impl.endswith("L") else "RIGHT")
     else:
         plan = P.hash_join(s, lsrc, rsrc, onp, jt, "LEFT" if impl.endswith("L") else "RIGHT")
-    return run(plan, {"l": left, "r": right})
+    td = P.task_definition(plan, stage_id=1, partition_id=0, task_id=7)
+    return runtime.run_task(td, {"l": [b for t in lparts for b in batches(t, chunk)], "r": [b for t in rparts for b in batches(t, chunk)]})
 
 
 IMPLS = ["smj", "bhjL", "bhjR", "shjL", "shjR"]   # joins/test.rs:366-381 runs every scenario on these five
@@ -592,6 +596,64 @@ def test_join_golden_scenarios(impl):
     assert canon(got) == [(N, 6, 9), (4, N, 10), (5, 8, 11)]
     got = _join(table_i32(a1=[1, 2, 3], b1=[4, 5, 7], c1=[7, 8, 9]), table_i32(**R1), [("b1", "b1")], "EXISTENCE", impl)
     assert canon(got) == [(1, 4, 7, True), (2, 5, 8, True), (3, 7, 9, False)]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_join_golden_scenarios_part2(impl):
+    # the rest of datafusion-ext-plans/src/joins/test.rs: the scenarios test_join_golden_scenarios does not restate
+    N = None
+    # join_inner_two_two :455-498 (duplicates on both sides of a two-column key)
+    got = _join(table_i32(a1=[1, 1, 2], b2=[1, 1, 2], c1=[7, 8, 9]), table_i32(a1=[1, 1, 3], b2=[1, 1, 2], c2=[70, 80, 90]),
+                [("a1", "a1"), ("b2", "b2")], "INNER", impl)
+    assert canon(got) == [(1, 1, 7, 1, 1, 70), (1, 1, 7, 1, 1, 80), (1, 1, 8, 1, 1, 70), (1, 1, 8, 1, 1, 80)]
+    # join_inner_batchsize :540-650 (5 x 7 rows of one key; the result must not depend on how the input is batched)
+    lb = table_i32(a1=[1] * 5, b1=[1, 2, 3, 4, 5], c1=[1, 2, 3, 4, 5])
+    rb = table_i32(a2=[1] * 7, b2=[1, 2, 3, 4, 5, 6, 7], c2=[1, 2, 3, 4, 5, 6, 7])
+    exp = sorted((1, i, i, 1, j, j) for i in range(1, 6) for j in range(1, 8))
+    for chunk in (2, 3, 4, 5, 6, 7):
+        assert canon(_join(lb, rb, [("a1", "a2")], "INNER", impl, chunk=chunk)) == exp
+    # join_with_duplicated_column_names :858-888 (left.a = right.b)
+    got = _join(table_i32(a=[1, 2, 3], b=[4, 5, 7], c=[7, 8, 9]), table_i32(a=[10, 20, 30], b=[1, 2, 7], c=[70, 80, 90]), [("a", "b")], "INNER", impl)
+    assert canon(got) == [(1, 4, 7, 10, 1, 70), (2, 5, 8, 20, 2, 80)]
+    # join_date32 :890-923 / join_date64 :925-959 (every column is a date)
+    d32 = lambda **c: pa.table({k: pa.array(v, type=pa.int32()).cast(pa.date32()) for k, v in c.items()})
+    got = _join(d32(a1=[1, 2, 3], b1=[19107, 19108, 19108], c1=[7, 8, 9]), d32(a2=[10, 20, 30], b1=[19107, 19108, 19109], c2=[70, 80, 90]),
+                [("b1", "b1")], "INNER", impl)
+    assert got.schema.types == [pa.date32()] * 6
+    day = lambda n: dt.date(1970, 1, 1) + dt.timedelta(days=n)
+    assert canon(got) == [tuple(day(v) for v in r) for r in [(1, 19107, 7, 10, 19107, 70), (2, 19108, 8, 20, 19108, 80), (3, 19108, 9, 20, 19108, 80)]]
+    assert day(19107) == dt.date(2022, 4, 25)
+    d64 = lambda **c: pa.table({k: pa.array(v, type=pa.int64()).cast(pa.date64()) for k, v in c.items()})
+    got = _join(d64(a1=[1, 2, 3], b1=[1650703441000, 1650903441000, 1650903441000], c1=[7, 8, 9]),
+                d64(a2=[10, 20, 30], b1=[1650703441000, 1650503441000, 1650903441000], c2=[70, 80, 90]), [("b1", "b1")], "INNER", impl)
+    assert got.schema.types == [pa.date64()] * 6
+    ms = [tuple(r) for r in zip(*[c.cast(pa.int64()).to_pylist() for c in got.columns])]
+    assert sorted(ms) == [(1, 1650703441000, 7, 10, 1650703441000, 70), (2, 1650903441000, 8, 30, 1650903441000, 90), (3, 1650903441000, 9, 30, 1650903441000, 90)]
+    # join_left_sort_order :961-997 / join_right_sort_order :999-1031
+    lo = table_i32(a1=[0, 1, 2, 3, 4, 5], b1=[3, 4, 5, 6, 6, 7], c1=[4, 5, 6, 7, 8, 9])
+    ro = table_i32(a2=[0, 10, 20, 30, 40], b2=[2, 4, 6, 6, 8], c2=[50, 60, 70, 80, 90])
+    left_exp = [(0, 3, 4, N, N, N), (1, 4, 5, 10, 4, 60), (2, 5, 6, N, N, N), (3, 6, 7, 20, 6, 70), (3, 6, 7, 30, 6, 80), (4, 6, 8, 20, 6, 70),
+                (4, 6, 8, 30, 6, 80), (5, 7, 9, N, N, N)]
+    got = _join(lo, ro, [("b1", "b2")], "LEFT", impl)
+    assert canon(got) == canon(pa.table([pa.array([r[i] for r in left_exp], type=pa.int32()) for i in range(6)], names=list("abcdef")))
+    got = _join(table_i32(a1=[0, 1, 2, 3], b1=[3, 4, 5, 7], c1=[6, 7, 8, 9]), table_i32(a2=[0, 10, 20, 30], b2=[2, 4, 5, 6], c2=[60, 70, 80, 90]),
+                [("b1", "b2")], "RIGHT", impl)
+    right_exp = [(N, N, N, 0, 2, 60), (1, 4, 7, 10, 4, 70), (2, 5, 8, 20, 5, 80), (N, N, N, 30, 6, 90)]
+    assert canon(got) == canon(pa.table([pa.array([r[i] for r in right_exp], type=pa.int32()) for i in range(6)], names=list("abcdef")))
+    # join_{left,right,full,existence}_multiple_batches :1033-1238 (both inputs arrive as two batches)
+    l2 = [table_i32(a1=[0, 1, 2], b1=[3, 4, 5], c1=[4, 5, 6]), table_i32(a1=[3, 4, 5, 6], b1=[6, 6, 7, 9], c1=[7, 8, 9, 9])]
+    r2 = [table_i32(a2=[0, 10, 20], b2=[2, 4, 6], c2=[50, 60, 70]), table_i32(a2=[30, 40], b2=[6, 8], c2=[80, 90])]
+    matched = [(1, 4, 5, 10, 4, 60), (3, 6, 7, 20, 6, 70), (3, 6, 7, 30, 6, 80), (4, 6, 8, 20, 6, 70), (4, 6, 8, 30, 6, 80)]
+    l_only = [(0, 3, 4, N, N, N), (2, 5, 6, N, N, N), (5, 7, 9, N, N, N), (6, 9, 9, N, N, N)]
+    r_only = [(N, N, N, 0, 2, 50), (N, N, N, 40, 8, 90)]
+    tab = lambda rows: pa.table([pa.array([r[i] for r in rows], type=pa.int32()) for i in range(6)], names=list("abcdef"))
+    assert canon(_join(l2, r2, [("b1", "b2")], "LEFT", impl)) == canon(tab(matched + l_only))
+    # join_right_multiple_batches swaps the two tables: the right side is the 7-row one
+    swapped = lambda rows: [r[3:] + r[:3] for r in rows]
+    assert canon(_join(r2, l2, [("b2", "b1")], "RIGHT", impl)) == canon(tab(swapped(matched + l_only)))
+    assert canon(_join(l2, r2, [("b1", "b2")], "FULL", impl)) == canon(tab(matched + l_only + r_only))
+    got = _join(l2, r2, [("b1", "b2")], "EXISTENCE", impl)
+    assert canon(got) == [(0, 3, 4, False), (1, 4, 5, True), (2, 5, 6, False), (3, 6, 7, True), (4, 6, 8, True), (5, 7, 9, False), (6, 9, 9, False)]
 
 
 @pytest.mark.parametrize("jt", ["INNER", "LEFT", "RIGHT", "FULL", "SEMI", "ANTI"])

@@ -35,6 +35,20 @@ def test_jni_symbols_exported():
         assert hasattr(L, f"Java_org_apache_auron_jni_JniBridge_{s}")
 
 
+def test_jni_natives_against_the_mock_jvm_without_a_gpu():
+    # The JNI natives run against the mock JVM (tests/jni_mock/mock_jvm.cc): callNative fetches the task definition through
+    # getRawTaskDefinition, and -- no GPU here, no CPU fallback -- fails by raising RuntimeException on the calling thread
+    # (exec.rs:42-118 throws from callNative the same way), with every JNI reference released again.
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("the GPU suite (test_gpu_jni.py) covers the same entry points with a device")
+    from jni_helpers import MockJvm
+    jvm = MockJvm(P.task_definition(P.ffi_reader(pa.schema([("a", pa.int32())]), "in")))
+    assert not jvm.call_native()
+    assert jvm.pending_exception() == "java/lang/RuntimeException: auron_b200 requires a CUDA device (no CPU fallback)"
+    jvm.assert_clean()
+
+
 def _parse(buf: bytes):
     """tiny generic proto reader: [(field, wire, value)]"""
     out, i = [], 0
