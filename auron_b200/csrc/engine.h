@@ -77,6 +77,8 @@ struct Task {
     std::string error;
     bool cancelled = false;
     bool is_running();
+    // configuration entry: the host's value (get_conf callback), else the environment variable `env`, else `dflt`
+    std::string conf(const char* key, const char* env, const char* dflt) const;
     explicit Task(int device) : ctx(device) {}
 };
 

@@ -5,7 +5,8 @@
 //
 //   AuronCallNativeWrapper.getRawTaskDefinition / importSchema / importBatch / setError / getMetrics
 //                                          (rt.rs:78-83,167-170,258-262,309-318,300-306; jni_bridge.rs:1485-1525)
-//   JniBridge.getResource / isTaskRunning / openFileAsDataInputWrapper      (jni_bridge.rs:651-712)
+//   JniBridge.getResource / isTaskRunning / openFileAsDataInputWrapper / stringConf / intConf /
+//             get+setContextClassLoader / get+setThreadContext                (jni_bridge.rs:651-777, rt.rs:117-134)
 //   AuronArrowFFIExporter.exportNextBatch + AutoCloseable.close            (ffi_reader_exec.rs:126-130,195,214-217)
 //   scala.Function1.apply (fs provider) + FSDataInputWrapper.readFully     (hadoop_fs.rs:55-66,85-96,145-153)
 //   scala.Function0.apply -> scala.collection.Iterator of BlockObject      (ipc_reader_exec.rs:147-154,186-207,279-330)
@@ -64,7 +65,7 @@ enum {
     FN_FindClass = 6, FN_Throw = 13, FN_ThrowNew = 14, FN_ExceptionOccurred = 15, FN_ExceptionClear = 17, FN_PushLocalFrame = 19,
     FN_PopLocalFrame = 20, FN_NewGlobalRef = 21, FN_DeleteGlobalRef = 22, FN_NewObjectA = 30, FN_GetObjectClass = 31, FN_GetMethodID = 33,
     FN_CallObjectMethodA = 36, FN_CallBooleanMethodA = 39, FN_CallIntMethodA = 51, FN_CallLongMethodA = 54, FN_CallVoidMethodA = 63,
-    FN_GetStaticMethodID = 113, FN_CallStaticObjectMethodA = 116, FN_CallStaticBooleanMethodA = 119, FN_NewStringUTF = 167,
+    FN_GetStaticMethodID = 113, FN_CallStaticObjectMethodA = 116, FN_CallStaticBooleanMethodA = 119, FN_CallStaticIntMethodA = 131, FN_CallStaticVoidMethodA = 143, FN_NewStringUTF = 167,
     FN_GetStringUTFChars = 169, FN_ReleaseStringUTFChars = 170, FN_GetArrayLength = 171, FN_GetByteArrayRegion = 200, FN_GetJavaVM = 219,
     FN_ExceptionCheck = 228, FN_NewDirectByteBuffer = 229, FN_GetDirectBufferAddress = 230,
 };
@@ -142,6 +143,17 @@ struct J {
         check();
         return r != 0;
     }
+    void call_static_void(jclass c, const char* name, const char* sig, const jvalue* a = nullptr) const {
+        jmethodID m = static_method(c, name, sig);
+        fn<void (*)(JNIEnv*, jclass, jmethodID, const jvalue*)>(FN_CallStaticVoidMethodA)(env, c, m, a);
+        check();
+    }
+    jint call_static_int(jclass c, const char* name, const char* sig, const jvalue* a = nullptr) const {
+        jmethodID m = static_method(c, name, sig);
+        jint r = fn<jint (*)(JNIEnv*, jclass, jmethodID, const jvalue*)>(FN_CallStaticIntMethodA)(env, c, m, a);
+        check();
+        return r;
+    }
     jobject new_object(jclass c, const char* ctor_sig, const jvalue* a) const {
         jmethodID m = method(c, "<init>", ctor_sig);
         jobject r = fn<jobject (*)(JNIEnv*, jclass, jmethodID, const jvalue*)>(FN_NewObjectA)(env, c, m, a);
@@ -189,11 +201,16 @@ struct LocalFrame {
     ~LocalFrame() { j.fn<jobject (*)(JNIEnv*, jobject)>(FN_PopLocalFrame)(j.env, nullptr); }
 };
 
+std::atomic<uint64_t> g_task_serial{0};
+
 struct JniTask {
+    const uint64_t serial = ++g_task_serial;   // identifies the task to threads that outlive it (addresses get reused)
     JavaVM* vm = nullptr;
     auron_task* task = nullptr;
     jobject wrapper = nullptr;         // global ref of AuronCallNativeWrapper (rt.rs:63-73 keeps the same)
     jclass bridge = nullptr;           // global ref of org.apache.auron.jni.JniBridge
+    jobject class_loader = nullptr;    // the calling task thread's context class loader and Spark thread context: installed on
+    jobject thread_context = nullptr;  // every engine thread that makes upcalls for this task (rt.rs:117-134)
     auron_callbacks cb{};
     std::mutex mu;
     std::map<std::string, jobject> exporters;       // resource id -> AuronArrowFFIExporter
@@ -230,12 +247,30 @@ J env_of(JniTask* jt) {
     return J{env};
 }
 
+// rt.rs:124-134 does this in the worker threads' on_thread_start; pool workers outlive tasks, so it is redone whenever a
+// thread first serves another task
+thread_local uint64_t tl_context_of = 0;
+void adopt_thread_context(const J& j, JniTask* jt) {
+    if (tl_context_of == jt->serial || !tl_attachment.vm) return;   // Java threads (the caller of the natives) already carry theirs
+    tl_context_of = jt->serial;
+    try {
+        jvalue a;
+        a.l = jt->class_loader;
+        j.call_static_void(jt->bridge, "setContextClassLoader", "(Ljava/lang/ClassLoader;)V", &a);
+        a.l = jt->thread_context;
+        j.call_static_void(jt->bridge, "setThreadContext", "(Ljava/lang/Object;)V", &a);
+    } catch (const JavaError&) {
+        j.fn<void (*)(JNIEnv*)>(FN_ExceptionClear)(j.env);   // "let _ =" in the reference: best effort
+    }
+}
+
 // run one upcall sequence; a Java exception is captured for nextBatch to rethrow and reported to the engine as -1
 template <typename F>
 int64_t upcall(JniTask* jt, F&& body) {
     J j = env_of(jt);
     if (!j.env) return -1;
     LocalFrame frame(j);
+    adopt_thread_context(j, jt);
     try {
         return body(j);
     } catch (const JavaError&) {
@@ -308,6 +343,29 @@ int cb_is_task_running(void* user) {
     auto* jt = (JniTask*)user;
     int64_t r = upcall(jt, [&](const J& j) -> int64_t { return j.call_static_bool(jt->bridge, "isTaskRunning", "()Z") ? 1 : 0; });
     return r > 0;   // an exception while asking counts as "not running" (auron-jni-bridge/src/lib.rs:35-50)
+}
+
+// conf.rs:62-116: string entries through JniBridge.stringConf, the integer ones through intConf
+int cb_get_conf(void* user, const char* key, char* value, int32_t cap) {
+    auto* jt = (JniTask*)user;
+    J j = env_of(jt);
+    if (!j.env) return -1;
+    LocalFrame frame(j);
+    try {
+        jvalue a;
+        a.l = j.new_string(key);
+        std::string v;
+        if (!strcmp(key, "SPARK_IO_COMPRESSION_CODEC") || !strcmp(key, "SPILL_COMPRESSION_CODEC") || !strcmp(key, "NATIVE_LOG_LEVEL"))
+            v = j.to_string((jstring)j.call_static_object(jt->bridge, "stringConf", "(Ljava/lang/String;)Ljava/lang/String;", &a));
+        else
+            v = std::to_string(j.call_static_int(jt->bridge, "intConf", "(Ljava/lang/String;)I", &a));
+        if ((int32_t)v.size() >= cap) return -1;
+        memcpy(value, v.c_str(), v.size() + 1);
+        return (int)v.size();
+    } catch (const JavaError&) {
+        j.fn<void (*)(JNIEnv*)>(FN_ExceptionClear)(j.env);   // an entry the JVM side does not know: the engine's default applies
+        return -1;
+    }
 }
 
 void close_current_block(const J& j, JniTask* jt) {
@@ -434,6 +492,8 @@ void release_refs(const J& j, JniTask* jt) {
     j.drop_global(jt->cur_buffer);
     j.drop_global(jt->failure);
     j.drop_global(jt->wrapper);
+    j.drop_global(jt->class_loader);
+    j.drop_global(jt->thread_context);
     j.drop_global(jt->bridge);
 }
 
@@ -452,6 +512,8 @@ jlong Java_org_apache_auron_jni_JniBridge_callNative(JNIEnv* env, jclass, jlong 
         j.fn<jint (*)(JNIEnv*, JavaVM**)>(FN_GetJavaVM)(env, &jt->vm);
         jt->wrapper = j.global(native_wrapper);
         jt->bridge = (jclass)j.global(j.find_class("org/apache/auron/jni/JniBridge"));
+        jt->thread_context = j.global(j.call_static_object(jt->bridge, "getThreadContext", "()Ljava/lang/Object;"));          // rt.rs:117-121
+        jt->class_loader = j.global(j.call_static_object(jt->bridge, "getContextClassLoader", "()Ljava/lang/ClassLoader;"));
         jbyteArray arr = (jbyteArray)j.call_object(native_wrapper, "getRawTaskDefinition", "()[B");   // rt.rs:78-83
         jint n = j.array_length(arr);
         std::vector<uint8_t> bytes((size_t)n);
@@ -462,6 +524,7 @@ jlong Java_org_apache_auron_jni_JniBridge_callNative(JNIEnv* env, jclass, jlong 
         jt->cb.is_task_running = cb_is_task_running;
         jt->cb.next_shuffle_block = cb_next_shuffle_block;
         jt->cb.upcalls_from_any_thread = 1;
+        jt->cb.get_conf = cb_get_conf;
         const char* dev = getenv("AURON_B200_DEVICE");
         jt->task = auron_b200_call_native(bytes.data(), bytes.size(), &jt->cb, dev ? atoi(dev) : 0);
         if (!jt->task) {

@@ -17,6 +17,17 @@ bool Task::is_running() {
     return true;
 }
 
+std::string Task::conf(const char* key, const char* env, const char* dflt) const {
+    if (cb && cb->get_conf) {
+        char buf[256];
+        int n = cb->get_conf(cb->user, key, buf, (int32_t)sizeof(buf));
+        if (n >= 0 && n < (int)sizeof(buf)) return std::string(buf, (size_t)n);
+    }
+    if (env)
+        if (const char* e = getenv(env)) return e;
+    return dflt ? dflt : "";
+}
+
 // ------------------------------------------------------------------------------------------ resources
 struct DevResource {
     std::vector<BatchPtr> batches;

@@ -62,14 +62,14 @@ const Codecs& codecs() {
 }
 
 // one block: u32_le compressed_len | codec stream
-void compress_block(bool zstd, const uint8_t* in, size_t n, std::vector<uint8_t>& out) {
+void compress_block(bool zstd, int zstd_level, const uint8_t* in, size_t n, std::vector<uint8_t>& out) {
     const Codecs& c = codecs();
     size_t bound, written;
     if (zstd) {
         AURON_CHECK(c.z_compress, "libzstd.so.1 not available");
         bound = c.z_bound(n);
         out.resize(4 + bound);
-        written = c.z_compress(out.data() + 4, bound, in, n, 1);   // spark.io.compression.zstd.level default 1 (ipc_compression.rs:186-189)
+        written = c.z_compress(out.data() + 4, bound, in, n, zstd_level);   // spark.io.compression.zstd.level (ipc_compression.rs:186-193)
         AURON_CHECK(!c.z_iserr(written), "zstd compression failed");
     } else {
         AURON_CHECK(c.lz4_compress, "liblz4.so.1 not available");
@@ -95,6 +95,7 @@ struct ShuffleWriterExec : Operator {
     std::string data_file, index_file;
     bool done = false;
     bool zstd = false;
+    int zstd_level = 1;
     // one finished chunk: the compressed blocks of every partition, back to back, in one host buffer
     struct ChunkOut {
         uint8_t* bytes = nullptr;          // pinned (from pinned_pool) when pinned_cap > 0, else owned
@@ -186,7 +187,7 @@ struct ShuffleWriterExec : Operator {
             to_host(ctx, host, ser.bytes->ptr, (size_t)total);
             parallel_for((size_t)num_parts, 32, [&](size_t p) {
                 int64_t b = ser.part_offsets[p], e = ser.part_offsets[p + 1];
-                if (e > b) compress_block(zstd, host + b, (size_t)(e - b), blocks[p]);
+                if (e > b) compress_block(zstd, zstd_level, host + b, (size_t)(e - b), blocks[p]);
             });
         } catch (...) {
             pinned_pool().put(host, cap);
@@ -454,9 +455,10 @@ OperatorPtr make_shuffle_writer(Task& t, OperatorPtr input, const uint8_t* node,
     if (op->kind == 4 && op->num_parts == 1) op->kind = 1;   // planner.rs:1161-1162
     if (op->kind == 4)
         for (auto& h : op->range_bounds_host) AURON_CHECK(h.len == op->num_parts - 1, "range partitioning needs partition_count - 1 bounds");
-    if (const char* c = getenv("AURON_IO_COMPRESSION_CODEC")) op->zstd = std::string(c) == "zstd";   // spark.io.compression.codec (lz4 | zstd)
+    // spark.io.compression.codec (lz4 | zstd) and spark.io.compression.zstd.level (conf.rs:46-47, ipc_compression.rs:180-200)
+    op->zstd = t.conf("SPARK_IO_COMPRESSION_CODEC", "AURON_IO_COMPRESSION_CODEC", "lz4") == "zstd";
+    op->zstd_level = atoi(t.conf("SPARK_IO_COMPRESSION_ZSTD_LEVEL", "AURON_IO_COMPRESSION_ZSTD_LEVEL", "1").c_str());
     op->children.push_back(std::move(input));
-    (void)t;
     return op;
 }
 

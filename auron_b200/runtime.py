@@ -42,7 +42,7 @@ _BLOCK_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p, C.POINTER(ShuffleBlockC
 
 class Callbacks(C.Structure):
     _fields_ = [("user", C.c_void_p), ("export_next_batch", _EXPORT_CB), ("read_fully", _READ_CB), ("is_task_running", _RUNNING_CB),
-                ("next_shuffle_block", _BLOCK_CB), ("upcalls_from_any_thread", C.c_int32)]
+                ("next_shuffle_block", _BLOCK_CB), ("upcalls_from_any_thread", C.c_int32), ("get_conf", C.c_void_p)]
 
 
 class AuronError(RuntimeError):

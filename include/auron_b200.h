@@ -63,6 +63,11 @@ typedef struct auron_callbacks {
      * thread-safe).  Zero: every upcall is made on the thread that calls auron_b200_next_batch, one at a time, and the
      * scan neither prefetches nor splits reads. */
     int32_t upcalls_from_any_thread;
+    /* JniBridge.{int,long,double,boolean,string}Conf(key) (auron-jni-bridge/src/conf.rs:20-116): the value of the
+     * configuration entry `key` (the reference's names: "SPARK_IO_COMPRESSION_CODEC", "SPARK_IO_COMPRESSION_ZSTD_LEVEL",
+     * ...) written to `value` as text, NUL-terminated.  Returns its length, or <0 when the host has no such entry (the
+     * engine then falls back to its AURON_* environment variable, then to the reference's default).  May be NULL. */
+    int (*get_conf)(void* user, const char* key, char* value, int32_t cap);
 } auron_callbacks;
 
 typedef struct auron_task auron_task;

@@ -44,6 +44,7 @@ def mock():
         M.mock_put_fs_provider.argtypes = [C.c_void_p, C.c_char_p]
         M.mock_add_block.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_char_p, C.c_int64, C.c_int64, C.c_char_p]
         M.mock_blocks_closed.argtypes = [C.c_void_p, C.c_char_p]
+        M.mock_set_conf.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         M.mock_set_task_running.argtypes = [C.c_void_p, C.c_int]
         M.mock_take_schema.argtypes = [C.c_void_p, C.c_void_p]
         M.mock_num_batches.argtypes = [C.c_void_p]
@@ -121,6 +122,9 @@ class MockJvm:
         fn = EXPORT_FN(export)
         self._keep.append(fn)
         self.M.mock_put_exporter(self.vm, resource_id.encode(), fn, None)
+
+    def set_conf(self, key: str, value: str):
+        self.M.mock_set_conf(self.vm, key.encode(), value.encode())
 
     def put_fs_provider(self, resource_id: str):
         self.M.mock_put_fs_provider(self.vm, resource_id.encode())

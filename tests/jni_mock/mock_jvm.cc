@@ -148,6 +148,8 @@ struct Method {
 struct Env {   // JNIEnv: first member is the function table pointer
     void* const* functions;
     Jvm* vm;
+    Obj* class_loader = nullptr;     // per-thread state of the Java side
+    Obj* thread_context = nullptr;
     ThrowableObj* pending = nullptr;
     int frames = 0;
 };
@@ -164,7 +166,9 @@ struct Jvm {
     std::vector<std::unique_ptr<Method>> methods;
     std::vector<std::unique_ptr<Env>> envs;
     std::map<std::string, Obj*> resources;
+    std::map<std::string, std::string> conf;
     std::multiset<void*> globals;
+    std::atomic<int64_t> reads_without_context{0};   // readFully on a thread that carries no class loader / thread context
     std::atomic<int64_t> global_new{0}, global_del{0}, attached{0}, detached{0}, frames_pushed{0}, frames_popped{0};
     bool task_running = true;
     std::string trouble;   // protocol violations noticed by the mock
@@ -214,6 +218,12 @@ const char* kMethods[][3] = {
     {"org/apache/auron/jni/JniBridge", "isTaskRunning", "()Z"},
     {"org/apache/auron/jni/JniBridge", "openFileAsDataInputWrapper",
      "(Lorg/apache/hadoop/fs/FileSystem;Ljava/lang/String;)Lorg/apache/auron/hadoop/fs/FSDataInputWrapper;"},
+    {"org/apache/auron/jni/JniBridge", "getContextClassLoader", "()Ljava/lang/ClassLoader;"},
+    {"org/apache/auron/jni/JniBridge", "setContextClassLoader", "(Ljava/lang/ClassLoader;)V"},
+    {"org/apache/auron/jni/JniBridge", "getThreadContext", "()Ljava/lang/Object;"},
+    {"org/apache/auron/jni/JniBridge", "setThreadContext", "(Ljava/lang/Object;)V"},
+    {"org/apache/auron/jni/JniBridge", "stringConf", "(Ljava/lang/String;)Ljava/lang/String;"},
+    {"org/apache/auron/jni/JniBridge", "intConf", "(Ljava/lang/String;)I"},
     {"org/apache/auron/arrowio/AuronArrowFFIExporter", "exportNextBatch", "(J)Z"},
     {"org/apache/auron/arrowio/AuronArrowFFIExporter", "close", "()V"},
     {"scala/Function0", "apply", "()Ljava/lang/Object;"},
@@ -281,6 +291,34 @@ jvalue invoke(Env* e, Obj* self, Method* m, const jvalue* a) {
             std::lock_guard<std::mutex> g(vm->mu);
             auto it = vm->resources.find(key->s);
             r.l = it == vm->resources.end() ? nullptr : it->second;
+        } else if (n == "getContextClassLoader") {
+            r.l = e->class_loader;
+        } else if (n == "getThreadContext") {
+            r.l = e->thread_context;
+        } else if (n == "setContextClassLoader") {
+            e->class_loader = (Obj*)a[0].l;
+        } else if (n == "setThreadContext") {
+            e->thread_context = (Obj*)a[0].l;
+        } else if (n == "stringConf" || n == "intConf") {
+            auto* key = (StringObj*)a[0].l;
+            std::string v;
+            bool found;
+            {
+                std::lock_guard<std::mutex> g(vm->mu);
+                auto it = vm->conf.find(key->s);
+                found = it != vm->conf.end();
+                if (found) v = it->second;
+            }
+            if (!found) {
+                raise(e, "java/util/NoSuchElementException", key->s);
+                return r;
+            }
+            if (n == "intConf") r.i = atoi(v.c_str());
+            else {
+                auto* s = vm->make<StringObj>("java/lang/String");
+                s->s = v;
+                r.l = s;
+            }
         } else if (n == "isTaskRunning") {
             r.z = vm->task_running;
         } else if (n == "openFileAsDataInputWrapper") {
@@ -401,6 +439,7 @@ jvalue invoke(Env* e, Obj* self, Method* m, const jvalue* a) {
                 done += got;
             }
             in->reads++;
+            if (!e->class_loader || !e->thread_context) vm->reads_without_context++;
             if (done < want) raise(e, "java/io/EOFException", "cannot read more " + std::to_string(want - done) + " bytes");
         }
         return r;
@@ -418,13 +457,6 @@ jvalue invoke(Env* e, Obj* self, Method* m, const jvalue* a) {
     vm->complain("call of " + m->cls + "." + m->name + " on an object of class " + self->cls);
     raise(e, "java/lang/IncompatibleClassChangeError", m->name);
     return r;
-}
-
-// an object may be called through any of the interfaces its real counterpart implements
-bool instance_of(Obj* o, const std::string& cls) {
-    if (o->cls == cls) return true;
-    if (cls == "java/lang/AutoCloseable") return true;
-    return false;
 }
 
 // ---- JNIEnv functions -------------------------------------------------------------------------------------------------
@@ -514,6 +546,10 @@ void f_GetByteArrayRegion(Env* e, ByteArrayObj* a, int32_t off, int32_t n, int8_
     }
     memcpy(dst, a->bytes.data() + off, (size_t)n);
 }
+void f_CallStaticVoidMethodA(Env* e, void*, Method* m, const jvalue* a) {
+    if (m) invoke(e, nullptr, m, a);
+}
+int32_t f_CallStaticIntMethodA(Env* e, void*, Method* m, const jvalue* a) { return m ? invoke(e, nullptr, m, a).i : 0; }
 int32_t f_GetJavaVM(Env* e, void** out) {
     *out = &e->vm->vm;
     return 0;
@@ -593,6 +629,8 @@ void init_tables() {
     g_table[113] = (void*)f_GetStaticMethodID;
     g_table[116] = (void*)f_CallStaticObjectMethodA;
     g_table[119] = (void*)f_CallStaticBooleanMethodA;
+    g_table[131] = (void*)f_CallStaticIntMethodA;
+    g_table[143] = (void*)f_CallStaticVoidMethodA;
     g_table[167] = (void*)f_NewStringUTF;
     g_table[169] = (void*)f_GetStringUTFChars;
     g_table[170] = (void*)f_ReleaseStringUTFChars;
@@ -631,6 +669,10 @@ void* mock_env(void* jvm) {
     if (!(tl_env && tl_env_owner == vm)) {
         tl_env = new_env(vm);
         tl_env_owner = vm;
+    }
+    if (!tl_env->class_loader) {   // a Spark task thread: has a context class loader and a TaskContext
+        tl_env->class_loader = vm->make<Obj>("java/lang/ClassLoader");
+        tl_env->thread_context = vm->make<Obj>("org/apache/spark/TaskContext");
     }
     return tl_env;
 }
@@ -724,6 +766,11 @@ int mock_blocks_closed(void* jvm, const char* resource_id) {
         for (auto* b : p->it->blocks) n += b->closed == 1;
     return n;
 }
+void mock_set_conf(void* jvm, const char* key, const char* value) {
+    auto* vm = (Jvm*)jvm;
+    std::lock_guard<std::mutex> g(vm->mu);
+    vm->conf[key] = value;
+}
 void mock_set_task_running(void* jvm, int running) { ((Jvm*)jvm)->task_running = running != 0; }
 
 int mock_take_schema(void* wrapper, void* out) {
@@ -773,6 +820,7 @@ int64_t mock_counter(void* jvm, const char* name) {
     if (n == "global_new") return vm->global_new;
     if (n == "attached_threads") return vm->attached;
     if (n == "detached_threads") return vm->detached;
+    if (n == "reads_without_context") return vm->reads_without_context;
     if (n == "frames_open") return vm->frames_pushed - vm->frames_popped;
     if (n == "frames_pushed") return vm->frames_pushed;
     if (n == "input_wrappers") {

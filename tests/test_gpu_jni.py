@@ -69,6 +69,8 @@ def test_parquet_scan_reads_through_the_hadoop_fs_wrapper(tmp_path):
     # the scan's own threads (producer + read workers) attached themselves to the JVM; the producer ended with the scan and
     # detached again
     assert jvm.counter("attached_threads") >= 2 and jvm.counter("detached_threads") >= 1
+    # ... after taking over the task thread's class loader and thread context (rt.rs:117-134)
+    assert jvm.counter("reads_without_context") == 0
     jvm.assert_clean()
 
 
@@ -154,3 +156,28 @@ def test_union_lands_metrics_on_sibling_nodes():
     m = jvm.metrics()
     assert m["/0:output_rows"] == 10_000 and m["/1:output_rows"] == 7_000   # MetricNode.getChild(i) per plan child
     jvm.assert_clean()
+
+
+def test_shuffle_writer_takes_its_codec_from_the_jvm_conf(tmp_path):
+    # conf.rs:46-47 + ipc_compression.rs:180-200: JniBridge.stringConf("SPARK_IO_COMPRESSION_CODEC") / intConf(...ZSTD_LEVEL)
+    t = _input(30_000, seed=4)
+    magic = {"lz4": b"\x04\x22\x4d\x18", "zstd": b"\x28\xb5\x2f\xfd"}
+    for codec in ("zstd", "lz4", None):
+        data, index = str(tmp_path / f"{codec}.data"), str(tmp_path / f"{codec}.index")
+        w = P.shuffle_writer(P.ffi_reader(t.schema, "in"), P.hash_repartition([P.col("k")], 3), data, index)
+        jvm = MockJvm(P.task_definition(w))
+        jvm.put_exporter("in", batches(t))
+        if codec:
+            jvm.set_conf("SPARK_IO_COMPRESSION_CODEC", codec)
+            jvm.set_conf("SPARK_IO_COMPRESSION_ZSTD_LEVEL", "3")
+        jvm.run()
+        raw = open(data, "rb").read()
+        assert raw[4:8] == magic[codec or "lz4"]                      # u32 block length, then the codec's frame magic
+        jvm.assert_clean()
+        # and the file reads back through the JNI block iterator
+        offs = struct.unpack("<4q", open(index, "rb").read())
+        rd = MockJvm(P.task_definition(P.ipc_reader(t.schema, "blocks")))
+        for p in range(3):
+            rd.add_block("blocks", "file", path=data, offset=offs[p], length=offs[p + 1] - offs[p])
+        assert_same_rows(rd.run(), t)
+        rd.assert_clean()
