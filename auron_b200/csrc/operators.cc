@@ -457,9 +457,93 @@ BatchPtr AggExec::finalize(Task& t, const BatchPtr& merged) {
     return out;
 }
 
+static int64_t batch_device_bytes(const Batch& b) {
+    int64_t n = 0;
+    for (auto& c : b.cols)
+        for (const Buf* buf : {&c->validity, &c->data, &c->offsets})
+            if (*buf) n += (int64_t)(*buf)->bytes;
+    return n;
+}
+
+AggExec::~AggExec() {
+    for (auto& pieces : spilled)
+        for (auto& a : pieces)
+            if (a.release) a.release(&a);
+}
+
+// AggTable::spill (agg_table.rs:323-353): the in-memory table is emptied into `spill_buckets` hash buckets (bucket = pmod
+// of the Spark murmur3 of the group keys, the same partitioner the shuffle uses) so that each bucket can later be merged on
+// its own.  The next memory tier of a B200 node is pinned host DRAM, so the buckets are kept there as plain Arrow buffers:
+// no serialization, no compression, D2H at PCIe rate.
+void AggExec::spill(Task& t) {
+    if (partials.empty()) return;
+    OpTimer timer(metrics, "spill_ns");
+    BatchPtr all = partials.size() == 1 ? partials[0] : merge_partials(t, concat_batches(t.ctx, partials));
+    partials.clear();
+    partial_rows = 0;
+    if (all->num_rows == 0) return;
+    if (spilled.empty()) {
+        spilled.resize((size_t)spill_buckets);
+        spill_schema.fields.clear();
+        for (size_t i = 0; i < all->cols.size(); i++) {
+            Field f;
+            f.name = "c" + std::to_string(i);
+            f.type = all->cols[i]->type;
+            spill_schema.fields.push_back(f);
+        }
+    }
+    std::vector<ColumnPtr> keys(all->cols.begin(), all->cols.begin() + group_exprs.size());
+    Buf pids = murmur3_partition_ids(t.ctx, keys, all->num_rows, spill_buckets, 42);
+    Buf rows, offs;
+    partition_rows(t.ctx, P<int32_t>(pids), all->num_rows, spill_buckets, &rows, &offs);
+    std::vector<int64_t> off((size_t)spill_buckets + 1, 0);
+    to_host(t.ctx, off.data(), offs->ptr, off.size() * 8);
+    BatchPtr sorted = take_batch(t.ctx, *all, P<int32_t>(rows), all->num_rows, false);
+    int64_t bytes = 0;
+    for (int b = 0; b < spill_buckets; b++) {
+        int64_t n = off[(size_t)b + 1] - off[(size_t)b];
+        if (n == 0) continue;
+        BatchPtr piece = slice_batch(t.ctx, *sorted, off[(size_t)b], n);
+        bytes += batch_device_bytes(*piece);
+        ArrowArray a;
+        memset(&a, 0, sizeof(a));
+        export_batch(t.ctx, *piece, spill_schema, &a);
+        spilled[(size_t)b].push_back(a);
+    }
+    metrics.add("mem_spill_count", 1);
+    metrics.add("mem_spill_size", bytes);
+}
+
+// AggTable::output after a spill (agg_table.rs:145-304): every bucket is merged by itself and emitted as one batch
+BatchPtr AggExec::next_spilled_bucket(Task& t) {
+    while (out_bucket < spill_buckets) {
+        auto& pieces = spilled[(size_t)out_bucket++];
+        if (pieces.empty()) continue;
+        std::vector<BatchPtr> parts;
+        for (auto& a : pieces) {
+            parts.push_back(import_batch(t.ctx, &a, spill_schema));
+            if (a.release) a.release(&a);
+        }
+        pieces.clear();
+        BatchPtr merged = merge_partials(t, parts.size() == 1 ? parts[0] : concat_batches(t.ctx, parts));
+        BatchPtr out = finalize(t, merged);
+        metrics.add("output_rows", out->num_rows);
+        return out;
+    }
+    return nullptr;
+}
+
 BatchPtr AggExec::next(Task& t) {
-    if (output_done) return nullptr;
+    if (output_done) return spilled.empty() ? nullptr : next_spilled_bucket(t);
     bool saw_input = false;
+    if (spill_budget == 0) {
+        if (const char* e = getenv("AURON_AGG_SPILL_BYTES")) spill_budget = atoll(e);
+        if (spill_budget <= 0) {
+            size_t free_b = 0, total_b = 0;
+            CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+            spill_budget = (int64_t)(total_b / 10 * 4);   // the table may hold 40 % of the HBM; inputs and scratch keep the rest
+        }
+    }
     while (!input_done) {
         AURON_CHECK(t.is_running(), "task killed");
         SelBatch s = children[0]->next_sel(t);
@@ -480,9 +564,18 @@ BatchPtr AggExec::next(Task& t) {
             partials.push_back(m);
             partial_rows = m->num_rows;
         }
+        if (!group_exprs.empty()) {
+            int64_t held = 0;
+            for (auto& b : partials) held += batch_device_bytes(*b);
+            if (held > spill_budget) spill(t);
+        }
     }
     (void)saw_input;
     output_done = true;
+    if (!spilled.empty()) {   // something was spilled: the rest follows it, then the buckets are merged one at a time
+        spill(t);
+        return next_spilled_bucket(t);
+    }
     if (partials.empty()) {
         if (!group_exprs.empty()) return nullptr;
         // no grouping, no input: one row of empty accumulators (agg_exec.rs:280-323)

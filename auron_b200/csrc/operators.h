@@ -1,5 +1,6 @@
 // operators.h -- operator classes (mirror of datafusion-ext-plans/src/*_exec.rs)
 #pragma once
+#include "arrow_bridge.h"
 #include "engine.h"
 
 namespace auron {
@@ -68,10 +69,20 @@ struct AggExec : Operator {
     int n_acc_cols = 0, input_acc_cols = 0;
     bool has_widened_key = false;   // single GROUP BY cast(int col AS wider int): grouped on the source column
     DType widened_key_type;
+    // memory-bounded table (agg_table.rs:99-135,323-353,474-721): when the partial results held in HBM outgrow the budget
+    // they are split into hash buckets and moved to pinned host memory; the output then merges bucket by bucket
+    int64_t spill_budget = 0;         // bytes of partials allowed to stay in HBM (0 = not yet sized)
+    int spill_buckets = 64;
+    std::vector<std::vector<ArrowArray>> spilled;   // [bucket] -> host-resident pieces ([group cols..., acc cols...])
+    Schema spill_schema;
+    int out_bucket = 0;
     AggExec(OperatorPtr input, std::vector<ExprPtr> group_exprs, std::vector<std::string> group_names, std::vector<AggExprSpec> aggs);
+    ~AggExec() override;
     BatchPtr next(Task& t) override;
 
    private:
+    void spill(Task& t);
+    BatchPtr next_spilled_bucket(Task& t);
     BatchPtr aggregate_chunk(Task& t, SelBatch& s);
     BatchPtr merge_partials(Task& t, const BatchPtr& all);
     BatchPtr finalize(Task& t, const BatchPtr& merged);

@@ -817,3 +817,44 @@ def test_agg_min_max_on_strings(keys):
     exp_rows = sorted([key + (None if a[0] is None else a[0].decode(), None if a[1] is None else a[1].decode()) for key, a in acc.items()], key=repr)
     got_rows = sorted(zip(*[c.to_pylist() for c in got.columns]), key=repr)
     assert got_rows == exp_rows
+
+
+@pytest.mark.parametrize("mode", ["PARTIAL", "FINAL"])
+def test_agg_spills_to_host_buckets_and_merges_them(mode, monkeypatch):
+    # A5 (agg_table.rs:99-135,323-353,474-721): with a budget of one byte every chunk's table is spilled into hash buckets held in
+    # host memory; the output merges bucket by bucket and must equal the unspilled result, one row per group
+    rng = np.random.default_rng(31)
+    n = 120_000
+    t = pa.table({"k": pa.array(rng.integers(0, 30_000, n), type=pa.int64(), mask=rng.random(n) < 0.01),
+                  "s": pa.array([f"g{int(i)}" for i in rng.integers(0, 7, n)]),
+                  "v": pa.array(rng.integers(-10**6, 10**6, n), type=pa.int64(), mask=rng.random(n) < 0.05),
+                  "d": pa.array([decimal.Decimal(int(x)) / 100 for x in rng.integers(0, 10**6, n)], type=pa.decimal128(7, 2)),
+                  "w": pa.array([f"w{int(i):05d}" for i in rng.integers(0, 50_000, n)])})
+
+    def plan():
+        src = P.ffi_reader(t.schema, "t")
+        part = P.agg(src, [P.col("k"), P.col("s")], ["k", "s"],
+                     [P.agg_expr("SUM", [P.col("v")], pa.int64()), P.agg_expr("COUNT", [P.col("v")], pa.int64()),
+                      P.agg_expr("AVG", [P.col("d")], pa.decimal128(11, 6)), P.agg_expr("MIN", [P.col("w")], pa.string()),
+                      P.agg_expr("MAX", [P.col("v")], pa.int64())], ["sv", "c", "ad", "mw", "xv"], ["PARTIAL"] * 5)
+        if mode == "PARTIAL":
+            return part
+        N = pa.null()
+        return P.agg(part, [P.col("k"), P.col("s")], ["k", "s"],
+                     [P.agg_expr("SUM", [P.lit(None, N)], pa.int64()), P.agg_expr("COUNT", [P.lit(None, N)], pa.int64()),
+                      P.agg_expr("AVG", [P.lit(None, N)], pa.decimal128(11, 6)), P.agg_expr("MIN", [P.lit(None, N)], pa.string()),
+                      P.agg_expr("MAX", [P.lit(None, N)], pa.int64())], ["sv", "c", "ad", "mw", "xv"], ["FINAL"] * 5)
+
+    exp = run(plan(), {"t": t}, chunk=25_000)
+    monkeypatch.setenv("AURON_AGG_SPILL_BYTES", "1")
+    monkeypatch.setenv("AURON_GPU_CHUNK_ROWS", "30000")               # several device chunks, so several spills
+    td = P.task_definition(plan())
+    with runtime.Task(td, {"t": batches(t, 25_000)}) as task:
+        out = list(task)
+        m = {(op, name): v for _, op, name, v in task.metrics()}
+    got = pa.Table.from_batches(out, schema=exp.schema)
+    assert m[("AggExec", "mem_spill_count")] >= 3 and m[("AggExec", "mem_spill_size")] > 0
+    assert len(out) > 8                                                # one output batch per non-empty bucket
+    assert_same_rows(got, exp)
+    keys = list(zip(got["k"].to_pylist(), got["s"].to_pylist()))
+    assert len(keys) == len(set(keys))                                 # every group exactly once: buckets partition the key space
