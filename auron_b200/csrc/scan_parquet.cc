@@ -293,9 +293,10 @@ struct ParquetScanExec : Operator {
             size_t page;   // index into pages, or SIZE_MAX for a dictionary
             size_t dict, sec;
             int64_t off;
+            bool dev;      // off is relative to the device scratch (decompressed by the GPU), else to `unc` (decompressed here)
         };
         std::vector<Fix> fixes;
-        // SNAPPY pages of fixed-width columns are decompressed on the device: jobs with dst as an OFFSET into a scratch
+        // SNAPPY pages are decompressed on the device (all but nullable v1 PLAIN string pages): jobs with dst as an OFFSET into a scratch
         // buffer of gpu_unc_bytes that the task thread allocates; `fixes` then patch the descriptors with the scratch base
         std::vector<PqDecompJob> jobs;
         int64_t gpu_unc_bytes = 0;
@@ -398,7 +399,7 @@ struct ParquetScanExec : Operator {
         const int64_t len = cm.total_compressed;
         const int max_def = el.repetition == 1 ? 1 : 0;
         const bool compressed = cm.codec != pq::CODEC_UNCOMPRESSED;
-        const bool dev_snappy = cm.codec == pq::CODEC_SNAPPY && !is_string && gpu_snappy();
+        const bool dev_snappy = cm.codec == pq::CODEC_SNAPPY && gpu_snappy();
         int64_t pos = 0, values_seen = 0, rows = ct.row_start;
         int cur_dict = -1;
         while (pos < len && values_seen < cm.num_values) {
@@ -411,11 +412,13 @@ struct ParquetScanExec : Operator {
             int64_t unc_off = -1;
             int32_t lvl_bytes = h.type == pq::PAGE_DATA_V2 ? h.def_bytes + h.rep_bytes : 0;
             const bool page_compressed = compressed && !(h.type == pq::PAGE_DATA_V2 && !h.v2_compressed);
-            // Where the page body ends up: in place (uncompressed, or "stored" below), decompressed on the device (Snappy pages
-            // of fixed-width columns; string pages may need their levels on the host), or decompressed on the host.
+            // Where the page body ends up: in place (uncompressed, or "stored" below), decompressed on the device (Snappy), or
+            // decompressed on the host (other codecs; and the one Snappy case whose levels the host must see: a PLAIN string
+            // page needs its non-null count to place its values, which a nullable v1 page only has inside its body).
+            const bool page_dev = dev_snappy && !(is_string && h.type == pq::PAGE_DATA && h.encoding == pq::ENC_PLAIN && max_def > 0);
             bool on_device = false;
             int64_t gap = 0;   // stored v2 page with level sections: Snappy framing bytes between the levels and the values
-            if (page_compressed && dev_snappy) {
+            if (page_compressed && page_dev) {
                 AURON_CHECK(h.uncompressed_size >= lvl_bytes && h.compressed_size >= lvl_bytes, "corrupt parquet page sizes");
                 // Incompressible pages (bit-packed dictionary indices of random keys) are one Snappy literal: preamble, literal
                 // tag, raw body.  The body is then already in HBM inside the chunk, a few bytes further on: no job, no copy.
@@ -436,7 +439,7 @@ struct ParquetScanExec : Operator {
                 out.jobs.push_back(PqDecompJob{payload_d + lvl_bytes, (uint8_t*)(intptr_t)(unc_off + lvl_bytes), h.compressed_size - lvl_bytes,
                                                h.uncompressed_size - lvl_bytes, 1, 0});
                 payload_h = nullptr;
-            } else if (page_compressed && !dev_snappy) {
+            } else if (page_compressed && !page_dev) {
                 unc_off = (int64_t)out.unc.size();
                 out.unc.resize(out.unc.size() + (size_t)h.uncompressed_size + 8);
                 if (lvl_bytes) memcpy(out.unc.data() + unc_off, payload_h, (size_t)lvl_bytes);   // v2 levels are never compressed
@@ -456,7 +459,7 @@ struct ParquetScanExec : Operator {
                     out.secs.push_back({payload_d, h.uncompressed_size, h.num_values, (int32_t)out.value_table_size});
                     out.value_table_size += h.num_values;
                 }
-                if (unc_off >= 0) out.fixes.push_back({SIZE_MAX, (size_t)cur_dict, sec_idx, unc_off});
+                if (unc_off >= 0) out.fixes.push_back({SIZE_MAX, (size_t)cur_dict, sec_idx, unc_off, on_device});
                 continue;
             }
             AURON_CHECK(h.type == pq::PAGE_DATA || h.type == pq::PAGE_DATA_V2, "unknown parquet page type");
@@ -517,7 +520,7 @@ struct ParquetScanExec : Operator {
                 out.secs.push_back({base_d ? pg.val_ptr : nullptr, pg.val_len, nn, (int32_t)out.value_table_size});
                 out.value_table_size += nn;
             }
-            if (unc_off >= 0) out.fixes.push_back({out.pages.size(), 0, sec_idx, unc_off});
+            if (unc_off >= 0) out.fixes.push_back({out.pages.size(), 0, sec_idx, unc_off, on_device});
             out.pages.push_back(pg);
             rows += h.num_values;
             values_seen += h.num_values;
@@ -1068,10 +1071,10 @@ struct ParquetScanExec : Operator {
             ChunkPages& cp = ct.out;
             const Slot& sl = slots[ti];
             if (!cp.unc.empty() || cp.gpu_unc_bytes > 0) {
-                const uint8_t* base;
+                const uint8_t* dev_base = nullptr;
                 if (cp.gpu_unc_bytes > 0) {   // decompressed by pq_decompress below, straight from the chunk bytes in HBM
                     uint8_t* cbase = P<uint8_t>(unc_scratch) + sl.unc_off;
-                    base = cbase;
+                    dev_base = cbase;
                     for (auto& pg : cp.pages)
                         if (pg.job >= 0) pg.job += (int32_t)sl.job_base;
                     for (size_t j = 0; j < cp.jobs.size(); j++) {
@@ -1079,8 +1082,10 @@ struct ParquetScanExec : Operator {
                         jb.dst = cbase + (intptr_t)jb.dst;
                         decomp_jobs[sl.job_base + j] = jb;
                     }
-                } else base = P<uint8_t>(sl.host_unc);
+                }
+                const uint8_t* host_base = P<uint8_t>(sl.host_unc);
                 for (auto& fx : cp.fixes) {
+                    const uint8_t* base = fx.dev ? dev_base : host_base;
                     if (fx.page == SIZE_MAX) {
                         cp.dicts[fx.dict].data = base + fx.off;
                         if (fx.sec != SIZE_MAX) cp.secs[fx.sec].ptr = base + fx.off;

@@ -175,6 +175,36 @@ def test_scan_snappy_pages_decompressed_on_device(tmp_path, version, dict_, monk
         assert got_host[name].to_pylist() == exp[name].to_pylist(), name
 
 
+@pytest.mark.parametrize("version", ["1.0", "2.0"])
+@pytest.mark.parametrize("dict_", [True, False])
+def test_scan_snappy_string_pages_decompressed_on_device(tmp_path, version, dict_, monkeypatch):
+    # string columns: dictionary pages (PLAIN byte arrays) + RLE index pages, PLAIN data pages (v2; v1 when the column is
+    # required), all decompressed by the GPU; nullable v1 PLAIN pages are the one case left to the host (their non-null count
+    # sits inside the compressed body) and share a column chunk with device-decompressed dictionary pages when the writer
+    # falls back from dictionary to PLAIN mid-chunk ("wide": the dictionary page size limit is hit)
+    rng = np.random.default_rng(12)
+    n = 120_001
+    brands = [f"brand #{i:03d} " + "x" * (i % 17) for i in range(300)]
+    wide = [f"{int(v):09d}-" + "payload" * 6 for v in rng.integers(0, 40_000, n)]
+    schema = pa.schema([pa.field("brand", pa.string()), pa.field("req", pa.string(), nullable=False), pa.field("wide", pa.string()),
+                        pa.field("bin", pa.binary()), pa.field("k", pa.int32())])
+    t = pa.table({"brand": pa.array([brands[int(i)] for i in rng.integers(0, 300, n)], mask=rng.random(n) < 0.04),
+                  "req": pa.array([brands[int(i) % 40] for i in rng.integers(0, 10**6, n)]),
+                  "wide": pa.array(wide, mask=rng.random(n) < 0.1),
+                  "bin": pa.array([bytes([int(i) % 251]) * (int(i) % 9) for i in rng.integers(0, 10**6, n)], type=pa.binary(), mask=rng.random(n) < 0.02),
+                  "k": pa.array(rng.integers(0, 1000, n), type=pa.int32())}, schema=schema)
+    path = str(tmp_path / "s.parquet")
+    pq.write_table(t, path, compression="SNAPPY", use_dictionary=dict_, data_page_version=version, row_group_size=50_000, data_page_size=16 * 1024,
+                   dictionary_pagesize_limit=64 * 1024)
+    exp = pq.read_table(path)
+    got = _scan(path, t.schema)
+    monkeypatch.setenv("AURON_HOST_SNAPPY", "1")
+    got_host = _scan(path, t.schema)
+    for name in t.column_names:
+        assert got[name].to_pylist() == exp[name].to_pylist(), name
+        assert got_host[name].to_pylist() == exp[name].to_pylist(), name
+
+
 def test_scan_reports_corrupt_snappy_page(tmp_path):
     n = 20_000
     t = pa.table({"a": pa.array(np.arange(n, dtype=np.int64) % 13)})
