@@ -5,6 +5,7 @@
 #include "operators.h"
 
 #include <algorithm>
+#include <map>
 #include <mutex>
 
 #include "../../include/auron_b200.h"
@@ -539,9 +540,18 @@ BatchPtr AggExec::next(Task& t) {
     if (spill_budget == 0) {
         if (const char* e = getenv("AURON_AGG_SPILL_BYTES")) spill_budget = atoll(e);
         if (spill_budget <= 0) {
-            size_t free_b = 0, total_b = 0;
-            CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
-            spill_budget = (int64_t)(total_b / 10 * 4);   // the table may hold 40 % of the HBM; inputs and scratch keep the rest
+            // the table may hold 40 % of the HBM; inputs and scratch keep the rest.  Asked once per process and device:
+            // cudaMemGetInfo takes the driver's context lock, which a scan's copy thread would wait behind.
+            static std::mutex mu;
+            static std::map<int, int64_t> total_by_device;
+            std::lock_guard<std::mutex> g(mu);
+            auto it = total_by_device.find(t.ctx.device);
+            if (it == total_by_device.end()) {
+                size_t free_b = 0, total_b = 0;
+                CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+                it = total_by_device.emplace(t.ctx.device, (int64_t)total_b).first;
+            }
+            spill_budget = it->second / 10 * 4;
         }
     }
     while (!input_done) {
