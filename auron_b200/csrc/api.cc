@@ -4,10 +4,13 @@
 #include <atomic>
 #include <chrono>
 #include <cstring>
+#include <mutex>
+#include <map>
 
 #include "../../include/auron_b200.h"
 #include "exchange.h"
 #include "operators.h"
+#include "tzdb.h"
 
 using namespace auron;
 
@@ -132,6 +135,26 @@ int auron_b200_metrics_walk(auron_task* task, auron_metric_node_fn enter, auron_
     API_GUARD_BEGIN
     AURON_CHECK(task && task->task && task->task->root && enter && fn, "null task or callback");
     walk_metric_nodes(*task->task->root, 0, 0, enter, fn, user);
+    return 0;
+    API_GUARD_END(-1)
+}
+
+int auron_b200_tz_offset(const char* zone, int64_t utc_second, int32_t* offset) {
+    API_GUARD_BEGIN
+    AURON_CHECK(zone && offset, "null argument");
+    static std::mutex mu;
+    static std::map<std::string, TzTable> cache;
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(zone);
+    if (it == cache.end()) {
+        TzTable t;
+        if (!load_tz_table(zone, &t)) {
+            g_last_error = std::string("unknown time zone ") + zone;
+            return -1;
+        }
+        it = cache.emplace(zone, std::move(t)).first;
+    }
+    *offset = it->second.offset_at(utc_second);
     return 0;
     API_GUARD_END(-1)
 }

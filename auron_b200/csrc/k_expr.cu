@@ -26,6 +26,7 @@
 #include "device_utils.cuh"
 #include "expr.h"
 #include "kernels.h"
+#include "tzdb.h"
 
 namespace auron {
 
@@ -48,7 +49,7 @@ enum Op : uint16_t {
     OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE, OP_NSEQ,
     OP_AND, OP_OR, OP_NOT, OP_ISNULL, OP_ISNOTNULL, OP_SELECT, OP_COALESCE, OP_CAST,
     OP_STARTS, OP_ENDS, OP_CONTAINS, OP_LIKE, OP_SUBSTR, OP_CHARLEN, OP_OCTLEN, OP_TRIM, OP_CASEXF,
-    OP_DATEPART, OP_NULLIFZERO, OP_ISNAN, OP_NORMNAN, OP_CHECK_OVERFLOW, OP_MAKE_DECIMAL, OP_UNSCALED,
+    OP_DATEPART, OP_TS_LOCAL_MS, OP_TIMEPART, OP_MS_TO_DAYS, OP_NULLIFZERO, OP_ISNAN, OP_NORMNAN, OP_CHECK_OVERFLOW, OP_MAKE_DECIMAL, OP_UNSCALED,
     OP_MATH1, OP_POW, OP_HASH,
     OP_BITAND, OP_BITOR, OP_BITXOR, OP_SHL, OP_SHR,
     OP_OUT, OP_OUT_PRED, OP_FMT_OUT,
@@ -241,6 +242,28 @@ __device__ inline int32_t date_part(int64_t days, int part) {
         }
     }
     return 0;
+}
+
+// E4 with a session time zone (spark_dates.rs:200-227,313-345): `v` in `unit` (0 s, 1 ms, 2 us, 3 ns, 4 = Date32 days) becomes
+// Timestamp(Millisecond) the way arrow's cast does it (division truncates toward zero), then the zone's UTC offset at that
+// instant is added.  The zone is a table in the constant pool: int64 n | int64 transition_second[n] | int32 offset[n + 1].
+__device__ inline int64_t ts_to_local_ms(int64_t v, int unit, const uint8_t* tz) {
+    int64_t ms = unit == 0 ? v * 1000 : unit == 1 ? v : unit == 2 ? v / 1000 : unit == 3 ? v / 1000000 : v * 86400000ll;
+    if (tz) {
+        const int64_t n = *(const int64_t*)tz;
+        const int64_t* trans = (const int64_t*)tz + 1;
+        const int32_t* offs = (const int32_t*)(trans + n);
+        // chrono: Utc.timestamp_millis_opt(ms) -> the instant's second is floor(ms / 1000)
+        const int64_t sec = ms >= 0 ? ms / 1000 : -((-ms + 999) / 1000);
+        int64_t lo = 0, hi = n;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (trans[mid] <= sec) lo = mid + 1;
+            else hi = mid;
+        }
+        ms += (int64_t)offs[lo] * 1000;
+    }
+    return ms;
 }
 
 __device__ __forceinline__ const uint8_t* str_ptr(const VmParams& p, int64_t bufid, uint64_t view) {
@@ -961,6 +984,30 @@ __global__ void __launch_bounds__(VM_THREADS) vm_kernel(VmParams p) {
                     SETV(ins.dst, v);
                     break;
                 }
+                case OP_TS_LOCAL_MS: {   // aux = pool offset of the zone table (-1: none), aux2 = unit of the input
+                    bool v = VALID(ins.a);
+                    RLO(ins.dst) = v ? (uint64_t)ts_to_local_ms((int64_t)RLO(ins.a), ins.aux2, ins.aux >= 0 ? p.pool + ins.aux : nullptr) : 0;
+                    SETV(ins.dst, v);
+                    break;
+                }
+                case OP_TIMEPART: {      // extract_hms_with_tz (spark_dates.rs:313-345): aux = 0 hour, 1 minute, 2 second of local ms
+                    bool v = VALID(ins.a);
+                    int64_t day_ms = (int64_t)RLO(ins.a) % 86400000ll;
+                    if (day_ms < 0) day_ms += 86400000ll;
+                    const int64_t r = ins.aux == 0 ? day_ms / 3600000 : ins.aux == 1 ? (day_ms % 3600000) / 60000 : (day_ms % 60000) / 1000;
+                    RLO(ins.dst) = v ? (uint64_t)r : 0;
+                    SETV(ins.dst, v);
+                    break;
+                }
+                case OP_MS_TO_DAYS: {    // aux = 0: floor (ts_ms_to_local_date32, spark_dates.rs:213-227); 1: toward zero (arrow cast to Date32)
+                    bool v = VALID(ins.a);
+                    const int64_t ms = (int64_t)RLO(ins.a);
+                    int64_t d = ms / 86400000ll;
+                    if (ins.aux == 0 && ms < 0 && ms % 86400000ll != 0) d -= 1;
+                    RLO(ins.dst) = v ? (uint64_t)(int64_t)(int32_t)d : 0;
+                    SETV(ins.dst, v);
+                    break;
+                }
                 case OP_NULLIFZERO: {
                     bool v = VALID(ins.a);
                     uint64_t a = RLO(ins.a);
@@ -1630,10 +1677,75 @@ struct Compiler {
             emit(OP_MATH1, a.reg, a.reg, 0, 0, VT_F64, 0, m);
             return Val{a.reg, DType(T_FLOAT64)};
         };
+        // optional second argument: the session time zone as a utf8 literal (spark_dates.rs:93-102); a NULL literal, a
+        // non-literal or a name chrono-tz would not parse means "no zone"
+        auto zone_table = [&](bool* named, std::string* name) -> int {
+            *named = false;
+            if (e.children.size() < 2) return -1;
+            const Expr& z = *e.children[1];
+            if (z.kind != E_LITERAL || z.lit.is_null || !z.lit.type.is_varlen()) return -1;
+            *named = true;
+            *name = z.lit.s;
+            TzTable tab;
+            if (!load_tz_table(z.lit.s, &tab)) return -1;
+            while (prog.pool.size() % 8) prog.pool.push_back('\0');
+            const int at = (int)prog.pool.size();
+            const int64_t n = (int64_t)tab.trans.size();
+            prog.pool.append((const char*)&n, 8);
+            prog.pool.append((const char*)tab.trans.data(), (size_t)n * 8);
+            prog.pool.append((const char*)tab.offs.data(), (size_t)(n + 1) * 4);
+            while (prog.pool.size() % 8) prog.pool.push_back('\0');
+            return at;
+        };
+        auto unit_of = [&](const DType& t) -> int {
+            if (t.id == T_DATE32) return 4;
+            if (t.id == T_TIMESTAMP) return t.unit;
+            if (t.id == T_DATE64) return 1;
+            fail(f + " needs a date or timestamp argument, got " + t.str());
+            return 0;
+        };
+        // resolve_local_date32 (spark_dates.rs:231-254): with a zone the argument is cast to Timestamp(ms) and localized; without
+        // one it is cast to Date32
+        auto local_days = [&](Val a, int tz_at) {
+            const int unit = unit_of(a.type);
+            if (tz_at >= 0) {
+                emit(OP_TS_LOCAL_MS, a.reg, a.reg, 0, 0, VT_I64, 0, tz_at, unit);
+                emit(OP_MS_TO_DAYS, a.reg, a.reg, 0, 0, VT_I32, 0, 0);
+            } else if (unit != 4) {
+                emit(OP_TS_LOCAL_MS, a.reg, a.reg, 0, 0, VT_I64, 0, -1, unit);
+                emit(OP_MS_TO_DAYS, a.reg, a.reg, 0, 0, VT_I32, 0, 1);
+            }
+            return a;
+        };
         auto date_fn = [&](int part) {
             Val a = gen(*e.children[0]);
-            if (a.type.id != T_DATE32) fail(f + " is only native for Date32 input");
+            bool named;
+            std::string zname;
+            int tz_at = zone_table(&named, &zname);
+            if (part == DP_WEEK) {
+                // spark_weekofyear (spark_dates.rs:36-91): an unknown zone is an error; only Timestamp(Millisecond) input is
+                // localized (default zone UTC), every other type goes through the plain cast to Date32
+                if (named && tz_at < 0) fail("spark_weekofyear invalid timezone: " + zname);
+                if (!(a.type.id == T_TIMESTAMP && a.type.unit == 1)) tz_at = -1;
+                else if (tz_at < 0) {
+                    emit(OP_TS_LOCAL_MS, a.reg, a.reg, 0, 0, VT_I64, 0, -1, 1);
+                    emit(OP_MS_TO_DAYS, a.reg, a.reg, 0, 0, VT_I32, 0, 0);   // UTC calendar date of the instant (floor)
+                    emit(OP_DATEPART, a.reg, a.reg, 0, 0, VT_I32, 0, part);
+                    return Val{a.reg, DType(T_INT32)};
+                }
+            }
+            a = local_days(a, tz_at);
             emit(OP_DATEPART, a.reg, a.reg, 0, 0, VT_I32, 0, part);
+            return Val{a.reg, DType(T_INT32)};
+        };
+        // spark_hour / spark_minute / spark_second (spark_dates.rs:347-399)
+        auto time_fn = [&](int which) {
+            Val a = gen(*e.children[0]);
+            bool named;
+            std::string zname;
+            const int tz_at = zone_table(&named, &zname);
+            emit(OP_TS_LOCAL_MS, a.reg, a.reg, 0, 0, VT_I64, 0, tz_at, unit_of(a.type));
+            emit(OP_TIMEPART, a.reg, a.reg, 0, 0, VT_I32, 0, which);
             return Val{a.reg, DType(T_INT32)};
         };
         Val r{-1, DType()};
@@ -1643,6 +1755,9 @@ struct Compiler {
         else if (f == "Spark_DayOfWeek") r = date_fn(DP_DOW);
         else if (f == "Spark_WeekOfYear") r = date_fn(DP_WEEK);
         else if (f == "Spark_Quarter") r = date_fn(DP_QUARTER);
+        else if (f == "Spark_Hour") r = time_fn(0);
+        else if (f == "Spark_Minute") r = time_fn(1);
+        else if (f == "Spark_Second") r = time_fn(2);
         else if (f == "DatePart") {   // date_part('part', date)
             AURON_CHECK(e.children.size() == 2 && e.children[0]->kind == E_LITERAL, "date_part needs a literal part");
             std::string part = e.children[0]->lit.s;

@@ -130,6 +130,10 @@ int auron_b200_k_hash(const struct ArrowArray* batch, const struct ArrowSchema* 
 /* evaluate_partition_ids (datafusion-ext-plans/src/shuffle/mod.rs:163-188) -> int32 column */
 int auron_b200_k_partition_ids(const struct ArrowArray* batch, const struct ArrowSchema* schema, const int32_t* cols, int32_t ncols,
                                int32_t num_partitions, struct ArrowArray* out, struct ArrowSchema* out_schema, int device);
+/* UTC offset (seconds east) the engine's time-zone tables give for `zone` at `utc_second`: what the device looks up for the
+ * date/time functions that take a session time zone (spark_dates.rs:93-110,200-227, chrono-tz in the reference).
+ * Returns 0 and fills *offset, or -1 when `zone` is not an IANA zone name.  Host only: usable without a GPU. */
+int auron_b200_tz_offset(const char* zone, int64_t utc_second, int32_t* offset);
 /* number of kernels this library has launched in the calling process (bench.py "gpu_launches") */
 int64_t auron_b200_kernel_launches(void);
 /* micro-benchmark hook: runs `iters` launches of a named kernel over device-resident resource data and

@@ -336,6 +336,90 @@ def test_date_parts_vs_python():
         assert [got[f][i].as_py() for f in fns] == exp, x
 
 
+def _utc_ms(y, mo, d, h, mi, s):
+    return int(dt.datetime(y, mo, d, h, mi, s, tzinfo=dt.timezone.utc).timestamp() * 1000)
+
+
+def test_time_parts_and_session_time_zone_goldens():
+    # datafusion-ext-functions/src/spark_dates.rs tests :661-952 (hour / minute / second) and :1077-1175 (date parts with a zone)
+    S, I = pa.string(), pa.int32()
+    hms = lambda h, m, s: (h * 3600 + m * 60 + s) * 1000
+    ts = pa.table({"t": pa.array([0, hms(1, 23, 45), None, hms(12, 34, 56), -1000, _utc_ms(2019, 3, 10, 6, 59, 59), _utc_ms(2019, 3, 10, 7, 0, 0)],
+                                 type=pa.timestamp("ms")),
+                   "d": pa.array([0, 1, None, 100, -1, 17965, 17965], type=pa.int32()).cast(pa.date32())})
+    f = lambda name, col, tz=None: P.scalar_fn(name, [P.col(col)] + ([P.lit(tz, S)] if tz is not None else []), I)
+    exprs = {"h": f("Spark_Hour", "t"), "m": f("Spark_Minute", "t"), "s": f("Spark_Second", "t"),
+             "hd": f("Spark_Hour", "d"), "md": f("Spark_Minute", "d"), "sd": f("Spark_Second", "d"),
+             "h_utc": f("Spark_Hour", "t", "UTC"), "h_sh": f("Spark_Hour", "t", "Asia/Shanghai"),
+             "m_kol": f("Spark_Minute", "t", "Asia/Kolkata"), "s_kol": f("Spark_Second", "t", "Asia/Kolkata"),
+             "m_kat": f("Spark_Minute", "t", "Asia/Kathmandu"), "m_ny": f("Spark_Minute", "t", "America/New_York"),
+             "s_ny": f("Spark_Second", "t", "America/New_York"), "h_ny": f("Spark_Hour", "t", "America/New_York"),
+             "h_bad": f("Spark_Hour", "t", "Mars/Olympus")}
+    got = _eval(ts, list(exprs.values()), list(exprs), [I] * len(exprs))
+    N = None
+    assert got["h"].to_pylist() == [0, 1, N, 12, 23, 6, 7]                 # :661-688, :714-744, :746-764 (-1000 ms -> 23:59:59)
+    assert got["m"].to_pylist() == [0, 23, N, 34, 59, 59, 0]
+    assert got["s"].to_pylist() == [0, 45, N, 56, 59, 59, 0]
+    assert got["hd"].to_pylist() == [0, 0, N, 0, 0, 0, 0] == got["md"].to_pylist() == got["sd"].to_pylist()   # :691-711
+    assert got["h_utc"].to_pylist() == got["h"].to_pylist()                # :805-833
+    assert got["h_sh"].to_pylist()[0] == 8                                 # :784-802
+    assert (got["m_kol"].to_pylist()[0], got["s_kol"].to_pylist()[0]) == (30, 0)    # :835-881
+    assert got["m_kat"].to_pylist()[0] == 30                               # :884-904 (UTC+5:30 in 1970)
+    assert got["m_ny"].to_pylist()[5:] == [59, 0] and got["s_ny"].to_pylist()[5:] == [59, 0]   # :907-937 spring forward
+    assert got["h_ny"].to_pylist()[5:] == [1, 3]                           # 01:59:59 EST -> 03:00:00 EDT
+    assert got["h_bad"].to_pylist() == got["h"].to_pylist()                # a zone chrono-tz cannot parse counts as none (:97-102)
+    # date parts of timestamps in a zone
+    t2 = pa.table({"t": pa.array([_utc_ms(2021, 1, 4, 4, 30, 0), _utc_ms(2021, 1, 4, 5, 30, 0), _utc_ms(2021, 4, 1, 3, 0, 0),
+                                  _utc_ms(2021, 12, 31, 17, 0, 0), None], type=pa.timestamp("ms")),
+                   "d": pa.array([0, 100, None, 4017, 16801], type=pa.int32()).cast(pa.date32())})
+    names = ["Spark_Year", "Spark_Month", "Spark_Day", "Spark_DayOfWeek", "Spark_Quarter", "Spark_WeekOfYear"]
+    ny = {n: P.scalar_fn(n, [P.col("t"), P.lit("America/New_York", S)], I) for n in names}
+    sh = {n: P.scalar_fn(n, [P.col("t"), P.lit("Asia/Shanghai", S)], I) for n in names}
+    g_ny = _eval(t2, list(ny.values()), names, [I] * 6)
+    g_sh = _eval(t2, list(sh.values()), names, [I] * 6)
+    row = lambda g, i: [g[n][i].as_py() for n in names]
+    assert row(g_ny, 0) == [2021, 1, 3, 1, 1, 53]                          # :1077-1110, :569-585: 23:30 on Sunday Jan 3, ISO week 53
+    assert row(g_ny, 1)[5] == 1                                            # 00:30 on Jan 4 local: ISO week 1
+    assert row(g_ny, 2)[4] == 1                                            # :1113-1123: 23:00 on Mar 31 -> Q1
+    assert row(g_sh, 3) == [2022, 1, 1, 7, 1, 52]                          # :1126-1153: 01:00 on Sat Jan 1 2022
+    assert row(g_ny, 4) == [N] * 6
+    # NULL zone literal == no zone (:1156-1175); dates keep their plain parts
+    nz = {n: P.scalar_fn(n, [P.col("d"), P.lit(None, S)], I) for n in names}
+    pl = {n: P.scalar_fn(n, [P.col("d")], I) for n in names}
+    a, b = _eval(t2, list(nz.values()), names, [I] * 6), _eval(t2, list(pl.values()), names, [I] * 6)
+    assert all(a[n].to_pylist() == b[n].to_pylist() for n in names)
+    assert b["Spark_WeekOfYear"].to_pylist() == [1, 15, N, 1, 53]          # :546-566 (0, 4017, 16801 of the golden list)
+    with pytest.raises(runtime.AuronError, match="invalid timezone"):      # :588-600
+        _eval(t2, [P.scalar_fn("Spark_WeekOfYear", [P.col("t"), P.lit("Mars/Olympus", S)], I)], ["w"], [I])
+
+
+@pytest.mark.parametrize("zone", ["America/New_York", "Europe/London", "Asia/Kolkata", "Australia/Lord_Howe", "America/Sao_Paulo"])
+def test_time_zone_functions_vs_python_zoneinfo(zone):
+    import zoneinfo
+    rng = np.random.default_rng(41)
+    n = 20_000
+    secs = rng.integers(-2_000_000_000, 6_000_000_000, n)                  # 1906 .. 2160: past the tz database's explicit transitions
+    us = secs * 1_000_000 + rng.integers(0, 1_000_000, n)
+    t = pa.table({"t": pa.array(us, type=pa.timestamp("us"), mask=rng.random(n) < 0.02)})
+    S, I = pa.string(), pa.int32()
+    names = ["Spark_Hour", "Spark_Minute", "Spark_Second", "Spark_Year", "Spark_Month", "Spark_Day", "Spark_DayOfWeek", "Spark_Quarter"]
+    got = _eval(t, [P.scalar_fn(f, [P.col("t"), P.lit(zone, S)], I) for f in names], names, [I] * len(names))
+    tz = zoneinfo.ZoneInfo(zone)
+    cols = [got[f].to_pylist() for f in names]
+    valid = t["t"].is_valid().to_pylist()
+    for i in range(n):
+        if not valid[i]:
+            assert all(c[i] is None for c in cols)
+            continue
+        # the reference first casts to Timestamp(Millisecond) (spark_dates.rs:348-351); arrow's unit cast divides toward zero,
+        # so a pre-epoch instant with a sub-millisecond part lands on the millisecond above it
+        u = int(us[i])
+        ms = u // 1000 if u >= 0 else -((-u) // 1000)
+        x = dt.datetime.fromtimestamp(ms // 1000, tz=dt.timezone.utc).astimezone(tz)
+        exp = [x.hour, x.minute, x.second, x.year, x.month, x.day, (x.isoweekday() % 7) + 1, (x.month - 1) // 3 + 1]
+        assert [c[i] for c in cols] == exp, (int(us[i]), x)
+
+
 def test_murmur3_expr_and_misc_functions():
     t = _random_table(2000, seed=11)
     got = _eval(t, [P.scalar_fn("Spark_Murmur3Hash", [P.col("i32"), P.col("s")], pa.int32()),

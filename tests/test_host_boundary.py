@@ -49,6 +49,29 @@ def test_jni_natives_against_the_mock_jvm_without_a_gpu():
     jvm.assert_clean()
 
 
+def test_time_zone_tables_match_python_zoneinfo():
+    # the UTC-offset tables the device searches (tzdb.cc: TZif transitions + the footer's POSIX rule expanded to 2200) against
+    # Python's independent reader of the same tz database, 1875 .. 2191
+    import ctypes as C
+    import datetime as dt
+    import random
+    import zoneinfo
+    L = runtime.lib()
+    L.auron_b200_tz_offset.argtypes = [C.c_char_p, C.c_int64, C.POINTER(C.c_int32)]
+    random.seed(7)
+    for zone in ["UTC", "America/New_York", "Asia/Shanghai", "Asia/Kolkata", "Asia/Kathmandu", "Europe/Dublin", "Australia/Lord_Howe",
+                 "America/Sao_Paulo", "Pacific/Apia", "Antarctica/Troll", "Etc/GMT+8", "America/St_Johns"]:
+        tz = zoneinfo.ZoneInfo(zone)
+        for _ in range(1500):
+            s = random.randint(-3_000_000_000, 7_000_000_000)
+            exp = dt.datetime.fromtimestamp(s, tz=dt.timezone.utc).astimezone(tz).utcoffset().total_seconds()
+            got = C.c_int32()
+            assert L.auron_b200_tz_offset(zone.encode(), s, C.byref(got)) == 0
+            assert got.value == exp, (zone, s)
+    for bad in ["Mars/Olympus", "../etc/passwd", "+08:00", "", "posix/UTC"]:
+        assert L.auron_b200_tz_offset(bad.encode(), 0, C.byref(C.c_int32())) == -1
+
+
 def _parse(buf: bytes):
     """tiny generic proto reader: [(field, wire, value)]"""
     out, i = [], 0
