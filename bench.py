@@ -388,5 +388,15 @@ def main():
     print(json.dumps(line))
 
 
+def _json_only_stdout():
+    """Everything libraries print to stdout while the bench runs (NCCL's "NCCL version ..." banner comes from C code) is sent
+    to stderr; only the JSON line reaches the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 if __name__ == "__main__":
+    _json_only_stdout()
     main()
