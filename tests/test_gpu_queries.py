@@ -1,0 +1,162 @@
+"""Query-level parity: TPC-DS-shaped plans (BASELINE config 5's building blocks) that run the whole operator path of SURVEY §8 in
+one task -- Parquet scans (SNAPPY, strings, decimals) -> filters -> broadcast joins -> projection -> partial + final aggregate ->
+sort with limit -- exactly as the Spark plan for the query would be handed to the native engine, compared row by row with the
+query evaluated in plain Python over the same tables (integers, strings and decimals exact)."""
+import decimal
+import os
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.parquet as pq
+import pytest
+
+from auron_b200 import proto as P
+from auron_b200 import runtime
+from helpers import run
+
+pytestmark = pytest.mark.gpu
+
+D = decimal.Decimal
+CATEGORIES = ["Books", "Music", "Home", "Sports", None]
+
+
+def _tables(tmp_path, n_sales=150_000, seed=77):
+    rng = np.random.default_rng(seed)
+    n_items, n_dates = 1_500, 3_000
+    date_dim = pa.table({"d_date_sk": pa.array(np.arange(2450000, 2450000 + n_dates, dtype=np.int32)),
+                         "d_year": pa.array((1998 + np.arange(n_dates) // 365).astype(np.int32)),
+                         "d_moy": pa.array((1 + (np.arange(n_dates) // 30) % 12).astype(np.int32))})
+    item = pa.table({"i_item_sk": pa.array(np.arange(1, n_items + 1, dtype=np.int32)),
+                     "i_brand_id": pa.array(rng.integers(1001, 1040, n_items).astype(np.int32)),
+                     "i_brand": pa.array([f"brand #{int(b):02d}" for b in rng.integers(1, 40, n_items)], mask=rng.random(n_items) < 0.02),
+                     "i_category": pa.array([CATEGORIES[int(c)] for c in rng.integers(0, 5, n_items)]),
+                     "i_manufact_id": pa.array(rng.integers(120, 136, n_items).astype(np.int32))})
+    price = rng.integers(0, 20_000, n_sales)
+    store_sales = pa.table({
+        "ss_sold_date_sk": pa.array(rng.integers(2450000 - 50, 2450000 + n_dates + 50, n_sales).astype(np.int32), mask=rng.random(n_sales) < 0.04),
+        "ss_item_sk": pa.array(rng.integers(1, n_items + 100, n_sales).astype(np.int32)),
+        "ss_quantity": pa.array(rng.integers(1, 101, n_sales).astype(np.int32), mask=rng.random(n_sales) < 0.03),
+        "ss_sales_price": pa.array([D(int(p)) / 100 for p in price], type=pa.decimal128(7, 2), mask=rng.random(n_sales) < 0.03),
+        "ss_ext_sales_price": pa.array([D(int(p)) / 100 for p in rng.integers(0, 999_999, n_sales)], type=pa.decimal128(7, 2), mask=rng.random(n_sales) < 0.03)})
+    paths = {}
+    for name, t, rg in (("date_dim", date_dim, 1_000), ("item", item, 400), ("store_sales", store_sales, 40_000)):
+        path = str(tmp_path / f"{name}.parquet")
+        pq.write_table(t, path, compression="snappy", row_group_size=rg, store_decimal_as_integer=True)   # decimals INT32-backed, as Spark writes them
+        paths[name] = path
+    return date_dim, item, store_sales, paths
+
+
+def _scan(t, path, cols):
+    idx = [t.schema.get_field_index(c) for c in cols]
+    return P.parquet_scan(t.schema, [(path, os.path.getsize(path))], idx)
+
+
+def _rows(t, cols):
+    return list(zip(*[t[c].to_pylist() for c in cols]))
+
+
+def test_q3_shape_two_broadcast_joins_two_phase_aggregate_sort_limit(tmp_path):
+    # select d_year, i_brand_id, i_brand, sum(ss_ext_sales_price) sum_agg from date_dim, store_sales, item
+    # where d_date_sk = ss_sold_date_sk and ss_item_sk = i_item_sk and i_manufact_id = 128 and d_moy = 11
+    # group by d_year, i_brand, i_brand_id order by d_year, sum_agg desc, i_brand_id limit 100          (TPC-DS q3)
+    date_dim, item, ss, paths = _tables(tmp_path)
+    I, S = pa.int32(), pa.string()
+    dd = P.projection(P.filter_(_scan(date_dim, paths["date_dim"], ["d_date_sk", "d_year", "d_moy"]),
+                                [P.binary("Eq", P.col("d_moy"), P.lit(11, I)), P.is_not_null(P.col("d_date_sk"))]),
+                      [P.col("d_date_sk"), P.col("d_year")], ["d_date_sk", "d_year"], [I, I])
+    it = P.projection(P.filter_(_scan(item, paths["item"], ["i_item_sk", "i_brand_id", "i_brand", "i_manufact_id"]),
+                                [P.binary("Eq", P.col("i_manufact_id"), P.lit(128, I))]),
+                      [P.col("i_item_sk"), P.col("i_brand_id"), P.col("i_brand")], ["i_item_sk", "i_brand_id", "i_brand"], [I, I, S])
+    sales = P.filter_(_scan(ss, paths["store_sales"], ["ss_sold_date_sk", "ss_item_sk", "ss_ext_sales_price"]),
+                      [P.is_not_null(P.col("ss_sold_date_sk"))])
+    dec = pa.decimal128(7, 2)
+    j1_schema = pa.schema([("d_date_sk", I), ("d_year", I), ("ss_sold_date_sk", I), ("ss_item_sk", I), ("ss_ext_sales_price", dec)])
+    j1 = P.broadcast_join(j1_schema, dd, sales, [(P.col("d_date_sk"), P.col("ss_sold_date_sk"))], "INNER", "LEFT")
+    j2_schema = pa.schema(list(j1_schema) + [pa.field("i_item_sk", I), pa.field("i_brand_id", I), pa.field("i_brand", S)])
+    j2 = P.broadcast_join(j2_schema, j1, it, [(P.col("ss_item_sk"), P.col("i_item_sk"))], "INNER", "RIGHT")
+    proj = P.projection(j2, [P.col("d_year"), P.col("ss_ext_sales_price"), P.col("i_brand_id"), P.col("i_brand")],
+                        ["d_year", "ss_ext_sales_price", "i_brand_id", "i_brand"], [I, dec, I, S])
+    keys, names = [P.col("d_year"), P.col("i_brand"), P.col("i_brand_id")], ["d_year", "i_brand", "i_brand_id"]
+    partial = P.agg(proj, keys, names, [P.agg_expr("SUM", [P.col("ss_ext_sales_price")], pa.decimal128(17, 2))], ["sum_agg"], ["PARTIAL"])
+    final = P.agg(partial, keys, names, [P.agg_expr("SUM", [P.lit(None, pa.null())], pa.decimal128(17, 2))], ["sum_agg"], ["FINAL"])
+    plan = P.sort(final, [P.sort_expr(P.col("d_year"), True, True), P.sort_expr(P.col("sum_agg"), False, False), P.sort_expr(P.col("i_brand_id"), True, True)],
+                  limit=100)
+    got = run(plan, {})
+    # the query in plain Python
+    year_of = {k: y for k, y, m in _rows(date_dim, ["d_date_sk", "d_year", "d_moy"]) if m == 11}
+    item_of = {k: (bid, b) for k, bid, b, mf in _rows(item, ["i_item_sk", "i_brand_id", "i_brand", "i_manufact_id"]) if mf == 128}
+    acc = {}
+    for d, i, p in _rows(ss, ["ss_sold_date_sk", "ss_item_sk", "ss_ext_sales_price"]):
+        if d in year_of and i in item_of:
+            key = (year_of[d], item_of[i][1], item_of[i][0])
+            cur = acc.get(key)
+            acc[key] = cur if p is None else (p if cur is None else cur + p)       # SUM skips NULLs; a group of only NULLs sums to NULL
+    rows = [(y, b, bid, s) for (y, b, bid), s in acc.items()]
+    # ORDER BY d_year ASC NULLS FIRST, sum_agg DESC NULLS LAST, i_brand_id ASC
+    rows.sort(key=lambda r: (r[0], r[3] is None, -(r[3] if r[3] is not None else D(0)), r[2]))
+    exp = rows[:100]
+    assert len(acc) > 100 and got.num_rows == 100
+    got_rows = _rows(got, ["d_year", "i_brand", "i_brand_id", "sum_agg"])
+    sort_key = lambda r: (r[0], r[3], r[2])
+    assert [sort_key(r) for r in got_rows] == [sort_key(r) for r in exp]            # the ordering columns, position by position
+    assert sorted(got_rows, key=repr) == sorted(exp, key=repr) or len({sort_key(r) for r in exp}) < len(exp)   # full rows (unless the sort keys tie)
+
+
+def test_string_predicates_decimal_average_and_string_sort(tmp_path):
+    # select i_category, substr(i_brand, 7, 3) b, count(*) c, avg(ss_sales_price) a, min(ss_sold_date_sk) d, max(i_brand) mb
+    # from store_sales join item on ss_item_sk = i_item_sk
+    # where i_brand like 'brand #1%' and ss_quantity between 10 and 50 and (ss_sales_price > 50.00 or i_category = 'Books')
+    # group by i_category, substr(i_brand, 7, 3) order by i_category nulls first, b desc
+    _, item, ss, paths = _tables(tmp_path, seed=78)
+    I, S, L = pa.int32(), pa.string(), pa.int64()
+    dec = pa.decimal128(7, 2)
+    it = P.filter_(_scan(item, paths["item"], ["i_item_sk", "i_brand", "i_category"]), [P.like(P.col("i_brand"), P.lit("brand #1%", S))])
+    sales = P.filter_(_scan(ss, paths["store_sales"], ["ss_sold_date_sk", "ss_item_sk", "ss_quantity", "ss_sales_price"]),
+                      [P.binary("GtEq", P.col("ss_quantity"), P.lit(10, I)), P.binary("LtEq", P.col("ss_quantity"), P.lit(50, I))])
+    j_schema = pa.schema([("ss_sold_date_sk", I), ("ss_item_sk", I), ("ss_quantity", I), ("ss_sales_price", dec),
+                          ("i_item_sk", I), ("i_brand", S), ("i_category", S)])
+    j = P.hash_join(j_schema, sales, it, [(P.col("ss_item_sk"), P.col("i_item_sk"))], "INNER", "RIGHT")
+    flt = P.filter_(j, [P.binary("Or", P.binary("Gt", P.col("ss_sales_price"), P.lit(D("50.00"), dec)),
+                                 P.binary("Eq", P.col("i_category"), P.lit("Books", S)))])
+    b = P.scalar_fn("Substr", [P.col("i_brand"), P.lit(7, L), P.lit(3, L)], S)
+    proj = P.projection(flt, [P.col("i_category"), b, P.col("ss_sales_price"), P.col("ss_sold_date_sk"), P.col("i_brand"), P.col("ss_item_sk")],
+                        ["i_category", "b", "ss_sales_price", "ss_sold_date_sk", "i_brand", "ss_item_sk"], [S, S, dec, I, S, I])
+    keys, names = [P.col("i_category"), P.col("b")], ["i_category", "b"]
+    avg_t = pa.decimal128(11, 6)
+    N = pa.null()
+    partial = P.agg(proj, keys, names, [P.agg_expr("COUNT", [P.col("ss_item_sk")], L), P.agg_expr("AVG", [P.col("ss_sales_price")], avg_t),
+                                        P.agg_expr("MIN", [P.col("ss_sold_date_sk")], I), P.agg_expr("MAX", [P.col("i_brand")], S)],
+                    ["c", "a", "d", "mb"], ["PARTIAL"] * 4)
+    final = P.agg(partial, keys, names, [P.agg_expr("COUNT", [P.lit(None, N)], L), P.agg_expr("AVG", [P.lit(None, N)], avg_t),
+                                         P.agg_expr("MIN", [P.lit(None, N)], I), P.agg_expr("MAX", [P.lit(None, N)], S)],
+                  ["c", "a", "d", "mb"], ["FINAL"] * 4)
+    plan = P.sort(final, [P.sort_expr(P.col("i_category"), True, True), P.sort_expr(P.col("b"), False, False)])
+    got = run(plan, {})
+    item_of = {k: (b_, c) for k, b_, c in _rows(item, ["i_item_sk", "i_brand", "i_category"]) if b_ is not None and b_.startswith("brand #1")}
+    acc = {}
+    for d, i, q, p in _rows(ss, ["ss_sold_date_sk", "ss_item_sk", "ss_quantity", "ss_sales_price"]):
+        if q is None or not (10 <= q <= 50) or i not in item_of:
+            continue
+        brand, cat = item_of[i]
+        # Kleene OR: TRUE if either side is TRUE; NULL (dropped) otherwise unless both are FALSE
+        if not ((p is not None and p > D("50.00")) or cat == "Books"):
+            continue
+        a = acc.setdefault((cat, brand[6:9]), [0, None, 0, None, None])
+        a[0] += 1
+        if p is not None:
+            a[1] = p if a[1] is None else a[1] + p
+            a[2] += 1
+        if d is not None:
+            a[3] = d if a[3] is None else min(a[3], d)
+        a[4] = brand if a[4] is None else max(a[4], brand)
+    exp = []
+    for (cat, b_), (c, s, n, d, mb) in acc.items():
+        avg = None
+        if n:
+            scaled = int(s.scaleb(2)) * 10**4                      # sum rescaled to decimal(11,6) (agg.rs:195), div_euclid by the count (avg.rs:165-170)
+            avg = D(scaled // n).scaleb(-6)
+        exp.append((cat, b_, c, avg, d, mb))
+    exp.sort(key=lambda r: (r[1],), reverse=True)                  # b DESC
+    exp.sort(key=lambda r: (r[0] is not None, r[0] or ""))          # i_category ASC NULLS FIRST (stable)
+    assert len(exp) > 10
+    assert _rows(got, ["i_category", "b", "c", "a", "d", "mb"]) == exp
