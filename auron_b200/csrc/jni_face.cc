@@ -319,6 +319,7 @@ int64_t cb_read_fully(void* user, const char* fs_resource_id, const char* path, 
                 auto fp = jt->fs_providers.find(fs_resource_id);
                 if (fp == jt->fs_providers.end())
                     fp = jt->fs_providers.emplace(fs_resource_id, j.global(get_resource(j, jt, fs_resource_id))).first;
+                if (!fp->second) return -1;   // no such resource: the engine reports the failed read
                 jvalue a[2];
                 a[0].l = j.new_string(path);
                 jobject fs = j.call_object(fp->second, "apply", "(Ljava/lang/Object;)Ljava/lang/Object;", a);   // FsProvider::provide
@@ -394,6 +395,7 @@ int cb_next_shuffle_block(void* user, const char* resource_id, struct auron_shuf
             auto f = jt->block_iters.find(resource_id);
             if (f == jt->block_iters.end()) {
                 jobject provider = get_resource(j, jt, resource_id);
+                if (!provider) return -1;
                 jobject blocks = j.call_object(provider, "apply", "()Ljava/lang/Object;");   // ipc_reader_exec.rs:150
                 f = jt->block_iters.emplace(resource_id, j.global(blocks)).first;
             }

@@ -181,3 +181,26 @@ def test_shuffle_writer_takes_its_codec_from_the_jvm_conf(tmp_path):
             rd.add_block("blocks", "file", path=data, offset=offs[p], length=offs[p + 1] - offs[p])
         assert_same_rows(rd.run(), t)
         rd.assert_clean()
+
+
+def test_whole_query_through_jni(tmp_path):
+    # the q3-shaped plan of test_gpu_queries.py (three Parquet scans through the Hadoop FS wrapper, two joins, two-phase aggregate,
+    # sort + limit) driven through the JNI natives: same rows, in the same order, as through the C ABI
+    from test_gpu_queries import FS_RESOURCE, q3_plan
+    plan, _ = q3_plan(tmp_path)
+    td = P.task_definition(plan)
+    exp = runtime.run_task(td, {})
+    jvm = MockJvm(td)
+    jvm.put_fs_provider(FS_RESOURCE)
+    got = jvm.run()
+    assert got.schema == exp.schema and got.num_rows == 100
+    assert got.to_pylist() == exp.to_pylist()
+    assert jvm.counter("input_wrappers") == 3 == jvm.counter("input_wrappers_closed")
+    jvm.assert_clean()
+    # a scan whose FS resource was never registered fails the task with an error, not a crash
+    jvm = MockJvm(td)
+    assert jvm.call_native()
+    assert jvm.load_next_batch() is None
+    assert "RuntimeException" in jvm.error()
+    jvm.close()
+    jvm.assert_clean()

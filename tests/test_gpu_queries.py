@@ -46,16 +46,20 @@ def _tables(tmp_path, n_sales=150_000, seed=77):
     return date_dim, item, store_sales, paths
 
 
+FS_RESOURCE = "hadoop-fs-provider-0"
+
+
 def _scan(t, path, cols):
     idx = [t.schema.get_field_index(c) for c in cols]
-    return P.parquet_scan(t.schema, [(path, os.path.getsize(path))], idx)
+    return P.parquet_scan(t.schema, [(path, os.path.getsize(path))], idx, fs_resource_id=FS_RESOURCE)
 
 
 def _rows(t, cols):
     return list(zip(*[t[c].to_pylist() for c in cols]))
 
 
-def test_q3_shape_two_broadcast_joins_two_phase_aggregate_sort_limit(tmp_path):
+def q3_plan(tmp_path):
+    """(plan bytes, (date_dim, item, store_sales)) of the q3-shaped query below"""
     # select d_year, i_brand_id, i_brand, sum(ss_ext_sales_price) sum_agg from date_dim, store_sales, item
     # where d_date_sk = ss_sold_date_sk and ss_item_sk = i_item_sk and i_manufact_id = 128 and d_moy = 11
     # group by d_year, i_brand, i_brand_id order by d_year, sum_agg desc, i_brand_id limit 100          (TPC-DS q3)
@@ -81,6 +85,11 @@ def test_q3_shape_two_broadcast_joins_two_phase_aggregate_sort_limit(tmp_path):
     final = P.agg(partial, keys, names, [P.agg_expr("SUM", [P.lit(None, pa.null())], pa.decimal128(17, 2))], ["sum_agg"], ["FINAL"])
     plan = P.sort(final, [P.sort_expr(P.col("d_year"), True, True), P.sort_expr(P.col("sum_agg"), False, False), P.sort_expr(P.col("i_brand_id"), True, True)],
                   limit=100)
+    return plan, (date_dim, item, ss)
+
+
+def test_q3_shape_two_broadcast_joins_two_phase_aggregate_sort_limit(tmp_path):
+    plan, (date_dim, item, ss) = q3_plan(tmp_path)
     got = run(plan, {})
     # the query in plain Python
     year_of = {k: y for k, y, m in _rows(date_dim, ["d_date_sk", "d_year", "d_moy"]) if m == 11}
