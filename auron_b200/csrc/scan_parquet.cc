@@ -1047,7 +1047,7 @@ struct ParquetScanExec : Operator {
                     cs.stat_ok = false;   // (an all-NULL chunk has no min / max and constrains nothing)
                 }
             }
-            if (!cp.unc.empty()) {   // host-decompressed payloads (ZSTD / LZ4_RAW pages, string columns) are uploaded here
+            if (!cp.unc.empty()) {   // host-decompressed payloads (ZSTD / LZ4_RAW pages, nullable v1 PLAIN string pages) are uploaded here
                 sl.host_unc = to_device(t.ctx, cp.unc.data(), cp.unc.size());
                 cs.keep.push_back(sl.host_unc);
             }
