@@ -462,13 +462,8 @@ __device__ __forceinline__ uint32_t def_tile_words(Hybrid& def, const uint8_t* d
 }
 
 // pass 1: one warp per page walks the run headers and checkpoints both streams every PQ_TILE rows
-__global__ void __launch_bounds__(PQ_WARPS * 32) pq_scout_kernel(PqLaunch L) {
-    __shared__ int s_exit[PQ_WARPS][32][33];
-    __shared__ int s_entry[PQ_WARPS][33];
+__device__ __forceinline__ void scout_page(const PqLaunch& L, int page_id, int (*s_exit_w)[33], int* s_entry_w) {
     const PqColumnArgs& a = L.a;
-    const int wid = threadIdx.x >> 5;
-    int page_id = blockIdx.x * PQ_WARPS + wid;
-    if (page_id >= a.n_pages) return;
     const unsigned lane = lane_id();
     const PqPage pg = a.pages[page_id];
     Hybrid def, idx;
@@ -489,7 +484,7 @@ __global__ void __launch_bounds__(PQ_WARPS * 32) pq_scout_kernel(PqLaunch L) {
     int64_t v0 = 0;
     const uint8_t* pf_idx = idx_base;
     int tile = L.tile_base[page_id];
-    if (has_def) lvl_page_bits(pg.def_ptr, pg.def_len, rows, lane, L.tile_valid + (int64_t)tile * 32, s_exit[wid], s_entry[wid]);
+    if (has_def) lvl_page_bits(pg.def_ptr, pg.def_len, rows, lane, L.tile_valid + (int64_t)tile * 32, s_exit_w, s_entry_w);
     for (int r = 0; r < rows; r += PQ_TILE, tile++) {
         int m = min(PQ_TILE, rows - r);
         if (lane == 0) {
@@ -523,6 +518,26 @@ __global__ void __launch_bounds__(PQ_WARPS * 32) pq_scout_kernel(PqLaunch L) {
         if (dict || bool_rle) hybrid_skip(idx, nvalid);
         v0 += nvalid;
     }
+}
+__global__ void __launch_bounds__(PQ_WARPS * 32) pq_scout_kernel(PqLaunch L) {
+    __shared__ int s_exit[PQ_WARPS][32][33];
+    __shared__ int s_entry[PQ_WARPS][33];
+    const int wid = threadIdx.x >> 5;
+    const int page_id = blockIdx.x * PQ_WARPS + wid;
+    if (page_id >= L.a.n_pages) return;
+    scout_page(L, page_id, s_exit[wid], s_entry[wid]);
+}
+// The scout of one column is a few thousand warps (one per page): too few to fill 148 SMs.  All columns of a batch are
+// scouted by ONE launch: warp g serves page g - page_base[c] of column c.
+__global__ void __launch_bounds__(PQ_WARPS * 32) pq_scout_multi_kernel(const PqLaunch* __restrict__ Ls, const int32_t* __restrict__ page_base, int ncols) {
+    __shared__ int s_exit[PQ_WARPS][32][33];
+    __shared__ int s_entry[PQ_WARPS][33];
+    const int wid = threadIdx.x >> 5;
+    const int g = blockIdx.x * PQ_WARPS + wid;
+    if (g >= page_base[ncols]) return;
+    int c = 0;
+    while (c + 1 < ncols && g >= page_base[c + 1]) c++;
+    scout_page(Ls[c], g - page_base[c], s_exit[wid], s_entry[wid]);
 }
 
 // pass 2: one warp per tile
@@ -813,28 +828,54 @@ __global__ void __launch_bounds__(PQ_WARPS * 32) pq_decode_tiles_fast_kernel(PqL
     }
 }
 
-void pq_decode_pages(Ctx& ctx, const PqColumnArgs& a, const std::vector<PqPage>& host_pages) {
-    if (a.n_pages == 0) return;
+PqPrepared pq_prepare(Ctx& ctx, const PqColumnArgs& a, const std::vector<PqPage>& host_pages) {
+    PqPrepared pr;
+    pr.a = a;
+    if (a.n_pages == 0) return pr;
     std::vector<int32_t> tb(host_pages.size() + 1, 0);
     for (size_t i = 0; i < host_pages.size(); i++) tb[i + 1] = tb[i] + (host_pages[i].num_values + PQ_TILE - 1) / PQ_TILE;
-    int n_tiles = tb.back();
-    if (n_tiles == 0) return;
-    Buf dtb = to_device(ctx, tb.data(), tb.size() * 4);
-    Buf tiles = dalloc(ctx, (size_t)n_tiles * sizeof(PqTile));
-    Buf tvalid = dalloc_zero(ctx, a.max_def > 0 ? (size_t)n_tiles * 128 : 4);   // zeroed: the scout ORs level bits into it
-    PqLaunch L{a, P<int32_t>(dtb), P<PqTile>(tiles), P<uint32_t>(tvalid)};
-    {
-        ProfScope ps(ctx, "pq_scout");
-        pq_scout_kernel<<<(a.n_pages + PQ_WARPS - 1) / PQ_WARPS, PQ_WARPS * 32, 0, ctx.stream>>>(L);
-        LAUNCH_CHECK(ctx);
+    pr.n_tiles = tb.back();
+    if (pr.n_tiles == 0) return pr;
+    pr.tile_base = to_device(ctx, tb.data(), tb.size() * 4);   // staged before returning (pinned arena copy, or the driver's pageable-copy staging)
+    pr.tiles = dalloc(ctx, (size_t)pr.n_tiles * sizeof(PqTile));
+    pr.tile_valid = dalloc_zero(ctx, a.max_def > 0 ? (size_t)pr.n_tiles * 128 : 4);   // zeroed: the scout ORs level bits into it
+    return pr;
+}
+static PqLaunch launch_of(const PqPrepared& pr) { return PqLaunch{pr.a, P<int32_t>(pr.tile_base), P<PqTile>(pr.tiles), P<uint32_t>(pr.tile_valid)}; }
+
+void pq_scout_many(Ctx& ctx, const std::vector<PqPrepared*>& cols) {
+    std::vector<PqLaunch> Ls;
+    std::vector<int32_t> base{0};
+    for (auto* pr : cols) {
+        if (pr->n_tiles == 0) continue;
+        Ls.push_back(launch_of(*pr));
+        base.push_back(base.back() + pr->a.n_pages);
     }
-    {
-        ProfScope ps(ctx, "pq_decode_pages");
-        if (a.phys_type == 0) pq_decode_tiles_kernel<<<(n_tiles + PQ_WARPS - 1) / PQ_WARPS, PQ_WARPS * 32, 0, ctx.stream>>>(L, n_tiles);
-        else pq_decode_tiles_fast_kernel<<<(n_tiles + PQ_WARPS - 1) / PQ_WARPS, PQ_WARPS * 32, 0, ctx.stream>>>(L, n_tiles);
-        LAUNCH_CHECK(ctx);
+    if (Ls.empty()) return;
+    ProfScope ps(ctx, "pq_scout");
+    if (Ls.size() == 1) {
+        pq_scout_kernel<<<(Ls[0].a.n_pages + PQ_WARPS - 1) / PQ_WARPS, PQ_WARPS * 32, 0, ctx.stream>>>(Ls[0]);
+    } else {
+        Buf dL = to_device(ctx, Ls.data(), Ls.size() * sizeof(PqLaunch));
+        Buf dbase = to_device(ctx, base.data(), base.size() * 4);
+        pq_scout_multi_kernel<<<(base.back() + PQ_WARPS - 1) / PQ_WARPS, PQ_WARPS * 32, 0, ctx.stream>>>(P<PqLaunch>(dL), P<int32_t>(dbase), (int)Ls.size());
     }
-    // no sync: to_device stages `tb` before returning (pinned arena copy, or the driver's pageable-copy staging)
+    LAUNCH_CHECK(ctx);
+}
+
+void pq_decode_prepared(Ctx& ctx, const PqPrepared& pr) {
+    if (pr.n_tiles == 0) return;
+    PqLaunch L = launch_of(pr);
+    ProfScope ps(ctx, "pq_decode_pages");
+    if (pr.a.phys_type == 0) pq_decode_tiles_kernel<<<(pr.n_tiles + PQ_WARPS - 1) / PQ_WARPS, PQ_WARPS * 32, 0, ctx.stream>>>(L, pr.n_tiles);
+    else pq_decode_tiles_fast_kernel<<<(pr.n_tiles + PQ_WARPS - 1) / PQ_WARPS, PQ_WARPS * 32, 0, ctx.stream>>>(L, pr.n_tiles);
+    LAUNCH_CHECK(ctx);
+}
+
+void pq_decode_pages(Ctx& ctx, const PqColumnArgs& a, const std::vector<PqPage>& host_pages) {
+    PqPrepared pr = pq_prepare(ctx, a, host_pages);
+    pq_scout_many(ctx, {&pr});
+    pq_decode_prepared(ctx, pr);
 }
 
 // ---- PLAIN BYTE_ARRAY sections (dictionary pages and non-dictionary data pages): one thread walks one section

@@ -64,7 +64,16 @@ PqDecompOut pq_decompress(Ctx& ctx, const std::vector<PqDecompJob>& jobs);
 // pages with def_len == -1: level / value sections from the body's length word (+ in-place value sections, see above)
 void pq_fix_v1_pages(Ctx& ctx, PqPage* pages, int n, const PqDecompResult* results);
 
+// scout + decode of one column; or in three steps, so that one scout launch serves every column of a batch
 void pq_decode_pages(Ctx& ctx, const PqColumnArgs& a, const std::vector<PqPage>& host_pages);
+struct PqPrepared {
+    PqColumnArgs a;
+    int n_tiles = 0;
+    Buf tile_base, tiles, tile_valid;
+};
+PqPrepared pq_prepare(Ctx& ctx, const PqColumnArgs& a, const std::vector<PqPage>& host_pages);
+void pq_scout_many(Ctx& ctx, const std::vector<PqPrepared*>& cols);
+void pq_decode_prepared(Ctx& ctx, const PqPrepared& pr);
 ColumnPtr pq_build_value_table(Ctx& ctx, const std::vector<PqByteSection>& secs, int64_t total_values, const DType& type);
 
 }  // namespace auron

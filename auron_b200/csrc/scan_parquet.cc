@@ -584,6 +584,18 @@ struct ParquetScanExec : Operator {
         AURON_CHECK(n_rows < (int64_t)INT32_MAX, "parquet batch too large");
         auto out = std::make_shared<Batch>();
         out->num_rows = n_rows;
+        // One scout launch for all columns of the batch (a column alone is a few thousand page-warps, too few for 148 SMs):
+        // the per-column work is prepared in the loop, scouted together, then decoded column by column.
+        // AURON_SCAN_SCOUT_PER_COLUMN=1 keeps one scout launch per column; the lane mode does too.
+        struct Pending {
+            size_t out_pos;
+            PqPrepared pr;
+            ColumnPtr table;   // strings: value table to gather from after the index decode
+            Buf idx, keep_pages, keep_dicts;
+            bool nullable;
+        };
+        std::vector<Pending> pending;
+        const bool batch_scout = !use_lanes && !getenv("AURON_SCAN_SCOUT_PER_COLUMN");
         for (size_t ci = 0; ci < projection.size(); ci++) {
             const Field& fld = table_schema.fields[projection[ci]];
             ColState& cs = cols[ci];
@@ -638,12 +650,17 @@ struct ParquetScanExec : Operator {
                 a.mode = PQ_MODE_INDEX;
                 a.out_idx = P<int32_t>(idx);
                 a.out_valid = nullptr;
-                pq_decode_pages(t.ctx, a, cs.pages);
-                col = take(t.ctx, *table, P<int32_t>(idx), n_rows, max_def > 0);
+                if (batch_scout) {
+                    pending.push_back(Pending{out->cols.size(), pq_prepare(t.ctx, a, cs.pages), table, idx, dpages, ddicts, max_def > 0});
+                } else {
+                    pq_decode_pages(t.ctx, a, cs.pages);
+                    col = take(t.ctx, *table, P<int32_t>(idx), n_rows, max_def > 0);
+                }
             } else {
                 a.out = col->data->ptr;
                 a.mode = PQ_MODE_VALUES;
-                pq_decode_pages(wc, a, cs.pages);
+                if (batch_scout) pending.push_back(Pending{out->cols.size(), pq_prepare(t.ctx, a, cs.pages), nullptr, nullptr, dpages, ddicts, false});
+                else pq_decode_pages(wc, a, cs.pages);
                 if (validity) {
                     col->validity = validity;
                     col->null_count = -1;
@@ -657,6 +674,16 @@ struct ParquetScanExec : Operator {
                 }
             }
             out->cols.push_back(col);
+        }
+        if (!pending.empty()) {
+            std::vector<PqPrepared*> prs;
+            for (auto& pd : pending) prs.push_back(&pd.pr);
+            pq_scout_many(t.ctx, prs);
+            for (auto& pd : pending) {
+                pq_decode_prepared(t.ctx, pd.pr);
+                if (pd.table) out->cols[pd.out_pos] = take(t.ctx, *pd.table, P<int32_t>(pd.idx), n_rows, pd.nullable);
+            }
+            pending.clear();
         }
         for (auto& l : lanes) chain(l->stream, t.ctx.stream);   // the batch is complete once every lane is
         fold_lanes(t);
