@@ -1,0 +1,162 @@
+"""The plan bytes that cross the boundary.  Every GPU parity test hands the engine a TaskDefinition built by auron_b200/proto.py; this
+module pins that encoder -- and through it the planner that decodes those bytes on the other side -- to the reference's own wire
+contract: tests/golden/auron_proto_schema.json is extracted from native-engine/auron-planner/proto/auron.proto (tools/
+extract_proto_schema.py, run where the reference is mounted), and a schema-driven protobuf decoder walks the encoder's output:
+every field number must exist in the message the reference declares at that position, with the wire type its declared type implies,
+enums must carry declared values, and nested messages are walked recursively."""
+import decimal
+import json
+import os
+
+import pyarrow as pa
+import pytest
+
+from auron_b200 import proto as P
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SCHEMA = json.load(open(os.path.join(HERE, "golden", "auron_proto_schema.json")))
+MSG, ENUM = SCHEMA["messages"], SCHEMA["enums"]
+VARINT_TYPES = {"int32", "int64", "uint32", "uint64", "sint32", "sint64", "bool"}
+LEN_TYPES = {"string", "bytes"}
+FIXED64, FIXED32 = {"double", "fixed64", "sfixed64"}, {"float", "fixed32", "sfixed32"}
+
+
+def _varint(buf, i):
+    v = s = 0
+    while True:
+        b = buf[i]
+        i += 1
+        v |= (b & 0x7F) << s
+        if not b & 0x80:
+            return v, i
+        s += 7
+
+
+def walk(msg: str, buf: bytes, seen: set, path: str = ""):
+    """decode `buf` as reference message `msg`; returns {field name: [values]} and records (message, field) in `seen`"""
+    by_num = {v[0]: (k, v[1], v[2]) for k, v in MSG[msg].items()}
+    out, i = {}, 0
+    while i < len(buf):
+        key, i = _varint(buf, i)
+        num, wire = key >> 3, key & 7
+        assert num in by_num, f"{path}{msg}: field number {num} is not declared by the reference"
+        name, typ, repeated = by_num[num]
+        seen.add((msg, name))
+        where = f"{path}{msg}.{name}"
+        if wire == 0:
+            v, i = _varint(buf, i)
+            assert typ in VARINT_TYPES or typ in ENUM, f"{where}: varint on the wire, declared {typ}"
+            if typ in ENUM:
+                assert v in ENUM[typ].values(), f"{where}: {v} is not a value of enum {typ}"
+        elif wire == 2:
+            n, i = _varint(buf, i)
+            v = buf[i:i + n]
+            i += n
+            assert len(v) == n, f"{where}: truncated"
+            if typ in MSG:
+                v = walk(typ, v, seen, path + msg + ".")
+            elif repeated and (typ in VARINT_TYPES or typ in ENUM):   # packed repeated scalars
+                vals, j = [], 0
+                while j < len(v):
+                    x, j = _varint(v, j)
+                    vals.append(x)
+                v = vals
+            else:
+                assert typ in LEN_TYPES, f"{where}: length-delimited on the wire, declared {typ}"
+                if typ == "string":
+                    v = v.decode("utf-8")
+        elif wire == 1:
+            assert typ in FIXED64, f"{where}: 64-bit on the wire, declared {typ}"
+            v, i = buf[i:i + 8], i + 8
+        elif wire == 5:
+            assert typ in FIXED32, f"{where}: 32-bit on the wire, declared {typ}"
+            v, i = buf[i:i + 4], i + 4
+        else:
+            raise AssertionError(f"{where}: wire type {wire}")
+        if not repeated and name in out and typ not in MSG:
+            raise AssertionError(f"{where}: singular field encoded twice")
+        out.setdefault(name, []).append(v)
+    return out
+
+
+I, L, S = pa.int32(), pa.int64(), pa.string()
+T = pa.schema([("a", I), ("b", L), ("s", S), ("d", pa.decimal128(7, 2)), ("t", pa.timestamp("us")), ("x", pa.float64()), ("dt", pa.date32()),
+               ("f", pa.bool_())])
+
+
+def _plans():
+    """one plan per node / expression kind the engine accepts, built exactly as the GPU tests build them"""
+    src = P.ffi_reader(T, "in")
+    dec = decimal.Decimal
+    exprs = [P.binary("Plus", P.col("a"), P.lit(1, I)), P.binary("And", P.is_null(P.col("a")), P.is_not_null(P.col("b"))), P.not_(P.col("f")),
+             P.negative(P.col("a")), P.case([(P.binary("Gt", P.col("a"), P.lit(0, I)), P.lit("p", S))], P.lit(None, S)),
+             P.cast(P.col("a"), L), P.try_cast(P.col("s"), pa.decimal128(12, 3)), P.in_list(P.col("a"), [P.lit(1, I), P.lit(2, I)], negated=True),
+             P.scalar_fn("Spark_Hour", [P.col("t"), P.lit("Asia/Shanghai", S)], I), P.scalar_fn("Substr", [P.col("s"), P.lit(1, L), P.lit(2, L)], S),
+             P.like(P.col("s"), P.lit("a%", S)), P.sc_and(P.col("f"), P.col("f")), P.sc_or(P.col("f"), P.col("f")),
+             P.starts_with(P.col("s"), "a"), P.ends_with(P.col("s"), "z"), P.contains(P.col("s"), "m"), P.bound_ref(0, I),
+             P.lit(dec("12.34"), pa.decimal128(7, 2)), P.lit(1.5, pa.float64()), P.lit(True, pa.bool_())]
+    names = [f"e{i}" for i in range(len(exprs))]
+    types = [I, pa.bool_(), pa.bool_(), I, S, L, pa.decimal128(12, 3), pa.bool_(), I, S] + [pa.bool_()] * 6 + [I, pa.decimal128(7, 2), pa.float64(), pa.bool_()]
+    proj = P.projection(P.filter_(src, [P.binary("GtEq", P.col("a"), P.lit(0, I))]), exprs, names, types)
+    aggs = [P.agg_expr(f, [P.col("b")], L) for f in ("SUM", "COUNT", "MIN", "MAX", "AVG", "FIRST")]
+    agg = P.agg(src, [P.col("a"), P.col("s")], ["a", "s"], aggs, [f"g{i}" for i in range(6)], ["PARTIAL"] * 6)
+    agg_f = P.agg(agg, [P.col("a")], ["a"], [P.agg_expr("SUM", [P.lit(None, pa.null())], L)], ["g"], ["FINAL"])
+    on = [(P.col("a"), P.col("a"))]
+    js = pa.schema(list(T) + list(T))
+    joins = [P.hash_join(js, src, src, on, "LEFT", "RIGHT"), P.sort_merge_join(js, src, src, on, "FULL"),
+             P.broadcast_join(js, src, src, on, "SEMI", "LEFT", cached_id="bc-1", null_aware_anti=True)]
+    sort = P.sort(src, [P.sort_expr(P.col("a"), False, False), P.sort_expr(P.col("s"))], limit=10, offset=2)
+    scan = P.parquet_scan(T, [("/tmp/x.parquet", 1234), ("/tmp/y.parquet", 99)], [0, 2, 3], fs_resource_id="fs", ranges=[(0, 100), (5, 50)],
+                          pruning_predicates=[P.binary("Lt", P.col("a"), P.lit(5, I))])
+    parts = [P.hash_repartition([P.col("a"), P.col("s")], 7), P.single_repartition(), P.round_robin_repartition(5),
+             P.range_repartition([P.sort_expr(P.col("a"))], 3, [([10, 20], I)])]
+    writers = [P.shuffle_writer(src, p, "/tmp/d", "/tmp/i") for p in parts]
+    misc = [P.limit(src, 5, 1), P.rename_columns(src, [f"c{i}" for i in range(len(T))]), P.union([src, src], T), P.ipc_reader(T, "blocks")]
+    return [proj, agg, agg_f, sort, scan] + joins + writers + misc
+
+
+def test_every_encoded_plan_is_a_well_formed_reference_message():
+    seen = set()
+    for plan in _plans():
+        td = walk("TaskDefinition", P.task_definition(plan, stage_id=3, partition_id=4, task_id=5), seen)
+        pid = td["task_id"][0]
+        assert (pid["stage_id"], pid["partition_id"], pid["task_id"]) == ([3], [4], [5])
+    # the walk really went through the messages of the path (a vacuous pass would not)
+    nodes = {f for m, f in seen if m == "PhysicalPlanNode"}
+    assert nodes == {"ffi_reader", "ipc_reader", "filter", "projection", "agg", "sort", "parquet_scan", "hash_join", "sort_merge_join", "broadcast_join",
+                     "shuffle_writer", "limit", "rename_columns", "union"}
+    exprs = {f for m, f in seen if m == "PhysicalExprNode"}
+    assert {"column", "literal", "bound_reference", "binary_expr", "agg_expr", "is_null_expr", "is_not_null_expr", "not_expr", "case_", "cast",
+            "try_cast", "sort", "negative", "in_list", "scalar_function", "like_expr", "sc_and_expr", "sc_or_expr", "string_starts_with_expr",
+            "string_ends_with_expr", "string_contains_expr"} <= exprs
+    reps = {f for m, f in seen if m == "PhysicalRepartition"}
+    assert reps == {"single_repartition", "hash_repartition", "round_robin_repartition", "range_repartition"}
+    assert {("AggExecNode", "mode"), ("FetchLimit", "offset"), ("FileScanExecConf", "projection"), ("ParquetScanExecNode", "fsResourceId"),
+            ("BroadcastJoinExecNode", "cached_build_hash_map_id"), ("BroadcastJoinExecNode", "is_null_aware_anti_join"), ("PartitionedFile", "range"),
+            ("FileRange", "end"), ("PhysicalRangeRepartition", "sort_expr") if "sort_expr" in MSG["PhysicalRangeRepartition"] else ("AggExecNode", "mode")} <= seen
+
+
+def test_decoded_values_mean_what_the_builders_were_given():
+    seen = set()
+    plan = P.agg(P.ffi_reader(T, "rid-7"), [P.col("a")], ["ka"], [P.agg_expr("MAX", [P.col("b")], L), P.agg_expr("AVG", [P.col("d")], pa.decimal128(11, 6))],
+                 ["m", "v"], ["PARTIAL", "PARTIAL"], supports_partial_skipping=True)
+    node = walk("PhysicalPlanNode", plan, seen)["agg"][0]
+    assert node["grouping_expr_name"] == ["ka"] and node["agg_expr_name"] == ["m", "v"]
+    modes = [x for v in node["mode"] for x in (v if isinstance(v, list) else [v])]
+    assert modes == [ENUM["AggMode"]["PARTIAL"]] * 2
+    assert node["supports_partial_skipping"] == [1]
+    fns = [a["agg_expr"][0]["agg_function"][0] for a in node["agg_expr"]]
+    assert fns == [ENUM["AggFunction"]["MAX"], ENUM["AggFunction"]["AVG"]]
+    reader = node["input"][0]["ffi_reader"][0]
+    assert reader["export_iter_provider_resource_id"] == ["rid-7"]
+    cols = reader["schema"][0]["columns"]
+    assert [c["name"][0] for c in cols] == T.names
+    assert "DECIMAL" in cols[3]["arrow_type"][0] and cols[3]["arrow_type"][0]["DECIMAL"][0]["whole"] == [7]
+    join = walk("PhysicalPlanNode", P.hash_join(pa.schema(list(T) + list(T)), P.ffi_reader(T, "l"), P.ffi_reader(T, "r"), [(P.col("a"), P.col("b"))],
+                                                "ANTI", "LEFT"), seen)["hash_join"][0]
+    assert join["join_type"] == [ENUM["JoinType"]["ANTI"]]
+    assert join["on"][0]["left"][0]["column"][0]["name"] == ["a"] and join["on"][0]["right"][0]["column"][0]["name"] == ["b"]
+    srt = walk("PhysicalPlanNode", P.sort(P.ffi_reader(T, "x"), [P.sort_expr(P.col("a"), False, True)], limit=9, offset=4), seen)["sort"][0]
+    key = srt["expr"][0]["sort"][0]
+    assert key.get("asc", [0]) == [0] and key["nulls_first"] == [1]
+    assert (srt["fetch_limit"][0]["limit"], srt["fetch_limit"][0]["offset"]) == ([9], [4])
