@@ -49,7 +49,7 @@ enum Op : uint16_t {
     OP_EQ, OP_NE, OP_LT, OP_LE, OP_GT, OP_GE, OP_NSEQ,
     OP_AND, OP_OR, OP_NOT, OP_ISNULL, OP_ISNOTNULL, OP_SELECT, OP_COALESCE, OP_CAST,
     OP_STARTS, OP_ENDS, OP_CONTAINS, OP_LIKE, OP_SUBSTR, OP_CHARLEN, OP_OCTLEN, OP_TRIM, OP_CASEXF,
-    OP_DATEPART, OP_TS_LOCAL_MS, OP_TIMEPART, OP_MS_TO_DAYS, OP_NULLIFZERO, OP_ISNAN, OP_NORMNAN, OP_CHECK_OVERFLOW, OP_MAKE_DECIMAL, OP_UNSCALED,
+    OP_DATEPART, OP_TS_LOCAL_MS, OP_TIMEPART, OP_MS_TO_DAYS, OP_ROUND, OP_NULLIFZERO, OP_ISNAN, OP_NORMNAN, OP_CHECK_OVERFLOW, OP_MAKE_DECIMAL, OP_UNSCALED,
     OP_MATH1, OP_POW, OP_HASH,
     OP_BITAND, OP_BITOR, OP_BITXOR, OP_SHL, OP_SHR,
     OP_OUT, OP_OUT_PRED, OP_FMT_OUT,
@@ -244,6 +244,22 @@ __device__ inline int32_t date_part(int64_t days, int part) {
     return 0;
 }
 
+// spark_round.rs:193-212: HALF_UP at 10^digits (digits > 0 digits dropped; <= 0: unchanged)
+__device__ inline __int128 round_half_up_i128(__int128 value, int digits) {
+    if (digits <= 0) return value;
+    if (digits > 38) return 0;
+    __int128 factor = 1;
+    for (int k = 0; k < digits; k++) factor *= 10;
+    const __int128 rem = value % factor, base = value - rem;
+    if (value >= 0) return rem * 2 >= factor ? base + factor : base;
+    return (-rem) * 2 >= factor ? base - factor : base;
+}
+// 10^n as llvm.powi computes it for the exponents that occur (exact for |n| <= 22; 1 / 10^|n| for negative n)
+__device__ inline double powi10(int n) {
+    double f = 1.0;
+    for (int k = 0; k < (n < 0 ? -n : n); k++) f *= 10.0;
+    return n < 0 ? 1.0 / f : f;
+}
 // E4 with a session time zone (spark_dates.rs:200-227,313-345): `v` in `unit` (0 s, 1 ms, 2 us, 3 ns, 4 = Date32 days) becomes
 // Timestamp(Millisecond) the way arrow's cast does it (division truncates toward zero), then the zone's UTC offset at that
 // instant is added.  The zone is a table in the constant pool: int64 n | int64 transition_second[n] | int32 offset[n + 1].
@@ -981,6 +997,44 @@ __global__ void __launch_bounds__(VM_THREADS) vm_kernel(VmParams p) {
                 case OP_DATEPART: {
                     bool v = VALID(ins.a);
                     RLO(ins.dst) = v ? (uint64_t)(int64_t)date_part((int64_t)RLO(ins.a), ins.aux) : 0;
+                    SETV(ins.dst, v);
+                    break;
+                }
+                case OP_ROUND: {   // Spark round(x, aux), HALF_UP (spark_round.rs:38-134); aux2 = scale of a decimal input
+                    bool v = VALID(ins.a);
+                    const int sc = ins.aux;
+                    uint64_t lo = RLO(ins.a);
+                    int64_t hi = HI ? RHI(ins.a) : 0;
+                    if (t == VT_DEC) {
+                        __int128 x = ((__int128)hi << 64) | (__int128)lo;
+                        const int diff = ins.aux2 - sc;   // digits of the stored scale that are rounded away
+                        if (diff >= 0) x = round_half_up_i128(x, diff);
+                        else
+                            for (int k = 0; k < -diff && k < 39; k++) x *= 10;   // the reference keeps the declared scale here (:69-75)
+                        lo = (uint64_t)x;
+                        hi = (int64_t)(x >> 64);
+                    } else if (t <= VT_I64) {
+                        const __int128 r = round_half_up_i128((__int128)(int64_t)lo, -sc);
+                        const int64_t w = t == VT_I64 ? (int64_t)r : t == VT_I32 ? (int64_t)(int32_t)r : t == VT_I16 ? (int64_t)(int16_t)r : (int64_t)(int8_t)r;
+                        lo = (uint64_t)w;
+                    } else if (t == VT_F64) {
+                        const double x = __longlong_as_double((int64_t)lo);
+                        if (!(isnan(x) || isinf(x))) {
+                            const double f = powi10(sc), y = x * f;
+                            lo = (uint64_t)__double_as_longlong((y >= 0.0 ? floor(y + 0.5) : ceil(y - 0.5)) / f);
+                        }
+                    } else if (t == VT_F32) {
+                        const float x = __int_as_float((int)(uint32_t)lo);
+                        if (!(isnan(x) || isinf(x))) {
+                            float f = 1.0f;
+                            for (int k = 0; k < (sc < 0 ? -sc : sc); k++) f *= 10.0f;
+                            if (sc < 0) f = 1.0f / f;
+                            const float y = x * f;
+                            lo = (uint64_t)(uint32_t)__float_as_int((y >= 0.0f ? floorf(y + 0.5f) : ceilf(y - 0.5f)) / f);
+                        }
+                    }
+                    RLO(ins.dst) = v ? lo : 0;
+                    if (HI) RHI(ins.dst) = v ? hi : 0;
                     SETV(ins.dst, v);
                     break;
                 }
@@ -1808,6 +1862,19 @@ struct Compiler {
             note_type(e.type);
             emit(OP_MAKE_DECIMAL, a.reg, a.reg, 0, 0, VT_I64, 0, e.type.precision);
             r = Val{a.reg, e.type};
+        } else if (f == "Spark_Round") {
+            // spark_round.rs:38-134: the scale is a literal integer; decimals keep their type, integers and floats theirs
+            AURON_CHECK(e.children.size() == 2 && e.children[1]->kind == E_LITERAL && !e.children[1]->lit.is_null &&
+                            (e.children[1]->lit.type.id == T_INT32 || e.children[1]->lit.type.id == T_INT64),
+                        "spark_round() scale must be a literal integer");
+            const int sc = (int)e.children[1]->lit.i;
+            Val a = gen(*e.children[0]);
+            const Vt vt = vt_of(a.type);
+            if (!(vt == VT_DEC || vt == VT_F32 || vt == VT_F64 || vt == VT_I16 || vt == VT_I32 || vt == VT_I64) || a.type.id == T_DATE32 ||
+                a.type.id == T_DATE64 || a.type.id == T_TIMESTAMP)
+                fail("spark_round() on " + a.type.str() + " is not native");
+            emit(OP_ROUND, a.reg, a.reg, 0, 0, vt, 0, sc, a.type.id == T_DECIMAL128 ? a.type.scale : 0);
+            r = Val{a.reg, a.type};
         } else if (f == "Spark_CheckOverflow") {
             Val a = gen(*e.children[0]);
             AURON_CHECK(a.type.id == T_DECIMAL128 && e.type.id == T_DECIMAL128, "CheckOverflow needs decimals");

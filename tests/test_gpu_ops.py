@@ -420,6 +420,57 @@ def test_time_zone_functions_vs_python_zoneinfo(zone):
         assert [c[i] for c in cols] == exp, (int(us[i]), x)
 
 
+def _round_f32_array_branch(x, sc):
+    x, f = np.float32(x), np.float32(1)
+    for _ in range(abs(sc)):
+        f = np.float32(f * np.float32(10))
+    if sc < 0:
+        f = np.float32(np.float32(1) / f)
+    y = np.float32(x * f)
+    r = np.floor(np.float32(y + np.float32(0.5))) if y >= 0 else np.ceil(np.float32(y - np.float32(0.5)))
+    return float(np.float32(np.float32(r) / f))
+
+
+def test_spark_round_goldens():
+    # datafusion-ext-functions/src/spark_round.rs:225-447 (HALF_UP; decimals keep precision and scale; integers round at negative scales)
+    I, D = pa.int32(), decimal.Decimal
+    t = pa.table({"d": pa.array([D("123.45"), D("-678.95"), None], type=pa.decimal128(10, 2)),
+                  "x": pa.array([123.45, -678.9, None]), "y": pa.array([1.2345, -2.3456, 0.5]), "z": pa.array([-0.5, -1.5, float("nan")]),
+                  "h": pa.array([31415, 31415, None], type=pa.int16()), "i": pa.array([314159265, -314159265, None], type=pa.int32()),
+                  "f": pa.array([3.1415, float("inf"), None], type=pa.float32()), "p": pa.array([math.pi, -math.pi, None]),
+                  "l": pa.array([D(31415926535897932), D(-31415926535897932), None], type=pa.decimal128(38, 0))})
+    rnd = lambda c, sc, ty: P.scalar_fn("Spark_Round", [P.col(c), P.lit(sc, I)], ty)
+    got = _eval(t, [rnd("d", 1, pa.decimal128(10, 2)), rnd("x", -1, pa.float64()), rnd("y", 2, pa.float64()), rnd("z", 0, pa.float64())],
+                ["d", "x", "y", "z"], [pa.decimal128(10, 2), pa.float64(), pa.float64(), pa.float64()])
+    assert got["d"].to_pylist() == [D("123.50"), D("-679.00"), None]                     # :225-245
+    assert got["x"].to_pylist() == [120.0, -680.0, None]                                 # :250-264
+    assert got["y"].to_pylist() == [1.23, -2.35, 0.5]                                    # :268-292
+    z = got["z"].to_pylist()
+    assert z[:2] == [-1.0, -2.0] and math.isnan(z[2])                                    # -0.5 -> -1 (HALF_UP), :297-306; NaN passes through
+    scales = list(range(-6, 7))
+    for col, ty, exp, tol in [
+            ("h", pa.int16(), [0, 0, 30000, 31000, 31400, 31420] + [31415] * 7, 0),                                                   # :309-327
+            ("i", pa.int32(), [314000000, 314200000, 314160000, 314159000, 314159300, 314159270] + [314159265] * 7, 0),                # :383-408
+            # :330-353 runs the scalar branch, which rounds a Float32 in f64 arithmetic (:146-151); a Float32 COLUMN takes the array
+            # branch in f32 arithmetic (:100-113), where 3.1415f * 1000f is exactly 3141.5 and rounds up: restated with numpy float32
+            ("f", pa.float32(), [_round_f32_array_branch(3.1415, sc) for sc in range(-6, 7)], 1e-7),
+            ("p", pa.float64(), [0.0] * 6 + [3.0, 3.1, 3.14, 3.142, 3.1416, 3.14159, 3.141593], 1e-9),                                # :356-380
+            # :410-447 up to scale 0; the golden runs the scalar branch, a COLUMN of decimals takes the array branch (:62-81), which for
+            # a scale above the stored one multiplies the unscaled value instead (the declared scale is kept): mirrored as is
+            ("l", pa.decimal128(38, 0), [31415926536000000, 31415926535900000, 31415926535900000, 31415926535898000, 31415926535897900,
+                                          31415926535897930, 31415926535897932] + [31415926535897932 * 10**k for k in range(1, 7)], 0)]:
+        g = _eval(t, [rnd(col, sc, ty) for sc in scales], [f"s{k}" for k in range(13)], [ty] * 13)
+        first = [g[f"s{k}"][0].as_py() for k in range(13)]
+        if tol:
+            assert all(abs(a - b) < tol for a, b in zip(first, exp)), (col, first)
+        else:
+            assert [int(v) for v in first] == exp, (col, first)
+        assert all(g[f"s{k}"][2].as_py() is None for k in range(13))
+        if col in ("i", "l"):      # negative values mirror (HALF_UP rounds away from zero)
+            assert [int(g[f"s{k}"][1].as_py()) for k in range(13)] == [-v for v in exp], col
+    assert math.isinf(_eval(t, [rnd("f", 2, pa.float32())], ["f"], [pa.float32()])["f"][1].as_py())
+
+
 def test_murmur3_expr_and_misc_functions():
     t = _random_table(2000, seed=11)
     got = _eval(t, [P.scalar_fn("Spark_Murmur3Hash", [P.col("i32"), P.col("s")], pa.int32()),
