@@ -254,6 +254,29 @@ __device__ inline __int128 round_half_up_i128(__int128 value, int digits) {
     if (value >= 0) return rem * 2 >= factor ? base + factor : base;
     return (-rem) * 2 >= factor ? base - factor : base;
 }
+// spark_bround.rs:219-247: HALF_EVEN at 10^digits
+__device__ inline __int128 round_half_even_i128(__int128 value, int digits) {
+    if (digits <= 0) return value;
+    if (digits > 38) return 0;
+    __int128 factor = 1;
+    for (int k = 0; k < digits; k++) factor *= 10;
+    const __int128 rem = value % factor, base = value - rem, twice = (rem < 0 ? -rem : rem) * 2;
+    if (twice > factor) return value >= 0 ? base + factor : base - factor;
+    if (twice < factor) return base;
+    if ((base / factor) % 2 == 0) return base;   // tie: the even multiple of `factor`
+    return value >= 0 ? base + factor : base - factor;
+}
+// spark_bround.rs:177-217 (x finite)
+__device__ inline double round_half_even_f64(double x) {
+    const double ax = fabs(x), f = floor(ax), diff = ax - f;
+    const double r = diff > 0.5 ? f + 1.0 : diff < 0.5 ? f : ((((long long)f) & 1) == 0 ? f : f + 1.0);
+    return copysign(r, x);
+}
+__device__ inline float round_half_even_f32(float x) {
+    const float ax = fabsf(x), f = floorf(ax), diff = ax - f;
+    const float r = diff > 0.5f ? f + 1.0f : diff < 0.5f ? f : ((((long long)f) & 1) == 0 ? f : f + 1.0f);
+    return copysignf(r, x);
+}
 // 10^n as llvm.powi computes it for the exponents that occur (exact for |n| <= 22; 1 / 10^|n| for negative n)
 __device__ inline double powi10(int n) {
     double f = 1.0;
@@ -1000,28 +1023,30 @@ __global__ void __launch_bounds__(VM_THREADS) vm_kernel(VmParams p) {
                     SETV(ins.dst, v);
                     break;
                 }
-                case OP_ROUND: {   // Spark round(x, aux), HALF_UP (spark_round.rs:38-134); aux2 = scale of a decimal input
+                case OP_ROUND: {   // Spark round / bround(x, aux): HALF_UP (spark_round.rs:38-134), flags = 1: HALF_EVEN (spark_bround.rs:38-134);
+                                   // aux2 = scale of a decimal input
                     bool v = VALID(ins.a);
                     const int sc = ins.aux;
+                    const bool even = ins.flags != 0;
                     uint64_t lo = RLO(ins.a);
                     int64_t hi = HI ? RHI(ins.a) : 0;
                     if (t == VT_DEC) {
                         __int128 x = ((__int128)hi << 64) | (__int128)lo;
                         const int diff = ins.aux2 - sc;   // digits of the stored scale that are rounded away
-                        if (diff >= 0) x = round_half_up_i128(x, diff);
+                        if (diff >= 0) x = even ? round_half_even_i128(x, diff) : round_half_up_i128(x, diff);
                         else
                             for (int k = 0; k < -diff && k < 39; k++) x *= 10;   // the reference keeps the declared scale here (:69-75)
                         lo = (uint64_t)x;
                         hi = (int64_t)(x >> 64);
                     } else if (t <= VT_I64) {
-                        const __int128 r = round_half_up_i128((__int128)(int64_t)lo, -sc);
+                        const __int128 r = even ? round_half_even_i128((__int128)(int64_t)lo, -sc) : round_half_up_i128((__int128)(int64_t)lo, -sc);
                         const int64_t w = t == VT_I64 ? (int64_t)r : t == VT_I32 ? (int64_t)(int32_t)r : t == VT_I16 ? (int64_t)(int16_t)r : (int64_t)(int8_t)r;
                         lo = (uint64_t)w;
                     } else if (t == VT_F64) {
                         const double x = __longlong_as_double((int64_t)lo);
                         if (!(isnan(x) || isinf(x))) {
                             const double f = powi10(sc), y = x * f;
-                            lo = (uint64_t)__double_as_longlong((y >= 0.0 ? floor(y + 0.5) : ceil(y - 0.5)) / f);
+                            lo = (uint64_t)__double_as_longlong((even ? round_half_even_f64(y) : (y >= 0.0 ? floor(y + 0.5) : ceil(y - 0.5))) / f);
                         }
                     } else if (t == VT_F32) {
                         const float x = __int_as_float((int)(uint32_t)lo);
@@ -1030,7 +1055,7 @@ __global__ void __launch_bounds__(VM_THREADS) vm_kernel(VmParams p) {
                             for (int k = 0; k < (sc < 0 ? -sc : sc); k++) f *= 10.0f;
                             if (sc < 0) f = 1.0f / f;
                             const float y = x * f;
-                            lo = (uint64_t)(uint32_t)__float_as_int((y >= 0.0f ? floorf(y + 0.5f) : ceilf(y - 0.5f)) / f);
+                            lo = (uint64_t)(uint32_t)__float_as_int((even ? round_half_even_f32(y) : (y >= 0.0f ? floorf(y + 0.5f) : ceilf(y - 0.5f))) / f);
                         }
                     }
                     RLO(ins.dst) = v ? lo : 0;
@@ -1862,18 +1887,18 @@ struct Compiler {
             note_type(e.type);
             emit(OP_MAKE_DECIMAL, a.reg, a.reg, 0, 0, VT_I64, 0, e.type.precision);
             r = Val{a.reg, e.type};
-        } else if (f == "Spark_Round") {
+        } else if (f == "Spark_Round" || f == "Spark_BRound") {
             // spark_round.rs:38-134: the scale is a literal integer; decimals keep their type, integers and floats theirs
             AURON_CHECK(e.children.size() == 2 && e.children[1]->kind == E_LITERAL && !e.children[1]->lit.is_null &&
                             (e.children[1]->lit.type.id == T_INT32 || e.children[1]->lit.type.id == T_INT64),
-                        "spark_round() scale must be a literal integer");
+                        "spark_round() / spark_bround() scale must be a literal integer");
             const int sc = (int)e.children[1]->lit.i;
             Val a = gen(*e.children[0]);
             const Vt vt = vt_of(a.type);
             if (!(vt == VT_DEC || vt == VT_F32 || vt == VT_F64 || vt == VT_I16 || vt == VT_I32 || vt == VT_I64) || a.type.id == T_DATE32 ||
                 a.type.id == T_DATE64 || a.type.id == T_TIMESTAMP)
                 fail("spark_round() on " + a.type.str() + " is not native");
-            emit(OP_ROUND, a.reg, a.reg, 0, 0, vt, 0, sc, a.type.id == T_DECIMAL128 ? a.type.scale : 0);
+            emit(OP_ROUND, a.reg, a.reg, 0, 0, vt, f == "Spark_BRound" ? 1 : 0, sc, a.type.id == T_DECIMAL128 ? a.type.scale : 0);
             r = Val{a.reg, a.type};
         } else if (f == "Spark_CheckOverflow") {
             Val a = gen(*e.children[0]);

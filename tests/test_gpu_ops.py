@@ -471,6 +471,34 @@ def test_spark_round_goldens():
     assert math.isinf(_eval(t, [rnd("f", 2, pa.float32())], ["f"], [pa.float32()])["f"][1].as_py())
 
 
+def test_spark_bround_goldens():
+    # datafusion-ext-functions/src/spark_bround.rs:256-513 (HALF_EVEN, "banker's rounding")
+    I, D = pa.int32(), decimal.Decimal
+    t = pa.table({"a": pa.array([1.5, 2.5, -0.5, -1.5, 0.5, 3.5, -2.5, -3.5]), "b": pa.array([125.0, 135.0, 145.0, 155.0, -35.0, None, 0.0, 1e300]),
+                  "c": pa.array([-0.35] + [None] * 7), "d": pa.array([D("123.45"), D("678.95"), D("-123.45"), D("-678.95")] + [None] * 4, type=pa.decimal128(10, 2)),
+                  "h": pa.array([31415] * 8, type=pa.int16()), "i": pa.array([314159265, -314159265] * 4, type=pa.int32()),
+                  "p": pa.array([math.pi] * 8), "l": pa.array([D(31415926535897932), D(-31415926535897932)] * 4, type=pa.decimal128(38, 0))})
+    br = lambda c, sc, ty: P.scalar_fn("Spark_BRound", [P.col(c), P.lit(sc, I)], ty)
+    F = pa.float64()
+    got = _eval(t, [br("a", 0, F), br("b", -1, F), br("c", 1, F), br("d", 1, pa.decimal128(10, 2))], ["a", "b", "c", "d"], [F, F, F, pa.decimal128(10, 2)])
+    assert got["a"].to_pylist() == [2.0, 2.0, 0.0, -2.0, 0.0, 4.0, -2.0, -4.0]          # :256-279, :487-498 (ties go to the even neighbour)
+    assert got["b"].to_pylist() == [120.0, 140.0, 140.0, 160.0, -40.0, None, 0.0, 1e300]   # :282-298
+    assert got["c"].to_pylist()[0] == -0.4
+    assert got["d"].to_pylist()[:4] == [D("123.40"), D("679.00"), D("-123.40"), D("-679.00")]   # :302-316 (12345 -> 12340: tie to even)
+    scales = list(range(-6, 7))
+    for col, ty, exp in [("h", pa.int16(), [0, 0, 30000, 31000, 31400, 31420] + [31415] * 7),                                          # :377-401
+                         ("i", pa.int32(), [314000000, 314200000, 314160000, 314159000, 314159300, 314159260] + [314159265] * 7),       # :404-430
+                         ("l", pa.decimal128(38, 0), [31415926536000000, 31415926535900000, 31415926535900000, 31415926535898000,
+                                                      31415926535897900, 31415926535897930, 31415926535897932])]:                       # :433-464 up to scale 0
+        g = _eval(t, [br(col, sc, ty) for sc in scales[:len(exp)]], [f"s{k}" for k in range(len(exp))], [ty] * len(exp))
+        assert [int(g[f"s{k}"][0].as_py()) for k in range(len(exp))] == exp, col
+        if col != "h":
+            assert [int(g[f"s{k}"][1].as_py()) for k in range(len(exp))] == [-v for v in exp], col
+    g = _eval(t, [br("p", sc, F) for sc in scales], [f"s{k}" for k in range(13)], [F] * 13)
+    exp = [0.0] * 6 + [3.0, 3.1, 3.14, 3.142, 3.1416, 3.14159, 3.141593]                 # :325-348
+    assert all(abs(g[f"s{k}"][0].as_py() - exp[k]) < 1e-9 for k in range(13))
+
+
 def test_murmur3_expr_and_misc_functions():
     t = _random_table(2000, seed=11)
     got = _eval(t, [P.scalar_fn("Spark_Murmur3Hash", [P.col("i32"), P.col("s")], pa.int32()),
