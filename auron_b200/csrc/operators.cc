@@ -607,7 +607,7 @@ BatchPtr AggExec::next(Task& t) {
 // ------------------------------------------------------------------------------------------ HashJoinExec
 HashJoinExec::HashJoinExec(OperatorPtr left, OperatorPtr right, std::vector<ExprPtr> lk, std::vector<ExprPtr> rk, int jt, int bs, const Schema& schema)
     : left_keys(std::move(lk)), right_keys(std::move(rk)), join_type(jt), build_side(bs) {
-    name = "HashJoinExec";
+    name = "BroadcastJoin";   // BroadcastJoinExec::name() for shuffled-hash and broadcast joins alike (broadcast_join_exec.rs:243)
     out_schema = schema;
     if (out_schema.fields.empty()) {   // derive: [left cols..., right cols...] (full_join.rs:137-140)
         for (auto& f : left->out_schema.fields) out_schema.fields.push_back(f);

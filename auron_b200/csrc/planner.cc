@@ -708,7 +708,6 @@ static OperatorPtr decode_join(Task& t, const uint8_t* b, size_t n, int kind /*0
     j->null_aware_anti = null_aware;
     j->cache_id = cache_id;
     if (kind == 1) j->name = "SortMergeJoinExec";
-    if (kind == 2) j->name = "BroadcastJoinExec";
     return OperatorPtr(j);
 }
 
