@@ -259,3 +259,87 @@ def sort_table_canonical(t: pa.Table) -> pa.Table:
         return t
     idx = pc.sort_indices(t, sort_keys=[(n, "ascending") for n in t.column_names], null_placement="at_start")
     return t.take(idx)
+
+
+# ---------------------------------------------------------------- expression functions (E4 / rounding)
+def spark_round(value, scale: int, kind: str, in_scale: int = 0, half_even: bool = False):
+    """spark_round / spark_bround on ONE column value (array branch: datafusion-ext-functions/src/spark_round.rs:62-132,
+    spark_bround.rs:59-131).  kind: 'decimal' (value = unscaled int, result = unscaled int at the same scale), 'int16/32/64',
+    'f32', 'f64'.  None stays None."""
+    if value is None:
+        return None
+
+    def int_round(v: int, digits: int) -> int:          # round_i128_half_up / round_i128_half_even with scale = -digits
+        if digits <= 0:
+            return v
+        factor = 10 ** digits
+        rem = abs(v) % factor * (1 if v >= 0 else -1)    # Rust `%` keeps the sign of the dividend
+        base = v - rem
+        twice = abs(rem) * 2
+        if half_even:
+            if twice > factor:
+                return base + factor if v >= 0 else base - factor
+            if twice < factor:
+                return base
+            q = abs(base) // factor
+            return base if q % 2 == 0 else (base + factor if v >= 0 else base - factor)
+        if twice >= factor:
+            return base + factor if v >= 0 else base - factor
+        return base
+
+    if kind == "decimal":
+        diff = in_scale - scale
+        return int_round(value, diff) if diff >= 0 else value * 10 ** (-diff)
+    if kind.startswith("int"):
+        bits = int(kind[3:])
+        r = int_round(int(value), -scale) & ((1 << bits) - 1)               # `as i16/i32/i64` wraps
+        return r - (1 << bits) if r >> (bits - 1) else r
+    ft = np.float32 if kind == "f32" else np.float64
+    x = ft(value)
+    if np.isnan(x) or np.isinf(x):
+        return float(x)
+    f = ft(1)
+    for _ in range(abs(scale)):                                             # powi: repeated multiplication, reciprocal for n < 0
+        f = ft(f * ft(10))
+    if scale < 0:
+        f = ft(ft(1) / f)
+    y = ft(x * f)
+    if half_even:
+        ax = abs(y)
+        fl = np.floor(ax)
+        d = ft(ax - fl)
+        r = fl + 1 if d > 0.5 else (fl if d < 0.5 else (fl if int(fl) % 2 == 0 else fl + 1))
+        r = np.copysign(ft(r), y)
+    else:
+        r = np.floor(ft(y + ft(0.5))) if y >= 0 else np.ceil(ft(y - ft(0.5)))
+    return float(ft(ft(r) / f))
+
+
+def spark_time_part(value, unit: str, which: str, zone: str | None = None):
+    """spark_hour / minute / second and the date parts with an optional session time zone (spark_dates.rs:200-345): `value` in
+    `unit` ('s', 'ms', 'us', 'ns', 'date32') is cast to Timestamp(ms) the way arrow does (division toward zero), shifted by the
+    zone's UTC offset at that instant (Python's zoneinfo reads the same tz database chrono-tz compiles in) and decomposed.
+    which: hour | minute | second | year | month | day | dayofweek | quarter."""
+    import datetime as dt
+    import zoneinfo
+    if value is None:
+        return None
+    v = int(value)
+    trunc = lambda a, b: abs(a) // b * (1 if a >= 0 else -1)
+    ms = {"s": v * 1000, "ms": v, "us": trunc(v, 1000), "ns": trunc(v, 1_000_000), "date32": v * 86_400_000}[unit]
+    if zone is not None:
+        try:
+            tz = zoneinfo.ZoneInfo(zone)
+            off = dt.datetime.fromtimestamp(ms // 1000, tz=dt.timezone.utc).astimezone(tz).utcoffset()
+            ms += int(off.total_seconds()) * 1000
+        except (zoneinfo.ZoneInfoNotFoundError, ValueError):
+            pass                                                            # a name chrono-tz cannot parse counts as no zone (:97-102)
+    if which in ("hour", "minute", "second"):
+        day_ms = ms % 86_400_000
+        return {"hour": day_ms // 3_600_000, "minute": day_ms % 3_600_000 // 60_000, "second": day_ms % 60_000 // 1000}[which]
+    if zone is None and unit != "date32":
+        days = trunc(ms, 86_400_000)                                        # arrow's cast to Date32 divides toward zero (unpinned)
+    else:
+        days = ms // 86_400_000                                             # ts_ms_to_local_date32 floors (:213-227)
+    d = dt.date(1970, 1, 1) + dt.timedelta(days=days)
+    return {"year": d.year, "month": d.month, "day": d.day, "dayofweek": d.isoweekday() % 7 + 1, "quarter": (d.month - 1) // 3 + 1}[which]

@@ -166,3 +166,53 @@ def test_agg_sum_count_vs_dict():
         exp[key] = (s + (0 if vm else vi), c + (0 if vm else 1))
     got = {r["k"]: (r["sum"] if r["sum"] is not None else 0, r["cnt"]) for r in t.to_pylist()}
     assert got == exp
+
+
+# datafusion-ext-functions/src/spark_round.rs:225-447 and spark_bround.rs:256-513
+def test_spark_round_and_bround_goldens():
+    R = oracle.spark_round
+    assert [R(v, 1, "decimal", in_scale=2) for v in (12345, -67895)] == [12350, -67900]                       # round.rs:225-245
+    assert [R(v, -1, "f64") for v in (123.45, -678.9)] == [120.0, -680.0]                                     # :250-264
+    assert [R(v, 2, "f64") for v in (1.2345, -2.3456, 0.5, -0.5, None)] == [1.23, -2.35, 0.5, -0.5, None]     # :268-292
+    assert R(-1.5, 0, "f64") == -2.0                                                                          # :297-306
+    scales = range(-6, 7)
+    assert [R(31415, s, "int16") for s in scales] == [0, 0, 30000, 31000, 31400, 31420] + [31415] * 7          # :309-327
+    assert [R(314159265, s, "int32") for s in scales] == [314000000, 314200000, 314160000, 314159000, 314159300, 314159270] + [314159265] * 7
+    pi = [0.0] * 6 + [3.0, 3.1, 3.14, 3.142, 3.1416, 3.14159, 3.141593]
+    assert all(abs(R(math.pi, s, "f64") - e) < 1e-9 for s, e in zip(scales, pi))                              # :356-380
+    long_pi = 31415926535897932
+    assert [R(long_pi, s, "decimal") for s in range(-6, 1)] == [31415926536000000, 31415926535900000, 31415926535900000, 31415926535898000,
+                                                               31415926535897900, 31415926535897930, long_pi]  # :410-447
+    B = lambda *a, **k: oracle.spark_round(*a, half_even=True, **k)
+    assert [B(v, 0, "f64") for v in (1.5, 2.5, -0.5, -1.5, 0.5)] == [2.0, 2.0, 0.0, -2.0, 0.0]                # bround.rs:256-279
+    assert [B(v, -1, "f64") for v in (125.0, 135.0, 145.0, 155.0)] == [120.0, 140.0, 140.0, 160.0]            # :282-298
+    assert [B(v, 1, "decimal", in_scale=2) for v in (12345, 67895)] == [12340, 67900]                         # :302-316
+    assert [B(31415, s, "int16") for s in scales] == [0, 0, 30000, 31000, 31400, 31420] + [31415] * 7          # :377-401
+    assert [B(314159265, s, "int32") for s in scales] == [314000000, 314200000, 314160000, 314159000, 314159300, 314159260] + [314159265] * 7
+    assert [B(long_pi, s, "decimal") for s in range(-6, 1)] == [31415926536000000, 31415926535900000, 31415926535900000, 31415926535898000,
+                                                               31415926535897900, 31415926535897930, long_pi]  # :433-464
+    assert [(B(v, s, "f64")) for v, s in ((2.5, 0), (3.5, 0), (-2.5, 0), (-3.5, 0), (-0.35, 1), (-35.0, -1))] == [2.0, 4.0, -2.0, -4.0, -0.4, -40.0]
+    assert all(abs(B(math.pi, s, "f64") - e) < 1e-9 for s, e in zip(scales, pi))                              # :325-348
+
+
+# datafusion-ext-functions/src/spark_dates.rs:661-952, 1077-1153
+def test_spark_time_parts_goldens():
+    import datetime as dt
+    T = oracle.spark_time_part
+    utc_ms = lambda *a: int(dt.datetime(*a, tzinfo=dt.timezone.utc).timestamp() * 1000)
+    hms = (1 * 3600 + 23 * 60 + 45) * 1000
+    assert [T(v, "ms", "hour") for v in (0, hms, None)] == [0, 1, None]                                       # :661-688
+    assert [T(v, "ms", "minute") for v in (0, hms)] == [0, 23] and [T(v, "ms", "second") for v in (0, hms)] == [0, 45]
+    assert [T(d, "date32", w) for d in (0, 1) for w in ("hour", "minute", "second")] == [0] * 6               # :691-711
+    assert (T(-1000, "ms", "hour"), T(-1000, "ms", "minute"), T(-1000, "ms", "second")) == (23, 59, 59)       # :746-764
+    assert T(0, "ms", "hour", "Asia/Shanghai") == 8                                                           # :784-802
+    assert (T(0, "ms", "minute", "Asia/Kolkata"), T(0, "ms", "second", "Asia/Kolkata")) == (30, 0)            # :835-881
+    assert T(0, "ms", "minute", "Asia/Kathmandu") == 30                                                       # :884-904
+    t1, t2 = utc_ms(2019, 3, 10, 6, 59, 59), utc_ms(2019, 3, 10, 7, 0, 0)                                     # :907-937
+    assert [T(t, "ms", w, "America/New_York") for t in (t1, t2) for w in ("minute", "second")] == [59, 59, 0, 0]
+    e = utc_ms(2021, 1, 4, 4, 30, 0)                                                                          # :1077-1110
+    assert [T(e, "ms", w, "America/New_York") for w in ("year", "month", "day", "dayofweek")] == [2021, 1, 3, 1]
+    assert T(utc_ms(2021, 4, 1, 3, 0, 0), "ms", "quarter", "America/New_York") == 1                           # :1113-1123
+    e = utc_ms(2021, 12, 31, 17, 0, 0)                                                                        # :1126-1153
+    assert [T(e, "ms", w, "Asia/Shanghai") for w in ("year", "month", "day", "quarter", "dayofweek")] == [2022, 1, 1, 1, 7]
+    assert T(0, "ms", "hour", "Mars/Olympus") == 0                                                            # unknown zone = none
