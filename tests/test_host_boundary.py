@@ -49,6 +49,52 @@ def test_jni_natives_against_the_mock_jvm_without_a_gpu():
     jvm.assert_clean()
 
 
+def _jni_function_table():
+    """JNINativeInterface_ in declaration order, generated from the structure of the JNI specification's "Interface Function
+    Table" (4 reserved slots, then the functions; the Call*Method families come as plain / V / A triples per result type)."""
+    types = ["Object", "Boolean", "Byte", "Char", "Short", "Int", "Long", "Float", "Double"]
+    prims = types[1:]
+    t = ["reserved0", "reserved1", "reserved2", "reserved3", "GetVersion", "DefineClass", "FindClass", "FromReflectedMethod", "FromReflectedField",
+         "ToReflectedMethod", "GetSuperclass", "IsAssignableFrom", "ToReflectedField", "Throw", "ThrowNew", "ExceptionOccurred", "ExceptionDescribe",
+         "ExceptionClear", "FatalError", "PushLocalFrame", "PopLocalFrame", "NewGlobalRef", "DeleteGlobalRef", "DeleteLocalRef", "IsSameObject",
+         "NewLocalRef", "EnsureLocalCapacity", "AllocObject", "NewObject", "NewObjectV", "NewObjectA", "GetObjectClass", "IsInstanceOf", "GetMethodID"]
+    calls = lambda prefix: [f"{prefix}{ty}Method{suffix}" for ty in types + ["Void"] for suffix in ("", "V", "A")]
+    t += calls("Call") + calls("CallNonvirtual")
+    t += ["GetFieldID"] + [f"Get{ty}Field" for ty in types] + [f"Set{ty}Field" for ty in types]
+    t += ["GetStaticMethodID"] + calls("CallStatic")
+    t += ["GetStaticFieldID"] + [f"GetStatic{ty}Field" for ty in types] + [f"SetStatic{ty}Field" for ty in types]
+    t += ["NewString", "GetStringLength", "GetStringChars", "ReleaseStringChars", "NewStringUTF", "GetStringUTFLength", "GetStringUTFChars",
+          "ReleaseStringUTFChars", "GetArrayLength", "NewObjectArray", "GetObjectArrayElement", "SetObjectArrayElement"]
+    t += [f"New{p}Array" for p in prims] + [f"Get{p}ArrayElements" for p in prims] + [f"Release{p}ArrayElements" for p in prims]
+    t += [f"Get{p}ArrayRegion" for p in prims] + [f"Set{p}ArrayRegion" for p in prims]
+    t += ["RegisterNatives", "UnregisterNatives", "MonitorEnter", "MonitorExit", "GetJavaVM", "GetStringRegion", "GetStringUTFRegion",
+          "GetPrimitiveArrayCritical", "ReleasePrimitiveArrayCritical", "GetStringCritical", "ReleaseStringCritical", "NewWeakGlobalRef",
+          "DeleteWeakGlobalRef", "ExceptionCheck", "NewDirectByteBuffer", "GetDirectBufferAddress", "GetDirectBufferCapacity", "GetObjectRefType",
+          "GetModule"]
+    return {name: i for i, name in enumerate(t)}
+
+
+def test_jni_function_indices_follow_the_specification_table():
+    # no jni.h in this image: jni_face.cc (product) and tests/jni_mock/mock_jvm.cc address JNIEnv functions by slot number.  Both are
+    # checked here against the table generated from the specification's declaration order, so that a wrong slot cannot hide in an
+    # agreement between the two files.
+    table = _jni_function_table()
+    assert len(table) == 234 and table["GetVersion"] == 4 and table["ExceptionCheck"] == 228 and table["GetModule"] == 233
+    face = open(os.path.join(ROOT, "auron_b200", "csrc", "jni_face.cc")).read()
+    used = re.findall(r"\bFN_(\w+) = (\d+)", face)
+    assert len(used) >= 30
+    for name, slot in used:
+        assert table[name] == int(slot), f"jni_face.cc: {name} is slot {table[name]}, not {slot}"
+    vm = dict(re.findall(r"\bVM_(\w+) = (\d+)", face))
+    assert vm == {"DetachCurrentThread": "5", "GetEnv": "6", "AttachCurrentThreadAsDaemon": "7"}   # JNIInvokeInterface_: 3 reserved, Destroy, Attach, ...
+    mock = open(os.path.join(ROOT, "tests", "jni_mock", "mock_jvm.cc")).read()
+    slots = re.findall(r"g_table\[(\d+)\] = \(void\*\)f_(\w+);", mock)
+    assert len(slots) >= 30
+    for slot, name in slots:
+        assert table[name] == int(slot), f"mock_jvm.cc: {name} is slot {table[name]}, not {slot}"
+    assert {name for name, _ in used} == {name for _, name in slots}      # the mock provides exactly what the product uses
+
+
 def test_time_zone_tables_match_python_zoneinfo():
     # the UTC-offset tables the device searches (tzdb.cc: TZif transitions + the footer's POSIX rule expanded to 2200) against
     # Python's independent reader of the same tz database, 1875 .. 2191
