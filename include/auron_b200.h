@@ -134,6 +134,12 @@ int auron_b200_k_partition_ids(const struct ArrowArray* batch, const struct Arro
  * date/time functions that take a session time zone (spark_dates.rs:93-110,200-227, chrono-tz in the reference).
  * Returns 0 and fills *offset, or -1 when `zone` is not an IANA zone name.  Host only: usable without a GPU. */
 int auron_b200_tz_offset(const char* zone, int64_t utc_second, int32_t* offset);
+/* What the engine's Parquet metadata reader sees in the local file `path`, as JSON: footer (schema elements, row groups, column
+ * chunks with codec / sizes / offsets / statistics as hex) plus, per chunk, the walk of its page headers (page counts, value
+ * counts, encodings; SNAPPY bodies are run through the engine's block decoder).  The reference reads the same structures with
+ * the `parquet` crate (parquet_exec.rs:175-197).  Returns the JSON length (the text is truncated to cap - 1 bytes), or -1 with the
+ * error message in `out`.  Host only: usable without a GPU. */
+int64_t auron_b200_parquet_describe(const char* path, char* out, int64_t cap);
 /* number of kernels this library has launched in the calling process (bench.py "gpu_launches") */
 int64_t auron_b200_kernel_launches(void);
 /* micro-benchmark hook: runs `iters` launches of a named kernel over device-resident resource data and

@@ -49,6 +49,86 @@ def test_jni_natives_against_the_mock_jvm_without_a_gpu():
     jvm.assert_clean()
 
 
+@pytest.mark.parametrize("compression,version,dict_", [("NONE", "1.0", True), ("SNAPPY", "1.0", True), ("SNAPPY", "2.0", True), ("SNAPPY", "1.0", False),
+                                                       ("ZSTD", "2.0", True)])
+def test_parquet_metadata_reader_against_pyarrow(tmp_path, compression, version, dict_):
+    # P1's host half (parquet_meta.cc: Thrift compact protocol footer + page headers, Snappy block decoder) pinned on the CPU against
+    # Arrow C++'s reader of the same file: every footer field the scan uses, the page chain of every chunk tiling it exactly, page
+    # value counts adding up, and every SNAPPY page body decoding to its declared size with the engine's own decoder
+    import ctypes as C
+    import decimal
+    import json
+    import numpy as np
+    import pyarrow.parquet as pq
+    rng = np.random.default_rng(3)
+    n = 60_000
+    t = pa.table({"i": pa.array(rng.integers(0, 500, n), type=pa.int32(), mask=rng.random(n) < 0.05),
+                  "l": pa.array(rng.integers(-2**40, 2**40, n), type=pa.int64()),
+                  "s": pa.array([f"v{int(x) % 300}" for x in rng.integers(0, 10**6, n)], mask=rng.random(n) < 0.1),
+                  "d": pa.array([decimal.Decimal(int(x)) / 100 for x in rng.integers(0, 10**6, n)], type=pa.decimal128(7, 2)),
+                  "f": pa.array(rng.standard_normal(n)), "b": pa.array(rng.random(n) < 0.5),
+                  "req": pa.array(np.arange(n, dtype=np.int64))},
+                 schema=pa.schema([("i", pa.int32()), ("l", pa.int64()), ("s", pa.string()), ("d", pa.decimal128(7, 2)), ("f", pa.float64()),
+                                   ("b", pa.bool_()), pa.field("req", pa.int64(), nullable=False)]))
+    path = str(tmp_path / "m.parquet")
+    pq.write_table(t, path, compression=compression, data_page_version=version, use_dictionary=dict_, row_group_size=25_000, data_page_size=16 * 1024,
+                   store_decimal_as_integer=True)
+    L = runtime.lib()
+    L.auron_b200_parquet_describe.restype = C.c_int64
+    L.auron_b200_parquet_describe.argtypes = [C.c_char_p, C.c_char_p, C.c_int64]
+    buf = C.create_string_buffer(4 << 20)
+    size = L.auron_b200_parquet_describe(path.encode(), buf, len(buf))
+    assert size > 0, buf.value
+    d = json.loads(buf.value.decode())
+    md = pq.ParquetFile(path).metadata
+    assert d["num_rows"] == md.num_rows == n and len(d["row_groups"]) == md.num_row_groups == 3
+    assert d["created_by"] == md.created_by
+    leaves = [e for e in d["schema"] if e["num_children"] == 0]
+    assert [e["name"] for e in leaves] == t.column_names
+    phys = {"BOOLEAN": 0, "INT32": 1, "INT64": 2, "INT96": 3, "FLOAT": 4, "DOUBLE": 5, "BYTE_ARRAY": 6, "FIXED_LEN_BYTE_ARRAY": 7}
+    codecs = {"UNCOMPRESSED": 0, "SNAPPY": 1, "GZIP": 2, "LZ4": 5, "ZSTD": 6, "LZ4_RAW": 7}
+    assert [e["repetition"] for e in leaves] == [1] * 6 + [0]                       # OPTIONAL ... REQUIRED
+    assert (leaves[3]["precision"], leaves[3]["scale"]) == (7, 2)                    # decimal(7,2) stored as INT32
+    snappy_pages = 0
+    for g, rg in enumerate(d["row_groups"]):
+        ref_rg = md.row_group(g)
+        assert rg["num_rows"] == ref_rg.num_rows
+        for c, cm in enumerate(rg["columns"]):
+            ref = ref_rg.column(c)
+            assert cm["path"] == ref.path_in_schema
+            assert cm["type"] == phys[ref.physical_type] and cm["codec"] == codecs[ref.compression]
+            assert cm["num_values"] == ref.num_values == cm["page_values"]           # the data pages add up to the chunk
+            assert cm["total_compressed"] == ref.total_compressed_size and cm["total_uncompressed"] == ref.total_uncompressed_size
+            assert cm["pages_uncompressed"] == ref.total_uncompressed_size           # page headers + uncompressed bodies
+            assert cm["data_page_offset"] == ref.data_page_offset
+            assert (cm["dictionary_page_offset"] > 0) == ref.has_dictionary_page == (cm["dictionary_pages"] == 1)
+            assert cm["data_pages"] >= 1
+            st = ref.statistics
+            if st is not None and st.has_null_count:
+                assert cm["null_count"] == st.null_count
+            if st is not None and st.has_min_max and ref.physical_type in ("INT32", "INT64"):
+                width = 4 if ref.physical_type == "INT32" else 8
+                lo, hi = (int.from_bytes(bytes.fromhex(cm[k]), "little", signed=True) for k in ("min", "max"))
+                assert len(cm["min"]) == 2 * width
+                if ref.path_in_schema == "d":
+                    assert (decimal.Decimal(lo) / 100, decimal.Decimal(hi) / 100) == (st.min, st.max)
+                else:
+                    assert (lo, hi) == (st.min, st.max)
+            if ref.path_in_schema == "s" and st is not None and st.has_min_max:
+                assert bytes.fromhex(cm["min"]).decode() == st.min and bytes.fromhex(cm["max"]).decode() == st.max
+            snappy_pages += cm["snappy_pages_decompressed"]
+    assert (snappy_pages > 0) == (compression == "SNAPPY")
+    # a damaged footer is an error message, not a crash
+    raw = bytearray(open(path, "rb").read())
+    raw[-30] ^= 0xFF
+    raw[-40] ^= 0xFF
+    bad = str(tmp_path / "bad.parquet")
+    open(bad, "wb").write(bytes(raw))
+    rc = L.auron_b200_parquet_describe(bad.encode(), buf, len(buf))
+    assert rc == -1 or rc > 0                                                      # rejected with a message, or parsed: never a crash
+    assert L.auron_b200_parquet_describe(str(tmp_path / "missing.parquet").encode(), buf, len(buf)) == -1 and b"cannot open" in buf.value
+
+
 def _jni_function_table():
     """JNINativeInterface_ in declaration order, generated from the structure of the JNI specification's "Interface Function
     Table" (4 reserved slots, then the functions; the Call*Method families come as plain / V / A triples per result type)."""
