@@ -287,7 +287,7 @@ static void export_column(Ctx& ctx, const Column& c, ArrowArray* out, const std:
     out->buffers = p->buffers.data();
 }
 
-void export_batch(Ctx& ctx, const Batch& b, const Schema& schema, ArrowArray* out) {
+void export_batch(Ctx& ctx, const Batch& b, const Schema& schema, ArrowArray* out, size_t pinned_from) {
     AURON_CHECK(b.cols.size() == schema.fields.size(), "export: batch/schema column count mismatch");
     auto* p = new ArrayPriv;
     memset(out, 0, sizeof(*out));
@@ -301,7 +301,7 @@ void export_batch(Ctx& ctx, const Batch& b, const Schema& schema, ArrowArray* ou
     auto block = std::make_shared<PinnedBlock>();
     size_t total = 64;
     for (auto& c : b.cols) total += export_bytes(*c);
-    if (total >= (1u << 20)) {
+    if (total >= pinned_from) {
         block->p = pinned_pool().get(total, &block->cap);
         block->pinned = true;
     } else {

@@ -43,6 +43,7 @@ void schema_to_arrow(const Schema& s, ArrowSchema* out);        // caller releas
 // H2D: copies the buffers of a struct array (one child per column) into HBM.  Does NOT release `arr`.
 BatchPtr import_batch(Ctx& ctx, const ArrowArray* arr, const Schema& schema);
 // D2H: materialises host Arrow buffers (malloc'd, freed by the release callback).
-void export_batch(Ctx& ctx, const Batch& b, const Schema& schema, ArrowArray* out);
+// Results of at least `pinned_from` bytes land in a block of the pinned pool (blocks are at least 64 MB), smaller ones in plain memory.
+void export_batch(Ctx& ctx, const Batch& b, const Schema& schema, ArrowArray* out, size_t pinned_from = 1u << 20);
 
 }  // namespace auron

@@ -508,7 +508,7 @@ void AggExec::spill(Task& t) {
         bytes += batch_device_bytes(*piece);
         ArrowArray a;
         memset(&a, 0, sizeof(a));
-        export_batch(t.ctx, *piece, spill_schema, &a);
+        export_batch(t.ctx, *piece, spill_schema, &a, (size_t)64 << 20);   // a pooled pinned block is >= 64 MB: only pieces that fill one
         spilled[(size_t)b].push_back(a);
     }
     metrics.add("mem_spill_count", 1);
