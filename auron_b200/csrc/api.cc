@@ -1,6 +1,7 @@
 // api.cc -- the extern "C" boundary (include/auron_b200.h).  Never throws across the ABI: every entry
 // point converts engine errors to a return code + thread-local message, the way the reference converts
 // Rust errors/panics into a Java exception and a false/0 return (auron/src/lib.rs:30-82, rt.rs:205-236).
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstring>
@@ -136,6 +137,36 @@ int auron_b200_metrics_walk(auron_task* task, auron_metric_node_fn enter, auron_
     AURON_CHECK(task && task->task && task->task->root && enter && fn, "null task or callback");
     walk_metric_nodes(*task->task->root, 0, 0, enter, fn, user);
     return 0;
+    API_GUARD_END(-1)
+}
+
+static void explain_op(const Operator& op, std::string& o) {
+    o += "{\"op\":" + json_quote(op.name) + ",\"schema\":[";
+    for (size_t i = 0; i < op.out_schema.fields.size(); i++)
+        o += std::string(i ? "," : "") + "[" + json_quote(op.out_schema.fields[i].name) + "," + json_quote(op.out_schema.fields[i].type.str()) + "]";
+    o += "]";
+    const std::string attrs = op.describe();
+    if (!attrs.empty()) o += "," + attrs;
+    o += ",\"children\":[";
+    for (size_t i = 0; i < op.children.size(); i++) {
+        if (i) o += ",";
+        explain_op(*op.children[i], o);
+    }
+    o += "]}";
+}
+int64_t auron_b200_explain(const uint8_t* task_definition, size_t len, char* out, int64_t cap) {
+    API_GUARD_BEGIN
+    std::unique_ptr<Task> t = create_task(task_definition, len, nullptr, -1);   // device -1: decode only, nothing is launched
+    std::string o = "{\"stage_id\":" + std::to_string(t->stage_id) + ",\"partition_id\":" + std::to_string(t->partition_id) + ",\"task_id\":" +
+                    std::to_string(t->task_id) + ",\"plan\":";
+    explain_op(*t->root, o);
+    o += "}";
+    if (out && cap > 0) {
+        const size_t n = std::min<size_t>(o.size(), (size_t)cap - 1);
+        memcpy(out, o.data(), n);
+        out[n] = 0;
+    }
+    return (int64_t)o.size();
     API_GUARD_END(-1)
 }
 

@@ -59,6 +59,8 @@ struct Operator {
     MetricSet metrics;
     virtual ~Operator() = default;
     virtual BatchPtr next(Task& t) = 0;          // nullptr at end of stream
+    // operator-specific attributes as JSON members (`"k":v,...`, no braces) for auron_b200_explain; "" = none
+    virtual std::string describe() const { return ""; }
     virtual SelBatch next_sel(Task& t) {         // default: no pending selection
         SelBatch s;
         s.batch = next(t);
@@ -94,6 +96,9 @@ void drop_device_file(const std::string& path);
 void put_host_file(const std::string& path, const uint8_t* bytes, size_t len);
 void drop_host_file(const std::string& path);
 
+// expression tree as text, e.g. `Gt(col(a), lit(int32:5))` (plan explain / error messages)
+std::string expr_to_string(const Expr& e);
+std::string json_quote(const std::string& s);
 // planner: TaskDefinition bytes -> Task (operator tree)
 std::unique_ptr<Task> create_task(const uint8_t* task_def, size_t len, const auron_callbacks* cb, int device);
 

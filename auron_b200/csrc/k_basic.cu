@@ -34,6 +34,7 @@ std::string DType::str() const {
 }
 
 Ctx::Ctx(int dev) : device(dev) {
+    if (dev < 0) return;   // plan-only context (auron_b200_explain): no stream, nothing may be launched on it
     CUDA_OK(cudaSetDevice(dev));
     CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));

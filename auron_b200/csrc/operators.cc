@@ -29,6 +29,105 @@ std::string Task::conf(const char* key, const char* env, const char* dflt) const
     return dflt ? dflt : "";
 }
 
+// ------------------------------------------------------------------------------------------ explain
+std::string json_quote(const std::string& s) {
+    std::string o = "\"";
+    for (char c : s) {
+        if (c == '"' || c == '\\') o.push_back('\\');
+        if ((unsigned char)c < 0x20) o += ' ';
+        else o.push_back(c);
+    }
+    return o + "\"";
+}
+static std::string lit_to_string(const Literal& l) {
+    if (l.is_null) return "lit(" + l.type.str() + ":NULL)";
+    std::string v;
+    switch (l.type.id) {
+        case T_FLOAT32: case T_FLOAT64: {
+            char buf[64];
+            snprintf(buf, sizeof(buf), "%.17g", l.d);
+            v = buf;
+            break;
+        }
+        case T_UTF8: case T_BINARY: v = "'" + l.s + "'"; break;
+        case T_DECIMAL128: {   // unscaled value
+            unsigned __int128 mag = ((unsigned __int128)(uint64_t)l.hi << 64) | l.lo;
+            const bool neg = l.hi < 0;
+            if (neg) mag = ~mag + 1;
+            std::string d;
+            do {
+                d.insert(d.begin(), (char)('0' + (int)(mag % 10)));
+                mag /= 10;
+            } while (mag);
+            v = (neg ? "-" : "") + d;
+            break;
+        }
+        default: v = std::to_string(l.i);
+    }
+    return "lit(" + l.type.str() + ":" + v + ")";
+}
+std::string expr_to_string(const Expr& e) {
+    auto args = [&](size_t from = 0) {
+        std::string a;
+        for (size_t i = from; i < e.children.size(); i++) a += (i > from ? ", " : "") + expr_to_string(*e.children[i]);
+        return a;
+    };
+    switch (e.kind) {
+        case E_COLUMN: return e.index >= 0 ? "col(#" + std::to_string(e.index) + ")" : "col(" + e.name + ")";
+        case E_LITERAL: return lit_to_string(e.lit);
+        case E_BINARY: return e.op + "(" + args() + ")";
+        case E_NOT: return "Not(" + args() + ")";
+        case E_IS_NULL: return "IsNull(" + args() + ")";
+        case E_IS_NOT_NULL: return "IsNotNull(" + args() + ")";
+        case E_NEGATIVE: return "Negative(" + args() + ")";
+        case E_CASE: return std::string("Case") + (e.has_case_expr ? "[expr]" : "") + (e.has_else ? "[else]" : "") + "(" + args() + ")";
+        case E_CAST: return "Cast(" + args() + " AS " + e.type.str() + ")";
+        case E_TRY_CAST: return "TryCast(" + args() + " AS " + e.type.str() + ")";
+        case E_IN_LIST: return std::string(e.negated ? "NotIn(" : "In(") + args() + ")";
+        case E_SCALAR_FN: return e.name + "(" + args() + ") -> " + e.type.str();
+        case E_LIKE: return std::string(e.negated ? "NotLike" : "Like") + (e.case_insensitive ? "[i](" : "(") + args() + ")";
+        case E_STARTS_WITH: return "StartsWith(" + args() + ", '" + e.lit.s + "')";
+        case E_ENDS_WITH: return "EndsWith(" + args() + ", '" + e.lit.s + "')";
+        case E_CONTAINS: return "Contains(" + args() + ", '" + e.lit.s + "')";
+        case E_SC_AND: return "SCAnd(" + args() + ")";
+        case E_SC_OR: return "SCOr(" + args() + ")";
+    }
+    return "?";
+}
+static std::string exprs_json(const std::vector<ExprPtr>& es) {
+    std::string o = "[";
+    for (size_t i = 0; i < es.size(); i++) o += (i ? "," : "") + json_quote(expr_to_string(*es[i]));
+    return o + "]";
+}
+
+std::string FFIReaderExec::describe() const { return "\"resource_id\":" + json_quote(resource_id); }
+std::string FilterExec::describe() const { return "\"predicates\":" + exprs_json(predicates); }
+std::string ProjectExec::describe() const { return "\"exprs\":" + exprs_json(exprs); }
+std::string AggExec::describe() const {
+    static const char* fn_names[] = {"MIN", "MAX", "SUM", "AVG", "COUNT", "?", "?", "FIRST", "FIRST_IGNORES_NULL"};
+    static const char* mode_names[] = {"PARTIAL", "PARTIAL_MERGE", "FINAL"};
+    std::string o = "\"grouping\":" + exprs_json(group_exprs) + ",\"aggs\":[";
+    for (size_t i = 0; i < aggs.size(); i++) {
+        const auto& a = aggs[i];
+        o += std::string(i ? "," : "") + "{\"fn\":\"" + (a.fn >= 0 && a.fn <= 8 ? fn_names[a.fn] : "?") + "\",\"mode\":\"" +
+             (a.mode >= 0 && a.mode <= 2 ? mode_names[a.mode] : "?") + "\",\"args\":" + exprs_json(a.children) + ",\"return_type\":" + json_quote(a.return_type.str()) + "}";
+    }
+    return o + "]";
+}
+std::string HashJoinExec::describe() const {
+    static const char* jt[] = {"INNER", "LEFT", "RIGHT", "FULL", "SEMI", "ANTI", "EXISTENCE"};
+    return std::string("\"join_type\":\"") + (join_type >= 0 && join_type <= 6 ? jt[join_type] : "?") + "\",\"build_side\":\"" +
+           (build_side == SIDE_LEFT ? "LEFT" : "RIGHT") + "\",\"left_keys\":" + exprs_json(left_keys) + ",\"right_keys\":" + exprs_json(right_keys) +
+           ",\"cached_build_hash_map_id\":" + json_quote(cache_id) + ",\"null_aware_anti\":" + (null_aware_anti ? "true" : "false");
+}
+std::string SortExec::describe() const {
+    std::string o = "\"keys\":[";
+    for (size_t i = 0; i < keys.size(); i++)
+        o += (i ? "," : "") + json_quote(expr_to_string(*keys[i].expr) + (keys[i].asc ? " ASC" : " DESC") + (keys[i].nulls_first ? " NULLS FIRST" : " NULLS LAST"));
+    return o + "],\"limit\":" + std::to_string(limit) + ",\"offset\":" + std::to_string(offset);
+}
+std::string LimitExec::describe() const { return "\"limit\":" + std::to_string(limit) + ",\"offset\":" + std::to_string(offset); }
+
 // ------------------------------------------------------------------------------------------ resources
 struct DevResource {
     std::vector<BatchPtr> batches;

@@ -18,6 +18,7 @@ struct FFIReaderExec : Operator {
     std::vector<BatchPtr> dev_batches;
     size_t dev_pos = 0;
     FFIReaderExec(const Schema& schema, const std::string& id);
+    std::string describe() const override;
     BatchPtr next(Task& t) override;
 };
 
@@ -26,6 +27,7 @@ struct FilterExec : Operator {
     std::vector<ExprPtr> predicates;
     VmProgram prog;
     FilterExec(OperatorPtr input, std::vector<ExprPtr> preds);
+    std::string describe() const override;
     BatchPtr next(Task& t) override;
     SelBatch next_sel(Task& t) override;
 };
@@ -38,6 +40,7 @@ struct ProjectExec : Operator {
     VmProgram prog;
     bool has_prog = false;
     ProjectExec(OperatorPtr input, std::vector<ExprPtr> exprs, std::vector<std::string> names, std::vector<DType> types);
+    std::string describe() const override;
     BatchPtr next(Task& t) override;
 };
 
@@ -78,6 +81,7 @@ struct AggExec : Operator {
     int out_bucket = 0;
     AggExec(OperatorPtr input, std::vector<ExprPtr> group_exprs, std::vector<std::string> group_names, std::vector<AggExprSpec> aggs);
     ~AggExec() override;
+    std::string describe() const override;
     BatchPtr next(Task& t) override;
 
    private:
@@ -102,6 +106,7 @@ struct HashJoinExec : Operator {
     std::shared_ptr<JoinTable> table;
     Buf matched_build;
     HashJoinExec(OperatorPtr left, OperatorPtr right, std::vector<ExprPtr> lk, std::vector<ExprPtr> rk, int join_type, int build_side, const Schema& schema);
+    std::string describe() const override;
     BatchPtr next(Task& t) override;
 
    private:
@@ -123,6 +128,7 @@ struct SortExec : Operator {
     int64_t limit = -1, offset = 0;
     bool done = false;
     SortExec(OperatorPtr input, std::vector<SortExprSpec> keys, int64_t limit, int64_t offset);
+    std::string describe() const override;
     BatchPtr next(Task& t) override;
 };
 
@@ -130,6 +136,7 @@ struct SortExec : Operator {
 struct LimitExec : Operator {
     int64_t limit, offset, seen = 0, emitted = 0;
     LimitExec(OperatorPtr input, int64_t limit, int64_t offset);
+    std::string describe() const override;
     BatchPtr next(Task& t) override;
 };
 

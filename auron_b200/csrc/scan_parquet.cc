@@ -118,6 +118,15 @@ struct LeafColumn {
 };
 
 struct ParquetScanExec : Operator {
+    std::string describe() const override {
+        std::string o = "\"fs_resource_id\":" + json_quote(fs_id) + ",\"projection\":[";
+        for (size_t i = 0; i < projection.size(); i++) o += (i ? "," : "") + std::to_string(projection[i]);
+        o += "],\"files\":[";
+        for (size_t i = 0; i < files.size(); i++)
+            o += std::string(i ? "," : "") + "{\"path\":" + json_quote(files[i].path) + ",\"size\":" + std::to_string(files[i].size) + ",\"range\":[" +
+                 std::to_string(files[i].range_start) + "," + std::to_string(files[i].range_end) + "]}";
+        return o + "]";
+    }
     std::vector<PqFileSpec> files;
     Schema table_schema;
     std::vector<int> projection;

@@ -224,6 +224,7 @@ uint64_t read_varint(const uint8_t* p, int64_t n, int64_t* pos) {   // io/mod.rs
 
 struct IpcReaderExec : Operator {
     std::string resource_id;
+    std::string describe() const override { return "\"resource_id\":" + json_quote(resource_id); }
     bool done = false;
     struct Block {
         std::string path;

@@ -107,6 +107,17 @@ struct ShuffleWriterExec : Operator {
     int64_t rows_so_far = 0;
     bool host_lz4 = getenv("AURON_HOST_LZ4") != nullptr;   // AURON_HOST_LZ4=1: compress LZ4 blocks with liblz4 on the host cores
 
+    std::string describe() const override {
+        static const char* kinds[] = {"?", "single", "hash", "round_robin", "range"};
+        std::string o = std::string("\"partitioning\":\"") + (kind >= 1 && kind <= 4 ? kinds[kind] : "?") + "\",\"partition_count\":" + std::to_string(num_parts) +
+                        ",\"data_file\":" + json_quote(data_file) + ",\"index_file\":" + json_quote(index_file) + ",\"codec\":\"" + (zstd ? "zstd" : "lz4") + "\",\"exprs\":[";
+        for (size_t i = 0; i < hash_exprs.size(); i++) o += (i ? "," : "") + json_quote(expr_to_string(*hash_exprs[i]));
+        for (size_t i = 0; i < range_keys.size(); i++)
+            o += (i ? "," : "") + json_quote(expr_to_string(*range_keys[i].expr) + (range_keys[i].asc ? " ASC" : " DESC") + (range_keys[i].nulls_first ? " NULLS FIRST" : " NULLS LAST"));
+        o += "],\"range_bound_rows\":[";
+        for (size_t i = 0; i < range_bounds_host.size(); i++) o += (i ? "," : "") + std::to_string(range_bounds_host[i].len);
+        return o + "]";
+    }
     ~ShuffleWriterExec() override {
         for (auto& c : chunks)
             if (c.pinned_cap) pinned_pool().put(c.bytes, c.pinned_cap);

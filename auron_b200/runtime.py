@@ -234,6 +234,20 @@ class Task:
             pass
 
 
+def explain(task_definition: bytes) -> dict:
+    """The operator tree the engine's planner builds for `task_definition`, decoded on no device (auron_b200_explain)."""
+    import json
+    L = lib()
+    L.auron_b200_explain.restype = C.c_int64
+    L.auron_b200_explain.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int64]
+    n = L.auron_b200_explain(task_definition, len(task_definition), None, 0)
+    if n < 0:
+        raise AuronError(_err())
+    buf = C.create_string_buffer(int(n) + 1)
+    L.auron_b200_explain(task_definition, len(task_definition), buf, len(buf))
+    return json.loads(buf.value.decode())
+
+
 def run_task(task_definition: bytes, inputs: dict[str, Iterable[pa.RecordBatch]] | None = None, device: int = 0, read_fully=None,
              shuffle_blocks: dict[str, Iterable] | None = None) -> pa.Table:
     """Execute a TaskDefinition and collect its output stream."""

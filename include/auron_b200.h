@@ -130,6 +130,12 @@ int auron_b200_k_hash(const struct ArrowArray* batch, const struct ArrowSchema* 
 /* evaluate_partition_ids (datafusion-ext-plans/src/shuffle/mod.rs:163-188) -> int32 column */
 int auron_b200_k_partition_ids(const struct ArrowArray* batch, const struct ArrowSchema* schema, const int32_t* cols, int32_t ncols,
                                int32_t num_partitions, struct ArrowArray* out, struct ArrowSchema* out_schema, int device);
+/* Decodes a TaskDefinition exactly as auron_b200_call_native does (same planner) but on no device, and writes the resulting
+ * operator tree as JSON: per operator its reference name (`ExecutionPlan::name()`), output schema, the attributes decoded from the
+ * plan node (expressions as text, join type / sides / keys, aggregate functions and modes, sort keys, limit, partitioning, scan files
+ * and projection, resource ids) and its children.  What PhysicalPlanner::create_plan (auron-planner/src/planner.rs:114-760) would
+ * build, made inspectable.  Returns the JSON length (text truncated to cap - 1 bytes) or -1 (auron_b200_last_error).  Host only. */
+int64_t auron_b200_explain(const uint8_t* task_definition, size_t len, char* out, int64_t cap);
 /* UTC offset (seconds east) the engine's time-zone tables give for `zone` at `utc_second`: what the device looks up for the
  * date/time functions that take a session time zone (spark_dates.rs:93-110,200-227, chrono-tz in the reference).
  * Returns 0 and fills *offset, or -1 when `zone` is not an IANA zone name.  Host only: usable without a GPU. */

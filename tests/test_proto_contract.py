@@ -160,3 +160,88 @@ def test_decoded_values_mean_what_the_builders_were_given():
     key = srt["expr"][0]["sort"][0]
     assert key.get("asc", [0]) == [0] and key["nulls_first"] == [1]
     assert (srt["fetch_limit"][0]["limit"], srt["fetch_limit"][0]["offset"]) == ([9], [4])
+
+
+def _explain(plan: bytes, **ids) -> dict:
+    import ctypes as C
+    from auron_b200 import runtime
+    L = runtime.lib()
+    L.auron_b200_explain.restype = C.c_int64
+    L.auron_b200_explain.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int64]
+    L.auron_b200_last_error.restype = C.c_char_p
+    td = P.task_definition(plan, **ids)
+    buf = C.create_string_buffer(1 << 20)
+    n = L.auron_b200_explain(td, len(td), buf, len(buf))
+    assert n > 0, L.auron_b200_last_error().decode()
+    return json.loads(buf.value.decode())
+
+
+def test_planner_decodes_every_plan_into_the_operators_it_was_built_as():
+    # the other side of the wire: the engine's own planner (planner.cc, the PhysicalPlanner::create_plan of this engine) decodes the
+    # same bytes -- on no device -- and its operator tree is read back: reference operator names, output schemas, every attribute of
+    # every node and every expression / literal (Arrow IPC ScalarValues) as they were encoded
+    plans = _plans()
+    top = _explain(plans[0], stage_id=3, partition_id=4, task_id=5)
+    assert (top["stage_id"], top["partition_id"], top["task_id"]) == (3, 4, 5)
+    proj = top["plan"]
+    assert proj["op"] == "ProjectExec" and proj["children"][0]["op"] == "FilterExec" and proj["children"][0]["children"][0]["op"] == "FFIReaderExec"
+    assert proj["exprs"] == ["Plus(col(a), lit(int32:1))", "And(IsNull(col(a)), IsNotNull(col(b)))", "Not(col(f))", "Negative(col(a))",
+                             "Case[else](Gt(col(a), lit(int32:0)), lit(utf8:'p'), lit(utf8:NULL))", "Cast(col(a) AS int64)",
+                             "TryCast(col(s) AS decimal128(12,3))", "NotIn(col(a), lit(int32:1), lit(int32:2))",
+                             "Spark_Hour(col(t), lit(utf8:'Asia/Shanghai')) -> int32", "Substr(col(s), lit(int64:1), lit(int64:2)) -> utf8",
+                             "Like(col(s), lit(utf8:'a%'))", "SCAnd(col(f), col(f))", "SCOr(col(f), col(f))", "StartsWith(col(s), 'a')", "EndsWith(col(s), 'z')",
+                             "Contains(col(s), 'm')", "col(#0)", "lit(decimal128(7,2):1234)", "lit(float64:1.5)", "lit(bool:1)"]
+    assert [f[0] for f in proj["schema"]] == [f"e{i}" for i in range(20)] and proj["schema"][6][1] == "decimal128(12,3)"
+    assert proj["children"][0]["predicates"] == ["GtEq(col(a), lit(int32:0))"]
+    src = proj["children"][0]["children"][0]
+    assert src["resource_id"] == "in" and [f[0] for f in src["schema"]] == T.names
+    assert [f[1] for f in src["schema"]] == ["int32", "int64", "utf8", "decimal128(7,2)", "timestamp", "float64", "date32", "bool"]
+
+    agg = _explain(plans[1])["plan"]
+    assert agg["op"] == "AggExec" and agg["grouping"] == ["col(a)", "col(s)"]
+    assert [(a["fn"], a["mode"], a["args"]) for a in agg["aggs"]] == [(f, "PARTIAL", ["col(b)"]) for f in ("SUM", "COUNT", "MIN", "MAX", "AVG", "FIRST")]
+    fin = _explain(plans[2])["plan"]
+    assert fin["aggs"] == [{"fn": "SUM", "mode": "FINAL", "args": ["lit(null:NULL)"], "return_type": "int64"}] and fin["children"][0]["op"] == "AggExec"
+    assert fin["schema"] == [["a", "int32"], ["g", "int64"]]
+
+    srt = _explain(plans[3])["plan"]
+    assert (srt["op"], srt["keys"], srt["limit"], srt["offset"]) == ("SortExec", ["col(a) DESC NULLS LAST", "col(s) ASC NULLS FIRST"], 10, 2)
+
+    scan = _explain(plans[4])["plan"]
+    assert scan["op"] == "ParquetExec" and scan["fs_resource_id"] == "fs" and scan["projection"] == [0, 2, 3]
+    assert scan["files"] == [{"path": "/tmp/x.parquet", "size": 1234, "range": [0, 100]}, {"path": "/tmp/y.parquet", "size": 99, "range": [5, 50]}]
+    assert scan["schema"] == [["a", "int32"], ["s", "utf8"], ["d", "decimal128(7,2)"]]
+
+    attrs = lambda d: {k: v for k, v in d.items() if k not in ("schema", "children")}
+    assert attrs(_explain(plans[5])["plan"]) == {"op": "BroadcastJoin", "join_type": "LEFT", "build_side": "RIGHT", "left_keys": ["col(a)"],
+                                                 "right_keys": ["col(a)"], "cached_build_hash_map_id": "", "null_aware_anti": False}
+    smj = _explain(plans[6])["plan"]
+    assert (smj["op"], smj["join_type"]) == ("SortMergeJoinExec", "FULL") and len(smj["schema"]) == 16 and len(smj["children"]) == 2
+    assert attrs(_explain(plans[7])["plan"]) == {"op": "BroadcastJoin", "join_type": "SEMI", "build_side": "LEFT", "left_keys": ["col(a)"],
+                                                 "right_keys": ["col(a)"], "cached_build_hash_map_id": "bc-1", "null_aware_anti": True}
+
+    writers = [attrs(_explain(p)["plan"]) for p in plans[8:12]]
+    assert [(w["partitioning"], w["partition_count"], w["exprs"], w["range_bound_rows"]) for w in writers] == [
+        ("hash", 7, ["col(a)", "col(s)"], []), ("single", 1, [], []), ("round_robin", 5, [], []), ("range", 3, ["col(a) ASC NULLS FIRST"], [2])]
+    assert all(w["op"] == "ShuffleWriterExec" and (w["data_file"], w["index_file"], w["codec"]) == ("/tmp/d", "/tmp/i", "lz4") for w in writers)
+
+    lim, ren, uni, ipc = (_explain(p)["plan"] for p in plans[12:16])
+    assert (lim["op"], lim["limit"], lim["offset"]) == ("LimitExec", 5, 1)
+    assert ren["op"] == "RenameColumnsExec" and [f[0] for f in ren["schema"]] == [f"c{i}" for i in range(8)]
+    assert uni["op"] == "UnionExec" and [c["op"] for c in uni["children"]] == ["FFIReaderExec"] * 2
+    assert (ipc["op"], ipc["resource_id"]) == ("IpcReaderExec", "blocks")
+
+
+def test_planner_rejects_what_is_outside_the_path_with_a_message():
+    import ctypes as C
+    from auron_b200 import runtime
+    L = runtime.lib()
+    L.auron_b200_explain.restype = C.c_int64
+    L.auron_b200_explain.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int64]
+    L.auron_b200_last_error.restype = C.c_char_p
+    src = P.ffi_reader(T, "in")
+    window = P.f_bytes(22, P.f_bytes(1, src))                                     # PhysicalPlanNode{window}: not on the path
+    for plan, needle in [(window, ""), (b"\x0a\x03abc", ""), (P.filter_(src, []), "predicate")]:
+        td = P.task_definition(plan) if plan != b"\x0a\x03abc" else plan
+        assert L.auron_b200_explain(td, len(td), None, 0) == -1
+        assert needle in L.auron_b200_last_error().decode().lower()
