@@ -245,3 +245,35 @@ def test_planner_rejects_what_is_outside_the_path_with_a_message():
         td = P.task_definition(plan) if plan != b"\x0a\x03abc" else plan
         assert L.auron_b200_explain(td, len(td), None, 0) == -1
         assert needle in L.auron_b200_last_error().decode().lower()
+
+
+def test_planner_skips_fields_of_the_reference_message_it_does_not_use():
+    # the JVM side fills fields this engine has no use for (TaskDefinition.output_partitioning, AggExecNode.initial_input_buffer_offset,
+    # FileScanExecConf.statistics / partition_schema, PartitionedFile.last_modified_ns ...): they must be skipped, not rejected
+    src = P.ffi_reader(T, "in")
+    agg = P.agg(src, [P.col("a")], ["a"], [P.agg_expr("COUNT", [P.col("b")], L)], ["c"], ["PARTIAL"])
+    # re-encode the agg node with an extra field 8 (uint64 initial_input_buffer_offset) appended to its body
+    seen = set()
+    node = walk("PhysicalPlanNode", agg, seen)
+    assert "agg" in node
+
+    def first_field(buf):
+        key, i = _varint(buf, 0)
+        n, j = _varint(buf, i)
+        return key, buf[j:j + n]
+
+    key, inner = first_field(agg)
+    inner2 = inner + P.f_varint(8, 12345)
+    agg2 = P.f_bytes(key >> 3, inner2)
+    walk("PhysicalPlanNode", agg2, seen)                        # still a valid reference message
+    td = P.task_definition(agg2) + P.f_bytes(3, P.single_repartition())      # TaskDefinition.output_partitioning = 3
+    walk("TaskDefinition", td, seen)
+    import ctypes as C
+    from auron_b200 import runtime
+    Lb = runtime.lib()
+    Lb.auron_b200_explain.restype = C.c_int64
+    Lb.auron_b200_explain.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int64]
+    buf = C.create_string_buffer(1 << 16)
+    assert Lb.auron_b200_explain(td, len(td), buf, len(buf)) > 0
+    d = json.loads(buf.value.decode())["plan"]
+    assert d["op"] == "AggExec" and d["aggs"][0]["fn"] == "COUNT" and d["children"][0]["resource_id"] == "in"
