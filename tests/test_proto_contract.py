@@ -277,3 +277,19 @@ def test_planner_skips_fields_of_the_reference_message_it_does_not_use():
     assert Lb.auron_b200_explain(td, len(td), buf, len(buf)) > 0
     d = json.loads(buf.value.decode())["plan"]
     assert d["op"] == "AggExec" and d["aggs"][0]["fn"] == "COUNT" and d["children"][0]["resource_id"] == "in"
+
+
+def test_wrapper_nodes_of_real_spark_plans_decode_under_their_reference_names():
+    # NativeBroadcastJoinBase wraps the broadcast side in BroadcastJoinBuildHashMapExecNode; converters also emit CoalesceBatches, Debug and
+    # EmptyPartitions nodes: pass-through / trivial operators here, named as the reference names them
+    src = P.ffi_reader(T, "in")
+    nodes = {"BroadcastJoinBuildHashMapExec": P.f_bytes(12, P.f_bytes(1, src) + P.f_bytes(2, P.col("a"))),
+             "CoalesceBatchesExec": P.f_bytes(19, P.f_bytes(1, src) + P.f_varint(2, 8192)),
+             "DebugExec": P.f_bytes(1, P.f_bytes(1, src) + P.f_str(2, "dbg")),
+             "EmptyPartitionsExec": P.f_bytes(15, P.f_bytes(1, P.schema(T)) + P.f_varint(2, 4))}
+    seen = set()
+    for name, plan in nodes.items():
+        walk("PhysicalPlanNode", plan, seen)
+        d = _explain(plan)["plan"]
+        assert d["op"] == name and [f[0] for f in d["schema"]] == T.names
+        assert [c["op"] for c in d["children"]] == ([] if name == "EmptyPartitionsExec" else ["FFIReaderExec"])
