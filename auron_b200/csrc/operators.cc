@@ -339,6 +339,8 @@ AggExec::AggExec(OperatorPtr input, std::vector<ExprPtr> ge, std::vector<std::st
             default: fail("aggregate function " + std::to_string(a.fn) + " is not native on device (collect/bloom/UDAF are out of scope)");
         }
         if (a.mode != MODE_PARTIAL) input_acc_cols += (a.fn == AGG_FIRST) ? 2 : (a.acc_types.empty() ? 1 : (int)a.acc_types.size());
+        AURON_CHECK(a.mode == MODE_PARTIAL || a.mode == MODE_PARTIAL_MERGE || a.mode == MODE_FINAL, "unknown aggregate mode");
+        AURON_CHECK(a.mode != MODE_PARTIAL || !a.children.empty(), "aggregate function without an argument");
     }
     // value types for MIN/MAX/FIRST: child type in partial mode, the trailing acc column type in merge modes
     int acc_pos = (int)in.fields.size() - input_acc_cols;
@@ -347,7 +349,10 @@ AggExec::AggExec(OperatorPtr input, std::vector<ExprPtr> ge, std::vector<std::st
         bool value_typed = a.fn == AGG_MIN || a.fn == AGG_MAX || a.fn == AGG_FIRST || a.fn == AGG_FIRST_IGNORES_NULL;
         if (value_typed) {
             if (a.mode == MODE_PARTIAL) a.value_type = infer_type(*a.children[0], in);
-            else a.value_type = in.fields[acc_pos].type;
+            else {
+                AURON_CHECK(acc_pos < (int)in.fields.size(), "aggregate input has fewer columns than accumulator arrays");
+                a.value_type = in.fields[acc_pos].type;
+            }
             a.acc_types = {a.value_type};
             if (a.fn == AGG_FIRST) a.acc_types.push_back(DType(T_BOOL));
         }

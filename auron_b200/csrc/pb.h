@@ -69,10 +69,12 @@ struct PbReader {
 };
 
 // ---- flatbuffers (read-only, just what an Arrow IPC Schema / RecordBatch message needs) ----
+// The bytes come from outside (a plan literal): every offset is checked against the message before it is followed, a
+// malformed buffer is an error, never an out-of-bounds read.
 struct FbTable {
-    const uint8_t* base = nullptr;   // buffer start (for bounds only)
+    const uint8_t* base = nullptr;   // message start
     const uint8_t* tbl = nullptr;    // table position
-    size_t size = 0;
+    size_t size = 0;                 // message length
     bool ok() const { return tbl != nullptr; }
     template <typename T>
     static T rd(const uint8_t* p) {
@@ -80,19 +82,38 @@ struct FbTable {
         memcpy(&v, p, sizeof(T));
         return v;
     }
+    // [p, p + n) lies inside the message
+    const uint8_t* chk(const uint8_t* p, size_t n) const {
+        const uintptr_t b = (uintptr_t)base, q = (uintptr_t)p;
+        AURON_CHECK(base && q >= b && q - b <= size && n <= size - (q - b), "Arrow IPC: flatbuffer offset outside the message");
+        return p;
+    }
+    template <typename T>
+    T rdc(const uint8_t* p) const {
+        return rd<T>(chk(p, sizeof(T)));
+    }
+    static FbTable root(const uint8_t* msg, size_t len) {
+        FbTable t;
+        t.base = msg;
+        t.size = len;
+        AURON_CHECK(len >= 8, "Arrow IPC: message too short");
+        t.tbl = msg + rd<uint32_t>(msg);
+        t.chk(t.tbl, 4);
+        return t;
+    }
     // offset of field `id` inside the table, or 0 if absent
     uint16_t field_off(int id) const {
-        int32_t vt_rel = rd<int32_t>(tbl);
-        const uint8_t* vt = tbl - vt_rel;
-        uint16_t vt_size = rd<uint16_t>(vt);
-        uint16_t pos = (uint16_t)(4 + 2 * id);
+        const int32_t vt_rel = rdc<int32_t>(tbl);
+        const uint8_t* vt = (const uint8_t*)((intptr_t)tbl - (intptr_t)vt_rel);
+        const uint16_t vt_size = rdc<uint16_t>(vt);
+        const uint16_t pos = (uint16_t)(4 + 2 * id);
         if (pos + 2 > vt_size) return 0;
-        return rd<uint16_t>(vt + pos);
+        return rdc<uint16_t>(vt + pos);
     }
     template <typename T>
     T scalar(int id, T def) const {
         uint16_t o = field_off(id);
-        return o ? rd<T>(tbl + o) : def;
+        return o ? rdc<T>(tbl + o) : def;
     }
     FbTable table(int id) const {
         uint16_t o = field_off(id);
@@ -101,35 +122,37 @@ struct FbTable {
         const uint8_t* p = tbl + o;
         t.base = base;
         t.size = size;
-        t.tbl = p + rd<uint32_t>(p);
+        t.tbl = p + rdc<uint32_t>(p);
+        chk(t.tbl, 4);
         return t;
     }
     std::string str(int id) const {
         uint16_t o = field_off(id);
         if (!o) return "";
         const uint8_t* p = tbl + o;
-        p += rd<uint32_t>(p);
-        uint32_t n = rd<uint32_t>(p);
-        return std::string((const char*)p + 4, n);
+        p += rdc<uint32_t>(p);
+        const uint32_t n = rdc<uint32_t>(p);
+        return std::string((const char*)chk(p + 4, n), n);
     }
-    // vector: returns pointer to first element and count
-    const uint8_t* vec(int id, uint32_t* n) const {
+    // vector of `elem`-byte elements: returns pointer to the first element and the count
+    const uint8_t* vec(int id, uint32_t* n, size_t elem = 4) const {
         uint16_t o = field_off(id);
         if (!o) {
             *n = 0;
             return nullptr;
         }
         const uint8_t* p = tbl + o;
-        p += rd<uint32_t>(p);
-        *n = rd<uint32_t>(p);
-        return p + 4;
+        p += rdc<uint32_t>(p);
+        *n = rdc<uint32_t>(p);
+        return chk(p + 4, (size_t)*n * elem);
     }
     FbTable vec_table(const uint8_t* elems, uint32_t i) const {
         FbTable t;
-        const uint8_t* p = elems + 4 * i;
+        const uint8_t* p = elems + 4 * (size_t)i;
         t.base = base;
         t.size = size;
-        t.tbl = p + rd<uint32_t>(p);
+        t.tbl = p + rdc<uint32_t>(p);
+        chk(t.tbl, 4);
         return t;
     }
 };

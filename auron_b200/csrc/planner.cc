@@ -113,13 +113,10 @@ static bool next_ipc_message(const uint8_t*& p, const uint8_t* end, const uint8_
     *meta = p;
     *meta_len = first;
     p += first;
-    FbTable msg;
-    msg.base = *meta;
-    msg.size = first;
-    msg.tbl = *meta + FbTable::rd<uint32_t>(*meta);
+    FbTable msg = FbTable::root(*meta, first);
     *body_len = msg.scalar<int64_t>(3, 0);
     *body = p;
-    AURON_CHECK(end - p >= *body_len, "Arrow IPC: truncated body");
+    AURON_CHECK(*body_len >= 0 && end - p >= *body_len, "Arrow IPC: truncated body");
     p += *body_len;
     return true;
 }
@@ -169,12 +166,10 @@ HostArray decode_list_scalar_ipc(const uint8_t* bytes, size_t n) {
     int64_t body_len;
     HostArray out;
     AURON_CHECK(next_ipc_message(p, end, &meta, &meta_len, &body, &body_len), "list ScalarValue: missing schema message");
-    FbTable msg;
-    msg.base = meta;
-    msg.size = meta_len;
-    msg.tbl = meta + FbTable::rd<uint32_t>(meta);
+    FbTable msg = FbTable::root(meta, meta_len);
     AURON_CHECK(msg.scalar<uint8_t>(1, 0) == 1, "list ScalarValue: first IPC message is not a Schema");
     FbTable schema = msg.table(2);
+    AURON_CHECK(schema.ok(), "list ScalarValue: Schema message without a header");
     uint32_t nfields;
     const uint8_t* fields = schema.vec(1, &nfields);
     AURON_CHECK(nfields == 1, "list ScalarValue: expected exactly one field");
@@ -187,21 +182,20 @@ HostArray decode_list_scalar_ipc(const uint8_t* bytes, size_t n) {
     AURON_CHECK(children && nchildren == 1, "list ScalarValue: malformed child field");
     out.type = fb_field_type(field.vec_table(children, 0));
     AURON_CHECK(next_ipc_message(p, end, &meta, &meta_len, &body, &body_len), "list ScalarValue: missing record batch");
-    msg.base = meta;
-    msg.size = meta_len;
-    msg.tbl = meta + FbTable::rd<uint32_t>(meta);
+    msg = FbTable::root(meta, meta_len);
     AURON_CHECK(msg.scalar<uint8_t>(1, 0) == 3, "list ScalarValue: second IPC message is not a RecordBatch");
     FbTable rb = msg.table(2);
+    AURON_CHECK(rb.ok(), "list ScalarValue: RecordBatch message without a header");
     uint32_t nnodes, nbufs;
-    const uint8_t* nodes = rb.vec(1, &nnodes);
-    const uint8_t* bufs = rb.vec(2, &nbufs);
+    const uint8_t* nodes = rb.vec(1, &nnodes, 16);   // FieldNode{length, null_count}
+    const uint8_t* bufs = rb.vec(2, &nbufs, 16);     // Buffer{offset, length}
     AURON_CHECK(rb.field_off(3) == 0, "list ScalarValue: compressed IPC bodies are not supported");
     AURON_CHECK(nnodes == 2 && rb.scalar<int64_t>(0, 0) == 1, "list ScalarValue: expected one list row");
     auto buf = [&](uint32_t i, int64_t* len) -> const uint8_t* {
         AURON_CHECK(i < nbufs, "list ScalarValue: missing buffer");
         int64_t off = FbTable::rd<int64_t>(bufs + 16 * i);
         *len = FbTable::rd<int64_t>(bufs + 16 * i + 8);
-        AURON_CHECK(off >= 0 && off + *len <= body_len, "list ScalarValue: buffer outside the body");
+        AURON_CHECK(off >= 0 && *len >= 0 && off <= body_len && *len <= body_len - off, "list ScalarValue: buffer outside the body");
         return body + off;
     };
     int64_t l;
@@ -277,12 +271,10 @@ Literal decode_scalar_ipc(const uint8_t* bytes, size_t n) {
     int64_t body_len;
     Literal lit;
     AURON_CHECK(next_ipc_message(p, end, &meta, &meta_len, &body, &body_len), "ScalarValue: missing schema message");
-    FbTable msg;
-    msg.base = meta;
-    msg.size = meta_len;
-    msg.tbl = meta + FbTable::rd<uint32_t>(meta);
+    FbTable msg = FbTable::root(meta, meta_len);
     AURON_CHECK(msg.scalar<uint8_t>(1, 0) == 1, "ScalarValue: first IPC message is not a Schema");
     FbTable schema = msg.table(2);
+    AURON_CHECK(schema.ok(), "ScalarValue: Schema message without a header");
     uint32_t nfields;
     const uint8_t* fields = schema.vec(1, &nfields);
     AURON_CHECK(nfields == 1, "ScalarValue: expected exactly one field");
@@ -292,15 +284,14 @@ Literal decode_scalar_ipc(const uint8_t* bytes, size_t n) {
         lit.is_null = true;
         return lit;
     }
-    msg.base = meta;
-    msg.size = meta_len;
-    msg.tbl = meta + FbTable::rd<uint32_t>(meta);
+    msg = FbTable::root(meta, meta_len);
     AURON_CHECK(msg.scalar<uint8_t>(1, 0) == 3, "ScalarValue: second IPC message is not a RecordBatch");
     FbTable rb = msg.table(2);
+    AURON_CHECK(rb.ok(), "ScalarValue: RecordBatch message without a header");
     int64_t length = rb.scalar<int64_t>(0, 0);
     uint32_t nnodes, nbufs;
-    const uint8_t* nodes = rb.vec(1, &nnodes);
-    const uint8_t* bufs = rb.vec(2, &nbufs);
+    const uint8_t* nodes = rb.vec(1, &nnodes, 16);   // FieldNode{length, null_count}
+    const uint8_t* bufs = rb.vec(2, &nbufs, 16);     // Buffer{offset, length}
     AURON_CHECK(rb.field_off(3) == 0, "ScalarValue: compressed IPC bodies are not supported");
     if (length == 0 || lit.type.id == T_NULL) {
         lit.is_null = true;
@@ -311,35 +302,43 @@ Literal decode_scalar_ipc(const uint8_t* bytes, size_t n) {
         AURON_CHECK(i < nbufs, "ScalarValue: missing buffer");
         int64_t off = FbTable::rd<int64_t>(bufs + 16 * i);
         *len = FbTable::rd<int64_t>(bufs + 16 * i + 8);
+        AURON_CHECK(off >= 0 && *len >= 0 && off <= body_len && *len <= body_len - off, "ScalarValue: buffer outside the body");
         return body + off;
+    };
+    // the value buffer of a one-row array holds at least one value of the type
+    auto value = [&](uint32_t i, int64_t need) -> const uint8_t* {
+        int64_t len;
+        const uint8_t* p = buf(i, &len);
+        AURON_CHECK(len >= need, "ScalarValue: short value buffer");
+        return p;
     };
     int64_t vlen;
     const uint8_t* validity = buf(0, &vlen);
-    if (null_count > 0 || (vlen > 0 && !(validity[0] & 1))) {
+    if (null_count > 0 || (vlen > 0 && !(validity[0] & 1))) {   // (buf() checked that vlen bytes exist)
         lit.is_null = true;
         return lit;
     }
     lit.is_null = false;
-    int64_t dlen;
     switch (lit.type.id) {
-        case T_BOOL: lit.i = buf(1, &dlen)[0] & 1; break;
-        case T_INT8: lit.i = (int8_t)buf(1, &dlen)[0]; break;
-        case T_INT16: lit.i = FbTable::rd<int16_t>(buf(1, &dlen)); break;
-        case T_INT32: case T_DATE32: lit.i = FbTable::rd<int32_t>(buf(1, &dlen)); break;
-        case T_INT64: case T_DATE64: case T_TIMESTAMP: lit.i = FbTable::rd<int64_t>(buf(1, &dlen)); break;
-        case T_FLOAT32: lit.d = FbTable::rd<float>(buf(1, &dlen)); break;
-        case T_FLOAT64: lit.d = FbTable::rd<double>(buf(1, &dlen)); break;
+        case T_BOOL: lit.i = value(1, 1)[0] & 1; break;
+        case T_INT8: lit.i = (int8_t)value(1, 1)[0]; break;
+        case T_INT16: lit.i = FbTable::rd<int16_t>(value(1, 2)); break;
+        case T_INT32: case T_DATE32: lit.i = FbTable::rd<int32_t>(value(1, 4)); break;
+        case T_INT64: case T_DATE64: case T_TIMESTAMP: lit.i = FbTable::rd<int64_t>(value(1, 8)); break;
+        case T_FLOAT32: lit.d = FbTable::rd<float>(value(1, 4)); break;
+        case T_FLOAT64: lit.d = FbTable::rd<double>(value(1, 8)); break;
         case T_DECIMAL128: {
-            const uint8_t* d = buf(1, &dlen);
+            const uint8_t* d = value(1, 16);
             lit.lo = FbTable::rd<uint64_t>(d);
             lit.hi = FbTable::rd<int64_t>(d + 8);
             break;
         }
         case T_UTF8: case T_BINARY: {
-            const uint8_t* offs = buf(1, &dlen);
+            const uint8_t* offs = value(1, 8);
             int32_t b0 = FbTable::rd<int32_t>(offs), b1 = FbTable::rd<int32_t>(offs + 4);
             int64_t l2;
             const uint8_t* data = buf(2, &l2);
+            AURON_CHECK(b0 >= 0 && b1 >= b0 && b1 <= l2, "ScalarValue: string offsets outside the data buffer");
             lit.s.assign((const char*)data + b0, (size_t)(b1 - b0));
             break;
         }
@@ -363,13 +362,42 @@ static const char* scalar_fn_name(int fun) {   // auron.proto ScalarFunction :21
     }
 }
 
+// the plan comes from outside: an expression node with missing operands is an error message, never a null dereference later
+static void validate_expr(const Expr& e) {
+    for (auto& c : e.children) AURON_CHECK(c != nullptr, "expression node with a missing operand");
+    const size_t n = e.children.size();
+    switch (e.kind) {
+        case E_BINARY: case E_LIKE: case E_SC_AND: case E_SC_OR: AURON_CHECK(n == 2, "expression node needs two operands"); break;
+        case E_NOT: case E_IS_NULL: case E_IS_NOT_NULL: case E_NEGATIVE: case E_CAST: case E_TRY_CAST: case E_STARTS_WITH: case E_ENDS_WITH:
+        case E_CONTAINS: AURON_CHECK(n == 1, "expression node needs one operand"); break;
+        case E_IN_LIST: AURON_CHECK(n >= 1, "IN list without an expression"); break;
+        case E_CASE: {
+            const size_t extra = (e.has_case_expr ? 1 : 0) + (e.has_else ? 1 : 0);
+            AURON_CHECK(n >= extra + 2 && (n - extra) % 2 == 0, "CASE without a complete when/then branch");
+            break;
+        }
+        default: break;
+    }
+}
+
 static ExprPtr decode_expr_required(const uint8_t* b, size_t n) {
     ExprPtr e = decode_expr(b, n);
     AURON_CHECK(e != nullptr, "Unexpected empty physical expression");
     return e;
 }
 
+// nesting guard for the two recursive decoders: a plan nested deeper than any real one is rejected before the stack runs out
+static thread_local int g_decode_depth = 0;
+struct DepthGuard {
+    DepthGuard() {
+        AURON_CHECK(g_decode_depth < 2000, "plan nested too deeply");   // (checked before counting: a throwing constructor runs no destructor)
+        ++g_decode_depth;
+    }
+    ~DepthGuard() { --g_decode_depth; }
+};
+
 ExprPtr decode_expr(const uint8_t* b, size_t n) {
+    DepthGuard depth;
     PbReader r(b, n);
     uint32_t f, w;
     ExprPtr out;
@@ -548,6 +576,7 @@ ExprPtr decode_expr(const uint8_t* b, size_t n) {
             default:
                 fail("physical expression kind #" + std::to_string(f) + " is not native on device (JVM-callback / nested-type expressions are out of scope)");
         }
+        validate_expr(*e);
         out = e;
     }
     return out;
@@ -712,6 +741,7 @@ static OperatorPtr decode_join(Task& t, const uint8_t* b, size_t n, int kind /*0
 }
 
 static OperatorPtr decode_plan(Task& t, const uint8_t* b, size_t n) {
+    DepthGuard depth;
     PbReader r(b, n);
     uint32_t f, w;
     OperatorPtr out;

@@ -452,7 +452,9 @@ OperatorPtr make_shuffle_writer(Task& t, OperatorPtr input, const uint8_t* node,
                         const uint8_t* eb;
                         size_t en;
                         s.bytes_view(&eb, &en);
-                        op->hash_exprs.push_back(decode_expr(eb, en));
+                        ExprPtr he = decode_expr(eb, en);
+                        AURON_CHECK(he != nullptr, "hash partitioning: empty expression");
+                        op->hash_exprs.push_back(he);
                     } else if (((pf == 2 && sf == 2) || (pf != 2 && sf == 1)) && sw == 0) op->num_parts = (int64_t)s.varint();
                     else s.skip(sw);
                 }

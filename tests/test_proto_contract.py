@@ -293,3 +293,38 @@ def test_wrapper_nodes_of_real_spark_plans_decode_under_their_reference_names():
         d = _explain(plan)["plan"]
         assert d["op"] == name and [f[0] for f in d["schema"]] == T.names
         assert [c["op"] for c in d["children"]] == ([] if name == "EmptyPartitionsExec" else ["FFIReaderExec"])
+
+
+def test_malformed_plans_are_errors_not_crashes():
+    # "Panics/aborts must not kill the JVM" (lib.rs:57-72 catches unwinds in the reference): byte-level damage to valid plans -- in the
+    # protobuf framing, in the Arrow IPC flatbuffers of literals, in operand counts -- and absurd nesting must come back as an error
+    # (or still decode); the planner is run on thousands of mutants in this process
+    import ctypes as C
+    import random
+    from auron_b200 import runtime
+    Lb = runtime.lib()
+    Lb.auron_b200_explain.restype = C.c_int64
+    Lb.auron_b200_explain.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int64]
+    random.seed(20250921)
+    tds = [P.task_definition(p) for p in _plans()]
+    ok = bad = 0
+    for _ in range(6000):
+        b = bytearray(random.choice(tds))
+        for _ in range(random.randint(1, 3)):
+            r = random.random()
+            if r < 0.6:
+                b[random.randrange(len(b))] = random.randrange(256)
+            elif r < 0.8:
+                del b[random.randrange(len(b))]
+            else:
+                b = b[:random.randrange(1, len(b) + 1)]
+        n = Lb.auron_b200_explain(bytes(b), len(b), None, 0)
+        ok += n > 0
+        bad += n < 0
+    assert ok > 100 and bad > 100                                  # both outcomes occur; reaching this line is the point
+    deep = P.col("f")
+    for _ in range(5000):
+        deep = P.not_(deep)
+    td = P.task_definition(P.filter_(P.ffi_reader(T, "in"), [deep]))
+    assert Lb.auron_b200_explain(td, len(td), None, 0) == -1
+    assert _explain(P.filter_(P.ffi_reader(T, "in"), [P.not_(P.col("f"))]))["plan"]["predicates"] == ["Not(col(f))"]   # and the planner still works
