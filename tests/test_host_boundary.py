@@ -129,6 +129,41 @@ def test_parquet_metadata_reader_against_pyarrow(tmp_path, compression, version,
     assert L.auron_b200_parquet_describe(str(tmp_path / "missing.parquet").encode(), buf, len(buf)) == -1 and b"cannot open" in buf.value
 
 
+def test_parquet_metadata_reader_survives_damaged_files(tmp_path):
+    # footers, page headers and Snappy bodies with flipped bytes: the reader answers with an error or a description, never with a crash
+    # (a corrupt file must fail one task, not the executor)
+    import ctypes as C
+    import random
+    import numpy as np
+    import pyarrow.parquet as pq
+    rng = np.random.default_rng(1)
+    n = 20_000
+    t = pa.table({"i": pa.array(rng.integers(0, 500, n), type=pa.int32(), mask=rng.random(n) < 0.05),
+                  "s": pa.array([f"v{int(x) % 300}" for x in rng.integers(0, 10**6, n)]), "f": pa.array(rng.standard_normal(n))})
+    L = runtime.lib()
+    L.auron_b200_parquet_describe.restype = C.c_int64
+    L.auron_b200_parquet_describe.argtypes = [C.c_char_p, C.c_char_p, C.c_int64]
+    buf = C.create_string_buffer(1 << 22)
+    random.seed(99)
+    ok = bad = 0
+    for comp, ver in (("SNAPPY", "1.0"), ("SNAPPY", "2.0"), ("ZSTD", "2.0")):
+        src = str(tmp_path / f"{comp}{ver}.parquet")
+        pq.write_table(t, src, compression=comp, data_page_version=ver, row_group_size=5000, data_page_size=4096)
+        raw = open(src, "rb").read()
+        mut = str(tmp_path / "mut.parquet")
+        for _ in range(300):
+            b = bytearray(raw)
+            for _ in range(random.randint(1, 4)):
+                r = random.random()
+                pos = len(b) - 8 - random.randint(1, 900) if r < 0.5 else (random.randint(4, len(b) - 9) if r < 0.9 else len(b) - random.randint(1, 8))
+                b[pos] = random.randint(0, 255)
+            open(mut, "wb").write(bytes(b))
+            rc = L.auron_b200_parquet_describe(mut.encode(), buf, len(buf))
+            ok += rc > 0
+            bad += rc < 0
+    assert ok > 50 and bad > 50
+
+
 def _jni_function_table():
     """JNINativeInterface_ in declaration order, generated from the structure of the JNI specification's "Interface Function
     Table" (4 reserved slots, then the functions; the Call*Method families come as plain / V / A triples per result type)."""
