@@ -340,7 +340,7 @@ AggExec::AggExec(OperatorPtr input, std::vector<ExprPtr> ge, std::vector<std::st
         }
         if (a.mode != MODE_PARTIAL) input_acc_cols += (a.fn == AGG_FIRST) ? 2 : (a.acc_types.empty() ? 1 : (int)a.acc_types.size());
         AURON_CHECK(a.mode == MODE_PARTIAL || a.mode == MODE_PARTIAL_MERGE || a.mode == MODE_FINAL, "unknown aggregate mode");
-        AURON_CHECK(a.mode != MODE_PARTIAL || !a.children.empty(), "aggregate function without an argument");
+        AURON_CHECK(a.mode != MODE_PARTIAL || a.fn == AGG_COUNT || !a.children.empty(), "aggregate function without an argument");   // COUNT() counts rows
     }
     // value types for MIN/MAX/FIRST: child type in partial mode, the trailing acc column type in merge modes
     int acc_pos = (int)in.fields.size() - input_acc_cols;

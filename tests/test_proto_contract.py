@@ -328,3 +328,16 @@ def test_malformed_plans_are_errors_not_crashes():
     td = P.task_definition(P.filter_(P.ffi_reader(T, "in"), [deep]))
     assert Lb.auron_b200_explain(td, len(td), None, 0) == -1
     assert _explain(P.filter_(P.ffi_reader(T, "in"), [P.not_(P.col("f"))]))["plan"]["predicates"] == ["Not(col(f))"]   # and the planner still works
+
+
+def test_count_without_arguments_is_count_star():
+    # AggCount over no children counts rows (agg/count.rs:89-157): the argument check of the planner must not reject it
+    plan = P.agg(P.ffi_reader(T, "in"), [P.col("a")], ["a"], [P.agg_expr("COUNT", [], L)], ["c"], ["PARTIAL"])
+    assert _explain(plan)["plan"]["aggs"] == [{"fn": "COUNT", "mode": "PARTIAL", "args": [], "return_type": "int64"}]
+    import ctypes as C
+    from auron_b200 import runtime
+    Lb = runtime.lib()
+    Lb.auron_b200_explain.restype = C.c_int64
+    Lb.auron_b200_explain.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int64]
+    bad = P.task_definition(P.agg(P.ffi_reader(T, "in"), [P.col("a")], ["a"], [P.agg_expr("MAX", [], L)], ["m"], ["PARTIAL"]))
+    assert Lb.auron_b200_explain(bad, len(bad), None, 0) == -1                # MAX() of nothing is an error, not a crash
