@@ -73,6 +73,10 @@ VmProgram compile_projection(const std::vector<ExprPtr>& exprs, const Schema& in
 // conjunction of predicates; NULL -> false (cached_exprs_evaluator.rs:514-519)
 VmProgram compile_predicate(const std::vector<ExprPtr>& conjuncts, const Schema& input);
 
+// conjunction folded into one closed interval per column (ordering comparisons against literals on non-decimal fixed-width
+// columns): the columns (schema indices) and their bounds in the int64 domain; false when the predicate has another shape
+bool predicate_intervals(const VmProgram& p, std::vector<int>* cols, std::vector<int64_t>* lo, std::vector<int64_t>* hi);
+
 // evaluate over rows sel[0..n_out) (sel == nullptr: rows 0..n_out)
 std::vector<ColumnPtr> eval_projection(Ctx& ctx, const VmProgram& p, const Batch& in, const int32_t* sel, int64_t n_out);
 // returns selection bitmap (whole 32-bit words) over the n_rows input rows

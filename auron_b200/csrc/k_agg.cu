@@ -846,9 +846,10 @@ static AccArgs prepare_accs(Ctx& ctx, const std::vector<AccSpec>& specs, int64_t
         for (int i = 0; i < args.n; i++) {
             const AccSpec& s = specs[i];
             bool value_acc = s.kind == ACC_SUM_I64 || s.kind == ACC_SUM_F64 || s.kind == ACC_SUM_DEC || s.kind == ACC_MIN || s.kind == ACC_MAX;
-            if (!value_acc || !s.input) continue;
+            if (!value_acc || (!s.input && s.input_id < 0)) continue;
             for (int j = 0; j < args.n; j++)
-                if (specs[j].kind == ACC_COUNT && specs[j].input && specs[j].input.get() == s.input.get() && specs[j].extra.empty()) {
+                if (specs[j].kind == ACC_COUNT && specs[j].extra.empty() &&
+                    (s.input ? (specs[j].input && specs[j].input.get() == s.input.get()) : (!specs[j].input && specs[j].input_id == s.input_id))) {
                     args.a[i].valid_cnt = args.a[j].acc_lo;
                     args.a[i].acc_valid = nullptr;   // the buffer stays allocated (zeroed) but is neither written nor read
                     break;
@@ -929,6 +930,108 @@ static void emit_accs(Ctx& ctx, const std::vector<AccSpec>& specs, const AccArgs
     }
 }
 
+
+// -------------------------------------------------------------------------------- persistent DIRECT table
+// The direct-address table as an object: created for a key range, updated by any number of kernel launches (the chunk
+// aggregate below, or the fused Parquet scan -> filter -> aggregate kernels of k_fused.cu, batch after batch), widened when a
+// later batch brings keys outside the range, and turned into [keys | accumulators] columns at the end.
+struct DirectAgg {
+    std::vector<AccSpec> specs;
+    AccBuffers bufs;
+    AccArgs args;
+    DirectTable dt;
+    Buf seen, oor;
+    int64_t slots = 0;
+};
+static void direct_agg_alloc(Ctx& ctx, DirectAgg& da, long long kmin, long long kmax) {
+    const bool any = kmin <= kmax;
+    da.dt.kmin = any ? kmin : 0;
+    da.dt.range = any ? (int64_t)((unsigned long long)kmax - (unsigned long long)kmin) + 1 : 0;
+    da.slots = da.dt.range + 1;   // + the NULL group
+    da.bufs = AccBuffers();
+    da.args = prepare_accs(ctx, da.specs, da.slots, da.bufs);
+    init_accs(ctx, da.specs, da.args, da.slots);
+    da.seen = dalloc_zero(ctx, (size_t)da.slots + 8);
+    da.dt.seen = P<uint8_t>(da.seen);
+    if (!da.oor) da.oor = dalloc_zero(ctx, 4);
+    da.dt.oor = P<int32_t>(da.oor);
+}
+std::shared_ptr<DirectAgg> direct_agg_create(Ctx& ctx, const std::vector<AccSpec>& specs, long long kmin, long long kmax) {
+    auto da = std::make_shared<DirectAgg>();
+    da->specs = specs;
+    direct_agg_alloc(ctx, *da, kmin, kmax);
+    return da;
+}
+bool direct_agg_out_of_range(Ctx& ctx, const DirectAgg& da) {
+    int32_t bad = 0;
+    to_host(ctx, &bad, da.oor->ptr, 4);
+    return bad != 0;
+}
+DirectAggView direct_agg_view(const DirectAgg& da) {
+    DirectAggView v;
+    memset(&v, 0, sizeof(v));
+    v.n = da.args.n;
+    for (int i = 0; i < da.args.n; i++) {
+        v.kind[i] = da.args.a[i].kind;
+        v.acc[i] = da.args.a[i].acc_lo;
+        v.valid[i] = da.args.a[i].acc_valid;
+    }
+    v.seen = da.dt.seen;
+    v.oor = da.dt.oor;
+    v.kmin = da.dt.kmin;
+    v.range = da.dt.range;
+    return v;
+}
+__global__ void __launch_bounds__(256) direct_rebase_kernel(const unsigned long long* __restrict__ src, unsigned long long* __restrict__ dst,
+                                                            const uint8_t* __restrict__ srcb, uint8_t* __restrict__ dstb, int64_t old_range, int64_t shift,
+                                                            int64_t new_range) {
+    const int64_t s = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (s > old_range) return;
+    const int64_t d = s == old_range ? new_range : s + shift;
+    if (src) dst[d] = src[s];
+    if (srcb) dstb[d] = srcb[s];
+}
+void direct_agg_grow(Ctx& ctx, DirectAgg& da, long long kmin, long long kmax) {
+    if (da.dt.range > 0) {
+        kmin = std::min(kmin, da.dt.kmin);
+        kmax = std::max(kmax, (long long)(da.dt.kmin + da.dt.range - 1));
+    }
+    if (da.dt.range > 0 && kmin == da.dt.kmin && kmax == da.dt.kmin + da.dt.range - 1) return;
+    DirectAgg old = da;   // keeps the old buffers alive until the copies below are queued (stream-ordered frees)
+    direct_agg_alloc(ctx, da, kmin, kmax);
+    const int64_t shift = old.dt.range > 0 ? (int64_t)(old.dt.kmin - da.dt.kmin) : 0;
+    const unsigned grid = (unsigned)((old.slots + 255) / 256);
+    for (int i = 0; i < da.args.n; i++) {
+        direct_rebase_kernel<<<grid, 256, 0, ctx.stream>>>(old.args.a[i].acc_lo, da.args.a[i].acc_lo, old.args.a[i].acc_valid, da.args.a[i].acc_valid, old.dt.range, shift,
+                                                           da.dt.range);
+        LAUNCH_CHECK(ctx);
+        AURON_CHECK(!old.args.a[i].acc_hi, "direct_agg_grow: wide accumulators are not rebased");
+    }
+    direct_rebase_kernel<<<grid, 256, 0, ctx.stream>>>(nullptr, nullptr, old.dt.seen, da.dt.seen, old.dt.range, shift, da.dt.range);
+    LAUNCH_CHECK(ctx);
+}
+int64_t direct_agg_span_limit() { return (int64_t)1 << 22; }
+GroupedResult direct_agg_finish(Ctx& ctx, DirectAgg& da, const DType& key_type, bool key_nullable, const int32_t* sel) {
+    GroupedResult res;
+    const int64_t slots = da.slots;
+    Buf occ = dalloc(ctx, bitmap_alloc_bytes(slots));
+    occupied_mask_direct_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, ctx.stream>>>(da.dt, da.args, P<uint32_t>(occ));
+    LAUNCH_CHECK(ctx);
+    int64_t g = 0;
+    Buf slot_ids = mask_to_indices(ctx, P<uint32_t>(occ), slots, &g);
+    res.num_groups = g;
+    res.keys = std::make_shared<Batch>();
+    res.keys->num_rows = g;
+    auto kc = make_column(ctx, key_type, g, key_nullable);
+    if (g) {
+        emit_direct_keys_kernel<<<(unsigned)((g + 255) / 256), 256, 0, ctx.stream>>>(da.dt, P<int32_t>(slot_ids), g, key_type.id, kc->data->ptr, P<uint32_t>(kc->validity));
+        LAUNCH_CHECK(ctx);
+    }
+    res.keys->cols.push_back(kc);
+    emit_accs(ctx, da.specs, da.args, P<int32_t>(slot_ids), g, sel, res.accs);
+    return res;
+}
+
 GroupedResult hash_aggregate(Ctx& ctx, const std::vector<ColumnPtr>& keys, const std::vector<AccSpec>& accs, const int32_t* sel,
                              int64_t n_rows, const DType* fast_key_out, const uint32_t* selmask, int64_t n_selected) {
     // selmask != nullptr: a filter's pending bit mask over the batch rows (n_rows = batch rows, n_selected = set bits); the
@@ -968,52 +1071,22 @@ GroupedResult hash_aggregate(Ctx& ctx, const std::vector<ColumnPtr>& keys, const
         const bool any = h[0] <= h[1];
         const unsigned long long span = any ? (unsigned long long)h[1] - (unsigned long long)h[0] : 0ull;
         if (span < (1ull << 22)) {
-            DirectTable dt;
-            dt.kmin = any ? h[0] : 0;
-            dt.range = any ? (int64_t)span + 1 : 0;
-            const int64_t slots = dt.range + 1;   // + the NULL group
-            AccBuffers bufs;
-            AccArgs args = prepare_accs(ctx, accs, slots, bufs);
-            init_accs(ctx, accs, args, slots);
-            Buf seen = dalloc_zero(ctx, (size_t)slots + 8);
-            dt.seen = P<uint8_t>(seen);
-            Buf oor = dalloc_zero(ctx, 4);
-            dt.oor = P<int32_t>(oor);
+            auto da = direct_agg_create(ctx, accs, any ? h[0] : 0, any ? h[1] : -1);
             {
                 ProfScope ps(ctx, "agg_update");
-                if (has_str) agg_direct_kernel<true><<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(k, dt, args, sel, n_rows, selmask);
-                else agg_direct_kernel<false><<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(k, dt, args, sel, n_rows, selmask);
+                if (has_str) agg_direct_kernel<true><<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(k, da->dt, da->args, sel, n_rows, selmask);
+                else agg_direct_kernel<false><<<agg_grid(ctx, n_rows), 256, 0, ctx.stream>>>(k, da->dt, da->args, sel, n_rows, selmask);
                 LAUNCH_CHECK(ctx);
             }
             bool trusted = !keys[0]->has_range;
-            if (!trusted) {
-                int32_t bad = 0;
-                to_host(ctx, &bad, oor->ptr, 4);
-                trusted = bad == 0;
-            }
+            if (!trusted) trusted = !direct_agg_out_of_range(ctx, *da);
             if (trusted) {
-            Buf occ = dalloc(ctx, bitmap_alloc_bytes(slots));
-            occupied_mask_direct_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, ctx.stream>>>(dt, args, P<uint32_t>(occ));
-            LAUNCH_CHECK(ctx);
-            int64_t g = 0;
-            Buf slot_ids = mask_to_indices(ctx, P<uint32_t>(occ), slots, &g);
-            res.num_groups = g;
-            res.keys = std::make_shared<Batch>();
-            res.keys->num_rows = g;
-            DType kt = keys[0]->type;
-            if (fast_key_out) {
-                AURON_CHECK(kt.is_integer() && fast_key_out->is_integer() && kt.width() <= fast_key_out->width(), "bad widened key type");
-                kt = *fast_key_out;
-            }
-            auto kc = make_column(ctx, kt, g, keys[0]->may_have_nulls());
-            if (g) {
-                emit_direct_keys_kernel<<<(unsigned)((g + 255) / 256), 256, 0, ctx.stream>>>(dt, P<int32_t>(slot_ids), g, kt.id, kc->data->ptr,
-                                                                                             P<uint32_t>(kc->validity));
-                LAUNCH_CHECK(ctx);
-            }
-            res.keys->cols.push_back(kc);
-            emit_accs(ctx, accs, args, P<int32_t>(slot_ids), g, sel, res.accs);
-            return res;
+                DType kt = keys[0]->type;
+                if (fast_key_out) {
+                    AURON_CHECK(kt.is_integer() && fast_key_out->is_integer() && kt.width() <= fast_key_out->width(), "bad widened key type");
+                    kt = *fast_key_out;
+                }
+                return direct_agg_finish(ctx, *da, kt, keys[0]->may_have_nulls(), sel);
             }   // else: the file's statistics did not cover the data -> the hash table below starts from scratch
         }
     }

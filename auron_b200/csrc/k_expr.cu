@@ -2214,6 +2214,16 @@ static bool try_compile_simple(const std::vector<ExprPtr>& conjuncts, const Sche
     return true;
 }
 
+bool predicate_intervals(const VmProgram& p, std::vector<int>* cols, std::vector<int64_t>* lo, std::vector<int64_t>* hi) {
+    if (!p.impl || p.impl->iv_lo.empty()) return false;
+    for (int vt : p.impl->simple_vt)
+        if (vt != VT_I8 && vt != VT_I16 && vt != VT_I32 && vt != VT_I64) return false;
+    *cols = p.impl->simple_cols;
+    *lo = p.impl->iv_lo;
+    *hi = p.impl->iv_hi;
+    return true;
+}
+
 VmProgram compile_predicate(const std::vector<ExprPtr>& conjuncts, const Schema& input) {
     VmProgram p;
     p.impl = std::make_shared<VmProgramImpl>();

@@ -73,6 +73,8 @@ struct AccSpec {
     std::vector<ColumnPtr> extra;     // extra args for COUNT(a,b,..) validity; FIRST merge: is_set column
     DType out_type;                   // accumulator column type
     ColumnPtr gather_from;            // FIRST merge: column the winning position is gathered from (default: input)
+    int input_id = -1;                // producers without input columns (fused scan): identifies the source column, so that
+                                      // SUM(x) pairs with COUNT(x) for its validity
 };
 struct GroupedResult {
     BatchPtr keys;                    // distinct key columns (dense groups)
@@ -84,6 +86,25 @@ struct GroupedResult {
 GroupedResult hash_aggregate(Ctx& ctx, const std::vector<ColumnPtr>& keys, const std::vector<AccSpec>& accs,
                              const int32_t* sel, int64_t n_rows, const DType* fast_key_out = nullptr,
                              const uint32_t* selmask = nullptr, int64_t n_selected = -1);   // selmask: pending filter bit mask (see k_agg.cu)
+// ---- persistent direct-address aggregate table (single integer key with a small value range)
+struct DirectAgg;
+constexpr int kDirectMaxAccs = 16;
+struct DirectAggView {            // device pointers a producer kernel updates: slot = key - kmin, slot `range` = NULL key
+    int32_t n;
+    int32_t kind[kDirectMaxAccs];                 // AccKind
+    unsigned long long* acc[kDirectMaxAccs];      // [range + 1]
+    uint8_t* valid[kDirectMaxAccs];               // [range + 1] "accumulator holds a value" flags, or nullptr (COUNT; SUM paired with a COUNT)
+    uint8_t* seen;                                // [range + 1] group exists although no accumulator shows it
+    int32_t* oor;                                 // set to 1 by a producer that meets a key outside the range
+    long long kmin;
+    int64_t range;
+};
+std::shared_ptr<DirectAgg> direct_agg_create(Ctx& ctx, const std::vector<AccSpec>& specs, long long kmin, long long kmax);   // kmin > kmax: empty range
+DirectAggView direct_agg_view(const DirectAgg& da);
+void direct_agg_grow(Ctx& ctx, DirectAgg& da, long long kmin, long long kmax);   // widen to cover [kmin, kmax] as well (rebases the table)
+bool direct_agg_out_of_range(Ctx& ctx, const DirectAgg& da);                      // synchronises
+int64_t direct_agg_span_limit();
+GroupedResult direct_agg_finish(Ctx& ctx, DirectAgg& da, const DType& key_type, bool key_nullable, const int32_t* sel = nullptr);
 // no grouping keys: one output row
 std::vector<ColumnPtr> global_aggregate(Ctx& ctx, const std::vector<AccSpec>& accs, const int32_t* sel, int64_t n_rows,
                                         const uint32_t* selmask = nullptr);

@@ -234,9 +234,12 @@ FilterExec::FilterExec(OperatorPtr input, std::vector<ExprPtr> preds) : predicat
     prog = compile_predicate(predicates, out_schema);
 }
 SelBatch FilterExec::next_sel(Task& t) {
-    SelBatch out;
     BatchPtr b = children[0]->next(t);
-    if (!b) return out;
+    if (!b) return SelBatch();
+    return apply(t, b);
+}
+SelBatch FilterExec::apply(Task& t, const BatchPtr& b) {
+    SelBatch out;
     OpTimer timer(metrics, "elapsed_ns");
     out.batch = b;
     // the selection stays a bit mask until a consumer needs row indices (ensure_sel): Filter -> HashAggregate never does
@@ -638,6 +641,73 @@ BatchPtr AggExec::next_spilled_bucket(Task& t) {
     return nullptr;
 }
 
+// one input batch (with its pending selection) into the partial list
+void AggExec::consume(Task& t, SelBatch& s) {
+    if (s.n == 0 && !group_exprs.empty()) return;
+    BatchPtr p = aggregate_chunk(t, s);
+    partials.push_back(p);
+    partial_rows += p->num_rows;
+    // keep the partial list bounded: re-merge when it outgrows one chunk
+    if (partials.size() > 1 && partial_rows > t.ctx.gpu_chunk_rows) {
+        BatchPtr m = merge_partials(t, concat_batches(t.ctx, partials));
+        partials.clear();
+        partials.push_back(m);
+        partial_rows = m->num_rows;
+    }
+    if (!group_exprs.empty()) {
+        int64_t held = 0;
+        for (auto& b : partials) held += batch_device_bytes(*b);
+        if (held > spill_budget) spill(t);
+    }
+}
+
+// Can this aggregate, its optional FilterExec child and the scan below run as the fused pass?  Single integer group key that
+// is a scan column (possibly under a widening cast), partial-mode SUM(int) / COUNT / MIN / MAX over scan columns, predicates
+// that fold into per-column intervals; everything else keeps the operator-by-operator path.
+void AggExec::setup_fusion() {
+    fuse_checked = true;
+    if (getenv("AURON_DISABLE_FUSED_SCAN_AGG")) return;
+    if (group_exprs.size() != 1 || !all_plain || aggs.empty()) return;
+    Operator* below = children[0].get();
+    FilterExec* flt = dynamic_cast<FilterExec*>(below);
+    if (flt) below = flt->children[0].get();
+    FusedScanSource* src = dynamic_cast<FusedScanSource*>(below);
+    if (!src) return;
+    FusedAggSpec spec;
+    if (flt && !predicate_intervals(flt->prog, &spec.pred_cols, &spec.pred_lo, &spec.pred_hi)) return;
+    spec.key_col = lowered_plain[0];
+    size_t pos = 1;
+    for (auto& a : aggs) {
+        if (a.mode != MODE_PARTIAL) return;
+        FusedAggSpec::Acc acc;
+        acc.col = a.children.empty() ? -1 : lowered_plain[pos];
+        pos += a.children.size();
+        switch (a.fn) {
+            case AGG_SUM:
+                if (a.acc_types[0].id != T_INT64) return;
+                acc.kind = ACC_SUM_I64;
+                acc.out_type = a.acc_types[0];
+                break;
+            case AGG_COUNT:
+                if (a.children.size() > 1) return;
+                acc.kind = ACC_COUNT;
+                acc.out_type = DType(T_INT64);
+                break;
+            case AGG_MIN: case AGG_MAX:
+                if (!(a.value_type.id == T_INT32 || a.value_type.id == T_DATE32 || a.value_type.id == T_INT64)) return;
+                acc.kind = a.fn == AGG_MIN ? ACC_MIN : ACC_MAX;
+                acc.out_type = a.value_type;
+                break;
+            default: return;
+        }
+        spec.accs.push_back(acc);
+    }
+    if (!src->can_fuse(spec)) return;
+    fused_src = src;
+    fused_filter = flt;
+    fused_spec = spec;
+}
+
 BatchPtr AggExec::next(Task& t) {
     if (output_done) return spilled.empty() ? nullptr : next_spilled_bucket(t);
     bool saw_input = false;
@@ -658,6 +728,44 @@ BatchPtr AggExec::next(Task& t) {
             spill_budget = it->second / 10 * 4;
         }
     }
+    if (!fuse_checked) setup_fusion();
+    while (!input_done && fused_src) {   // ParquetScan -> [Filter] -> this aggregate as one pass per batch (k_fused.cu)
+        AURON_CHECK(t.is_running(), "task killed");
+        OpTimer timer(metrics, "hashing_ns");
+        BatchPtr fb;
+        const int r = fused_src->next_fused(t, fused_spec, fused_state, &fb);
+        if (r == FUSED_END) {
+            input_done = true;
+            if (fused_state.table) {
+                if (direct_agg_out_of_range(t.ctx, *fused_state.table))
+                    fail("parquet column statistics do not cover the values of the group key column (corrupt file?); "
+                         "AURON_DISABLE_FUSED_SCAN_AGG=1 reads it without trusting them");
+                unsigned long long sel_rows = 0;
+                to_host(t.ctx, &sel_rows, fused_state.selected->ptr, 8);
+                if (fused_filter) fused_filter->metrics.add("output_rows", (int64_t)sel_rows);
+                metrics.add("fused_scan_rows", fused_state.rows);
+                const DType key_type = has_widened_key ? widened_key_type : children[0]->out_schema.fields[(size_t)fused_spec.key_col].type;
+                GroupedResult g = direct_agg_finish(t.ctx, *fused_state.table, key_type, fused_state.key_nullable);
+                auto pb = std::make_shared<Batch>();
+                pb->num_rows = g.num_groups;
+                pb->cols = g.keys->cols;
+                for (auto& c : g.accs) pb->cols.push_back(c);
+                fused_state.table.reset();
+                if (pb->num_rows) {
+                    partials.push_back(pb);
+                    partial_rows += pb->num_rows;
+                }
+            }
+        } else if (r == FUSED_FALLBACK) {
+            SelBatch s;
+            if (fused_filter) s = fused_filter->apply(t, fb);
+            else {
+                s.batch = fb;
+                s.n = fb->num_rows;
+            }
+            consume(t, s);
+        }
+    }
     while (!input_done) {
         AURON_CHECK(t.is_running(), "task killed");
         SelBatch s = children[0]->next_sel(t);
@@ -666,23 +774,8 @@ BatchPtr AggExec::next(Task& t) {
             break;
         }
         saw_input = true;
-        if (s.n == 0 && !group_exprs.empty()) continue;
         OpTimer timer(metrics, "hashing_ns");
-        BatchPtr p = aggregate_chunk(t, s);
-        partials.push_back(p);
-        partial_rows += p->num_rows;
-        // keep the partial list bounded: re-merge when it outgrows one chunk
-        if (partials.size() > 1 && partial_rows > t.ctx.gpu_chunk_rows) {
-            BatchPtr m = merge_partials(t, concat_batches(t.ctx, partials));
-            partials.clear();
-            partials.push_back(m);
-            partial_rows = m->num_rows;
-        }
-        if (!group_exprs.empty()) {
-            int64_t held = 0;
-            for (auto& b : partials) held += batch_device_bytes(*b);
-            if (held > spill_budget) spill(t);
-        }
+        consume(t, s);
     }
     (void)saw_input;
     output_done = true;

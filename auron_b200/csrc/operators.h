@@ -22,6 +22,37 @@ struct FFIReaderExec : Operator {
     BatchPtr next(Task& t) override;
 };
 
+// ---- fused ParquetScan -> Filter -> HashAggregate (k_fused.cu): the handshake between AggExec and a scan that can run the
+// three operators as one pass over the encoded pages.  The operator tree keeps its shape (metrics are reported per plan node,
+// metrics.rs:22-50); AggExec pulls `next_fused` instead of `next_sel` when its own expressions, its FilterExec child's
+// predicates and the scan's column types allow it.
+struct FusedAggSpec {
+    std::vector<int> pred_cols;              // scan output columns under a closed-interval test (NULL never passes)
+    std::vector<int64_t> pred_lo, pred_hi;
+    int key_col = -1;                        // scan output column of the single group key
+    struct Acc {
+        int kind;                            // AccKind: ACC_SUM_I64 / ACC_COUNT / ACC_MIN / ACC_MAX
+        int col;                             // scan output column of the argument, -1 = COUNT(*)
+        DType out_type;                      // accumulator column type
+    };
+    std::vector<Acc> accs;
+};
+struct FusedAggState {
+    std::shared_ptr<DirectAgg> table;        // persistent direct-address table, widened batch by batch
+    Buf selected;                            // device u64: rows that passed the predicates
+    bool has_range = false, key_nullable = false;
+    long long kmin = 0, kmax = -1;
+    int64_t rows = 0, batches = 0;
+};
+enum { FUSED_END = 0, FUSED_DONE = 1, FUSED_FALLBACK = 2 };
+struct FusedScanSource {
+    virtual ~FusedScanSource() = default;
+    virtual bool can_fuse(const FusedAggSpec& spec) const = 0;
+    // FUSED_DONE: the next batch went through the fused kernels into `st`; FUSED_FALLBACK: it could not, *fallback holds it as
+    // a regular batch; FUSED_END: no more input (all kernels of earlier batches have completed)
+    virtual int next_fused(Task& t, const FusedAggSpec& spec, FusedAggState& st, BatchPtr* fallback) = 0;
+};
+
 // filter_exec.rs:128-224
 struct FilterExec : Operator {
     std::vector<ExprPtr> predicates;
@@ -30,6 +61,7 @@ struct FilterExec : Operator {
     std::string describe() const override;
     BatchPtr next(Task& t) override;
     SelBatch next_sel(Task& t) override;
+    SelBatch apply(Task& t, const BatchPtr& b);   // the predicates over one batch
 };
 
 // project_exec.rs:135-232 (fuses with a FilterExec child through next_sel)
@@ -79,6 +111,12 @@ struct AggExec : Operator {
     std::vector<std::vector<ArrowArray>> spilled;   // [bucket] -> host-resident pieces ([group cols..., acc cols...])
     Schema spill_schema;
     int out_bucket = 0;
+    // fused scan -> filter -> aggregate (see FusedScanSource)
+    bool fuse_checked = false;
+    FusedScanSource* fused_src = nullptr;
+    FilterExec* fused_filter = nullptr;
+    FusedAggSpec fused_spec;
+    FusedAggState fused_state;
     AggExec(OperatorPtr input, std::vector<ExprPtr> group_exprs, std::vector<std::string> group_names, std::vector<AggExprSpec> aggs);
     ~AggExec() override;
     std::string describe() const override;
@@ -86,6 +124,8 @@ struct AggExec : Operator {
 
    private:
     void spill(Task& t);
+    void setup_fusion();
+    void consume(Task& t, SelBatch& s);
     BatchPtr next_spilled_bucket(Task& t);
     BatchPtr aggregate_chunk(Task& t, SelBatch& s);
     BatchPtr merge_partials(Task& t, const BatchPtr& all);

@@ -76,4 +76,83 @@ void pq_scout_many(Ctx& ctx, const std::vector<PqPrepared*>& cols);
 void pq_decode_prepared(Ctx& ctx, const PqPrepared& pr);
 ColumnPtr pq_build_value_table(Ctx& ctx, const std::vector<PqByteSection>& secs, int64_t total_values, const DType& type);
 
+// ---- fused ParquetScan -> Filter -> HashAggregate (k_fused.cu) -------------------------------------------------------
+// The three operators of BASELINE config 2 run as ONE pass over the encoded pages: row tiles of FZ_TILE rows are unpacked
+// into shared memory, the filter's per-column intervals are tested, and the selected rows update the direct-address
+// accumulators -- the decoded Arrow columns are never written to HBM (parquet_exec.rs:151-204 -> filter_exec.rs:200-224 ->
+// agg/agg_table.rs:99-135 as one kernel).  Pages of different columns need not line up: the scout cuts every page at the
+// global-row multiples of FZ_TILE ("segments"), so a tile of any column is a short list of segments.
+constexpr int FZ_TILE = 1024;
+constexpr int FZ_MAX_COLS = 8;    // role-columns (a column used as predicate and as key counts twice)
+constexpr int FZ_MAX_ACCS = 6;
+// checkpoint of an RLE / bit-packed hybrid stream (offsets relative to the stream's first byte)
+struct HybridCk {
+    int32_t p_off, run_remaining, bp_base_off, bp_consumed;
+    uint32_t rle_value;
+    int32_t is_rle;
+};
+struct FzSeg {                    // rows [row0, row0 + n) of one page, all inside one global tile
+    int32_t page, row0, n, nvalid;   // nvalid: non-null values among them
+    int64_t v0;                      // non-null values of the page before row0
+    HybridCk idx;                    // dictionary-index stream at the segment's first value
+};
+struct FzScoutCol {               // one physical column to scout
+    const PqPage* pages;
+    int32_t n_pages, max_def;
+    const int32_t* seg_base;      // [n_pages + 1] first segment of every page
+    FzSeg* segs;
+    int32_t* first_seg;           // [n_tiles] segment that starts global tile T
+    uint32_t* valid;              // batch-wide validity bitmap (zeroed; nullptr when max_def == 0)
+};
+enum { FZ_PRED = 0, FZ_KEY = 1, FZ_VALUE = 2 };
+struct FzColumn {                 // one role-column of the fused kernel
+    const PqPage* pages;
+    const PqDict* dicts;
+    const FzSeg* segs;
+    const int32_t* first_seg;
+    const uint32_t* valid;
+    int32_t role, pad;
+    int64_t lo, hi;               // FZ_PRED: closed interval the value must lie in (NULL never passes)
+    const uint32_t* pass_bits;    // FZ_PRED: the interval test evaluated on every dictionary entry, one bit each
+    const int32_t* pass_off;      //          [n_dicts] first word of each dictionary in pass_bits
+    const int32_t* dslot_base;    // FZ_KEY : [n_dicts] first slot of each dictionary in the dictionary-space accumulators
+};
+struct FzAcc {
+    int32_t kind;                 // AccKind: ACC_SUM_I64, ACC_COUNT, ACC_MIN, ACC_MAX
+    int32_t col;                  // role-column holding the argument, -1 = COUNT(*)
+    unsigned long long* direct;   // [range + 1] accumulators addressed by key - kmin (slot `range` = NULL key)
+    unsigned long long* dspace;   // [dict_slots] accumulators addressed by dictionary entry (merged into `direct` after the batch)
+    uint8_t* direct_valid;        // "holds a value" flags or nullptr
+    uint8_t* dspace_valid;
+};
+struct FzLaunch {
+    FzColumn col[FZ_MAX_COLS];
+    FzAcc acc[FZ_MAX_ACCS];
+    int32_t ncols, npred, key_col, nacc;
+    int64_t n_rows;
+    int32_t n_tiles, pad;
+    long long kmin;
+    int64_t range;
+    uint8_t* seen_direct;
+    uint8_t* seen_dspace;
+    int32_t* oor;                         // a key outside [kmin, kmin + range): the column statistics were wrong
+    unsigned long long* selected_rows;    // rows that passed the predicates (FilterExec's output_rows)
+};
+struct FzMerge {                  // dictionary space -> direct table, one launch per batch
+    const PqDict* dicts;
+    const int32_t* dslot_base;    // [n_dicts + 1]
+    int32_t n_dicts, nacc;
+    FzAcc acc[FZ_MAX_ACCS];
+    long long kmin;
+    int64_t range;
+    uint8_t* seen_direct;
+    const uint8_t* seen_dspace;
+    int32_t* oor;
+};
+void fz_scout(Ctx& ctx, const std::vector<FzScoutCol>& cols);
+void fz_dict_pass(Ctx& ctx, const PqDict* dicts, const int32_t* pass_off, int n_dicts, int total_words, int64_t lo, int64_t hi, uint32_t* pass_bits);
+void fz_init_dspace(Ctx& ctx, const FzLaunch& L, int64_t dict_slots);
+void fz_run(Ctx& ctx, const FzLaunch& L);
+void fz_merge(Ctx& ctx, const FzMerge& M, int64_t dict_slots);
+
 }  // namespace auron

@@ -207,7 +207,9 @@ HostArray decode_list_scalar_ipc(const uint8_t* bytes, size_t n) {
     out.len = last - first;
     int64_t vl;
     const uint8_t* cv = buf(2, &vl);
+    AURON_CHECK(child_len >= 0 && child_len <= (int64_t)INT32_MAX, "list ScalarValue: bad child length");
     if (child_nulls > 0 && vl > 0) {
+        AURON_CHECK(vl >= ((int64_t)last + 7) / 8, "list ScalarValue: short validity buffer");
         out.validity.assign((size_t)((out.len + 7) / 8), 0);
         for (int64_t i = 0; i < out.len; i++)
             if ((cv[(first + i) >> 3] >> ((first + i) & 7)) & 1) out.validity[(size_t)(i >> 3)] |= (uint8_t)(1u << (i & 7));
@@ -219,12 +221,17 @@ HostArray decode_list_scalar_ipc(const uint8_t* bytes, size_t n) {
         AURON_CHECK(ol >= (child_len + 1) * 4, "list ScalarValue: short offsets buffer");
         const int32_t b0 = FbTable::rd<int32_t>(co + 4 * (size_t)first);
         out.offsets.resize((size_t)out.len + 1);
-        for (int64_t i = 0; i <= out.len; i++) out.offsets[(size_t)i] = FbTable::rd<int32_t>(co + 4 * (size_t)(first + i)) - b0;
-        AURON_CHECK(b0 >= 0 && b0 + out.offsets.back() <= dl, "list ScalarValue: string data outside the buffer");
+        AURON_CHECK(b0 >= 0 && b0 <= dl, "list ScalarValue: string data outside the buffer");
+        for (int64_t i = 0; i <= out.len; i++) {
+            const int32_t o = FbTable::rd<int32_t>(co + 4 * (size_t)(first + i));
+            AURON_CHECK(o >= b0 && o <= dl && (i == 0 || o - b0 >= out.offsets[(size_t)i - 1]), "list ScalarValue: string offsets are not monotonic inside the data buffer");
+            out.offsets[(size_t)i] = o - b0;
+        }
         out.data.assign(cd + b0, cd + b0 + out.offsets.back());
     } else if (out.type.id == T_BOOL) {
         int64_t dl;
         const uint8_t* cd = buf(3, &dl);
+        AURON_CHECK(dl >= ((int64_t)last + 7) / 8, "list ScalarValue: short boolean data buffer");
         out.data.assign((size_t)((out.len + 7) / 8), 0);
         for (int64_t i = 0; i < out.len; i++)
             if ((cd[(first + i) >> 3] >> ((first + i) & 7)) & 1) out.data[(size_t)(i >> 3)] |= (uint8_t)(1u << (i & 7));
@@ -716,7 +723,7 @@ static OperatorPtr decode_join(Task& t, const uint8_t* b, size_t n, int kind /*0
     Schema schema;
     OperatorPtr left, right;
     std::vector<ExprPtr> lk, rk;
-    int jt = JOIN_INNER, side = SIDE_RIGHT;
+    int jt = JOIN_INNER, side = SIDE_LEFT;   // proto3: a zero-valued enum (LEFT_SIDE = 0) is not on the wire
     bool null_aware = false;
     std::string cache_id;
     while (r.next(&f, &w)) {

@@ -117,7 +117,7 @@ struct LeafColumn {
     pq::SchemaElement el;
 };
 
-struct ParquetScanExec : Operator {
+struct ParquetScanExec : Operator, FusedScanSource {
     std::string describe() const override {
         std::string o = "\"fs_resource_id\":" + json_quote(fs_id) + ",\"projection\":[";
         for (size_t i = 0; i < projection.size(); i++) o += (i ? "," : "") + std::to_string(projection[i]);
@@ -941,6 +941,13 @@ struct ParquetScanExec : Operator {
     }
 
     ~ParquetScanExec() override {
+        if (inflight) {   // fused batch still running: its landing buffers go back only once the kernels are done
+            cudaEventSynchronize(inflight->done);
+            cudaEventDestroy(inflight->done);
+            if (inflight->sg.dec0) cudaEventDestroy(inflight->sg.dec0);
+            release(*inflight->sg.ready);
+            inflight.reset();
+        }
         stop();
         if (copy_stream) {
             cudaStreamSynchronize(copy_stream);
@@ -979,8 +986,17 @@ struct ParquetScanExec : Operator {
         return p;
     }
 
-    BatchPtr next(Task& t) override {
-        OpTimer timer(metrics, "elapsed_ns");
+    // One batch taken from the prefetch pipeline with its descriptors merged and its page decompression queued
+    struct Staged {
+        std::unique_ptr<Prepared> ready;
+        Buf status;            // page decompression status word (device)
+        bool has_jobs = false;
+        cudaEvent_t dec0 = nullptr;
+        bool tl = false;
+    };
+    // nullptr ready = end of the scan
+    Staged stage_next(Task& t) {
+        Staged sg;
         AURON_CHECK(t.is_running(), "task killed");
         std::unique_ptr<Prepared> ready;
         {
@@ -994,27 +1010,23 @@ struct ParquetScanExec : Operator {
                             timeline[i].copy0, timeline[i].copy1, timeline[i].dec0, timeline[i].dec1);
                 timeline.clear();
             }
-            return nullptr;
+            return sg;
         }
         const bool tl = want_timeline && t.ctx.profile;
-        cudaEvent_t dec0 = nullptr, dec1 = nullptr;
+        sg.tl = tl;
+        cudaEvent_t dec0 = nullptr;
         if (tl && !tl_base) {
             CUDA_OK(cudaEventCreate(&tl_base));
             CUDA_OK(cudaEventRecord(tl_base, t.ctx.stream));
         }
-        struct Releaser {
+        struct Guard {   // an exception below must not leak the landing buffers
             ParquetScanExec* op;
-            Prepared* p;
-            cudaStream_t st;
+            std::unique_ptr<Prepared>* p;
             int exc;
-            ~Releaser() {
-                if (std::uncaught_exceptions() > exc) {   // decode kernels may still read the landing buffer
-                    for (auto& l : op->lanes) cudaStreamSynchronize(l->stream);
-                    cudaStreamSynchronize(st);
-                }
-                op->release(*p);
+            ~Guard() {
+                if (std::uncaught_exceptions() > exc && *p) op->release(**p);
             }
-        } releaser{this, ready.get(), t.ctx.stream, std::uncaught_exceptions()};
+        } guard{this, &ready, std::uncaught_exceptions()};
         metrics.add("fetch_ns", ready->fetch_ns);
         metrics.add("parse_ns", ready->parse_ns);
         if (ready->dev_bytes) {
@@ -1023,7 +1035,6 @@ struct ParquetScanExec : Operator {
         }
         if (tl) {
             CUDA_OK(cudaEventCreate(&dec0));
-            CUDA_OK(cudaEventCreate(&dec1));
             CUDA_OK(cudaEventRecord(dec0, t.ctx.stream));
         }
         Prepared& p = *ready;
@@ -1153,32 +1164,63 @@ struct ParquetScanExec : Operator {
             }
         });
         delete tmerge;
-        BatchPtr b;
         {
-            OpTimer timer2(metrics, "decode_ns");
             Ctx& dc = (use_lanes && !decomp_jobs.empty()) ? lane(t, kLanes) : t.ctx;
             if (&dc != &t.ctx) chain(t.ctx.stream, dc.stream);   // scratch allocated, chunk bytes uploaded
             PqDecompOut dec = pq_decompress(dc, decomp_jobs);
-            Buf status = dec.status;
+            sg.status = dec.status;
+            sg.has_jobs = !decomp_jobs.empty();
+            decomp_results_buf = dec.results;
             decomp_results = P<PqDecompResult>(dec.results);
             if (&dc != &t.ctx) {
                 CUDA_OK(cudaEventCreateWithFlags(&decomp_done, cudaEventDisableTiming));
                 CUDA_OK(cudaEventRecord(decomp_done, dc.stream));
             }
-            struct EvGuard {
-                cudaEvent_t& e;
-                ~EvGuard() {
-                    if (e) cudaEventDestroy(e);
-                    e = nullptr;
+        }
+        sg.dec0 = dec0;
+        sg.ready = std::move(ready);
+        return sg;
+    }
+    Buf decomp_results_buf;   // keeps the results of the batch being decoded alive
+    void check_decomp_status(Task& t, const Staged& sg) {   // synchronises
+        if (!sg.has_jobs) return;
+        int32_t st = 0;
+        to_host(t.ctx, &st, sg.status->ptr, 4);
+        AURON_CHECK(st == 0, "corrupt Snappy page in the parquet file (decompression job " + std::to_string(st - 1) + ")");
+    }
+
+    BatchPtr next(Task& t) override {
+        OpTimer timer(metrics, "elapsed_ns");
+        retire_fused(t);
+        Staged sg = stage_next(t);
+        if (!sg.ready) return nullptr;
+        return decode_staged(t, sg);
+    }
+    // the regular path: Arrow columns of the staged batch
+    BatchPtr decode_staged(Task& t, Staged& sg) {
+        Prepared& p = *sg.ready;
+        struct Releaser {
+            ParquetScanExec* op;
+            Prepared* p;
+            cudaStream_t st;
+            int exc;
+            ~Releaser() {
+                if (std::uncaught_exceptions() > exc) {   // decode kernels may still read the landing buffer
+                    for (auto& l : op->lanes) cudaStreamSynchronize(l->stream);
+                    cudaStreamSynchronize(st);
                 }
-            } evg{decomp_done};
-            b = build_batch(t, p.cols, p.rows);   // ends with a stream sync of the task stream, which has joined every lane
-            decomp_results = nullptr;
-            if (!decomp_jobs.empty()) {
-                int32_t st = 0;
-                to_host(t.ctx, &st, status->ptr, 4);
-                AURON_CHECK(st == 0, "corrupt Snappy page in the parquet file (decompression job " + std::to_string(st - 1) + ")");
+                op->release(*p);
+                if (op->decomp_done) cudaEventDestroy(op->decomp_done);
+                op->decomp_done = nullptr;
+                op->decomp_results = nullptr;
+                op->decomp_results_buf.reset();
             }
+        } releaser{this, sg.ready.get(), t.ctx.stream, std::uncaught_exceptions()};
+        BatchPtr b;
+        {
+            OpTimer timer2(metrics, "decode_ns");
+            b = build_batch(t, p.cols, p.rows);   // ends with a stream sync of the task stream, which has joined every lane
+            check_decomp_status(t, sg);
         }
         if (p.copy_begin && p.copied) {
             float ms = 0;
@@ -1186,7 +1228,9 @@ struct ParquetScanExec : Operator {
             CUDA_OK(cudaEventElapsedTime(&ms, p.copy_begin, p.copied));
             metrics.add("h2d_device_us", (int64_t)(ms * 1000));
         }
-        if (tl) {
+        if (sg.tl) {
+            cudaEvent_t dec1 = nullptr;
+            CUDA_OK(cudaEventCreate(&dec1));
             CUDA_OK(cudaEventRecord(dec1, t.ctx.stream));
             CUDA_OK(cudaEventSynchronize(dec1));
             TimelineRow r{0, 0, 0, 0, p.rows};
@@ -1194,14 +1238,270 @@ struct ParquetScanExec : Operator {
                 cudaEventElapsedTime(&r.copy0, tl_base, p.copy_begin);
                 cudaEventElapsedTime(&r.copy1, tl_base, p.copied);
             }
-            cudaEventElapsedTime(&r.dec0, tl_base, dec0);
+            cudaEventElapsedTime(&r.dec0, tl_base, sg.dec0);
             cudaEventElapsedTime(&r.dec1, tl_base, dec1);
             timeline.push_back(r);
-            cudaEventDestroy(dec0);
+            cudaEventDestroy(sg.dec0);
             cudaEventDestroy(dec1);
+            sg.dec0 = nullptr;
         }
         metrics.add("output_rows", b->num_rows);
         return b;
+    }
+
+    // ------------------------------------------------------------------------------------------ fused scan -> filter -> aggregate
+    // (FusedScanSource, operators.h; kernels in k_fused.cu).  A batch whose columns the fused kernels cannot take (strings,
+    // INT64 / FLBA physical types, missing statistics of the key, a key range too wide for the direct table) comes back as a
+    // regular batch and the caller runs the unfused operators on it.
+    struct Inflight {   // the batch whose kernels are still running: its landing buffers are recycled once they are done
+        Staged sg;
+        cudaEvent_t done = nullptr;
+    };
+    std::unique_ptr<Inflight> inflight;
+    void retire_fused(Task& t) {
+        if (!inflight) return;
+        std::unique_ptr<Inflight> f = std::move(inflight);
+        cudaEventSynchronize(f->done);
+        cudaEventDestroy(f->done);
+        struct R {
+            ParquetScanExec* op;
+            Prepared* p;
+            ~R() { op->release(*p); }
+        } r{this, f->sg.ready.get()};
+        if (f->sg.dec0) cudaEventDestroy(f->sg.dec0);
+        check_decomp_status(t, f->sg);
+    }
+    static bool fused_type_ok(const DType& t) { return t.id == T_INT32 || t.id == T_DATE32 || t.id == T_INT64; }
+    bool can_fuse(const FusedAggSpec& spec) const override {
+        if (use_lanes || getenv("AURON_DISABLE_FUSED_SCAN_AGG")) return false;
+        auto col_ok = [&](int c) { return c >= 0 && c < (int)projection.size() && fused_type_ok(table_schema.fields[projection[c]].type); };
+        if (!col_ok(spec.key_col)) return false;
+        for (int c : spec.pred_cols)
+            if (!col_ok(c)) return false;
+        for (auto& a : spec.accs)
+            if (a.col >= 0 && !col_ok(a.col)) return false;
+        return (int)spec.accs.size() <= FZ_MAX_ACCS;
+    }
+    int next_fused(Task& t, const FusedAggSpec& spec, FusedAggState& st, BatchPtr* fallback) override {
+        OpTimer timer(metrics, "elapsed_ns");
+        Staged sg = stage_next(t);
+        if (!sg.ready) {
+            retire_fused(t);
+            return FUSED_END;
+        }
+        bool ok = false;
+        try {
+            ok = run_fused(t, sg, spec, st);
+        } catch (...) {
+            cudaStreamSynchronize(t.ctx.stream);
+            release(*sg.ready);
+            throw;
+        }
+        if (!ok) {
+            retire_fused(t);
+            *fallback = decode_staged(t, sg);
+            return FUSED_FALLBACK;
+        }
+        // the kernels of this batch are queued: now wait for the previous batch and recycle its buffers
+        auto f = std::make_unique<Inflight>();
+        CUDA_OK(cudaEventCreateWithFlags(&f->done, cudaEventDisableTiming));
+        CUDA_OK(cudaEventRecord(f->done, t.ctx.stream));
+        metrics.add("output_rows", sg.ready->rows);
+        metrics.add("fused_batches", 1);
+        f->sg = std::move(sg);
+        retire_fused(t);
+        inflight = std::move(f);
+        decomp_results = nullptr;
+        decomp_results_buf.reset();
+        return FUSED_DONE;
+    }
+    bool run_fused(Task& t, Staged& sg, const FusedAggSpec& spec, FusedAggState& st) {
+        Prepared& p = *sg.ready;
+        const int64_t n_rows = p.rows;
+        if (n_rows <= 0 || n_rows >= (int64_t)INT32_MAX - FZ_TILE) return false;
+        // distinct physical columns
+        std::vector<int> used;
+        auto phys_of = [&](int c) {
+            for (size_t i = 0; i < used.size(); i++)
+                if (used[i] == c) return (int)i;
+            used.push_back(c);
+            return (int)used.size() - 1;
+        };
+        for (int c : spec.pred_cols) phys_of(c);
+        phys_of(spec.key_col);
+        for (auto& a : spec.accs)
+            if (a.col >= 0) phys_of(a.col);
+        for (int c : used) {
+            const ColState& cs = p.cols[(size_t)c];
+            const DType& ft = table_schema.fields[projection[(size_t)c]].type;
+            if (cs.leaf < 0 || cs.is_string || cs.el.type != pq::PT_INT32 || !fused_type_ok(ft)) return false;
+        }
+        // key range of this batch from the column-chunk statistics; the table is widened to the union
+        const ColState& kcs = p.cols[(size_t)spec.key_col];
+        if (!kcs.stat_ok || getenv("AURON_SCAN_NO_STATS")) return false;
+        long long bmin = kcs.stat_min, bmax = kcs.stat_max;   // min > max: every key of the batch is NULL
+        long long umin = bmin, umax = bmax;
+        if (st.table && st.has_range) {
+            if (bmin <= bmax) {
+                umin = std::min<long long>(bmin, st.kmin);
+                umax = std::max<long long>(bmax, st.kmax);
+            } else {
+                umin = st.kmin;
+                umax = st.kmax;
+            }
+        }
+        if (umin <= umax && (unsigned long long)umax - (unsigned long long)umin >= (unsigned long long)direct_agg_span_limit()) return false;
+        int64_t dict_slots = 0;
+        for (auto& d : kcs.dicts) dict_slots += d.num_values;
+        if (dict_slots >= (int64_t)1 << 31) return false;
+
+        const int n_tiles = (int)((n_rows + FZ_TILE - 1) / FZ_TILE);
+        struct Phys {
+            Buf dpages, ddicts, seg_base, segs, first_seg, valid;
+        };
+        std::vector<Phys> ph(used.size());
+        std::vector<FzScoutCol> scout;
+        for (size_t u = 0; u < used.size(); u++) {
+            ColState& cs = p.cols[(size_t)used[u]];
+            const int max_def = cs.el.repetition == 1 ? 1 : 0;
+            Phys& x = ph[u];
+            x.dpages = to_device(t.ctx, cs.pages.data(), cs.pages.size() * sizeof(PqPage));
+            x.ddicts = to_device(t.ctx, cs.dicts.empty() ? (const void*)"" : (const void*)cs.dicts.data(), cs.dicts.size() * sizeof(PqDict));
+            if (cs.has_v1_inline) pq_fix_v1_pages(t.ctx, P<PqPage>(x.dpages), (int)cs.pages.size(), decomp_results);
+            std::vector<int32_t> sb(cs.pages.size() + 1, 0);
+            for (size_t i = 0; i < cs.pages.size(); i++) {
+                const int64_t r0 = cs.pages[i].row_start, n = cs.pages[i].num_values;
+                sb[i + 1] = sb[i] + (n > 0 ? (int32_t)((r0 + n - 1) / FZ_TILE - r0 / FZ_TILE + 1) : 0);
+            }
+            x.seg_base = to_device(t.ctx, sb.data(), sb.size() * 4);
+            x.segs = dalloc(t.ctx, (size_t)std::max<int32_t>(sb.back(), 1) * sizeof(FzSeg));
+            x.first_seg = dalloc_zero(t.ctx, (size_t)n_tiles * 4);
+            if (max_def > 0) x.valid = dalloc_zero(t.ctx, (size_t)n_tiles * (FZ_TILE / 8));
+            FzScoutCol sc;
+            sc.pages = P<PqPage>(x.dpages);
+            sc.n_pages = (int32_t)cs.pages.size();
+            sc.max_def = max_def;
+            sc.seg_base = P<int32_t>(x.seg_base);
+            sc.segs = P<FzSeg>(x.segs);
+            sc.first_seg = P<int32_t>(x.first_seg);
+            sc.valid = P<uint32_t>(x.valid);
+            scout.push_back(sc);
+            if (max_def > 0 && (size_t)used[u] == (size_t)spec.key_col) st.key_nullable = true;
+        }
+        fz_scout(t.ctx, scout);
+
+        FzLaunch L;
+        memset(&L, 0, sizeof(L));
+        std::vector<Buf> keep;
+        auto add_role = [&](int c, int role) {
+            AURON_CHECK(L.ncols < FZ_MAX_COLS, "too many columns in the fused scan");
+            const Phys& x = ph[(size_t)phys_of(c)];
+            FzColumn& C = L.col[L.ncols];
+            C.pages = P<PqPage>(x.dpages);
+            C.dicts = P<PqDict>(x.ddicts);
+            C.segs = P<FzSeg>(x.segs);
+            C.first_seg = P<int32_t>(x.first_seg);
+            C.valid = P<uint32_t>(x.valid);
+            C.role = role;
+            return L.ncols++;
+        };
+        for (size_t i = 0; i < spec.pred_cols.size(); i++) {
+            const int c = spec.pred_cols[i];
+            const int rc = add_role(c, FZ_PRED);
+            const ColState& cs = p.cols[(size_t)c];
+            L.col[rc].lo = spec.pred_lo[i];
+            L.col[rc].hi = spec.pred_hi[i];
+            std::vector<int32_t> off(cs.dicts.size() + 1, 0);
+            for (size_t d = 0; d < cs.dicts.size(); d++) off[d + 1] = off[d] + (cs.dicts[d].num_values + 31) / 32;
+            Buf doff = to_device(t.ctx, off.data(), off.size() * 4);
+            Buf bits = dalloc(t.ctx, (size_t)std::max<int32_t>(off.back(), 1) * 4);
+            fz_dict_pass(t.ctx, L.col[rc].dicts, P<int32_t>(doff), (int)cs.dicts.size(), off.back(), spec.pred_lo[i], spec.pred_hi[i], P<uint32_t>(bits));
+            L.col[rc].pass_off = P<int32_t>(doff);
+            L.col[rc].pass_bits = P<uint32_t>(bits);
+            keep.push_back(doff);
+            keep.push_back(bits);
+        }
+        L.npred = L.ncols;
+        L.key_col = add_role(spec.key_col, FZ_KEY);
+        std::vector<int32_t> dbase(kcs.dicts.size() + 1, 0);
+        for (size_t d = 0; d < kcs.dicts.size(); d++) dbase[d + 1] = dbase[d] + kcs.dicts[d].num_values;
+        Buf ddbase = to_device(t.ctx, dbase.data(), dbase.size() * 4);
+        L.col[L.key_col].dslot_base = P<int32_t>(ddbase);
+        std::vector<int> value_role(projection.size(), -1);
+        for (auto& a : spec.accs)
+            if (a.col >= 0 && a.kind != ACC_COUNT && value_role[(size_t)a.col] < 0) value_role[(size_t)a.col] = add_role(a.col, FZ_VALUE);
+        // COUNT(x) only needs x's validity: any role-column over x serves
+        auto any_role = [&](int c) {
+            if (value_role[(size_t)c] >= 0) return value_role[(size_t)c];
+            if (c == spec.key_col) return (int)L.key_col;
+            for (size_t i = 0; i < spec.pred_cols.size(); i++)
+                if (spec.pred_cols[i] == c) return (int)i;
+            return value_role[(size_t)c] = add_role(c, FZ_VALUE);
+        };
+        // the persistent table
+        if (!st.table) {
+            std::vector<AccSpec> specs;
+            for (auto& a : spec.accs) {
+                AccSpec s;
+                s.kind = (AccKind)a.kind;
+                s.out_type = a.out_type;
+                s.input_id = a.col;
+                specs.push_back(s);
+            }
+            st.table = direct_agg_create(t.ctx, specs, umin, umax);
+            st.selected = dalloc_zero(t.ctx, 8);
+        } else {
+            direct_agg_grow(t.ctx, *st.table, umin, umax);
+        }
+        if (umin <= umax) {
+            st.has_range = true;
+            st.kmin = umin;
+            st.kmax = umax;
+        }
+        const DirectAggView dv = direct_agg_view(*st.table);
+        L.nacc = (int)spec.accs.size();
+        Buf dseen = dalloc(t.ctx, (size_t)std::max<int64_t>(dict_slots, 1));
+        for (int a = 0; a < L.nacc; a++) {
+            FzAcc& A = L.acc[a];
+            A.kind = spec.accs[(size_t)a].kind;
+            A.col = spec.accs[(size_t)a].col >= 0 ? any_role(spec.accs[(size_t)a].col) : -1;
+            A.direct = dv.acc[a];
+            A.direct_valid = dv.valid[a];
+            Buf d = dalloc(t.ctx, (size_t)std::max<int64_t>(dict_slots, 1) * 8);
+            keep.push_back(d);
+            A.dspace = P<unsigned long long>(d);
+            if (A.direct_valid) {
+                Buf v = dalloc(t.ctx, (size_t)std::max<int64_t>(dict_slots, 1));
+                keep.push_back(v);
+                A.dspace_valid = P<uint8_t>(v);
+            }
+        }
+        L.n_rows = n_rows;
+        L.n_tiles = n_tiles;
+        L.kmin = dv.kmin;
+        L.range = dv.range;
+        L.seen_direct = dv.seen;
+        L.seen_dspace = P<uint8_t>(dseen);
+        L.oor = dv.oor;
+        L.selected_rows = P<unsigned long long>(st.selected);
+        fz_init_dspace(t.ctx, L, dict_slots);
+        fz_run(t.ctx, L);
+        FzMerge M;
+        memset(&M, 0, sizeof(M));
+        M.dicts = L.col[L.key_col].dicts;
+        M.dslot_base = P<int32_t>(ddbase);
+        M.n_dicts = (int32_t)kcs.dicts.size();
+        M.nacc = L.nacc;
+        for (int a = 0; a < L.nacc; a++) M.acc[a] = L.acc[a];
+        M.kmin = dv.kmin;
+        M.range = dv.range;
+        M.seen_direct = dv.seen;
+        M.seen_dspace = P<uint8_t>(dseen);
+        M.oor = dv.oor;
+        fz_merge(t.ctx, M, dict_slots);
+        st.rows += n_rows;
+        st.batches++;
+        return true;
     }
 };
 

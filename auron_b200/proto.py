@@ -25,7 +25,11 @@ def _varint(n: int) -> bytes:
             return bytes(out)
 
 
-def f_varint(num: int, v: int) -> bytes:
+def f_varint(num: int, v: int, always: bool = False) -> bytes:
+    """proto3 scalar field: a zero value is NOT written (protobuf-java and prost both omit default-valued scalars), so the
+    planner's defaults are exercised the way real plans exercise them.  `always` is for oneof members and packed elements."""
+    if int(v) == 0 and not always:
+        return b""
     return _varint(num << 3) + _varint(int(v))
 
 
@@ -228,7 +232,7 @@ def agg(inp: bytes, grouping: list[bytes], grouping_names: list[str], aggs: list
     body = f_bytes(1, inp) + f_varint(2, exec_mode)
     body += b"".join(f_bytes(3, g) for g in grouping)
     body += b"".join(f_bytes(4, a) for a in aggs)
-    body += b"".join(f_varint(5, AGG_MODE[m]) for m in modes)
+    body += b"".join(f_varint(5, AGG_MODE[m], always=True) for m in modes)   # repeated: every element is written
     body += b"".join(f_str(6, n) for n in grouping_names)
     body += b"".join(f_str(7, n) for n in agg_names)
     body += f_varint(9, int(supports_partial_skipping))
@@ -314,7 +318,7 @@ def parquet_scan(s: pa.Schema, files: list[tuple[str, int]], projection_idx: lis
             pf += f_bytes(5, f_varint(1, ranges[i][0]) + f_varint(2, ranges[i][1]))
         pfiles += f_bytes(1, pf)
     conf = f_varint(1, 1) + f_varint(2, 0) + f_bytes(3, pfiles) + f_bytes(4, schema(s))
-    conf += b"".join(f_varint(6, p) for p in projection_idx)
+    conf += b"".join(f_varint(6, p, always=True) for p in projection_idx)   # repeated
     body = f_bytes(1, conf) + b"".join(f_bytes(2, p) for p in (pruning_predicates or [])) + f_str(3, fs_resource_id)
     return f_bytes(5, body)
 
