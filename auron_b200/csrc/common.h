@@ -119,7 +119,8 @@ struct Ctx {
     int64_t batch_size = 10000;             // auron.batchSize (datafusion-ext-commons/src/lib.rs:72-75)
     int64_t gpu_chunk_rows = 64 << 20;      // device-side accumulation target (SURVEY hard part 2); AURON_GPU_CHUNK_ROWS overrides
     int64_t kernel_launches = 0;            // number of our kernels launched on this ctx
-    explicit Ctx(int dev = 0);
+    // stream_priority: 0 = default; < 0 = higher (kernels queued on it get SM slots before those of lower-priority streams)
+    explicit Ctx(int dev = 0, int stream_priority = 0);
     ~Ctx();
     Ctx(const Ctx&) = delete;
     void sync();   // cudaStreamSynchronize + recycles the staged-upload arena

@@ -33,10 +33,16 @@ std::string DType::str() const {
     return "?";
 }
 
-Ctx::Ctx(int dev) : device(dev) {
+Ctx::Ctx(int dev, int stream_priority) : device(dev) {
     if (dev < 0) return;   // plan-only context (auron_b200_explain): no stream, nothing may be launched on it
     CUDA_OK(cudaSetDevice(dev));
-    CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (stream_priority != 0) {
+        int least = 0, greatest = 0;
+        CUDA_OK(cudaDeviceGetStreamPriorityRange(&least, &greatest));   // numerically lower = higher priority
+        CUDA_OK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, std::max(greatest, std::min(least, stream_priority))));
+    } else {
+        CUDA_OK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    }
     CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     if (const char* e = getenv("AURON_PROFILE")) profile = atoi(e) != 0;
     if (const char* e = getenv("AURON_GPU_CHUNK_ROWS")) {   // device-side accumulation target (tests shrink it to force merges)

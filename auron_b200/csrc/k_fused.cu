@@ -107,6 +107,7 @@ __device__ __forceinline__ void fz_scout_page(const FzScoutCol& C, int page_id, 
     if (dict) idx.init(idx_base, vals + pg.val_len, pg.val_len > 0 ? vals[0] : 0);
     else idx.init(vals, vals, 0);
     const uint8_t* pf_idx = idx_base;
+    const PqDict dd = dict ? C.dicts[pg.dict_id] : PqDict{nullptr, 0, 0};
     int seg = C.seg_base[page_id];
     int64_t v0 = 0;
     for (int r = 0; r < rows; seg++) {
@@ -124,6 +125,13 @@ __device__ __forceinline__ void fz_scout_page(const FzScoutCol& C, int page_id, 
             S.nvalid = nvalid;
             S.v0 = v0;
             S.idx = dict ? hybrid_save(idx, idx_base) : HybridCk{0, 0, 0, 0, 0, 1};
+            S.vals = vals;
+            S.val_len = pg.val_len;
+            S.bw = dict ? (pg.val_len > 0 ? (int32_t)vals[0] : 0) : -1;
+            S.ddata = dict ? dd.data : nullptr;
+            S.ndict = dict ? dd.num_values : 0;
+            S.dict_id = pg.dict_id;
+            S.pad[0] = S.pad[1] = 0;
             C.segs[seg] = S;
             if (((gr0 + r) & (FZ_TILE - 1)) == 0) C.first_seg[(gr0 + r) / FZ_TILE] = seg;
         }
@@ -191,126 +199,133 @@ void fz_dict_pass(Ctx& ctx, const PqDict* dicts, const int32_t* pass_off, int n_
 }
 
 // ------------------------------------------------------------------------------------------------------------ fused kernel
+// One warp per tile of FZ_TILE rows; lane L owns rows [32 L, 32 L + 32) of the tile: its validity word, the number of
+// non-null values before it (warp scan) and its selection word live in registers, so the row loop needs no ballots and no
+// broadcast reads.  Columns are unpacked in VALUE order (rank = position among the non-null values of the tile), lanes
+// striding over each run for coalesced loads:
+//   predicate columns -> one PASS BIT per value in a 32-word rank-space bitmap (dictionary pages: a lookup in the per-entry
+//                        bits of fz_dict_pass; PLAIN pages: the interval test), then every lane deposits its bits into the
+//                        positions of its valid rows;
+//   key column        -> accumulator slot per value (dictionary pages: slot base of the dictionary + index -- no lookup);
+//   argument columns  -> value per value (dictionary lookup at unpack time).
+// A lane then walks the set bits of its selection word.
+//
+// Latency: a tile's page bytes are a few KB per column, first touched by this warp.  Unpacking them step by step paid one DRAM
+// round trip per step (35 % of all stall samples sat on the funnel shift behind those loads); instead the warp asks for ALL lines
+// of ALL columns of the tile at once (prefetch.global.L2) before it starts on the first column.
 constexpr int FZ_WARPS = 4;
-struct FzSmemCol {
-    uint32_t vals[FZ_TILE];   // per non-null value of the tile, in row order: pass bit / accumulator slot / argument value
-    uint32_t w[32];           // validity words of the tile
-    int32_t pref[32];         // non-null values before each word
-};
-struct FzSegCtx {
-    int32_t role;
-    bool dict;
+constexpr int FZ_VSTRIDE = FZ_TILE + 32;    // value planes are padded by one word per 32 (rank r lives at r + r / 32): lanes that
+                                            // read ranks 32 apart (columns without NULLs) hit different banks
+__device__ __forceinline__ int fz_pi(int r) { return r + (r >> 5); }
+
+struct FzX {                // what the transform of one segment needs
+    bool dict, ddata_aligned;
     uint32_t ndict;
     const uint8_t* ddata;
-    const uint32_t* pass;   // FZ_PRED: first pass word of this dictionary
-    uint32_t slot_base;     // FZ_KEY
+    const uint32_t* pass;
+    uint32_t slot_base;
     int64_t lo, hi;
     long long kmin;
     int64_t range;
     int32_t* oor;
 };
-__device__ __forceinline__ uint32_t fz_xform(const FzSegCtx& x, uint32_t raw) {
+template <int ROLE>
+__device__ __forceinline__ uint32_t fz_xform(const FzX& x, uint32_t raw) {
     if (x.dict) {
         const uint32_t i = raw < x.ndict ? raw : 0u;   // corrupt index guard
-        if (x.ndict == 0) return x.role == FZ_KEY ? x.slot_base : 0u;
-        switch (x.role) {
-            case FZ_PRED: return (x.pass[i >> 5] >> (i & 31)) & 1u;
-            case FZ_KEY: return x.slot_base + i;
-            default: return ld_u32_unaligned(x.ddata + (int64_t)i * 4);
-        }
+        if (ROLE == FZ_KEY) return x.slot_base + i;
+        if (x.ndict == 0) return 0u;
+        if (ROLE == FZ_PRED) return (__ldg(x.pass + (i >> 5)) >> (i & 31)) & 1u;
+        if (x.ddata_aligned) return __ldg((const uint32_t*)x.ddata + i);
+        return ld_u32_unaligned(x.ddata + (int64_t)i * 4);
     }
-    switch (x.role) {
-        case FZ_PRED: {
-            const int64_t v = (int64_t)(int32_t)raw;
-            return (v >= x.lo && v <= x.hi) ? 1u : 0u;
+    if (ROLE == FZ_PRED) {
+        const int64_t v = (int64_t)(int32_t)raw;
+        return (v >= x.lo && v <= x.hi) ? 1u : 0u;
+    }
+    if (ROLE == FZ_KEY) {
+        int64_t s = (int64_t)(int32_t)raw - x.kmin;
+        if ((uint64_t)s >= (uint64_t)x.range) {   // the column statistics did not cover this value
+            *x.oor = 1;
+            s = x.range;
         }
-        case FZ_KEY: {
-            int64_t s = (int64_t)(int32_t)raw - x.kmin;
-            if ((uint64_t)s >= (uint64_t)x.range) {   // the column statistics did not cover this value
-                *x.oor = 1;
-                s = x.range;
-            }
-            return 0x80000000u | (uint32_t)s;
+        return 0x80000000u | (uint32_t)s;
+    }
+    return raw;
+}
+// value k of a run -> rank pos + k.  Predicate columns: the ballot of 32 consecutive values is ORed into the rank-space
+// bitmap at bit pos + k0 (two words when it straddles); lane 0 is the only writer of the bitmap.
+template <int ROLE>
+__device__ __forceinline__ void fz_store(uint32_t* dst, uint32_t* d, int rank0, unsigned lane, bool act, uint32_t o) {
+    // value planes: d = &plane[fz_pi(rank0 + lane)], advanced by the caller (33 words per 32 ranks)
+    if (ROLE == FZ_PRED) {
+        const uint32_t word = __ballot_sync(FULL_MASK, act && o != 0);
+        if (lane == 0 && word) {
+            const int sh = rank0 & 31;
+            dst[rank0 >> 5] |= word << sh;
+            if (sh) dst[(rank0 >> 5) + 1] |= word >> (32 - sh);
         }
-        default: return raw;
+    } else if (act) {
+        *d = o;
     }
 }
-// the nvs non-null values of segment S, transformed for the column's role, to dst[0, nvs)
-__device__ __forceinline__ void fz_unpack(const FzLaunch& L, const FzColumn& C, const FzSeg& S, const PqPage& pg, uint32_t* dst, int nvs, unsigned lane) {
-    FzSegCtx x;
-    x.role = C.role;
-    x.dict = pg.encoding == 2 || pg.encoding == 8;
-    x.lo = C.lo;
-    x.hi = C.hi;
-    x.kmin = L.kmin;
-    x.range = L.range;
-    x.oor = L.oor;
-    x.ndict = 0;
-    x.ddata = nullptr;
-    x.pass = nullptr;
-    x.slot_base = 0;
-    const uint8_t* vals = pg.val_ptr;
-    if (x.dict) {
-        const PqDict dd = C.dicts[pg.dict_id];
-        x.ndict = (uint32_t)dd.num_values;
-        x.ddata = dd.data;
-        if (C.role == FZ_PRED) x.pass = C.pass_bits + C.pass_off[pg.dict_id];
-        if (C.role == FZ_KEY) x.slot_base = (uint32_t)C.dslot_base[pg.dict_id];
-        const int bw = pg.val_len > 0 ? vals[0] : 0;
-        Hybrid idx;
-        hybrid_restore(idx, S.idx, vals + 1, vals + pg.val_len, bw);
-        int pos = 0;
-        while (pos < nvs) {
-            if (idx.run_remaining == 0) idx.next_run();
-            const int t = min(nvs - pos, idx.run_remaining);
-            if (idx.is_rle) {
-                const uint32_t o = fz_xform(x, idx.rle_value);
-                for (int k = lane; k < t; k += 32) dst[pos + k] = o;
-            } else {
-                // lane L unpacks values L, L + 32, ...: 32 values are exactly `bw` 32-bit words, so the word pointer advances by
-                // bw per step and the sub-word shift is a per-lane constant of the run
-                const int64_t bit0 = (int64_t)(idx.bp_consumed + (int)lane) * bw;
-                const uintptr_t qa = (uintptr_t)(idx.bp_base + (bit0 >> 3));
-                const uint32_t* wp = (const uint32_t*)(qa & ~(uintptr_t)3);
-                const unsigned sh = (unsigned)(qa & 3) * 8 + (unsigned)(bit0 & 7);
-                const uint32_t vmask = bw >= 32 ? 0xffffffffu : ((1u << bw) - 1u);
-                uint32_t* d = dst + pos + (int)lane;
-                int k = lane;
-                for (; k + 96 < t; k += 128) {   // 4 independent unpacks in flight per lane
-                    uint32_t v[4];
+// t values of a bit-packed run starting at value `first` of the packed area -> ranks [pos, pos + t)
+template <int ROLE>
+__device__ __forceinline__ void fz_unpack_bits(const FzX& x, uint32_t* dst, int pos, int t, unsigned lane, const uint8_t* bp_base, int first, int bw) {
+    // lane L unpacks values L, L + 32, ...: 32 values are exactly `bw` 32-bit words, so the word pointer advances by bw per
+    // step and the sub-word shift is a per-lane constant of the run
+    const int64_t bit0 = (int64_t)(first + (int)lane) * bw;
+    const uintptr_t qa = (uintptr_t)(bp_base + (bit0 >> 3));
+    const uint32_t* wp = (const uint32_t*)(qa & ~(uintptr_t)3);
+    const unsigned sh = (unsigned)(qa & 3) * 8 + (unsigned)(bit0 & 7);
+    const uint32_t vmask = bw >= 32 ? 0xffffffffu : ((1u << bw) - 1u);
+    uint32_t* d = dst + fz_pi(pos + (int)lane);
+    int k0 = 0;
+    for (; k0 + 128 <= t; k0 += 128) {   // 4 groups per step: all eight loads are issued before the first value is used
+        uint32_t lo[4], hi[4];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) v[u] = __funnelshift_r(wp[u * bw], wp[u * bw + 1], sh) & vmask;
+        for (int u = 0; u < 4; u++) {
+            lo[u] = __ldg(wp + u * bw);
+            hi[u] = __ldg(wp + u * bw + 1);
+        }
 #pragma unroll
-                    for (int u = 0; u < 4; u++) d[32 * u] = fz_xform(x, v[u]);
-                    wp += 4 * bw;
-                    d += 128;
-                }
-                for (; k < t; k += 32) {
-                    *d = fz_xform(x, __funnelshift_r(wp[0], wp[1], sh) & vmask);
-                    wp += bw;
-                    d += 32;
-                }
-            }
-            pos += t;
-            idx.run_remaining -= t;
-            if (!idx.is_rle) idx.bp_consumed += t;
-        }
-    } else {   // PLAIN INT32: value k of the segment is the 32-bit word at vals + 4 (v0 + k) (no alignment guarantee)
-        const uintptr_t ba = (uintptr_t)(vals + S.v0 * 4);
-        const uint32_t* bw32 = (const uint32_t*)(ba & ~(uintptr_t)3);
-        const unsigned bsh = (unsigned)(ba & 3) * 8;
-        for (int k = lane; k < nvs; k += 32) {
-            const uint32_t raw = bsh ? __funnelshift_r(bw32[k], bw32[k + 1], bsh) : bw32[k];
-            dst[k] = fz_xform(x, raw);
-        }
+        for (int u = 0; u < 4; u++) fz_store<ROLE>(dst, d + 33 * u, pos + k0 + 32 * u, lane, true, fz_xform<ROLE>(x, __funnelshift_r(lo[u], hi[u], sh) & vmask));
+        wp += 4 * bw;
+        d += 4 * 33;
+    }
+    for (; k0 < t; k0 += 32) {
+        const bool act = k0 + (int)lane < t;
+        uint32_t o = 0;
+        if (act) o = fz_xform<ROLE>(x, __funnelshift_r(__ldg(wp), __ldg(wp + 1), sh) & vmask);
+        fz_store<ROLE>(dst, d, pos + k0, lane, act, o);
+        wp += bw;
+        d += 33;
     }
 }
-// validity words + rank bases + transformed values of role-column c for tile T
-__device__ __forceinline__ void fz_load_col(const FzLaunch& L, int c, int T, int n_tile, FzSmemCol& sc, unsigned lane) {
-    const FzColumn& C = L.col[c];
+template <int ROLE>
+__device__ __forceinline__ void fz_unpack_const(const FzX& x, uint32_t* dst, int pos, int t, unsigned lane, uint32_t raw) {
+    const uint32_t o = fz_xform<ROLE>(x, raw);
+    uint32_t* d = dst + fz_pi(pos + (int)lane);
+    for (int k0 = 0; k0 < t; k0 += 32, d += 33) fz_store<ROLE>(dst, d, pos + k0, lane, k0 + (int)lane < t, o);
+}
+template <int ROLE>
+__device__ __forceinline__ void fz_unpack_plain(const FzX& x, uint32_t* dst, int pos, int t, unsigned lane, const uint8_t* first) {
+    const uintptr_t ba = (uintptr_t)first;   // no alignment guarantee: page payloads sit at arbitrary file offsets
+    const uint32_t* wp = (const uint32_t*)(ba & ~(uintptr_t)3) + lane;
+    const unsigned bsh = (unsigned)(ba & 3) * 8;
+    uint32_t* d = dst + fz_pi(pos + (int)lane);
+    for (int k0 = 0; k0 < t; k0 += 32, wp += 32, d += 33) {
+        const bool act = k0 + (int)lane < t;
+        uint32_t o = 0;
+        if (act) o = fz_xform<ROLE>(x, bsh ? __funnelshift_r(__ldg(wp), __ldg(wp + 1), bsh) : __ldg(wp));
+        fz_store<ROLE>(dst, d, pos + k0, lane, act, o);
+    }
+}
+// validity word + rank base of this lane's rows
+__device__ __forceinline__ void fz_rows(const FzColumn& C, int T, int n_tile, unsigned lane, uint32_t* w_out, int* pref_out) {
     const int cnt = n_tile - 32 * (int)lane;
     uint32_t w = cnt >= 32 ? 0xffffffffu : (cnt > 0 ? (1u << cnt) - 1u : 0u);
-    if (C.valid) w &= C.valid[(int64_t)T * (FZ_TILE / 32) + lane];
+    if (C.valid) w &= __ldg(C.valid + (int64_t)T * (FZ_TILE / 32) + lane);
     const int pc = __popc(w);
     int inc = pc;
 #pragma unroll
@@ -318,98 +333,275 @@ __device__ __forceinline__ void fz_load_col(const FzLaunch& L, int c, int T, int
         const int t = __shfl_up_sync(FULL_MASK, inc, d);
         if ((int)lane >= d) inc += t;
     }
-    sc.w[lane] = w;
-    sc.pref[lane] = inc - pc;
-    int seg = C.first_seg[T], covered = 0, pos = 0;
+    *w_out = w;
+    *pref_out = inc - pc;
+}
+// unpack role-column c of tile T: values / pass bits to shared memory.  Not inlined: the three roles are shared by every
+// instantiation of the kernel below.
+template <int ROLE>
+__device__ __forceinline__ bool fz_load_col(const FzLaunch& L, int c, int T, int n_tile, uint32_t* dst, unsigned lane) {
+    bool all_dict = true;
+    const FzColumn& C = L.col[c];
+    if (ROLE == FZ_PRED) {
+        dst[lane] = 0;
+        if (lane < 2) dst[32 + lane] = 0;
+        __syncwarp();
+    }
+    FzX x;
+    x.lo = C.lo;
+    x.hi = C.hi;
+    x.kmin = L.kmin;
+    x.range = L.range;
+    x.oor = L.oor;
+    int seg = __ldg(C.first_seg + T), covered = 0, pos = 0;
     for (int guard = 0; covered < n_tile && guard < FZ_TILE; guard++, seg++) {
-        const FzSeg S = C.segs[seg];
-        const PqPage pg = C.pages[S.page];
-        const int nvs = min(S.nvalid, FZ_TILE - pos);
-        if (nvs > 0) fz_unpack(L, C, S, pg, sc.vals + pos, nvs, lane);
-        pos += max(nvs, 0);
-        covered += S.n > 0 ? S.n : FZ_TILE;
+        const FzSeg* sp = C.segs + seg;
+        const int4 s0 = __ldg((const int4*)sp);   // page, row0, n, nvalid
+        const int nvs = min(s0.w, FZ_TILE - pos);
+        covered += s0.z > 0 ? s0.z : FZ_TILE;
+        if (nvs <= 0) continue;
+        const int4 s1 = __ldg((const int4*)sp + 1);   // v0 (2 words), idx.p_off, idx.run_remaining
+        const int4 s2 = __ldg((const int4*)sp + 2);   // idx.bp_base_off, idx.bp_consumed, idx.rle_value, idx.is_rle
+        const int4 s3 = __ldg((const int4*)sp + 3);   // vals (2 words), ddata (2 words)
+        const int4 s4 = __ldg((const int4*)sp + 4);   // val_len, bw, ndict, dict_id
+        const uint8_t* vals = (const uint8_t*)(((uint64_t)(uint32_t)s3.y << 32) | (uint32_t)s3.x);
+        const int bw = s4.y;
+        x.dict = bw >= 0;
+        all_dict = all_dict && x.dict;
+        x.ndict = (uint32_t)s4.z;
+        x.ddata = (const uint8_t*)(((uint64_t)(uint32_t)s3.w << 32) | (uint32_t)s3.z);
+        x.ddata_aligned = ((uintptr_t)x.ddata & 3) == 0;
+        x.pass = nullptr;
+        x.slot_base = 0;
+        if (x.dict) {
+            if (ROLE == FZ_PRED) x.pass = C.pass_bits + __ldg(C.pass_off + s4.w);
+            if (ROLE == FZ_KEY) x.slot_base = (uint32_t)__ldg(C.dslot_base + s4.w);
+            Hybrid idx;
+            hybrid_restore(idx, HybridCk{s1.z, s1.w, s2.x, s2.y, (uint32_t)s2.z, s2.w}, vals + 1, vals + s4.x, bw);
+            int done = 0;
+            while (done < nvs) {
+                if (idx.run_remaining == 0) idx.next_run();
+                const int t = min(nvs - done, idx.run_remaining);
+                if (idx.is_rle) fz_unpack_const<ROLE>(x, dst, pos + done, t, lane, idx.rle_value);
+                else fz_unpack_bits<ROLE>(x, dst, pos + done, t, lane, idx.bp_base, idx.bp_consumed, bw);
+                done += t;
+                idx.run_remaining -= t;
+                if (!idx.is_rle) idx.bp_consumed += t;
+            }
+        } else {   // PLAIN INT32: value k of the segment is the 32-bit word at vals + 4 (v0 + k)
+            const int64_t v0 = (int64_t)(((uint64_t)(uint32_t)s1.y << 32) | (uint32_t)s1.x);
+            fz_unpack_plain<ROLE>(x, dst, pos, nvs, lane, vals + v0 * 4);
+        }
+        pos += nvs;
     }
     __syncwarp();
+    return all_dict;
 }
+// ask L2 for the page bytes of tile T of every column (lane c looks up column c, then all lanes issue the line prefetches)
+__device__ __forceinline__ void fz_prefetch_tile(const FzLaunch& L, int T, unsigned lane) {
+    const uint8_t* beg = nullptr;
+    int bytes = 0;
+    if ((int)lane < L.ncols) {
+        const FzColumn& C = L.col[lane];
+        const FzSeg* sp = C.segs + __ldg(C.first_seg + T);
+        const int4 s0 = __ldg((const int4*)sp);
+        const int4 s1 = __ldg((const int4*)sp + 1);
+        const int4 s2 = __ldg((const int4*)sp + 2);
+        const int4 s3 = __ldg((const int4*)sp + 3);
+        const int4 s4 = __ldg((const int4*)sp + 4);
+        const uint8_t* vals = (const uint8_t*)(((uint64_t)(uint32_t)s3.y << 32) | (uint32_t)s3.x);
+        if (s4.y >= 0) {   // index stream from the checkpoint on (later segments of the tile start a new page: not prefetched)
+            const int64_t off = s2.w ? (int64_t)s1.z : (int64_t)s2.x + (((int64_t)s2.y * s4.y) >> 3);
+            beg = vals + 1 + off;
+            bytes = (int)min((int64_t)((s0.w * s4.y) >> 3) + 64, (int64_t)s4.x - off);
+        } else {
+            const int64_t v0 = (int64_t)(((uint64_t)(uint32_t)s1.y << 32) | (uint32_t)s1.x);
+            beg = vals + v0 * 4;
+            bytes = s0.w * 4;
+        }
+    }
+    for (int c = 0; c < L.ncols; c++) {
+        const uint8_t* b = (const uint8_t*)__shfl_sync(FULL_MASK, (unsigned long long)beg, c);
+        const int n = __shfl_sync(FULL_MASK, bytes, c);
+        for (int o = 128 * (int)lane; o < n; o += 128 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + o));
+    }
+}
+// bits[0, popc(w)) deposited into the set positions of w (PDEP)
+__device__ __forceinline__ uint32_t fz_deposit(uint32_t bits, uint32_t w) {
+    if (w == 0xffffffffu) return bits;
+    uint32_t out = 0;
+    while (w) {
+        const uint32_t b = w & (0u - w);
+        if (bits & 1u) out |= b;
+        bits >>= 1;
+        w ^= b;
+    }
+    return out;
+}
+// The selected rows of this lane -> accumulators.  Everything that does not depend on the row is decided before the loop:
+// per accumulator the operation, the plane of its argument and the base pointers; ALLDICT (every key of the tile came from a
+// dictionary page, the common case) drops the per-row choice between the dictionary-space and the direct arrays.
+template <int NV, int NACC, bool ALLDICT>
+__device__ __forceinline__ void fz_rows_to_accs(const FzLaunch& L, uint32_t sel, uint32_t wk, int prefk, const uint32_t* wv, const int* prefv,
+                                                const uint32_t* s_plane) {
+    constexpr int NVR = NV < 0 ? FZ_MAX_COLS - 1 : (NV == 0 ? 1 : NV);
+    constexpr int NA = NACC < 0 ? FZ_MAX_ACCS : NACC;
+    const int nacc = NACC < 0 ? L.nacc : NACC;
+    unsigned long long* bd[NA];   // dictionary-space base
+    unsigned long long* bx[NA];   // direct base
+    uint8_t* vd[NA];
+    uint8_t* vx[NA];
+    int op[NA], plane[NA];        // op: 0 add value, 1 add one, 2 min, 3 max ; plane: -1 COUNT(*), 0 key validity, 1 + v argument plane v
+    bool need_seen = true, any_flags = false;
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+        bd[a] = bx[a] = nullptr;
+        vd[a] = vx[a] = nullptr;
+        op[a] = 0;
+        plane[a] = -1;
+        if (a < nacc) {
+            const FzAcc& A = L.acc[a];
+            bd[a] = A.dspace;
+            bx[a] = A.direct;
+            vd[a] = A.dspace_valid;
+            vx[a] = A.direct_valid;
+            op[a] = A.kind == ACC_COUNT ? 1 : A.kind == ACC_MIN ? 2 : A.kind == ACC_MAX ? 3 : 0;
+            plane[a] = A.col < 0 ? -1 : A.col - L.npred;
+            if (A.kind == ACC_COUNT && A.col < 0) need_seen = false;   // COUNT(*) marks every selected row's group
+            any_flags = any_flags || A.direct_valid != nullptr;
+        }
+    }
+    const uint32_t null_slot = 0x80000000u | (uint32_t)L.range;
+    while (sel) {
+        const int i = __ffs(sel) - 1;
+        sel &= sel - 1;
+        const uint32_t below = (1u << i) - 1u;
+        uint32_t U = null_slot;
+        if ((wk >> i) & 1u) U = s_plane[fz_pi(prefk + __popc(wk & below))];
+        const bool dsp = ALLDICT ? true : !(U >> 31);
+        const int64_t slot = (int64_t)(U & 0x7fffffffu);
+        long long val[NVR];
+        bool ok[NVR];
+#pragma unroll
+        for (int v = 0; v < NVR; v++) {
+            ok[v] = (wv[v] >> i) & 1u;
+            val[v] = ok[v] ? (long long)(int32_t)s_plane[(size_t)(1 + v) * FZ_VSTRIDE + fz_pi(prefv[v] + __popc(wv[v] & below))] : 0ll;
+        }
+        bool marked = false;
+#pragma unroll
+        for (int a = 0; a < NA; a++) {
+            if (a >= nacc) break;
+            long long v = 1;
+            bool valid = true;
+            if (plane[a] == 0) valid = (wk >> i) & 1u;
+#pragma unroll
+            for (int q = 0; q < NVR; q++)
+                if (plane[a] == 1 + q) {
+                    valid = ok[q];
+                    v = val[q];
+                }
+            if (!valid) continue;
+            unsigned long long* p = (dsp ? bd[a] : bx[a]) + slot;
+            if (op[a] == 1) atomicAdd(p, 1ull);
+            else if (op[a] == 0) atomicAdd(p, (unsigned long long)v);   // SUM (wrapping, sum.rs:115)
+            else if (op[a] == 2) atomicMin((long long*)p, v);
+            else atomicMax((long long*)p, v);
+            if (any_flags) {
+                uint8_t* vb = dsp ? vd[a] : vx[a];
+                if (vb) {
+                    vb[slot] = 1;
+                    marked = true;
+                }
+            }
+            marked = marked || op[a] == 1;
+        }
+        if (need_seen && !marked) (dsp ? L.seen_dspace : L.seen_direct)[slot] = 1;   // the group exists although no accumulator shows it
+    }
+}
+// NV argument planes, NACC accumulators (compile time: the row loop is fully unrolled, descriptors come straight from the
+// constant bank); NV = -1: any shape, loops at run time
+template <int NV, int NACC>
 __global__ void __launch_bounds__(FZ_WARPS * 32) fz_kernel(const __grid_constant__ FzLaunch L) {
     extern __shared__ __align__(16) uint8_t fz_smem[];
     const int wid = threadIdx.x >> 5;
     const unsigned lane = threadIdx.x & 31;
     const int T = blockIdx.x * FZ_WARPS + wid;
     if (T >= L.n_tiles) return;
-    FzSmemCol* sc = (FzSmemCol*)fz_smem + (size_t)wid * L.ncols;
-    uint32_t* s_sel = (uint32_t*)((FzSmemCol*)fz_smem + (size_t)FZ_WARPS * L.ncols) + wid * 32;
+    fz_prefetch_tile(L, T, lane);
+    const int nplanes = L.ncols - L.npred;   // key + argument columns
+    // per warp: [36 words pass bits][nplanes value planes]
+    const size_t per_warp = 36 * 4 + (size_t)nplanes * FZ_VSTRIDE * 4;
+    uint32_t* s_bits = (uint32_t*)(fz_smem + (size_t)wid * per_warp);
+    uint32_t* s_plane = s_bits + 36;
     const int n_tile = (int)min((int64_t)FZ_TILE, L.n_rows - (int64_t)T * FZ_TILE);
-    const unsigned lt = lanemask_lt();
-    // ---- 1. predicate columns -> selection words of the tile (lane j ends up with the word of rows [32 j, 32 j + 32))
-    for (int c = 0; c < L.npred; c++) fz_load_col(L, c, T, n_tile, sc[c], lane);
-    uint32_t my_sel = 0;
-    for (int j = 0; j * 32 < n_tile; j++) {
-        bool pass = 32 * j + (int)lane < n_tile;
-        for (int p = 0; p < L.npred; p++) {
-            const uint32_t w = sc[p].w[j];
-            const bool v = (w >> lane) & 1u;
-            const uint32_t bit = v ? sc[p].vals[sc[p].pref[j] + __popc(w & lt)] : 0u;
-            pass = pass && bit;
-        }
-        const uint32_t word = __ballot_sync(FULL_MASK, pass);
-        if ((int)lane == j) my_sel = word;
+    // ---- 1. selection word of this lane's rows
+    const int cnt = n_tile - 32 * (int)lane;
+    uint32_t sel = cnt >= 32 ? 0xffffffffu : (cnt > 0 ? (1u << cnt) - 1u : 0u);
+    for (int p = 0; p < L.npred; p++) {
+        uint32_t w;
+        int pref;
+        fz_rows(L.col[p], T, n_tile, lane, &w, &pref);
+        fz_load_col<FZ_PRED>(L, p, T, n_tile, s_bits, lane);
+        const uint32_t bits = __funnelshift_r(s_bits[pref >> 5], s_bits[(pref >> 5) + 1], pref & 31);   // pass bits of my values, from bit 0
+        sel &= fz_deposit(bits, w);
+        __syncwarp();
     }
-    int nsel = __popc(my_sel);
+    int nsel = __popc(sel);
 #pragma unroll
     for (int d = 16; d; d >>= 1) nsel += __shfl_xor_sync(FULL_MASK, nsel, d);
     if (nsel == 0) return;   // nothing of this tile survives the filter: the other columns are not even unpacked
     if (lane == 0) atomicAdd(L.selected_rows, (unsigned long long)nsel);
-    s_sel[lane] = my_sel;
     // ---- 2. key and argument columns
-    for (int c = L.npred; c < L.ncols; c++) fz_load_col(L, c, T, n_tile, sc[c], lane);
+    uint32_t wk;
+    int prefk;
+    fz_rows(L.col[L.key_col], T, n_tile, lane, &wk, &prefk);
+    const bool key_all_dict = fz_load_col<FZ_KEY>(L, L.key_col, T, n_tile, s_plane, lane);
+    constexpr int NVR = NV < 0 ? FZ_MAX_COLS - 1 : (NV == 0 ? 1 : NV);
+    uint32_t wv[NVR];
+    int prefv[NVR];
+#pragma unroll
+    for (int v = 0; v < NVR; v++) {
+        wv[v] = 0;
+        prefv[v] = 0;
+        if (v < (NV < 0 ? nplanes - 1 : NV)) {
+            fz_rows(L.col[L.key_col + 1 + v], T, n_tile, lane, &wv[v], &prefv[v]);
+            fz_load_col<FZ_VALUE>(L, L.key_col + 1 + v, T, n_tile, s_plane + (size_t)(1 + v) * FZ_VSTRIDE, lane);
+        }
+    }
     __syncwarp();
     // ---- 3. selected rows -> accumulators
-    const FzSmemCol& K = sc[L.key_col];
-    for (int j = 0; j * 32 < n_tile; j++) {
-        const uint32_t sw = s_sel[j];
-        if (sw == 0) continue;
-        if (!((sw >> lane) & 1u)) continue;
-        const uint32_t wk = K.w[j];
-        uint32_t U = 0x80000000u | (uint32_t)L.range;   // NULL key group
-        if ((wk >> lane) & 1u) U = K.vals[K.pref[j] + __popc(wk & lt)];
-        const bool dsp = !(U >> 31);
-        const int64_t slot = (int64_t)(U & 0x7fffffffu);
-        bool marked = false;
-        for (int a = 0; a < L.nacc; a++) {
-            const FzAcc& A = L.acc[a];
-            bool ok = true;
-            long long v = 1;
-            if (A.col >= 0) {
-                const uint32_t wv = sc[A.col].w[j];
-                ok = (wv >> lane) & 1u;
-                if (ok && A.kind != ACC_COUNT) v = (long long)(int32_t)sc[A.col].vals[sc[A.col].pref[j] + __popc(wv & lt)];
-            }
-            if (!ok) continue;
-            unsigned long long* p = (dsp ? A.dspace : A.direct) + slot;
-            switch (A.kind) {
-                case ACC_MIN: atomicMin((long long*)p, v); break;
-                case ACC_MAX: atomicMax((long long*)p, v); break;
-                default: atomicAdd(p, (unsigned long long)v); break;   // SUM (wrapping, sum.rs:115) / COUNT
-            }
-            uint8_t* vb = dsp ? A.dspace_valid : A.direct_valid;
-            if (vb) vb[slot] = 1;
-            marked = marked || A.kind == ACC_COUNT || vb != nullptr;
-        }
-        if (!marked) (dsp ? L.seen_dspace : L.seen_direct)[slot] = 1;   // the group exists although no accumulator shows it
-    }
+    const uint32_t rowmask = cnt >= 32 ? 0xffffffffu : (cnt > 0 ? (1u << cnt) - 1u : 0u);
+    const bool dict_no_null = key_all_dict && __all_sync(FULL_MASK, wk == rowmask);   // NULL keys live in the direct table
+    if (dict_no_null) fz_rows_to_accs<NV, NACC, true>(L, sel, wk, prefk, wv, prefv, s_plane);
+    else fz_rows_to_accs<NV, NACC, false>(L, sel, wk, prefk, wv, prefv, s_plane);
 }
-static size_t fz_smem_bytes(int ncols) { return (size_t)FZ_WARPS * ncols * sizeof(FzSmemCol) + (size_t)FZ_WARPS * 32 * 4; }
+static size_t fz_smem_bytes(int nplanes) { return (size_t)FZ_WARPS * (36 * 4 + (size_t)nplanes * FZ_VSTRIDE * 4); }
+template <int NV, int NACC>
+static void fz_launch(Ctx& ctx, const FzLaunch& L, size_t smem) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_OK(cudaFuncSetAttribute(fz_kernel<NV, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz_smem_bytes(FZ_MAX_COLS)));
+        attr_set = true;
+    }
+    fz_kernel<NV, NACC><<<(L.n_tiles + FZ_WARPS - 1) / FZ_WARPS, FZ_WARPS * 32, smem, ctx.stream>>>(L);
+}
 void fz_run(Ctx& ctx, const FzLaunch& L) {
     if (L.n_tiles <= 0) return;
-    static size_t attr_set = 0;
-    const size_t smem = fz_smem_bytes(L.ncols);
-    if (smem > attr_set) {
-        CUDA_OK(cudaFuncSetAttribute(fz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz_smem_bytes(FZ_MAX_COLS)));
-        attr_set = fz_smem_bytes(FZ_MAX_COLS);
-    }
+    const int nplanes = L.ncols - L.npred, nv = nplanes - 1;
+    const size_t smem = fz_smem_bytes(nplanes);
     ProfScope ps(ctx, "fz_scan_filter_agg");
-    fz_kernel<<<(L.n_tiles + FZ_WARPS - 1) / FZ_WARPS, FZ_WARPS * 32, smem, ctx.stream>>>(L);
+    const int key = getenv("AURON_FUSED_GENERIC") ? -1 : nv * 10 + L.nacc;
+    switch (key) {
+        case 1: fz_launch<0, 1>(ctx, L, smem); break;    // COUNT(*) / COUNT(key)
+        case 11: fz_launch<1, 1>(ctx, L, smem); break;   // SUM(x)
+        case 12: fz_launch<1, 2>(ctx, L, smem); break;   // SUM(x), COUNT(x)            (AVG's partial state)
+        case 13: fz_launch<1, 3>(ctx, L, smem); break;   // SUM(x), COUNT(x), COUNT(*) ; MIN / MAX / SUM of one column
+        case 22: fz_launch<2, 2>(ctx, L, smem); break;   // SUM(x), SUM(y)
+        case 23: fz_launch<2, 3>(ctx, L, smem); break;
+        case 24: fz_launch<2, 4>(ctx, L, smem); break;
+        case 33: fz_launch<3, 3>(ctx, L, smem); break;
+        default: fz_launch<-1, -1>(ctx, L, smem); break;
+    }
     LAUNCH_CHECK(ctx);
 }
 

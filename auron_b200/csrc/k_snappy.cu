@@ -34,15 +34,122 @@ namespace auron {
 // last SN_RING output bytes, and references that fall inside the ring are served from it; long literals bypass the ring
 // (ring_from marks the first output position the ring is valid from).
 constexpr int SN_RING = 4096;
+// Where the prefix pass (below) left a job: ip < 0 = finished there, ip == 0 = not started (the warp parses the preamble),
+// else resume at input offset ip / output offset op.
+struct PqDecompState {
+    int32_t ip, op;
+};
+
+// ---- prefix pass: ONE THREAD per nullable-v1-page job.  The body of such a page is [u32 length][definition levels][values]; with
+// dictionary-encoded values the Snappy stream is a few hundred tiny elements for the level bytes (4..8 bytes each: the level
+// runs repeat) followed by one literal that holds the value section.  A warp per job executed every one of those elements
+// 32-fold redundantly: 800 M warp instructions per SF100 pass, the whole kernel instruction-bound at 1.06 ms.  Element-level
+// work has no parallelism to offer, job-level work has plenty (one job per page), so here every lane walks its own stream
+// byte by byte.  A job that does not have the expected shape within the budget (long literal in the middle, large output) is
+// handed to the warp kernel, which resumes it from the recorded offsets.
+constexpr int SN_PREFIX_MAX_OUT = 24 * 1024, SN_PREFIX_MAX_ELEMS = 6000;
+__global__ void __launch_bounds__(128) pq_decompress_prefix_kernel(const PqDecompJob* __restrict__ jobs, int n_jobs, int32_t* __restrict__ status,
+                                                                   PqDecompResult* __restrict__ results, PqDecompState* __restrict__ states) {
+    const int job = blockIdx.x * 128 + threadIdx.x;
+    if (job >= n_jobs) return;
+    results[job] = PqDecompResult{nullptr, -1, 0};
+    states[job] = PqDecompState{0, 0};
+    const PqDecompJob jb = jobs[job];
+    if (jb.kind != 1 || !jb.v1_levels) return;
+    const uint8_t* __restrict__ src = jb.src;
+    uint8_t* dst = jb.dst;
+    const int n_in = jb.src_len, n_out = jb.dst_len;
+    int ip = 0, op = 0;
+    {
+        uint32_t v = 0;
+        int shift = 0;
+        for (;;) {
+            if (ip >= n_in || shift > 28) return;   // malformed preamble: the warp kernel reports it
+            const uint8_t b = src[ip++];
+            v |= (uint32_t)(b & 0x7f) << shift;
+            if (!(b & 0x80)) break;
+            shift += 7;
+        }
+        if ((int)v != n_out) return;
+    }
+    for (int elems = 0; ip < n_in; elems++) {
+        const int ip0 = ip;
+        if (op >= SN_PREFIX_MAX_OUT || elems >= SN_PREFIX_MAX_ELEMS) {
+            states[job] = PqDecompState{ip0, op};
+            return;
+        }
+        const uint32_t tag = src[ip++];
+        const uint32_t kind = tag & 3;
+        if (kind == 0) {
+            int len = (int)(tag >> 2) + 1;
+            if (len > 60) {
+                const int nb = len - 60;
+                if (ip + nb > n_in) break;
+                uint32_t v = 0;
+                for (int k = 0; k < nb; k++) v |= (uint32_t)src[ip + k] << (8 * k);
+                ip += nb;
+                if (v >= 0x7fffffffu) break;
+                len = (int)v + 1;
+            }
+            if (len > n_in - ip || len > n_out - op) break;
+            if (len > 128) {
+                // the literal that holds the value section: only the level bytes that spill into it are copied (see the warp kernel)
+                if (ip + len == n_in && op + len == n_out && op >= 4) {
+                    const int64_t val_off = 4 + (int64_t)((uint32_t)dst[0] | ((uint32_t)dst[1] << 8) | ((uint32_t)dst[2] << 16) | ((uint32_t)dst[3] << 24));
+                    const int64_t keep = val_off - op;
+                    if (keep >= 0 && keep <= 512 && len - keep >= 256) {
+                        for (int i = 0; i < (int)keep; i++) dst[op + i] = src[ip + i];
+                        results[job] = PqDecompResult{src + ip + keep, (int32_t)val_off, 0};
+                        states[job] = PqDecompState{-1, 0};
+                        return;
+                    }
+                }
+                states[job] = PqDecompState{ip0, op};   // a long literal in the middle of the stream: a warp copies it
+                return;
+            }
+            for (int i = 0; i < len; i++) dst[op + i] = src[ip + i];
+            ip += len;
+            op += len;
+        } else {
+            int len, off;
+            if (kind == 1) {
+                if (ip + 1 > n_in) break;
+                len = 4 + (int)((tag >> 2) & 7);
+                off = (int)(((tag >> 5) << 8) | src[ip]);
+                ip += 1;
+            } else if (kind == 2) {
+                if (ip + 2 > n_in) break;
+                len = (int)(tag >> 2) + 1;
+                off = (int)((uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8));
+                ip += 2;
+            } else {
+                if (ip + 4 > n_in) break;
+                len = (int)(tag >> 2) + 1;
+                const uint32_t o4 = (uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8) | ((uint32_t)src[ip + 2] << 16) | ((uint32_t)src[ip + 3] << 24);
+                if (o4 > 0x7fffffffu) break;
+                off = (int)o4;
+                ip += 4;
+            }
+            if (off <= 0 || off > op || len > n_out - op) break;
+            const uint8_t* from = dst + op - off;
+            for (int i = 0; i < len; i++) dst[op + i] = from[i];   // byte order makes overlapping runs come out right
+            op += len;
+        }
+    }
+    if (ip == n_in && op == n_out) states[job] = PqDecompState{-1, 0};
+    else atomicCAS(status, 0, job + 1);   // malformed stream
+}
+
 __global__ void __launch_bounds__(128) pq_decompress_kernel(const PqDecompJob* __restrict__ jobs, int n_jobs, int32_t* __restrict__ status,
-                                                            PqDecompResult* __restrict__ results) {
+                                                            PqDecompResult* __restrict__ results, const PqDecompState* __restrict__ states) {
     __shared__ uint8_t s_ring[4][SN_RING];
     const int job = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (job >= n_jobs) return;
     const unsigned lane = threadIdx.x & 31;
     uint8_t* ring = s_ring[threadIdx.x >> 5];
     const PqDecompJob jb = jobs[job];
-    if (lane == 0) results[job] = PqDecompResult{nullptr, -1, 0};
+    const PqDecompState st0 = states[job];
+    if (st0.ip < 0) return;   // finished by the prefix pass
     const uint8_t* __restrict__ src = jb.src;
     uint8_t* dst = jb.dst;
     if (jb.kind == 0) {   // stored bytes (v2 level sections)
@@ -50,10 +157,10 @@ __global__ void __launch_bounds__(128) pq_decompress_kernel(const PqDecompJob* _
         return;
     }
     const int n_in = jb.src_len, n_out = jb.dst_len;
-    int ip = 0, op = 0, ring_from = 0;
+    int ip = st0.ip, op = st0.op, ring_from = st0.op;   // resumed jobs: the ring holds nothing of the output so far
     bool bad = false;
     // preamble: uncompressed length
-    {
+    if (st0.ip == 0) {
         uint32_t v = 0;
         int shift = 0;
         for (;;) {
@@ -182,9 +289,13 @@ PqDecompOut pq_decompress(Ctx& ctx, const std::vector<PqDecompJob>& jobs) {
     if (jobs.empty()) return out;
     out.results = dalloc(ctx, jobs.size() * sizeof(PqDecompResult));
     Buf dj = to_device(ctx, jobs.data(), jobs.size() * sizeof(PqDecompJob));
+    Buf states = dalloc(ctx, jobs.size() * sizeof(PqDecompState));
     ProfScope ps(ctx, "pq_decompress");
+    pq_decompress_prefix_kernel<<<(unsigned)((jobs.size() + 127) / 128), 128, 0, ctx.stream>>>(P<PqDecompJob>(dj), (int)jobs.size(), P<int32_t>(out.status),
+                                                                                                 P<PqDecompResult>(out.results), P<PqDecompState>(states));
+    LAUNCH_CHECK(ctx);
     pq_decompress_kernel<<<(unsigned)((jobs.size() + 3) / 4), 128, 0, ctx.stream>>>(P<PqDecompJob>(dj), (int)jobs.size(), P<int32_t>(out.status),
-                                                                                       P<PqDecompResult>(out.results));
+                                                                                       P<PqDecompResult>(out.results), P<PqDecompState>(states));
     LAUNCH_CHECK(ctx);
     return out;
 }

@@ -91,13 +91,21 @@ struct HybridCk {
     uint32_t rle_value;
     int32_t is_rle;
 };
-struct FzSeg {                    // rows [row0, row0 + n) of one page, all inside one global tile
+struct FzSeg {                    // rows [row0, row0 + n) of one page, all inside one global tile; self-contained (96 bytes) so
+                                  // that the fused kernel reaches the page bytes with ONE dependent load per column
     int32_t page, row0, n, nvalid;   // nvalid: non-null values among them
     int64_t v0;                      // non-null values of the page before row0
     HybridCk idx;                    // dictionary-index stream at the segment's first value
+    const uint8_t* vals;             // the page's value section (dictionary pages: its bit-width byte)
+    const uint8_t* ddata;            // dictionary pages: PLAIN values of the dictionary
+    int32_t val_len, bw;             // bw = bit width of the indices, -1 = PLAIN page
+    int32_t ndict, dict_id;
+    int64_t pad[2];
 };
+static_assert(sizeof(FzSeg) == 96, "FzSeg is read with 16-byte vector loads");
 struct FzScoutCol {               // one physical column to scout
     const PqPage* pages;
+    const PqDict* dicts;
     int32_t n_pages, max_def;
     const int32_t* seg_base;      // [n_pages + 1] first segment of every page
     FzSeg* segs;

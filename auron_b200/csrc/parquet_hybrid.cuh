@@ -254,8 +254,12 @@ __device__ inline void lvl_page_bits(const uint8_t* base, int len, int64_t rows,
             int p = b0 + o, nx;
             if (p >= len) nx = 32;
             else {
-                LvlHdr h = lvl_parse(base, p, len);
-                nx = o + h.hl + h.payload;
+                const uint32_t h0 = base[p];
+                if (!(h0 & 0x80)) nx = o + ((h0 & 1) ? 1 + (int)(h0 >> 1) : 2);   // one-byte header: bit-packed groups / RLE value byte
+                else {
+                    LvlHdr h = lvl_parse(base, p, len);
+                    nx = o + h.hl + h.payload;
+                }
             }
             exitT[lane][o] = nx >= 32 ? nx : exitT[lane][nx];
         }

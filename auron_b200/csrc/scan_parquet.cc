@@ -396,6 +396,41 @@ struct ParquetScanExec : Operator, FusedScanSource {
         }
         return (len == unc && i + len == n) ? i : 0;
     }
+    // `p[0, n)` is a Snappy block of `unc` bytes made only of literals (incompressible data: one literal per 64 KB fragment of
+    // the compressor): fills their (offset in p, length) and returns true; at most `max_pieces`
+    struct LitPiece {
+        int64_t src_off, len;
+    };
+    static bool snappy_literal_chain(const uint8_t* p, int64_t n, int64_t unc, size_t max_pieces, std::vector<LitPiece>* pieces) {
+        int64_t i = 0, out = 0;
+        uint64_t v = 0;
+        for (int shift = 0;; shift += 7) {
+            if (i >= n || shift > 28) return false;
+            const uint8_t b = p[i++];
+            v |= (uint64_t)(b & 0x7f) << shift;
+            if (!(b & 0x80)) break;
+        }
+        if ((int64_t)v != unc || unc <= 0) return false;
+        pieces->clear();
+        while (i < n) {
+            const uint8_t tag = p[i++];
+            if (tag & 3) return false;   // a back reference
+            int64_t len = (tag >> 2) + 1;
+            if (len > 60) {
+                const int nb = (int)len - 60;
+                if (i + nb > n) return false;
+                uint32_t w = 0;
+                for (int k = 0; k < nb; k++) w |= (uint32_t)p[i + k] << (8 * k);
+                i += nb;
+                len = (int64_t)w + 1;
+            }
+            if (len > n - i || len > unc - out || pieces->size() >= max_pieces) return false;
+            pieces->push_back(LitPiece{i, len});
+            i += len;
+            out += len;
+        }
+        return out == unc;
+    }
     static bool gpu_snappy() {
         return getenv("AURON_HOST_SNAPPY") == nullptr;   // AURON_HOST_SNAPPY=1: decompress on the host cores instead
     }
@@ -445,8 +480,26 @@ struct ParquetScanExec : Operator, FusedScanSource {
                 unc_off = out.gpu_unc_bytes;
                 out.gpu_unc_bytes += ((int64_t)h.uncompressed_size + 8 + 15) & ~(int64_t)15;
                 if (lvl_bytes) out.jobs.push_back(PqDecompJob{payload_d, (uint8_t*)(intptr_t)unc_off, lvl_bytes, lvl_bytes, 0, 0});   // v2 levels are stored
-                out.jobs.push_back(PqDecompJob{payload_d + lvl_bytes, (uint8_t*)(intptr_t)(unc_off + lvl_bytes), h.compressed_size - lvl_bytes,
-                                               h.uncompressed_size - lvl_bytes, 1, 0});
+                // A large incompressible body (an 816 KB dictionary of surrogate keys, a 1 MB page of bit-packed indices) is a
+                // chain of 64 KB literals: one warp walking it serially was the long pole of the whole launch (0.5 ms).  Its
+                // pieces become independent stored-copy jobs of <= 16 KB instead.  (Nullable v1 data pages keep the Snappy job:
+                // their level prefix is compressed.)
+                std::vector<LitPiece> pieces;
+                const bool v1_nullable = h.type == pq::PAGE_DATA && max_def > 0;
+                if (!v1_nullable && h.uncompressed_size - lvl_bytes > (64 << 10) &&
+                    snappy_literal_chain(payload_h + lvl_bytes, h.compressed_size - lvl_bytes, h.uncompressed_size - lvl_bytes, 256, &pieces)) {
+                    int64_t dst = unc_off + lvl_bytes;
+                    for (auto& pc : pieces) {
+                        for (int64_t o = 0; o < pc.len; o += 16 << 10) {
+                            const int32_t l = (int32_t)std::min<int64_t>(16 << 10, pc.len - o);
+                            out.jobs.push_back(PqDecompJob{payload_d + lvl_bytes + pc.src_off + o, (uint8_t*)(intptr_t)(dst + o), l, l, 0, 0});
+                        }
+                        dst += pc.len;
+                    }
+                } else {
+                    out.jobs.push_back(PqDecompJob{payload_d + lvl_bytes, (uint8_t*)(intptr_t)(unc_off + lvl_bytes), h.compressed_size - lvl_bytes,
+                                                   h.uncompressed_size - lvl_bytes, 1, 0});
+                }
                 payload_h = nullptr;
             } else if (page_compressed && !page_dev) {
                 unc_off = (int64_t)out.unc.size();
@@ -570,8 +623,8 @@ struct ParquetScanExec : Operator, FusedScanSource {
     static constexpr int kLanes = 3;
     std::vector<std::unique_ptr<Ctx>> lanes;
     bool use_lanes = getenv("AURON_SCAN_LANES") != nullptr;
-    Ctx& lane(Task& t, int i) {
-        while ((int)lanes.size() <= i) lanes.emplace_back(new Ctx(t.ctx.device));
+    Ctx& lane(Task& t, int i, int priority = 0) {
+        while ((int)lanes.size() <= i) lanes.emplace_back(new Ctx(t.ctx.device, priority));
         return *lanes[(size_t)i];
     }
     static void chain(cudaStream_t from, cudaStream_t to) {   // work queued on `to` from here on runs after everything queued on `from` so far
@@ -941,13 +994,14 @@ struct ParquetScanExec : Operator, FusedScanSource {
     }
 
     ~ParquetScanExec() override {
-        if (inflight) {   // fused batch still running: its landing buffers go back only once the kernels are done
-            cudaEventSynchronize(inflight->done);
-            cudaEventDestroy(inflight->done);
-            if (inflight->sg.dec0) cudaEventDestroy(inflight->sg.dec0);
-            release(*inflight->sg.ready);
-            inflight.reset();
-        }
+        for (auto& f : inflight)
+            if (f) {   // fused batch still running: its landing buffers go back only once the kernels are done
+                cudaEventSynchronize(f->done);
+                cudaEventDestroy(f->done);
+                if (f->sg.dec0) cudaEventDestroy(f->sg.dec0);
+                release(*f->sg.ready);
+                f.reset();
+            }
         stop();
         if (copy_stream) {
             cudaStreamSynchronize(copy_stream);
@@ -995,7 +1049,8 @@ struct ParquetScanExec : Operator, FusedScanSource {
         bool tl = false;
     };
     // nullptr ready = end of the scan
-    Staged stage_next(Task& t) {
+    // `wc`: the context (stream) the batch's device work is queued on -- the task's own, or one of the two lanes the fused path alternates between
+    Staged stage_next(Task& t, Ctx& wc) {
         Staged sg;
         AURON_CHECK(t.is_running(), "task killed");
         std::unique_ptr<Prepared> ready;
@@ -1031,11 +1086,11 @@ struct ParquetScanExec : Operator, FusedScanSource {
         metrics.add("parse_ns", ready->parse_ns);
         if (ready->dev_bytes) {
             metrics.add("h2d_bytes", ready->dev_bytes);
-            CUDA_OK(cudaStreamWaitEvent(t.ctx.stream, ready->copied, 0));
+            CUDA_OK(cudaStreamWaitEvent(wc.stream, ready->copied, 0));
         }
         if (tl) {
             CUDA_OK(cudaEventCreate(&dec0));
-            CUDA_OK(cudaEventRecord(dec0, t.ctx.stream));
+            CUDA_OK(cudaEventRecord(dec0, wc.stream));
         }
         Prepared& p = *ready;
         // ordered merge, rebasing dictionary ids / value-table positions; compressed chunks upload their payloads first
@@ -1095,13 +1150,13 @@ struct ParquetScanExec : Operator, FusedScanSource {
                 }
             }
             if (!cp.unc.empty()) {   // host-decompressed payloads (ZSTD / LZ4_RAW pages, nullable v1 PLAIN string pages) are uploaded here
-                sl.host_unc = to_device(t.ctx, cp.unc.data(), cp.unc.size());
+                sl.host_unc = to_device(wc, cp.unc.data(), cp.unc.size());
                 cs.keep.push_back(sl.host_unc);
             }
         }
         Buf unc_scratch;   // one scratch allocation for every device-decompressed page of the batch
         if (unc_total > 0) {
-            unc_scratch = dalloc(t.ctx, (size_t)unc_total + 256);
+            unc_scratch = dalloc(wc, (size_t)unc_total + 256);
             for (auto& cs : p.cols)
                 if (cs.needs_decomp) cs.keep.push_back(unc_scratch);
         }
@@ -1165,14 +1220,14 @@ struct ParquetScanExec : Operator, FusedScanSource {
         });
         delete tmerge;
         {
-            Ctx& dc = (use_lanes && !decomp_jobs.empty()) ? lane(t, kLanes) : t.ctx;
-            if (&dc != &t.ctx) chain(t.ctx.stream, dc.stream);   // scratch allocated, chunk bytes uploaded
+            Ctx& dc = (use_lanes && !decomp_jobs.empty()) ? lane(t, kLanes) : wc;
+            if (&dc != &wc) chain(wc.stream, dc.stream);   // scratch allocated, chunk bytes uploaded
             PqDecompOut dec = pq_decompress(dc, decomp_jobs);
             sg.status = dec.status;
             sg.has_jobs = !decomp_jobs.empty();
             decomp_results_buf = dec.results;
             decomp_results = P<PqDecompResult>(dec.results);
-            if (&dc != &t.ctx) {
+            if (&dc != &wc) {
                 CUDA_OK(cudaEventCreateWithFlags(&decomp_done, cudaEventDisableTiming));
                 CUDA_OK(cudaEventRecord(decomp_done, dc.stream));
             }
@@ -1192,7 +1247,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
     BatchPtr next(Task& t) override {
         OpTimer timer(metrics, "elapsed_ns");
         retire_fused(t);
-        Staged sg = stage_next(t);
+        Staged sg = stage_next(t, t.ctx);
         if (!sg.ready) return nullptr;
         return decode_staged(t, sg);
     }
@@ -1253,14 +1308,18 @@ struct ParquetScanExec : Operator, FusedScanSource {
     // (FusedScanSource, operators.h; kernels in k_fused.cu).  A batch whose columns the fused kernels cannot take (strings,
     // INT64 / FLBA physical types, missing statistics of the key, a key range too wide for the direct table) comes back as a
     // regular batch and the caller runs the unfused operators on it.
-    struct Inflight {   // the batch whose kernels are still running: its landing buffers are recycled once they are done
+    struct Inflight {   // a batch whose kernels are still running: its landing buffers are recycled once they are done
         Staged sg;
         cudaEvent_t done = nullptr;
     };
-    std::unique_ptr<Inflight> inflight;
-    void retire_fused(Task& t) {
-        if (!inflight) return;
-        std::unique_ptr<Inflight> f = std::move(inflight);
+    // Two batches are in flight at a time, on alternating lanes (streams): scout / decompress / fused kernel of one batch are
+    // each latency-bound on their own, so the next batch's early stages fill the SMs the current batch leaves idle, and the
+    // host-side preparation of a batch overlaps the kernels of the previous one.
+    std::unique_ptr<Inflight> inflight[2];
+    int64_t fused_seq = 0;
+    void retire_lane(Task& t, int li) {
+        if (!inflight[li]) return;
+        std::unique_ptr<Inflight> f = std::move(inflight[li]);
         cudaEventSynchronize(f->done);
         cudaEventDestroy(f->done);
         struct R {
@@ -1269,7 +1328,16 @@ struct ParquetScanExec : Operator, FusedScanSource {
             ~R() { op->release(*p); }
         } r{this, f->sg.ready.get()};
         if (f->sg.dec0) cudaEventDestroy(f->sg.dec0);
-        check_decomp_status(t, f->sg);
+        if (f->sg.has_jobs) {
+            int32_t st = 0;
+            CUDA_OK(cudaMemcpy(&st, f->sg.status->ptr, 4, cudaMemcpyDeviceToHost));   // the batch is complete: plain copy, no stream involved
+            AURON_CHECK(st == 0, "corrupt Snappy page in the parquet file (decompression job " + std::to_string(st - 1) + ")");
+        }
+    }
+    void retire_fused(Task& t) {
+        retire_lane(t, 0);
+        retire_lane(t, 1);
+        if (!lanes.empty() && !use_lanes) fold_lanes(t);
     }
     static bool fused_type_ok(const DType& t) { return t.id == T_INT32 || t.id == T_DATE32 || t.id == T_INT64; }
     bool can_fuse(const FusedAggSpec& spec) const override {
@@ -1284,38 +1352,53 @@ struct ParquetScanExec : Operator, FusedScanSource {
     }
     int next_fused(Task& t, const FusedAggSpec& spec, FusedAggState& st, BatchPtr* fallback) override {
         OpTimer timer(metrics, "elapsed_ns");
-        Staged sg = stage_next(t);
+        const int li = (int)(fused_seq & 1);
+        const bool two = !getenv("AURON_FUSED_ONE_LANE");
+        // lane li = a high-priority stream for the batch's preparation (page decompression, scout: one warp per page, a few
+        // long serial chains that leave the SMs mostly idle) + a normal-priority stream for its fused kernel.  While the fused
+        // kernel of batch k fills the machine, the preparation of batch k+1 gets the SM slots it needs as soon as it asks.
+        if (two && lanes.size() < 4) {
+            lane(t, 0, -1);
+            lane(t, 1, -1);
+            lane(t, 2, 0);
+            lane(t, 3, 0);
+        }
+        Ctx& wc = two ? lane(t, li) : t.ctx;
+        Ctx& fc = two ? lane(t, 2 + li) : t.ctx;
+        if (two) retire_lane(t, li);   // the batch before last ran on this lane: its buffers go back before the lane is reused
+        Staged sg = stage_next(t, wc);
         if (!sg.ready) {
             retire_fused(t);
             return FUSED_END;
         }
         bool ok = false;
         try {
-            ok = run_fused(t, sg, spec, st);
+            ok = run_fused(t, wc, fc, sg, spec, st);
         } catch (...) {
-            cudaStreamSynchronize(t.ctx.stream);
+            cudaStreamSynchronize(wc.stream);
             release(*sg.ready);
             throw;
         }
         if (!ok) {
             retire_fused(t);
+            if (&wc != &t.ctx) chain(wc.stream, t.ctx.stream);   // page decompression was queued on the lane
             *fallback = decode_staged(t, sg);
             return FUSED_FALLBACK;
         }
-        // the kernels of this batch are queued: now wait for the previous batch and recycle its buffers
         auto f = std::make_unique<Inflight>();
         CUDA_OK(cudaEventCreateWithFlags(&f->done, cudaEventDisableTiming));
-        CUDA_OK(cudaEventRecord(f->done, t.ctx.stream));
+        CUDA_OK(cudaEventRecord(f->done, wc.stream));
         metrics.add("output_rows", sg.ready->rows);
         metrics.add("fused_batches", 1);
         f->sg = std::move(sg);
-        retire_fused(t);
-        inflight = std::move(f);
+        if (!two) retire_lane(t, li);   // single stream: the previous batch is retired once this one is queued behind it
+        inflight[li] = std::move(f);
         decomp_results = nullptr;
         decomp_results_buf.reset();
+        fused_seq++;
         return FUSED_DONE;
     }
-    bool run_fused(Task& t, Staged& sg, const FusedAggSpec& spec, FusedAggState& st) {
+    bool run_fused(Task& t, Ctx& wc, Ctx& fc, Staged& sg, const FusedAggSpec& spec, FusedAggState& st) {
         Prepared& p = *sg.ready;
         const int64_t n_rows = p.rows;
         if (n_rows <= 0 || n_rows >= (int64_t)INT32_MAX - FZ_TILE) return false;
@@ -1365,20 +1448,21 @@ struct ParquetScanExec : Operator, FusedScanSource {
             ColState& cs = p.cols[(size_t)used[u]];
             const int max_def = cs.el.repetition == 1 ? 1 : 0;
             Phys& x = ph[u];
-            x.dpages = to_device(t.ctx, cs.pages.data(), cs.pages.size() * sizeof(PqPage));
-            x.ddicts = to_device(t.ctx, cs.dicts.empty() ? (const void*)"" : (const void*)cs.dicts.data(), cs.dicts.size() * sizeof(PqDict));
-            if (cs.has_v1_inline) pq_fix_v1_pages(t.ctx, P<PqPage>(x.dpages), (int)cs.pages.size(), decomp_results);
+            x.dpages = to_device(wc, cs.pages.data(), cs.pages.size() * sizeof(PqPage));
+            x.ddicts = to_device(wc, cs.dicts.empty() ? (const void*)"" : (const void*)cs.dicts.data(), cs.dicts.size() * sizeof(PqDict));
+            if (cs.has_v1_inline) pq_fix_v1_pages(wc, P<PqPage>(x.dpages), (int)cs.pages.size(), decomp_results);
             std::vector<int32_t> sb(cs.pages.size() + 1, 0);
             for (size_t i = 0; i < cs.pages.size(); i++) {
                 const int64_t r0 = cs.pages[i].row_start, n = cs.pages[i].num_values;
                 sb[i + 1] = sb[i] + (n > 0 ? (int32_t)((r0 + n - 1) / FZ_TILE - r0 / FZ_TILE + 1) : 0);
             }
-            x.seg_base = to_device(t.ctx, sb.data(), sb.size() * 4);
-            x.segs = dalloc(t.ctx, (size_t)std::max<int32_t>(sb.back(), 1) * sizeof(FzSeg));
-            x.first_seg = dalloc_zero(t.ctx, (size_t)n_tiles * 4);
-            if (max_def > 0) x.valid = dalloc_zero(t.ctx, (size_t)n_tiles * (FZ_TILE / 8));
+            x.seg_base = to_device(wc, sb.data(), sb.size() * 4);
+            x.segs = dalloc(wc, (size_t)std::max<int32_t>(sb.back(), 1) * sizeof(FzSeg));
+            x.first_seg = dalloc_zero(wc, (size_t)n_tiles * 4);
+            if (max_def > 0) x.valid = dalloc_zero(wc, (size_t)n_tiles * (FZ_TILE / 8));
             FzScoutCol sc;
             sc.pages = P<PqPage>(x.dpages);
+            sc.dicts = P<PqDict>(x.ddicts);
             sc.n_pages = (int32_t)cs.pages.size();
             sc.max_def = max_def;
             sc.seg_base = P<int32_t>(x.seg_base);
@@ -1388,7 +1472,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
             scout.push_back(sc);
             if (max_def > 0 && (size_t)used[u] == (size_t)spec.key_col) st.key_nullable = true;
         }
-        fz_scout(t.ctx, scout);
+        fz_scout(wc, scout);
 
         FzLaunch L;
         memset(&L, 0, sizeof(L));
@@ -1413,9 +1497,9 @@ struct ParquetScanExec : Operator, FusedScanSource {
             L.col[rc].hi = spec.pred_hi[i];
             std::vector<int32_t> off(cs.dicts.size() + 1, 0);
             for (size_t d = 0; d < cs.dicts.size(); d++) off[d + 1] = off[d] + (cs.dicts[d].num_values + 31) / 32;
-            Buf doff = to_device(t.ctx, off.data(), off.size() * 4);
-            Buf bits = dalloc(t.ctx, (size_t)std::max<int32_t>(off.back(), 1) * 4);
-            fz_dict_pass(t.ctx, L.col[rc].dicts, P<int32_t>(doff), (int)cs.dicts.size(), off.back(), spec.pred_lo[i], spec.pred_hi[i], P<uint32_t>(bits));
+            Buf doff = to_device(wc, off.data(), off.size() * 4);
+            Buf bits = dalloc(wc, (size_t)std::max<int32_t>(off.back(), 1) * 4);
+            fz_dict_pass(wc, L.col[rc].dicts, P<int32_t>(doff), (int)cs.dicts.size(), off.back(), spec.pred_lo[i], spec.pred_hi[i], P<uint32_t>(bits));
             L.col[rc].pass_off = P<int32_t>(doff);
             L.col[rc].pass_bits = P<uint32_t>(bits);
             keep.push_back(doff);
@@ -1425,33 +1509,39 @@ struct ParquetScanExec : Operator, FusedScanSource {
         L.key_col = add_role(spec.key_col, FZ_KEY);
         std::vector<int32_t> dbase(kcs.dicts.size() + 1, 0);
         for (size_t d = 0; d < kcs.dicts.size(); d++) dbase[d + 1] = dbase[d] + kcs.dicts[d].num_values;
-        Buf ddbase = to_device(t.ctx, dbase.data(), dbase.size() * 4);
+        Buf ddbase = to_device(wc, dbase.data(), dbase.size() * 4);
         L.col[L.key_col].dslot_base = P<int32_t>(ddbase);
         std::vector<int> value_role(projection.size(), -1);
         for (auto& a : spec.accs)
             if (a.col >= 0 && a.kind != ACC_COUNT && value_role[(size_t)a.col] < 0) value_role[(size_t)a.col] = add_role(a.col, FZ_VALUE);
-        // COUNT(x) only needs x's validity: any role-column over x serves
+        // COUNT(x) only needs x's validity: the key column serves as it is, any other column gets an argument plane
         auto any_role = [&](int c) {
             if (value_role[(size_t)c] >= 0) return value_role[(size_t)c];
             if (c == spec.key_col) return (int)L.key_col;
-            for (size_t i = 0; i < spec.pred_cols.size(); i++)
-                if (spec.pred_cols[i] == c) return (int)i;
             return value_role[(size_t)c] = add_role(c, FZ_VALUE);
         };
         // the persistent table
-        if (!st.table) {
-            std::vector<AccSpec> specs;
-            for (auto& a : spec.accs) {
-                AccSpec s;
-                s.kind = (AccKind)a.kind;
-                s.out_type = a.out_type;
-                s.input_id = a.col;
-                specs.push_back(s);
+        // The table belongs to the task stream; the lanes only update it.  Creating / widening it is rare (first batch, or a
+        // batch whose keys leave the range so far): everything in flight on the lanes is drained first, the lanes then wait
+        // for the new table.
+        const bool widen = st.table && st.has_range && umin <= umax && (umin < st.kmin || umax > st.kmax);
+        if (!st.table || widen || !st.has_range) {
+            for (auto& l : lanes) CUDA_OK(cudaStreamSynchronize(l->stream));
+            if (!st.table) {
+                std::vector<AccSpec> specs;
+                for (auto& a : spec.accs) {
+                    AccSpec s;
+                    s.kind = (AccKind)a.kind;
+                    s.out_type = a.out_type;
+                    s.input_id = a.col;
+                    specs.push_back(s);
+                }
+                st.table = direct_agg_create(t.ctx, specs, umin, umax);
+                st.selected = dalloc_zero(t.ctx, 8);
+            } else {
+                direct_agg_grow(t.ctx, *st.table, umin, umax);
             }
-            st.table = direct_agg_create(t.ctx, specs, umin, umax);
-            st.selected = dalloc_zero(t.ctx, 8);
-        } else {
-            direct_agg_grow(t.ctx, *st.table, umin, umax);
+            CUDA_OK(cudaStreamSynchronize(t.ctx.stream));
         }
         if (umin <= umax) {
             st.has_range = true;
@@ -1460,18 +1550,18 @@ struct ParquetScanExec : Operator, FusedScanSource {
         }
         const DirectAggView dv = direct_agg_view(*st.table);
         L.nacc = (int)spec.accs.size();
-        Buf dseen = dalloc(t.ctx, (size_t)std::max<int64_t>(dict_slots, 1));
+        Buf dseen = dalloc(wc, (size_t)std::max<int64_t>(dict_slots, 1));
         for (int a = 0; a < L.nacc; a++) {
             FzAcc& A = L.acc[a];
             A.kind = spec.accs[(size_t)a].kind;
             A.col = spec.accs[(size_t)a].col >= 0 ? any_role(spec.accs[(size_t)a].col) : -1;
             A.direct = dv.acc[a];
             A.direct_valid = dv.valid[a];
-            Buf d = dalloc(t.ctx, (size_t)std::max<int64_t>(dict_slots, 1) * 8);
+            Buf d = dalloc(wc, (size_t)std::max<int64_t>(dict_slots, 1) * 8);
             keep.push_back(d);
             A.dspace = P<unsigned long long>(d);
             if (A.direct_valid) {
-                Buf v = dalloc(t.ctx, (size_t)std::max<int64_t>(dict_slots, 1));
+                Buf v = dalloc(wc, (size_t)std::max<int64_t>(dict_slots, 1));
                 keep.push_back(v);
                 A.dspace_valid = P<uint8_t>(v);
             }
@@ -1484,8 +1574,9 @@ struct ParquetScanExec : Operator, FusedScanSource {
         L.seen_dspace = P<uint8_t>(dseen);
         L.oor = dv.oor;
         L.selected_rows = P<unsigned long long>(st.selected);
-        fz_init_dspace(t.ctx, L, dict_slots);
-        fz_run(t.ctx, L);
+        fz_init_dspace(wc, L, dict_slots);
+        if (&fc != &wc) chain(wc.stream, fc.stream);
+        fz_run(fc, L);
         FzMerge M;
         memset(&M, 0, sizeof(M));
         M.dicts = L.col[L.key_col].dicts;
@@ -1498,7 +1589,8 @@ struct ParquetScanExec : Operator, FusedScanSource {
         M.seen_direct = dv.seen;
         M.seen_dspace = P<uint8_t>(dseen);
         M.oor = dv.oor;
-        fz_merge(t.ctx, M, dict_slots);
+        fz_merge(fc, M, dict_slots);
+        if (&fc != &wc) chain(fc.stream, wc.stream);   // the batch's buffers are freed (stream-ordered) on wc: after its kernels
         st.rows += n_rows;
         st.batches++;
         return true;
