@@ -191,6 +191,23 @@ BatchPtr import_batch(Ctx& ctx, const ArrowArray* arr, const Schema& schema) {
     return b;
 }
 
+BatchPtr import_batch_slice(Ctx& ctx, const ArrowArray* arr, const Schema& schema, int64_t lo, int64_t len) {
+    AURON_CHECK(arr->n_children == (int64_t)schema.fields.size(), "batch/schema column count mismatch");
+    AURON_CHECK(arr->offset == 0 && lo >= 0 && len >= 0 && lo + len <= arr->length, "slice outside the host batch");
+    auto b = std::make_shared<Batch>();
+    b->num_rows = len;
+    for (int64_t i = 0; i < arr->n_children; i++) {
+        ArrowArray view = *arr->children[i];   // shallow: same buffers, shifted window, never released
+        view.offset += lo;
+        view.length = len;
+        if (view.null_count != 0) view.null_count = -1;
+        view.release = nullptr;
+        b->cols.push_back(import_column(ctx, &view, schema.fields[(size_t)i].type));
+    }
+    ctx.sync();
+    return b;
+}
+
 // ------------------------------------------------------------------------------------------- export
 // All buffers of an exported batch live in ONE pinned block (D2H at full PCIe rate, one stream sync per batch instead of one
 // pageable copy + sync per buffer); the block goes back to the pinned pool when the last array pointing into it is released

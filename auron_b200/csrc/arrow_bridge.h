@@ -42,6 +42,8 @@ void schema_to_arrow(const Schema& s, ArrowSchema* out);        // caller releas
 
 // H2D: copies the buffers of a struct array (one child per column) into HBM.  Does NOT release `arr`.
 BatchPtr import_batch(Ctx& ctx, const ArrowArray* arr, const Schema& schema);
+// rows [lo, lo + len) of a host struct array (a spilled sorted run read back range by range)
+BatchPtr import_batch_slice(Ctx& ctx, const ArrowArray* arr, const Schema& schema, int64_t lo, int64_t len);
 // D2H: materialises host Arrow buffers (malloc'd, freed by the release callback).
 // Results of at least `pinned_from` bytes land in a block of the pinned pool (blocks are at least 64 MB), smaller ones in plain memory.
 void export_batch(Ctx& ctx, const Batch& b, const Schema& schema, ArrowArray* out, size_t pinned_from = 1u << 20);

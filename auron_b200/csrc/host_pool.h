@@ -1,6 +1,7 @@
 // host_pool.h -- process-wide host-side helpers shared by the scan and the shuffle writer: a persistent worker pool
 // (parallel_for) and a pool of pinned staging buffers.
 #pragma once
+#include <sched.h>
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
@@ -14,6 +15,19 @@
 #include "common.h"
 
 namespace auron {
+
+// CPUs this process may run on (sched_getaffinity): with one process per GPU bound to the GPU's NUMA node that is the node's
+// share of the box, not all of it.  Sizing the pools by hardware_concurrency() put 8 x 64 workers on 128 CPUs at 8 GPUs.
+inline unsigned usable_cpus() {
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+        const int n = CPU_COUNT(&set);
+        if (n > 0) return (unsigned)n;
+    }
+    const unsigned h = std::thread::hardware_concurrency();
+    return h ? h : 1u;
+}
 
 // Persistent host worker pool (process-wide).  Spawning 32 std::threads per parallel_for cost ~0.6 ms per scan batch,
 // more than the page-header parsing they were spawned for.
@@ -50,7 +64,7 @@ class WorkerPool {
 
   private:
     WorkerPool() {
-        unsigned n = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+        unsigned n = std::max(1u, std::min(64u, usable_cpus()));
         for (unsigned i = 0; i < n; i++) {
             workers_.emplace_back([this] { loop(); });
             workers_.back().detach();

@@ -62,6 +62,24 @@ Ctx::Ctx(int dev, int stream_priority) : device(dev) {
 std::vector<Ctx::ProfTotal> Ctx::prof_summary() {
     std::vector<ProfTotal> out;
     if (prof.empty()) return out;
+    if (getenv("AURON_PROF_TIMELINE")) {   // start / end of every timed launch site relative to the first one (streams overlap: a timeline, not a sum)
+        for (auto& e : prof) cudaEventSynchronize(e.e1);
+        cudaEvent_t base = prof[0].e0;
+        float best = 0;
+        for (auto& e : prof) {
+            float d = 0;
+            if (cudaEventElapsedTime(&d, e.e0, base) == cudaSuccess && d > best) {   // e.e0 earlier than base
+                best = d;
+                base = e.e0;
+            }
+        }
+        for (auto& e : prof) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, base, e.e0);
+            cudaEventElapsedTime(&b, base, e.e1);
+            fprintf(stderr, "[timeline] %-22s %8.3f .. %8.3f ms\n", e.name, a, b);
+        }
+    }
     cudaStreamSynchronize(stream);
     for (auto& e : prof) {
         float ms = 0;

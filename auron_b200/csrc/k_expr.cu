@@ -1710,8 +1710,19 @@ struct Compiler {
             else if (a.type.is_integer() && b.type.is_integer()) {
                 if (a.type.width() < b.type.width()) a = cast_to(a, b.type);
                 else b = cast_to(b, a.type);
-            } else if (a.type.id == T_DECIMAL128 && b.type.id == T_DECIMAL128 && a.type.scale == b.type.scale) {
-            } else if (vt_of(a.type) == vt_of(b.type)) {
+            } else if (a.type.id == T_DECIMAL128 && b.type.id == T_DECIMAL128) {
+                // the kernels compare / add the unscaled i128 values: both operands must carry the same scale (arrow-rs rescales,
+                // Spark inserts the casts itself; 1.00@2 vs 1.0000@4 must not compare 100 with 10000)
+                if (a.type.scale != b.type.scale) {
+                    const int sc = std::max(a.type.scale, b.type.scale);
+                    const int ip = std::max(a.type.precision - a.type.scale, b.type.precision - b.type.scale);
+                    const DType common = DType::decimal(std::min(38, ip + sc), sc);
+                    if (a.type.scale != sc) a = cast_to(a, common);
+                    if (b.type.scale != sc) b = cast_to(b, common);
+                }
+            } else if (a.type.id == T_TIMESTAMP && b.type.id == T_TIMESTAMP) {
+                AURON_CHECK(a.type.unit == b.type.unit, "binary operator " + op + " on timestamps of different units");
+            } else if (vt_of(a.type) == vt_of(b.type) && a.type.id != T_DECIMAL128 && a.type.id != T_TIMESTAMP) {
             } else fail("binary operator " + op + " on mismatched types " + a.type.str() + " / " + b.type.str());
         }
         Vt t = vt_of(a.type);

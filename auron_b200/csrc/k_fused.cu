@@ -281,7 +281,19 @@ __device__ __forceinline__ void fz_unpack_bits(const FzX& x, uint32_t* dst, int 
     const uint32_t vmask = bw >= 32 ? 0xffffffffu : ((1u << bw) - 1u);
     uint32_t* d = dst + fz_pi(pos + (int)lane);
     int k0 = 0;
-    for (; k0 + 128 <= t; k0 += 128) {   // 4 groups per step: all eight loads are issued before the first value is used
+    for (; k0 + 256 <= t; k0 += 256) {   // 8 groups per step: all sixteen loads are issued before the first value is used
+        uint32_t lo[8], hi[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            lo[u] = __ldg(wp + u * bw);
+            hi[u] = __ldg(wp + u * bw + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) fz_store<ROLE>(dst, d + 33 * u, pos + k0 + 32 * u, lane, true, fz_xform<ROLE>(x, __funnelshift_r(lo[u], hi[u], sh) & vmask));
+        wp += 8 * bw;
+        d += 8 * 33;
+    }
+    for (; k0 + 128 <= t; k0 += 128) {   // 4 groups
         uint32_t lo[4], hi[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -438,10 +450,18 @@ __device__ __forceinline__ uint32_t fz_deposit(uint32_t bits, uint32_t w) {
     }
     return out;
 }
-// The selected rows of this lane -> accumulators.  Everything that does not depend on the row is decided before the loop:
-// per accumulator the operation, the plane of its argument and the base pointers; ALLDICT (every key of the tile came from a
-// dictionary page, the common case) drops the per-row choice between the dictionary-space and the direct arrays.
-template <int NV, int NACC, bool ALLDICT>
+// The selected rows of this lane -> accumulators.  Everything that does not depend on the row is decided before the loop;
+// ALLDICT (every key of the tile came from a dictionary page and none is NULL, the common case) drops the per-row choice between
+// the dictionary-space and the direct arrays.  SIG != 0: the accumulator list itself is a compile-time constant (6 bits per
+// accumulator: operation, argument plane, "has a valid-flag array") -- the loop body is then straight-line code; the shapes that
+// TPC-DS aggregates produce most are instantiated, any other list runs the SIG = 0 body that reads the list at run time.
+constexpr uint32_t fz_sig1(int op, int plane /* -1 COUNT(*), 0 key, 1 + v */, bool flag) { return 0x20u | (uint32_t)op | ((uint32_t)(plane + 1) << 2) | (flag ? 0x10u : 0u); }
+constexpr uint32_t FZ_SIG_SUM_COUNT = fz_sig1(0, 1, false) | (fz_sig1(1, 1, false) << 6);          // SUM(x), COUNT(x)   (AVG's partial state)
+constexpr uint32_t FZ_SIG_SUM = fz_sig1(0, 1, true);                                               // SUM(x)
+constexpr uint32_t FZ_SIG_COUNT_STAR = fz_sig1(1, -1, false);                                      // COUNT(*)
+constexpr uint32_t FZ_SIG_SUM_COUNT_STAR = fz_sig1(0, 1, true) | (fz_sig1(1, -1, false) << 6);     // SUM(x), COUNT(*)
+constexpr uint32_t FZ_SIG_SUM_SUM = fz_sig1(0, 1, true) | (fz_sig1(0, 2, true) << 6);              // SUM(x), SUM(y)
+template <int NV, int NACC, bool ALLDICT, uint32_t SIG>
 __device__ __forceinline__ void fz_rows_to_accs(const FzLaunch& L, uint32_t sel, uint32_t wk, int prefk, const uint32_t* wv, const int* prefv,
                                                 const uint32_t* s_plane) {
     constexpr int NVR = NV < 0 ? FZ_MAX_COLS - 1 : (NV == 0 ? 1 : NV);
@@ -452,23 +472,34 @@ __device__ __forceinline__ void fz_rows_to_accs(const FzLaunch& L, uint32_t sel,
     uint8_t* vd[NA];
     uint8_t* vx[NA];
     int op[NA], plane[NA];        // op: 0 add value, 1 add one, 2 min, 3 max ; plane: -1 COUNT(*), 0 key validity, 1 + v argument plane v
-    bool need_seen = true, any_flags = false;
+    bool flag[NA];
+    bool need_seen = true;
 #pragma unroll
     for (int a = 0; a < NA; a++) {
         bd[a] = bx[a] = nullptr;
         vd[a] = vx[a] = nullptr;
         op[a] = 0;
         plane[a] = -1;
+        flag[a] = false;
         if (a < nacc) {
             const FzAcc& A = L.acc[a];
             bd[a] = A.dspace;
             bx[a] = A.direct;
             vd[a] = A.dspace_valid;
             vx[a] = A.direct_valid;
-            op[a] = A.kind == ACC_COUNT ? 1 : A.kind == ACC_MIN ? 2 : A.kind == ACC_MAX ? 3 : 0;
-            plane[a] = A.col < 0 ? -1 : A.col - L.npred;
-            if (A.kind == ACC_COUNT && A.col < 0) need_seen = false;   // COUNT(*) marks every selected row's group
-            any_flags = any_flags || A.direct_valid != nullptr;
+            if (SIG) {
+                constexpr uint32_t dummy = 0;
+                (void)dummy;
+                const uint32_t s6 = (SIG >> (6 * a)) & 0x3fu;
+                op[a] = (int)(s6 & 3u);
+                plane[a] = (int)((s6 >> 2) & 3u) - 1;
+                flag[a] = (s6 & 0x10u) != 0;
+            } else {
+                op[a] = A.kind == ACC_COUNT ? 1 : A.kind == ACC_MIN ? 2 : A.kind == ACC_MAX ? 3 : 0;
+                plane[a] = A.col < 0 ? -1 : A.col - L.npred;
+                flag[a] = A.direct_valid != nullptr;
+            }
+            if (op[a] == 1 && plane[a] < 0) need_seen = false;   // COUNT(*) marks every selected row's group
         }
     }
     const uint32_t null_slot = 0x80000000u | (uint32_t)L.range;
@@ -477,7 +508,7 @@ __device__ __forceinline__ void fz_rows_to_accs(const FzLaunch& L, uint32_t sel,
         sel &= sel - 1;
         const uint32_t below = (1u << i) - 1u;
         uint32_t U = null_slot;
-        if ((wk >> i) & 1u) U = s_plane[fz_pi(prefk + __popc(wk & below))];
+        if (ALLDICT || ((wk >> i) & 1u)) U = s_plane[fz_pi(prefk + __popc(wk & below))];
         const bool dsp = ALLDICT ? true : !(U >> 31);
         const int64_t slot = (int64_t)(U & 0x7fffffffu);
         long long val[NVR];
@@ -493,7 +524,7 @@ __device__ __forceinline__ void fz_rows_to_accs(const FzLaunch& L, uint32_t sel,
             if (a >= nacc) break;
             long long v = 1;
             bool valid = true;
-            if (plane[a] == 0) valid = (wk >> i) & 1u;
+            if (plane[a] == 0) valid = ALLDICT ? true : ((wk >> i) & 1u);
 #pragma unroll
             for (int q = 0; q < NVR; q++)
                 if (plane[a] == 1 + q) {
@@ -506,12 +537,9 @@ __device__ __forceinline__ void fz_rows_to_accs(const FzLaunch& L, uint32_t sel,
             else if (op[a] == 0) atomicAdd(p, (unsigned long long)v);   // SUM (wrapping, sum.rs:115)
             else if (op[a] == 2) atomicMin((long long*)p, v);
             else atomicMax((long long*)p, v);
-            if (any_flags) {
-                uint8_t* vb = dsp ? vd[a] : vx[a];
-                if (vb) {
-                    vb[slot] = 1;
-                    marked = true;
-                }
+            if (flag[a]) {
+                (dsp ? vd[a] : vx[a])[slot] = 1;
+                marked = true;
             }
             marked = marked || op[a] == 1;
         }
@@ -520,7 +548,7 @@ __device__ __forceinline__ void fz_rows_to_accs(const FzLaunch& L, uint32_t sel,
 }
 // NV argument planes, NACC accumulators (compile time: the row loop is fully unrolled, descriptors come straight from the
 // constant bank); NV = -1: any shape, loops at run time
-template <int NV, int NACC>
+template <int NV, int NACC, uint32_t SIG>
 __global__ void __launch_bounds__(FZ_WARPS * 32) fz_kernel(const __grid_constant__ FzLaunch L) {
     extern __shared__ __align__(16) uint8_t fz_smem[];
     const int wid = threadIdx.x >> 5;
@@ -572,36 +600,43 @@ __global__ void __launch_bounds__(FZ_WARPS * 32) fz_kernel(const __grid_constant
     // ---- 3. selected rows -> accumulators
     const uint32_t rowmask = cnt >= 32 ? 0xffffffffu : (cnt > 0 ? (1u << cnt) - 1u : 0u);
     const bool dict_no_null = key_all_dict && __all_sync(FULL_MASK, wk == rowmask);   // NULL keys live in the direct table
-    if (dict_no_null) fz_rows_to_accs<NV, NACC, true>(L, sel, wk, prefk, wv, prefv, s_plane);
-    else fz_rows_to_accs<NV, NACC, false>(L, sel, wk, prefk, wv, prefv, s_plane);
+    if (dict_no_null) fz_rows_to_accs<NV, NACC, true, SIG>(L, sel, wk, prefk, wv, prefv, s_plane);
+    else fz_rows_to_accs<NV, NACC, false, SIG>(L, sel, wk, prefk, wv, prefv, s_plane);
 }
 static size_t fz_smem_bytes(int nplanes) { return (size_t)FZ_WARPS * (36 * 4 + (size_t)nplanes * FZ_VSTRIDE * 4); }
-template <int NV, int NACC>
+template <int NV, int NACC, uint32_t SIG>
 static void fz_launch(Ctx& ctx, const FzLaunch& L, size_t smem) {
     static bool attr_set = false;
     if (!attr_set) {
-        CUDA_OK(cudaFuncSetAttribute(fz_kernel<NV, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz_smem_bytes(FZ_MAX_COLS)));
+        CUDA_OK(cudaFuncSetAttribute(fz_kernel<NV, NACC, SIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz_smem_bytes(FZ_MAX_COLS)));
         attr_set = true;
     }
-    fz_kernel<NV, NACC><<<(L.n_tiles + FZ_WARPS - 1) / FZ_WARPS, FZ_WARPS * 32, smem, ctx.stream>>>(L);
+    fz_kernel<NV, NACC, SIG><<<(L.n_tiles + FZ_WARPS - 1) / FZ_WARPS, FZ_WARPS * 32, smem, ctx.stream>>>(L);
 }
 void fz_run(Ctx& ctx, const FzLaunch& L) {
     if (L.n_tiles <= 0) return;
     const int nplanes = L.ncols - L.npred, nv = nplanes - 1;
     const size_t smem = fz_smem_bytes(nplanes);
+    // signature of the accumulator list (see fz_rows_to_accs)
+    uint32_t sig = 0;
+    if (L.nacc <= 4 && !getenv("AURON_FUSED_GENERIC"))
+        for (int a = 0; a < L.nacc; a++) {
+            const FzAcc& A = L.acc[a];
+            const int op = A.kind == ACC_COUNT ? 1 : A.kind == ACC_MIN ? 2 : A.kind == ACC_MAX ? 3 : 0;
+            const int plane = A.col < 0 ? -1 : A.col - L.npred;
+            if (plane > 2) {
+                sig = 0;
+                break;
+            }
+            sig |= fz_sig1(op, plane, A.direct_valid != nullptr) << (6 * a);
+        }
     ProfScope ps(ctx, "fz_scan_filter_agg");
-    const int key = getenv("AURON_FUSED_GENERIC") ? -1 : nv * 10 + L.nacc;
-    switch (key) {
-        case 1: fz_launch<0, 1>(ctx, L, smem); break;    // COUNT(*) / COUNT(key)
-        case 11: fz_launch<1, 1>(ctx, L, smem); break;   // SUM(x)
-        case 12: fz_launch<1, 2>(ctx, L, smem); break;   // SUM(x), COUNT(x)            (AVG's partial state)
-        case 13: fz_launch<1, 3>(ctx, L, smem); break;   // SUM(x), COUNT(x), COUNT(*) ; MIN / MAX / SUM of one column
-        case 22: fz_launch<2, 2>(ctx, L, smem); break;   // SUM(x), SUM(y)
-        case 23: fz_launch<2, 3>(ctx, L, smem); break;
-        case 24: fz_launch<2, 4>(ctx, L, smem); break;
-        case 33: fz_launch<3, 3>(ctx, L, smem); break;
-        default: fz_launch<-1, -1>(ctx, L, smem); break;
-    }
+    if (sig == FZ_SIG_SUM_COUNT && nv == 1 && L.nacc == 2) fz_launch<1, 2, FZ_SIG_SUM_COUNT>(ctx, L, smem);
+    else if (sig == FZ_SIG_SUM && nv == 1 && L.nacc == 1) fz_launch<1, 1, FZ_SIG_SUM>(ctx, L, smem);
+    else if (sig == FZ_SIG_COUNT_STAR && nv == 0 && L.nacc == 1) fz_launch<0, 1, FZ_SIG_COUNT_STAR>(ctx, L, smem);
+    else if (sig == FZ_SIG_SUM_COUNT_STAR && nv == 1 && L.nacc == 2) fz_launch<1, 2, FZ_SIG_SUM_COUNT_STAR>(ctx, L, smem);
+    else if (sig == FZ_SIG_SUM_SUM && nv == 2 && L.nacc == 2) fz_launch<2, 2, FZ_SIG_SUM_SUM>(ctx, L, smem);
+    else fz_launch<-1, -1, 0>(ctx, L, smem);
     LAUNCH_CHECK(ctx);
 }
 

@@ -82,6 +82,87 @@ __global__ void __launch_bounds__(256) hash_rows_kernel(HashArgs a, int64_t n, u
     }
 }
 
+// Fixed-width keys (the shuffle / join keys of TPC-DS are int32 / int64 surrogate keys): four consecutive rows per thread, one
+// 128-bit load per 4-byte column (two per 8-byte column), one validity nibble, one 128-bit store of the four results; the
+// partition id is Lemire's fastmod (two multiplies, exact for 32-bit operands) instead of a runtime integer division.
+// Round 1's row-per-thread kernel reached 27.8 % of the HBM peak on 64M int32 keys.
+struct FastMod {
+    uint64_t m;        // floor(2^64 / d) + 1
+    uint32_t d, c;     // divisor, 2^31 mod d
+};
+__device__ __forceinline__ uint32_t fastmod_u32(uint32_t v, const FastMod& f) { return (uint32_t)__umul64hi(f.m * (uint64_t)v, (uint64_t)f.d); }
+// ((int32)hv).rem_euclid(d) (shuffle/mod.rs:178-188) without a signed division: hv + 2^31 is non-negative
+__device__ __forceinline__ int32_t pmod_i32(int32_t hv, const FastMod& f) {
+    const uint32_t r = fastmod_u32((uint32_t)hv ^ 0x80000000u, f);
+    return (int32_t)(r >= f.c ? r - f.c : r + f.d - f.c);
+}
+template <int KIND, int OUT_MODE>
+__global__ void __launch_bounds__(256) hash_fixed4_kernel(HashArgs a, int64_t n, uint64_t seed, FastMod fm, void* __restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * 256 * 4;
+    for (int64_t r0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4; r0 < n; r0 += stride) {
+        uint64_t h[4] = {seed, seed, seed, seed};
+        const bool full = r0 + 4 <= n;
+        for (int c = 0; c < a.ncols; c++) {
+            const HashCol& col = a.c[c];
+            const uint32_t vm = col.validity ? (uint32_t)(col.validity[r0 >> 3] >> (r0 & 4)) & 0xFu : 0xFu;   // r0 is a multiple of 4
+            const bool w8 = col.type == T_INT64 || col.type == T_DATE64 || col.type == T_TIMESTAMP || col.type == T_FLOAT64;
+            if (!w8) {
+                uint32_t v[4];
+                if (full) {
+                    const uint4 q = *(const uint4*)((const uint32_t*)col.data + r0);
+                    v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) v[k] = r0 + k < n ? ((const uint32_t*)col.data)[r0 + k] : 0u;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if ((vm >> k) & 1u) h[k] = KIND == 0 ? (uint64_t)murmur3_u32(v[k], (uint32_t)h[k]) : xxhash64_u32(v[k], h[k]);
+            } else {
+                uint64_t v[4];
+                if (full) {
+                    const ulonglong2 q0 = *(const ulonglong2*)((const uint64_t*)col.data + r0), q1 = *(const ulonglong2*)((const uint64_t*)col.data + r0 + 2);
+                    v[0] = q0.x, v[1] = q0.y, v[2] = q1.x, v[3] = q1.y;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) v[k] = r0 + k < n ? ((const uint64_t*)col.data)[r0 + k] : 0ull;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if ((vm >> k) & 1u) h[k] = KIND == 0 ? (uint64_t)murmur3_u64(v[k], (uint32_t)h[k]) : xxhash64_u64(v[k], h[k]);
+            }
+        }
+        if (KIND == 0) {
+            int32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) o[k] = OUT_MODE == 1 ? pmod_i32((int32_t)(uint32_t)h[k], fm) : (int32_t)(uint32_t)h[k];
+            if (full) *(int4*)((int32_t*)out + r0) = make_int4(o[0], o[1], o[2], o[3]);
+            else
+                for (int k = 0; k < 4 && r0 + k < n; k++) ((int32_t*)out)[r0 + k] = o[k];
+        } else {
+            for (int k = 0; k < 4 && r0 + k < n; k++) ((int64_t*)out)[r0 + k] = (int64_t)h[k];
+        }
+    }
+}
+static bool all_fixed_4_or_8(const std::vector<ColumnPtr>& cols) {
+    if (cols.empty() || getenv("AURON_DISABLE_HASH_FIXED4")) return false;
+    for (auto& c : cols) {
+        switch (c->type.id) {
+            case T_INT32: case T_DATE32: case T_FLOAT32: case T_INT64: case T_DATE64: case T_TIMESTAMP: case T_FLOAT64: break;
+            default: return false;
+        }
+        if (!c->data || ((uintptr_t)c->data->ptr & 15)) return false;   // 128-bit loads
+    }
+    return true;
+}
+static FastMod make_fastmod(int32_t d) {
+    FastMod f;
+    f.d = (uint32_t)d;
+    f.m = ~0ull / (uint64_t)f.d + 1;
+    f.c = (uint32_t)((1ull << 31) % f.d);
+    return f;
+}
+
 static HashArgs make_args(const std::vector<ColumnPtr>& cols) {
     AURON_CHECK((int)cols.size() <= kMaxHashCols, "too many hash columns");
     HashArgs a;
@@ -106,10 +187,11 @@ Buf hash_columns(Ctx& ctx, const std::vector<ColumnPtr>& cols, int64_t n, int ki
     HashArgs a = make_args(cols);
     Buf out = dalloc(ctx, (size_t)std::max<int64_t>(n, 1) * (kind == 0 ? 4 : 8));
     if (n == 0) return out;
-    if (kind == 0)
-        hash_rows_kernel<0, 0><<<grid_for(ctx, n), 256, 0, ctx.stream>>>(a, n, (uint64_t)(uint32_t)(int32_t)seed, 1, out->ptr);
-    else
-        hash_rows_kernel<1, 0><<<grid_for(ctx, n), 256, 0, ctx.stream>>>(a, n, (uint64_t)seed, 1, out->ptr);
+    const bool fixed = all_fixed_4_or_8(cols);
+    if (kind == 0 && fixed) hash_fixed4_kernel<0, 0><<<grid_for(ctx, (n + 3) / 4), 256, 0, ctx.stream>>>(a, n, (uint64_t)(uint32_t)(int32_t)seed, make_fastmod(1), out->ptr);
+    else if (kind == 0) hash_rows_kernel<0, 0><<<grid_for(ctx, n), 256, 0, ctx.stream>>>(a, n, (uint64_t)(uint32_t)(int32_t)seed, 1, out->ptr);
+    else if (fixed) hash_fixed4_kernel<1, 0><<<grid_for(ctx, (n + 3) / 4), 256, 0, ctx.stream>>>(a, n, (uint64_t)seed, make_fastmod(1), out->ptr);
+    else hash_rows_kernel<1, 0><<<grid_for(ctx, n), 256, 0, ctx.stream>>>(a, n, (uint64_t)seed, 1, out->ptr);
     CUDA_OK(cudaGetLastError());
     launch_count(ctx);
     return out;
@@ -135,7 +217,8 @@ Buf murmur3_partition_ids(Ctx& ctx, const std::vector<ColumnPtr>& cols, int64_t 
     Buf out = dalloc(ctx, (size_t)std::max<int64_t>(n, 1) * 4);
     if (n == 0) return out;
     ProfScope ps(ctx, "murmur3_partition_ids");
-    hash_rows_kernel<0, 1><<<grid_for(ctx, n), 256, 0, ctx.stream>>>(a, n, (uint64_t)(uint32_t)seed, num_parts, out->ptr);
+    if (all_fixed_4_or_8(cols)) hash_fixed4_kernel<0, 1><<<grid_for(ctx, (n + 3) / 4), 256, 0, ctx.stream>>>(a, n, (uint64_t)(uint32_t)seed, make_fastmod(num_parts), out->ptr);
+    else hash_rows_kernel<0, 1><<<grid_for(ctx, n), 256, 0, ctx.stream>>>(a, n, (uint64_t)(uint32_t)seed, num_parts, out->ptr);
     CUDA_OK(cudaGetLastError());
     launch_count(ctx);
     return out;

@@ -55,6 +55,19 @@ __device__ __forceinline__ void store_converted(const PqColumnArgs& a, const uin
             }
             break;
         }
+        case 3: {   // INT96 timestamp: 8 bytes nanoseconds of the day (LE) + 4 bytes Julian day (LE) -> the output column's unit
+            const int64_t nanos = (int64_t)ld_u64_unaligned(src);
+            const int64_t days = (int64_t)(int32_t)ld_u32_unaligned(src + 8) - 2440588;   // Julian day of 1970-01-01
+            int64_t v;
+            switch (a.out_unit) {
+                case 0: v = days * 86400ll + nanos / 1000000000ll; break;
+                case 1: v = days * 86400000ll + nanos / 1000000ll; break;
+                case 3: v = days * 86400000000000ll + nanos; break;
+                default: v = days * 86400000000ll + nanos / 1000ll; break;
+            }
+            ((int64_t*)a.out)[row] = v;
+            break;
+        }
         case 7: {   // FIXED_LEN_BYTE_ARRAY decimal: big-endian two's complement
             int n = a.type_length;
             uint64_t hi = (src[0] & 0x80) ? ~0ull : 0ull, lo = hi;

@@ -40,104 +40,239 @@ struct PqDecompState {
     int32_t ip, op;
 };
 
-// ---- prefix pass: ONE THREAD per nullable-v1-page job.  The body of such a page is [u32 length][definition levels][values]; with
-// dictionary-encoded values the Snappy stream is a few hundred tiny elements for the level bytes (4..8 bytes each: the level
-// runs repeat) followed by one literal that holds the value section.  A warp per job executed every one of those elements
-// 32-fold redundantly: 800 M warp instructions per SF100 pass, the whole kernel instruction-bound at 1.06 ms.  Element-level
-// work has no parallelism to offer, job-level work has plenty (one job per page), so here every lane walks its own stream
-// byte by byte.  A job that does not have the expected shape within the budget (long literal in the middle, large output) is
-// handed to the warp kernel, which resumes it from the recorded offsets.
-constexpr int SN_PREFIX_MAX_OUT = 24 * 1024, SN_PREFIX_MAX_ELEMS = 6000;
+// ---- prefix pass: FOUR LANES per nullable-v1-page job (eight jobs per warp).  The body of such a page is [u32 length][definition
+// levels][values]; with dictionary-encoded values the Snappy stream is a few hundred tiny elements for the level bytes (4..8 bytes
+// each: the level runs repeat) followed by one literal that holds the value section.  A warp per job executed every one of those
+// elements 32-fold redundantly: 800 M warp instructions per SF100 pass, the kernel instruction-bound at 1.06 ms.  An element offers
+// a few bytes of parallelism, a launch offers one job per page, so a warp now advances eight streams at once, each by one
+// element per iteration, with a 1 KB shared-memory ring per stream for the back references.  (One THREAD per stream was also
+// measured: 32 unrelated byte streams per load instruction thrash L1 -- 1.7 ms per launch.)  A job that does not have the
+// expected shape within the budget (long literal in the middle, far back reference, large output) is handed to the warp kernel
+// below, which resumes it from the recorded offsets.
+constexpr int SN_TEAM = 4, SN_TEAMS = 32 / SN_TEAM, SN_TRING = 1024, SN_WIN = 256;
+constexpr int SN_PREFIX_MAX_OUT = 48 * 1024, SN_PREFIX_MAX_ELEMS = 12000;
 __global__ void __launch_bounds__(128) pq_decompress_prefix_kernel(const PqDecompJob* __restrict__ jobs, int n_jobs, int32_t* __restrict__ status,
                                                                    PqDecompResult* __restrict__ results, PqDecompState* __restrict__ states) {
-    const int job = blockIdx.x * 128 + threadIdx.x;
-    if (job >= n_jobs) return;
-    results[job] = PqDecompResult{nullptr, -1, 0};
-    states[job] = PqDecompState{0, 0};
-    const PqDecompJob jb = jobs[job];
-    if (jb.kind != 1 || !jb.v1_levels) return;
-    const uint8_t* __restrict__ src = jb.src;
-    uint8_t* dst = jb.dst;
-    const int n_in = jb.src_len, n_out = jb.dst_len;
-    int ip = 0, op = 0;
-    {
-        uint32_t v = 0;
-        int shift = 0;
-        for (;;) {
-            if (ip >= n_in || shift > 28) return;   // malformed preamble: the warp kernel reports it
-            const uint8_t b = src[ip++];
-            v |= (uint32_t)(b & 0x7f) << shift;
-            if (!(b & 0x80)) break;
-            shift += 7;
+    __shared__ uint8_t s_ring[4][SN_TEAMS][SN_TRING];
+    // The compressed bytes are read through a 256-byte window per stream, refilled with 16-byte loads: with 40 KB of shared memory
+    // per CTA the SM has next to no L1 left, and byte loads straight from global memory paid an L2 round trip each (measured:
+    // 1.2 ms for the launch, every element three dependent L2 accesses).
+    __shared__ uint4 s_win[4][SN_TEAMS][SN_WIN / 16];
+    const unsigned lane = threadIdx.x & 31, team = lane / SN_TEAM, sub = lane % SN_TEAM;
+    const int job = (blockIdx.x * 4 + (threadIdx.x >> 5)) * SN_TEAMS + (int)team;
+    uint8_t* ring = s_ring[threadIdx.x >> 5][team];
+    uint4* win4 = s_win[threadIdx.x >> 5][team];
+    const uint8_t* win = (const uint8_t*)win4;
+    bool active = false;
+    const uint8_t* __restrict__ src = nullptr;
+    uint8_t* dst = nullptr;
+    int n_in = 0, n_out = 0, ip = 0, op = 0, elems = 0;
+    int wbase = 0;   // input offset of win[0]
+    bool have_win = false;
+    if (job < n_jobs) {
+        const PqDecompJob jb = jobs[job];
+        if (sub == 0) {
+            results[job] = PqDecompResult{nullptr, -1, 0};
+            states[job] = PqDecompState{0, 0};
         }
-        if ((int)v != n_out) return;
+        if (jb.kind == 1 && jb.v1_levels) {
+            active = true;
+            src = jb.src;
+            dst = jb.dst;
+            n_in = jb.src_len;
+            n_out = jb.dst_len;
+        }
     }
-    for (int elems = 0; ip < n_in; elems++) {
-        const int ip0 = ip;
-        if (op >= SN_PREFIX_MAX_OUT || elems >= SN_PREFIX_MAX_ELEMS) {
-            states[job] = PqDecompState{ip0, op};
-            return;
-        }
-        const uint32_t tag = src[ip++];
-        const uint32_t kind = tag & 3;
-        if (kind == 0) {
-            int len = (int)(tag >> 2) + 1;
-            if (len > 60) {
-                const int nb = len - 60;
-                if (ip + nb > n_in) break;
-                uint32_t v = 0;
-                for (int k = 0; k < nb; k++) v |= (uint32_t)src[ip + k] << (8 * k);
-                ip += nb;
-                if (v >= 0x7fffffffu) break;
-                len = (int)v + 1;
+    __syncwarp();   // the state records above are written before any lane of the team overwrites them below
+    uint32_t head = 0;        // the body's first four bytes (the length of the level section), read from the ring before it wraps
+    bool have_head = false, preamble = true;
+    while (__any_sync(FULL_MASK, active)) {
+        // ---- refill the input window when fewer than 136 bytes of it lie ahead (an element: <= 5 header bytes + <= 128 literal bytes)
+        const bool refill = active && (!have_win || ip - wbase > SN_WIN - 136);
+        if (refill) {
+            const uintptr_t g = (uintptr_t)(src + ip), ga = g & ~(uintptr_t)15;
+            wbase = ip - (int)(g - ga);
+            const uint8_t* lim = src + n_in + 16;
+#pragma unroll
+            for (int j = 0; j < SN_WIN / 16 / SN_TEAM; j++) {
+                const int q = j * SN_TEAM + (int)sub;
+                const uint8_t* a = (const uint8_t*)ga + 16 * q;
+                win4[q] = a < lim ? *(const uint4*)a : make_uint4(0, 0, 0, 0);
             }
-            if (len > n_in - ip || len > n_out - op) break;
-            if (len > 128) {
-                // the literal that holds the value section: only the level bytes that spill into it are copied (see the warp kernel)
-                if (ip + len == n_in && op + len == n_out && op >= 4) {
-                    const int64_t val_off = 4 + (int64_t)((uint32_t)dst[0] | ((uint32_t)dst[1] << 8) | ((uint32_t)dst[2] << 16) | ((uint32_t)dst[3] << 24));
-                    const int64_t keep = val_off - op;
-                    if (keep >= 0 && keep <= 512 && len - keep >= 256) {
-                        for (int i = 0; i < (int)keep; i++) dst[op + i] = src[ip + i];
-                        results[job] = PqDecompResult{src + ip + keep, (int32_t)val_off, 0};
-                        states[job] = PqDecompState{-1, 0};
-                        return;
+            have_win = true;
+        }
+        __syncwarp();
+        if (active) {
+#define SN_RD(pos) ((uint32_t)win[(pos) - wbase])
+            if (preamble) {   // uncompressed length (a malformed one is left to the warp kernel, which reports it)
+                preamble = false;
+                uint32_t v = 0;
+                int shift = 0;
+                for (;;) {
+                    if (ip >= n_in || shift > 28) {
+                        active = false;
+                        break;
+                    }
+                    const uint32_t b = SN_RD(ip);
+                    ip++;
+                    v |= (b & 0x7f) << shift;
+                    if (!(b & 0x80)) break;
+                    shift += 7;
+                }
+                if (active && (int)v != n_out) active = false;
+            }
+        }
+        if (active) {
+            if (!have_head && op >= 4 && op <= SN_TRING) {
+                head = (uint32_t)ring[0] | ((uint32_t)ring[1] << 8) | ((uint32_t)ring[2] << 16) | ((uint32_t)ring[3] << 24);
+                have_head = true;
+            }
+            const int ip0 = ip;
+            bool bad = false, handoff = false;
+            if (ip >= n_in) {
+                active = false;
+                if (op == n_out) {
+                    if (sub == 0) states[job] = PqDecompState{-1, 0};
+                } else bad = true;
+            } else if (op >= SN_PREFIX_MAX_OUT || elems++ >= SN_PREFIX_MAX_ELEMS) {
+                handoff = true;
+            } else if ([&]() {
+                           // ---- fast path, the same instruction stream for every element type (the eight streams of the warp are at
+                           // different kinds of elements: separate literal / copy branches serialise): short literal, or a 1- / 2-byte-
+                           // offset copy whose source is still in the ring
+                           const uint32_t tag = SN_RD(ip), kind = tag & 3, b1 = SN_RD(ip + 1), b2 = SN_RD(ip + 2);
+                           const bool is_lit = kind == 0;
+                           const int len = kind == 1 ? 4 + (int)((tag >> 2) & 7) : (int)(tag >> 2) + 1;
+                           const int hdr = is_lit ? 1 : (kind == 1 ? 2 : 3);
+                           const int off = kind == 1 ? (int)(((tag >> 5) << 8) | b1) : (int)(b1 | (b2 << 8));
+                           const bool ok = kind != 3 && len <= n_out - op &&
+                                           (is_lit ? (len <= 60 && ip + 1 + len <= n_in) : (ip + hdr <= n_in && off > 0 && off <= op && off <= SN_TRING - 64));
+                           if (!ok) return false;
+                           const uint8_t* sbase = is_lit ? win + (ip + 1 - wbase) : ring;
+                           const int from = op - off;
+                           for (int i = (int)sub; i < len; i += SN_TEAM) {
+                               const int si = is_lit ? i : ((from + (off >= len ? i : (int)((unsigned)i % (unsigned)off))) & (SN_TRING - 1));
+                               const uint8_t c = sbase[si];
+                               dst[op + i] = c;
+                               ring[(op + i) & (SN_TRING - 1)] = c;
+                           }
+                           ip += is_lit ? 1 + len : hdr;
+                           op += len;
+                           return true;
+                       }()) {
+            } else {
+                const uint32_t tag = SN_RD(ip);
+                ip++;
+                const uint32_t kind = tag & 3;
+                if (kind == 0) {
+                    int len = (int)(tag >> 2) + 1;
+                    if (len > 60) {
+                        const int nb = len - 60;
+                        if (ip + nb > n_in) bad = true;
+                        else {
+                            uint32_t v = 0;
+                            for (int k = 0; k < nb; k++) v |= SN_RD(ip + k) << (8 * k);
+                            ip += nb;
+                            if (v >= 0x7fffffffu) bad = true;
+                            len = (int)v + 1;
+                        }
+                    }
+                    if (!bad && (len > n_in - ip || len > n_out - op)) bad = true;
+                    if (!bad) {
+                        if (len > 128) {
+                            // the literal that holds the value section: only the level bytes that spill into it are copied (see the
+                            // warp kernel); anything else of that size is the warp kernel's business
+                            handoff = true;
+                            if (ip + len == n_in && op + len == n_out && have_head) {
+                                const int64_t val_off = 4 + (int64_t)head;
+                                const int64_t keep = val_off - op;
+                                if (keep >= 0 && keep <= 512 && len - keep >= 256) {
+                                    for (int i = (int)sub; i < (int)keep; i += SN_TEAM) dst[op + i] = src[ip + i];
+                                    if (sub == 0) {
+                                        results[job] = PqDecompResult{src + ip + keep, (int32_t)val_off, 0};
+                                        states[job] = PqDecompState{-1, 0};
+                                    }
+                                    handoff = false;
+                                    active = false;
+                                }
+                            }
+                            if (handoff) ip = ip0;
+                        } else {
+                            for (int i = (int)sub; i < len; i += SN_TEAM) {
+                                const uint8_t c = (uint8_t)SN_RD(ip + i);
+                                dst[op + i] = c;
+                                ring[(op + i) & (SN_TRING - 1)] = c;
+                            }
+                            ip += len;
+                            op += len;
+                        }
+                    }
+                } else {
+                    int len = 0, off = 0;
+                    if (kind == 1) {
+                        if (ip + 1 > n_in) bad = true;
+                        else {
+                            len = 4 + (int)((tag >> 2) & 7);
+                            off = (int)(((tag >> 5) << 8) | SN_RD(ip));
+                            ip += 1;
+                        }
+                    } else if (kind == 2) {
+                        if (ip + 2 > n_in) bad = true;
+                        else {
+                            len = (int)(tag >> 2) + 1;
+                            off = (int)(SN_RD(ip) | (SN_RD(ip + 1) << 8));
+                            ip += 2;
+                        }
+                    } else {
+                        if (ip + 4 > n_in) bad = true;
+                        else {
+                            len = (int)(tag >> 2) + 1;
+                            const uint32_t o4 = SN_RD(ip) | (SN_RD(ip + 1) << 8) | (SN_RD(ip + 2) << 16) | (SN_RD(ip + 3) << 24);
+                            if (o4 > 0x7fffffffu) bad = true;
+                            off = (int)o4;
+                            ip += 4;
+                        }
+                    }
+                    if (!bad && (off <= 0 || off > op || len > n_out - op)) bad = true;
+                    if (!bad) {
+                        if (off > SN_TRING - 64) {
+                            // the source left the ring (a dozen elements per page reach back further than 1 KB): read it back from
+                            // global memory.  Those bytes were stored by this team before earlier __syncwarp barriers, which order
+                            // them for the warp; ld.cg goes to L2, past any stale L1 line.
+                            const uint8_t* from = dst + op - off;
+                            for (int i = (int)sub; i < len; i += SN_TEAM) {
+                                const int k = off >= len ? i : (int)((unsigned)i % (unsigned)off);
+                                const uint8_t c = __ldcg(from + k);
+                                dst[op + i] = c;
+                                ring[(op + i) & (SN_TRING - 1)] = c;
+                            }
+                            op += len;
+                        } else {
+                            const int from = op - off;
+                            // byte i of the run is out[from + i % off]: every source byte is older than this element, so the four
+                            // lanes copy in parallel; a ring slot written here (op + i) is never one read here (off + len <= ring size)
+                            for (int i = (int)sub; i < len; i += SN_TEAM) {
+                                const int k = off >= len ? i : (int)((unsigned)i % (unsigned)off);
+                                const uint8_t c = ring[(from + k) & (SN_TRING - 1)];
+                                dst[op + i] = c;
+                                ring[(op + i) & (SN_TRING - 1)] = c;
+                            }
+                            op += len;
+                        }
                     }
                 }
-                states[job] = PqDecompState{ip0, op};   // a long literal in the middle of the stream: a warp copies it
-                return;
             }
-            for (int i = 0; i < len; i++) dst[op + i] = src[ip + i];
-            ip += len;
-            op += len;
-        } else {
-            int len, off;
-            if (kind == 1) {
-                if (ip + 1 > n_in) break;
-                len = 4 + (int)((tag >> 2) & 7);
-                off = (int)(((tag >> 5) << 8) | src[ip]);
-                ip += 1;
-            } else if (kind == 2) {
-                if (ip + 2 > n_in) break;
-                len = (int)(tag >> 2) + 1;
-                off = (int)((uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8));
-                ip += 2;
-            } else {
-                if (ip + 4 > n_in) break;
-                len = (int)(tag >> 2) + 1;
-                const uint32_t o4 = (uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8) | ((uint32_t)src[ip + 2] << 16) | ((uint32_t)src[ip + 3] << 24);
-                if (o4 > 0x7fffffffu) break;
-                off = (int)o4;
-                ip += 4;
+#undef SN_RD
+            if (bad) {
+                if (sub == 0) atomicCAS(status, 0, job + 1);
+                active = false;
+            } else if (handoff) {
+                if (sub == 0) states[job] = PqDecompState{ip, op};
+                active = false;
             }
-            if (off <= 0 || off > op || len > n_out - op) break;
-            const uint8_t* from = dst + op - off;
-            for (int i = 0; i < len; i++) dst[op + i] = from[i];   // byte order makes overlapping runs come out right
-            op += len;
         }
+        __syncwarp();   // ring bytes of this element are visible to the team before the next one reads them
     }
-    if (ip == n_in && op == n_out) states[job] = PqDecompState{-1, 0};
-    else atomicCAS(status, 0, job + 1);   // malformed stream
 }
 
 __global__ void __launch_bounds__(128) pq_decompress_kernel(const PqDecompJob* __restrict__ jobs, int n_jobs, int32_t* __restrict__ status,
@@ -291,7 +426,7 @@ PqDecompOut pq_decompress(Ctx& ctx, const std::vector<PqDecompJob>& jobs) {
     Buf dj = to_device(ctx, jobs.data(), jobs.size() * sizeof(PqDecompJob));
     Buf states = dalloc(ctx, jobs.size() * sizeof(PqDecompState));
     ProfScope ps(ctx, "pq_decompress");
-    pq_decompress_prefix_kernel<<<(unsigned)((jobs.size() + 127) / 128), 128, 0, ctx.stream>>>(P<PqDecompJob>(dj), (int)jobs.size(), P<int32_t>(out.status),
+    pq_decompress_prefix_kernel<<<(unsigned)((jobs.size() + 4 * SN_TEAMS - 1) / (4 * SN_TEAMS)), 128, 0, ctx.stream>>>(P<PqDecompJob>(dj), (int)jobs.size(), P<int32_t>(out.status),
                                                                                                  P<PqDecompResult>(out.results), P<PqDecompState>(states));
     LAUNCH_CHECK(ctx);
     pq_decompress_kernel<<<(unsigned)((jobs.size() + 3) / 4), 128, 0, ctx.stream>>>(P<PqDecompJob>(dj), (int)jobs.size(), P<int32_t>(out.status),

@@ -327,6 +327,102 @@ Buf sort_indices(Ctx& ctx, const std::vector<SortKeySpec>& keys, int64_t n) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// external sort support (sort_exec.rs:390-447 spill, :913-1061 Merger): sorted runs are merged by key RANGES -- splitters are
+// sampled from the runs, every run is cut at the splitters by binary search over its normalised key words, and the slices
+// of one range (from all runs) are sorted together.  The words of a run are comparable with those of any other run: the
+// NULL rank is always part of the plan here, whether or not the run's column carries a validity bitmap.
+// ---------------------------------------------------------------------------------------------
+bool sort_key_words(Ctx& ctx, const std::vector<SortKeySpec>& keys, int64_t n, std::vector<Buf>* words) {
+    std::vector<WordPlan> plan;
+    std::vector<SortCol> cols;
+    for (size_t ci = 0; ci < keys.size(); ci++) {
+        const Column& c = *keys[ci].col;
+        if (c.type.is_varlen()) return false;   // word count depends on the longest value of the run
+        cols.push_back(SortCol{c.data ? c.data->ptr : nullptr, c.vbits(), P<int32_t>(c.offsets), (int32_t)c.type.id, keys[ci].asc ? 1 : 0, keys[ci].nulls_first ? 1 : 0});
+        if (c.type.id == T_NULL) continue;
+        if (c.type.id == T_DECIMAL128) {
+            plan.push_back({(int)ci, 1, 0, false});
+            plan.push_back({(int)ci, 0, 0, false});
+            plan.push_back({(int)ci, 0, 1, false});
+        } else if (c.type.width() == 8) {
+            plan.push_back({(int)ci, 1, 0, false});
+            plan.push_back({(int)ci, 0, 0, false});
+        } else {
+            plan.push_back({(int)ci, 0, 0, true});
+        }
+    }
+    words->clear();
+    const unsigned blocks = (unsigned)((std::max<int64_t>(n, 1) + 255) / 256);
+    for (auto& wp : plan) {
+        Buf w = dalloc(ctx, (size_t)std::max<int64_t>(n, 1) * 8);
+        if (n > 0) {
+            make_sort_word_kernel<<<blocks, 256, 0, ctx.stream>>>(cols[(size_t)wp.col], wp.kind, wp.word_idx, wp.fold_null, nullptr, n, P<uint64_t>(w));
+            LAUNCH_CHECK(ctx);
+        }
+        words->push_back(w);
+    }
+    return true;
+}
+struct WordPtrs {
+    const uint64_t* w[16];
+    int nw;
+};
+// out[s * W + w] = word w of row floor((2 s + 1) n / (2 S)): S evenly spaced samples of a sorted run
+__global__ void sample_words_kernel(WordPtrs wp, int64_t n, int S, uint64_t* __restrict__ out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const int64_t row = min(n - 1, (int64_t)(((2 * (long long)s + 1) * n) / (2 * (long long)S)));
+    for (int w = 0; w < wp.nw; w++) out[(int64_t)s * wp.nw + w] = wp.w[w][row];
+}
+// out[s] = number of rows of the run whose word tuple is lexicographically < splitter s
+__global__ void lower_bound_words_kernel(WordPtrs wp, int64_t n, const uint64_t* __restrict__ splitters, int S, int64_t* __restrict__ out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = lo + ((hi - lo) >> 1);
+        bool less = false;
+        for (int w = 0; w < wp.nw; w++) {
+            const uint64_t a = wp.w[w][mid], b = splitters[(int64_t)s * wp.nw + w];
+            if (a != b) {
+                less = a < b;
+                break;
+            }
+        }
+        if (less) lo = mid + 1;
+        else hi = mid;
+    }
+    out[s] = lo;
+}
+static WordPtrs word_ptrs(const std::vector<Buf>& words) {
+    AURON_CHECK(words.size() <= 16, "too many sort key words");
+    WordPtrs wp;
+    wp.nw = (int)words.size();
+    for (int i = 0; i < wp.nw; i++) wp.w[i] = P<uint64_t>(words[(size_t)i]);
+    return wp;
+}
+std::vector<uint64_t> sample_sorted_words(Ctx& ctx, const std::vector<Buf>& words, int64_t n, int S) {
+    std::vector<uint64_t> host((size_t)S * words.size());
+    if (S <= 0 || n <= 0 || words.empty()) return host;
+    Buf out = dalloc(ctx, host.size() * 8);
+    sample_words_kernel<<<(S + 127) / 128, 128, 0, ctx.stream>>>(word_ptrs(words), n, S, P<uint64_t>(out));
+    LAUNCH_CHECK(ctx);
+    to_host(ctx, host.data(), out->ptr, host.size() * 8);
+    return host;
+}
+std::vector<int64_t> lower_bound_sorted_words(Ctx& ctx, const std::vector<Buf>& words, int64_t n, const std::vector<uint64_t>& splitters, int S) {
+    std::vector<int64_t> host((size_t)S, 0);
+    if (S <= 0) return host;
+    if (n <= 0 || words.empty()) return host;
+    Buf ds = to_device(ctx, splitters.data(), splitters.size() * 8);
+    Buf out = dalloc(ctx, (size_t)S * 8);
+    lower_bound_words_kernel<<<(S + 127) / 128, 128, 0, ctx.stream>>>(word_ptrs(words), n, P<uint64_t>(ds), S, P<int64_t>(out));
+    LAUNCH_CHECK(ctx);
+    to_host(ctx, host.data(), out->ptr, (size_t)S * 8);
+    return host;
+}
+
+// ---------------------------------------------------------------------------------------------
 // partitioner
 // ---------------------------------------------------------------------------------------------
 __global__ void widen_pid_kernel(const int32_t* __restrict__ pid, int64_t n, uint64_t* __restrict__ out) {

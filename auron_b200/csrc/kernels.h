@@ -132,6 +132,11 @@ struct SortKeySpec {
 };
 // returns permutation (int32 row indices) that orders rows by keys (stable)
 Buf sort_indices(Ctx& ctx, const std::vector<SortKeySpec>& keys, int64_t n_rows);
+// external sort: normalised key words (most significant first) of the rows of a batch in row order -- comparable across batches;
+// false when a key column is variable-length.  Samples / lower bounds over the words of a SORTED batch.
+bool sort_key_words(Ctx& ctx, const std::vector<SortKeySpec>& keys, int64_t n, std::vector<Buf>* words);
+std::vector<uint64_t> sample_sorted_words(Ctx& ctx, const std::vector<Buf>& words, int64_t n, int S);   // [S][W]
+std::vector<int64_t> lower_bound_sorted_words(Ctx& ctx, const std::vector<Buf>& words, int64_t n, const std::vector<uint64_t>& splitters, int S);
 // stable LSD radix sort of (u64 key, i32 value) pairs, in place over ping-pong buffers; bits [begin_bit, end_bit)
 void radix_sort_pairs_u64(Ctx& ctx, Buf& keys, Buf& vals, int64_t n, int begin_bit, int end_bit);
 // stable counting partition of rows by partition id: returns row order + offsets[num_parts+1] (device int64)

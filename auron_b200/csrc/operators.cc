@@ -311,6 +311,61 @@ BatchPtr ProjectExec::next(Task& t) {
     return out;
 }
 
+// ------------------------------------------------------------------------------------------ ExpandExec
+ExpandExec::ExpandExec(OperatorPtr input, const Schema& schema, std::vector<std::vector<ExprPtr>> projs) : projections(std::move(projs)) {
+    name = "ExpandExec";
+    out_schema = schema;
+    const Schema& in = input->out_schema;
+    AURON_CHECK(!projections.empty(), "ExpandExecNode without projections");
+    for (auto& pr : projections) {
+        AURON_CHECK(pr.size() == schema.fields.size(), "ExpandExec: a projection does not match the output schema");
+        std::vector<ExprPtr> computed;
+        std::vector<int> pl;
+        for (size_t i = 0; i < pr.size(); i++) {
+            const DType actual = infer_type(*pr[i], in);
+            if (actual != schema.fields[i].type) {   // expand_exec.rs:166-168
+                auto c = std::make_shared<Expr>();
+                c->kind = E_TRY_CAST;
+                c->type = schema.fields[i].type;
+                c->children.push_back(pr[i]);
+                pr[i] = c;
+            }
+            int idx = -1;
+            if (is_plain_column(*pr[i], in, &idx)) pl.push_back(idx);
+            else {
+                pl.push_back(-1);
+                computed.push_back(pr[i]);
+            }
+        }
+        plain.push_back(pl);
+        progs.push_back(computed.empty() ? VmProgram() : compile_projection(computed, in));
+    }
+    children.push_back(std::move(input));
+}
+std::string ExpandExec::describe() const {
+    std::string o = "\"projections\":[";
+    for (size_t i = 0; i < projections.size(); i++) o += (i ? "," : "") + exprs_json(projections[i]);
+    return o + "]";
+}
+BatchPtr ExpandExec::next(Task& t) {
+    if (!cur || next_proj >= projections.size()) {
+        cur = children[0]->next(t);
+        next_proj = 0;
+        if (!cur) return nullptr;
+    }
+    OpTimer timer(metrics, "elapsed_ns");
+    const size_t pi = next_proj++;
+    auto out = std::make_shared<Batch>();
+    out->num_rows = cur->num_rows;
+    std::vector<ColumnPtr> computed;
+    if (progs[pi].impl) computed = eval_projection(t.ctx, progs[pi], *cur, nullptr, cur->num_rows);
+    size_t ci = 0;
+    for (int idx : plain[pi]) out->cols.push_back(idx >= 0 ? cur->cols[(size_t)idx] : computed[ci++]);
+    if (next_proj >= projections.size()) cur.reset();
+    metrics.add("output_rows", out->num_rows);
+    return out;
+}
+
 // ------------------------------------------------------------------------------------------ AggExec
 static bool load_compatible(const DType& child, const DType& acc) {
     if (child == acc) return true;
@@ -737,9 +792,18 @@ BatchPtr AggExec::next(Task& t) {
         if (r == FUSED_END) {
             input_done = true;
             if (fused_state.table) {
-                if (direct_agg_out_of_range(t.ctx, *fused_state.table))
-                    fail("parquet column statistics do not cover the values of the group key column (corrupt file?); "
-                         "AURON_DISABLE_FUSED_SCAN_AGG=1 reads it without trusting them");
+                if (direct_agg_out_of_range(t.ctx, *fused_state.table)) {
+                    // the column statistics did not cover the key values (buggy writer): everything aggregated so far is void.
+                    // Read the input again, operator by operator (that path detects lying statistics per chunk and falls back to its hash table).
+                    AURON_CHECK(spilled.empty(), "parquet column statistics do not cover the values of the group key column");
+                    fused_src->restart(t);
+                    fused_src = nullptr;
+                    fused_state = FusedAggState();
+                    partials.clear();
+                    partial_rows = 0;
+                    input_done = false;
+                    break;
+                }
                 unsigned long long sel_rows = 0;
                 to_host(t.ctx, &sel_rows, fused_state.selected->ptr, 8);
                 if (fused_filter) fused_filter->metrics.add("output_rows", (int64_t)sel_rows);
@@ -970,32 +1034,374 @@ BatchPtr HashJoinExec::next(Task& t) {
     return out;
 }
 
+// ------------------------------------------------------------------------------------------ SortMergeJoinExec
+namespace {
+struct BatchListExec : Operator {   // a fixed list of batches as an operator (one piece of one side)
+    std::vector<BatchPtr> batches;
+    size_t pos = 0;
+    BatchListExec(const Schema& s, std::vector<BatchPtr> b) : batches(std::move(b)) {
+        name = "SmjPiece";
+        out_schema = s;
+    }
+    BatchPtr next(Task&) override { return pos < batches.size() ? batches[pos++] : nullptr; }
+};
+struct ForwardExec : Operator {     // forwards to an operator owned elsewhere
+    Operator* target;
+    explicit ForwardExec(Operator* o) : target(o) {
+        name = o->name;
+        out_schema = o->out_schema;
+    }
+    BatchPtr next(Task& t) override { return target->next(t); }
+};
+}  // namespace
+
+SortMergeJoinExec::SortMergeJoinExec(OperatorPtr left, OperatorPtr right, std::vector<ExprPtr> lk, std::vector<ExprPtr> rk, std::vector<std::pair<bool, bool>> opts,
+                                     int jt, const Schema& schema)
+    : left_keys(std::move(lk)), right_keys(std::move(rk)), sort_opts(std::move(opts)), join_type(jt) {
+    name = "SortMergeJoinExec";
+    // output schema exactly as the hash join derives it: [left cols..., right cols...] (+ exists)
+    HashJoinExec probe_schema(std::make_unique<BatchListExec>(left->out_schema, std::vector<BatchPtr>()),
+                              std::make_unique<BatchListExec>(right->out_schema, std::vector<BatchPtr>()), left_keys, right_keys, jt, SIDE_RIGHT, schema);
+    out_schema = probe_schema.out_schema;
+    while (sort_opts.size() < left_keys.size()) sort_opts.emplace_back(true, true);   // SortOptions::default(): ascending, nulls first
+    children.push_back(std::move(left));
+    children.push_back(std::move(right));
+}
+std::string SortMergeJoinExec::describe() const {
+    static const char* jt[] = {"INNER", "LEFT", "RIGHT", "FULL", "SEMI", "ANTI", "EXISTENCE"};
+    return std::string("\"join_type\":\"") + (join_type >= 0 && join_type <= 6 ? jt[join_type] : "?") + "\",\"left_keys\":" + exprs_json(left_keys) +
+           ",\"right_keys\":" + exprs_json(right_keys);
+}
+bool SortMergeJoinExec::pull(Task& t, int s) {
+    if (side[s].done) return false;
+    BatchPtr b = children[(size_t)s]->next(t);
+    if (!b) {
+        side[s].done = true;
+        return false;
+    }
+    if (b->num_rows == 0) return true;
+    side[s].buf = side[s].buf && side[s].buf->num_rows ? concat_batches(t.ctx, {side[s].buf, b}) : b;
+    return true;
+}
+std::vector<Buf> SortMergeJoinExec::words_of(Task& t, int s, const BatchPtr& b) {
+    const auto& keys = s == 0 ? left_keys : right_keys;
+    std::vector<SortKeySpec> specs;
+    for (size_t i = 0; i < keys.size(); i++) specs.push_back({eval_to_column(t, keys[i], children[(size_t)s]->out_schema, *b), sort_opts[i].first, sort_opts[i].second});
+    std::vector<Buf> w;
+    AURON_CHECK(sort_key_words(t.ctx, specs, b->num_rows, &w), "sort-merge join pieces need fixed-width keys");
+    return w;
+}
+void SortMergeJoinExec::join_piece(Task& t, const BatchPtr& l, const BatchPtr& r) {
+    // the driving side is probed (its order is the output order), the other side is built
+    const int build = join_type == JOIN_RIGHT ? SIDE_LEFT : SIDE_RIGHT;
+    std::vector<BatchPtr> lb, rb;
+    if (l && l->num_rows) lb.push_back(l);
+    if (r && r->num_rows) rb.push_back(r);
+    HashJoinExec j(std::make_unique<BatchListExec>(children[0]->out_schema, lb), std::make_unique<BatchListExec>(children[1]->out_schema, rb), left_keys, right_keys, join_type,
+                   build, Schema());
+    while (BatchPtr b = j.next(t))
+        if (b->num_rows) out_q.push_back(b);
+    metrics.add("pieces", 1);
+}
+BatchPtr SortMergeJoinExec::next(Task& t) {
+    if (!fallback_checked) {
+        fallback_checked = true;
+        bool varlen = false;
+        for (auto& k : left_keys) varlen = varlen || infer_type(*k, children[0]->out_schema).is_varlen();
+        for (auto& k : right_keys) varlen = varlen || infer_type(*k, children[1]->out_schema).is_varlen();
+        if (varlen || getenv("AURON_SMJ_AS_HASH_JOIN")) {
+            const int build = join_type == JOIN_RIGHT ? SIDE_LEFT : SIDE_RIGHT;
+            whole.reset(new HashJoinExec(std::make_unique<ForwardExec>(children[0].get()), std::make_unique<ForwardExec>(children[1].get()), left_keys, right_keys, join_type,
+                                         build, Schema()));
+        }
+    }
+    if (whole) {
+        BatchPtr b = whole->next(t);
+        if (b) metrics.add("output_rows", b->num_rows);
+        return b;
+    }
+    const int D = join_type == JOIN_RIGHT ? 1 : 0, O = 1 - D;
+    for (;;) {
+        if (out_pos < out_q.size()) {
+            BatchPtr b = out_q[out_pos++];
+            if (out_pos == out_q.size()) {
+                out_q.clear();
+                out_pos = 0;
+            }
+            metrics.add("output_rows", b->num_rows);
+            return b;
+        }
+        if (finished) return nullptr;
+        AURON_CHECK(t.is_running(), "task killed");
+        // ---- 1. a piece of the driving side that ends at a key boundary
+        if (!(side[D].buf && side[D].buf->num_rows) && !side[D].done) {
+            pull(t, D);
+            continue;
+        }
+        const bool d_empty = !(side[D].buf && side[D].buf->num_rows);
+        BatchPtr dpiece, opiece;
+        if (d_empty) {
+            // the driving side is exhausted: what is left of the other side matches nothing; only FULL OUTER still emits it
+            if (join_type != JOIN_FULL) {
+                finished = true;
+                continue;
+            }
+            if (!(side[O].buf && side[O].buf->num_rows) && !pull(t, O)) {
+                if (side[O].done) finished = true;
+                continue;
+            }
+            opiece = side[O].buf;
+            side[O].buf.reset();
+            if (opiece && opiece->num_rows) join_piece(t, D == 0 ? dpiece : opiece, D == 0 ? opiece : dpiece);
+            continue;
+        }
+        std::vector<uint64_t> bound;   // key words (exclusive) below which every row of this piece lies; empty = unbounded
+        {
+            std::vector<Buf> w = words_of(t, D, side[D].buf);
+            const int64_t n = side[D].buf->num_rows;
+            std::vector<uint64_t> last(w.size());
+            for (size_t i = 0; i < w.size(); i++) to_host(t.ctx, &last[i], P<uint64_t>(w[i]) + (n - 1), 8);
+            if (side[D].done) {
+                // last piece: everything buffered; the other side contributes the rows up to and including the last key
+                dpiece = side[D].buf;
+                side[D].buf.reset();
+                bound = last;
+                int i = (int)bound.size() - 1;
+                while (i >= 0 && ++bound[(size_t)i] == 0) i--;   // tuple + 1 (lexicographic successor)
+                if (i < 0) bound.clear();                        // the largest tuple there is: no upper bound
+            } else {
+                const int64_t cut = w.empty() ? 0 : lower_bound_sorted_words(t.ctx, w, n, last, 1)[0];
+                if (cut == 0) {   // one key group so far: it may continue in the next batch
+                    pull(t, D);
+                    continue;
+                }
+                dpiece = slice_batch(t.ctx, *side[D].buf, 0, cut);
+                side[D].buf = slice_batch(t.ctx, *side[D].buf, cut, n - cut);
+                bound = last;
+            }
+        }
+        // ---- 2. the rows of the other side below the bound
+        for (;;) {
+            const int64_t on = side[O].buf ? side[O].buf->num_rows : 0;
+            if (on > 0 && !bound.empty()) {
+                std::vector<Buf> w = words_of(t, O, side[O].buf);
+                const int64_t ocut = lower_bound_sorted_words(t.ctx, w, on, bound, 1)[0];
+                if (ocut < on || side[O].done) {   // a row at or above the bound is buffered: nothing below it can still arrive
+                    opiece = ocut ? slice_batch(t.ctx, *side[O].buf, 0, ocut) : nullptr;
+                    side[O].buf = ocut < on ? slice_batch(t.ctx, *side[O].buf, ocut, on - ocut) : nullptr;
+                    break;
+                }
+            } else if (side[O].done) {
+                opiece = side[O].buf;   // (unbounded: all of it)
+                side[O].buf.reset();
+                break;
+            }
+            pull(t, O);
+        }
+        join_piece(t, D == 0 ? dpiece : opiece, D == 0 ? opiece : dpiece);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ SortExec
 SortExec::SortExec(OperatorPtr input, std::vector<SortExprSpec> k, int64_t lim, int64_t off) : keys(std::move(k)), limit(lim), offset(off) {
     name = "SortExec";
     out_schema = input->out_schema;
     children.push_back(std::move(input));
 }
-BatchPtr SortExec::next(Task& t) {
-    if (done) return nullptr;
-    done = true;
-    std::vector<BatchPtr> all;
-    while (BatchPtr b = children[0]->next(t)) {
-        AURON_CHECK(t.is_running(), "task killed");
-        if (b->num_rows) all.push_back(b);
-    }
-    if (all.empty()) return nullptr;
-    BatchPtr in = concat_batches(t.ctx, all);
-    all.clear();
+static void release_sort_runs(std::vector<SortExec::Run>& runs) {
+    for (auto& r : runs)
+        if (r.spilled && r.host.release) r.host.release(&r.host);
+    runs.clear();
+}
+SortExec::~SortExec() { release_sort_runs(runs); }
+BatchPtr SortExec::sort_batch(Task& t, const BatchPtr& in, int64_t keep_rows) {
     std::vector<SortKeySpec> specs;
     for (auto& k : keys) specs.push_back({eval_to_column(t, k.expr, out_schema, *in), k.asc, k.nulls_first});
     Buf perm = sort_indices(t.ctx, specs, in->num_rows);
-    // fetch limit: keep sorted rows [offset, limit)  (sort_exec.rs:663,720-722,964)
-    int64_t n = in->num_rows, begin = std::min<int64_t>(offset, n), end = limit >= 0 ? std::min<int64_t>(limit, n) : n;
-    if (end <= begin) return nullptr;
-    BatchPtr out = take_batch(t.ctx, *in, P<int32_t>(perm) + begin, end - begin, false);
-    metrics.add("output_rows", out->num_rows);
-    return out;
+    const int64_t n = keep_rows >= 0 ? std::min<int64_t>(keep_rows, in->num_rows) : in->num_rows;
+    return take_batch(t.ctx, *in, P<int32_t>(perm), n, false);
+}
+static int64_t sort_batch_bytes(const Batch& b) {
+    int64_t n = 0;
+    for (auto& c : b.cols)
+        for (const Buf* buf : {&c->validity, &c->data, &c->offsets})
+            if (*buf) n += (int64_t)(*buf)->bytes;
+    return n;
+}
+void SortExec::add_run(Task& t, const BatchPtr& sorted) {
+    Run r;
+    r.dev = sorted;
+    r.rows = sorted->num_rows;
+    r.bytes = sort_batch_bytes(*sorted);
+    std::vector<SortKeySpec> specs;
+    for (auto& k : keys) specs.push_back({eval_to_column(t, k.expr, out_schema, *sorted), k.asc, k.nulls_first});
+    AURON_CHECK(sort_key_words(t.ctx, specs, sorted->num_rows, &r.words), "external sort over variable-length keys");
+    memset(&r.host, 0, sizeof(r.host));
+    runs.push_back(std::move(r));
+    metrics.add("sorted_runs", 1);
+}
+// runs that do not fit the HBM budget move to pinned host memory, oldest first (sort_exec.rs:390-447: spill of the in-memory runs)
+void SortExec::spill_if_needed(Task& t) {
+    int64_t held = 0;
+    for (auto& r : runs)
+        if (!r.spilled) held += r.bytes;
+    for (auto& r : runs) {
+        if (held <= spill_budget) break;
+        if (r.spilled) continue;
+        OpTimer timer(metrics, "spill_ns");
+        export_batch(t.ctx, *r.dev, out_schema, &r.host, (size_t)1 << 20);
+        r.dev.reset();
+        r.spilled = true;
+        held -= r.bytes;
+        metrics.add("mem_spill_count", 1);
+        metrics.add("mem_spill_size", r.bytes);
+    }
+}
+// Splitters: every run contributes evenly spaced samples of its key words (each standing for rows / samples rows); the sorted
+// sample is cut where the cumulated weight crosses a multiple of the target range size; every run is then cut at the splitters.
+void SortExec::prepare_merge(Task& t) {
+    merge_ready = true;
+    int64_t total = 0;
+    for (auto& r : runs) total += r.rows;
+    const int64_t target = std::max<int64_t>(1, run_rows / 2);
+    const int W = runs.empty() ? 0 : (int)runs[0].words.size();
+    struct Sample {
+        std::vector<uint64_t> w;
+        double weight;
+    };
+    std::vector<Sample> samples;
+    if (W > 0)
+        for (auto& r : runs) {
+            const int S = (int)std::min<int64_t>(r.rows, 1024);
+            if (S <= 0) continue;
+            std::vector<uint64_t> sw = sample_sorted_words(t.ctx, r.words, r.rows, S);
+            for (int i = 0; i < S; i++) samples.push_back(Sample{std::vector<uint64_t>(sw.begin() + (size_t)i * W, sw.begin() + (size_t)(i + 1) * W), (double)r.rows / S});
+        }
+    std::sort(samples.begin(), samples.end(), [](const Sample& a, const Sample& b) { return a.w < b.w; });
+    std::vector<uint64_t> splitters;   // [S][W], strictly increasing
+    double acc = 0, next_cut = (double)target;
+    const std::vector<uint64_t>* last = nullptr;
+    for (auto& sm : samples) {
+        acc += sm.weight;
+        if (acc >= next_cut && acc < (double)total) {
+            if (!last || *last < sm.w) {
+                splitters.insert(splitters.end(), sm.w.begin(), sm.w.end());
+                last = &sm.w;
+            }
+            while (next_cut <= acc) next_cut += (double)target;
+        }
+    }
+    const int S = W ? (int)(splitters.size() / (size_t)W) : 0;
+    n_ranges = (size_t)S + 1;
+    for (auto& r : runs) {
+        std::vector<int64_t> lb = S ? lower_bound_sorted_words(t.ctx, r.words, r.rows, splitters, S) : std::vector<int64_t>();
+        r.cuts.assign(1, 0);
+        for (int64_t v : lb) r.cuts.push_back(v);
+        r.cuts.push_back(r.rows);
+        r.words.clear();   // not needed any more
+    }
+    metrics.add("merge_ranges", (int64_t)n_ranges);
+}
+BatchPtr SortExec::window(const BatchPtr& b, Task& t) {
+    // rows [offset, limit) of the whole sorted stream (sort_exec.rs:720-722,964)
+    const int64_t first = emitted_seen, n = b->num_rows;
+    emitted_seen += n;
+    const int64_t lo = std::max<int64_t>(offset - first, 0), hi = limit >= 0 ? std::min<int64_t>(n, limit - first) : n;
+    if (hi <= lo) return nullptr;
+    if (lo == 0 && hi == n) return b;
+    return slice_batch(t.ctx, *b, lo, hi - lo);
+}
+BatchPtr SortExec::next(Task& t) {
+    if (done) return nullptr;
+    if (run_rows == 0) {
+        run_rows = t.ctx.gpu_chunk_rows;
+        if (const char* e = getenv("AURON_SORT_RUN_ROWS")) run_rows = std::max<int64_t>(1, atoll(e));
+        run_rows = std::min<int64_t>(run_rows, (int64_t)1 << 30);   // row ids inside a run are 32-bit
+        if (const char* e = getenv("AURON_SORT_SPILL_BYTES")) spill_budget = atoll(e);
+        if (spill_budget <= 0) {
+            size_t free_b = 0, total_b = 0;
+            CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+            spill_budget = (int64_t)(total_b / 10 * 4);
+        }
+    }
+    bool varlen_key = false;
+    for (auto& k : keys) varlen_key = varlen_key || infer_type(*k.expr, out_schema).is_varlen();
+    // ---- run generation
+    while (!input_done) {
+        std::vector<BatchPtr> chunk;
+        int64_t rows = 0;
+        // (variable-length keys: one run holds everything -- their word count depends on the longest value, see sort_key_words)
+        while (varlen_key || rows < run_rows) {
+            AURON_CHECK(t.is_running(), "task killed");
+            BatchPtr b = children[0]->next(t);
+            if (!b) {
+                input_done = true;
+                break;
+            }
+            if (b->num_rows == 0) continue;
+            // a batch larger than the run size is cut: runs stay within the 32-bit row ids of the sort kernels
+            for (int64_t o = 0; o < b->num_rows; o += run_rows) {
+                const int64_t m = std::min<int64_t>(run_rows, b->num_rows - o);
+                chunk.push_back(m == b->num_rows ? b : slice_batch(t.ctx, *b, o, m));
+                rows += m;
+            }
+        }
+        if (chunk.empty()) break;
+        // group the pieces into runs of at most run_rows rows
+        size_t i = 0;
+        while (i < chunk.size()) {
+            std::vector<BatchPtr> grp;
+            int64_t g = 0;
+            while (i < chunk.size() && (grp.empty() || varlen_key || g + chunk[i]->num_rows <= run_rows)) {
+                g += chunk[i]->num_rows;
+                grp.push_back(chunk[i++]);
+            }
+            AURON_CHECK(g < (int64_t)INT32_MAX, "sort run too large (variable-length sort keys are sorted in one run)");
+            OpTimer timer(metrics, "sort_ns");
+            BatchPtr in = grp.size() == 1 ? grp[0] : concat_batches(t.ctx, grp);
+            grp.clear();
+            BatchPtr sorted = sort_batch(t, in, limit);   // only the first `limit` rows of a run can reach the output (sort_exec.rs:663)
+            if (input_done && runs.empty() && i >= chunk.size()) {   // everything fitted one run: no merge
+                done = true;
+                BatchPtr out = window(sorted, t);
+                if (out) metrics.add("output_rows", out->num_rows);
+                return out;
+            }
+            add_run(t, sorted);
+            spill_if_needed(t);
+        }
+    }
+    if (runs.empty()) {
+        done = true;
+        return nullptr;
+    }
+    // ---- merge, one key range per call
+    if (!merge_ready) prepare_merge(t);
+    while (next_range < n_ranges) {
+        const size_t r = next_range++;
+        if (limit >= 0 && emitted_seen >= limit) break;
+        OpTimer timer(metrics, "merge_ns");
+        std::vector<BatchPtr> pieces;
+        for (auto& run : runs) {
+            const int64_t lo = run.cuts[r], n = run.cuts[r + 1] - lo;
+            if (n <= 0) continue;
+            pieces.push_back(run.spilled ? import_batch_slice(t.ctx, &run.host, out_schema, lo, n) : slice_batch(t.ctx, *run.dev, lo, n));
+        }
+        if (pieces.empty()) continue;
+        BatchPtr in = pieces.size() == 1 ? pieces[0] : concat_batches(t.ctx, pieces);
+        const bool single = pieces.size() == 1;
+        pieces.clear();
+        AURON_CHECK(in->num_rows < (int64_t)INT32_MAX, "a key range of the external sort exceeds 2^31 rows (one key value repeated that often?)");
+        BatchPtr sorted = single ? in : sort_batch(t, in, -1);
+        BatchPtr out = window(sorted, t);
+        if (out) {
+            metrics.add("output_rows", out->num_rows);
+            return out;
+        }
+    }
+    done = true;
+    release_sort_runs(runs);
+    return nullptr;
 }
 
 // ------------------------------------------------------------------------------------------ misc

@@ -51,6 +51,9 @@ struct FusedScanSource {
     // FUSED_DONE: the next batch went through the fused kernels into `st`; FUSED_FALLBACK: it could not, *fallback holds it as
     // a regular batch; FUSED_END: no more input (all kernels of earlier batches have completed)
     virtual int next_fused(Task& t, const FusedAggSpec& spec, FusedAggState& st, BatchPtr* fallback) = 0;
+    // rewind to the first row (after FUSED_END): the fused pass met keys outside the range the file statistics promised, its
+    // result is void and the caller reads the input again through the regular path
+    virtual void restart(Task& t) = 0;
 };
 
 // filter_exec.rs:128-224
@@ -157,6 +160,35 @@ struct HashJoinExec : Operator {
     Operator& probe_child() { return *children[build_side == SIDE_LEFT ? 1 : 0]; }
 };
 
+// sort_merge_join_exec.rs:135-205,294-372 + joins/smj/*.rs.  Both inputs arrive sorted on the join keys.  The reference advances two
+// row cursors; here the two streams are cut into KEY-DISJOINT pieces (a piece ends where the key of the driving side changes, the
+// other side contributes exactly the rows below that key) and every piece is joined with the hash kernels.  Memory is bounded
+// by the piece (one input chunk per side plus the key group that straddles its end), both sides are streamed, and the output
+// keeps the order of the driving side (left; right for RIGHT OUTER), which is what Spark assumes after a SortMergeJoin.
+struct SortMergeJoinExec : Operator {
+    std::vector<ExprPtr> left_keys, right_keys;
+    std::vector<std::pair<bool, bool>> sort_opts;   // (asc, nulls_first) per key
+    int join_type = JOIN_INNER;
+    struct Side {
+        BatchPtr buf;
+        bool done = false;
+    };
+    Side side[2];   // 0 = left, 1 = right
+    std::vector<BatchPtr> out_q;
+    size_t out_pos = 0;
+    bool finished = false, fallback_checked = false;
+    std::unique_ptr<Operator> whole;   // variable-length keys: one hash join over the whole inputs (no key words to cut by)
+    SortMergeJoinExec(OperatorPtr left, OperatorPtr right, std::vector<ExprPtr> lk, std::vector<ExprPtr> rk, std::vector<std::pair<bool, bool>> opts,
+                      int join_type, const Schema& schema);
+    std::string describe() const override;
+    BatchPtr next(Task& t) override;
+
+   private:
+    bool pull(Task& t, int s);
+    std::vector<Buf> words_of(Task& t, int s, const BatchPtr& b);
+    void join_piece(Task& t, const BatchPtr& l, const BatchPtr& r);
+};
+
 struct SortExprSpec {
     ExprPtr expr;
     bool asc = true, nulls_first = true;
@@ -167,9 +199,31 @@ struct SortExec : Operator {
     std::vector<SortExprSpec> keys;
     int64_t limit = -1, offset = 0;
     bool done = false;
+    // ExternalSorter (sort_exec.rs:390-447,637-768,913-1061): the input is sorted in runs of at most `run_rows` rows; runs beyond
+    // the HBM budget are spilled to pinned host memory; the output merges the runs key range by key range
+    struct Run {
+        BatchPtr dev;                 // sorted rows in HBM (null once spilled)
+        ArrowArray host;              // pinned host copy (spilled runs)
+        bool spilled = false;
+        std::vector<Buf> words;       // normalised key words of the sorted rows (stay in HBM: 8..24 B per row)
+        int64_t rows = 0, bytes = 0;
+        std::vector<int64_t> cuts;    // [ranges + 1] row positions of the range boundaries
+    };
+    std::vector<Run> runs;
+    bool input_done = false, merge_ready = false;
+    int64_t run_rows = 0, spill_budget = 0, emitted_seen = 0;
+    size_t next_range = 0, n_ranges = 0;
     SortExec(OperatorPtr input, std::vector<SortExprSpec> keys, int64_t limit, int64_t offset);
+    ~SortExec() override;
     std::string describe() const override;
     BatchPtr next(Task& t) override;
+
+   private:
+    BatchPtr sort_batch(Task& t, const BatchPtr& in, int64_t keep_rows);   // rows of `in` in key order (first keep_rows of them; < 0 = all)
+    void add_run(Task& t, const BatchPtr& sorted);
+    void spill_if_needed(Task& t);
+    void prepare_merge(Task& t);
+    BatchPtr window(const BatchPtr& b, Task& t);   // rows of an output batch that fall into [offset, limit)
 };
 
 // limit_exec.rs:132-180
@@ -192,6 +246,19 @@ struct PassThroughExec : Operator {   // CoalesceBatches / BroadcastJoinBuildHas
     PassThroughExec(OperatorPtr input, const std::string& nm);
     BatchPtr next(Task& t) override { return children[0]->next(t); }
 };
+// expand_exec.rs:127-185: every input batch is emitted once per projection list (GROUPING SETS / ROLLUP / CUBE), each expression
+// cast to the declared output field type
+struct ExpandExec : Operator {
+    std::vector<std::vector<ExprPtr>> projections;
+    std::vector<VmProgram> progs;
+    std::vector<std::vector<int>> plain;   // per projection, per output column: >= 0 bare input column, -1 computed (next program output)
+    BatchPtr cur;
+    size_t next_proj = 0;
+    ExpandExec(OperatorPtr input, const Schema& schema, std::vector<std::vector<ExprPtr>> projections);
+    std::string describe() const override;
+    BatchPtr next(Task& t) override;
+};
+
 // union_exec.rs:118-160
 struct UnionExec : Operator {
     size_t cur = 0;

@@ -31,6 +31,7 @@ struct PqColumnArgs {
     int32_t out_type, out_width;
     int32_t max_def;
     int32_t mode;
+    int32_t out_unit, pad0;   // T_TIMESTAMP output: 0 s, 1 ms, 2 us, 3 ns (INT96 pages are converted to it)
     void* out;
     uint32_t* out_valid;
     int32_t* out_idx;

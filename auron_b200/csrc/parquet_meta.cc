@@ -56,7 +56,14 @@ struct TReader {
         *size = h >> 4;
         if (*size == 15) *size = (uint32_t)varint();
     }
+    int depth = 0;   // nesting of skipped containers / structs (a footer of 0x1C bytes would otherwise recurse once per byte)
+    struct DepthGuard {
+        int& d;
+        explicit DepthGuard(int& x) : d(x) { AURON_CHECK(++d <= 64, "parquet: thrift structure nested too deeply"); }
+        ~DepthGuard() { --d; }
+    };
     void skip(int type) {
+        DepthGuard g(depth);
         switch (type) {
             case 1: case 2: break;   // bool in field header
             case 3: byte(); break;
@@ -67,6 +74,7 @@ struct TReader {
                 int et;
                 uint32_t n;
                 list_header(&et, &n);
+                AURON_CHECK((size_t)(end - p) >= n, "parquet: truncated thrift list");
                 for (uint32_t i = 0; i < n; i++) {
                     if (et == 1 || et == 2) byte();
                     else skip(et);
@@ -77,9 +85,12 @@ struct TReader {
                 uint32_t n = (uint32_t)varint();
                 if (n) {
                     uint8_t kv = byte();
+                    AURON_CHECK((size_t)(end - p) >= n, "parquet: truncated thrift map");   // every entry takes at least one byte
                     for (uint32_t i = 0; i < n; i++) {
-                        skip(kv >> 4);
-                        skip(kv & 0x0f);
+                        for (int et : {kv >> 4, kv & 0x0f}) {
+                            if (et == 1 || et == 2) byte();   // bools inside containers are one byte each
+                            else skip(et);
+                        }
                     }
                 }
                 break;

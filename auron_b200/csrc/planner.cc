@@ -726,12 +726,27 @@ static OperatorPtr decode_join(Task& t, const uint8_t* b, size_t n, int kind /*0
     int jt = JOIN_INNER, side = SIDE_LEFT;   // proto3: a zero-valued enum (LEFT_SIDE = 0) is not on the wire
     bool null_aware = false;
     std::string cache_id;
+    std::vector<std::pair<bool, bool>> sort_opts;
     while (r.next(&f, &w)) {
         if (f == 1 && w == 2) schema = schema_field(r);
         else if (f == 2 && w == 2) left = plan_field(t, r);
         else if (f == 3 && w == 2) right = plan_field(t, r);
         else if (f == 4 && w == 2) decode_join_on(r, &lk, &rk);
         else if (kind == 1 && f == 6 && w == 0) jt = (int)r.varint();
+        else if (kind == 1 && f == 5 && w == 2) {   // repeated SortOptions{asc=1, nulls_first=2}: one per join key
+            const uint8_t* ob;
+            size_t on;
+            r.bytes_view(&ob, &on);
+            PbReader o(ob, on);
+            uint32_t of, ow;
+            bool asc = false, nf = false;   // proto3 defaults
+            while (o.next(&of, &ow)) {
+                if (of == 1 && ow == 0) asc = o.varint() != 0;
+                else if (of == 2 && ow == 0) nf = o.varint() != 0;
+                else o.skip(ow);
+            }
+            sort_opts.emplace_back(asc, nf);
+        }
         else if (kind != 1 && f == 5 && w == 0) jt = (int)r.varint();
         else if (kind != 1 && f == 6 && w == 0) side = (int)r.varint();
         else if (kind == 2 && f == 7 && w == 2) cache_id = r.bytes();
@@ -739,11 +754,10 @@ static OperatorPtr decode_join(Task& t, const uint8_t* b, size_t n, int kind /*0
         else r.skip(w);
     }
     AURON_CHECK(left && right, "join without both inputs");
-    if (kind == 1) side = (jt == JOIN_RIGHT) ? SIDE_LEFT : SIDE_RIGHT;   // SMJ: stream the preserved side, keep its order
+    if (kind == 1) return OperatorPtr(new SortMergeJoinExec(std::move(left), std::move(right), lk, rk, sort_opts, jt, schema));
     auto* j = new HashJoinExec(std::move(left), std::move(right), lk, rk, jt, side, schema);
     j->null_aware_anti = null_aware;
     j->cache_id = cache_id;
-    if (kind == 1) j->name = "SortMergeJoinExec";
     return OperatorPtr(j);
 }
 
@@ -913,6 +927,39 @@ static OperatorPtr decode_plan(Task& t, const uint8_t* b, size_t n) {
                 }
                 if (schema.fields.empty() && !inputs.empty()) schema = inputs[0]->out_schema;
                 out.reset(new UnionExec(std::move(inputs), schema));
+                break;
+            }
+            case 20: {   // ExpandExecNode{input=1, schema=2, projections=3{expr=1}} (planner.rs:587-602)
+                OperatorPtr input;
+                Schema schema;
+                std::vector<std::vector<std::vector<uint8_t>>> raw;   // expressions are resolved against the input's schema: decoded after it
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) input = plan_field(t, s);
+                    else if (sf == 2 && sw == 2) schema = schema_field(s);
+                    else if (sf == 3 && sw == 2) {
+                        const uint8_t* pb;
+                        size_t pn;
+                        s.bytes_view(&pb, &pn);
+                        PbReader pr(pb, pn);
+                        uint32_t pf, pw;
+                        raw.emplace_back();
+                        while (pr.next(&pf, &pw)) {
+                            if (pf == 1 && pw == 2) {
+                                const uint8_t* eb;
+                                size_t en;
+                                pr.bytes_view(&eb, &en);
+                                raw.back().emplace_back(eb, eb + en);
+                            } else pr.skip(pw);
+                        }
+                    } else s.skip(sw);
+                }
+                AURON_CHECK(input, "ExpandExecNode without input");
+                std::vector<std::vector<ExprPtr>> projs;
+                for (auto& pr : raw) {
+                    projs.emplace_back();
+                    for (auto& e : pr) projs.back().push_back(decode_expr(e.data(), e.size()));
+                }
+                out.reset(new ExpandExec(std::move(input), schema, std::move(projs)));
                 break;
             }
             case 5: out = make_parquet_scan(t, sb, sn); break;

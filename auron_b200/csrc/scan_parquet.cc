@@ -111,6 +111,7 @@ static void host_decompress(int codec, const uint8_t* in, size_t in_len, uint8_t
 struct PqFileSpec {
     std::string path;
     int64_t size = 0, range_start = -1, range_end = -1;
+    std::vector<Literal> partition_values;   // Hive partition directory values, one per column of the partition schema
 };
 struct LeafColumn {
     int leaf_index;
@@ -129,7 +130,17 @@ struct ParquetScanExec : Operator, FusedScanSource {
     }
     std::vector<PqFileSpec> files;
     Schema table_schema;
+    // FileScanConfig semantics (auron-planner/src/planner.rs:1415-1501): projection indices address [file columns..., partition columns...];
+    // a partition column is the file's directory value repeated for every row of the file
+    Schema part_schema;
     std::vector<int> projection;
+    bool is_part_col(int pj) const { return pj >= (int)table_schema.fields.size(); }
+    const Field& proj_field(int pj) const { return is_part_col(pj) ? part_schema.fields[(size_t)pj - table_schema.fields.size()] : table_schema.fields[(size_t)pj]; }
+    // ParquetScanExecNode.pruning_predicates folded into closed intervals per table column (planner.rs:172-194: row groups whose
+    // statistics cannot satisfy them are skipped; predicates of another shape prune nothing)
+    std::vector<int> prune_cols;
+    std::vector<int64_t> prune_lo, prune_hi;
+    int64_t row_groups_pruned = 0;
     std::string fs_id;
     size_t file_pos = 0;
 
@@ -261,10 +272,42 @@ struct ParquetScanExec : Operator, FusedScanSource {
             if (rg.columns.empty()) continue;
             int64_t start = rg.columns[0].start_offset();
             if (fs->spec.range_start >= 0 && !(start >= fs->spec.range_start && start < fs->spec.range_end)) continue;
+            if (!prune_cols.empty() && row_group_pruned(*fs, rg)) {
+                row_groups_pruned++;
+                continue;
+            }
             fs->row_groups.push_back(g);
         }
         rg_pos = 0;
         cur = fs;
+    }
+    // can no row of this row group satisfy the pruning intervals?  (min / max statistics of INT32 / INT64 chunks; a chunk whose
+    // values are all NULL satisfies no comparison)
+    bool row_group_pruned(const FileState& f, const pq::RowGroup& rg) const {
+        for (size_t i = 0; i < prune_cols.size(); i++) {
+            const int li = find_leaf(f, table_schema.fields[(size_t)prune_cols[i]].name);
+            if (li < 0) continue;
+            const int leaf_index = f.leaves[(size_t)li].leaf_index;
+            if ((size_t)leaf_index >= rg.columns.size()) continue;
+            const pq::ColumnMeta& cm = rg.columns[(size_t)leaf_index];
+            const pq::Statistics& st = cm.stats;
+            if (st.has_null_count && st.null_count == cm.num_values && cm.num_values > 0) return true;
+            const int pt = f.leaves[(size_t)li].el.type;
+            const size_t w = pt == pq::PT_INT32 ? 4 : pt == pq::PT_INT64 ? 8 : 0;
+            if (!w || !st.has_min || !st.has_max || st.min_value.size() != w || st.max_value.size() != w) continue;
+            int64_t mn, mx;
+            if (w == 4) {
+                int32_t a, b;
+                memcpy(&a, st.min_value.data(), 4);
+                memcpy(&b, st.max_value.data(), 4);
+                mn = a, mx = b;
+            } else {
+                memcpy(&mn, st.min_value.data(), 8);
+                memcpy(&mx, st.max_value.data(), 8);
+            }
+            if (mx < prune_lo[i] || mn > prune_hi[i]) return true;
+        }
+        return false;
     }
     static int find_leaf(const FileState& f, const std::string& name) {
         for (size_t i = 0; i < f.leaves.size(); i++)
@@ -282,6 +325,10 @@ struct ParquetScanExec : Operator, FusedScanSource {
     std::string signature(const FileState& f) const {
         std::string s;
         for (int pj : projection) {
+            if (is_part_col(pj)) {
+                s += "P;";
+                continue;
+            }
             int li = find_leaf(f, table_schema.fields[pj].name);
             if (li < 0) s += "-;";
             else s += std::to_string(f.leaves[li].leaf_index) + ":" + std::to_string(f.leaves[li].el.type) + ":" + std::to_string(f.leaves[li].el.repetition) +
@@ -322,8 +369,13 @@ struct ParquetScanExec : Operator, FusedScanSource {
         int64_t dev_off = -1;      // offset in the batch's device buffer (every chunk that is uploaded)
         ChunkPages out;
     };
+    struct FileSeg {
+        size_t file;         // index into files
+        int64_t row0, rows;
+    };
     struct ColState {
         int leaf = -1;   // index into leaves, -1 = missing
+        int part_col = -1;   // >= 0: column of the partition schema (no file column at all)
         pq::SchemaElement el;
         bool is_string = false;
         std::vector<PqPage> pages;
@@ -450,6 +502,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
             pq::PageHeader h = pq::parse_page_header(host + pos, (size_t)(len - pos));
             const uint8_t* payload_h = host + pos + h.header_len;
             const uint8_t* payload_d = dev + pos + h.header_len;
+            AURON_CHECK(h.compressed_size >= 0 && h.uncompressed_size >= 0 && h.num_values >= 0, "corrupt parquet page header (negative size)");
             AURON_CHECK(pos + h.header_len + h.compressed_size <= len, "parquet page overruns its column chunk");
             pos += h.header_len + h.compressed_size;
             if (h.type == pq::PAGE_INDEX) continue;
@@ -594,6 +647,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
             case pq::PT_INT32: case pq::PT_FLOAT: return 4;
             case pq::PT_INT64: case pq::PT_DOUBLE: return 8;
             case pq::PT_FLBA: return type_length;
+            case pq::PT_INT96: return 12;
             default: return 0;
         }
     }
@@ -603,6 +657,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
             case pq::PT_BOOLEAN: ok = t.id == T_BOOL; break;
             case pq::PT_INT32: ok = t.id == T_INT8 || t.id == T_INT16 || t.id == T_INT32 || t.id == T_DATE32 || t.id == T_INT64 || t.id == T_DECIMAL128 || t.id == T_FLOAT64; break;
             case pq::PT_INT64: ok = t.id == T_INT64 || t.id == T_TIMESTAMP || t.id == T_DATE64 || t.id == T_DECIMAL128 || t.id == T_INT32; break;
+            case pq::PT_INT96: ok = t.id == T_TIMESTAMP; break;   // Spark's legacy timestamp encoding (parquet_exec.rs:192 coerces it)
             case pq::PT_FLOAT: ok = t.id == T_FLOAT32 || t.id == T_FLOAT64; break;
             case pq::PT_DOUBLE: ok = t.id == T_FLOAT64; break;
             case pq::PT_BYTE_ARRAY: ok = t.is_varlen(); break;
@@ -642,7 +697,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
             l->kernel_launches = 0;
         }
     }
-    BatchPtr build_batch(Task& t, std::vector<ColState>& cols, int64_t n_rows) {
+    BatchPtr build_batch(Task& t, std::vector<ColState>& cols, int64_t n_rows, const std::vector<FileSeg>& file_segs) {
         AURON_CHECK(n_rows < (int64_t)INT32_MAX, "parquet batch too large");
         auto out = std::make_shared<Batch>();
         out->num_rows = n_rows;
@@ -659,8 +714,32 @@ struct ParquetScanExec : Operator, FusedScanSource {
         std::vector<Pending> pending;
         const bool batch_scout = !use_lanes && !getenv("AURON_SCAN_SCOUT_PER_COLUMN");
         for (size_t ci = 0; ci < projection.size(); ci++) {
-            const Field& fld = table_schema.fields[projection[ci]];
+            const Field& fld = proj_field(projection[ci]);
             ColState& cs = cols[ci];
+            if (cs.part_col >= 0) {   // Hive partition column: the directory value of each file, repeated for its rows
+                std::vector<ColumnPtr> pieces;
+                for (auto& fsg : file_segs) {
+                    const auto& pv = files[fsg.file].partition_values;
+                    AURON_CHECK((size_t)cs.part_col < pv.size(), "PartitionedFile carries fewer partition values than the partition schema has columns");
+                    auto le = std::make_shared<Expr>();
+                    le->kind = E_LITERAL;
+                    le->lit = pv[(size_t)cs.part_col];
+                    ExprPtr e = le;
+                    if (le->lit.type != fld.type) {   // the literal's Arrow type may differ from the declared column type (e.g. int32 vs date32)
+                        auto c = std::make_shared<Expr>();
+                        c->kind = E_TRY_CAST;
+                        c->type = fld.type;
+                        c->children.push_back(le);
+                        e = c;
+                    }
+                    Batch dummy;
+                    dummy.num_rows = fsg.rows;
+                    VmProgram prog = compile_projection({e}, Schema());
+                    pieces.push_back(eval_projection(t.ctx, prog, dummy, nullptr, fsg.rows)[0]);
+                }
+                out->cols.push_back(pieces.size() == 1 ? pieces[0] : concat_columns(t.ctx, pieces));
+                continue;
+            }
             if (cs.leaf < 0) {   // missing column -> NULL (scan/mod.rs:84-100)
                 if (fld.type.is_varlen()) {
                     auto c = make_column(t.ctx, fld.type, n_rows, true);
@@ -704,6 +783,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
             a.phys_width = phys_width(el.type, el.type_length);
             a.out_type = fld.type.id;
             a.out_width = fld.type.width();
+            a.out_unit = fld.type.unit;
             a.max_def = max_def;
             a.out_valid = P<uint32_t>(validity);
             if (is_string) {
@@ -761,6 +841,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
         std::vector<ColState> cols;
         std::vector<ChunkTask> tasks;
         int64_t rows = 0, stage_bytes = 0, dev_bytes = 0;
+        std::vector<FileSeg> file_segs;   // which rows of the batch come from which file (partition column values)
         void* pinned = nullptr;
         size_t pinned_cap = 0;
         void* dev = nullptr;   // from dev_stage_pool()
@@ -826,6 +907,10 @@ struct ParquetScanExec : Operator, FusedScanSource {
                 batch_sig = sig;
                 p.cols.assign(projection.size(), ColState());
                 for (size_t ci = 0; ci < projection.size(); ci++) {
+                    if (is_part_col(projection[ci])) {
+                        p.cols[ci].part_col = projection[ci] - (int)table_schema.fields.size();
+                        continue;
+                    }
                     const Field& fld = table_schema.fields[projection[ci]];
                     int li = find_leaf(*cur, fld.name);
                     p.cols[ci].leaf = li;
@@ -846,6 +931,8 @@ struct ParquetScanExec : Operator, FusedScanSource {
                 ct.row_start = p.rows;
                 p.tasks.push_back(std::move(ct));
             }
+            if (!p.file_segs.empty() && p.file_segs.back().file == file_pos) p.file_segs.back().rows += rg.num_rows;
+            else p.file_segs.push_back(FileSeg{file_pos, p.rows, rg.num_rows});
             p.rows += rg.num_rows;
             rg_pos++;
         }
@@ -994,14 +1081,13 @@ struct ParquetScanExec : Operator, FusedScanSource {
     }
 
     ~ParquetScanExec() override {
-        for (auto& f : inflight)
-            if (f) {   // fused batch still running: its landing buffers go back only once the kernels are done
-                cudaEventSynchronize(f->done);
-                cudaEventDestroy(f->done);
-                if (f->sg.dec0) cudaEventDestroy(f->sg.dec0);
-                release(*f->sg.ready);
-                f.reset();
-            }
+        for (auto& f : inflight) {   // fused batches still running: their landing buffers go back only once the kernels are done
+            cudaEventSynchronize(f->done);
+            cudaEventDestroy(f->done);
+            if (f->sg.dec0) cudaEventDestroy(f->sg.dec0);
+            release(*f->sg.ready);
+        }
+        inflight.clear();
         stop();
         if (copy_stream) {
             cudaStreamSynchronize(copy_stream);
@@ -1059,6 +1145,10 @@ struct ParquetScanExec : Operator, FusedScanSource {
             ready = take_ready(t);
         }
         if (!ready) {
+            if (row_groups_pruned) {
+                metrics.add("row_groups_pruned", row_groups_pruned);
+                row_groups_pruned = 0;
+            }
             if (want_timeline && !timeline.empty()) {
                 for (size_t i = 0; i < timeline.size(); i++)
                     fprintf(stderr, "[scan timeline] batch %zu rows=%lld  copy %.2f..%.2f ms  decode %.2f..%.2f ms\n", i, (long long)timeline[i].rows,
@@ -1274,7 +1364,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
         BatchPtr b;
         {
             OpTimer timer2(metrics, "decode_ns");
-            b = build_batch(t, p.cols, p.rows);   // ends with a stream sync of the task stream, which has joined every lane
+            b = build_batch(t, p.cols, p.rows, p.file_segs);   // ends with a stream sync of the task stream, which has joined every lane
             check_decomp_status(t, sg);
         }
         if (p.copy_begin && p.copied) {
@@ -1312,14 +1402,18 @@ struct ParquetScanExec : Operator, FusedScanSource {
         Staged sg;
         cudaEvent_t done = nullptr;
     };
-    // Two batches are in flight at a time, on alternating lanes (streams): scout / decompress / fused kernel of one batch are
-    // each latency-bound on their own, so the next batch's early stages fill the SMs the current batch leaves idle, and the
-    // host-side preparation of a batch overlaps the kernels of the previous one.
-    std::unique_ptr<Inflight> inflight[2];
+    // Several batches are in flight at a time, on alternating lanes (stream pairs): scout / decompress / fused kernel of one batch
+    // are each latency-bound on their own, so the next batches' early stages fill the SMs the current one leaves idle, and the
+    // host-side preparation of a batch overlaps the kernels of the previous ones.  The host never waits for a batch unless
+    // kMaxInflight of them are queued (their landing buffers are recycled as their completion events fire).
+    static constexpr int kFusedLanes = 3, kMaxInflight = 6;
+    std::deque<std::unique_ptr<Inflight>> inflight;
     int64_t fused_seq = 0;
-    void retire_lane(Task& t, int li) {
-        if (!inflight[li]) return;
-        std::unique_ptr<Inflight> f = std::move(inflight[li]);
+    void retire_one(Task& t, bool wait) {
+        if (inflight.empty()) return;
+        if (!wait && cudaEventQuery(inflight.front()->done) != cudaSuccess) return;
+        std::unique_ptr<Inflight> f = std::move(inflight.front());
+        inflight.pop_front();
         cudaEventSynchronize(f->done);
         cudaEventDestroy(f->done);
         struct R {
@@ -1335,14 +1429,26 @@ struct ParquetScanExec : Operator, FusedScanSource {
         }
     }
     void retire_fused(Task& t) {
-        retire_lane(t, 0);
-        retire_lane(t, 1);
+        while (!inflight.empty()) retire_one(t, true);
         if (!lanes.empty() && !use_lanes) fold_lanes(t);
+    }
+    void restart(Task& t) override {
+        retire_fused(t);
+        stop();
+        cur.reset();
+        file_pos = 0;
+        rg_pos = 0;
+        batches_planned = 0;
+        producer_started = producer_done = stop_producer = false;
+        producer_err.clear();
+        for (auto& kv : metrics.values)
+            if (kv.first == "output_rows" || kv.first == "fused_batches") kv.second = 0;
+        metrics.add("restarted_unfused", 1);
     }
     static bool fused_type_ok(const DType& t) { return t.id == T_INT32 || t.id == T_DATE32 || t.id == T_INT64; }
     bool can_fuse(const FusedAggSpec& spec) const override {
         if (use_lanes || getenv("AURON_DISABLE_FUSED_SCAN_AGG")) return false;
-        auto col_ok = [&](int c) { return c >= 0 && c < (int)projection.size() && fused_type_ok(table_schema.fields[projection[c]].type); };
+        auto col_ok = [&](int c) { return c >= 0 && c < (int)projection.size() && !is_part_col(projection[c]) && fused_type_ok(table_schema.fields[projection[c]].type); };
         if (!col_ok(spec.key_col)) return false;
         for (int c : spec.pred_cols)
             if (!col_ok(c)) return false;
@@ -1352,27 +1458,34 @@ struct ParquetScanExec : Operator, FusedScanSource {
     }
     int next_fused(Task& t, const FusedAggSpec& spec, FusedAggState& st, BatchPtr* fallback) override {
         OpTimer timer(metrics, "elapsed_ns");
-        const int li = (int)(fused_seq & 1);
-        const bool two = !getenv("AURON_FUSED_ONE_LANE");
+        const bool multi = !getenv("AURON_FUSED_ONE_LANE");
+        const int li = multi ? (int)(fused_seq % kFusedLanes) : 0;
         // lane li = a high-priority stream for the batch's preparation (page decompression, scout: one warp per page, a few
         // long serial chains that leave the SMs mostly idle) + a normal-priority stream for its fused kernel.  While the fused
         // kernel of batch k fills the machine, the preparation of batch k+1 gets the SM slots it needs as soon as it asks.
-        if (two && lanes.size() < 4) {
-            lane(t, 0, -1);
-            lane(t, 1, -1);
-            lane(t, 2, 0);
-            lane(t, 3, 0);
+        if (multi && (int)lanes.size() < 2 * kFusedLanes) {
+            for (int i = 0; i < kFusedLanes; i++) lane(t, i, -1);
+            for (int i = 0; i < kFusedLanes; i++) lane(t, kFusedLanes + i, 0);
         }
-        Ctx& wc = two ? lane(t, li) : t.ctx;
-        Ctx& fc = two ? lane(t, 2 + li) : t.ctx;
-        if (two) retire_lane(t, li);   // the batch before last ran on this lane: its buffers go back before the lane is reused
-        Staged sg = stage_next(t, wc);
+        Ctx& wc = multi ? lane(t, li) : t.ctx;
+        Ctx& fc = multi ? lane(t, kFusedLanes + li) : t.ctx;
+        {
+            OpTimer tr(metrics, "fused_retire_ns");
+            while (!inflight.empty() && cudaEventQuery(inflight.front()->done) == cudaSuccess) retire_one(t, false);
+            while ((int)inflight.size() >= (multi ? kMaxInflight : 1)) retire_one(t, true);
+        }
+        Staged sg;
+        {
+            OpTimer ts(metrics, "fused_stage_ns");
+            sg = stage_next(t, wc);
+        }
         if (!sg.ready) {
             retire_fused(t);
             return FUSED_END;
         }
         bool ok = false;
         try {
+            OpTimer tq(metrics, "fused_enqueue_ns");
             ok = run_fused(t, wc, fc, sg, spec, st);
         } catch (...) {
             cudaStreamSynchronize(wc.stream);
@@ -1391,8 +1504,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
         metrics.add("output_rows", sg.ready->rows);
         metrics.add("fused_batches", 1);
         f->sg = std::move(sg);
-        if (!two) retire_lane(t, li);   // single stream: the previous batch is retired once this one is queued behind it
-        inflight[li] = std::move(f);
+        inflight.push_back(std::move(f));
         decomp_results = nullptr;
         decomp_results_buf.reset();
         fused_seq++;
@@ -1416,7 +1528,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
             if (a.col >= 0) phys_of(a.col);
         for (int c : used) {
             const ColState& cs = p.cols[(size_t)c];
-            const DType& ft = table_schema.fields[projection[(size_t)c]].type;
+            const DType& ft = proj_field(projection[(size_t)c]).type;
             if (cs.leaf < 0 || cs.is_string || cs.el.type != pq::PT_INT32 || !fused_type_ok(ft)) return false;
         }
         // key range of this batch from the column-chunk statistics; the table is widened to the union
@@ -1521,12 +1633,13 @@ struct ParquetScanExec : Operator, FusedScanSource {
             return value_role[(size_t)c] = add_role(c, FZ_VALUE);
         };
         // the persistent table
-        // The table belongs to the task stream; the lanes only update it.  Creating / widening it is rare (first batch, or a
-        // batch whose keys leave the range so far): everything in flight on the lanes is drained first, the lanes then wait
-        // for the new table.
+        // The table belongs to the task stream; the lanes only update it.  Creating / widening it is rare (first batch, or a batch
+        // whose keys leave the range so far).  No host-side wait: the task stream first waits for everything queued on the lanes
+        // (kernels that update the old table), creates / rebases the table, and the lanes wait for that before they go on.
         const bool widen = st.table && st.has_range && umin <= umax && (umin < st.kmin || umax > st.kmax);
         if (!st.table || widen || !st.has_range) {
-            for (auto& l : lanes) CUDA_OK(cudaStreamSynchronize(l->stream));
+            if (st.table)   // (a table that does not exist yet has no users to wait for)
+                for (auto& l : lanes) chain(l->stream, t.ctx.stream);
             if (!st.table) {
                 std::vector<AccSpec> specs;
                 for (auto& a : spec.accs) {
@@ -1541,7 +1654,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
             } else {
                 direct_agg_grow(t.ctx, *st.table, umin, umax);
             }
-            CUDA_OK(cudaStreamSynchronize(t.ctx.stream));
+            for (auto& l : lanes) chain(t.ctx.stream, l->stream);
         }
         if (umin <= umax) {
             st.has_range = true;
@@ -1600,12 +1713,13 @@ struct ParquetScanExec : Operator, FusedScanSource {
 OperatorPtr make_parquet_scan(Task& t, const uint8_t* node, size_t n) {
     auto op = std::make_unique<ParquetScanExec>();
     op->name = "ParquetExec";
-    op->host_threads = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    op->host_threads = std::max(1u, std::min(32u, usable_cpus()));
     if (const char* e = getenv("AURON_SCAN_THREADS")) op->host_threads = (unsigned)std::max(1, atoi(e));
     if (const char* e = getenv("AURON_SCAN_PREFETCH_DEPTH")) op->prefetch_depth = atoi(e);
     if (getenv("AURON_SCAN_NO_PREFETCH")) op->prefetch_depth = 0;
     PbReader r(node, n);
     uint32_t f, w;
+    std::vector<std::vector<uint8_t>> prune_exprs;
     while (r.next(&f, &w)) {
         if (f == 1 && w == 2) {   // FileScanExecConf
             const uint8_t* cb;
@@ -1631,6 +1745,23 @@ OperatorPtr make_parquet_scan(Task& t, const uint8_t* node, size_t n) {
                             while (pf.next(&pff, &pfw)) {
                                 if (pff == 1 && pfw == 2) spec.path = pf.bytes();
                                 else if (pff == 2 && pfw == 0) spec.size = (int64_t)pf.varint();
+                                else if (pff == 4 && pfw == 2) {   // repeated ScalarValue partition_values {ipc_bytes = 1}
+                                    const uint8_t* vb;
+                                    size_t vn;
+                                    pf.bytes_view(&vb, &vn);
+                                    PbReader sv(vb, vn);
+                                    uint32_t svf, svw;
+                                    Literal lit;
+                                    while (sv.next(&svf, &svw)) {
+                                        if (svf == 1 && svw == 2) {
+                                            const uint8_t* ib;
+                                            size_t in;
+                                            sv.bytes_view(&ib, &in);
+                                            lit = decode_scalar_ipc(ib, in);
+                                        } else sv.skip(svw);
+                                    }
+                                    spec.partition_values.push_back(lit);
+                                }
                                 else if (pff == 5 && pfw == 2) {
                                     const uint8_t* rb;
                                     size_t rn;
@@ -1665,17 +1796,33 @@ OperatorPtr make_parquet_scan(Task& t, const uint8_t* node, size_t n) {
                     const uint8_t* sb;
                     size_t sn;
                     c.bytes_view(&sb, &sn);
-                    AURON_CHECK(decode_schema(sb, sn).fields.empty(), "hive partition columns are not supported by the device scan yet");
+                    op->part_schema = decode_schema(sb, sn);
                 } else c.skip(cw);
             }
         } else if (f == 3 && w == 2) op->fs_id = r.bytes();
-        else r.skip(w);   // pruning_predicates: row-group pruning is an optimisation, results are identical without it
+        else if (f == 2 && w == 2) {   // repeated PhysicalExprNode pruning_predicates
+            const uint8_t* eb;
+            size_t en;
+            r.bytes_view(&eb, &en);
+            prune_exprs.emplace_back(eb, eb + en);
+        } else r.skip(w);
+    }
+    // row-group pruning is an optimisation: a predicate this engine cannot fold into per-column intervals prunes nothing
+    if (!prune_exprs.empty() && !getenv("AURON_SCAN_NO_PRUNING")) {
+        try {
+            std::vector<ExprPtr> es;
+            for (auto& b : prune_exprs) es.push_back(decode_expr(b.data(), b.size()));
+            VmProgram pp = compile_predicate(es, op->table_schema);
+            if (!predicate_intervals(pp, &op->prune_cols, &op->prune_lo, &op->prune_hi)) op->prune_cols.clear();
+        } catch (const std::exception&) {
+            op->prune_cols.clear();
+        }
     }
     if (op->projection.empty())
-        for (size_t i = 0; i < op->table_schema.fields.size(); i++) op->projection.push_back((int)i);
+        for (size_t i = 0; i < op->table_schema.fields.size() + op->part_schema.fields.size(); i++) op->projection.push_back((int)i);
     for (int p : op->projection) {
-        AURON_CHECK(p >= 0 && p < (int)op->table_schema.fields.size(), "scan projection out of range");
-        op->out_schema.fields.push_back(op->table_schema.fields[p]);
+        AURON_CHECK(p >= 0 && p < (int)(op->table_schema.fields.size() + op->part_schema.fields.size()), "scan projection out of range");
+        op->out_schema.fields.push_back(op->proj_field(p));
     }
     (void)t;
     return op;

@@ -463,7 +463,7 @@ OperatorPtr make_shuffle_writer(Task& t, OperatorPtr input, const uint8_t* node,
         else if (f == 4 && w == 2) op->index_file = r.bytes();
         else r.skip(w);
     }
-    AURON_CHECK(op->num_parts >= 1, "shuffle writer needs at least one output partition");
+    AURON_CHECK(op->num_parts >= 1 && op->num_parts < (1 << 24), "shuffle writer: partition count out of range (1 .. 2^24 - 1)");
     if (op->kind == 1) op->num_parts = 1;   // SingleShuffleRepartitioner (single_repartitioner.rs:64-97)
     if (op->kind == 4 && op->num_parts == 1) op->kind = 1;   // planner.rs:1161-1162
     if (op->kind == 4)

@@ -283,6 +283,12 @@ def union(inputs: list[bytes], s: pa.Schema) -> bytes:
     return f_bytes(9, b"".join(f_bytes(1, f_bytes(1, i) + f_varint(2, 0)) for i in inputs) + f_bytes(2, schema(s)) + f_varint(3, 1))
 
 
+def expand(inp: bytes, s: pa.Schema, projections: list[list[bytes]]) -> bytes:
+    """PhysicalPlanNode{expand{input, schema, projections{expr}}} (auron.proto:745-754)"""
+    body = f_bytes(1, inp) + f_bytes(2, schema(s)) + b"".join(f_bytes(3, b"".join(f_bytes(1, e) for e in pr)) for pr in projections)
+    return f_bytes(20, body)
+
+
 def hash_repartition(exprs: list[bytes], n: int) -> bytes:
     """PhysicalRepartition{hash_repartition}"""
     return f_bytes(2, b"".join(f_bytes(1, e) for e in exprs) + f_varint(2, n))
@@ -309,16 +315,24 @@ def shuffle_writer(inp: bytes, repartition: bytes, data_file: str, index_file: s
 
 
 def parquet_scan(s: pa.Schema, files: list[tuple[str, int]], projection_idx: list[int], fs_resource_id: str = "",
-                 pruning_predicates: list[bytes] | None = None, ranges: list[tuple[int, int]] | None = None) -> bytes:
-    """PhysicalPlanNode{parquet_scan{base_conf{...}, pruning_predicates, fsResourceId}} (NativeParquetScanBase.scala:73-85)"""
+                 pruning_predicates: list[bytes] | None = None, ranges: list[tuple[int, int]] | None = None,
+                 partition_schema: pa.Schema | None = None, partition_values: list[list] | None = None) -> bytes:
+    """PhysicalPlanNode{parquet_scan{base_conf{...}, pruning_predicates, fsResourceId}} (NativeParquetScanBase.scala:73-85).
+    partition_schema / partition_values: Hive partition columns (NativeFileSourceScanBase.scala:105-129): one value per partition
+    column and file; projection indices >= len(s) address them."""
     pfiles = b""
     for i, (path, size) in enumerate(files):
         pf = f_str(1, path) + f_varint(2, size)
+        if partition_schema is not None:
+            for fld, v in zip(partition_schema, partition_values[i]):
+                pf += f_bytes(4, scalar_value(v, fld.type))
         if ranges is not None:
             pf += f_bytes(5, f_varint(1, ranges[i][0]) + f_varint(2, ranges[i][1]))
         pfiles += f_bytes(1, pf)
     conf = f_varint(1, 1) + f_varint(2, 0) + f_bytes(3, pfiles) + f_bytes(4, schema(s))
     conf += b"".join(f_varint(6, p, always=True) for p in projection_idx)   # repeated
+    if partition_schema is not None:
+        conf += f_bytes(9, schema(partition_schema))
     body = f_bytes(1, conf) + b"".join(f_bytes(2, p) for p in (pruning_predicates or [])) + f_str(3, fs_resource_id)
     return f_bytes(5, body)
 

@@ -156,14 +156,16 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (config 2)
-def _cpu_one_file(path: str):
+def _cpu_one_split(split):
     """One Spark task's worth of the reference pipeline on ONE core: Arrow C++ Parquet reader + filter (stand-in for the parquet
     crate / arrow-rs kernels the reference delegates to) feeding the oracle's C hash aggregate (port of agg_hash_map.rs / sum.rs /
-    count.rs).  Auron runs one such task per core; so does this arm."""
+    count.rs).  A split is one row group of one file (Spark cuts input splits at row-group boundaries: 128 MB); Auron runs one
+    such task per core, so does this arm."""
     import oracle
+    path, rg = split
     pa.set_cpu_count(1)
     pa.set_io_thread_count(1)
-    t = pq.read_table(path, columns=["ss_item_sk", "ss_quantity", "ss_sold_date_sk"], use_threads=False)
+    t = pq.ParquetFile(path).read_row_group(rg, columns=["ss_item_sk", "ss_quantity", "ss_sold_date_sk"], use_threads=False)
     d = t["ss_sold_date_sk"]
     mask = pc.and_kleene(pc.greater_equal(d, FILTER_LO), pc.less(d, FILTER_HI))
     ft = t.filter(mask)
@@ -176,41 +178,21 @@ def _cpu_warm(_):
     return 0
 
 
-def _cpu_split_files(files: list[str], directory: str, pieces: int) -> list[str]:
-    """The reference parallelises over input splits (one per task); 18 files cannot occupy 128 cores, so every file is re-cut into
-    `pieces` files (same rows, same encoding parameters) -- done once, cached next to the dataset."""
-    out = []
-    todo = []
-    for f in files:
-        base = os.path.basename(f)[:-8]
-        parts = [os.path.join(directory, f"{base}_split{pieces}_{i:02d}.parquet") for i in range(pieces)]
-        if not all(os.path.exists(p) for p in parts):
-            todo.append((f, parts))
-        out += parts
-
-    def cut(job):
-        f, parts = job
-        t = pq.read_table(f)
-        n = t.num_rows
-        for i, p in enumerate(parts):
-            lo, hi = n * i // len(parts), n * (i + 1) // len(parts)
-            pq.write_table(t.slice(lo, hi - lo), p + ".tmp", compression=CODEC, use_dictionary=True, row_group_size=8_000_000, data_page_size=1 << 20)
-            os.replace(p + ".tmp", p)
-
-    if todo:
-        with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
-            list(ex.map(cut, todo))
-    return out
-
-
 class CpuArm:
-    """All host cores, one split per worker at a time, partial aggregates merged at the end (the final merge a Spark stage does)."""
+    """All host cores, one split (row group) per worker at a time, partial aggregates merged at the end (the final merge a Spark stage
+    does).  The table has fewer splits (36) than a big host has cores, so one step runs `passes` passes over the table concurrently --
+    every core holds a task, rows/s counts every row processed."""
 
-    def __init__(self, files: list[str], directory: str, cores: int):
+    def __init__(self, files: list[str], cores: int):
         self.cores = cores
-        pieces = min(8, max(1, -(-cores // len(files))))          # >= one split per core (up to 8 per file)
-        self.splits = _cpu_split_files(files, directory, pieces) if pieces > 1 else list(files)
-        self.pool = ProcessPoolExecutor(max_workers=cores)
+        splits = []
+        for f in files:
+            splits += [(f, g) for g in range(pq.ParquetFile(f).metadata.num_row_groups)]
+        self.passes = max(1, -(-cores // len(splits)))
+        self.splits = splits * self.passes
+        import multiprocessing
+        # spawn, not fork: the GPU arm calls this from a process that holds a CUDA context and worker threads
+        self.pool = ProcessPoolExecutor(max_workers=cores, mp_context=multiprocessing.get_context("spawn"))
         list(self.pool.map(_cpu_warm, range(cores)))
 
     def run(self) -> tuple[int, float]:
@@ -218,12 +200,16 @@ class CpuArm:
         rows = 0
         sums = np.zeros(N_ITEMS + 2, dtype=np.int64)
         cnts = np.zeros(N_ITEMS + 2, dtype=np.int64)
-        for n, k, s, c in self.pool.map(_cpu_one_file, self.splits):
+        for n, k, s, c in self.pool.map(_cpu_one_split, self.splits):
             rows += n
             kk = np.nan_to_num(k.astype(np.float64), nan=N_ITEMS + 1).astype(np.int64)
             np.add.at(sums, kk, np.nan_to_num(s.astype(np.float64)).astype(np.int64))
             np.add.at(cnts, kk, c.astype(np.int64))
         return rows, time.perf_counter() - t0
+
+    def describe(self, nfiles: int) -> str:
+        return (f"{self.passes} concurrent pass(es) over all {nfiles} files = {len(self.splits)} row-group splits per step, one single-threaded worker "
+                "process per core: Arrow C++ scan+filter, oracle C hash aggregate, partials merged")
 
     def close(self):
         self.pool.shutdown()
@@ -247,6 +233,10 @@ def decimal_words(unscaled: np.ndarray) -> np.ndarray:
     out[0::2] = unscaled.view(np.uint64)
     out[1::2] = np.where(unscaled < 0, np.uint64(0xFFFFFFFFFFFFFFFF), np.uint64(0))
     return out
+
+
+def do_workload(args, w: str) -> bool:
+    return args.workload in ("all", w)
 
 
 def main():
@@ -280,12 +270,12 @@ def main():
             return
         files = gen_dataset(args.data_dir, args.rows)
         paths = [f for f, _ in files]
-        arm = CpuArm(paths, args.data_dir, cores)
+        arm = CpuArm(paths, cores)
         warm = min(args.warmup, 1)
         for _ in range(warm):
             arm.run()
         rows, secs = 0, 0.0
-        steps = max(1, min(args.steps, 3))               # every step is the WHOLE table (all files): bounded to a few of them
+        steps = max(1, min(args.steps, 3))               # every step is the WHOLE table (all files) at least once: bounded to a few of them
         for _ in range(steps):
             r, s = arm.run()
             rows += r
@@ -296,10 +286,18 @@ def main():
                           "warmup": warm, "ms_per_step": 1000 * secs / steps, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "int64", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": v, "unit": "rows/s", "cores": cores, "kind": "port",
-                                           "sample": f"all {len(files)} files ({args.rows} rows) per step, re-cut into {len(arm.splits)} splits; one single-threaded "
-                                                     "worker process per core (Arrow C++ scan+filter, oracle C hash aggregate), partials merged"},
+                                           "sample": arm.describe(len(files))},
                           "e2e": {"value": v, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
+
+    cpu_line = None
+    if world == 1 and rank == 0 and do_workload(args, "scan_agg") and not os.environ.get("AURON_BENCH_NO_CPU"):
+        # the CPU baseline of the headline runs first, before this process owns a CUDA context (worker processes, all cores)
+        files0 = gen_dataset(args.data_dir, args.rows)
+        arm = CpuArm([f for f, _ in files0], cores)
+        r, s = arm.run()
+        arm.close()
+        cpu_line = {"value": r / s, "unit": "rows/s", "cores": cores, "kind": "port", "sample": arm.describe(len(files0))}
 
     import torch
     import torch.distributed as dist
@@ -308,6 +306,12 @@ def main():
     torch.cuda.set_device(local_rank)
     numa = bind_to_gpu_numa_node(torch, local_rank)    # before any pinned allocation / worker thread exists
     config["numa_node"] = numa
+    # host worker threads of this rank: its share of the CPUs it is bound to (ranks on the same NUMA node share them)
+    bound = len(os.sched_getaffinity(0))
+    nodes = max(1, len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")])) if os.path.isdir("/sys/devices/system/node") else 1
+    ranks_per_node = max(1, -(-world // nodes))
+    os.environ.setdefault("AURON_SCAN_THREADS", str(max(4, min(32, bound // ranks_per_node))))
+    config["host_threads_per_rank"] = int(os.environ["AURON_SCAN_THREADS"])
     from auron_b200 import proto as P
     from auron_b200 import runtime
 
@@ -381,7 +385,7 @@ def main():
                         "can exceed the step time"}
 
     ctx = dict(args=args, torch=torch, dist=dist, P=P, runtime=runtime, timed=timed, roofline_of=roofline_of, world=world, rank=rank, local_rank=local_rank, cores=cores)
-    do = (lambda w: args.workload in ("all", w))
+    do = (lambda w: do_workload(args, w))
     line = None
 
     # ================================================================================================ config 2: scan -> filter -> aggregate
@@ -458,14 +462,7 @@ def main():
                 "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e,
                 "gpu_launches": int(kern.get("total_launches", 0)), "roofline": roofline, "cpu_baseline": None,
                 "result_groups": out.num_rows, "selected_rows_est": sel_rows}
-        if world == 1 and rank == 0:
-            arm = CpuArm(paths, args.data_dir, cores)
-            arm.run()
-            r, s = arm.run()
-            arm.close()
-            line["cpu_baseline"] = {"value": r / s, "unit": "rows/s", "cores": cores, "kind": "port",
-                                    "sample": f"all {len(paths)} files ({r} rows), re-cut into {len(arm.splits)} splits, one single-threaded worker process per core: "
-                                              "Arrow C++ scan+filter, oracle C hash aggregate, partials merged"}
+        line["cpu_baseline"] = cpu_line
 
     # ================================================================================================ config 3 / 4 sub-results
     workloads = {}

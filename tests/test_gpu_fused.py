@@ -223,3 +223,64 @@ def test_fused_falls_back_when_it_must(tmp_path):
                    "date": pa.array(rng.integers(2450816, 2452642, n, dtype=np.int32))})
     p2 = _write(str(tmp_path / "b.parquet"), t2)
     _check([p2], t2, "item", DATE_PREDS, SUM_COUNT, expect_fused=False)
+
+
+def test_fused_survives_wrong_key_statistics(tmp_path):
+    # chunk statistics that do not cover the data (buggy writer): the fused pass notices the out-of-range key, its result is
+    # discarded and the input is read again operator by operator -- same answer
+    rng = np.random.default_rng(8)
+    n = 80_000
+    k = rng.integers(1000, 2000, n).astype(np.int32)
+    k[:10] = [1000, 1999] * 5
+    t = pa.table({"item": pa.array(k), "qty": pa.array(rng.integers(1, 101, n, dtype=np.int32)), "date": pa.array(rng.integers(2450816, 2452642, n, dtype=np.int32))})
+    path = str(tmp_path / "stats.parquet")
+    pq.write_table(t, path, compression="NONE", use_dictionary=False)
+    raw = bytearray(open(path, "rb").read())
+    footer_len = int.from_bytes(raw[-8:-4], "little")
+    foot = len(raw) - 8 - footer_len
+    patched = raw[:foot] + raw[foot:].replace((1999).to_bytes(4, "little"), (1500).to_bytes(4, "little"))
+    assert patched != raw and len(patched) == len(raw)
+    open(path, "wb").write(bytes(patched))
+    assert pq.ParquetFile(path).metadata.row_group(0).column(0).statistics.max == 1500
+    td = _plan([path], t.schema, "item", DATE_PREDS, SUM_COUNT)
+    got, met = _run(td, fused=True)
+    assert met.get(("ParquetExec", "restarted_unfused")) == 1
+    assert _rows(got) == _expected(t, "item", DATE_PREDS, SUM_COUNT)
+
+
+def test_scan_partition_columns_and_row_group_pruning(tmp_path):
+    # Hive partition columns (FileScanConfig: projection indices past the file schema) + pruning_predicates
+    rng = np.random.default_rng(9)
+    paths, parts, pvals = [], [], []
+    for i, (day, lo) in enumerate([(2451000, 0), (2451001, 100_000), (2451002, 200_000)]):
+        n = 50_000
+        t = pa.table({"item": pa.array(np.sort(rng.integers(lo, lo + 100_000, n, dtype=np.int32))), "qty": pa.array(rng.integers(1, 101, n, dtype=np.int32))})
+        p = str(tmp_path / f"p{i}.parquet")
+        pq.write_table(t, p, row_group_size=10_000)
+        paths.append(p)
+        pvals.append([day, f"store{i}"])
+        parts.append(t.append_column("day", pa.array([day] * n, type=pa.int32())).append_column("store", pa.array([f"store{i}"] * n)))
+    full = pa.concat_tables(parts)
+    file_schema = pa.schema([("item", pa.int32()), ("qty", pa.int32())])
+    part_schema = pa.schema([("day", pa.int32()), ("store", pa.string())])
+    files = [(p, os.path.getsize(p)) for p in paths]
+    # every column, partition columns included (indices 2, 3), in a shuffled order
+    scan = P.parquet_scan(file_schema, files, [3, 0, 2, 1], partition_schema=part_schema, partition_values=pvals)
+    with runtime.Task(P.task_definition(scan)) as task:
+        out = pa.Table.from_batches(list(task), schema=task.schema)
+    assert out.column_names == ["store", "item", "day", "qty"]
+    assert out.select(["item", "qty", "day", "store"]).equals(full.cast(out.select(["item", "qty", "day", "store"]).schema))
+    # filter on a partition column + aggregate; row groups that cannot match `item` are pruned by their statistics
+    prune = [P.binary("GtEq", P.col("item"), P.lit(150_000, pa.int32())), P.binary("Lt", P.col("item"), P.lit(160_000, pa.int32()))]
+    scan = P.parquet_scan(file_schema, files, [0, 1, 2], pruning_predicates=prune, partition_schema=part_schema, partition_values=pvals)
+    flt = P.filter_(scan, prune + [P.binary("Eq", P.col("day"), P.lit(2451001, pa.int32()))])
+    plan = P.agg(flt, [P.col("day")], ["day"], [P.agg_expr("SUM", [P.col("qty")], pa.int64()), P.agg_expr("COUNT", [P.col("item")], pa.int64())], ["s", "c"], ["PARTIAL"] * 2)
+    with runtime.Task(P.task_definition(plan)) as task:
+        got = pa.Table.from_batches(list(task), schema=task.schema)
+        met = {(op, name): v for _, op, name, v in task.metrics()}
+    item, qty = full["item"].to_numpy(), full["qty"].to_numpy()
+    keep = (item >= 150_000) & (item < 160_000) & (full["day"].to_numpy() == 2451001)
+    assert got.to_pydict() == {"day": [2451001], "": [int(qty[keep].sum())], "_": [int(keep.sum())]} or \
+        (got.column(0).to_pylist(), got.column(1).to_pylist(), got.column(2).to_pylist()) == ([2451001], [int(qty[keep].sum())], [int(keep.sum())])
+    assert met.get(("ParquetExec", "row_groups_pruned"), 0) >= 12, met      # 15 row groups, at most 2-3 can hold items in [150000, 160000)
+    assert met[("ParquetExec", "output_rows")] <= 30_000

@@ -715,7 +715,9 @@ def _join(left, right, on, jt, impl, chunk=None):
         fields = [pa.field(f"l_{f.name}", f.type) for f in left.schema] + [pa.field(f"r_{f.name}", f.type) for f in right.schema]
     s = pa.schema(fields)
     onp = [(P.col(l), P.col(r)) for l, r in on]
-    if impl == "smj":
+    if impl == "smj":   # Spark plans a SortExec on the join keys (ascending, nulls first) under each side of a SortMergeJoin
+        lsrc = P.sort(lsrc, [P.sort_expr(P.col(l), True, True) for l, _ in on])
+        rsrc = P.sort(rsrc, [P.sort_expr(P.col(r), True, True) for _, r in on])
         plan = P.sort_merge_join(s, lsrc, rsrc, onp, jt)
     elif impl.startswith("bhj"):
         plan = P.broadcast_join(s, lsrc, rsrc, onp, jt, "LEFT" if impl.endswith("L") else "RIGHT")
@@ -837,6 +839,46 @@ def test_join_fuzz_vs_arrow(jt):
         assert_same_rows(got, e)
 
 
+@pytest.mark.parametrize("jt", ["INNER", "LEFT", "RIGHT", "FULL", "SEMI", "ANTI", "EXISTENCE"])
+def test_sort_merge_join_streams_sorted_inputs_in_pieces(jt, monkeypatch):
+    monkeypatch.setenv("AURON_GPU_CHUNK_ROWS", "2500")     # the FFI reader coalesces exported batches up to this many rows
+    # sort_merge_join_exec.rs:294-372: both sides arrive SORTED and in many batches; key groups straddle batch boundaries on both
+    # sides, NULL keys lead both streams.  The operator cuts the streams into key-disjoint pieces (metric `pieces`), never holds
+    # more than a piece, and its output keeps the order of the driving side (left; right for RIGHT OUTER).
+    rng = np.random.default_rng(31)
+    nl, nr = 30_000, 12_000
+    lk = np.sort(rng.integers(0, 4000, nl)).astype(np.int32)
+    rk = np.sort(rng.integers(500, 4500, nr)).astype(np.int32)
+    lnull, rnull = np.arange(nl) < 700, np.arange(nr) < 300            # nulls first
+    left = pa.table({"k": pa.array(lk, mask=lnull), "d": pa.array((lk % 3).astype(np.int64)), "lv": pa.array(np.arange(nl), type=pa.int64())})
+    right = pa.table({"k": pa.array(rk, mask=rnull), "rv": pa.array(np.arange(nr), type=pa.int64())})
+    fields = [pa.field(f"l_{f.name}", f.type) for f in left.schema]
+    if jt == "EXISTENCE":
+        fields.append(pa.field("exists", pa.bool_()))
+    elif jt not in ("SEMI", "ANTI"):
+        fields += [pa.field(f"r_{f.name}", f.type) for f in right.schema]
+    plan = P.sort_merge_join(pa.schema(fields), P.ffi_reader(left.schema, "l"), P.ffi_reader(right.schema, "r"), [(P.col("k"), P.col("k"))], jt)
+    td = P.task_definition(plan)
+    with runtime.Task(td, {"l": batches(left, 1_000), "r": batches(right, 700)}) as task:
+        got = pa.Table.from_batches(list(task), schema=task.schema)
+        met = {(op, name): v for _, op, name, v in task.metrics()}
+    assert met[("SortMergeJoinExec", "pieces")] >= 4, met
+    how = {"INNER": "inner", "LEFT": "left outer", "RIGHT": "right outer", "FULL": "full outer", "SEMI": "left semi", "ANTI": "left anti", "EXISTENCE": "left outer"}[jt]
+    exp = left.join(right, keys="k", join_type=how, coalesce_keys=False, right_suffix="_r")
+    if jt in ("SEMI", "ANTI"):
+        assert_same_rows(got, exp.select(["k", "d", "lv"]))
+    elif jt == "EXISTENCE":
+        matched = set(exp.filter(pc.is_valid(exp["rv"]))["lv"].to_pylist())
+        assert sorted(zip(got["l_lv"].to_pylist(), got["exists"].to_pylist())) == [(i, i in matched) for i in range(nl)]
+    else:
+        assert_same_rows(got, exp.select(["k", "d", "lv", "k_r", "rv"]))
+    # output order = order of the driving side's key (NULL keys first), as Spark's SortMergeJoinExec.outputOrdering promises
+    if jt in ("INNER", "LEFT", "SEMI", "ANTI", "EXISTENCE", "RIGHT"):
+        col = got.column(3 if jt == "RIGHT" else 0).to_pylist()
+        keyed = [(-1 if v is None else v) for v in col]
+        assert keyed == sorted(keyed)
+
+
 def test_join_string_and_multi_key_general_path():
     rng = np.random.default_rng(23)
     n = 20_000
@@ -886,6 +928,56 @@ def test_sort_fuzz_vs_arrow(n):
         # ties are unordered in the reference (sort_exec.rs:648-662): compare the key sequence, then the multiset of rows
         assert got.select(key_names).to_pylist() == exp.select(key_names).to_pylist(), keys
         assert sorted(got["row"].to_pylist()) == list(range(n))
+
+
+@pytest.mark.parametrize("spill", [False, True])
+def test_external_sort_runs_spill_and_range_merge(monkeypatch, spill):
+    # ExternalSorter (sort_exec.rs:390-447,637-768,913-1061): the input is sorted in runs, runs beyond the memory budget are spilled
+    # (pinned host memory here), the output merges them.  Runs of 7,000 rows over 100,000 input rows (15 runs, ~30 key ranges), with
+    # a budget that spills every run in the second variant; the fuzz oracle of sort_exec.rs:1617-1697: equality with an independent sorter.
+    monkeypatch.setenv("AURON_SORT_RUN_ROWS", "7000")
+    if spill:
+        monkeypatch.setenv("AURON_SORT_SPILL_BYTES", "1")
+    n = 100_000
+    rng = np.random.default_rng(11)
+    t = pa.table({"u": pa.array(rng.integers(0, 300, n), type=pa.int32(), mask=rng.random(n) < 0.05),
+                  "f": pa.array(rng.standard_normal(n), mask=rng.random(n) < 0.05),
+                  "d": pa.array(rng.integers(-2**40, 2**40, n), type=pa.int64()).cast(pa.decimal128(20, 0)),
+                  "s": pa.array([f"payload-{int(i)}" for i in rng.integers(0, 1000, n)], mask=rng.random(n) < 0.1),
+                  "row": pa.array(np.arange(n), type=pa.int64())})
+    cases = [([("u", True, True), ("f", False, False)], [("u", "ascending"), ("f", "descending")], None),
+             ([("d", False, True)], [("d", "descending")], "at_start"),
+             ([("f", True, True), ("row", True, True)], [("f", "ascending"), ("row", "ascending")], "at_start")]
+    for keys, akeys, placement in cases:
+        td = P.task_definition(P.sort(P.ffi_reader(t.schema, "t"), [P.sort_expr(P.col(k), asc, nf) for k, asc, nf in keys]))
+        with runtime.Task(td, {"t": batches(t, 9_000)}) as task:
+            got = pa.Table.from_batches(list(task), schema=task.schema)
+            met = {(op, name): v for _, op, name, v in task.metrics()}
+        assert met[("SortExec", "sorted_runs")] >= 14 and met[("SortExec", "merge_ranges")] >= 10, met
+        assert (met.get(("SortExec", "mem_spill_count"), 0) > 0) == spill
+        key_names = [k for k, _, _ in keys]
+        if placement is None:   # mixed null placement: build the expected order key by key
+            tt = t.to_pandas()
+            exp = t.take(pa.array(tt.sort_values(by=["u", "f"], ascending=[True, False], na_position="first", kind="stable").index.to_numpy()))
+            u_first = exp["u"].to_pylist()
+            assert got["u"].to_pylist() == u_first     # u ascending, NULLs first
+            # f descending with NULLs last inside every u group
+            gu, gf = got["u"].to_pylist(), got["f"].to_pylist()
+            for i in range(1, n):
+                if gu[i] == gu[i - 1]:
+                    a, b = gf[i - 1], gf[i]
+                    assert (b is None) or (a is not None and a >= b), (i, a, b)
+        else:
+            exp = t.take(pc.sort_indices(t, sort_keys=akeys, null_placement=placement))
+            assert got.select(key_names).to_pylist() == exp.select(key_names).to_pylist(), keys
+        assert sorted(got["row"].to_pylist()) == list(range(n))
+        rows = dict(zip(got["row"].to_pylist(), got["s"].to_pylist()))
+        assert all(rows[i] == v for i, v in enumerate(t["s"].to_pylist()))     # payload travelled with its row
+    # limit / offset across runs
+    td = P.task_definition(P.sort(P.ffi_reader(t.schema, "t"), [P.sort_expr(P.col("row"), False, True)], limit=20_000, offset=19_990))
+    with runtime.Task(td, {"t": batches(t, 9_000)}) as task:
+        got = pa.Table.from_batches(list(task), schema=task.schema)
+    assert got["row"].to_pylist() == list(range(n - 1 - 19_990, n - 1 - 20_000, -1))
 
 
 # =============================================================================== misc operators

@@ -251,3 +251,26 @@ def test_aggregate_survives_wrong_column_statistics(tmp_path, lie):
     exp = oracle.agg_sum_count_i64(t["k"].combine_chunks().cast(pa.int64()), t["v"].combine_chunks())
     got = pa.table({"k": got.column(0).cast(pa.int64()), "s": got.column(1), "c": got.column(2)})
     assert_same_rows(got, exp)
+
+
+@pytest.mark.parametrize("dict_", [True, False])
+def test_scan_int96_timestamps(tmp_path, dict_):
+    # Spark's default timestamp encoding in Parquet is INT96 (nanoseconds of the day + Julian day); the scan converts it to the
+    # unit of the table schema's timestamp column (parquet_exec.rs:192 coerce_int96 + AuronSchemaAdapter)
+    rng = np.random.default_rng(12)
+    n = 30_000
+    us = rng.integers(-2_000_000_000_000_000, 4_000_000_000_000_000, n)          # 1906 .. 2096, microseconds
+    if dict_:
+        us = us[rng.integers(0, 500, n)]                                        # few distinct values -> dictionary pages
+    t = pa.table({"ts": pa.array(us, type=pa.timestamp("us"), mask=rng.random(n) < 0.05), "k": pa.array(np.arange(n), type=pa.int32())})
+    path = str(tmp_path / "int96.parquet")
+    pq.write_table(t, path, use_deprecated_int96_timestamps=True, use_dictionary=dict_, compression="SNAPPY", data_page_size=20_000)
+    assert pq.ParquetFile(path).schema.column(0).physical_type == "INT96"
+    for unit in ("us", "ms"):
+        schema = pa.schema([("ts", pa.timestamp(unit)), ("k", pa.int32())])
+        got = _scan(path, schema)
+        exp = us // (1 if unit == "us" else 1000)
+        g = got["ts"].cast(pa.int64()).to_pylist()
+        e = t["ts"].to_pylist()
+        assert [None if v is None else int(x) for v, x in zip(e, exp)] == g
+        assert got["k"].to_pylist() == list(range(n))

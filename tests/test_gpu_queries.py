@@ -169,3 +169,32 @@ def test_string_predicates_decimal_average_and_string_sort(tmp_path):
     exp.sort(key=lambda r: (r[0] is not None, r[0] or ""))          # i_category ASC NULLS FIRST (stable)
     assert len(exp) > 10
     assert _rows(got, ["i_category", "b", "c", "a", "d", "mb"]) == exp
+
+
+def test_expand_rollup_aggregate():
+    # GROUP BY ROLLUP(a, b): Spark plans Expand[(a, b, 0), (a, NULL, 1), (NULL, NULL, 3)] -> partial aggregate on (a, b, gid).
+    # expand_exec.rs:127-185: every input batch once per projection, expressions cast to the declared output types.
+    rng = np.random.default_rng(5)
+    n = 20_000
+    t = pa.table({"a": pa.array(rng.integers(0, 5, n), type=pa.int32(), mask=rng.random(n) < 0.02),
+                  "b": pa.array([f"s{int(x)}" for x in rng.integers(0, 7, n)], mask=rng.random(n) < 0.02),
+                  "v": pa.array(rng.integers(-100, 100, n), type=pa.int64(), mask=rng.random(n) < 0.05)})
+    out_schema = pa.schema([("v", pa.int64()), ("a", pa.int32()), ("b", pa.string()), ("gid", pa.int64())])
+    src = P.ffi_reader(t.schema, "t")
+    projs = [[P.col("v"), P.col("a"), P.col("b"), P.lit(0, pa.int32())],                       # gid literal is int32: cast to the declared int64
+             [P.col("v"), P.col("a"), P.lit(None, pa.string()), P.lit(1, pa.int64())],
+             [P.col("v"), P.lit(None, pa.int32()), P.lit(None, pa.string()), P.lit(3, pa.int64())]]
+    ex = P.expand(src, out_schema, projs)
+    plan = P.agg(ex, [P.col("a"), P.col("b"), P.col("gid")], ["a", "b", "gid"],
+                 [P.agg_expr("SUM", [P.col("v")], pa.int64()), P.agg_expr("COUNT", [P.col("v")], pa.int64())], ["s", "c"], ["PARTIAL"] * 2)
+    got = run(plan, {"t": t}, chunk=7_000)
+    exp = {}
+    for a, b, v in zip(t["a"].to_pylist(), t["b"].to_pylist(), t["v"].to_pylist()):
+        for key in ((a, b, 0), (a, None, 1), (None, None, 3)):
+            e = exp.setdefault(key, [None, 0])
+            if v is not None:
+                e[0] = v if e[0] is None else e[0] + v
+                e[1] += 1
+    rows = {(a, b, g): [s, c] for a, b, g, s, c in zip(*[got.column(i).to_pylist() for i in range(5)])}
+    assert rows == exp
+    assert got.schema.field(2).type == pa.int64()

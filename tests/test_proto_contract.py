@@ -341,3 +341,25 @@ def test_count_without_arguments_is_count_star():
     Lb.auron_b200_explain.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int64]
     bad = P.task_definition(P.agg(P.ffi_reader(T, "in"), [P.col("a")], ["a"], [P.agg_expr("MAX", [], L)], ["m"], ["PARTIAL"]))
     assert Lb.auron_b200_explain(bad, len(bad), None, 0) == -1                # MAX() of nothing is an error, not a crash
+
+
+def test_expand_and_partitioned_scan_decode_on_the_cpu():
+    # ExpandExecNode (auron.proto:745-754) and the Hive-partition fields of FileScanExecConf / PartitionedFile decode into the operators
+    # the reference builds (planner.rs:587-602, 1415-1501); walk() checks the bytes against the reference schema first
+    src = P.ffi_reader(T, "in")
+    out = pa.schema([("a", pa.int64()), ("g", pa.int64())])
+    ex = P.expand(src, out, [[P.col("a"), P.lit(0, pa.int64())], [P.lit(None, pa.int64()), P.lit(1, pa.int64())]])
+    seen = set()
+    walk("PhysicalPlanNode", ex, seen)
+    assert ("ExpandExecNode", "projections") in seen and ("ExpandProjection", "expr") in seen
+    d = _explain(ex)["plan"]
+    assert d["op"] == "ExpandExec" and [f[0] for f in d["schema"]] == ["a", "g"] and len(d["projections"]) == 2
+    assert [c["op"] for c in d["children"]] == ["FFIReaderExec"]
+    file_schema = pa.schema([("x", pa.int32()), ("y", pa.string())])
+    part_schema = pa.schema([("day", pa.int32()), ("region", pa.string())])
+    scan = P.parquet_scan(file_schema, [("/data/day=7/region=eu/f.parquet", 123)], [1, 2, 3, 0], partition_schema=part_schema, partition_values=[[7, "eu"]],
+                          pruning_predicates=[P.binary("Gt", P.col("x"), P.lit(5, pa.int32()))])
+    walk("PhysicalPlanNode", scan, seen)
+    assert {("FileScanExecConf", "partition_schema"), ("PartitionedFile", "partition_values"), ("ParquetScanExecNode", "pruning_predicates")} <= seen
+    d = _explain(scan)["plan"]
+    assert d["op"] == "ParquetExec" and [f[0] for f in d["schema"]] == ["y", "day", "region", "x"]      # projection order over [file columns..., partition columns...]
