@@ -118,6 +118,7 @@ ColumnPtr host_array_to_device(Ctx& ctx, const HostArray& a);
 OperatorPtr make_parquet_scan(Task& t, const uint8_t* node, size_t n);
 OperatorPtr make_shuffle_writer(Task& t, OperatorPtr input, const uint8_t* node, size_t n);
 OperatorPtr make_ipc_reader(Task& t, const Schema& schema, const std::string& resource_id);
+OperatorPtr make_ipc_writer(Task& t, OperatorPtr input, const std::string& consumer_resource_id);
 
 // expression decode (shared by planner + scan pruning)
 ExprPtr decode_expr(const uint8_t* b, size_t n);

@@ -218,6 +218,7 @@ struct JniTask {
     std::map<std::string, jobject> inputs;          // path -> FSDataInputWrapper
     std::map<std::string, jobject> block_iters;     // resource id -> scala.collection.Iterator[BlockObject]
     jobject cur_block = nullptr, cur_buffer = nullptr;
+    jobject last_block = nullptr;      // the block handed out last, kept after its close() for throwFetchFailed
     std::string cur_path;
     std::vector<uint8_t> cur_bytes;
     jthrowable failure = nullptr;      // first Java exception raised inside an upcall (any thread)
@@ -340,6 +341,40 @@ int64_t cb_read_fully(void* user, const char* fs_resource_id, const char* path, 
     });
 }
 
+// IpcWriterExec's consumer: JniBridge.getResource(id) is a Scala `ByteBuffer => Unit` (ipc_writer_exec.rs:112-118,143-152); every
+// delivery wraps the native bytes in a direct ByteBuffer for the duration of the call
+int cb_write_ipc(void* user, const char* resource_id, const uint8_t* data, int64_t len) {
+    auto* jt = (JniTask*)user;
+    return (int)upcall(jt, [&](const J& j) -> int64_t {
+        jobject consumer;
+        {
+            std::lock_guard<std::mutex> g(jt->mu);
+            auto it = jt->exporters.find(resource_id);
+            if (it == jt->exporters.end()) it = jt->exporters.emplace(resource_id, j.global(get_resource(j, jt, resource_id))).first;
+            consumer = it->second;
+        }
+        if (!consumer) return -1;
+        jvalue a;
+        a.l = j.direct_buffer(const_cast<uint8_t*>(data), len);
+        j.call_object(consumer, "apply", "(Ljava/lang/Object;)Ljava/lang/Object;", &a);
+        return 0;
+    });
+}
+
+// AuronBlockObject.throwFetchFailed(errmsg) on the block handed out last (ipc_reader_exec.rs:211-219; the Java side raises Spark's
+// FetchFailedException from it, which stays pending and is rethrown when nextBatch returns)
+void cb_fetch_failed(void* user, const char* /*resource_id*/, const char* message) {
+    auto* jt = (JniTask*)user;
+    upcall(jt, [&](const J& j) -> int64_t {
+        jobject block = jt->cur_block ? jt->cur_block : jt->last_block;
+        if (!block) return 0;
+        jvalue a;
+        a.l = j.new_string(message);
+        j.call_void(block, "throwFetchFailed", "(Ljava/lang/String;)V", &a);
+        return 0;
+    });
+}
+
 int cb_is_task_running(void* user) {
     auto* jt = (JniTask*)user;
     int64_t r = upcall(jt, [&](const J& j) -> int64_t { return j.call_static_bool(jt->bridge, "isTaskRunning", "()Z") ? 1 : 0; });
@@ -375,13 +410,9 @@ void close_current_block(const J& j, JniTask* jt) {
         jt->cur_block = nullptr;
         j.drop_global(jt->cur_buffer);
         jt->cur_buffer = nullptr;
-        try {
-            j.call_void(b, "close", "()V");   // the readers close their block when dropped (ipc_reader_exec.rs:383-402)
-        } catch (const JavaError&) {
-            j.drop_global(b);
-            throw;
-        }
-        j.drop_global(b);
+        j.drop_global(jt->last_block);
+        jt->last_block = b;                   // the reader decodes after it has drained the block: a decode failure names this one
+        j.call_void(b, "close", "()V");       // the readers close their block when dropped (ipc_reader_exec.rs:383-402)
     }
 }
 
@@ -491,6 +522,7 @@ void release_refs(const J& j, JniTask* jt) {
         j.drop_global(kv.second);
     }
     j.drop_global(jt->cur_block);
+    j.drop_global(jt->last_block);
     j.drop_global(jt->cur_buffer);
     j.drop_global(jt->failure);
     j.drop_global(jt->wrapper);
@@ -527,6 +559,8 @@ jlong Java_org_apache_auron_jni_JniBridge_callNative(JNIEnv* env, jclass, jlong 
         jt->cb.next_shuffle_block = cb_next_shuffle_block;
         jt->cb.upcalls_from_any_thread = 1;
         jt->cb.get_conf = cb_get_conf;
+        jt->cb.write_ipc = cb_write_ipc;
+        jt->cb.fetch_failed = cb_fetch_failed;
         const char* dev = getenv("AURON_B200_DEVICE");
         jt->task = auron_b200_call_native(bytes.data(), bytes.size(), &jt->cb, dev ? atoi(dev) : 0);
         if (!jt->task) {

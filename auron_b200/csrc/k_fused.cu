@@ -110,6 +110,81 @@ __device__ __forceinline__ void fz_scout_page(const FzScoutCol& C, int page_id, 
     const PqDict dd = dict ? C.dicts[pg.dict_id] : PqDict{nullptr, 0, 0};
     int seg = C.seg_base[page_id];
     int64_t v0 = 0;
+    // ---- 2a. all segments at once.  Writers emit the indices of a high-cardinality column as maximal bit-packed runs (63 groups =
+    // 504 values behind a one-byte header 0x7F; parquet-cpp and parquet-mr both close a literal run there), so the stream position
+    // of any value is arithmetic -- once every run header has been checked to sit where that arithmetic puts it (induction over
+    // the runs: a verified header fixes the start of the next run).  Lane s then builds segment s by itself: its non-null count
+    // from the bitmap, its first value from a warp scan, its checkpoint from the value number.  Anything else (RLE runs, short
+    // literal runs, pages of more than 32 segments, pages that went through the global bitmap) takes the serial walk below.
+    const int first_len = min(rows, FZ_TILE - (int)(gr0 & (FZ_TILE - 1)));
+    const int nseg = 1 + (rows - first_len + FZ_TILE - 1) / FZ_TILE;
+    if (nseg <= 32 && (!has_def || use_sb)) {
+        const int r_s = lane == 0 ? 0 : first_len + ((int)lane - 1) * FZ_TILE;
+        const int m_s = (int)lane < nseg ? min(rows - r_s, lane == 0 ? first_len : FZ_TILE) : 0;
+        int nv_s = m_s;
+        if (C.max_def > 0) {
+            if (has_def) {
+                nv_s = 0;
+                if (m_s > 0) {
+                    const int w0 = r_s >> 5, w1 = (r_s + m_s - 1) >> 5;
+                    for (int w = w0; w <= w1; w++) {
+                        uint32_t x = sb[w];
+                        if (w == w0) x &= 0xffffffffu << (r_s & 31);
+                        if (w == w1) x &= 0xffffffffu >> (31 - ((r_s + m_s - 1) & 31));
+                        nv_s += __popc(x);
+                    }
+                }
+            } else if (pg.all_null) nv_s = 0;
+        }
+        int inc = nv_s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(FULL_MASK, inc, d);
+            if ((int)lane >= d) inc += t;
+        }
+        const int total_valid = __shfl_sync(FULL_MASK, inc, 31);
+        const int v_s = inc - nv_s;
+        const int bw = dict ? (pg.val_len > 0 ? (int)vals[0] : 0) : -1;
+        const int run_bytes = 1 + 63 * bw, nfull = total_valid / 504, rem = total_valid % 504, g_last = (rem + 7) / 8;
+        bool regular = true;
+        if (dict) {
+            const int64_t ilen = (int64_t)pg.val_len - 1;
+            regular = bw > 0 && bw <= 32 && (int64_t)nfull * run_bytes + (rem ? 1 + (int64_t)g_last * bw : 0) <= ilen;
+            if (regular) {
+                for (int j = lane; j < nfull; j += 32) regular = regular && idx_base[(int64_t)j * run_bytes] == 0x7F;
+                if (rem && lane == 0) regular = regular && idx_base[(int64_t)nfull * run_bytes] == (uint8_t)((g_last << 1) | 1);
+            }
+            regular = __all_sync(FULL_MASK, regular);
+        }
+        if (regular) {
+            if ((int)lane < nseg) {
+                FzSeg S;
+                S.page = page_id;
+                S.row0 = r_s;
+                S.n = m_s;
+                S.nvalid = nv_s;
+                S.v0 = v_s;
+                S.idx = HybridCk{0, 0, 0, 0, 0, 1};
+                if (dict) {
+                    const int j = v_s / 504, r = v_s % 504;
+                    const int groups = j < nfull ? 63 : g_last;
+                    const int hdr = j * run_bytes;
+                    if (r == 0) S.idx = HybridCk{hdr, 0, hdr, 0, 0, 0};                                  // at a run boundary: the header is read on demand
+                    else S.idx = HybridCk{hdr + 1 + groups * bw, groups * 8 - r, hdr + 1, r, 0, 0};      // inside run j
+                }
+                S.vals = vals;
+                S.val_len = pg.val_len;
+                S.bw = bw;
+                S.ddata = dict ? dd.data : nullptr;
+                S.ndict = dict ? dd.num_values : 0;
+                S.dict_id = pg.dict_id;
+                S.pad[0] = S.pad[1] = 0;
+                C.segs[seg + (int)lane] = S;
+                if (((gr0 + r_s) & (FZ_TILE - 1)) == 0) C.first_seg[(gr0 + r_s) / FZ_TILE] = seg + (int)lane;
+            }
+            return;
+        }
+    }
     for (int r = 0; r < rows; seg++) {
         const int m = min(rows - r, FZ_TILE - (int)((gr0 + r) & (FZ_TILE - 1)));
         int nvalid = m;
@@ -255,15 +330,24 @@ __device__ __forceinline__ uint32_t fz_xform(const FzX& x, uint32_t raw) {
 }
 // value k of a run -> rank pos + k.  Predicate columns: the ballot of 32 consecutive values is ORed into the rank-space
 // bitmap at bit pos + k0 (two words when it straddles); lane 0 is the only writer of the bitmap.
+// pass bits of a predicate column are appended, in value order, to the tile's rank-space bitmap: the writer state is the same in
+// every lane (the ballots are warp-uniform), lane 0 stores each completed word
+struct FzBits {
+    uint64_t acc = 0;
+    int fill = 0, w = 0;
+};
 template <int ROLE>
-__device__ __forceinline__ void fz_store(uint32_t* dst, uint32_t* d, int rank0, unsigned lane, bool act, uint32_t o) {
-    // value planes: d = &plane[fz_pi(rank0 + lane)], advanced by the caller (33 words per 32 ranks)
+__device__ __forceinline__ void fz_store(uint32_t* dst, uint32_t* d, unsigned lane, bool act, uint32_t o, FzBits& bits, int n /* values of this group */) {
+    // value planes: d = &plane[fz_pi(rank)], advanced by the caller (33 words per 32 ranks)
     if (ROLE == FZ_PRED) {
         const uint32_t word = __ballot_sync(FULL_MASK, act && o != 0);
-        if (lane == 0 && word) {
-            const int sh = rank0 & 31;
-            dst[rank0 >> 5] |= word << sh;
-            if (sh) dst[(rank0 >> 5) + 1] |= word >> (32 - sh);
+        bits.acc |= (uint64_t)word << bits.fill;
+        bits.fill += n;
+        if (bits.fill >= 32) {
+            if (lane == 0) dst[bits.w] = (uint32_t)bits.acc;
+            bits.w++;
+            bits.acc >>= 32;
+            bits.fill -= 32;
         }
     } else if (act) {
         *d = o;
@@ -271,7 +355,7 @@ __device__ __forceinline__ void fz_store(uint32_t* dst, uint32_t* d, int rank0, 
 }
 // t values of a bit-packed run starting at value `first` of the packed area -> ranks [pos, pos + t)
 template <int ROLE>
-__device__ __forceinline__ void fz_unpack_bits(const FzX& x, uint32_t* dst, int pos, int t, unsigned lane, const uint8_t* bp_base, int first, int bw) {
+__device__ __forceinline__ void fz_unpack_bits(const FzX& x, uint32_t* dst, int pos, int t, unsigned lane, const uint8_t* bp_base, int first, int bw, FzBits& bits) {
     // lane L unpacks values L, L + 32, ...: 32 values are exactly `bw` 32-bit words, so the word pointer advances by bw per
     // step and the sub-word shift is a per-lane constant of the run
     const int64_t bit0 = (int64_t)(first + (int)lane) * bw;
@@ -289,7 +373,7 @@ __device__ __forceinline__ void fz_unpack_bits(const FzX& x, uint32_t* dst, int 
             hi[u] = __ldg(wp + u * bw + 1);
         }
 #pragma unroll
-        for (int u = 0; u < 8; u++) fz_store<ROLE>(dst, d + 33 * u, pos + k0 + 32 * u, lane, true, fz_xform<ROLE>(x, __funnelshift_r(lo[u], hi[u], sh) & vmask));
+        for (int u = 0; u < 8; u++) fz_store<ROLE>(dst, d + 33 * u, lane, true, fz_xform<ROLE>(x, __funnelshift_r(lo[u], hi[u], sh) & vmask), bits, 32);
         wp += 8 * bw;
         d += 8 * 33;
     }
@@ -301,7 +385,7 @@ __device__ __forceinline__ void fz_unpack_bits(const FzX& x, uint32_t* dst, int 
             hi[u] = __ldg(wp + u * bw + 1);
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) fz_store<ROLE>(dst, d + 33 * u, pos + k0 + 32 * u, lane, true, fz_xform<ROLE>(x, __funnelshift_r(lo[u], hi[u], sh) & vmask));
+        for (int u = 0; u < 4; u++) fz_store<ROLE>(dst, d + 33 * u, lane, true, fz_xform<ROLE>(x, __funnelshift_r(lo[u], hi[u], sh) & vmask), bits, 32);
         wp += 4 * bw;
         d += 4 * 33;
     }
@@ -309,19 +393,19 @@ __device__ __forceinline__ void fz_unpack_bits(const FzX& x, uint32_t* dst, int 
         const bool act = k0 + (int)lane < t;
         uint32_t o = 0;
         if (act) o = fz_xform<ROLE>(x, __funnelshift_r(__ldg(wp), __ldg(wp + 1), sh) & vmask);
-        fz_store<ROLE>(dst, d, pos + k0, lane, act, o);
+        fz_store<ROLE>(dst, d, lane, act, o, bits, min(32, t - k0));
         wp += bw;
         d += 33;
     }
 }
 template <int ROLE>
-__device__ __forceinline__ void fz_unpack_const(const FzX& x, uint32_t* dst, int pos, int t, unsigned lane, uint32_t raw) {
+__device__ __forceinline__ void fz_unpack_const(const FzX& x, uint32_t* dst, int pos, int t, unsigned lane, uint32_t raw, FzBits& bits) {
     const uint32_t o = fz_xform<ROLE>(x, raw);
     uint32_t* d = dst + fz_pi(pos + (int)lane);
-    for (int k0 = 0; k0 < t; k0 += 32, d += 33) fz_store<ROLE>(dst, d, pos + k0, lane, k0 + (int)lane < t, o);
+    for (int k0 = 0; k0 < t; k0 += 32, d += 33) fz_store<ROLE>(dst, d, lane, k0 + (int)lane < t, o, bits, min(32, t - k0));
 }
 template <int ROLE>
-__device__ __forceinline__ void fz_unpack_plain(const FzX& x, uint32_t* dst, int pos, int t, unsigned lane, const uint8_t* first) {
+__device__ __forceinline__ void fz_unpack_plain(const FzX& x, uint32_t* dst, int pos, int t, unsigned lane, const uint8_t* first, FzBits& bits) {
     const uintptr_t ba = (uintptr_t)first;   // no alignment guarantee: page payloads sit at arbitrary file offsets
     const uint32_t* wp = (const uint32_t*)(ba & ~(uintptr_t)3) + lane;
     const unsigned bsh = (unsigned)(ba & 3) * 8;
@@ -330,7 +414,7 @@ __device__ __forceinline__ void fz_unpack_plain(const FzX& x, uint32_t* dst, int
         const bool act = k0 + (int)lane < t;
         uint32_t o = 0;
         if (act) o = fz_xform<ROLE>(x, bsh ? __funnelshift_r(__ldg(wp), __ldg(wp + 1), bsh) : __ldg(wp));
-        fz_store<ROLE>(dst, d, pos + k0, lane, act, o);
+        fz_store<ROLE>(dst, d, lane, act, o, bits, min(32, t - k0));
     }
 }
 // validity word + rank base of this lane's rows
@@ -365,6 +449,7 @@ __device__ __forceinline__ bool fz_load_col(const FzLaunch& L, int c, int T, int
     x.kmin = L.kmin;
     x.range = L.range;
     x.oor = L.oor;
+    FzBits bits;
     int seg = __ldg(C.first_seg + T), covered = 0, pos = 0;
     for (int guard = 0; covered < n_tile && guard < FZ_TILE; guard++, seg++) {
         const FzSeg* sp = C.segs + seg;
@@ -394,18 +479,19 @@ __device__ __forceinline__ bool fz_load_col(const FzLaunch& L, int c, int T, int
             while (done < nvs) {
                 if (idx.run_remaining == 0) idx.next_run();
                 const int t = min(nvs - done, idx.run_remaining);
-                if (idx.is_rle) fz_unpack_const<ROLE>(x, dst, pos + done, t, lane, idx.rle_value);
-                else fz_unpack_bits<ROLE>(x, dst, pos + done, t, lane, idx.bp_base, idx.bp_consumed, bw);
+                if (idx.is_rle) fz_unpack_const<ROLE>(x, dst, pos + done, t, lane, idx.rle_value, bits);
+                else fz_unpack_bits<ROLE>(x, dst, pos + done, t, lane, idx.bp_base, idx.bp_consumed, bw, bits);
                 done += t;
                 idx.run_remaining -= t;
                 if (!idx.is_rle) idx.bp_consumed += t;
             }
         } else {   // PLAIN INT32: value k of the segment is the 32-bit word at vals + 4 (v0 + k)
             const int64_t v0 = (int64_t)(((uint64_t)(uint32_t)s1.y << 32) | (uint32_t)s1.x);
-            fz_unpack_plain<ROLE>(x, dst, pos, nvs, lane, vals + v0 * 4);
+            fz_unpack_plain<ROLE>(x, dst, pos, nvs, lane, vals + v0 * 4, bits);
         }
         pos += nvs;
     }
+    if (ROLE == FZ_PRED && bits.fill > 0 && lane == 0) dst[bits.w] = (uint32_t)bits.acc;   // the last, partial word
     __syncwarp();
     return all_dict;
 }

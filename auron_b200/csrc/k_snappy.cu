@@ -68,15 +68,16 @@ __global__ void __launch_bounds__(128) pq_decompress_prefix_kernel(const PqDecom
     uint8_t* dst = nullptr;
     int n_in = 0, n_out = 0, ip = 0, op = 0, elems = 0;
     int wbase = 0;   // input offset of win[0]
-    bool have_win = false;
+    bool have_win = false, head_only = false;   // head_only: the job is the front part of a block (its preamble counts the whole block)
     if (job < n_jobs) {
         const PqDecompJob jb = jobs[job];
         if (sub == 0) {
             results[job] = PqDecompResult{nullptr, -1, 0};
             states[job] = PqDecompState{0, 0};
         }
-        if (jb.kind == 1 && jb.v1_levels) {
+        if (jb.kind >= 1 && jb.v1_levels) {
             active = true;
+            head_only = jb.kind == 2;
             src = jb.src;
             dst = jb.dst;
             n_in = jb.src_len;
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(128) pq_decompress_prefix_kernel(const PqDecom
                     if (!(b & 0x80)) break;
                     shift += 7;
                 }
-                if (active && (int)v != n_out) active = false;
+                if (active && (head_only ? (int)v < n_out : (int)v != n_out)) active = false;
             }
         }
         if (active) {
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(128) pq_decompress_kernel(const PqDecompJob* _
             if (!(b & 0x80)) break;
             shift += 7;
         }
-        if ((int)v != n_out) bad = true;
+        if (jb.kind == 2 ? (int)v < n_out : (int)v != n_out) bad = true;
     }
     while (!bad && ip < n_in) {
         const uint32_t tag = src[ip++];
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(128) pq_decompress_kernel(const PqDecompJob* _
             // Nullable v1 data page whose stream ends with one literal that contains the whole value section (bit-packed
             // dictionary indices do not compress; the level bytes in front of them do): copy only the level bytes that
             // spill into this literal and let the page read its values in place from the compressed buffer.
-            if (jb.v1_levels && ip + len == n_in && op + len == n_out && op >= 4) {
+            if (jb.v1_levels && jb.kind == 1 && ip + len == n_in && op + len == n_out && op >= 4) {
                 __syncwarp();
                 const int64_t val_off = 4 + (int64_t)((uint32_t)dst[0] | ((uint32_t)dst[1] << 8) | ((uint32_t)dst[2] << 16) | ((uint32_t)dst[3] << 24));
                 const int64_t keep = val_off - op;

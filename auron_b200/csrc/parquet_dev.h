@@ -48,7 +48,8 @@ struct PqDecompJob {
     const uint8_t* src;
     uint8_t* dst;
     int32_t src_len, dst_len;
-    int32_t kind;       // 0 = stored bytes, 1 = Snappy raw block
+    int32_t kind;       // 0 = stored bytes, 1 = Snappy raw block, 2 = the front elements of a Snappy raw block (the preamble
+                        //     counts the whole block; the job ends after src_len bytes, which decode to dst_len bytes)
     int32_t v1_levels;  // 1 = body of a nullable v1 data page ([u32 length][levels][values]): a final literal that holds the
                         //     whole value section is NOT copied, the page then reads its values from the compressed buffer
 };

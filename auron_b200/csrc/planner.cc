@@ -962,6 +962,18 @@ static OperatorPtr decode_plan(Task& t, const uint8_t* b, size_t n) {
                 out.reset(new ExpandExec(std::move(input), schema, std::move(projs)));
                 break;
             }
+            case 4: {   // IpcWriterExecNode{input=1, ipc_consumer_resource_id=2}
+                OperatorPtr input;
+                std::string rid;
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) input = plan_field(t, s);
+                    else if (sf == 2 && sw == 2) rid = s.bytes();
+                    else s.skip(sw);
+                }
+                AURON_CHECK(input, "IpcWriterExecNode without input");
+                out = make_ipc_writer(t, std::move(input), rid);
+                break;
+            }
             case 5: out = make_parquet_scan(t, sb, sn); break;
             case 2: {   // ShuffleWriterExecNode{input=1, ...}
                 OperatorPtr input;

@@ -483,6 +483,51 @@ struct ParquetScanExec : Operator, FusedScanSource {
         }
         return out == unc;
     }
+    // Walk the elements of a raw Snappy block without decoding it (tags only).  True when the block is well formed up to
+    // `max_tokens` elements; then [0, *head_in) / [0, *head_out) are the compressed / uncompressed bytes up to and including the
+    // last back reference, and `pieces` are the literals after it (nothing refers back into them or reads them again).
+    static bool snappy_split(const uint8_t* p, int64_t n, int64_t unc, int max_tokens, int64_t* head_in, int64_t* head_out, std::vector<LitPiece>* pieces) {
+        int64_t i = 0, out = 0;
+        uint64_t v = 0;
+        for (int shift = 0;; shift += 7) {
+            if (i >= n || shift > 28) return false;
+            const uint8_t b = p[i++];
+            v |= (uint64_t)(b & 0x7f) << shift;
+            if (!(b & 0x80)) break;
+        }
+        if ((int64_t)v != unc || unc <= 0) return false;
+        pieces->clear();
+        *head_in = i;
+        *head_out = 0;
+        for (int tok = 0; i < n; tok++) {
+            if (tok >= max_tokens) return false;
+            const uint8_t tag = p[i++];
+            if ((tag & 3) == 0) {
+                int64_t len = (tag >> 2) + 1;
+                if (len > 60) {
+                    const int nb = (int)len - 60;
+                    if (i + nb > n) return false;
+                    uint32_t w = 0;
+                    for (int k = 0; k < nb; k++) w |= (uint32_t)p[i + k] << (8 * k);
+                    i += nb;
+                    len = (int64_t)w + 1;
+                }
+                if (len > n - i || len > unc - out) return false;
+                pieces->push_back(LitPiece{i, len});
+                i += len;
+                out += len;
+            } else {
+                const int64_t len = (tag & 3) == 1 ? 4 + ((tag >> 2) & 7) : (tag >> 2) + 1;
+                i += (tag & 3) == 1 ? 1 : (tag & 3) == 2 ? 2 : 4;
+                if (i > n || len > unc - out) return false;
+                out += len;
+                pieces->clear();        // literals before a back reference belong to the head
+                *head_in = i;
+                *head_out = out;
+            }
+        }
+        return out == unc;
+    }
     static bool gpu_snappy() {
         return getenv("AURON_HOST_SNAPPY") == nullptr;   // AURON_HOST_SNAPPY=1: decompress on the host cores instead
     }
@@ -534,24 +579,33 @@ struct ParquetScanExec : Operator, FusedScanSource {
                 out.gpu_unc_bytes += ((int64_t)h.uncompressed_size + 8 + 15) & ~(int64_t)15;
                 if (lvl_bytes) out.jobs.push_back(PqDecompJob{payload_d, (uint8_t*)(intptr_t)unc_off, lvl_bytes, lvl_bytes, 0, 0});   // v2 levels are stored
                 // A large incompressible body (an 816 KB dictionary of surrogate keys, a 1 MB page of bit-packed indices) is a
-                // chain of 64 KB literals: one warp walking it serially was the long pole of the whole launch (0.5 ms).  Its
-                // pieces become independent stored-copy jobs of <= 16 KB instead.  (Nullable v1 data pages keep the Snappy job:
-                // their level prefix is compressed.)
+                // chain of 64 KB literals, in a nullable v1 data page behind a few back references that compress the level bytes:
+                // one warp walking the chain serially was the long pole of the whole launch (0.85 ms per 1 MB page, however few
+                // pages the batch holds).  The host walks the tags (16 per MB); the literals behind the last back reference
+                // become independent stored-copy jobs of <= 16 KB, the elements before them a short Snappy job of their own.
+                // Not split: a body whose tail is ONE literal in a nullable v1 page (the decoder leaves that one in place), and
+                // bodies of many elements (compressible data: the walk stops after 4096 tags).
                 std::vector<LitPiece> pieces;
                 const bool v1_nullable = h.type == pq::PAGE_DATA && max_def > 0;
-                if (!v1_nullable && h.uncompressed_size - lvl_bytes > (64 << 10) &&
-                    snappy_literal_chain(payload_h + lvl_bytes, h.compressed_size - lvl_bytes, h.uncompressed_size - lvl_bytes, 256, &pieces)) {
+                const uint8_t* body_h = payload_h + lvl_bytes;
+                const uint8_t* body_d = payload_d + lvl_bytes;
+                const int64_t body_in = h.compressed_size - lvl_bytes, body_out = h.uncompressed_size - lvl_bytes;
+                int64_t head_in = 0, head_out = 0;
+                if (body_out > (64 << 10) && snappy_split(body_h, body_in, body_out, 4096, &head_in, &head_out, &pieces) &&
+                    body_out - head_out >= (32 << 10) && !(v1_nullable && pieces.size() == 1)) {
                     int64_t dst = unc_off + lvl_bytes;
+                    if (head_out > 0)   // kind 2: the preamble states the length of the whole body, the job ends after head_out bytes
+                        out.jobs.push_back(PqDecompJob{body_d, (uint8_t*)(intptr_t)dst, (int32_t)head_in, (int32_t)head_out, 2, v1_nullable ? 1 : 0});
+                    dst += head_out;
                     for (auto& pc : pieces) {
                         for (int64_t o = 0; o < pc.len; o += 16 << 10) {
                             const int32_t l = (int32_t)std::min<int64_t>(16 << 10, pc.len - o);
-                            out.jobs.push_back(PqDecompJob{payload_d + lvl_bytes + pc.src_off + o, (uint8_t*)(intptr_t)(dst + o), l, l, 0, 0});
+                            out.jobs.push_back(PqDecompJob{body_d + pc.src_off + o, (uint8_t*)(intptr_t)(dst + o), l, l, 0, 0});
                         }
                         dst += pc.len;
                     }
                 } else {
-                    out.jobs.push_back(PqDecompJob{payload_d + lvl_bytes, (uint8_t*)(intptr_t)(unc_off + lvl_bytes), h.compressed_size - lvl_bytes,
-                                                   h.uncompressed_size - lvl_bytes, 1, 0});
+                    out.jobs.push_back(PqDecompJob{body_d, (uint8_t*)(intptr_t)(unc_off + lvl_bytes), (int32_t)body_in, (int32_t)body_out, 1, 0});
                 }
                 payload_h = nullptr;
             } else if (page_compressed && !page_dev) {
@@ -598,7 +652,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
                         AURON_CHECK(total >= 4, "corrupt parquet page");
                         pg.def_len = -1;
                         pg.job = (int32_t)out.jobs.size() - 1;   // the Snappy job pushed for this page above
-                        out.jobs.back().v1_levels = 1;
+                        if (out.jobs.back().kind == 1) out.jobs.back().v1_levels = 1;   // (a split body has its flag already)
                         out.has_v1_inline = true;
                     } else {
                         uint32_t dl;

@@ -392,7 +392,17 @@ struct IpcReaderExec : Operator {
         return out;
     }
 
+    // ipc_reader_exec.rs:211-219: a block that cannot be decoded is reported to the host as a fetch failure before the task fails
     BatchPtr next(Task& t) override {
+        try {
+            return next_chunk(t);
+        } catch (const Error& e) {
+            const std::string msg = e.what();
+            if (msg.rfind("shuffle read:", 0) == 0 && t.cb && t.cb->fetch_failed) t.cb->fetch_failed(t.cb->user, resource_id.c_str(), msg.c_str());
+            throw;
+        }
+    }
+    BatchPtr next_chunk(Task& t) {
         if (done) return nullptr;
         OpTimer timer(metrics, "elapsed_ns");
         const int ncols = (int)out_schema.fields.size();

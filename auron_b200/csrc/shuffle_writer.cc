@@ -23,6 +23,7 @@
 
 #include "exchange.h"
 #include "host_pool.h"
+#include "../../include/auron_b200.h"
 #include "operators.h"
 #include "pb.h"
 
@@ -375,9 +376,33 @@ struct ShuffleWriterExec : Operator {
         return out;
     }
 
+    // IpcWriterExec (ipc_writer_exec.rs:106-190): the same serialisation + block compression, one partition, every finished chunk of
+    // blocks handed to the consumer callback as soon as it exists
+    std::string ipc_consumer_id;
+    bool is_ipc_writer = false;
+    void deliver_chunks(Task& t) {
+        AURON_CHECK(t.cb && t.cb->write_ipc, "IpcWriterExec needs the write_ipc callback");
+        for (auto& ch : chunks) {
+            const int64_t b = ch.part_off[0], e = ch.part_off[1];
+            if (e > b && t.cb->write_ipc(t.cb->user, ipc_consumer_id.c_str(), ch.bytes + b, e - b) < 0) fail("write_ipc failed for resource " + ipc_consumer_id);
+            metrics.add("data_size_written", e - b);
+        }
+        chunks.clear();
+    }
+
     BatchPtr next(Task& t) override {
         if (done) return nullptr;
         done = true;
+        if (is_ipc_writer) {
+            while (BatchPtr b = children[0]->next(t)) {
+                AURON_CHECK(t.is_running(), "task killed");
+                if (b->num_rows == 0) continue;
+                write_chunk(t, b);
+                deliver_chunks(t);
+            }
+            metrics.add("output_rows", rows_so_far);
+            return nullptr;
+        }
         if (data_file.rfind("nccl://", 0) == 0) return exchange(t);
         while (BatchPtr b = children[0]->next(t)) {
             AURON_CHECK(t.is_running(), "task killed");
@@ -388,6 +413,20 @@ struct ShuffleWriterExec : Operator {
         return nullptr;   // the output stream of a shuffle writer is empty (shuffle/mod.rs:61-108)
     }
 };
+
+OperatorPtr make_ipc_writer(Task& t, OperatorPtr input, const std::string& consumer_id) {
+    auto op = std::make_unique<ShuffleWriterExec>();
+    op->name = "IpcWriterExec";
+    op->out_schema = input->out_schema;
+    op->kind = 1;
+    op->num_parts = 1;
+    op->is_ipc_writer = true;
+    op->ipc_consumer_id = consumer_id;
+    op->zstd = t.conf("SPARK_IO_COMPRESSION_CODEC", "AURON_IO_COMPRESSION_CODEC", "lz4") == "zstd";
+    op->zstd_level = atoi(t.conf("SPARK_IO_COMPRESSION_ZSTD_LEVEL", "AURON_IO_COMPRESSION_ZSTD_LEVEL", "1").c_str());
+    op->children.push_back(std::move(input));
+    return op;
+}
 
 OperatorPtr make_shuffle_writer(Task& t, OperatorPtr input, const uint8_t* node, size_t n) {
     auto op = std::make_unique<ShuffleWriterExec>();

@@ -289,6 +289,11 @@ def expand(inp: bytes, s: pa.Schema, projections: list[list[bytes]]) -> bytes:
     return f_bytes(20, body)
 
 
+def ipc_writer(inp: bytes, consumer_resource_id: str) -> bytes:
+    """PhysicalPlanNode{ipc_writer{input, ipc_consumer_resource_id}} (auron.proto:631-634; NativeBroadcastExchangeBase.scala:317-328)"""
+    return f_bytes(4, f_bytes(1, inp) + f_str(2, consumer_resource_id))
+
+
 def hash_repartition(exprs: list[bytes], n: int) -> bytes:
     """PhysicalRepartition{hash_repartition}"""
     return f_bytes(2, b"".join(f_bytes(1, e) for e in exprs) + f_varint(2, n))

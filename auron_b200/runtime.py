@@ -38,11 +38,13 @@ class ShuffleBlockC(C.Structure):
 
 
 _BLOCK_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p, C.POINTER(ShuffleBlockC))
+_IPC_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64)
+_FETCH_FAILED_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_char_p, C.c_char_p)
 
 
 class Callbacks(C.Structure):
     _fields_ = [("user", C.c_void_p), ("export_next_batch", _EXPORT_CB), ("read_fully", _READ_CB), ("is_task_running", _RUNNING_CB),
-                ("next_shuffle_block", _BLOCK_CB), ("upcalls_from_any_thread", C.c_int32), ("get_conf", C.c_void_p)]
+                ("next_shuffle_block", _BLOCK_CB), ("upcalls_from_any_thread", C.c_int32), ("get_conf", C.c_void_p), ("write_ipc", _IPC_CB), ("fetch_failed", _FETCH_FAILED_CB)]
 
 
 class AuronError(RuntimeError):
@@ -116,7 +118,7 @@ class Task:
     """One native task: callNative -> nextBatch* -> finalizeNative (JniBridge.java:49-55)."""
 
     def __init__(self, task_definition: bytes, inputs: dict[str, Iterable[pa.RecordBatch]] | None = None, device: int = 0,
-                 read_fully=None, shuffle_blocks: dict[str, Iterable] | None = None):
+                 read_fully=None, shuffle_blocks: dict[str, Iterable] | None = None, ipc_consumers: dict[str, list] | None = None):
         """shuffle_blocks: resource id -> iterable of blocks for IpcReaderExec; a block is (path, offset, length) for a file
         segment or a bytes object for an in-memory buffer (AuronBlockObject.hasFileSegment / hasByteBuffer)."""
         self._inputs = {k: iter(v) for k, v in (inputs or {}).items()}
@@ -179,8 +181,25 @@ class Task:
                 self._cb_error = e
                 return -1
 
+        def _write_ipc(user, rid, data, length):
+            # IpcWriterExec's consumer: ipc_consumers[resource id] is a list that receives every delivered block sequence as bytes
+            try:
+                sink = (ipc_consumers or {}).get(rid.decode())
+                if sink is None:
+                    return -1
+                sink.append(C.string_at(data, length))
+                return 0
+            except BaseException as e:  # noqa: BLE001
+                self._cb_error = e
+                return -1
+
+        self.fetch_failures: list[tuple[str, str]] = []   # (resource id, message) of every fetch_failed upcall
+
+        def _fetch_failed(user, rid, msg):
+            self.fetch_failures.append((rid.decode(), msg.decode(errors="replace")))
+
         self._cbs = Callbacks(None, _EXPORT_CB(_export_next), _READ_CB(_read) if read_fully is not None else _READ_CB(0), _RUNNING_CB(0),
-                              _BLOCK_CB(_next_block))
+                              _BLOCK_CB(_next_block), 0, None, _IPC_CB(_write_ipc), _FETCH_FAILED_CB(_fetch_failed))
         self._handle = lib().auron_b200_call_native(task_definition, len(task_definition), C.addressof(self._cbs), device)
         if not self._handle:
             raise AuronError(_err())

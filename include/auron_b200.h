@@ -68,6 +68,15 @@ typedef struct auron_callbacks {
      * ...) written to `value` as text, NUL-terminated.  Returns its length, or <0 when the host has no such entry (the
      * engine then falls back to its AURON_* environment variable, then to the reference's default).  May be NULL. */
     int (*get_conf)(void* user, const char* key, char* value, int32_t cap);
+    /* IpcWriterExec (datafusion-ext-plans/src/ipc_writer_exec.rs:106-190): the consumer registered under resource_id -- a
+     * Scala `ByteBuffer => Unit` on the JVM side (broadcast exchange: NativeBroadcastExchangeBase.scala:317-328) -- receives
+     * the Auron compacted batch format, block by block (`u32 length | codec stream`, ipc_compression.rs:84-103).  `data` is
+     * valid during the call only.  Returns 0, or <0 on error.  Only needed when the plan has an IpcWriterExecNode. */
+    int (*write_ipc)(void* user, const char* resource_id, const uint8_t* data, int64_t len);
+    /* AuronBlockObject.throwFetchFailed(errmsg) (ipc_reader_exec.rs:211-219): the shuffle data read through resource_id is
+     * corrupt.  A Spark host turns this into a FetchFailedException, so that the map output is recomputed instead of the
+     * task failing for good.  Called before the engine returns the error from next_batch.  May be NULL. */
+    void (*fetch_failed)(void* user, const char* resource_id, const char* message);
 } auron_callbacks;
 
 typedef struct auron_task auron_task;

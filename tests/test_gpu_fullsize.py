@@ -38,6 +38,8 @@ def test_config2_full_size_checksums(tmp_path_factory):
     paths = [f for f, _ in files]
     exp_cnt = exp_sum = 0
     seen = np.zeros(bench.N_ITEMS + 1, dtype=bool)
+    cnt_g = np.zeros(bench.N_ITEMS + 1, dtype=np.int64)           # per group: COUNT(ss_quantity), SUM(ss_quantity)
+    sum_g = np.zeros(bench.N_ITEMS + 1, dtype=np.int64)
     for i, (_, rows) in enumerate(files):
         rng = np.random.default_rng(42 + i)                       # same draws as bench.gen_file
         item = rng.integers(1, bench.N_ITEMS + 1, rows, dtype=np.int32)
@@ -49,11 +51,21 @@ def test_config2_full_size_checksums(tmp_path_factory):
         exp_cnt += int(np.count_nonzero(keep & ~qnull))
         exp_sum += int(qty[keep & ~qnull].astype(np.int64).sum())
         seen[item[keep]] = True
+        sel = keep & ~qnull
+        cnt_g += np.bincount(item[sel], minlength=bench.N_ITEMS + 1)
+        sum_g += np.bincount(item[sel], weights=qty[sel].astype(np.float64), minlength=bench.N_ITEMS + 1).astype(np.int64)   # exact: < 2^53
     out = _run(bench.build_plan(P, paths, [os.path.getsize(p) for p in paths]), is_task_definition=True)
     assert out.num_rows == int(seen.sum())                                  # every selected item is a group, exactly once
     assert len(set(out.column(0).to_pylist())) == out.num_rows
     assert int(out.column(2).to_numpy().sum()) == exp_cnt                   # COUNT(ss_quantity)
     assert int(np.nansum(out.column(1).to_numpy(zero_copy_only=False).astype(np.float64))) == exp_sum   # SUM(ss_quantity) (exact in f64: < 2^53)
+    # every group's own COUNT and SUM, not only their totals
+    keys = out.column(0).to_numpy()
+    assert np.array_equal(np.sort(keys), np.nonzero(seen)[0])
+    assert np.array_equal(out.column(2).to_numpy(), cnt_g[keys])
+    sums = out.column(1).combine_chunks()
+    assert np.array_equal(np.asarray(sums.is_valid()), cnt_g[keys] > 0)         # SUM of no values is NULL (sum.rs:115)
+    assert np.array_equal(sums.fill_null(0).to_numpy(), sum_g[keys])
 
 
 def test_config3_full_size_join_counts():

@@ -284,3 +284,18 @@ def test_scan_partition_columns_and_row_group_pruning(tmp_path):
         (got.column(0).to_pylist(), got.column(1).to_pylist(), got.column(2).to_pylist()) == ([2451001], [int(qty[keep].sum())], [int(keep.sum())])
     assert met.get(("ParquetExec", "row_groups_pruned"), 0) >= 12, met      # 15 row groups, at most 2-3 can hold items in [150000, 160000)
     assert met[("ParquetExec", "output_rows")] <= 30_000
+
+
+def test_fused_rle_runs_and_mixed_streams(tmp_path):
+    # sorted / clustered columns: the dictionary-index streams are RLE runs and short literal runs, not the maximal bit-packed runs
+    # of random data -- the scout's arithmetic checkpoints do not apply and it walks the run headers
+    rng = np.random.default_rng(10)
+    n = 150_000
+    item = np.sort(rng.integers(1, 400, n)).astype(np.int32)                      # long RLE runs
+    qty = np.repeat(rng.integers(1, 101, n // 10), 10).astype(np.int32)           # runs of exactly 10: RLE(8) + literal groups mixed
+    date = rng.integers(2450816, 2452642, n, dtype=np.int32)
+    date[: n // 2] = 2451500                                                      # half constant, half random
+    t = pa.table({"item": pa.array(item, mask=rng.random(n) < 0.01), "qty": pa.array(qty, mask=rng.random(n) < 0.03), "date": pa.array(date, mask=rng.random(n) < 0.04)})
+    p = _write(str(tmp_path / "a.parquet"), t, row_group_size=70_000, data_page_size=16_000)
+    _check([p], t, "item", DATE_PREDS, SUM_COUNT + [("COUNT*", None)])
+    _check([p], t, "qty", [("item", "Gt", 100)], [("SUM", "date"), ("MIN", "item"), ("MAX", "item")])

@@ -13,6 +13,7 @@ from auron_b200 import proto as P
 from auron_b200 import runtime
 from helpers import assert_same_rows, batches, canon
 from jni_helpers import MockJvm
+import oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -96,6 +97,28 @@ def test_ipc_reader_takes_blocks_of_every_kind_from_the_scala_iterator(tmp_path)
     got = jvm.run()
     assert_same_rows(got, t)
     assert jvm.M.mock_blocks_closed(jvm.vm, b"blocks") == 4           # each block closed exactly once (:383-402)
+    jvm.assert_clean()
+
+
+def test_corrupt_block_raises_fetch_failed_on_the_block_object():
+    # ipc_reader_exec.rs:211-219: a block that does not decode -> BlockObject.throwFetchFailed(message); Spark's
+    # FetchFailedException is the cause the task fails with, so the scheduler recomputes the map output
+    t = _input(8_000, seed=3)
+    payload = b"".join(oracle.serde_write_batch(b) for b in batches(t, 2_000))
+    sink = pa.BufferOutputStream()
+    with pa.CompressedOutputStream(sink, "zstd") as z:
+        z.write(payload)
+    comp = bytearray(sink.getvalue().to_pybytes())
+    for i in range(30, 90):
+        comp[i] ^= 0xA5
+    jvm = MockJvm(P.task_definition(P.ipc_reader(t.schema, "blocks")))
+    jvm.add_block("blocks", "heap", data=struct.pack("<I", len(comp)) + bytes(comp))
+    assert jvm.call_native()
+    while jvm.load_next_batch() is not None:
+        pass
+    err = jvm.error()
+    assert "shuffle read:" in err and "<- org/apache/spark/shuffle/FetchFailedException: shuffle read:" in err, err
+    jvm.close()
     jvm.assert_clean()
 
 

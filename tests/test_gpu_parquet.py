@@ -176,6 +176,30 @@ def test_scan_snappy_pages_decompressed_on_device(tmp_path, version, dict_, monk
 
 
 @pytest.mark.parametrize("version", ["1.0", "2.0"])
+def test_scan_snappy_large_pages_split_into_head_and_stored_pieces(tmp_path, version):
+    # 1 MB pages whose bodies are a few back references (the compressed level bytes) followed by a chain of 64 KB literals: the
+    # host hands the literals out as stored-copy jobs and the elements before them as a Snappy job of their own; a body whose
+    # back references come last ("tail_runs") and one with a dictionary ("keys") take the other routes
+    rng = np.random.default_rng(17)
+    n = 900_001
+    half = n // 2
+    t = pa.table({
+        "noise": pa.array(rng.integers(-2**31, 2**31 - 1, n).astype(np.int32), mask=rng.random(n) < 0.05),
+        "noise_nn": pa.array(rng.integers(-2**62, 2**62, n).astype(np.int64)),
+        "tail_runs": pa.array(np.concatenate([rng.integers(-2**31, 2**31 - 1, half), np.repeat(rng.integers(0, 9, (n - half) // 500 + 1), 500)[:n - half]]).astype(np.int32),
+                              mask=rng.random(n) < 0.02),
+        "keys": pa.array(rng.integers(1, 150_000, n).astype(np.int32), mask=rng.random(n) < 0.03),
+    })
+    path = str(tmp_path / "big.parquet")
+    pq.write_table(t, path, compression="SNAPPY", use_dictionary=["keys"], data_page_version=version, row_group_size=600_000)
+    exp = pq.read_table(path)
+    got = _scan(path, t.schema)
+    for name in t.column_names:
+        assert got[name].to_numpy(zero_copy_only=False).tobytes() == exp[name].to_numpy(zero_copy_only=False).tobytes(), name
+        assert got[name].null_count == exp[name].null_count, name
+
+
+@pytest.mark.parametrize("version", ["1.0", "2.0"])
 @pytest.mark.parametrize("dict_", [True, False])
 def test_scan_snappy_string_pages_decompressed_on_device(tmp_path, version, dict_, monkeypatch):
     # string columns: dictionary pages (PLAIN byte arrays) + RLE index pages, PLAIN data pages (v2; v1 when the column is
