@@ -135,21 +135,26 @@ static Buf exchange_buffer(Ctx& ctx, const uint8_t* send, int esz, const std::ve
     return out;
 }
 
+// num_parts > 0: rows [part_row_off[p], part_row_off[p + 1]) go to the rank that owns partition p (all-to-all-v).
+// num_parts == 0: every rank receives every rank's rows, in rank order (all-gather-v) -- the build side of a broadcast join, collected
+// from the partitions the ranks hold and replicated over NVLink instead of once per GPU over PCIe.
 BatchPtr nccl_exchange(Ctx& ctx, const Batch& sorted, const std::vector<int64_t>& part_row_off, int64_t num_parts, int64_t* bytes_sent) {
     AURON_CHECK(g_comm.comm != nullptr, "NCCL exchange requested but auron_b200_nccl_init was not called");
     AURON_CHECK(ctx.device == g_comm.device, "exchange on a different device than the communicator");
     const int world = g_comm.world;
     // rows per destination rank: partition p belongs to rank p * world / num_parts
-    std::vector<int64_t> send_off(world + 1, 0);
-    {
+    std::vector<int64_t> send_off(world + 1, 0);   // destination r gets rows [send_off[r], send_off[r] + send_cnt[r])
+    std::vector<int64_t> send_cnt(world);
+    if (num_parts > 0) {
         int r = 0;
         for (int64_t p = 0; p <= num_parts; p++) {
             int owner = p == num_parts ? world : (int)(p * world / num_parts);
             while (r < owner) send_off[++r] = part_row_off[p];
         }
+        for (int q = 0; q < world; q++) send_cnt[q] = send_off[q + 1] - send_off[q];
+    } else {
+        for (int q = 0; q < world; q++) send_cnt[q] = sorted.num_rows;
     }
-    std::vector<int64_t> send_cnt(world);
-    for (int r = 0; r < world; r++) send_cnt[r] = send_off[r + 1] - send_off[r];
     const size_t ncols = sorted.cols.size();
     // counts matrix: [rows, bytes of each varlen column] per destination
     std::vector<int> varlen_cols;
@@ -160,17 +165,16 @@ BatchPtr nccl_exchange(Ctx& ctx, const Batch& sorted, const std::vector<int64_t>
     std::vector<std::vector<int64_t>> byte_off(varlen_cols.size());
     for (size_t v = 0; v < varlen_cols.size(); v++) {
         const Column& col = *sorted.cols[varlen_cols[v]];
-        std::vector<int32_t> tmp(world + 1);
-        for (int r = 0; r <= world; r++) {   // offsets at the rank boundaries
-            int32_t o = 0;
-            to_host(ctx, &o, P<int32_t>(col.offsets) + send_off[r], 4);
-            tmp[r] = o;
+        std::vector<int32_t> tmp(2 * (size_t)world);   // byte offsets at the first row and behind the last row of every destination's range
+        for (int r = 0; r < world; r++) {
+            to_host(ctx, &tmp[2 * (size_t)r], P<int32_t>(col.offsets) + send_off[r], 4);
+            to_host(ctx, &tmp[2 * (size_t)r + 1], P<int32_t>(col.offsets) + send_off[r] + send_cnt[r], 4);
         }
         byte_off[v].assign(tmp.begin(), tmp.end());
     }
     for (int r = 0; r < world; r++) {
         my_counts[(size_t)r * kstride] = send_cnt[r];
-        for (size_t v = 0; v < varlen_cols.size(); v++) my_counts[(size_t)r * kstride + 1 + v] = byte_off[v][r + 1] - byte_off[v][r];
+        for (size_t v = 0; v < varlen_cols.size(); v++) my_counts[(size_t)r * kstride + 1 + v] = byte_off[v][2 * (size_t)r + 1] - byte_off[v][2 * (size_t)r];
     }
     Buf d_my = to_device(ctx, my_counts.data(), my_counts.size() * 8);
     Buf d_all = dalloc(ctx, (size_t)world * my_counts.size() * 8);
@@ -251,8 +255,11 @@ BatchPtr nccl_exchange(Ctx& ctx, const Batch& sorted, const std::vector<int64_t>
             exclusive_scan_i32(ctx, P<int32_t>(rl), P<int32_t>(oc->offsets), n_recv, P<int32_t>(oc->offsets) + n_recv);
             if (n_recv == 0) CUDA_OK(cudaMemsetAsync(oc->offsets->ptr, 0, 4, ctx.stream));
             auto rbytes = recv_counts(1 + (int)v);
-            std::vector<int64_t> sboff(byte_off[v].begin(), byte_off[v].begin() + world), sbcnt(world);
-            for (int r = 0; r < world; r++) sbcnt[r] = byte_off[v][r + 1] - byte_off[v][r];
+            std::vector<int64_t> sboff(world), sbcnt(world);
+            for (int r = 0; r < world; r++) {
+                sboff[r] = byte_off[v][2 * (size_t)r];
+                sbcnt[r] = byte_off[v][2 * (size_t)r + 1] - byte_off[v][2 * (size_t)r];
+            }
             oc->data = exchange_buffer(ctx, P<uint8_t>(col.data), 1, sboff, sbcnt, rbytes.first, rbytes.second);
             oc->data_bytes = rbytes.first[world - 1] + rbytes.second[world - 1];
             AURON_CHECK(oc->data_bytes <= (int64_t)INT32_MAX, "utf8 column exceeds 2 GiB after the exchange");
@@ -261,7 +268,7 @@ BatchPtr nccl_exchange(Ctx& ctx, const Batch& sorted, const std::vector<int64_t>
         out->cols.push_back(oc);
     }
     ctx.sync();
-    if (bytes_sent) *bytes_sent = sent;
+    if (bytes_sent) *bytes_sent = sent * (num_parts > 0 ? 1 : world);   // (the all-gather sends every row to every rank)
     return out;
 }
 

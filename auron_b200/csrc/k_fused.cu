@@ -113,39 +113,39 @@ __device__ __forceinline__ void fz_scout_page(const FzScoutCol& C, int page_id, 
     // ---- 2a. all segments at once.  Writers emit the indices of a high-cardinality column as maximal bit-packed runs (63 groups =
     // 504 values behind a one-byte header 0x7F; parquet-cpp and parquet-mr both close a literal run there), so the stream position
     // of any value is arithmetic -- once every run header has been checked to sit where that arithmetic puts it (induction over
-    // the runs: a verified header fixes the start of the next run).  Lane s then builds segment s by itself: its non-null count
-    // from the bitmap, its first value from a warp scan, its checkpoint from the value number.  Anything else (RLE runs, short
-    // literal runs, pages of more than 32 segments, pages that went through the global bitmap) takes the serial walk below.
+    // the runs: a verified header fixes the start of the next run).  Lane s then builds segment s by itself (32 segments per
+    // round): its non-null count from the bitmap, its first value from a warp scan, its checkpoint from the value number.
+    // Anything else (RLE runs, short literal runs) takes the serial walk below.
     const int first_len = min(rows, FZ_TILE - (int)(gr0 & (FZ_TILE - 1)));
     const int nseg = 1 + (rows - first_len + FZ_TILE - 1) / FZ_TILE;
-    if (nseg <= 32 && (!has_def || use_sb)) {
-        const int r_s = lane == 0 ? 0 : first_len + ((int)lane - 1) * FZ_TILE;
-        const int m_s = (int)lane < nseg ? min(rows - r_s, lane == 0 ? first_len : FZ_TILE) : 0;
-        int nv_s = m_s;
-        if (C.max_def > 0) {
-            if (has_def) {
-                nv_s = 0;
-                if (m_s > 0) {
-                    const int w0 = r_s >> 5, w1 = (r_s + m_s - 1) >> 5;
-                    for (int w = w0; w <= w1; w++) {
-                        uint32_t x = sb[w];
-                        if (w == w0) x &= 0xffffffffu << (r_s & 31);
-                        if (w == w1) x &= 0xffffffffu >> (31 - ((r_s + m_s - 1) & 31));
-                        nv_s += __popc(x);
-                    }
-                }
-            } else if (pg.all_null) nv_s = 0;
-        }
-        int inc = nv_s;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(FULL_MASK, inc, d);
-            if ((int)lane >= d) inc += t;
-        }
-        const int total_valid = __shfl_sync(FULL_MASK, inc, 31);
-        const int v_s = inc - nv_s;
+    {
         const int bw = dict ? (pg.val_len > 0 ? (int)vals[0] : 0) : -1;
-        const int run_bytes = 1 + 63 * bw, nfull = total_valid / 504, rem = total_valid % 504, g_last = (rem + 7) / 8;
+        const int run_bytes = 1 + 63 * bw;
+        // non-null values of the page (the stream's length in values) -> where its runs must sit
+        int total_valid = rows;
+        if (C.max_def > 0) {
+            if (has_def) total_valid = 0;
+            else if (pg.all_null) total_valid = 0;
+        }
+        if (C.max_def > 0 && has_def) {
+            int c = 0;
+            if (use_sb) {
+                const int nw = (rows + 31) >> 5;   // (bits behind `rows` are zero)
+                for (int w = lane; w < nw; w += 32) c += __popc(sb[w]);
+            } else {
+                const int64_t w0 = gr0 >> 5, w1 = (gr0 + rows - 1) >> 5;
+                for (int64_t w = w0 + lane; w <= w1; w += 32) {
+                    uint32_t x = __ldcg(C.valid + w);
+                    if (w == w0) x &= 0xffffffffu << (gr0 & 31);
+                    if (w == w1) x &= 0xffffffffu >> (31 - ((gr0 + rows - 1) & 31));
+                    c += __popc(x);
+                }
+            }
+#pragma unroll
+            for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(FULL_MASK, c, d);
+            total_valid = c;
+        }
+        const int nfull = total_valid / 504, rem = total_valid % 504, g_last = (rem + 7) / 8;
         bool regular = true;
         if (dict) {
             const int64_t ilen = (int64_t)pg.val_len - 1;
@@ -157,30 +157,61 @@ __device__ __forceinline__ void fz_scout_page(const FzScoutCol& C, int page_id, 
             regular = __all_sync(FULL_MASK, regular);
         }
         if (regular) {
-            if ((int)lane < nseg) {
-                FzSeg S;
-                S.page = page_id;
-                S.row0 = r_s;
-                S.n = m_s;
-                S.nvalid = nv_s;
-                S.v0 = v_s;
-                S.idx = HybridCk{0, 0, 0, 0, 0, 1};
-                if (dict) {
-                    const int j = v_s / 504, r = v_s % 504;
-                    const int groups = j < nfull ? 63 : g_last;
-                    const int hdr = j * run_bytes;
-                    if (r == 0) S.idx = HybridCk{hdr, 0, hdr, 0, 0, 0};                                  // at a run boundary: the header is read on demand
-                    else S.idx = HybridCk{hdr + 1 + groups * bw, groups * 8 - r, hdr + 1, r, 0, 0};      // inside run j
+            int carry = 0;   // non-null values of the segments before this round
+            for (int s0 = 0; s0 < nseg; s0 += 32) {
+                const int sg = s0 + (int)lane;
+                const int r_s = sg == 0 ? 0 : first_len + (sg - 1) * FZ_TILE;
+                const int m_s = sg < nseg ? min(rows - r_s, sg == 0 ? first_len : FZ_TILE) : 0;
+                int nv_s = m_s;
+                if (C.max_def > 0) {
+                    if (has_def) {
+                        nv_s = 0;
+                        if (m_s > 0) {
+                            const int64_t b = use_sb ? (int64_t)r_s : gr0 + r_s;
+                            const int64_t w0 = b >> 5, w1 = (b + m_s - 1) >> 5;
+                            for (int64_t w = w0; w <= w1; w++) {
+                                uint32_t x = use_sb ? sb[w] : __ldcg(C.valid + w);
+                                if (w == w0) x &= 0xffffffffu << (b & 31);
+                                if (w == w1) x &= 0xffffffffu >> (31 - ((b + m_s - 1) & 31));
+                                nv_s += __popc(x);
+                            }
+                        }
+                    } else if (pg.all_null) nv_s = 0;
                 }
-                S.vals = vals;
-                S.val_len = pg.val_len;
-                S.bw = bw;
-                S.ddata = dict ? dd.data : nullptr;
-                S.ndict = dict ? dd.num_values : 0;
-                S.dict_id = pg.dict_id;
-                S.pad[0] = S.pad[1] = 0;
-                C.segs[seg + (int)lane] = S;
-                if (((gr0 + r_s) & (FZ_TILE - 1)) == 0) C.first_seg[(gr0 + r_s) / FZ_TILE] = seg + (int)lane;
+                int inc = nv_s;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(FULL_MASK, inc, d);
+                    if ((int)lane >= d) inc += t;
+                }
+                const int v_s = carry + inc - nv_s;
+                carry += __shfl_sync(FULL_MASK, inc, 31);
+                if (sg < nseg) {
+                    FzSeg S;
+                    S.page = page_id;
+                    S.row0 = r_s;
+                    S.n = m_s;
+                    S.nvalid = nv_s;
+                    S.v0 = v_s;
+                    S.idx = HybridCk{0, 0, 0, 0, 0, 1};
+                    if (dict) {
+                        const int j = v_s / 504, r = v_s % 504;
+                        const int groups = j < nfull ? 63 : g_last;
+                        const int hdr = j * run_bytes;
+                        if (r == 0) S.idx = HybridCk{hdr, 0, hdr, 0, 0, 0};                                  // at a run boundary: the header is read on demand
+                        else S.idx = HybridCk{hdr + 1 + groups * bw, groups * 8 - r, hdr + 1, r, 0, 0};      // inside run j
+                    }
+                    S.vals = vals;
+                    S.val_len = pg.val_len;
+                    S.bw = bw;
+                    S.ddata = dict ? dd.data : nullptr;
+                    S.ndict = dict ? dd.num_values : 0;
+                    S.dict_id = pg.dict_id;
+                    S.pad[0] = 1;
+                    S.pad[1] = 0;
+                    C.segs[seg + sg] = S;
+                    if (((gr0 + r_s) & (FZ_TILE - 1)) == 0) C.first_seg[(gr0 + r_s) / FZ_TILE] = seg + sg;
+                }
             }
             return;
         }
@@ -547,9 +578,10 @@ constexpr uint32_t FZ_SIG_SUM = fz_sig1(0, 1, true);                            
 constexpr uint32_t FZ_SIG_COUNT_STAR = fz_sig1(1, -1, false);                                      // COUNT(*)
 constexpr uint32_t FZ_SIG_SUM_COUNT_STAR = fz_sig1(0, 1, true) | (fz_sig1(1, -1, false) << 6);     // SUM(x), COUNT(*)
 constexpr uint32_t FZ_SIG_SUM_SUM = fz_sig1(0, 1, true) | (fz_sig1(0, 2, true) << 6);              // SUM(x), SUM(y)
-template <int NV, int NACC, bool ALLDICT, uint32_t SIG>
+// key_at(rank) -> the key's accumulator slot word (bit 31: direct table), val_at(v, rank) -> argument v's value
+template <int NV, int NACC, bool ALLDICT, uint32_t SIG, class KF, class VF>
 __device__ __forceinline__ void fz_rows_to_accs(const FzLaunch& L, uint32_t sel, uint32_t wk, int prefk, const uint32_t* wv, const int* prefv,
-                                                const uint32_t* s_plane) {
+                                                KF key_at, VF val_at) {
     constexpr int NVR = NV < 0 ? FZ_MAX_COLS - 1 : (NV == 0 ? 1 : NV);
     constexpr int NA = NACC < 0 ? FZ_MAX_ACCS : NACC;
     const int nacc = NACC < 0 ? L.nacc : NACC;
@@ -594,7 +626,7 @@ __device__ __forceinline__ void fz_rows_to_accs(const FzLaunch& L, uint32_t sel,
         sel &= sel - 1;
         const uint32_t below = (1u << i) - 1u;
         uint32_t U = null_slot;
-        if (ALLDICT || ((wk >> i) & 1u)) U = s_plane[fz_pi(prefk + __popc(wk & below))];
+        if (ALLDICT || ((wk >> i) & 1u)) U = key_at(prefk + __popc(wk & below));
         const bool dsp = ALLDICT ? true : !(U >> 31);
         const int64_t slot = (int64_t)(U & 0x7fffffffu);
         long long val[NVR];
@@ -602,7 +634,7 @@ __device__ __forceinline__ void fz_rows_to_accs(const FzLaunch& L, uint32_t sel,
 #pragma unroll
         for (int v = 0; v < NVR; v++) {
             ok[v] = (wv[v] >> i) & 1u;
-            val[v] = ok[v] ? (long long)(int32_t)s_plane[(size_t)(1 + v) * FZ_VSTRIDE + fz_pi(prefv[v] + __popc(wv[v] & below))] : 0ll;
+            val[v] = ok[v] ? (long long)(int32_t)val_at(v, prefv[v] + __popc(wv[v] & below)) : 0ll;
         }
         bool marked = false;
 #pragma unroll
@@ -632,15 +664,308 @@ __device__ __forceinline__ void fz_rows_to_accs(const FzLaunch& L, uint32_t sel,
         if (need_seen && !marked) (dsp ? L.seen_dspace : L.seen_direct)[slot] = 1;   // the group exists although no accumulator shows it
     }
 }
-// NV argument planes, NACC accumulators (compile time: the row loop is fully unrolled, descriptors come straight from the
-// constant bank); NV = -1: any shape, loops at run time
+// ------------------------------------------------------------------------------------------------ TMA-staged tiles
+// Tiles whose columns are each ONE segment of a "regular" index stream (or of a PLAIN page) need no run walk: value k of the page
+// sits at an arithmetic bit position.  For those the packed bytes of the tile -- 128 bytes per bit of width and column -- are
+// brought into shared memory with one bulk copy per column (cp.async.bulk, completion on an mbarrier; SASS UBLKCP), double
+// buffered: a persistent warp issues the copies of its next tile before it works on the current one, so global latency is off
+// the critical path, and every access to the packed stream is a shared-memory window read.  Nothing is unpacked that is not
+// used: predicate columns are decoded for the rows of the lane, key and argument columns only for the rows that pass.
+// Tiles that do not qualify (a page boundary inside the tile, RLE runs, short literal runs, wide PLAIN pages in a dictionary
+// column) are left to fz_kernel, which skips the tiles done here by evaluating the same plan.
+struct FzStagePlan {      // lane c: column c of the tile
+    const uint8_t* src;   // 16-byte aligned first byte to copy
+    int32_t bytes;        // multiple of 16, 0 = the tile holds no value of this column
+    int32_t sub;          // stream offset of src (relative to the first byte of the index stream / of the PLAIN values)
+    int32_t bw, v0, ndict, dict_id;
+    const uint8_t* ddata;
+};
+__device__ __forceinline__ bool fz_stage_plan(const FzLaunch& L, int T, unsigned lane, FzStagePlan& pl) {
+    bool ok = true;
+    pl.src = nullptr;
+    pl.bytes = 0;
+    pl.sub = 0;
+    pl.bw = 0;
+    pl.v0 = 0;
+    pl.ndict = 0;
+    pl.dict_id = 0;
+    pl.ddata = nullptr;
+    if ((int)lane < L.ncols) {
+        const FzColumn& C = L.col[lane];
+        const int n_tile = (int)min((int64_t)FZ_TILE, L.n_rows - (int64_t)T * FZ_TILE);
+        const FzSeg* sp = C.segs + __ldg(C.first_seg + T);
+        const int4 s0 = __ldg((const int4*)sp);       // page, row0, n, nvalid
+        const int4 s1 = __ldg((const int4*)sp + 1);   // v0 (2 words), ...
+        const int4 s3 = __ldg((const int4*)sp + 3);   // vals (2 words), ddata (2 words)
+        const int4 s4 = __ldg((const int4*)sp + 4);   // val_len, bw, ndict, dict_id
+        const int4 s5 = __ldg((const int4*)sp + 5);   // flags
+        const int64_t v0 = (int64_t)(((uint64_t)(uint32_t)s1.y << 32) | (uint32_t)s1.x);
+        const uint8_t* vals = (const uint8_t*)(((uint64_t)(uint32_t)s3.y << 32) | (uint32_t)s3.x);
+        const int bw = s4.y, nv = s0.w;
+        ok = C.stage_cap > 0 && s0.z == n_tile && (s5.x & 1) && (bw < 0 || (bw >= 1 && bw <= 32)) && v0 + nv < (int64_t)0x7fffffff;
+        if (ok && nv > 0) {
+            int64_t fb, lb;   // stream bytes [fb, lb) hold the tile's values
+            const uint8_t* stream;
+            if (bw < 0) {
+                stream = vals;
+                fb = 4 * v0;
+                lb = 4 * (v0 + nv);
+            } else {
+                stream = vals + 1;
+                const int64_t k1 = v0 + nv - 1, q0 = v0 / 504, q1 = k1 / 504, run_bytes = 1 + 63 * bw;
+                fb = q0 * run_bytes + 1 + (((v0 - 504 * q0) * bw) >> 3);
+                lb = q1 * run_bytes + 1 + (((k1 - 504 * q1) * bw + bw + 7) >> 3);
+            }
+            const uintptr_t a0 = (uintptr_t)(stream + fb) & ~(uintptr_t)15, a1 = ((uintptr_t)(stream + lb) + 15) & ~(uintptr_t)15;
+            pl.src = (const uint8_t*)a0;
+            pl.bytes = (int32_t)(a1 - a0);
+            pl.sub = (int32_t)((int64_t)a0 - (int64_t)(uintptr_t)stream);
+            ok = (int64_t)(a1 - a0) + 16 <= C.stage_cap && lb + (bw >= 0 ? 1 : 0) <= (int64_t)s4.x;   // (+16: the 8-byte windows read behind the last value)
+        }
+        pl.bw = bw;
+        pl.v0 = (int32_t)v0;
+        pl.ndict = s4.z;
+        pl.dict_id = s4.w;
+        pl.ddata = (const uint8_t*)(((uint64_t)(uint32_t)s3.w << 32) | (uint32_t)s3.z);
+    }
+    return __all_sync(FULL_MASK, ok);
+}
+__device__ __forceinline__ uint32_t fz_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fz_mbar_init(uint64_t* b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(fz_smem_u32(b)), "r"(count) : "memory"); }
+__device__ __forceinline__ void fz_mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fz_smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fz_mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(fz_smem_u32(b)) : "memory"); }
+__device__ __forceinline__ void fz_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(fz_smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(fz_smem_u32(b))
+                 : "memory");
+}
+// false: the phase did not complete within ~2^26 polls (a lost copy: reported, never spun on forever)
+__device__ __forceinline__ bool fz_mbar_wait(uint64_t* b, uint32_t parity) {
+    for (int spin = 0; spin < (1 << 26); spin++) {
+        uint32_t done;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(fz_smem_u32(b)), "r"(parity) : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+struct FzStaged {        // one column of the current tile, as every lane sees it
+    uint32_t st;         // shared-window address of the column's stage
+    int32_t adj;         // stream byte x sits at st + x + adj ... for run q, value r of the run: st + q * run_bytes + adj + (r * bw >> 3)
+    uint32_t bw, run_bytes, hdr_bits;   // PLAIN pages are "runs" of 504 32-bit values without a header: bw 32, run_bytes 2016
+    uint32_t mask;
+    int32_t v0, ndict;
+    bool dict;
+    uint32_t aux;        // predicate: first word of the dictionary's pass bits; key: first slot of the dictionary
+    const uint8_t* ddata;
+};
+__device__ __forceinline__ uint32_t fz_lds(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));   // (volatile: the async proxy rewrites the stage between tiles)
+    return v;
+}
+// bits [X, X + bw) of the stage, X a bit address
+__device__ __forceinline__ uint32_t fz_staged_bits(const FzStaged& S, uint32_t X) {
+    const uint32_t a = S.st + ((X >> 3) & ~3u);
+    return __funnelshift_r(fz_lds(a), fz_lds(a + 4), X & 31u) & S.mask;
+}
+// value k of the page (an index for dictionary pages, the value itself for PLAIN pages)
+__device__ __forceinline__ uint32_t fz_staged_get(const FzStaged& S, int k) {
+    const uint32_t q = (uint32_t)k / 504u, r = (uint32_t)k - q * 504u;
+    return fz_staged_bits(S, 8u * (q * S.run_bytes + (uint32_t)S.adj) + r * S.bw);
+}
 template <int NV, int NACC, uint32_t SIG>
-__global__ void __launch_bounds__(FZ_WARPS * 32) fz_kernel(const __grid_constant__ FzLaunch L) {
+__global__ void __launch_bounds__(FZ_WARPS * 32) fz_staged_kernel(const __grid_constant__ FzLaunch L, int per_warp_bytes) {
     extern __shared__ __align__(16) uint8_t fz_smem[];
     const int wid = threadIdx.x >> 5;
     const unsigned lane = threadIdx.x & 31;
-    const int T = blockIdx.x * FZ_WARPS + wid;
-    if (T >= L.n_tiles) return;
+    uint8_t* base = fz_smem + (size_t)wid * per_warp_bytes;
+    uint64_t* mbar = (uint64_t*)base;              // [2]
+    int32_t* meta = (int32_t*)(base + 16);         // [2][FZ_MAX_COLS][8]
+    uint8_t* stage0 = base + 16 + 2 * FZ_MAX_COLS * 32;
+    int my_off = 0, stage_bytes = 0;               // lane c: offset of column c inside a stage
+    for (int c = 0; c < L.ncols; c++) {
+        if (c == (int)lane) my_off = stage_bytes;
+        stage_bytes += L.col[c].stage_cap;
+    }
+    if (lane == 0) {
+        fz_mbar_init(&mbar[0], L.ncols);
+        fz_mbar_init(&mbar[1], L.ncols);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int nw = gridDim.x * FZ_WARPS;
+    auto issue = [&](int T, int s) -> bool {
+        FzStagePlan pl;
+        if (!fz_stage_plan(L, T, lane, pl)) return false;
+        if ((int)lane < L.ncols) {
+            const FzColumn& C = L.col[lane];
+            int32_t* m = meta + (s * FZ_MAX_COLS + (int)lane) * 8;
+            uint32_t aux = 0;
+            if (pl.bw >= 0 && C.role == FZ_PRED) aux = (uint32_t)__ldg(C.pass_off + pl.dict_id);
+            if (pl.bw >= 0 && C.role == FZ_KEY) aux = (uint32_t)__ldg(C.dslot_base + pl.dict_id);
+            m[0] = pl.sub;
+            m[1] = pl.bw;
+            m[2] = pl.v0;
+            m[3] = pl.ndict;
+            m[4] = (int32_t)aux;
+            m[5] = (int32_t)(uint32_t)(uintptr_t)pl.ddata;
+            m[6] = (int32_t)(uint32_t)((uintptr_t)pl.ddata >> 32);
+            if (pl.bytes > 0) {
+                fz_mbar_expect_tx(&mbar[s], (uint32_t)pl.bytes);
+                fz_bulk_load(stage0 + (size_t)s * stage_bytes + my_off, pl.src, (uint32_t)pl.bytes, &mbar[s]);
+            } else {
+                fz_mbar_arrive(&mbar[s]);
+            }
+        }
+        return true;
+    };
+    auto column = [&](int c, int s) -> FzStaged {
+        const int32_t* m = meta + (s * FZ_MAX_COLS + c) * 8;
+        FzStaged S;
+        int off = 0;
+        for (int q = 0; q < c; q++) off += L.col[q].stage_cap;
+        S.st = fz_smem_u32(stage0 + (size_t)s * stage_bytes + off);
+        const int bw = m[1];
+        S.dict = bw >= 0;
+        S.bw = S.dict ? (uint32_t)bw : 32u;
+        S.run_bytes = S.dict ? 1u + 63u * (uint32_t)bw : 2016u;
+        S.hdr_bits = S.dict ? 8u : 0u;
+        S.adj = (S.dict ? 1 : 0) - m[0];
+        S.mask = S.bw >= 32u ? 0xffffffffu : (1u << S.bw) - 1u;
+        S.v0 = m[2];
+        S.ndict = m[3];
+        S.aux = (uint32_t)m[4];
+        S.ddata = (const uint8_t*)(((uint64_t)(uint32_t)m[6] << 32) | (uint32_t)m[5]);
+        return S;
+    };
+    uint32_t phase = 0;
+    int n_done = 0;
+    int T = blockIdx.x * FZ_WARPS + wid, s = 0;
+    bool staged = T < L.n_tiles ? issue(T, 0) : false;
+    for (; T < L.n_tiles; T += nw, s ^= 1) {
+        __syncwarp();   // every lane is done with the other stage (the tile before this one)
+        const bool staged_next = T + nw < L.n_tiles ? issue(T + nw, s ^ 1) : false;
+        const bool mine = staged;
+        staged = staged_next;
+        if (!mine) {   // left to the tile kernel
+            if (lane == 0) L.left[1 + atomicAdd(L.left, 1)] = T;
+            continue;
+        }
+        if (!fz_mbar_wait(&mbar[s], (phase >> s) & 1u)) {
+            *L.oor = 2;   // (the operator restarts the scan unfused)
+            return;
+        }
+        phase ^= 1u << s;
+        n_done++;
+        const int n_tile = (int)min((int64_t)FZ_TILE, L.n_rows - (int64_t)T * FZ_TILE);
+        const int cnt = n_tile - 32 * (int)lane;
+        const uint32_t rowmask = cnt >= 32 ? 0xffffffffu : (cnt > 0 ? (1u << cnt) - 1u : 0u);
+        // ---- 1. predicates: the pass bit of every value of this lane's rows
+        uint32_t sel = rowmask;
+        for (int p = 0; p < L.npred; p++) {
+            uint32_t w;
+            int pref;
+            fz_rows(L.col[p], T, n_tile, lane, &w, &pref);
+            const FzStaged S = column(p, s);
+            const FzColumn& C = L.col[p];
+            const uint32_t* pass = C.pass_bits + S.aux;
+            uint32_t res = 0;
+            const int k0 = S.v0 + pref;
+            if (p == 0) {   // every valid row is looked at: walk the lane's values in stream order (no division per value)
+                uint32_t q = (uint32_t)k0 / 504u, r = (uint32_t)k0 - q * 504u;
+                uint32_t X = 8u * (q * S.run_bytes + (uint32_t)S.adj) + r * S.bw;
+                for (uint32_t ww = w; ww;) {
+                    const int i = __ffs(ww) - 1;
+                    ww &= ww - 1;
+                    const uint32_t raw = fz_staged_bits(S, X);
+                    X += S.bw;
+                    if (++r == 504u) {
+                        r = 0;
+                        X += S.hdr_bits;
+                    }
+                    uint32_t bit;
+                    if (S.dict) {
+                        const uint32_t e = raw < (uint32_t)S.ndict ? raw : 0u;
+                        bit = S.ndict > 0 ? (__ldg(pass + (e >> 5)) >> (e & 31)) & 1u : 0u;
+                    } else {
+                        const int64_t v = (int64_t)(int32_t)raw;
+                        bit = (v >= C.lo && v <= C.hi) ? 1u : 0u;
+                    }
+                    res |= bit << i;
+                }
+            } else {        // rows already dropped by an earlier predicate are not looked at
+                for (uint32_t ww = w & sel; ww;) {
+                    const int i = __ffs(ww) - 1;
+                    ww &= ww - 1;
+                    const uint32_t raw = fz_staged_get(S, k0 + __popc(w & ((1u << i) - 1u)));
+                    uint32_t bit;
+                    if (S.dict) {
+                        const uint32_t e = raw < (uint32_t)S.ndict ? raw : 0u;
+                        bit = S.ndict > 0 ? (__ldg(pass + (e >> 5)) >> (e & 31)) & 1u : 0u;
+                    } else {
+                        const int64_t v = (int64_t)(int32_t)raw;
+                        bit = (v >= C.lo && v <= C.hi) ? 1u : 0u;
+                    }
+                    res |= bit << i;
+                }
+            }
+            sel &= res;
+        }
+        int nsel = __popc(sel);
+#pragma unroll
+        for (int d = 16; d; d >>= 1) nsel += __shfl_xor_sync(FULL_MASK, nsel, d);
+        if (nsel == 0) continue;
+        if (lane == 0) atomicAdd(L.selected_rows, (unsigned long long)nsel);
+        // ---- 2. selected rows -> accumulators; keys and arguments are unpacked on demand
+        uint32_t wk;
+        int prefk;
+        fz_rows(L.col[L.key_col], T, n_tile, lane, &wk, &prefk);
+        const FzStaged K = column(L.key_col, s);
+        constexpr int NVR = NV < 0 ? FZ_MAX_COLS - 1 : (NV == 0 ? 1 : NV);
+        const int nplanes = L.ncols - L.npred;
+        uint32_t wv[NVR];
+        int prefv[NVR];
+        FzStaged V[NVR];
+#pragma unroll
+        for (int v = 0; v < NVR; v++) {
+            wv[v] = 0;
+            prefv[v] = 0;
+            V[v] = K;
+            if (v < (NV < 0 ? nplanes - 1 : NV)) {
+                fz_rows(L.col[L.key_col + 1 + v], T, n_tile, lane, &wv[v], &prefv[v]);
+                V[v] = column(L.key_col + 1 + v, s);
+            }
+        }
+        auto key_at = [&](int rank) -> uint32_t {
+            const uint32_t raw = fz_staged_get(K, K.v0 + rank);
+            if (K.dict) return K.aux + (raw < (uint32_t)K.ndict ? raw : 0u);
+            int64_t slot = (int64_t)(int32_t)raw - L.kmin;
+            if ((uint64_t)slot >= (uint64_t)L.range) {   // the column statistics did not cover this value
+                *L.oor = 1;
+                slot = L.range;
+            }
+            return 0x80000000u | (uint32_t)slot;
+        };
+        auto val_at = [&](int v, int rank) -> uint32_t {
+            const FzStaged& S = V[v];
+            const uint32_t raw = fz_staged_get(S, S.v0 + rank);
+            if (!S.dict) return raw;
+            if (S.ndict <= 0) return 0u;
+            const uint32_t e = raw < (uint32_t)S.ndict ? raw : 0u;
+            return ((uintptr_t)S.ddata & 3) == 0 ? __ldg((const uint32_t*)S.ddata + e) : ld_u32_unaligned(S.ddata + (int64_t)e * 4);
+        };
+        const bool dict_no_null = K.dict && __all_sync(FULL_MASK, wk == rowmask);   // NULL keys live in the direct table
+        if (dict_no_null) fz_rows_to_accs<NV, NACC, true, SIG>(L, sel, wk, prefk, wv, prefv, key_at, val_at);
+        else fz_rows_to_accs<NV, NACC, false, SIG>(L, sel, wk, prefk, wv, prefv, key_at, val_at);
+    }
+    if (lane == 0 && n_done) atomicAdd(L.selected_rows + 1, (unsigned long long)n_done);
+}
+// NV argument planes, NACC accumulators (compile time: the row loop is fully unrolled, descriptors come straight from the
+// constant bank); NV = -1: any shape, loops at run time
+template <int NV, int NACC, uint32_t SIG>
+__device__ __forceinline__ void fz_tile(const FzLaunch& L, int T, uint8_t* fz_smem, int wid, unsigned lane) {
     fz_prefetch_tile(L, T, lane);
     const int nplanes = L.ncols - L.npred;   // key + argument columns
     // per warp: [36 words pass bits][nplanes value planes]
@@ -686,8 +1011,27 @@ __global__ void __launch_bounds__(FZ_WARPS * 32) fz_kernel(const __grid_constant
     // ---- 3. selected rows -> accumulators
     const uint32_t rowmask = cnt >= 32 ? 0xffffffffu : (cnt > 0 ? (1u << cnt) - 1u : 0u);
     const bool dict_no_null = key_all_dict && __all_sync(FULL_MASK, wk == rowmask);   // NULL keys live in the direct table
-    if (dict_no_null) fz_rows_to_accs<NV, NACC, true, SIG>(L, sel, wk, prefk, wv, prefv, s_plane);
-    else fz_rows_to_accs<NV, NACC, false, SIG>(L, sel, wk, prefk, wv, prefv, s_plane);
+    auto key_at = [&](int rank) -> uint32_t { return s_plane[fz_pi(rank)]; };
+    auto val_at = [&](int v, int rank) -> uint32_t { return s_plane[(size_t)(1 + v) * FZ_VSTRIDE + fz_pi(rank)]; };
+    if (dict_no_null) fz_rows_to_accs<NV, NACC, true, SIG>(L, sel, wk, prefk, wv, prefv, key_at, val_at);
+    else fz_rows_to_accs<NV, NACC, false, SIG>(L, sel, wk, prefk, wv, prefv, key_at, val_at);
+}
+// one warp per tile; behind the staged kernel (L.staged): persistent warps over the tiles it left (L.left: count, then the tiles)
+template <int NV, int NACC, uint32_t SIG>
+__global__ void __launch_bounds__(FZ_WARPS * 32) fz_kernel(const __grid_constant__ FzLaunch L) {
+    extern __shared__ __align__(16) uint8_t fz_smem[];
+    const int wid = threadIdx.x >> 5;
+    const unsigned lane = threadIdx.x & 31;
+    if (!L.staged) {
+        const int T = blockIdx.x * FZ_WARPS + wid;
+        if (T < L.n_tiles) fz_tile<NV, NACC, SIG>(L, T, fz_smem, wid, lane);
+        return;
+    }
+    const int count = __ldg(L.left);
+    for (int i = blockIdx.x * FZ_WARPS + wid; i < count; i += gridDim.x * FZ_WARPS) {
+        fz_tile<NV, NACC, SIG>(L, __ldg(L.left + 1 + i), fz_smem, wid, lane);
+        __syncwarp();
+    }
 }
 static size_t fz_smem_bytes(int nplanes) { return (size_t)FZ_WARPS * (36 * 4 + (size_t)nplanes * FZ_VSTRIDE * 4); }
 template <int NV, int NACC, uint32_t SIG>
@@ -695,12 +1039,49 @@ static void fz_launch(Ctx& ctx, const FzLaunch& L, size_t smem) {
     static bool attr_set = false;
     if (!attr_set) {
         CUDA_OK(cudaFuncSetAttribute(fz_kernel<NV, NACC, SIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fz_smem_bytes(FZ_MAX_COLS)));
+        CUDA_OK(cudaFuncSetAttribute(fz_staged_kernel<NV, NACC, SIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
         attr_set = true;
+    }
+    if (L.staged) {
+        int stage_bytes = 0;
+        for (int c = 0; c < L.ncols; c++) stage_bytes += L.col[c].stage_cap;
+        const int per_warp = 16 + 2 * FZ_MAX_COLS * 32 + 2 * stage_bytes;
+        const size_t smem2 = (size_t)FZ_WARPS * per_warp;
+        int per_sm = 0;
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fz_staged_kernel<NV, NACC, SIG>, FZ_WARPS * 32, smem2));
+        AURON_CHECK(per_sm > 0, "the staged scan kernel does not fit an SM");
+        static int n_sm = 0;
+        if (!n_sm) CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx.device));
+        const int blocks = std::min((L.n_tiles + FZ_WARPS - 1) / FZ_WARPS, n_sm * per_sm);   // persistent warps, round robin over the tiles
+        fz_staged_kernel<NV, NACC, SIG><<<blocks, FZ_WARPS * 32, smem2, ctx.stream>>>(L, per_warp);
+        CUDA_OK(cudaGetLastError());
+        launch_count(ctx);
+        int per_sm1 = 0;
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, fz_kernel<NV, NACC, SIG>, FZ_WARPS * 32, smem));
+        fz_kernel<NV, NACC, SIG><<<std::min((L.n_tiles + FZ_WARPS - 1) / FZ_WARPS, n_sm * std::max(per_sm1, 1)), FZ_WARPS * 32, smem, ctx.stream>>>(L);
+        return;
     }
     fz_kernel<NV, NACC, SIG><<<(L.n_tiles + FZ_WARPS - 1) / FZ_WARPS, FZ_WARPS * 32, smem, ctx.stream>>>(L);
 }
-void fz_run(Ctx& ctx, const FzLaunch& L) {
-    if (L.n_tiles <= 0) return;
+void fz_run(Ctx& ctx, const FzLaunch& L0) {
+    if (L0.n_tiles <= 0) return;
+    FzLaunch L = L0;
+    {   // the staged kernel needs a stage of every column in shared memory, twice, for at least 8 warps per SM
+        int stage_bytes = 0;
+        bool all = true;
+        for (int c = 0; c < L.ncols; c++) {
+            stage_bytes += L.col[c].stage_cap;
+            all = all && L.col[c].stage_cap > 0;
+        }
+        const bool off = getenv("AURON_FUSED_NO_TMA") != nullptr;
+        L.staged = all && !off && (16 + 2 * FZ_MAX_COLS * 32 + 2 * stage_bytes) * 8 <= (200 << 10) ? 1 : 0;
+    }
+    Buf left;   // tiles the staged kernel leaves to the tile kernel: [0] count, then the tile numbers
+    if (L.staged) {
+        left = dalloc(ctx, ((size_t)L.n_tiles + 1) * 4);
+        CUDA_OK(cudaMemsetAsync(left->ptr, 0, 4, ctx.stream));
+        L.left = P<int32_t>(left);
+    }
     const int nplanes = L.ncols - L.npred, nv = nplanes - 1;
     const size_t smem = fz_smem_bytes(nplanes);
     // signature of the accumulator list (see fz_rows_to_accs)

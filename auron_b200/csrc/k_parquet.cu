@@ -519,6 +519,107 @@ __global__ void __launch_bounds__(PQ_WARPS * 32) pq_decode_tiles_fast_kernel(PqL
     }
 }
 
+// ---------------------------------------------------------------------------------------------- DELTA_BINARY_PACKED -> PLAIN
+// Parquet's delta encoding (Encodings.md, "Delta Encoding"): header = block size, miniblocks per block, total count (ULEB128), first
+// value (zigzag ULEB128); every block = min delta (zigzag ULEB128), one bit-width byte per miniblock, then the miniblocks, each
+// (block size / miniblocks) deltas bit-packed LSB first.  value[i] = value[i - 1] + min_delta + packed[i] in wrapping arithmetic.
+// One warp per page walks the blocks in order (a block's position depends on the widths of the one before); inside a miniblock
+// the lanes unpack 32 deltas at a time and a warp scan turns them into values.
+__device__ __forceinline__ bool dl_varint(const uint8_t* p, int64_t n, int64_t& pos, uint64_t& v) {
+    v = 0;
+    for (int shift = 0; shift < 70; shift += 7) {
+        if (pos >= n) return false;
+        const uint8_t b = p[pos++];
+        v |= (uint64_t)(b & 0x7f) << shift;
+        if (!(b & 0x80)) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ int64_t dl_zigzag(uint64_t v) { return (int64_t)(v >> 1) ^ -(int64_t)(v & 1); }
+__global__ void __launch_bounds__(128) pq_delta_to_plain_kernel(PqPage* __restrict__ pages, int n_pages, uint8_t* __restrict__ scratch, int width, int32_t* __restrict__ status) {
+    const int pi = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (pi >= n_pages) return;
+    const unsigned lane = threadIdx.x & 31;
+    PqPage pg = pages[pi];
+    if (pg.delta_dst16 == 0) return;
+    uint8_t* dst = scratch + 16 * (int64_t)(pg.delta_dst16 - 1);
+    const uint8_t* p = pg.val_ptr;
+    const int64_t n = pg.val_len;
+    int64_t pos = 0;
+    uint64_t block_size = 0, n_mini = 0, total = 0, fv = 0;
+    bool ok = dl_varint(p, n, pos, block_size) && dl_varint(p, n, pos, n_mini) && dl_varint(p, n, pos, total) && dl_varint(p, n, pos, fv);
+    ok = ok && n_mini > 0 && n_mini <= 512 && block_size > 0 && block_size <= (1u << 20) && block_size % n_mini == 0 && (block_size / n_mini) % 32 == 0 &&
+         total <= (uint64_t)pg.num_values;
+    const int per_mini = ok ? (int)(block_size / n_mini) : 32;
+    int64_t last = dl_zigzag(fv);   // value before the next delta
+    int64_t done = 0;
+    if (ok && total > 0) {
+        if (lane == 0) {
+            if (width == 4) ((int32_t*)dst)[0] = (int32_t)last;
+            else ((int64_t*)dst)[0] = last;
+        }
+        done = 1;
+    }
+    while (ok && done < (int64_t)total) {
+        uint64_t md = 0;
+        if (!dl_varint(p, n, pos, md) || pos + (int64_t)n_mini > n) {
+            ok = false;
+            break;
+        }
+        const int64_t min_delta = dl_zigzag(md);
+        const uint8_t* widths = p + pos;
+        pos += (int64_t)n_mini;
+        for (int m = 0; m < (int)n_mini && done < (int64_t)total; m++) {
+            const int bw = widths[m];
+            const int64_t bytes = (int64_t)per_mini * bw / 8;
+            if (bw > 64 || pos + bytes > n) {
+                ok = false;
+                break;
+            }
+            for (int g = 0; g < per_mini && done < (int64_t)total; g += 32) {
+                uint64_t d = 0;
+                if (bw) {   // packed value g + lane: bits [(g + lane) * bw, +bw) of the miniblock
+                    const int64_t bit = (int64_t)(g + (int)lane) * bw;
+                    const uint8_t* q = p + pos + (bit >> 3);
+                    const int sh = (int)(bit & 7), nb = (sh + bw + 7) >> 3;   // <= 9 bytes
+                    uint64_t lo = 0;
+                    for (int k = 0; k < nb && k < 8; k++) lo |= (uint64_t)q[k] << (8 * k);
+                    d = lo >> sh;
+                    if (nb > 8) d |= (uint64_t)q[8] << (64 - sh);
+                    if (bw < 64) d &= (1ull << bw) - 1ull;
+                }
+                int64_t x = (int64_t)((uint64_t)min_delta + d);   // this lane's delta; inclusive scan -> offset from `last`
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int64_t y = __shfl_up_sync(FULL_MASK, x, o);
+                    if ((int)lane >= o) x = (int64_t)((uint64_t)x + (uint64_t)y);
+                }
+                const int64_t v = (int64_t)((uint64_t)last + (uint64_t)x);
+                if (done + (int64_t)lane < (int64_t)total) {
+                    if (width == 4) ((int32_t*)dst)[done + lane] = (int32_t)v;
+                    else ((int64_t*)dst)[done + lane] = v;
+                }
+                last = __shfl_sync(FULL_MASK, v, 31);
+                done += 32;
+            }
+            pos += bytes;
+        }
+    }
+    if (lane == 0) {
+        if (!ok) atomicCAS(status, 0, 0x40000000 + pi);
+        pg.val_ptr = dst;
+        pg.val_len = ok ? (int32_t)min((uint64_t)INT32_MAX, total * (uint64_t)width) : 0;
+        pg.delta_dst16 = 0;
+        pages[pi] = pg;
+    }
+}
+void pq_delta_to_plain(Ctx& ctx, PqPage* pages, int n, uint8_t* scratch, int width, int32_t* status) {
+    if (n <= 0) return;
+    ProfScope ps(ctx, "pq_delta_to_plain");
+    pq_delta_to_plain_kernel<<<(n + 3) / 4, 128, 0, ctx.stream>>>(pages, n, scratch, width, status);
+    LAUNCH_CHECK(ctx);
+}
+
 PqPrepared pq_prepare(Ctx& ctx, const PqColumnArgs& a, const std::vector<PqPage>& host_pages) {
     PqPrepared pr;
     pr.a = a;

@@ -804,9 +804,11 @@ BatchPtr AggExec::next(Task& t) {
                     input_done = false;
                     break;
                 }
-                unsigned long long sel_rows = 0;
-                to_host(t.ctx, &sel_rows, fused_state.selected->ptr, 8);
+                unsigned long long counters[2] = {0, 0};   // rows that passed the predicates, tiles done by the TMA-staged kernel
+                to_host(t.ctx, counters, fused_state.selected->ptr, 16);
+                const unsigned long long sel_rows = counters[0];
                 if (fused_filter) fused_filter->metrics.add("output_rows", (int64_t)sel_rows);
+                metrics.add("fused_staged_tiles", (int64_t)counters[1]);
                 metrics.add("fused_scan_rows", fused_state.rows);
                 const DType key_type = has_widened_key ? widened_key_type : children[0]->out_schema.fields[(size_t)fused_spec.key_col].type;
                 GroupedResult g = direct_agg_finish(t.ctx, *fused_state.table, key_type, fused_state.key_nullable);

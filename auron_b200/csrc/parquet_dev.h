@@ -15,7 +15,8 @@ struct PqPage {
     int32_t all_null;
     int32_t plain_value_base; // strings: position of this page's first PLAIN value in the chunk value table
     int32_t job;              // v1 page decompressed on the device: index of its PqDecompJob / PqDecompResult, else -1
-    int32_t pad;
+    int32_t delta_dst16;      // DELTA_BINARY_PACKED page: 1 + (offset / 16) of its PLAIN transcription in the batch's scratch buffer
+                              // (pq_delta_to_plain rewrites val_ptr / val_len; `encoding` already says PLAIN), 0 = none
 };
 struct PqDict {
     const uint8_t* data;      // PLAIN-encoded fixed-width dictionary values
@@ -65,6 +66,9 @@ struct PqDecompOut {
 PqDecompOut pq_decompress(Ctx& ctx, const std::vector<PqDecompJob>& jobs);
 // pages with def_len == -1: level / value sections from the body's length word (+ in-place value sections, see above)
 void pq_fix_v1_pages(Ctx& ctx, PqPage* pages, int n, const PqDecompResult* results);
+// pages with delta_dst16 != 0: DELTA_BINARY_PACKED values (width 4 or 8 bytes) -> PLAIN values at scratch + 16 (delta_dst16 - 1);
+// status (int32, may be the decompression status word) is set to 0x40000000 + page when a stream is malformed
+void pq_delta_to_plain(Ctx& ctx, PqPage* pages, int n, uint8_t* scratch, int width, int32_t* status);
 
 // scout + decode of one column; or in three steps, so that one scout launch serves every column of a batch
 void pq_decode_pages(Ctx& ctx, const PqColumnArgs& a, const std::vector<PqPage>& host_pages);
@@ -102,7 +106,8 @@ struct FzSeg {                    // rows [row0, row0 + n) of one page, all insi
     const uint8_t* ddata;            // dictionary pages: PLAIN values of the dictionary
     int32_t val_len, bw;             // bw = bit width of the indices, -1 = PLAIN page
     int32_t ndict, dict_id;
-    int64_t pad[2];
+    int64_t pad[2];                  // pad[0] bit 0: the index stream is "regular" (only full 63-group bit-packed runs before a last shorter
+                                     // one, each behind a one-byte header), or the page is PLAIN: value k sits at an arithmetic position
 };
 static_assert(sizeof(FzSeg) == 96, "FzSeg is read with 16-byte vector loads");
 struct FzScoutCol {               // one physical column to scout
@@ -121,7 +126,8 @@ struct FzColumn {                 // one role-column of the fused kernel
     const FzSeg* segs;
     const int32_t* first_seg;
     const uint32_t* valid;
-    int32_t role, pad;
+    int32_t role;
+    int32_t stage_cap;            // bytes of shared memory one tile of this column may occupy in the TMA-staged kernel (0 = never staged)
     int64_t lo, hi;               // FZ_PRED: closed interval the value must lie in (NULL never passes)
     const uint32_t* pass_bits;    // FZ_PRED: the interval test evaluated on every dictionary entry, one bit each
     const int32_t* pass_off;      //          [n_dicts] first word of each dictionary in pass_bits
@@ -140,13 +146,15 @@ struct FzLaunch {
     FzAcc acc[FZ_MAX_ACCS];
     int32_t ncols, npred, key_col, nacc;
     int64_t n_rows;
-    int32_t n_tiles, pad;
+    int32_t n_tiles;
+    int32_t staged;                       // 1: tiles that qualify are done by the TMA-staged kernel, the tile kernel skips them
     long long kmin;
     int64_t range;
     uint8_t* seen_direct;
     uint8_t* seen_dspace;
     int32_t* oor;                         // a key outside [kmin, kmin + range): the column statistics were wrong
-    unsigned long long* selected_rows;    // rows that passed the predicates (FilterExec's output_rows)
+    unsigned long long* selected_rows;    // [0] rows that passed the predicates (FilterExec's output_rows), [1] tiles done by the staged kernel
+    int32_t* left;                        // staged mode: [0] number of tiles left to the tile kernel, then their numbers
 };
 struct FzMerge {                  // dictionary space -> direct table, one launch per batch
     const PqDict* dicts;

@@ -357,6 +357,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
         std::vector<PqDecompJob> jobs;
         int64_t gpu_unc_bytes = 0;
         bool has_v1_inline = false;
+        bool has_delta = false;   // some pages are DELTA_BINARY_PACKED: transcribed to PLAIN in the scratch buffer (pq_delta_to_plain)
     };
     struct ChunkTask {
         std::shared_ptr<FileState> file;
@@ -385,6 +386,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
         std::vector<Buf> keep;
         bool has_v1_inline = false;   // some v1 pages still need their level / value sections split on the device
         bool needs_decomp = false;    // some pages of this column are produced by the batch's decompression launch
+        bool has_delta = false;
         // bounds of the non-null values from the column-chunk statistics of every chunk in the batch (INT32 / INT64)
         bool stat_ok = true;
         int64_t stat_min = INT64_MAX, stat_max = INT64_MIN;
@@ -528,6 +530,77 @@ struct ParquetScanExec : Operator, FusedScanSource {
         }
         return out == unc;
     }
+    // ---- DELTA_LENGTH_BYTE_ARRAY / DELTA_BYTE_ARRAY string pages are rewritten as PLAIN on the host (each value of the second
+    // depends on the bytes of the one before it; both are rare next to dictionary and PLAIN pages)
+    static bool delta_varint(const uint8_t* p, size_t n, size_t& pos, uint64_t& v) {
+        v = 0;
+        for (int shift = 0; shift < 70; shift += 7) {
+            if (pos >= n) return false;
+            const uint8_t b = p[pos++];
+            v |= (uint64_t)(b & 0x7f) << shift;
+            if (!(b & 0x80)) return true;
+        }
+        return false;
+    }
+    // one DELTA_BINARY_PACKED stream at p[pos...] -> values; pos ends behind the stream
+    static void delta_binary_decode(const uint8_t* p, size_t n, size_t& pos, std::vector<int64_t>& out) {
+        uint64_t bs = 0, nm = 0, total = 0, fv = 0;
+        AURON_CHECK(delta_varint(p, n, pos, bs) && delta_varint(p, n, pos, nm) && delta_varint(p, n, pos, total) && delta_varint(p, n, pos, fv), "corrupt DELTA_BINARY_PACKED header");
+        AURON_CHECK(nm > 0 && nm <= 512 && bs > 0 && bs <= (1u << 20) && bs % nm == 0 && (bs / nm) % 8 == 0 && total <= (1ull << 31), "corrupt DELTA_BINARY_PACKED header");
+        const size_t per_mini = (size_t)(bs / nm);
+        out.clear();
+        out.reserve((size_t)total);
+        uint64_t last = (fv >> 1) ^ (0 - (fv & 1));
+        if (total) out.push_back((int64_t)last);
+        while (out.size() < total) {
+            uint64_t md = 0;
+            AURON_CHECK(delta_varint(p, n, pos, md) && pos + nm <= n, "corrupt DELTA_BINARY_PACKED block");
+            const uint64_t min_delta = (md >> 1) ^ (0 - (md & 1));
+            const uint8_t* widths = p + pos;
+            pos += (size_t)nm;
+            for (size_t m = 0; m < nm && out.size() < total; m++) {
+                const unsigned bw = widths[m];
+                const size_t bytes = per_mini * bw / 8;
+                AURON_CHECK(bw <= 64 && pos + bytes <= n, "corrupt DELTA_BINARY_PACKED miniblock");
+                for (size_t i = 0; i < per_mini && out.size() < total; i++) {
+                    uint64_t d = 0;
+                    const size_t bit = i * bw;
+                    for (unsigned k = 0; k < bw; k++) {
+                        const size_t b = bit + k;
+                        d |= (uint64_t)((p[pos + (b >> 3)] >> (b & 7)) & 1) << k;
+                    }
+                    last += min_delta + d;
+                    out.push_back((int64_t)last);
+                }
+                pos += bytes;
+            }
+        }
+    }
+    // value section of a DELTA_LENGTH_BYTE_ARRAY (`front_coded` false) or DELTA_BYTE_ARRAY page -> PLAIN ([u32 length][bytes] ...)
+    static std::vector<uint8_t> delta_strings_to_plain(const uint8_t* p, size_t n, bool front_coded, int32_t* n_values) {
+        size_t pos = 0;
+        std::vector<int64_t> prefix, lens;
+        if (front_coded) delta_binary_decode(p, n, pos, prefix);
+        delta_binary_decode(p, n, pos, lens);
+        AURON_CHECK(!front_coded || prefix.size() == lens.size(), "corrupt DELTA_BYTE_ARRAY page");
+        std::vector<uint8_t> out;
+        size_t prev_at = 0, prev_len = 0;
+        for (size_t i = 0; i < lens.size(); i++) {
+            const int64_t pl = front_coded ? prefix[i] : 0, sl = lens[i];
+            AURON_CHECK(pl >= 0 && sl >= 0 && (size_t)pl <= prev_len && (size_t)sl <= n - pos && pl + sl <= INT32_MAX, "corrupt delta-encoded string page");
+            const uint32_t len = (uint32_t)(pl + sl);
+            const size_t at = out.size();
+            out.resize(at + 4 + len);
+            memcpy(out.data() + at, &len, 4);
+            if (pl) memmove(out.data() + at + 4, out.data() + prev_at + 4, (size_t)pl);
+            memcpy(out.data() + at + 4 + pl, p + pos, (size_t)sl);
+            pos += (size_t)sl;
+            prev_at = at;
+            prev_len = len;
+        }
+        *n_values = (int32_t)lens.size();
+        return out;
+    }
     static bool gpu_snappy() {
         return getenv("AURON_HOST_SNAPPY") == nullptr;   // AURON_HOST_SNAPPY=1: decompress on the host cores instead
     }
@@ -557,7 +630,8 @@ struct ParquetScanExec : Operator, FusedScanSource {
             // Where the page body ends up: in place (uncompressed, or "stored" below), decompressed on the device (Snappy), or
             // decompressed on the host (other codecs; and the one Snappy case whose levels the host must see: a PLAIN string
             // page needs its non-null count to place its values, which a nullable v1 page only has inside its body).
-            const bool page_dev = dev_snappy && !(is_string && h.type == pq::PAGE_DATA && h.encoding == pq::ENC_PLAIN && max_def > 0);
+            const bool delta_strings = is_string && (h.encoding == pq::ENC_DELTA_LENGTH_BYTE_ARRAY || h.encoding == pq::ENC_DELTA_BYTE_ARRAY);
+            const bool page_dev = dev_snappy && !(is_string && h.type == pq::PAGE_DATA && h.encoding == pq::ENC_PLAIN && max_def > 0) && !delta_strings;
             bool on_device = false;
             int64_t gap = 0;   // stored v2 page with level sections: Snappy framing bytes between the levels and the values
             if (page_compressed && page_dev) {
@@ -639,10 +713,18 @@ struct ParquetScanExec : Operator, FusedScanSource {
             pg.row_start = (int32_t)rows;
             pg.encoding = h.encoding;
             pg.dict_id = cur_dict;
+            const bool delta_ints = h.encoding == pq::ENC_DELTA_BINARY_PACKED && (el.type == pq::PT_INT32 || el.type == pq::PT_INT64);
             AURON_CHECK(h.encoding == pq::ENC_PLAIN || ((h.encoding == pq::ENC_RLE_DICTIONARY || h.encoding == pq::ENC_PLAIN_DICTIONARY) && cur_dict >= 0) ||
-                            (h.encoding == pq::ENC_RLE && el.type == pq::PT_BOOLEAN),
-                        "parquet encoding " + std::to_string(h.encoding) + " is not supported on device (PLAIN / RLE_DICTIONARY are)");
+                            (h.encoding == pq::ENC_RLE && el.type == pq::PT_BOOLEAN) || delta_ints || delta_strings,
+                        "parquet encoding " + std::to_string(h.encoding) + " is not supported (PLAIN, RLE_DICTIONARY, RLE booleans and the DELTA encodings are)");
+            if (delta_ints) {   // transcribed on the device, after the sections of the page are known (pq_delta_to_plain)
+                pg.encoding = pq::ENC_PLAIN;
+                pg.delta_dst16 = (int32_t)(out.gpu_unc_bytes / 16) + 1;
+                out.gpu_unc_bytes += ((int64_t)h.num_values * (el.type == pq::PT_INT32 ? 4 : 8) + 16 + 15) & ~(int64_t)15;
+                out.has_delta = true;
+            }
             int64_t o = 0, total = h.uncompressed_size;
+            int32_t delta_nn = -1;   // non-null values of a delta-encoded string page (its streams say so)
             if (h.type == pq::PAGE_DATA) {
                 if (max_def > 0) {
                     AURON_CHECK(h.def_encoding == pq::ENC_RLE, "only RLE definition levels are supported");
@@ -671,6 +753,19 @@ struct ParquetScanExec : Operator, FusedScanSource {
                 o += h.def_bytes;
             }
             AURON_CHECK(o <= total, "corrupt parquet page levels");
+            if (delta_strings) {   // (never on_device: the body is on the host, in the file image or in out.unc)
+                const std::vector<uint8_t> head(hp(0), hp(0) + o);
+                int32_t nn = 0;
+                const std::vector<uint8_t> plain = delta_strings_to_plain(hp(o + gap), (size_t)(total - o - gap), h.encoding == pq::ENC_DELTA_BYTE_ARRAY, &nn);
+                unc_off = (int64_t)out.unc.size();
+                out.unc.resize(out.unc.size() + head.size() + plain.size() + 8);
+                if (!head.empty()) memcpy(out.unc.data() + unc_off, head.data(), head.size());
+                if (!plain.empty()) memcpy(out.unc.data() + unc_off + o, plain.data(), plain.size());
+                total = o + (int64_t)plain.size();
+                gap = 0;
+                pg.encoding = pq::ENC_PLAIN;
+                delta_nn = nn;
+            }
             int64_t val_off = o + gap;
             pg.val_len = (int32_t)(total - o);   // v1 inline: the whole body until the device splits it
             const uint8_t* base_d = unc_off >= 0 ? nullptr : payload_d;
@@ -681,9 +776,9 @@ struct ParquetScanExec : Operator, FusedScanSource {
                 pg.val_ptr = (const uint8_t*)(intptr_t)val_off;
             }
             size_t sec_idx = SIZE_MAX;
-            if (is_string && h.encoding == pq::ENC_PLAIN) {
+            if (is_string && pg.encoding == pq::ENC_PLAIN) {
                 // PLAIN string pages need their exact non-null count: v2 gives it, v1 requires the def levels
-                int32_t nn = h.type == pq::PAGE_DATA_V2 ? h.num_values - h.num_nulls : count_non_null_v1(hp(0), max_def, h.num_values);
+                int32_t nn = delta_nn >= 0 ? delta_nn : h.type == pq::PAGE_DATA_V2 ? h.num_values - h.num_nulls : count_non_null_v1(hp(0), max_def, h.num_values);
                 pg.plain_value_base = (int32_t)out.value_table_size;
                 sec_idx = out.secs.size();
                 out.secs.push_back({base_d ? pg.val_ptr : nullptr, pg.val_len, nn, (int32_t)out.value_table_size});
@@ -722,6 +817,8 @@ struct ParquetScanExec : Operator, FusedScanSource {
     }
 
     const PqDecompResult* decomp_results = nullptr;   // results of the current batch's decompression launch (device)
+    uint8_t* unc_scratch_ptr = nullptr;               // the current batch's scratch buffer and status word (device)
+    int32_t* status_ptr = nullptr;
     cudaEvent_t decomp_done = nullptr;                // recorded on the decompression lane (nullptr: nothing to wait for)
     // Side streams ("lanes"): the decompress -> scout -> decode chains of a batch's columns are independent, and each of
     // these kernels leaves most of the GPU idle on its own (latency-bound header walks, L1-bound gathers), so the chains
@@ -829,6 +926,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
             Buf dpages = to_device(wc, cs.pages.data(), cs.pages.size() * sizeof(PqPage));
             Buf ddicts = to_device(wc, cs.dicts.empty() ? (const void*)"" : (const void*)cs.dicts.data(), cs.dicts.size() * sizeof(PqDict));
             if (cs.has_v1_inline) pq_fix_v1_pages(wc, P<PqPage>(dpages), (int)cs.pages.size(), decomp_results);
+            if (cs.has_delta) pq_delta_to_plain(wc, P<PqPage>(dpages), (int)cs.pages.size(), unc_scratch_ptr, el.type == pq::PT_INT32 ? 4 : 8, status_ptr);
             a.pages = P<PqPage>(dpages);
             a.dicts = P<PqDict>(ddicts);
             a.n_pages = (int)cs.pages.size();
@@ -1271,6 +1369,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
             cs.value_table_size += cp.value_table_size;
             if (cp.gpu_unc_bytes > 0) {
                 cs.has_v1_inline = cs.has_v1_inline || cp.has_v1_inline;
+                cs.has_delta = cs.has_delta || cp.has_delta;
                 cs.needs_decomp = true;
             }
             {   // statistics -> value bounds (Statistics.min_value / max_value are PLAIN-encoded: little-endian two's complement)
@@ -1358,6 +1457,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
             for (size_t i = 0; i < cp.pages.size(); i++) {
                 PqPage pg = cp.pages[i];
                 if (pg.dict_id >= 0) pg.dict_id += (int32_t)sl.dict_base;
+                if (pg.delta_dst16) pg.delta_dst16 += (int32_t)(sl.unc_off / 16);
                 pg.plain_value_base += sl.vbase;
                 dst[i] = pg;
             }
@@ -1368,7 +1468,11 @@ struct ParquetScanExec : Operator, FusedScanSource {
             if (&dc != &wc) chain(wc.stream, dc.stream);   // scratch allocated, chunk bytes uploaded
             PqDecompOut dec = pq_decompress(dc, decomp_jobs);
             sg.status = dec.status;
-            sg.has_jobs = !decomp_jobs.empty();
+            bool any_delta = false;
+            for (auto& cs : p.cols) any_delta = any_delta || cs.has_delta;
+            sg.has_jobs = !decomp_jobs.empty() || any_delta;
+            unc_scratch_ptr = unc_scratch ? P<uint8_t>(unc_scratch) : nullptr;
+            status_ptr = P<int32_t>(dec.status);
             decomp_results_buf = dec.results;
             decomp_results = P<PqDecompResult>(dec.results);
             if (&dc != &wc) {
@@ -1385,7 +1489,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
         if (!sg.has_jobs) return;
         int32_t st = 0;
         to_host(t.ctx, &st, sg.status->ptr, 4);
-        AURON_CHECK(st == 0, "corrupt Snappy page in the parquet file (decompression job " + std::to_string(st - 1) + ")");
+        AURON_CHECK(st == 0, st >= 0x40000000 ? std::string("corrupt DELTA_BINARY_PACKED page in the parquet file") : "corrupt Snappy page in the parquet file (decompression job " + std::to_string(st - 1) + ")");
     }
 
     BatchPtr next(Task& t) override {
@@ -1479,7 +1583,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
         if (f->sg.has_jobs) {
             int32_t st = 0;
             CUDA_OK(cudaMemcpy(&st, f->sg.status->ptr, 4, cudaMemcpyDeviceToHost));   // the batch is complete: plain copy, no stream involved
-            AURON_CHECK(st == 0, "corrupt Snappy page in the parquet file (decompression job " + std::to_string(st - 1) + ")");
+            AURON_CHECK(st == 0, st >= 0x40000000 ? std::string("corrupt DELTA_BINARY_PACKED page in the parquet file") : "corrupt Snappy page in the parquet file (decompression job " + std::to_string(st - 1) + ")");
         }
     }
     void retire_fused(Task& t) {
@@ -1617,6 +1721,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
             x.dpages = to_device(wc, cs.pages.data(), cs.pages.size() * sizeof(PqPage));
             x.ddicts = to_device(wc, cs.dicts.empty() ? (const void*)"" : (const void*)cs.dicts.data(), cs.dicts.size() * sizeof(PqDict));
             if (cs.has_v1_inline) pq_fix_v1_pages(wc, P<PqPage>(x.dpages), (int)cs.pages.size(), decomp_results);
+            if (cs.has_delta) pq_delta_to_plain(wc, P<PqPage>(x.dpages), (int)cs.pages.size(), unc_scratch_ptr, cs.el.type == pq::PT_INT32 ? 4 : 8, status_ptr);
             std::vector<int32_t> sb(cs.pages.size() + 1, 0);
             for (size_t i = 0; i < cs.pages.size(); i++) {
                 const int64_t r0 = cs.pages[i].row_start, n = cs.pages[i].num_values;
@@ -1653,6 +1758,17 @@ struct ParquetScanExec : Operator, FusedScanSource {
             C.first_seg = P<int32_t>(x.first_seg);
             C.valid = P<uint32_t>(x.valid);
             C.role = role;
+            {   // shared memory for one tile of the column in the TMA-staged kernel: 128 bytes per bit of index width (the writer's
+                // width is that of the largest index), run headers, 16-byte alignment at both ends and the window slack; PLAIN pages
+                // of a dictionary column are wider than that and stay with the tile kernel
+                const ColState& cs = p.cols[(size_t)c];
+                int32_t max_dict = 0;
+                for (auto& d : cs.dicts) max_dict = std::max(max_dict, d.num_values);
+                int bits = 1;
+                while (bits < 32 && (1ll << bits) < (int64_t)max_dict) bits++;
+                C.stage_cap = cs.dicts.empty() ? 4 * FZ_TILE + 48 : 128 * bits + 64;
+                if (cs.el.type != pq::PT_INT32) C.stage_cap = 0;
+            }
             return L.ncols++;
         };
         for (size_t i = 0; i < spec.pred_cols.size(); i++) {
@@ -1704,7 +1820,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
                     specs.push_back(s);
                 }
                 st.table = direct_agg_create(t.ctx, specs, umin, umax);
-                st.selected = dalloc_zero(t.ctx, 8);
+                st.selected = dalloc_zero(t.ctx, 16);   // [0] rows that passed the predicates, [1] tiles done by the TMA-staged kernel
             } else {
                 direct_agg_grow(t.ctx, *st.table, umin, umax);
             }

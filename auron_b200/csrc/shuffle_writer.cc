@@ -342,7 +342,9 @@ struct ShuffleWriterExec : Operator {
     }
 
     // in-box repartition: output_data_file = "nccl://<name>" turns the writer into an exchange whose output stream is
-    // the set of rows this rank owns after the all-to-all (so the next stage can be chained in the same task plan)
+    // the set of rows this rank owns after the all-to-all (so the next stage can be chained in the same task plan);
+    // "nccl-bcast://<name>" is the broadcast exchange (BroadcastExchangeExec on the Spark side: the build side of a broadcast
+    // join is collected from every partition and replicated) as an all-gather-v over NVLink
     BatchPtr exchange(Task& t) {
         std::vector<BatchPtr> all;
         while (BatchPtr b = children[0]->next(t)) {
@@ -356,6 +358,17 @@ struct ShuffleWriterExec : Operator {
         } else in = concat_batches(t.ctx, all);
         all.clear();
         int64_t n = in->num_rows;
+        if (data_file.rfind("nccl-bcast://", 0) == 0) {   // broadcast exchange: every rank ends up with the rows of all ranks
+            int64_t sent = 0;
+            BatchPtr out;
+            {
+                OpTimer timer(metrics, "exchange_ns");
+                out = nccl_exchange(t.ctx, *in, {}, 0, &sent);
+            }
+            metrics.add("data_size", sent);
+            metrics.add("output_rows", out->num_rows);
+            return out;
+        }
         AURON_CHECK(kind == 2, "the NCCL exchange implements hash repartitioning");
         std::vector<ColumnPtr> keys;
         for (auto& e : hash_exprs) keys.push_back(eval_to_column(t, e, children[0]->out_schema, *in));
@@ -403,7 +416,7 @@ struct ShuffleWriterExec : Operator {
             metrics.add("output_rows", rows_so_far);
             return nullptr;
         }
-        if (data_file.rfind("nccl://", 0) == 0) return exchange(t);
+        if (data_file.rfind("nccl://", 0) == 0 || data_file.rfind("nccl-bcast://", 0) == 0) return exchange(t);
         while (BatchPtr b = children[0]->next(t)) {
             AURON_CHECK(t.is_running(), "task killed");
             if (b->num_rows == 0) continue;

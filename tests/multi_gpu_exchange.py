@@ -7,6 +7,9 @@ all-to-all-v over NVLink (exchange.cu), and each rank finishes the groups of the
 the per-rank results and checks (a) the union equals the oracle's aggregate over all shards, (b) every group landed on
 the rank that owns its Spark partition id (pmod(murmur3(k, 42), P) * world / P).
 
+A second task checks the broadcast exchange ("nccl-bcast://", an all-gather-v): every rank holds a slice of a dimension table,
+collects the whole of it over NVLink and joins its own shard against it.
+
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_exchange.py
 """
 import os
@@ -86,6 +89,33 @@ def main():
             print(f"[rank {r}] groups={len(keys)} step={secs * 1e3:.1f} ms {m}")
         ok = got == exp
         print("EXCHANGE_OK" if ok else f"EXCHANGE_MISMATCH got={len(got)} exp={len(exp)}")
+    # ---- broadcast exchange: the build side of a join lives in slices on the ranks ("nccl-bcast://": all-gather-v over NVLink),
+    # every rank joins its own shard against the whole of it
+    dim_ids = np.arange(rank, 50_000, world, dtype=np.int64)            # rank r holds the ids congruent to r
+    dim = pa.table({"id": pa.array(dim_ids), "label": pa.array([f"item-{int(i) % 97}" for i in dim_ids]),
+                    "w": pa.array((dim_ids * 7 % 1000).astype(np.int64), mask=dim_ids % 11 == 0)})
+    bcast = P.shuffle_writer(P.ffi_reader(dim.schema, "dim"), P.single_repartition(1), "nccl-bcast://dim", "")
+    js = pa.schema(list(t.schema) + list(dim.schema))
+    join = P.hash_join(js, P.ffi_reader(t.schema, "shard"), bcast, [(P.col("k"), P.col("id"))], "INNER", "RIGHT")
+    agg = P.agg(join, [P.col("label")], ["label"], [P.agg_expr("COUNT", [P.col("k")], pa.int64()), P.agg_expr("SUM", [P.col("w")], pa.int64())], ["c", "sw"],
+                ["PARTIAL"] * 2)
+    with runtime.Task(P.task_definition(agg, stage_id=3, partition_id=rank), {"shard": t.to_batches(), "dim": dim.to_batches()}, device=local) as task:
+        jout = pa.Table.from_batches(list(task), schema=task.schema)
+    got_j = {l: (c, sw) for l, c, sw in zip(jout["label"].to_pylist(), jout["c"].to_pylist(), jout["sw"].to_pylist())}
+    exp_j = {}
+    for k in t["k"].to_pylist():
+        if k is None:
+            continue
+        a = exp_j.setdefault(f"item-{k % 97}", [0, None])
+        a[0] += 1
+        if k % 11 != 0:
+            a[1] = (a[1] or 0) + k * 7 % 1000
+    bok = got_j == {l: (c, sw) for l, (c, sw) in exp_j.items()}
+    flags = [None] * world if rank == 0 else None
+    dist.gather_object(bok, flags, dst=0)
+    if rank == 0:
+        print("BROADCAST_OK" if all(flags) else f"BROADCAST_MISMATCH {flags}")
+        ok = ok and all(flags)
     runtime.nccl_finalize()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

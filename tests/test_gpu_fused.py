@@ -299,3 +299,31 @@ def test_fused_rle_runs_and_mixed_streams(tmp_path):
     p = _write(str(tmp_path / "a.parquet"), t, row_group_size=70_000, data_page_size=16_000)
     _check([p], t, "item", DATE_PREDS, SUM_COUNT + [("COUNT*", None)])
     _check([p], t, "qty", [("item", "Gt", 100)], [("SUM", "date"), ("MIN", "item"), ("MAX", "item")])
+
+
+def test_fused_staged_tiles_match_the_tile_kernel(tmp_path, monkeypatch):
+    # The TMA-staged kernel takes the tiles whose columns are single segments of regular index streams (large pages of
+    # high-cardinality columns); page boundaries, NULLs at any density and PLAIN fallback pages leave a mix of staged and
+    # unstaged tiles.  Both kernels must produce the same groups as the numpy restatement, with and without staging.
+    rng = np.random.default_rng(41)
+    n = 700_000
+    t = pa.table({
+        "item": pa.array(rng.integers(1, 60_000, n, dtype=np.int32), mask=rng.random(n) < 0.01),
+        "qty": pa.array(rng.integers(-100, 101, n, dtype=np.int32), mask=rng.random(n) < 0.3),
+        "date": pa.array(rng.integers(2450816, 2452642, n, dtype=np.int32), mask=rng.random(n) < 0.04),
+        "dense": pa.array(rng.integers(0, 1 << 20, n, dtype=np.int32)),
+    })
+    p = _write(str(tmp_path / "a.parquet"), t, row_group_size=300_000, data_page_size=256 * 1024)
+    aggs = SUM_COUNT + [("MIN", "qty"), ("COUNT*", None), ("MAX", "dense")]
+    got, met = _check([p], t, "item", DATE_PREDS, aggs)
+    staged = sum(v for (op, name), v in met.items() if name == "fused_staged_tiles")
+    assert staged > 0.8 * (n // 1024), met
+    monkeypatch.setenv("AURON_FUSED_NO_TMA", "1")
+    got2, met2 = _check([p], t, "item", DATE_PREDS, aggs)
+    assert sum(v for (op, name), v in met2.items() if name == "fused_staged_tiles") == 0
+    assert _rows(got) == _rows(got2)
+    # no predicate, a nullable key, PLAIN-only argument column (dictionary disabled for it)
+    monkeypatch.delenv("AURON_FUSED_NO_TMA")
+    p2 = _write(str(tmp_path / "b.parquet"), t, row_group_size=300_000, data_page_size=128 * 1024, use_dictionary=["item", "date", "qty"])
+    got3, met3 = _check([p2], t, "item", [("date", "Gt", 2451500)], [("SUM", "dense"), ("COUNT", "qty")])
+    assert sum(v for (op, name), v in met3.items() if name == "fused_staged_tiles") > 0, met3

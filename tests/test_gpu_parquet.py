@@ -277,6 +277,39 @@ def test_aggregate_survives_wrong_column_statistics(tmp_path, lie):
     assert_same_rows(got, exp)
 
 
+@pytest.mark.parametrize("compression", ["NONE", "SNAPPY", "ZSTD"])
+@pytest.mark.parametrize("version", ["1.0", "2.0"])
+def test_scan_delta_encodings(tmp_path, compression, version):
+    # DELTA_BINARY_PACKED INT32 / INT64 pages are transcribed to PLAIN on the device (one warp per page walks the blocks);
+    # DELTA_LENGTH_BYTE_ARRAY / DELTA_BYTE_ARRAY string pages are rewritten as PLAIN by the host walker.  Sorted keys (tiny deltas,
+    # zero-width miniblocks), noise (wide miniblocks, wrap-around deltas), NULLs, page counts that are not multiples of a block.
+    rng = np.random.default_rng(23)
+    n = 150_011
+    words = ["", "a", "prefix", "prefix-shared", "prefix-shared-longer", "天地玄黄", "z" * 70]
+    t = pa.table({
+        "sorted32": pa.array(np.sort(rng.integers(-2**31, 2**31 - 1, n)).astype(np.int32), mask=rng.random(n) < 0.03),
+        "noise32": pa.array(rng.integers(-2**31, 2**31 - 1, n).astype(np.int32)),
+        "const64": pa.array(np.full(n, 7_000_000_000, dtype=np.int64), mask=rng.random(n) < 0.5),
+        "noise64": pa.array(rng.integers(-2**63, 2**63 - 1, n, dtype=np.int64), mask=rng.random(n) < 0.02),
+        "ts": pa.array(np.cumsum(rng.integers(0, 1000, n)).astype(np.int64), type=pa.timestamp("us")),
+        "dl": pa.array([words[int(i)] + str(int(i) * 37 % 11) for i in rng.integers(0, len(words), n)], mask=rng.random(n) < 0.05),
+        "db": pa.array(sorted(f"key-{int(x):09d}" for x in rng.integers(0, 10**9, n))),
+        "allnull": pa.array([None] * n, type=pa.int64()),
+    })
+    enc = {"sorted32": "DELTA_BINARY_PACKED", "noise32": "DELTA_BINARY_PACKED", "const64": "DELTA_BINARY_PACKED", "noise64": "DELTA_BINARY_PACKED",
+           "ts": "DELTA_BINARY_PACKED", "dl": "DELTA_LENGTH_BYTE_ARRAY", "db": "DELTA_BYTE_ARRAY", "allnull": "DELTA_BINARY_PACKED"}
+    path = str(tmp_path / "delta.parquet")
+    pq.write_table(t, path, compression=compression, use_dictionary=False, column_encoding=enc, data_page_version=version, row_group_size=70_001,
+                   data_page_size=64 * 1024)
+    md = pq.ParquetFile(path).metadata.row_group(0)
+    assert "DELTA_BINARY_PACKED" in md.column(0).encodings and "DELTA_BYTE_ARRAY" in md.column(6).encodings
+    exp = pq.read_table(path)
+    got = _scan(path, t.schema)
+    assert got.num_rows == exp.num_rows
+    for name in t.column_names:
+        assert got[name].to_pylist() == exp[name].to_pylist(), name
+
+
 @pytest.mark.parametrize("dict_", [True, False])
 def test_scan_int96_timestamps(tmp_path, dict_):
     # Spark's default timestamp encoding in Parquet is INT96 (nanoseconds of the day + Julian day); the scan converts it to the

@@ -65,4 +65,4 @@ def test_nccl_exchange_two_gpus():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     r = _torchrun(["tests/multi_gpu_exchange.py"])
-    assert r.returncode == 0 and "EXCHANGE_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.returncode == 0 and "EXCHANGE_OK" in r.stdout and "BROADCAST_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
