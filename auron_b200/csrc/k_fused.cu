@@ -621,20 +621,38 @@ __device__ __forceinline__ void fz_rows_to_accs(const FzLaunch& L, uint32_t sel,
         }
     }
     const uint32_t null_slot = 0x80000000u | (uint32_t)L.range;
-    while (sel) {
-        const int i = __ffs(sel) - 1;
-        sel &= sel - 1;
-        const uint32_t below = (1u << i) - 1u;
-        uint32_t U = null_slot;
-        if (ALLDICT || ((wk >> i) & 1u)) U = key_at(prefk + __popc(wk & below));
-        const bool dsp = ALLDICT ? true : !(U >> 31);
-        const int64_t slot = (int64_t)(U & 0x7fffffffu);
+    // Software pipeline: the key and the arguments of the next selected row are fetched (shared-memory windows, dictionary
+    // lookups) before the atomics of the current row are issued, so the two latencies overlap.
+    struct Row {
+        int i;
+        uint32_t U;
         long long val[NVR];
         bool ok[NVR];
+    };
+    auto fetch = [&](Row& R) {
+        R.i = __ffs(sel) - 1;
+        sel &= sel - 1;
+        const uint32_t below = (1u << R.i) - 1u;
+        R.U = null_slot;
+        if (ALLDICT || ((wk >> R.i) & 1u)) R.U = key_at(prefk + __popc(wk & below));
 #pragma unroll
         for (int v = 0; v < NVR; v++) {
-            ok[v] = (wv[v] >> i) & 1u;
-            val[v] = ok[v] ? (long long)(int32_t)val_at(v, prefv[v] + __popc(wv[v] & below)) : 0ll;
+            R.ok[v] = (wv[v] >> R.i) & 1u;
+            R.val[v] = R.ok[v] ? (long long)(int32_t)val_at(v, prefv[v] + __popc(wv[v] & below)) : 0ll;
+        }
+    };
+    auto commit = [&](const Row& R) {
+        const bool dsp = ALLDICT ? true : !(R.U >> 31);
+        const int64_t slot = (int64_t)(R.U & 0x7fffffffu);
+        if (SIG == FZ_SIG_SUM_COUNT && L.pack_shift > 0 && dsp) {   // both accumulators of the row in one atomic
+            if (R.ok[0]) {
+                const unsigned long long d = (unsigned long long)(R.val[0] - L.pack_bias);
+                if (d >> L.pack_bits) *L.oor = 1;   // the column statistics did not cover this value
+                else atomicAdd(bd[0] + slot, (1ull << L.pack_shift) | d);
+            } else {
+                L.seen_dspace[slot] = 1;
+            }
+            return;
         }
         bool marked = false;
 #pragma unroll
@@ -642,12 +660,12 @@ __device__ __forceinline__ void fz_rows_to_accs(const FzLaunch& L, uint32_t sel,
             if (a >= nacc) break;
             long long v = 1;
             bool valid = true;
-            if (plane[a] == 0) valid = ALLDICT ? true : ((wk >> i) & 1u);
+            if (plane[a] == 0) valid = ALLDICT ? true : ((wk >> R.i) & 1u);
 #pragma unroll
             for (int q = 0; q < NVR; q++)
                 if (plane[a] == 1 + q) {
-                    valid = ok[q];
-                    v = val[q];
+                    valid = R.ok[q];
+                    v = R.val[q];
                 }
             if (!valid) continue;
             unsigned long long* p = (dsp ? bd[a] : bx[a]) + slot;
@@ -662,7 +680,16 @@ __device__ __forceinline__ void fz_rows_to_accs(const FzLaunch& L, uint32_t sel,
             marked = marked || op[a] == 1;
         }
         if (need_seen && !marked) (dsp ? L.seen_dspace : L.seen_direct)[slot] = 1;   // the group exists although no accumulator shows it
+    };
+    if (!sel) return;
+    Row cur, nxt;
+    fetch(cur);
+    while (sel) {
+        fetch(nxt);
+        commit(cur);
+        cur = nxt;
     }
+    commit(cur);
 }
 // ------------------------------------------------------------------------------------------------ TMA-staged tiles
 // Tiles whose columns are each ONE segment of a "regular" index stream (or of a PLAIN page) need no run walk: value k of the page
@@ -720,7 +747,7 @@ __device__ __forceinline__ bool fz_stage_plan(const FzLaunch& L, int T, unsigned
             pl.src = (const uint8_t*)a0;
             pl.bytes = (int32_t)(a1 - a0);
             pl.sub = (int32_t)((int64_t)a0 - (int64_t)(uintptr_t)stream);
-            ok = (int64_t)(a1 - a0) + 16 <= C.stage_cap && lb + (bw >= 0 ? 1 : 0) <= (int64_t)s4.x;   // (+16: the 8-byte windows read behind the last value)
+            ok = (int64_t)(a1 - a0) + 32 <= C.stage_cap && lb + (bw >= 0 ? 1 : 0) <= (int64_t)s4.x;   // (+32: 8-byte windows, up to three values behind the last one)
         }
         pl.bw = bw;
         pl.v0 = (int32_t)v0;
@@ -776,7 +803,7 @@ __device__ __forceinline__ uint32_t fz_staged_get(const FzStaged& S, int k) {
     return fz_staged_bits(S, 8u * (q * S.run_bytes + (uint32_t)S.adj) + r * S.bw);
 }
 template <int NV, int NACC, uint32_t SIG>
-__global__ void __launch_bounds__(FZ_WARPS * 32) fz_staged_kernel(const __grid_constant__ FzLaunch L, int per_warp_bytes) {
+__global__ void __launch_bounds__(FZ_WARPS * 32) fz_staged_kernel(const __grid_constant__ FzLaunch L, int per_warp_bytes, int nstage) {
     extern __shared__ __align__(16) uint8_t fz_smem[];
     const int wid = threadIdx.x >> 5;
     const unsigned lane = threadIdx.x & 31;
@@ -795,7 +822,6 @@ __global__ void __launch_bounds__(FZ_WARPS * 32) fz_staged_kernel(const __grid_c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    const int nw = gridDim.x * FZ_WARPS;
     auto issue = [&](int T, int s) -> bool {
         FzStagePlan pl;
         if (!fz_stage_plan(L, T, lane, pl)) return false;
@@ -842,15 +868,29 @@ __global__ void __launch_bounds__(FZ_WARPS * 32) fz_staged_kernel(const __grid_c
     };
     uint32_t phase = 0;
     int n_done = 0;
-    int T = blockIdx.x * FZ_WARPS + wid, s = 0;
-    bool staged = T < L.n_tiles ? issue(T, 0) : false;
-    for (; T < L.n_tiles; T += nw, s ^= 1) {
+    // Tiles are handed out by a counter: the kernel shares the GPU with the decompression and scout kernels of the next batch, so
+    // only part of the grid is resident at first -- a fixed tile-to-warp map would leave the late blocks' share for the end.
+    auto grab = [&]() -> int {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(L.left + 1, 1);
+        return __shfl_sync(FULL_MASK, t, 0);
+    };
+    int T = grab(), s = 0;
+    const int toggle = nstage == 2 ? 1 : 0;   // one stage: the copies of a tile are issued when the tile before it is done (more warps per SM instead)
+    bool staged = toggle && T < L.n_tiles ? issue(T, 0) : false;
+    for (int Tn = 0; T < L.n_tiles; T = Tn, s ^= toggle) {
         __syncwarp();   // every lane is done with the other stage (the tile before this one)
-        const bool staged_next = T + nw < L.n_tiles ? issue(T + nw, s ^ 1) : false;
-        const bool mine = staged;
-        staged = staged_next;
+        Tn = grab();
+        bool mine;
+        if (toggle) {
+            const bool staged_next = Tn < L.n_tiles ? issue(Tn, s ^ 1) : false;
+            mine = staged;
+            staged = staged_next;
+        } else {
+            mine = issue(T, 0);
+        }
         if (!mine) {   // left to the tile kernel
-            if (lane == 0) L.left[1 + atomicAdd(L.left, 1)] = T;
+            if (lane == 0) L.left[2 + atomicAdd(L.left, 1)] = T;
             continue;
         }
         if (!fz_mbar_wait(&mbar[s], (phase >> s) & 1u)) {
@@ -876,24 +916,40 @@ __global__ void __launch_bounds__(FZ_WARPS * 32) fz_staged_kernel(const __grid_c
             if (p == 0) {   // every valid row is looked at: walk the lane's values in stream order (no division per value)
                 uint32_t q = (uint32_t)k0 / 504u, r = (uint32_t)k0 - q * 504u;
                 uint32_t X = 8u * (q * S.run_bytes + (uint32_t)S.adj) + r * S.bw;
-                for (uint32_t ww = w; ww;) {
-                    const int i = __ffs(ww) - 1;
-                    ww &= ww - 1;
-                    const uint32_t raw = fz_staged_bits(S, X);
-                    X += S.bw;
-                    if (++r == 504u) {
-                        r = 0;
-                        X += S.hdr_bits;
+                // four values per round: the eight window reads and the four pass-bit loads are issued before the first is used
+                // (reads behind the lane's last value stay inside the stage: it carries 32 spare bytes)
+                uint32_t ww = w;
+                for (int n = __popc(w); n > 0; n -= 4) {
+                    uint32_t raw[4], bit[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        raw[u] = fz_staged_bits(S, X);
+                        X += S.bw;
+                        if (++r == 504u) {
+                            r = 0;
+                            X += S.hdr_bits;
+                        }
                     }
-                    uint32_t bit;
                     if (S.dict) {
-                        const uint32_t e = raw < (uint32_t)S.ndict ? raw : 0u;
-                        bit = S.ndict > 0 ? (__ldg(pass + (e >> 5)) >> (e & 31)) & 1u : 0u;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const uint32_t e = raw[u] < (uint32_t)S.ndict ? raw[u] : 0u;
+                            bit[u] = S.ndict > 0 ? (__ldg(pass + (e >> 5)) >> (e & 31)) & 1u : 0u;
+                        }
                     } else {
-                        const int64_t v = (int64_t)(int32_t)raw;
-                        bit = (v >= C.lo && v <= C.hi) ? 1u : 0u;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int64_t v = (int64_t)(int32_t)raw[u];
+                            bit[u] = (v >= C.lo && v <= C.hi) ? 1u : 0u;
+                        }
                     }
-                    res |= bit << i;
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (u < n) {
+                            const int i = __ffs(ww) - 1;
+                            ww &= ww - 1;
+                            res |= bit[u] << i;
+                        }
                 }
             } else {        // rows already dropped by an earlier predicate are not looked at
                 for (uint32_t ww = w & sel; ww;) {
@@ -1029,7 +1085,7 @@ __global__ void __launch_bounds__(FZ_WARPS * 32) fz_kernel(const __grid_constant
     }
     const int count = __ldg(L.left);
     for (int i = blockIdx.x * FZ_WARPS + wid; i < count; i += gridDim.x * FZ_WARPS) {
-        fz_tile<NV, NACC, SIG>(L, __ldg(L.left + 1 + i), fz_smem, wid, lane);
+        fz_tile<NV, NACC, SIG>(L, __ldg(L.left + 2 + i), fz_smem, wid, lane);
         __syncwarp();
     }
 }
@@ -1045,7 +1101,11 @@ static void fz_launch(Ctx& ctx, const FzLaunch& L, size_t smem) {
     if (L.staged) {
         int stage_bytes = 0;
         for (int c = 0; c < L.ncols; c++) stage_bytes += L.col[c].stage_cap;
-        const int per_warp = 16 + 2 * FZ_MAX_COLS * 32 + 2 * stage_bytes;
+        // One stage per warp by default (AURON_FUSED_STAGES=2: double buffering).  Measured on B200, SF100 bench, three batches in
+        // flight: 5.59 ms per step with one stage, 6.02 ms with two -- half the shared memory lets twice as many warps hide the copy
+        // latency themselves and leaves room for the decompression / scout kernels of the next batch on the same SMs.
+        static const int nstage = getenv("AURON_FUSED_STAGES") ? std::max(1, std::min(2, atoi(getenv("AURON_FUSED_STAGES")))) : 1;
+        const int per_warp = 16 + 2 * FZ_MAX_COLS * 32 + nstage * stage_bytes;
         const size_t smem2 = (size_t)FZ_WARPS * per_warp;
         int per_sm = 0;
         CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fz_staged_kernel<NV, NACC, SIG>, FZ_WARPS * 32, smem2));
@@ -1053,7 +1113,7 @@ static void fz_launch(Ctx& ctx, const FzLaunch& L, size_t smem) {
         static int n_sm = 0;
         if (!n_sm) CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx.device));
         const int blocks = std::min((L.n_tiles + FZ_WARPS - 1) / FZ_WARPS, n_sm * per_sm);   // persistent warps, round robin over the tiles
-        fz_staged_kernel<NV, NACC, SIG><<<blocks, FZ_WARPS * 32, smem2, ctx.stream>>>(L, per_warp);
+        fz_staged_kernel<NV, NACC, SIG><<<blocks, FZ_WARPS * 32, smem2, ctx.stream>>>(L, per_warp, nstage);
         CUDA_OK(cudaGetLastError());
         launch_count(ctx);
         int per_sm1 = 0;
@@ -1076,10 +1136,10 @@ void fz_run(Ctx& ctx, const FzLaunch& L0) {
         const bool off = getenv("AURON_FUSED_NO_TMA") != nullptr;
         L.staged = all && !off && (16 + 2 * FZ_MAX_COLS * 32 + 2 * stage_bytes) * 8 <= (200 << 10) ? 1 : 0;
     }
-    Buf left;   // tiles the staged kernel leaves to the tile kernel: [0] count, then the tile numbers
+    Buf left;   // work list of the staged kernel and what it leaves to the tile kernel
     if (L.staged) {
-        left = dalloc(ctx, ((size_t)L.n_tiles + 1) * 4);
-        CUDA_OK(cudaMemsetAsync(left->ptr, 0, 4, ctx.stream));
+        left = dalloc(ctx, ((size_t)L.n_tiles + 2) * 4);   // [0] tiles left to the tile kernel, [1] next tile to hand out, then the tiles left
+        CUDA_OK(cudaMemsetAsync(left->ptr, 0, 8, ctx.stream));
         L.left = P<int32_t>(left);
     }
     const int nplanes = L.ncols - L.npred, nv = nplanes - 1;
@@ -1131,6 +1191,7 @@ __global__ void __launch_bounds__(256) fz_merge_kernel(const __grid_constant__ F
     if (g >= dict_slots) return;
     bool any = M.seen_dspace[g] != 0;
     unsigned long long v[FZ_MAX_ACCS];
+    unsigned long long packed_cnt = 0;
     bool vb[FZ_MAX_ACCS];
 #pragma unroll
     for (int a = 0; a < FZ_MAX_ACCS; a++) {
@@ -1138,6 +1199,12 @@ __global__ void __launch_bounds__(256) fz_merge_kernel(const __grid_constant__ F
         vb[a] = false;
         if (a < M.nacc) {
             v[a] = M.acc[a].dspace[g];
+            if (M.pack_shift > 0 && a == 0) {   // SUM and COUNT of the entry in one word (see FzLaunch)
+                packed_cnt = v[0] >> M.pack_shift;
+                v[0] = (v[0] & ((1ull << M.pack_shift) - 1ull)) + packed_cnt * (unsigned long long)M.pack_bias;
+            } else if (M.pack_shift > 0 && a == 1) {
+                v[1] += packed_cnt;
+            }
             vb[a] = M.acc[a].dspace_valid && M.acc[a].dspace_valid[g];
             const unsigned long long init = M.acc[a].kind == ACC_MIN ? 0x7fffffffffffffffull : M.acc[a].kind == ACC_MAX ? 0x8000000000000000ull : 0ull;
             any = any || v[a] != init || vb[a];

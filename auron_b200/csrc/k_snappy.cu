@@ -49,7 +49,7 @@ struct PqDecompState {
 // measured: 32 unrelated byte streams per load instruction thrash L1 -- 1.7 ms per launch.)  A job that does not have the
 // expected shape within the budget (long literal in the middle, far back reference, large output) is handed to the warp kernel
 // below, which resumes it from the recorded offsets.
-constexpr int SN_TEAM = 4, SN_TEAMS = 32 / SN_TEAM, SN_TRING = 1024, SN_WIN = 256;
+constexpr int SN_TEAM = 4, SN_TEAMS = 32 / SN_TEAM, SN_TRING = 512, SN_WIN = 256;
 constexpr int SN_PREFIX_MAX_OUT = 48 * 1024, SN_PREFIX_MAX_ELEMS = 12000;
 __global__ void __launch_bounds__(128) pq_decompress_prefix_kernel(const PqDecompJob* __restrict__ jobs, int n_jobs, int32_t* __restrict__ status,
                                                                    PqDecompResult* __restrict__ results, PqDecompState* __restrict__ states) {

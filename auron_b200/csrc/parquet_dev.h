@@ -154,7 +154,12 @@ struct FzLaunch {
     uint8_t* seen_dspace;
     int32_t* oor;                         // a key outside [kmin, kmin + range): the column statistics were wrong
     unsigned long long* selected_rows;    // [0] rows that passed the predicates (FilterExec's output_rows), [1] tiles done by the staged kernel
-    int32_t* left;                        // staged mode: [0] number of tiles left to the tile kernel, then their numbers
+    int32_t* left;                        // staged mode: [0] number of tiles left to the tile kernel, [1] next tile to hand out, then the tiles left
+    // SUM(x), COUNT(x) of a narrow x (accumulators 0 and 1): rows whose key is a dictionary entry add ((1 << pack_shift) | (x - pack_bias))
+    // to the entry's SUM word with ONE atomic -- the atomic unit, not the issue slots, bounds the kernel (1.29 cycles per lane
+    // and SM); fz_merge splits the word.  pack_shift = 0: off.  x outside [pack_bias, pack_bias + 2^pack_bits) raises `oor`.
+    int32_t pack_shift, pack_bits;
+    long long pack_bias;
 };
 struct FzMerge {                  // dictionary space -> direct table, one launch per batch
     const PqDict* dicts;
@@ -166,6 +171,8 @@ struct FzMerge {                  // dictionary space -> direct table, one launc
     uint8_t* seen_direct;
     const uint8_t* seen_dspace;
     int32_t* oor;
+    int32_t pack_shift, pack_bits;    // as in FzLaunch
+    long long pack_bias;
 };
 void fz_scout(Ctx& ctx, const std::vector<FzScoutCol>& cols);
 void fz_dict_pass(Ctx& ctx, const PqDict* dicts, const int32_t* pass_off, int n_dicts, int total_words, int64_t lo, int64_t hi, uint32_t* pass_bits);

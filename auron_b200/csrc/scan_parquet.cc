@@ -1766,7 +1766,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
                 for (auto& d : cs.dicts) max_dict = std::max(max_dict, d.num_values);
                 int bits = 1;
                 while (bits < 32 && (1ll << bits) < (int64_t)max_dict) bits++;
-                C.stage_cap = cs.dicts.empty() ? 4 * FZ_TILE + 48 : 128 * bits + 64;
+                C.stage_cap = cs.dicts.empty() ? 4 * FZ_TILE + 64 : 128 * bits + 80;
                 if (cs.el.type != pq::PT_INT32) C.stage_cap = 0;
             }
             return L.ncols++;
@@ -1857,6 +1857,23 @@ struct ParquetScanExec : Operator, FusedScanSource {
         L.seen_dspace = P<uint8_t>(dseen);
         L.oor = dv.oor;
         L.selected_rows = P<unsigned long long>(st.selected);
+        // SUM(x), COUNT(x) (AVG's partial state) of a narrow x: one atomic per row instead of two.  The SUM word of a dictionary entry
+        // holds (count << shift) | sum(x - min) for the batch: sum(x - min) < rows * 2^bits needs bits + ceil(log2 rows) bits, the
+        // count the rest.  min / max come from the chunk statistics; a value outside them raises `oor` like a key would.
+        if (L.nacc == 2 && L.acc[0].kind == ACC_SUM_I64 && L.acc[1].kind == ACC_COUNT && L.acc[0].col >= 0 && L.acc[0].col == L.acc[1].col &&
+            L.acc[0].col != L.key_col && !L.acc[0].direct_valid && !L.acc[1].direct_valid && !getenv("AURON_FUSED_NO_PACK")) {
+            const ColState& vcs = p.cols[(size_t)spec.accs[0].col];
+            if (vcs.stat_ok && vcs.stat_min <= vcs.stat_max && !getenv("AURON_SCAN_NO_STATS")) {
+                int bits = 1, rbits = 1;
+                while (bits < 40 && (vcs.stat_max - vcs.stat_min) >= (1ll << bits)) bits++;
+                while ((1ll << rbits) <= n_rows) rbits++;
+                if (bits + 2 * rbits + 1 <= 64) {
+                    L.pack_bits = bits;
+                    L.pack_shift = bits + rbits;
+                    L.pack_bias = vcs.stat_min;
+                }
+            }
+        }
         fz_init_dspace(wc, L, dict_slots);
         if (&fc != &wc) chain(wc.stream, fc.stream);
         fz_run(fc, L);
@@ -1872,6 +1889,9 @@ struct ParquetScanExec : Operator, FusedScanSource {
         M.seen_direct = dv.seen;
         M.seen_dspace = P<uint8_t>(dseen);
         M.oor = dv.oor;
+        M.pack_shift = L.pack_shift;
+        M.pack_bits = L.pack_bits;
+        M.pack_bias = L.pack_bias;
         fz_merge(fc, M, dict_slots);
         if (&fc != &wc) chain(fc.stream, wc.stream);   // the batch's buffers are freed (stream-ordered) on wc: after its kernels
         st.rows += n_rows;

@@ -406,8 +406,9 @@ def main():
                     cc = md.row_group(g).column(c)
                     h2d_bytes += cc.total_compressed_size
                     unc_bytes += cc.total_uncompressed_size
-        # device batches of 3 files (48M rows): the host prepares batch k+1 while the GPU works on batch k, two batches in flight
-        os.environ.setdefault("AURON_GPU_CHUNK_ROWS", str(48_000_000))
+        # device batches of 6 files (96M rows = 12 row groups): the host prepares batch k+1 while the GPU works on batch k; measured on
+        # B200: 5.6 ms per step at 96M, 5.9 ms at 72M, 5.7 ms at 144M, 6.5 ms with the whole table as one batch
+        os.environ.setdefault("AURON_GPU_CHUNK_ROWS", str(96_000_000))
         # ---- value: file images resident in HBM
         hbm_paths = [f"hbm://{os.path.basename(p)}@{local_rank}" for p in paths]
         for p, hp in zip(paths, hbm_paths):
