@@ -127,6 +127,13 @@ inline void parallel_for(size_t n, unsigned threads, F fn) {
 struct PinnedPool {
     std::mutex mu;
     std::vector<std::pair<void*, size_t>> free_list;
+    size_t total = 0;   // bytes handed out + bytes in the free list
+    // cudaHostAlloc / cudaFreeHost cost ~0.3 ms per MB: blocks are kept and reused (best fit); idle blocks are only released when
+    // the pool would otherwise exceed its cap (AURON_PINNED_POOL_BYTES, default 12 GB), smallest first
+    static size_t cap_bytes() {
+        static const size_t c = getenv("AURON_PINNED_POOL_BYTES") ? (size_t)atoll(getenv("AURON_PINNED_POOL_BYTES")) : (size_t)12 << 30;
+        return c;
+    }
     void* get(size_t n, size_t* cap) {
         std::lock_guard<std::mutex> l(mu);
         size_t best = SIZE_MAX;
@@ -138,11 +145,18 @@ struct PinnedPool {
             *cap = e.second;
             return e.first;
         }
-        for (auto& e : free_list) cudaFreeHost(e.first);   // too small: replace rather than accumulate
-        free_list.clear();
+        const size_t c = std::max<size_t>(n + n / 8, 64 << 20);
+        while (total + c > cap_bytes() && !free_list.empty()) {   // make room: idle blocks that are too small for this request
+            size_t smallest = 0;
+            for (size_t i = 1; i < free_list.size(); i++)
+                if (free_list[i].second < free_list[smallest].second) smallest = i;
+            cudaFreeHost(free_list[smallest].first);
+            total -= free_list[smallest].second;
+            free_list.erase(free_list.begin() + smallest);
+        }
         void* p = nullptr;
-        size_t c = std::max<size_t>(n + n / 8, 64 << 20);
         CUDA_OK(cudaHostAlloc(&p, c, cudaHostAllocDefault));
+        total += c;
         *cap = c;
         return p;
     }

@@ -223,7 +223,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
         void put(void* p, size_t cap, int device) {
             std::lock_guard<std::mutex> l(mu);
             free_list.push_back(Blk{p, cap, device});
-            while (free_list.size() > 8) {   // keep the cache bounded: drop the smallest block
+            while (free_list.size() > 16) {   // keep the cache bounded: drop the smallest block
                 size_t worst = 0;
                 for (size_t i = 1; i < free_list.size(); i++)
                     if (free_list[i].cap < free_list[worst].cap) worst = i;
@@ -997,6 +997,9 @@ struct ParquetScanExec : Operator, FusedScanSource {
         void* pinned = nullptr;
         size_t pinned_cap = 0;
         void* dev = nullptr;   // from dev_stage_pool()
+        void* unc_dev = nullptr;   // scratch for pages decompressed / transcribed on the device, from dev_stage_pool() (a fresh
+        size_t unc_cap = 0;        // stream-ordered allocation of this size grew the driver's pool now and then: 5..140 ms stalls)
+        int unc_device = 0;
         size_t dev_cap = 0;
         int device = 0;
         cudaEvent_t copied = nullptr, copy_begin = nullptr;
@@ -1030,6 +1033,10 @@ struct ParquetScanExec : Operator, FusedScanSource {
             if (p.copied) cudaEventSynchronize(p.copied);
             dev_stage_pool().put(p.dev, p.dev_cap, p.device);
             p.dev = nullptr;
+        }
+        if (p.unc_dev) {   // (released with the batch: every kernel that read it has finished, see above)
+            dev_stage_pool().put(p.unc_dev, p.unc_cap, p.unc_device);
+            p.unc_dev = nullptr;
         }
         if (p.copied) cudaEventDestroy(p.copied);
         if (p.copy_begin) cudaEventDestroy(p.copy_begin);
@@ -1397,11 +1404,11 @@ struct ParquetScanExec : Operator, FusedScanSource {
                 cs.keep.push_back(sl.host_unc);
             }
         }
-        Buf unc_scratch;   // one scratch allocation for every device-decompressed page of the batch
+        uint8_t* unc_scratch = nullptr;   // one scratch block for every device-decompressed page of the batch
         if (unc_total > 0) {
-            unc_scratch = dalloc(wc, (size_t)unc_total + 256);
-            for (auto& cs : p.cols)
-                if (cs.needs_decomp) cs.keep.push_back(unc_scratch);
+            p.unc_device = t.ctx.device;
+            p.unc_dev = dev_stage_pool().get((size_t)unc_total + 256, p.unc_device, &p.unc_cap);
+            unc_scratch = (uint8_t*)p.unc_dev;
         }
         decomp_jobs.resize(n_jobs);
         parallel_for(p.cols.size(), (unsigned)p.cols.size(), [&](size_t c) {   // (value-initialisation = page faults: one thread per column)
@@ -1418,7 +1425,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
             if (!cp.unc.empty() || cp.gpu_unc_bytes > 0) {
                 const uint8_t* dev_base = nullptr;
                 if (cp.gpu_unc_bytes > 0) {   // decompressed by pq_decompress below, straight from the chunk bytes in HBM
-                    uint8_t* cbase = P<uint8_t>(unc_scratch) + sl.unc_off;
+                    uint8_t* cbase = unc_scratch + sl.unc_off;
                     dev_base = cbase;
                     for (auto& pg : cp.pages)
                         if (pg.job >= 0) pg.job += (int32_t)sl.job_base;
@@ -1471,7 +1478,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
             bool any_delta = false;
             for (auto& cs : p.cols) any_delta = any_delta || cs.has_delta;
             sg.has_jobs = !decomp_jobs.empty() || any_delta;
-            unc_scratch_ptr = unc_scratch ? P<uint8_t>(unc_scratch) : nullptr;
+            unc_scratch_ptr = unc_scratch;
             status_ptr = P<int32_t>(dec.status);
             decomp_results_buf = dec.results;
             decomp_results = P<PqDecompResult>(dec.results);

@@ -587,11 +587,24 @@ def bench_sort_shuffle(args, torch, dist, P, runtime, timed, roofline_of, world,
     if world == 1:
         d = "/dev/shm/auron_bench_shuffle"
         os.makedirs(d, exist_ok=True)
-        td_sh = P.task_definition(P.shuffle_writer(P.ffi_reader(t4.schema, rid), P.hash_repartition([P.col("ss_item_sk")], 200), f"{d}/s.data", f"{d}/s.index"))
-        mk = lambda: runtime.Task(td_sh, device=local_rank)
+        # every map task writes its own new .data / .index pair (as in Spark): rewriting one path would charge the release of the old
+        # file's pages to the step
+        import glob
+        import itertools
+        for f in glob.glob(f"{d}/s*"):
+            os.remove(f)
+        serial = itertools.count()
+
+        def mk():
+            k = next(serial)
+            return runtime.Task(P.task_definition(P.shuffle_writer(P.ffi_reader(t4.schema, rid), P.hash_repartition([P.col("ss_item_sk")], 200),
+                                                                   f"{d}/s{k}.data", f"{d}/s{k}.index")), device=local_rank)
+
         timed(mk, warm, False)
         dt, kern, out, spread = timed(mk, steps, True)
-        fsz = os.path.getsize(f"{d}/s.data")
+        fsz = os.path.getsize(f"{d}/s0.data")
+        for f in glob.glob(f"{d}/s*"):
+            os.remove(f)
         res["shuffle"] = {"value": n * steps / dt, "unit": "rows/s", "ms_per_step": 1000 * dt / steps, "step_ms": spread, "file_bytes": fsz,
                           "file_gbs": fsz * steps / dt / 1e9, "mode": "ShuffleWriterExec -> .data/.index on tmpfs (LZ4 frames, Auron compacted format)",
                           "roofline": roofline_of(kern, steps, dt, {"murmur3_partition_ids": 8 * n, "partition_rows": 8 * n, "take": 2 * 28 * n, "serde_write": 2 * 28 * n,

@@ -25,8 +25,8 @@ for b in t4.to_batches(max_chunksize=16_000_000):
     runtime.put_device_batch("diag", b, device=0)
 d = "/dev/shm/auron_bench_shuffle"
 os.makedirs(d, exist_ok=True)
-td = P.task_definition(P.shuffle_writer(P.ffi_reader(t4.schema, "diag"), P.hash_repartition([P.col("ss_item_sk")], 200), f"{d}/s.data", f"{d}/s.index"))
-for it in range(3):
+for it in range(4):
+    td = P.task_definition(P.shuffle_writer(P.ffi_reader(t4.schema, "diag"), P.hash_repartition([P.col("ss_item_sk")], 200), f"{d}/diag{it}.data", f"{d}/diag{it}.index"))
     t0 = time.perf_counter()
     with runtime.Task(td) as task:
         for _ in task:
@@ -34,3 +34,7 @@ for it in range(3):
         t1 = time.perf_counter()
         m = task.metrics()
     print(f"run {it}: {1000 * (t1 - t0):.1f} ms", {name: round(v / 1e6, 2) if name.endswith("_ns") else v for _, _, name, v in m if v})
+for it in range(4):
+    for ext in ("data", "index"):
+        os.remove(f"{d}/diag{it}.{ext}")
+runtime.drop_device_resource("diag")
