@@ -101,7 +101,7 @@ def main():
                 ["PARTIAL"] * 2)
     with runtime.Task(P.task_definition(agg, stage_id=3, partition_id=rank), {"shard": t.to_batches(), "dim": dim.to_batches()}, device=local) as task:
         jout = pa.Table.from_batches(list(task), schema=task.schema)
-    got_j = {l: (c, sw) for l, c, sw in zip(jout["label"].to_pylist(), jout["c"].to_pylist(), jout["sw"].to_pylist())}
+    got_j = {l: (c, sw) for l, c, sw in zip(jout.column(0).to_pylist(), jout.column(1).to_pylist(), jout.column(2).to_pylist())}   # (partial aggregate: columns by position)
     exp_j = {}
     for k in t["k"].to_pylist():
         if k is None:

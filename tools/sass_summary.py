@@ -1,6 +1,6 @@
 """Static evidence per kernel of libauron_b200.so, generated without a GPU: resource usage (`cuobjdump -res-usage`) and counts of the
 SASS instructions that tell how a kernel touches memory (`cuobjdump -sass`): 128-bit global loads / stores, atomics and reductions,
-shared-memory traffic, warp shuffles / votes.  Writes profiles/r01_sass_summary.md.
+shared-memory traffic, warp shuffles / votes.  Writes profiles/r02_sass_summary.md.
 
     python tools/sass_summary.py
 """
@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "auron_b200", "libauron_b200.so")
 PATTERNS = [("LDG.128", r"\bLDG\.E(\.\w+)*\.128"), ("LDG.64", r"\bLDG\.E(\.\w+)*\.64"), ("LDG", r"\bLDG\b"), ("STG.128", r"\bSTG\.E(\.\w+)*\.128"), ("STG", r"\bSTG\b"),
             ("ATOMG/RED", r"\b(ATOMG|RED|ATOM)\b"), ("ATOMS", r"\bATOMS\b"), ("LDS", r"\bLDS\b"), ("STS", r"\bSTS\b"), ("SHFL", r"\bSHFL\b"),
-            ("VOTE/MATCH", r"\b(VOTE|MATCH|VOTEU)\b"), ("BAR", r"\bBAR\b"), ("POPC", r"\bPOPC\b"), ("SHF (funnel)", r"\bSHF\b")]
+            ("VOTE/MATCH", r"\b(VOTE|MATCH|VOTEU)\b"), ("UBLKCP (TMA bulk copy)", r"\bUBLKCP\b"), ("SYNCS (mbarrier)", r"\bSYNCS\b"), ("BAR", r"\bBAR\b"), ("POPC", r"\bPOPC\b"), ("SHF (funnel)", r"\bSHF\b")]
 
 
 def demangle(names):
@@ -60,7 +60,7 @@ def main():
         r, st, sh, lo = usage[n]
         rows.append((pretty[n], r, st, sh, lo, total[n], counts[n]))
     rows.sort(key=lambda x: x[0])
-    with open(os.path.join(ROOT, "profiles", "r01_sass_summary.md"), "w") as f:
+    with open(os.path.join(ROOT, "profiles", "r02_sass_summary.md"), "w") as f:
         f.write("# Static per-kernel summary (sm_100a SASS of `libauron_b200.so`, `tools/sass_summary.py`)\n\n")
         f.write("Columns: registers per thread, per-thread stack frame in bytes (local arrays: the expression VM's spill-free register file, the scout's "
                 "run tables), static shared memory (1024 B are reserved by the system), then counts of SASS instructions by kind.  `LDG.128` / `STG.128` are "
@@ -71,7 +71,7 @@ def main():
         f.write("| " + " | ".join(hdr) + " |\n|" + "---|" * len(hdr) + "\n")
         for name, r, st, sh, lo, tot, c in rows:
             f.write("| `" + name + "` | " + " | ".join(str(x) for x in (r, st, sh, lo, tot)) + " | " + " | ".join(str(c.get(p[0], 0)) for p in PATTERNS) + " |\n")
-    print(f"{len(rows)} kernels -> profiles/r01_sass_summary.md")
+    print(f"{len(rows)} kernels -> profiles/r02_sass_summary.md")
 
 
 if __name__ == "__main__":
