@@ -38,8 +38,16 @@ struct JoinTable {
     Buf rows;      // int32[n_rows_in_table] build row indices grouped by key
     std::vector<ColumnPtr> keys;   // build key columns (kept alive for verification)
     bool has_null_key = false;
+    bool unique = false;           // no key occurs twice on the build side (a dimension table joined on its primary key)
+    // unique integer keys spanning a small range (surrogate keys): build row by key - dmin, -1 = absent.  One 4-byte load per probe
+    // row from a table that mostly stays in L1 (date_dim: 292 KB), where the hashed table costs four dependent 32-byte L2 sectors
+    // (slot, count, offset, row) -- the probe kernel was L2-bandwidth bound at 5.3 TB/s of sector traffic.
+    Buf direct;
+    long long dmin = 0;
+    int64_t drange = -1;
 };
 bool join_table_has_null_key(const JoinTable& t) { return t.has_null_key; }
+bool join_table_unique_fast(const JoinTable& t) { return t.unique && t.fast; }
 
 struct JKey {
     const void* data;
@@ -242,6 +250,80 @@ __global__ void __launch_bounds__(256) jprobe_write(const int32_t* __restrict__ 
     }
 }
 
+__global__ void __launch_bounds__(256) jcount_max(const int32_t* __restrict__ counts, int64_t n, int32_t* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    int c = i < n ? counts[i] : 0;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) c = max(c, __shfl_xor_sync(FULL_MASK, c, d));
+    if (lane_id() == 0 && c > 1) atomicMax(out, c);
+}
+// Probe of a build side without duplicate keys: every probe row has at most one partner, so the result is a partner index per probe row
+// (-1 = none) plus a match mask -- one pass, no pair list; the probe-side columns are used in place under the mask.
+__global__ void __launch_bounds__(256) jprobe_unique_fast(JKey key, const unsigned long long* __restrict__ table, int64_t cap, const int32_t* __restrict__ counts,
+                                                          const int32_t* __restrict__ offsets, const int32_t* __restrict__ rows, int64_t n,
+                                                          int32_t* __restrict__ build_idx, uint32_t* __restrict__ mask, unsigned long long* __restrict__ matched) {
+    int cnt = 0;
+    const int64_t n32 = (n + 31) & ~(int64_t)31;
+    for (int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x; row < n32; row += (int64_t)gridDim.x * 256) {
+        int32_t b = -1;
+        if (row < n && !(key.validity && !bit_get(key.validity, row))) {
+            const int64_t s = jfind_fast(table, cap, jload_key64(key, row));
+            if (s >= 0 && counts[s] > 0) b = rows[offsets[s]];
+        }
+        if (row < n) build_idx[row] = b;
+        const uint32_t w = __ballot_sync(FULL_MASK, b >= 0);
+        if (lane_id() == 0) mask[row >> 5] = w;
+        cnt += b >= 0;
+    }
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    if (cnt) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) atomicAdd(matched, (unsigned long long)s_cnt);
+}
+__global__ void __launch_bounds__(256) jkey_minmax(JKey key, int64_t n, long long* __restrict__ out) {
+    const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    long long mn = 0x7fffffffffffffffll, mx = -0x7fffffffffffffffll - 1;
+    if (row < n && !(key.validity && !bit_get(key.validity, row))) mn = mx = (long long)jload_key64(key, row);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        mn = min(mn, __shfl_xor_sync(FULL_MASK, mn, d));
+        mx = max(mx, __shfl_xor_sync(FULL_MASK, mx, d));
+    }
+    if (lane_id() == 0 && mn <= mx) {
+        atomicMin(&out[0], mn);
+        atomicMax(&out[1], mx);
+    }
+}
+__global__ void __launch_bounds__(256) jdirect_fill(JKey key, int64_t n, long long dmin, int32_t* __restrict__ direct) {
+    const int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (row < n && !(key.validity && !bit_get(key.validity, row))) direct[(long long)jload_key64(key, row) - dmin] = (int32_t)row;
+}
+// (grid-stride: a block counts its matches in registers and adds them once -- one atomic per warp on a single address
+// serialised in L2 and cost 10x the lookups)
+__global__ void __launch_bounds__(256) jprobe_unique_direct(JKey key, const int32_t* __restrict__ direct, long long dmin, int64_t drange, int64_t n,
+                                                            int32_t* __restrict__ build_idx, uint32_t* __restrict__ mask, unsigned long long* __restrict__ matched) {
+    int cnt = 0;
+    const int64_t n32 = (n + 31) & ~(int64_t)31;   // whole warps take part in the ballot
+    for (int64_t row = (int64_t)blockIdx.x * 256 + threadIdx.x; row < n32; row += (int64_t)gridDim.x * 256) {
+        int32_t b = -1;
+        if (row < n && !(key.validity && !bit_get(key.validity, row))) {
+            const unsigned long long d = (unsigned long long)((long long)jload_key64(key, row) - dmin);
+            if (d <= (unsigned long long)drange) b = __ldg(direct + d);
+        }
+        if (row < n) build_idx[row] = b;
+        const uint32_t w = __ballot_sync(FULL_MASK, b >= 0);
+        if (lane_id() == 0) mask[row >> 5] = w;
+        cnt += b >= 0;
+    }
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    if (cnt) atomicAdd(&s_cnt, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) atomicAdd(matched, (unsigned long long)s_cnt);
+}
 static int64_t jnext_pow2(int64_t v) {
     int64_t p = 1;
     while (p < v) p <<= 1;
@@ -293,11 +375,14 @@ std::shared_ptr<JoinTable> join_build(Ctx& ctx, const std::vector<ColumnPtr>& bu
     }
     Buf total = dalloc(ctx, 4);
     exclusive_scan_i32(ctx, P<int32_t>(t->counts), P<int32_t>(t->offsets), cap + 1, P<int32_t>(total));
+    jcount_max<<<(unsigned)((cap + 1 + 255) / 256), 256, 0, ctx.stream>>>(P<int32_t>(t->counts), cap + 1, P<int32_t>(flags) + 2);
+    LAUNCH_CHECK(ctx);
     int32_t hflags[4], htotal = 0;
     to_host(ctx, hflags, flags->ptr, 16);
     to_host(ctx, &htotal, total->ptr, 4);
     AURON_CHECK(!hflags[1], "join hash table probe overflow");
     t->has_null_key = hflags[0] != 0;
+    t->unique = hflags[2] <= 1;
     t->n_rows_in_table = htotal;
     CUDA_OK(cudaMemcpyAsync(P<int32_t>(t->offsets) + cap + 1, total->ptr, 4, cudaMemcpyDeviceToDevice, ctx.stream));
     t->rows = dalloc(ctx, (size_t)std::max<int32_t>(htotal, 1) * 4);
@@ -308,6 +393,22 @@ std::shared_ptr<JoinTable> join_build(Ctx& ctx, const std::vector<ColumnPtr>& bu
         LAUNCH_CHECK(ctx);
         jbuild_sort_runs<<<(unsigned)((cap + 1 + 255) / 256), 256, 0, ctx.stream>>>(P<int32_t>(t->offsets), P<int32_t>(t->rows), cap + 1);
         LAUNCH_CHECK(ctx);
+    }
+    const int kt = t->key_type;
+    if (t->fast && t->unique && htotal > 0 && (kt == T_INT8 || kt == T_INT16 || kt == T_INT32 || kt == T_INT64 || kt == T_DATE32)) {
+        const long long init[2] = {0x7fffffffffffffffll, -0x7fffffffffffffffll - 1};
+        Buf mm = to_device(ctx, init, 16);
+        jkey_minmax<<<blocks, 256, 0, ctx.stream>>>(jk, n_build, P<long long>(mm));
+        LAUNCH_CHECK(ctx);
+        long long h[2];
+        to_host(ctx, h, mm->ptr, 16);
+        if (h[0] <= h[1] && (unsigned long long)(h[1] - h[0]) < (16ull << 20)) {
+            t->dmin = h[0];
+            t->drange = (int64_t)(h[1] - h[0]);
+            t->direct = dalloc_fill(ctx, (size_t)(t->drange + 1) * 4, 0xff);
+            jdirect_fill<<<blocks, 256, 0, ctx.stream>>>(jk, n_build, t->dmin, P<int32_t>(t->direct));
+            LAUNCH_CHECK(ctx);
+        }
     }
     return t;
 }
@@ -359,6 +460,32 @@ JoinPairs join_probe(Ctx& ctx, const JoinTable& t, const std::vector<ColumnPtr>&
         LAUNCH_CHECK(ctx);
     }
     return out;
+}
+
+int64_t join_probe_unique(Ctx& ctx, const JoinTable& t, const ColumnPtr& probe_key, int64_t n_probe, Buf* build_idx, Buf* mask) {
+    ProfScope ps_fn(ctx, "join_probe");
+    AURON_CHECK(t.unique && t.fast, "join_probe_unique needs a build side without duplicate keys and a single fixed-width key");
+    AURON_CHECK(n_probe < (int64_t)INT32_MAX, "probe chunk too large");
+    const DType& pt = probe_key->type;
+    AURON_CHECK(pt.width() >= 1 && (pt.width() <= 8 || pt.id == T_DECIMAL128), "probe key type incompatible with build key");
+    *build_idx = dalloc(ctx, (size_t)std::max<int64_t>(n_probe, 1) * 4);
+    *mask = dalloc_zero(ctx, bitmap_alloc_bytes(n_probe));
+    if (n_probe == 0) return 0;
+    Buf matched = dalloc_zero(ctx, 8);
+    JKey jk{probe_key->data->ptr, probe_key->vbits(), (int32_t)pt.id};
+    const unsigned pgrid = (unsigned)std::min<int64_t>((n_probe + 255) / 256, (int64_t)ctx.sm_count * 16);   // 8 resident blocks per SM, two rounds
+    const bool int_key = pt.id == T_INT8 || pt.id == T_INT16 || pt.id == T_INT32 || pt.id == T_INT64 || pt.id == T_DATE32;
+    if (t.direct && int_key)
+        jprobe_unique_direct<<<pgrid, 256, 0, ctx.stream>>>(jk, P<int32_t>(t.direct), t.dmin, t.drange, n_probe, P<int32_t>(*build_idx),
+                                                                                     P<uint32_t>(*mask), P<unsigned long long>(matched));
+    else
+        jprobe_unique_fast<<<pgrid, 256, 0, ctx.stream>>>(jk, P<unsigned long long>(t.table), t.cap, P<int32_t>(t.counts), P<int32_t>(t.offsets),
+                                                                                   P<int32_t>(t.rows), n_probe, P<int32_t>(*build_idx), P<uint32_t>(*mask),
+                                                                                   P<unsigned long long>(matched));
+    LAUNCH_CHECK(ctx);
+    unsigned long long h = 0;
+    to_host(ctx, &h, matched->ptr, 8);
+    return (int64_t)h;
 }
 
 }  // namespace auron

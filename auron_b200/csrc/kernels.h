@@ -115,6 +115,9 @@ ColumnPtr avg_finalize(Ctx& ctx, const Column& sum, const Column& cnt, const DTy
 struct JoinTable;   // opaque device hash table over build keys
 std::shared_ptr<JoinTable> join_build(Ctx& ctx, const std::vector<ColumnPtr>& build_keys, int64_t n_build);
 bool join_table_has_null_key(const JoinTable& t);
+bool join_table_unique_fast(const JoinTable& t);   // no duplicate build keys, single fixed-width key
+// probe of such a table: partner build row per probe row (-1 = none) + match mask; returns the number of matches
+int64_t join_probe_unique(Ctx& ctx, const JoinTable& t, const ColumnPtr& probe_key, int64_t n_probe, Buf* build_idx, Buf* mask);
 struct JoinPairs {
     Buf probe_idx, build_idx;   // int32 each; -1 = no partner (outer)
     int64_t count = 0;

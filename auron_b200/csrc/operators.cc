@@ -1013,6 +1013,47 @@ BatchPtr HashJoinExec::finish(Task& t) {
     return out;
 }
 
+SelBatch HashJoinExec::next_sel(Task& t) {
+    SelBatch s;
+    if (finished) return s;
+    if (!built) build(t);
+    const bool eligible = join_type == JOIN_INNER && table && join_table_unique_fast(*table) && !getenv("AURON_JOIN_NO_MASK");
+    if (!eligible) {
+        s.batch = next(t);
+        s.n = s.batch ? s.batch->num_rows : 0;
+        return s;
+    }
+    const bool probe_is_left = build_side == SIDE_RIGHT;
+    while (!probe_done) {
+        AURON_CHECK(t.is_running(), "task killed");
+        BatchPtr p = probe_child().next(t);
+        if (!p) {
+            probe_done = true;
+            break;
+        }
+        if (p->num_rows == 0) continue;
+        OpTimer timer(metrics, "probed_side_compare_time");
+        auto pkeys = eval_keys(t, probe_is_left ? left_keys : right_keys, probe_child().out_schema, *p);
+        Buf idx, mask;
+        const int64_t matched = join_probe_unique(t.ctx, *table, pkeys[0], p->num_rows, &idx, &mask);
+        if (matched == 0) continue;
+        BatchPtr bcols = take_batch(t.ctx, *build_batch, P<int32_t>(idx), p->num_rows, true);   // (-1 -> NULL: rows outside the mask)
+        auto out = std::make_shared<Batch>();
+        out->num_rows = p->num_rows;
+        const BatchPtr& l = probe_is_left ? p : bcols;
+        const BatchPtr& r = probe_is_left ? bcols : p;
+        for (auto& c : l->cols) out->cols.push_back(c);
+        for (auto& c : r->cols) out->cols.push_back(c);
+        metrics.add("output_rows", matched);
+        s.batch = out;
+        s.n = matched;
+        if (matched != p->num_rows) s.mask = mask;
+        return s;
+    }
+    finished = true;
+    return s;
+}
+
 BatchPtr HashJoinExec::next(Task& t) {
     if (finished) return nullptr;
     if (!built) build(t);

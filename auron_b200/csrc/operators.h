@@ -151,6 +151,10 @@ struct HashJoinExec : Operator {
     HashJoinExec(OperatorPtr left, OperatorPtr right, std::vector<ExprPtr> lk, std::vector<ExprPtr> rk, int join_type, int build_side, const Schema& schema);
     std::string describe() const override;
     BatchPtr next(Task& t) override;
+    // INNER join against a build side without duplicate keys (a dimension table on its primary key): the probe batch passes through
+    // with a match mask and the build columns gathered beside it -- the probe columns are never copied (joins/bhj/full_join.rs:148-367
+    // emits the same rows; consumers that skip rows themselves, the aggregate and the projection, take the mask as it is)
+    SelBatch next_sel(Task& t) override;
 
    private:
     void build(Task& t);
