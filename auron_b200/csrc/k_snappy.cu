@@ -276,6 +276,155 @@ __global__ void __launch_bounds__(128) pq_decompress_prefix_kernel(const PqDecom
     }
 }
 
+// ---- prefix pass, one THREAD per job (alternative to the teams above, off by default: see pq_decompress).  The four-lane teams spend
+// ~2,600 cycles per element round (eight streams in lockstep, each at a different kind of element) and leave 89 % of the warp slots empty; the level prefix of a page is only ~1.5 KB of output behind
+// ~400 elements, so a thread can walk it alone in ~30 k instructions -- if its byte traffic stays out of global memory: the last 512
+// output bytes and a 64-byte input window live in shared memory, word-interleaved across the warp (byte j of lane L sits in bank L), so
+// 32 unrelated streams never conflict and never touch L1.  Far back references (beyond the ring) read the thread's own earlier stores
+// back from global memory.  Same protocol as the team kernel: a finished job leaves state {-1, 0}, anything unusual (a large literal
+// that is not the page's value section, budget exceeded, malformed input) is left to the warp kernel, which resumes at {ip, op}.
+constexpr int ST_RING = 512, ST_WIN = 64, ST_MAX_OUT = 16 * 1024, ST_MAX_ELEMS = 6000;
+__global__ void __launch_bounds__(64) pq_decompress_thread_kernel(const PqDecompJob* __restrict__ jobs, int n_jobs, int32_t* __restrict__ status,
+                                                                   PqDecompResult* __restrict__ results, PqDecompState* __restrict__ states) {
+    __shared__ uint32_t s_ring[2][ST_RING / 4][32];   // [warp][word of the ring][lane]: 36 KB per block of two warps, six blocks per SM
+    __shared__ uint32_t s_win[2][ST_WIN / 4][32];
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int job = blockIdx.x * 64 + threadIdx.x;
+    if (job >= n_jobs) return;
+    const PqDecompJob jb = jobs[job];
+    results[job] = PqDecompResult{nullptr, -1, 0};
+    states[job] = PqDecompState{0, 0};
+    if (!(jb.kind >= 1 && jb.v1_levels)) return;   // not a level prefix: the warp kernel's business from the start
+    uint8_t* ring = (uint8_t*)&s_ring[wid][0][lane];   // byte j: ring[(j >> 2) * 128 + (j & 3)]
+    uint8_t* win = (uint8_t*)&s_win[wid][0][lane];
+    const uint8_t* __restrict__ src = jb.src;
+    uint8_t* dst = jb.dst;
+    const int n_in = jb.src_len, n_out = jb.dst_len;
+    int ip = 0, op = 0, wbase = -(1 << 30);
+    auto rd = [&](int pos) -> uint32_t {   // input byte `pos` through the window (16-byte aligned refills; bytes behind the stream read as 0)
+        if (pos < wbase || pos >= wbase + ST_WIN) {
+            const uintptr_t g = (uintptr_t)(src + pos), ga = g & ~(uintptr_t)15;
+            wbase = pos - (int)(g - ga);
+            const uint8_t* lim = src + n_in + 16;
+#pragma unroll
+            for (int q = 0; q < ST_WIN / 16; q++) {
+                const uint8_t* a = (const uint8_t*)ga + 16 * q;
+                const uint4 v = a < lim ? *(const uint4*)a : make_uint4(0, 0, 0, 0);
+                s_win[wid][4 * q + 0][lane] = v.x;
+                s_win[wid][4 * q + 1][lane] = v.y;
+                s_win[wid][4 * q + 2][lane] = v.z;
+                s_win[wid][4 * q + 3][lane] = v.w;
+            }
+        }
+        const int j = pos - wbase;
+        return win[(j >> 2) * 128 + (j & 3)];
+    };
+    auto put = [&](int o, uint8_t c) {
+        dst[o] = c;
+        const int j = o & (ST_RING - 1);
+        ring[(j >> 2) * 128 + (j & 3)] = c;
+    };
+    auto ring_at = [&](int o) -> uint8_t {
+        const int j = o & (ST_RING - 1);
+        return ring[(j >> 2) * 128 + (j & 3)];
+    };
+    // preamble: uncompressed length (a malformed one is left to the warp kernel, which reports it)
+    {
+        uint32_t v = 0;
+        int shift = 0;
+        for (;;) {
+            if (ip >= n_in || shift > 28) return;
+            const uint32_t b = rd(ip);
+            ip++;
+            v |= (b & 0x7f) << shift;
+            if (!(b & 0x80)) break;
+            shift += 7;
+        }
+        if (jb.kind == 2 ? (int)v < n_out : (int)v != n_out) return;
+    }
+    const int ip_first = ip;
+    for (int elems = 0;; elems++) {
+        if (ip >= n_in) {
+            if (op == n_out) states[job] = PqDecompState{-1, 0};
+            else states[job] = PqDecompState{ip_first == ip ? 0 : ip, op};   // short output: the warp kernel reports it
+            return;
+        }
+        const int ip0 = ip;
+        bool handoff = op >= ST_MAX_OUT || elems >= ST_MAX_ELEMS;
+        if (!handoff) {
+            const uint32_t tag = rd(ip);
+            ip++;
+            const uint32_t kind = tag & 3;
+            if (kind == 0) {
+                int len = (int)(tag >> 2) + 1;
+                if (len > 60) {
+                    const int nb = len - 60;
+                    uint32_t v = 0;
+                    if (ip + nb > n_in) handoff = true;
+                    else {
+                        for (int k = 0; k < nb; k++) v |= rd(ip + k) << (8 * k);
+                        ip += nb;
+                        if (v >= 0x7fffffffu) handoff = true;
+                        len = (int)v + 1;
+                    }
+                }
+                if (!handoff && (len > n_in - ip || len > n_out - op)) handoff = true;   // malformed: reported by the warp kernel
+                if (!handoff) {
+                    if (len > 256) {
+                        // the literal that holds the value section: only the level bytes that spill into it are copied, the page reads its
+                        // values in place from the compressed buffer (see the warp kernel); any other large literal is not for this kernel
+                        handoff = true;
+                        if (jb.kind == 1 && ip + len == n_in && op + len == n_out && op >= 4) {
+                            const uint32_t head = (uint32_t)dst[0] | ((uint32_t)dst[1] << 8) | ((uint32_t)dst[2] << 16) | ((uint32_t)dst[3] << 24);
+                            const int64_t val_off = 4 + (int64_t)head, keep = val_off - op;
+                            if (keep >= 0 && keep <= 64 && len - keep >= 256) {   // (a longer spill is a job for 32 lanes: the warp kernel resumes here)
+                                for (int i = 0; i < (int)keep; i++) dst[op + i] = src[ip + i];
+                                results[job] = PqDecompResult{src + ip + keep, (int32_t)val_off, 0};
+                                states[job] = PqDecompState{-1, 0};
+                                return;
+                            }
+                        }
+                    } else {
+                        for (int i = 0; i < len; i++) put(op + i, (uint8_t)rd(ip + i));
+                        ip += len;
+                        op += len;
+                    }
+                }
+            } else {
+                int len, off;
+                if (kind == 1) {
+                    len = 4 + (int)((tag >> 2) & 7);
+                    off = (int)(((tag >> 5) << 8) | rd(ip));
+                    ip += 1;
+                } else if (kind == 2) {
+                    len = (int)(tag >> 2) + 1;
+                    off = (int)(rd(ip) | (rd(ip + 1) << 8));
+                    ip += 2;
+                } else {
+                    len = (int)(tag >> 2) + 1;
+                    const uint32_t o4 = rd(ip) | (rd(ip + 1) << 8) | (rd(ip + 2) << 16) | (rd(ip + 3) << 24);
+                    off = o4 > 0x7fffffffu ? 0 : (int)o4;
+                    ip += 4;
+                }
+                if (ip > n_in || off <= 0 || off > op || len > n_out - op) handoff = true;   // malformed: reported by the warp kernel
+                else if (off + len <= ST_RING) {   // every source byte is still in the ring, none of them is overwritten by this element
+                    const int from = op - off;
+                    for (int i = 0; i < len; i++) put(op + i, ring_at(from + (off >= len ? i : (int)((unsigned)i % (unsigned)off))));
+                    op += len;
+                } else {                           // far back reference: the thread's own earlier stores, read back from global memory
+                    const uint8_t* from = dst + op - off;
+                    for (int i = 0; i < len; i++) put(op + i, from[off >= len ? i : (int)((unsigned)i % (unsigned)off)]);
+                    op += len;
+                }
+            }
+        }
+        if (handoff) {
+            states[job] = PqDecompState{ip0 == ip_first ? 0 : ip0, op};
+            return;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128) pq_decompress_kernel(const PqDecompJob* __restrict__ jobs, int n_jobs, int32_t* __restrict__ status,
                                                             PqDecompResult* __restrict__ results, const PqDecompState* __restrict__ states) {
     __shared__ uint8_t s_ring[4][SN_RING];
@@ -427,8 +576,16 @@ PqDecompOut pq_decompress(Ctx& ctx, const std::vector<PqDecompJob>& jobs) {
     Buf dj = to_device(ctx, jobs.data(), jobs.size() * sizeof(PqDecompJob));
     Buf states = dalloc(ctx, jobs.size() * sizeof(PqDecompState));
     ProfScope ps(ctx, "pq_decompress");
-    pq_decompress_prefix_kernel<<<(unsigned)((jobs.size() + 4 * SN_TEAMS - 1) / (4 * SN_TEAMS)), 128, 0, ctx.stream>>>(P<PqDecompJob>(dj), (int)jobs.size(), P<int32_t>(out.status),
-                                                                                                 P<PqDecompResult>(out.results), P<PqDecompState>(states));
+    // AURON_SNAPPY_THREADS=1: the one-thread-per-job prefix pass.  Measured on B200 (SF100 bench, 10,000 pages per launch): 1.94 ms per
+    // launch against 0.93 ms for the four-lane teams, step 6.8 vs 5.9 ms -- a thread alone pays the full shared-memory latency per byte
+    // (load, store, next byte), the teams overlap four bytes and eight streams per warp.  Kept selectable as the measured alternative.
+    static const bool teams = getenv("AURON_SNAPPY_THREADS") == nullptr;
+    if (teams)
+        pq_decompress_prefix_kernel<<<(unsigned)((jobs.size() + 4 * SN_TEAMS - 1) / (4 * SN_TEAMS)), 128, 0, ctx.stream>>>(P<PqDecompJob>(dj), (int)jobs.size(), P<int32_t>(out.status),
+                                                                                                     P<PqDecompResult>(out.results), P<PqDecompState>(states));
+    else
+        pq_decompress_thread_kernel<<<(unsigned)((jobs.size() + 63) / 64), 64, 0, ctx.stream>>>(P<PqDecompJob>(dj), (int)jobs.size(), P<int32_t>(out.status),
+                                                                                                   P<PqDecompResult>(out.results), P<PqDecompState>(states));
     LAUNCH_CHECK(ctx);
     pq_decompress_kernel<<<(unsigned)((jobs.size() + 3) / 4), 128, 0, ctx.stream>>>(P<PqDecompJob>(dj), (int)jobs.size(), P<int32_t>(out.status),
                                                                                        P<PqDecompResult>(out.results), P<PqDecompState>(states));
