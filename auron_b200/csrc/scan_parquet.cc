@@ -1721,6 +1721,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
         };
         std::vector<Phys> ph(used.size());
         std::vector<FzScoutCol> scout;
+        auto tphase = std::make_unique<OpTimer>(metrics, "fused_host_descr_ns");   // host phases of the enqueue, one after the other
         for (size_t u = 0; u < used.size(); u++) {
             ColState& cs = p.cols[(size_t)used[u]];
             const int max_def = cs.el.repetition == 1 ? 1 : 0;
@@ -1750,7 +1751,9 @@ struct ParquetScanExec : Operator, FusedScanSource {
             scout.push_back(sc);
             if (max_def > 0 && (size_t)used[u] == (size_t)spec.key_col) st.key_nullable = true;
         }
+        tphase = std::make_unique<OpTimer>(metrics, "fused_host_scout_ns");
         fz_scout(wc, scout);
+        tphase = std::make_unique<OpTimer>(metrics, "fused_host_roles_ns");
 
         FzLaunch L;
         memset(&L, 0, sizeof(L));
@@ -1813,6 +1816,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
         // The table belongs to the task stream; the lanes only update it.  Creating / widening it is rare (first batch, or a batch
         // whose keys leave the range so far).  No host-side wait: the task stream first waits for everything queued on the lanes
         // (kernels that update the old table), creates / rebases the table, and the lanes wait for that before they go on.
+        tphase = std::make_unique<OpTimer>(metrics, "fused_host_table_ns");
         const bool widen = st.table && st.has_range && umin <= umax && (umin < st.kmin || umax > st.kmax);
         if (!st.table || widen || !st.has_range) {
             if (st.table)   // (a table that does not exist yet has no users to wait for)
@@ -1840,6 +1844,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
         }
         const DirectAggView dv = direct_agg_view(*st.table);
         L.nacc = (int)spec.accs.size();
+        tphase = std::make_unique<OpTimer>(metrics, "fused_host_launch_ns");
         Buf dseen = dalloc(wc, (size_t)std::max<int64_t>(dict_slots, 1));
         for (int a = 0; a < L.nacc; a++) {
             FzAcc& A = L.acc[a];

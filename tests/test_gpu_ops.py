@@ -1113,3 +1113,50 @@ def test_agg_spills_to_host_buckets_and_merges_them(mode, monkeypatch):
     assert_same_rows(got, exp)
     keys = list(zip(got["k"].to_pylist(), got["s"].to_pylist()))
     assert len(keys) == len(set(keys))                                 # every group exactly once: buckets partition the key space
+
+
+@pytest.mark.parametrize("key_type,span", [(pa.int32(), 5_000), (pa.int64(), 10**15), (pa.date32(), 30_000)])
+@pytest.mark.parametrize("side", ["LEFT", "RIGHT"])
+def test_inner_join_on_unique_build_keys_passes_the_probe_side_through_a_mask(key_type, span, side, monkeypatch):
+    # A dimension table joined on its primary key: the probe is one pass into a partner index + match mask (direct-address table for
+    # small-range integer keys, the hashed table otherwise) and the probe columns reach the consumers unmaterialised -- a projection,
+    # an aggregate, and the plain materialised output must all equal the pair-list path (AURON_JOIN_NO_MASK=1) and pandas.
+    rng = np.random.default_rng(31)
+    nb, n = 4_000, 120_000
+    keys = rng.choice(span, nb, replace=False).astype(np.int64)
+    def as_key(a, mask=None):
+        base = pa.int64() if key_type == pa.int64() else pa.int32()
+        return pa.array(a.astype(np.int64 if base == pa.int64() else np.int32), type=base, mask=mask).cast(key_type)
+
+    dim = pa.table({"id": as_key(keys), "name": pa.array([f"n{int(k) % 101}" for k in keys]),
+                    "w": pa.array((keys % 1000).astype(np.int64), mask=keys % 13 == 0)})
+    probe_keys = np.where(rng.random(n) < 0.7, rng.choice(keys, n), rng.integers(0, span, n)).astype(np.int64)
+    fact = pa.table({"k": as_key(probe_keys, rng.random(n) < 0.03),
+                     "v": pa.array(rng.integers(-50, 50, n), type=pa.int64(), mask=rng.random(n) < 0.05),
+                     "s": pa.array([f"s{int(x)}" for x in rng.integers(0, 9, n)])})
+    fs, ds = P.ffi_reader(fact.schema, "f"), P.ffi_reader(dim.schema, "d")
+    if side == "RIGHT":   # build side on the right: output [fact..., dim...]
+        js = pa.schema(list(fact.schema) + list(dim.schema))
+        join = P.hash_join(js, fs, ds, [(P.col("k"), P.col("id"))], "INNER", "RIGHT")
+    else:
+        js = pa.schema(list(dim.schema) + list(fact.schema))
+        join = P.hash_join(js, ds, fs, [(P.col("id"), P.col("k"))], "INNER", "LEFT")
+    plans = {
+        "rows": join,
+        "project": P.projection(join, [P.col("s"), P.binary("Plus", P.col("v"), P.col("w")), P.col("name")], ["s", "vw", "name"], [pa.string(), pa.int64(), pa.string()]),
+        "agg": P.agg(join, [P.col("name")], ["name"], [P.agg_expr("SUM", [P.col("v")], pa.int64()), P.agg_expr("COUNT", [P.col("w")], pa.int64())], ["sv", "cw"], ["PARTIAL"] * 2),
+    }
+    inputs = lambda: {"f": batches(fact, 25_000), "d": batches(dim)}
+    got = {name: runtime.run_task(P.task_definition(pl), inputs()) for name, pl in plans.items()}
+    monkeypatch.setenv("AURON_JOIN_NO_MASK", "1")
+    ref = {name: runtime.run_task(P.task_definition(pl), inputs()) for name, pl in plans.items()}
+    for name in plans:
+        assert got[name].schema == ref[name].schema
+        assert canon(got[name]) == canon(ref[name]), name
+    m = fact.to_pandas().merge(dim.to_pandas(), left_on="k", right_on="id")
+    assert got["rows"].num_rows == len(m) > 0.5 * n
+    exp = m.groupby("name").agg(sv=("v", "sum"), cw=("w", "count"))
+    agg = {r[0]: (r[1], r[2]) for r in zip(*[got["agg"].column(i).to_pylist() for i in range(3)])}
+    for name_, row in exp.iterrows():
+        sv = None if m[m.name == name_].v.notna().sum() == 0 else int(row.sv)
+        assert agg[name_] == (sv, int(row.cw)), name_
