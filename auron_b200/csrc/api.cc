@@ -11,6 +11,7 @@
 #include "../../include/auron_b200.h"
 #include "exchange.h"
 #include "operators.h"
+#include "mem_manager.h"
 #include "tzdb.h"
 
 using namespace auron;
@@ -211,6 +212,13 @@ int auron_b200_put_device_batch(const char* resource_id, const struct ArrowArray
     put_device_resource(resource_id, {b}, s);
     return 0;
     API_GUARD_END(-1)
+}
+int64_t auron_b200_set_hbm_budget(int device, int64_t bytes) {
+    try {
+        return MemManager::of(device).set_budget(bytes);
+    } catch (...) {
+        return -1;
+    }
 }
 void auron_b200_drop_device_resource(const char* resource_id) {
     try {

@@ -3,6 +3,7 @@
 // (datafusion-ext-commons/src/lib.rs:72-75) only survives as the JVM-facing default and is not part of
 // the result contract.
 #include "operators.h"
+#include "mem_manager.h"
 
 #include <algorithm>
 #include <map>
@@ -632,6 +633,7 @@ AggExec::~AggExec() {
     for (auto& pieces : spilled)
         for (auto& a : pieces)
             if (a.release) a.release(&a);
+    if (mem_id) MemManager::of(mem_device).remove(mem_id);
 }
 
 // AggTable::spill (agg_table.rs:323-353): the in-memory table is emptied into `spill_buckets` hash buckets (bucket = pmod
@@ -712,7 +714,19 @@ void AggExec::consume(Task& t, SelBatch& s) {
     if (!group_exprs.empty()) {
         int64_t held = 0;
         for (auto& b : partials) held += batch_device_bytes(*b);
-        if (held > spill_budget) spill(t);
+        if (spill_budget > 0) {   // an explicit budget for this operator (AURON_AGG_SPILL_BYTES)
+            if (held > spill_budget) spill(t);
+        } else {                  // the device-wide budget shared with every other spillable consumer (mem_manager.h)
+            MemManager& mm = MemManager::of(t.ctx.device);
+            if (!mem_id) {
+                mem_id = mm.add("AggExec");
+                mem_device = t.ctx.device;
+            }
+            if (mm.update(mem_id, held)) {
+                spill(t);
+                mm.update(mem_id, 0);
+            }
+        }
     }
 }
 
@@ -767,21 +781,8 @@ BatchPtr AggExec::next(Task& t) {
     if (output_done) return spilled.empty() ? nullptr : next_spilled_bucket(t);
     bool saw_input = false;
     if (spill_budget == 0) {
-        if (const char* e = getenv("AURON_AGG_SPILL_BYTES")) spill_budget = atoll(e);
-        if (spill_budget <= 0) {
-            // the table may hold 40 % of the HBM; inputs and scratch keep the rest.  Asked once per process and device:
-            // cudaMemGetInfo takes the driver's context lock, which a scan's copy thread would wait behind.
-            static std::mutex mu;
-            static std::map<int, int64_t> total_by_device;
-            std::lock_guard<std::mutex> g(mu);
-            auto it = total_by_device.find(t.ctx.device);
-            if (it == total_by_device.end()) {
-                size_t free_b = 0, total_b = 0;
-                CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
-                it = total_by_device.emplace(t.ctx.device, (int64_t)total_b).first;
-            }
-            spill_budget = it->second / 10 * 4;
-        }
+        spill_budget = -1;   // no budget of its own: the device-wide MemManager decides (consume())
+        if (const char* e = getenv("AURON_AGG_SPILL_BYTES")) spill_budget = atoll(e) > 0 ? atoll(e) : -1;
     }
     if (!fuse_checked) setup_fusion();
     while (!input_done && fused_src) {   // ParquetScan -> [Filter] -> this aggregate as one pass per batch (k_fused.cu)
@@ -1256,7 +1257,10 @@ static void release_sort_runs(std::vector<SortExec::Run>& runs) {
         if (r.spilled && r.host.release) r.host.release(&r.host);
     runs.clear();
 }
-SortExec::~SortExec() { release_sort_runs(runs); }
+SortExec::~SortExec() {
+    release_sort_runs(runs);
+    if (mem_id) MemManager::of(mem_device).remove(mem_id);
+}
 BatchPtr SortExec::sort_batch(Task& t, const BatchPtr& in, int64_t keep_rows) {
     std::vector<SortKeySpec> specs;
     for (auto& k : keys) specs.push_back({eval_to_column(t, k.expr, out_schema, *in), k.asc, k.nulls_first});
@@ -1288,8 +1292,17 @@ void SortExec::spill_if_needed(Task& t) {
     int64_t held = 0;
     for (auto& r : runs)
         if (!r.spilled) held += r.bytes;
+    int64_t limit = spill_budget;
+    if (spill_budget < 0) {   // the device-wide budget (mem_manager.h): when told to spill, give back down to half of what is held
+        MemManager& mm = MemManager::of(t.ctx.device);
+        if (!mem_id) {
+            mem_id = mm.add("SortExec");
+            mem_device = t.ctx.device;
+        }
+        limit = mm.update(mem_id, held) ? held / 2 : held;
+    }
     for (auto& r : runs) {
-        if (held <= spill_budget) break;
+        if (held <= limit) break;
         if (r.spilled) continue;
         OpTimer timer(metrics, "spill_ns");
         export_batch(t.ctx, *r.dev, out_schema, &r.host, (size_t)1 << 20);
@@ -1299,6 +1312,7 @@ void SortExec::spill_if_needed(Task& t) {
         metrics.add("mem_spill_count", 1);
         metrics.add("mem_spill_size", r.bytes);
     }
+    if (mem_id) MemManager::of(t.ctx.device).update(mem_id, held);
 }
 // Splitters: every run contributes evenly spaced samples of its key words (each standing for rows / samples rows); the sorted
 // sample is cut where the cumulated weight crosses a multiple of the target range size; every run is then cut at the splitters.
@@ -1360,12 +1374,8 @@ BatchPtr SortExec::next(Task& t) {
         run_rows = t.ctx.gpu_chunk_rows;
         if (const char* e = getenv("AURON_SORT_RUN_ROWS")) run_rows = std::max<int64_t>(1, atoll(e));
         run_rows = std::min<int64_t>(run_rows, (int64_t)1 << 30);   // row ids inside a run are 32-bit
-        if (const char* e = getenv("AURON_SORT_SPILL_BYTES")) spill_budget = atoll(e);
-        if (spill_budget <= 0) {
-            size_t free_b = 0, total_b = 0;
-            CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
-            spill_budget = (int64_t)(total_b / 10 * 4);
-        }
+        spill_budget = -1;   // no budget of its own: the device-wide MemManager decides
+        if (const char* e = getenv("AURON_SORT_SPILL_BYTES")) spill_budget = atoll(e) > 0 ? atoll(e) : -1;
     }
     bool varlen_key = false;
     for (auto& k : keys) varlen_key = varlen_key || infer_type(*k.expr, out_schema).is_varlen();

@@ -109,7 +109,8 @@ struct AggExec : Operator {
     DType widened_key_type;
     // memory-bounded table (agg_table.rs:99-135,323-353,474-721): when the partial results held in HBM outgrow the budget
     // they are split into hash buckets and moved to pinned host memory; the output then merges bucket by bucket
-    int64_t spill_budget = 0;         // bytes of partials allowed to stay in HBM (0 = not yet sized)
+    int64_t spill_budget = 0;         // bytes of partials allowed to stay in HBM (0 = not yet sized, -1 = the device-wide MemManager decides)
+    int mem_id = 0, mem_device = 0;   // consumer id at the MemManager of that device
     int spill_buckets = 64;
     std::vector<std::vector<ArrowArray>> spilled;   // [bucket] -> host-resident pieces ([group cols..., acc cols...])
     Schema spill_schema;
@@ -216,6 +217,7 @@ struct SortExec : Operator {
     std::vector<Run> runs;
     bool input_done = false, merge_ready = false;
     int64_t run_rows = 0, spill_budget = 0, emitted_seen = 0;
+    int mem_id = 0, mem_device = 0;   // consumer id at the MemManager (mem_manager.h)
     size_t next_range = 0, n_ranges = 0;
     SortExec(OperatorPtr input, std::vector<SortExprSpec> keys, int64_t limit, int64_t offset);
     ~SortExec() override;

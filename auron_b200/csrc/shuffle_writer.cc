@@ -103,8 +103,52 @@ struct ShuffleWriterExec : Operator {
         size_t pinned_cap = 0;
         std::vector<uint8_t> owned;
         std::vector<int64_t> part_off;     // num_parts + 1 offsets into bytes
+        int spill = -1;                    // >= 0: the bytes live in spill file `spill` at `spill_off` (bytes == nullptr)
+        int64_t spill_off = 0;
     };
     std::vector<ChunkOut> chunks;
+    // Memory-bounded buffering (sort_repartitioner.rs:98-112: the repartitioner spills under memory pressure).  Finished chunks wait in
+    // pinned host memory for write_files(); once more than `spill_budget` bytes wait (AURON_SHUFFLE_SPILL_BYTES, default 16 GB) they
+    // are appended to a spill file next to the data file and their memory goes back to the pool.  write_files() then takes a
+    // partition's blocks from memory or from the spill files, in chunk order, so the .data file is byte-identical either way.
+    int64_t buffered = 0, spill_budget = -1;
+    std::vector<int> spill_fds;
+    std::vector<std::string> spill_paths;
+    void spill_chunks(Task&) {
+        OpTimer timer(metrics, "spill_ns");
+        const std::string path = data_file + ".spill" + std::to_string(spill_fds.size());
+        int fd = open(path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0600);
+        AURON_CHECK(fd >= 0, "cannot create shuffle spill file " + path);
+        spill_fds.push_back(fd);
+        spill_paths.push_back(path);
+        int64_t off = 0;
+        for (auto& c : chunks) {
+            if (c.spill >= 0 || !c.bytes) continue;
+            const int64_t len = c.part_off.back();
+            int64_t done = 0;
+            while (done < len) {
+                ssize_t w = pwrite(fd, c.bytes + done, (size_t)(len - done), off + done);
+                AURON_CHECK(w > 0, "short write on " + path);
+                done += w;
+            }
+            c.spill = (int)spill_fds.size() - 1;
+            c.spill_off = off;
+            off += len;
+            if (c.pinned_cap) pinned_pool().put(c.bytes, c.pinned_cap);
+            c.pinned_cap = 0;
+            c.owned = std::vector<uint8_t>();
+            c.bytes = nullptr;
+            metrics.add("mem_spill_count", 1);
+            metrics.add("mem_spill_size", len);
+        }
+        buffered = 0;
+    }
+    void drop_spills() {
+        for (int fd : spill_fds) close(fd);
+        for (auto& p : spill_paths) unlink(p.c_str());
+        spill_fds.clear();
+        spill_paths.clear();
+    }
     int64_t rows_so_far = 0;
     bool host_lz4 = getenv("AURON_HOST_LZ4") != nullptr;   // AURON_HOST_LZ4=1: compress LZ4 blocks with liblz4 on the host cores
 
@@ -122,6 +166,7 @@ struct ShuffleWriterExec : Operator {
     ~ShuffleWriterExec() override {
         for (auto& c : chunks)
             if (c.pinned_cap) pinned_pool().put(c.bytes, c.pinned_cap);
+        drop_spills();
     }
 
     // LZ4 frames produced on the GPU (k_lz4.cu): compress 64 KB blocks, size them, assemble the partition streams, one D2H
@@ -278,6 +323,11 @@ struct ShuffleWriterExec : Operator {
             OpTimer timer(metrics, "compress_ns");
             chunks.push_back((zstd || host_lz4) ? compress_on_host(ctx, ser) : compress_on_device(ctx, ser));
         }
+        if (!is_ipc_writer && data_file.rfind("nccl", 0) != 0) {
+            if (spill_budget < 0) spill_budget = getenv("AURON_SHUFFLE_SPILL_BYTES") ? atoll(getenv("AURON_SHUFFLE_SPILL_BYTES")) : (int64_t)16 << 30;
+            buffered += chunks.back().part_off.back();
+            if (buffered > spill_budget) spill_chunks(t);
+        }
         rows_so_far += n;
     }
 
@@ -287,8 +337,10 @@ struct ShuffleWriterExec : Operator {
         // segments are written with pwrite from the worker pool
         std::vector<int64_t> offsets((size_t)num_parts + 1, 0);
         struct Seg {
-            const uint8_t* src;
+            const uint8_t* src;   // nullptr: read from spill file `fd` at `off`
             int64_t len, pos;
+            int fd;
+            int64_t off;
         };
         std::vector<Seg> segs;
         int64_t pos = 0;
@@ -297,7 +349,7 @@ struct ShuffleWriterExec : Operator {
             for (auto& ch : chunks) {
                 int64_t b = ch.part_off[(size_t)p], e = ch.part_off[(size_t)p + 1];
                 if (e == b) continue;
-                segs.push_back(Seg{ch.bytes + b, e - b, pos});
+                segs.push_back(ch.spill >= 0 ? Seg{nullptr, e - b, pos, spill_fds[(size_t)ch.spill], ch.spill_off + b} : Seg{ch.bytes + b, e - b, pos, -1, 0});
                 pos += e - b;
             }
         }
@@ -317,11 +369,13 @@ struct ShuffleWriterExec : Operator {
                 struct Piece {
                     const uint8_t* src;
                     int64_t len, pos;
+                    int fd;
+                    int64_t off;
                 };
                 std::vector<Piece> pieces;
                 const int64_t kPiece = 2 << 20;
                 for (auto& sg : segs)
-                    for (int64_t o = 0; o < sg.len; o += kPiece) pieces.push_back(Piece{sg.src + o, std::min(kPiece, sg.len - o), sg.pos + o});
+                    for (int64_t o = 0; o < sg.len; o += kPiece) pieces.push_back(Piece{sg.src ? sg.src + o : nullptr, std::min(kPiece, sg.len - o), sg.pos + o, sg.fd, sg.off + o});
                 parallel_for(pieces.size(), wthreads, [&](size_t i) {
                     uint8_t* dst = (uint8_t*)map + pieces[i].pos;
 #ifdef MADV_POPULATE_WRITE
@@ -330,14 +384,35 @@ struct ShuffleWriterExec : Operator {
                         (void)madvise((void*)a, (size_t)(e - a), MADV_POPULATE_WRITE);
                     }
 #endif
-                    memcpy(dst, pieces[i].src, (size_t)pieces[i].len);
+                    if (pieces[i].src) {
+                        memcpy(dst, pieces[i].src, (size_t)pieces[i].len);
+                    } else {   // spilled: straight from the spill file into the mapping
+                        int64_t done = 0;
+                        while (done < pieces[i].len) {
+                            ssize_t r = pread(pieces[i].fd, dst + done, (size_t)(pieces[i].len - done), pieces[i].off + done);
+                            AURON_CHECK(r > 0, "short read on a shuffle spill file");
+                            done += r;
+                        }
+                    }
                 });
                 munmap(map, (size_t)pos);
             } else {
                 parallel_for(segs.size(), wthreads, [&](size_t i) {
+                    std::vector<uint8_t> tmp;
+                    const uint8_t* src = segs[i].src;
+                    if (!src) {   // spilled segment: through a bounce buffer
+                        tmp.resize((size_t)segs[i].len);
+                        int64_t got = 0;
+                        while (got < segs[i].len) {
+                            ssize_t r = pread(segs[i].fd, tmp.data() + got, (size_t)(segs[i].len - got), segs[i].off + got);
+                            AURON_CHECK(r > 0, "short read on a shuffle spill file");
+                            got += r;
+                        }
+                        src = tmp.data();
+                    }
                     int64_t done = 0;
                     while (done < segs[i].len) {
-                        ssize_t w = pwrite(fd, segs[i].src + done, (size_t)(segs[i].len - done), segs[i].pos + done);
+                        ssize_t w = pwrite(fd, src + done, (size_t)(segs[i].len - done), segs[i].pos + done);
                         AURON_CHECK(w > 0, "short write on " + data_file);
                         done += w;
                     }
@@ -349,6 +424,7 @@ struct ShuffleWriterExec : Operator {
             throw;
         }
         close(fd);
+        drop_spills();
         FILE* xf = fopen(index_file.c_str(), "wb");
         AURON_CHECK(xf, "cannot create shuffle index file " + index_file);
         AURON_CHECK(fwrite(offsets.data(), 8, offsets.size(), xf) == offsets.size(), "short write on " + index_file);

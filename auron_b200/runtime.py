@@ -91,7 +91,7 @@ EXPORTED_SYMBOLS = [
     "auron_b200_call_native", "auron_b200_schema", "auron_b200_next_batch", "auron_b200_finalize_native", "auron_b200_on_exit",
     "auron_b200_last_error", "auron_b200_metrics", "auron_b200_put_device_batch", "auron_b200_drop_device_resource", "auron_b200_k_hash",
     "auron_b200_put_device_file", "auron_b200_drop_device_file", "auron_b200_put_host_file", "auron_b200_drop_host_file", "auron_b200_nccl_unique_id", "auron_b200_nccl_init", "auron_b200_nccl_finalize",
-    "auron_b200_k_partition_ids", "auron_b200_kernel_launches", "auron_b200_time_kernel",
+    "auron_b200_k_partition_ids", "auron_b200_kernel_launches", "auron_b200_time_kernel", "auron_b200_set_hbm_budget",
 ]
 
 
@@ -283,6 +283,14 @@ def put_device_batch(resource_id: str, batch: pa.RecordBatch, device: int = 0):
     finally:
         _release(arr)
         _release(sch)
+
+
+def set_hbm_budget(bytes_: int, device: int = 0) -> int:
+    """HBM budget shared by the spillable operators on `device` (0 or less: the default); returns the budget in force"""
+    L = lib()
+    L.auron_b200_set_hbm_budget.restype = C.c_int64
+    L.auron_b200_set_hbm_budget.argtypes = [C.c_int, C.c_int64]
+    return int(L.auron_b200_set_hbm_budget(device, bytes_))
 
 
 def drop_device_resource(resource_id: str):

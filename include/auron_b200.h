@@ -110,6 +110,10 @@ int auron_b200_metrics_walk(auron_task* task, auron_metric_node_fn enter, auron_
  * host transfer.  The batch is NOT released by the call. */
 int auron_b200_put_device_batch(const char* resource_id, const struct ArrowArray* batch, const struct ArrowSchema* schema, int device);
 void auron_b200_drop_device_resource(const char* resource_id);
+/* The HBM budget all spillable operators of this process share on `device` (aggregate tables, sorted runs): the analogue of the
+ * executor-wide budget of auron-memmgr (native-engine/auron-memmgr/src/lib.rs:201-423, sized there from spark.auron.memoryFraction).
+ * bytes <= 0 restores the default (40 % of the device memory, or AURON_HBM_BUDGET_BYTES).  Returns the budget now in force. */
+int64_t auron_b200_set_hbm_budget(int device, int64_t bytes);
 /* Same idea for Parquet: copies a whole file image to HBM under `path`; a ParquetScanExec whose
  * PartitionedFile.path equals `path` then decodes page payloads in place (no host transfer, no IO). */
 int auron_b200_put_device_file(const char* path, const uint8_t* bytes, size_t len, int device);

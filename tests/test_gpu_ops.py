@@ -4,6 +4,7 @@ unit tests (file:line cited per test, paths relative to native-engine/)."""
 import datetime as dt
 import decimal
 import math
+import os
 
 import numpy as np
 import pyarrow as pa
@@ -1160,3 +1161,43 @@ def test_inner_join_on_unique_build_keys_passes_the_probe_side_through_a_mask(ke
     for name_, row in exp.iterrows():
         sv = None if m[m.name == name_].v.notna().sum() == 0 else int(row.sv)
         assert agg[name_] == (sv, int(row.cw)), name_
+
+
+def test_device_wide_memory_budget_makes_aggregate_and_sort_spill():
+    # auron-memmgr/src/lib.rs:201-423: one budget shared by every spillable consumer.  With a tiny HBM budget (no per-operator
+    # override) the aggregate spills its partial tables into host buckets and the sorter spills runs, and both still return the
+    # results of the unconstrained run.
+    rng = np.random.default_rng(44)
+    n = 150_000
+    t = pa.table({"k": pa.array(rng.integers(0, 40_000, n), type=pa.int64(), mask=rng.random(n) < 0.01),
+                  "v": pa.array(rng.integers(-10**6, 10**6, n), type=pa.int64(), mask=rng.random(n) < 0.05),
+                  "w": pa.array([f"w{int(i):05d}" for i in rng.integers(0, 50_000, n)])})
+    src = lambda: P.ffi_reader(t.schema, "t")
+    agg = lambda: P.agg(src(), [P.col("k")], ["k"], [P.agg_expr("SUM", [P.col("v")], pa.int64()), P.agg_expr("MAX", [P.col("w")], pa.string())], ["sv", "mw"], ["PARTIAL"] * 2)
+    srt = lambda: P.sort(src(), [P.sort_expr(P.col("v"), True, True), P.sort_expr(P.col("k"), False, False)])
+
+    def go(plan):
+        os.environ["AURON_GPU_CHUNK_ROWS"] = "30000"
+        os.environ["AURON_SORT_RUN_ROWS"] = "30000"
+        try:
+            with runtime.Task(P.task_definition(plan), {"t": batches(t, 25_000)}) as task:
+                out = pa.Table.from_batches(list(task), schema=task.schema)
+                return out, {name: v for _, _, name, v in task.metrics()}
+        finally:
+            os.environ.pop("AURON_GPU_CHUNK_ROWS", None)
+            os.environ.pop("AURON_SORT_RUN_ROWS", None)
+
+    exp_agg, m0 = go(agg())
+    exp_sort, m1 = go(srt())
+    assert m0.get("mem_spill_count", 0) == 0 and m1.get("mem_spill_count", 0) == 0
+    default = runtime.set_hbm_budget(0)
+    assert default > (1 << 30)
+    try:
+        assert runtime.set_hbm_budget(200_000) == 200_000
+        got_agg, ma = go(agg())
+        got_sort, ms = go(srt())
+    finally:
+        assert runtime.set_hbm_budget(0) == default
+    assert ma["mem_spill_count"] >= 1 and ms["mem_spill_count"] >= 1
+    assert_same_rows(got_agg, exp_agg)
+    assert got_sort.column("v").to_pylist() == exp_sort.column("v").to_pylist() and got_sort.column("k").to_pylist() == exp_sort.column("k").to_pylist()

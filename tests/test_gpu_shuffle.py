@@ -351,3 +351,37 @@ def test_corrupt_shuffle_block_is_reported_as_fetch_failure():
         list(task)
     assert task.fetch_failures and task.fetch_failures[0][0] == "blocks" and task.fetch_failures[0][1].startswith("shuffle read:")
     task.close()
+
+
+@pytest.mark.parametrize("codec", ["lz4", "zstd"])
+@pytest.mark.parametrize("pwrite", [False, True])
+def test_shuffle_writer_spills_buffered_chunks_and_writes_the_same_file(tmp_path, codec, pwrite, monkeypatch):
+    # sort_repartitioner.rs:98-112: the repartitioner spills under memory pressure.  Here finished chunks wait in pinned host memory;
+    # with a budget of one byte every chunk goes to a spill file next to the data file, and the final .data / .index must be
+    # byte-identical to the unspilled run (same blocks, same chunk order inside every partition), the spill files gone.
+    t = _table(120_000, seed=77)
+    monkeypatch.setenv("AURON_IO_COMPRESSION_CODEC", codec)
+    monkeypatch.setenv("AURON_GPU_CHUNK_ROWS", "25000")
+    if pwrite:
+        monkeypatch.setenv("AURON_SHUFFLE_PWRITE", "1")
+    files = {}
+    for mode in ("mem", "spill"):
+        if mode == "spill":
+            monkeypatch.setenv("AURON_SHUFFLE_SPILL_BYTES", "1")
+        data, index = str(tmp_path / f"{mode}.data"), str(tmp_path / f"{mode}.index")
+        plan = P.shuffle_writer(P.ffi_reader(t.schema, "t"), P.hash_repartition([P.col("k"), P.col("s")], 17), data, index)
+        with runtime.Task(P.task_definition(plan), {"t": t.to_batches(max_chunksize=25_000)}) as task:
+            assert list(task) == []
+            met = {name: v for _, _, name, v in task.metrics()}
+        files[mode] = (open(data, "rb").read(), open(index, "rb").read(), met)
+    assert files["mem"][2].get("mem_spill_count", 0) == 0 and files["spill"][2]["mem_spill_count"] >= 4
+    assert sorted(os.listdir(tmp_path)) == ["mem.data", "mem.index", "spill.data", "spill.index"]
+    # same rows in the same order inside every partition (the GPU LZ4 match finder is free to pick different matches from run to run,
+    # so the compressed bytes are compared only when the host codec produced them)
+    parts_s, off_s = read_shuffle_files(str(tmp_path / "spill.data"), str(tmp_path / "spill.index"), t.schema, codec)
+    parts_m, off_m = read_shuffle_files(str(tmp_path / "mem.data"), str(tmp_path / "mem.index"), t.schema, codec)
+    assert len(parts_s) == len(parts_m) == 17 and sum(p.num_rows for p in parts_s) == t.num_rows
+    for a, b in zip(parts_s, parts_m):
+        assert a.equals(b)
+    if codec == "zstd":
+        assert files["spill"][0] == files["mem"][0] and files["spill"][1] == files["mem"][1]
