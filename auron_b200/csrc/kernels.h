@@ -127,6 +127,13 @@ struct JoinPairs {
 JoinPairs join_probe(Ctx& ctx, const JoinTable& t, const std::vector<ColumnPtr>& probe_keys, int64_t n_probe, bool probe_outer,
                      uint32_t* matched_build, Buf* probe_matched_out);
 
+// ----------------------------------------------------------------------------- k_window.cu
+// rows sorted by (partition keys, order keys): flags[i] = 1 where row i starts a new group of `keys` (row 0 always; `also`: boundaries to inherit)
+Buf window_boundaries(Ctx& ctx, const std::vector<ColumnPtr>& keys, int64_t n, const uint8_t* also);
+ColumnPtr window_rank_column(Ctx& ctx, int func /* 0 ROW_NUMBER, 1 RANK, 2 DENSE_RANK */, const uint8_t* pflags, const uint8_t* oflags, int64_t n);
+ColumnPtr window_agg_column(Ctx& ctx, int fn /* AggFunction: 0 MIN, 1 MAX, 2 SUM, 3 AVG, 4 COUNT */, const ColumnPtr& arg, const DType& out_type, const uint8_t* pflags, int64_t n);
+Buf window_le_mask(Ctx& ctx, const ColumnPtr& rank_col, int32_t k);   // bit mask of rows with rank <= k (WindowGroupLimit)
+
 // ----------------------------------------------------------------------------- k_sort.cu
 struct SortKeySpec {
     ColumnPtr col;

@@ -1078,6 +1078,82 @@ BatchPtr HashJoinExec::next(Task& t) {
     return out;
 }
 
+// ------------------------------------------------------------------------------------------ WindowExec
+WindowExec::WindowExec(OperatorPtr input, std::vector<ExprPtr> part, std::vector<ExprPtr> order, std::vector<WindowFuncSpec> fs, int64_t limit, bool out_cols)
+    : partition_exprs(std::move(part)), order_exprs(std::move(order)), funcs(std::move(fs)), group_limit(limit), output_window_cols(out_cols) {
+    name = "WindowExec";
+    out_schema = input->out_schema;
+    if (output_window_cols)
+        for (auto& f : funcs) out_schema.fields.push_back(f.field);
+    AURON_CHECK(group_limit < 0 || funcs.size() == 1, "WindowGroupLimit expects exactly one rank-like window function (window_exec.rs:341-344)");
+    for (auto& f : funcs) {
+        if (f.is_agg) AURON_CHECK(f.func >= 0 && f.func <= 4, "window aggregate function #" + std::to_string(f.func) + " is not native in auron_b200 (MIN / MAX / SUM / AVG / COUNT are)");
+        else AURON_CHECK(f.func >= 0 && f.func <= 2, "window function #" + std::to_string(f.func) + " is not native in auron_b200 (ROW_NUMBER / RANK / DENSE_RANK are)");
+    }
+    children.push_back(std::move(input));
+}
+std::string WindowExec::describe() const {
+    std::string o = "\"partition_by\":[";
+    for (size_t i = 0; i < partition_exprs.size(); i++) o += (i ? "," : "") + json_quote(expr_to_string(*partition_exprs[i]));
+    o += "],\"order_by\":[";
+    for (size_t i = 0; i < order_exprs.size(); i++) o += (i ? "," : "") + json_quote(expr_to_string(*order_exprs[i]));
+    o += "],\"functions\":[";
+    static const char* wf[] = {"ROW_NUMBER", "RANK", "DENSE_RANK"};
+    static const char* af[] = {"MIN", "MAX", "SUM", "AVG", "COUNT"};
+    for (size_t i = 0; i < funcs.size(); i++) o += (i ? "," : "") + json_quote(std::string(funcs[i].is_agg ? af[funcs[i].func] : wf[funcs[i].func]) + " AS " + funcs[i].field.name);
+    return o + "],\"group_limit\":" + std::to_string(group_limit) + ",\"output_window_cols\":" + (output_window_cols ? "true" : "false");
+}
+BatchPtr WindowExec::next(Task& t) {
+    if (done) return nullptr;
+    done = true;
+    // every function is a scan over the complete sorted input (the reference streams partition by partition; here the whole input
+    // of the task is one device batch, like the sort below it that produced the order)
+    std::vector<BatchPtr> all;
+    while (BatchPtr b = children[0]->next(t)) {
+        AURON_CHECK(t.is_running(), "task killed");
+        if (b->num_rows) all.push_back(b);
+    }
+    if (all.empty()) return nullptr;
+    BatchPtr in = all.size() == 1 ? all[0] : concat_batches(t.ctx, all);
+    all.clear();
+    OpTimer timer(metrics, "elapsed_ns");
+    const int64_t n = in->num_rows;
+    const Schema& is = children[0]->out_schema;
+    std::vector<ColumnPtr> pk, ok;
+    for (auto& e : partition_exprs) pk.push_back(eval_to_column(t, e, is, *in));
+    for (auto& e : order_exprs) ok.push_back(eval_to_column(t, e, is, *in));
+    Buf pflags = window_boundaries(t.ctx, pk, n, nullptr);
+    Buf oflags = window_boundaries(t.ctx, ok, n, P<uint8_t>(pflags));   // a new partition starts a new peer group
+    std::vector<ColumnPtr> wcols;
+    for (auto& f : funcs) {
+        if (!f.is_agg) {
+            AURON_CHECK(f.field.type.id == T_INT32, "rank-like window functions return int32");
+            wcols.push_back(window_rank_column(t.ctx, f.func, P<uint8_t>(pflags), P<uint8_t>(oflags), n));
+        } else {
+            ColumnPtr arg;
+            if (f.args.empty()) {   // COUNT(*)-like: every row counts
+                AURON_CHECK(f.func == 4, "window aggregate without an argument");
+                arg = make_column(t.ctx, DType(T_INT8), n, false);
+            } else arg = eval_to_column(t, f.args[0], is, *in);
+            wcols.push_back(window_agg_column(t.ctx, f.func, arg, f.field.type, P<uint8_t>(pflags), n));
+        }
+    }
+    auto out = std::make_shared<Batch>();
+    out->num_rows = n;
+    out->cols = in->cols;
+    if (output_window_cols)
+        for (auto& c : wcols) out->cols.push_back(c);
+    if (group_limit >= 0) {   // keep the rows whose rank is <= k (window_exec.rs:341-356)
+        Buf mask = window_le_mask(t.ctx, wcols[0], (int32_t)std::min<int64_t>(group_limit, INT32_MAX));
+        int64_t cnt = 0;
+        Buf idx = mask_to_indices(t.ctx, P<uint32_t>(mask), n, &cnt);
+        if (cnt == 0) return nullptr;
+        if (cnt != n) out = take_batch(t.ctx, *out, P<int32_t>(idx), cnt, false);
+    }
+    metrics.add("output_rows", out->num_rows);
+    return out;
+}
+
 // ------------------------------------------------------------------------------------------ SortMergeJoinExec
 namespace {
 struct BatchListExec : Operator {   // a fixed list of batches as an operator (one piece of one side)

@@ -165,6 +165,26 @@ struct HashJoinExec : Operator {
     Operator& probe_child() { return *children[build_side == SIDE_LEFT ? 1 : 0]; }
 };
 
+// window_exec.rs:162-345 + window/processors/*.rs.  The input arrives sorted by (partition spec, order spec); every window function is a
+// segmented scan over the whole input (k_window.cu).  Built: ROW_NUMBER, RANK, DENSE_RANK, running SUM / COUNT / MIN / MAX / AVG over
+// integers, dates and floats, WindowGroupLimit (keep the rows with rank <= k) and output_window_cols = false.  Not built: LEAD,
+// NTH_VALUE, PERCENT_RANK, CUME_DIST, aggregates over decimals / strings (the planner rejects them by name).
+struct WindowFuncSpec {
+    bool is_agg = false;
+    int func = 0;                 // WindowFunction (ROW_NUMBER 0, RANK 1, DENSE_RANK 2) or AggFunction (MIN 0, MAX 1, SUM 2, AVG 3, COUNT 4)
+    std::vector<ExprPtr> args;
+    Field field;
+};
+struct WindowExec : Operator {
+    std::vector<ExprPtr> partition_exprs, order_exprs;
+    std::vector<WindowFuncSpec> funcs;
+    int64_t group_limit = -1;
+    bool output_window_cols = true, done = false;
+    WindowExec(OperatorPtr input, std::vector<ExprPtr> part, std::vector<ExprPtr> order, std::vector<WindowFuncSpec> fs, int64_t limit, bool out_cols);
+    std::string describe() const override;
+    BatchPtr next(Task& t) override;
+};
+
 // sort_merge_join_exec.rs:135-205,294-372 + joins/smj/*.rs.  Both inputs arrive sorted on the join keys.  The reference advances two
 // row cursors; here the two streams are cut into KEY-DISJOINT pieces (a piece ends where the key of the driving side changes, the
 // other side contributes exactly the rows below that key) and every piece is joined with the hash kernels.  Memory is bounded

@@ -962,6 +962,69 @@ static OperatorPtr decode_plan(Task& t, const uint8_t* b, size_t n) {
                 out.reset(new ExpandExec(std::move(input), schema, std::move(projs)));
                 break;
             }
+            case 22: {   // WindowExecNode{input=1, window_expr=2, partition_spec=3, order_spec=4, group_limit=5{k=1}, output_window_cols=6} (planner.rs:604-760)
+                OperatorPtr input;
+                std::vector<std::vector<uint8_t>> raw_funcs, raw_part, raw_order;
+                int64_t limit = -1;
+                bool out_cols = false;   // proto3: an omitted bool is false
+                while (s.next(&sf, &sw)) {
+                    if (sf == 1 && sw == 2) input = plan_field(t, s);
+                    else if ((sf == 2 || sf == 3 || sf == 4) && sw == 2) {
+                        const uint8_t* eb;
+                        size_t en;
+                        s.bytes_view(&eb, &en);
+                        (sf == 2 ? raw_funcs : sf == 3 ? raw_part : raw_order).emplace_back(eb, eb + en);
+                    } else if (sf == 5 && sw == 2) {
+                        const uint8_t* lb;
+                        size_t ln;
+                        s.bytes_view(&lb, &ln);
+                        PbReader l(lb, ln);
+                        uint32_t lf, lw;
+                        limit = 0;
+                        while (l.next(&lf, &lw)) {
+                            if (lf == 1 && lw == 0) limit = (int64_t)l.varint();
+                            else l.skip(lw);
+                        }
+                    } else if (sf == 6 && sw == 0) out_cols = s.varint() != 0;
+                    else s.skip(sw);
+                }
+                AURON_CHECK(input, "WindowExecNode without input");
+                std::vector<ExprPtr> part, order;
+                for (auto& e : raw_part) part.push_back(decode_expr(e.data(), e.size()));
+                for (auto& e : raw_order) order.push_back(decode_sort_expr(e.data(), e.size()).expr);   // (the direction is the sort's business: only equality of neighbours matters here)
+                std::vector<WindowFuncSpec> funcs;
+                for (auto& wbytes : raw_funcs) {   // WindowExprNode{field=1, return_type=1000, func_type=2, window_func=3, agg_func=4, children=5}
+                    PbReader w(wbytes.data(), wbytes.size());
+                    uint32_t wf, ww;
+                    WindowFuncSpec spec;
+                    int func_type = 0, window_func = 0, agg_func = 0;
+                    bool have_type = false;
+                    while (w.next(&wf, &ww)) {
+                        const uint8_t* vb;
+                        size_t vn;
+                        if (wf == 1 && ww == 2) {
+                            w.bytes_view(&vb, &vn);
+                            spec.field = decode_field(vb, vn);
+                        } else if (wf == 1000 && ww == 2) {
+                            w.bytes_view(&vb, &vn);
+                            spec.field.type = decode_arrow_type(vb, vn);
+                            have_type = true;
+                        } else if (wf == 2 && ww == 0) func_type = (int)w.varint();
+                        else if (wf == 3 && ww == 0) window_func = (int)w.varint();
+                        else if (wf == 4 && ww == 0) agg_func = (int)w.varint();
+                        else if (wf == 5 && ww == 2) {
+                            w.bytes_view(&vb, &vn);
+                            spec.args.push_back(decode_expr(vb, vn));
+                        } else w.skip(ww);
+                    }
+                    (void)have_type;   // return_type repeats the field's type
+                    spec.is_agg = func_type == 1;
+                    spec.func = spec.is_agg ? agg_func : window_func;
+                    funcs.push_back(std::move(spec));
+                }
+                out.reset(new WindowExec(std::move(input), std::move(part), std::move(order), std::move(funcs), limit, out_cols));
+                break;
+            }
             case 4: {   // IpcWriterExecNode{input=1, ipc_consumer_resource_id=2}
                 OperatorPtr input;
                 std::string rid;

@@ -289,6 +289,29 @@ def expand(inp: bytes, s: pa.Schema, projections: list[list[bytes]]) -> bytes:
     return f_bytes(20, body)
 
 
+WINDOW_FUNCTION = {"ROW_NUMBER": 0, "RANK": 1, "DENSE_RANK": 2, "LEAD": 3, "NTH_VALUE": 4, "NTH_VALUE_IGNORE_NULLS": 5, "PERCENT_RANK": 6, "CUME_DIST": 7}
+
+
+def window_expr(name: str, t: pa.DataType, fn: str, children: list[bytes] | None = None) -> bytes:
+    """WindowExprNode{field=1, return_type=1000, func_type=2, window_func=3, agg_func=4, children=5} (auron.proto:575-582); fn is a
+    WindowFunction name or an AggFunction name"""
+    body = f_bytes(1, field(name, t)) + f_bytes(1000, arrow_type(t))
+    if fn in WINDOW_FUNCTION:
+        body += f_varint(2, 0) + f_varint(3, WINDOW_FUNCTION[fn])
+    else:
+        body += f_varint(2, 1) + f_varint(4, AGG_FN[fn])
+    return body + b"".join(f_bytes(5, c) for c in (children or []))
+
+
+def window(inp: bytes, window_exprs: list[bytes], partition_spec: list[bytes], order_spec: list[bytes], group_limit: int | None = None,
+           output_window_cols: bool = True) -> bytes:
+    """PhysicalPlanNode{window} (auron.proto:566-573); order_spec entries are sort expressions (sort_expr)"""
+    body = f_bytes(1, inp) + b"".join(f_bytes(2, w) for w in window_exprs) + b"".join(f_bytes(3, e) for e in partition_spec) + b"".join(f_bytes(4, e) for e in order_spec)
+    if group_limit is not None:
+        body += f_bytes(5, f_varint(1, group_limit, always=True))
+    return f_bytes(22, body + f_varint(6, int(output_window_cols)))
+
+
 def ipc_writer(inp: bytes, consumer_resource_id: str) -> bytes:
     """PhysicalPlanNode{ipc_writer{input, ipc_consumer_resource_id}} (auron.proto:631-634; NativeBroadcastExchangeBase.scala:317-328)"""
     return f_bytes(4, f_bytes(1, inp) + f_str(2, consumer_resource_id))

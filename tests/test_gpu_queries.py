@@ -198,3 +198,93 @@ def test_expand_rollup_aggregate():
     rows = {(a, b, g): [s, c] for a, b, g, s, c in zip(*[got.column(i).to_pylist() for i in range(5)])}
     assert rows == exp
     assert got.schema.field(2).type == pa.int64()
+
+
+def _window_reference(rows, funcs):
+    """The reference's processors restated row by row (window/processors/*.rs): rows = [(p, o, v, f)], already in window order"""
+    out = []
+    cur_p = object()
+    for p, o, v, f in rows:
+        if p != cur_p or isinstance(cur_p, object) and cur_p.__class__ is object:
+            cur_p, cur_o = p, object()
+            rn = rank = dense = 0
+            equals = 1
+            sv = cv = mn = mx = sf = cf = None
+            cv = cf = 0
+        rn += 1
+        if o == cur_o and rn > 1:
+            equals += 1
+        else:
+            rank += equals if rn > 1 else 1
+            dense += 1
+            equals = 1
+            cur_o = o
+        if v is not None:
+            sv = v if sv is None else sv + v
+            cv += 1
+            mn = v if mn is None else min(mn, v)
+            mx = v if mx is None else max(mx, v)
+        if f is not None:
+            sf = f if sf is None else sf + f
+            cf += 1
+        vals = {"ROW_NUMBER": rn, "RANK": rank, "DENSE_RANK": dense, "SUM_v": sv, "COUNT_v": cv, "MIN_v": mn, "MAX_v": mx,
+                "AVG_v": None if cv == 0 else sv / cv, "SUM_f": sf}
+        out.append(tuple(vals[k] for k in funcs))
+    return out
+
+
+@pytest.mark.parametrize("n,n_parts", [(5_000, 40), (300_000, 7), (120_000, 30_000)])
+def test_window_functions_over_sorted_partitions(n, n_parts):
+    # WindowExec (window_exec.rs:162-345): input sorted by (partition, order); ROW_NUMBER / RANK / DENSE_RANK and running SUM / COUNT /
+    # MIN / MAX / AVG per row.  Partitions far larger than a scan block (300k rows in 7 partitions), far smaller (4 rows each), NULL
+    # partition / order keys (one group each), ties in the order key, NULL arguments.
+    rng = np.random.default_rng(n)
+    t = pa.table({"p": pa.array(rng.integers(0, n_parts, n), type=pa.int32(), mask=rng.random(n) < 0.02),
+                  "o": pa.array(rng.integers(0, max(3, n // n_parts // 3), n), type=pa.int64(), mask=rng.random(n) < 0.03),
+                  "v": pa.array(rng.integers(-1000, 1000, n), type=pa.int64(), mask=rng.random(n) < 0.1),
+                  "f": pa.array(np.round(rng.standard_normal(n), 3), mask=rng.random(n) < 0.1)})
+    src = P.sort(P.ffi_reader(t.schema, "t"), [P.sort_expr(P.col("p")), P.sort_expr(P.col("o"))])
+    I, L, F = pa.int32(), pa.int64(), pa.float64()
+    wex = [P.window_expr("rn", I, "ROW_NUMBER"), P.window_expr("rk", I, "RANK"), P.window_expr("dr", I, "DENSE_RANK"),
+           P.window_expr("sv", L, "SUM", [P.col("v")]), P.window_expr("cv", L, "COUNT", [P.col("v")]), P.window_expr("mn", L, "MIN", [P.col("v")]),
+           P.window_expr("mx", L, "MAX", [P.col("v")]), P.window_expr("av", F, "AVG", [P.col("v")]), P.window_expr("sf", F, "SUM", [P.col("f")])]
+    plan = P.window(src, wex, [P.col("p")], [P.sort_expr(P.col("o"))])
+    got = run(plan, {"t": t}, chunk=50_000)
+    assert got.num_rows == n and got.schema.names == ["p", "o", "v", "f", "rn", "rk", "dr", "sv", "cv", "mn", "mx", "av", "sf"]
+    rows = list(zip(*[got[c].to_pylist() for c in ["p", "o", "v", "f"]]))
+    assert sorted(rows, key=repr) == sorted(zip(*[t[c].to_pylist() for c in ["p", "o", "v", "f"]]), key=repr)          # same rows
+    keys = [(r[0] is not None, r[0] if r[0] is not None else 0, r[1] is not None, r[1] if r[1] is not None else 0) for r in rows]
+    assert keys == sorted(keys)                                                                                       # in window order
+    exp = _window_reference(rows, ["ROW_NUMBER", "RANK", "DENSE_RANK", "SUM_v", "COUNT_v", "MIN_v", "MAX_v", "AVG_v", "SUM_f"])
+    out = list(zip(*[got[c].to_pylist() for c in ["rn", "rk", "dr", "sv", "cv", "mn", "mx", "av", "sf"]]))
+    for i, (g, e) in enumerate(zip(out, exp)):
+        assert g[:7] == e[:7], (i, rows[i], g, e)
+        for a, b in zip(g[7:], e[7:]):                       # float results: scan order differs from row order (1e-6 relative, north_star)
+            assert (a is None) == (b is None) and (a is None or abs(a - b) <= 1e-6 * max(1.0, abs(b))), (i, g, e)
+
+
+@pytest.mark.parametrize("out_cols", [True, False])
+def test_window_group_limit_keeps_the_top_ranks(out_cols):
+    # WindowGroupLimit (window_exec.rs:56-65,341-356): rows whose rank is <= k, with or without the rank column
+    rng = np.random.default_rng(9)
+    n = 60_000
+    t = pa.table({"p": pa.array(rng.integers(0, 500, n), type=pa.int32()), "o": pa.array(rng.integers(0, 40, n), type=pa.int64()),
+                  "s": pa.array([f"s{int(x)}" for x in rng.integers(0, 100, n)])})
+    src = P.sort(P.ffi_reader(t.schema, "t"), [P.sort_expr(P.col("p")), P.sort_expr(P.col("o"), False, False)])
+    plan = P.window(src, [P.window_expr("rk", pa.int32(), "RANK")], [P.col("p")], [P.sort_expr(P.col("o"), False, False)], group_limit=2, output_window_cols=out_cols)
+    got = run(plan, {"t": t})
+    assert got.schema.names == (["p", "o", "s", "rk"] if out_cols else ["p", "o", "s"])
+    import collections
+    by_p = collections.defaultdict(list)
+    for p, o, s in zip(t["p"].to_pylist(), t["o"].to_pylist(), t["s"].to_pylist()):
+        by_p[p].append((o, s))
+    exp = []
+    for p, items in by_p.items():
+        top = sorted({o for o, _ in items}, reverse=True)
+        first = top[0]
+        n_first = sum(1 for o, _ in items if o == first)
+        keep = {first} | ({top[1]} if len(top) > 1 and n_first < 2 else set())          # RANK: the second value has rank 1 + (rows of the first)
+        exp += [(p, o, s) for o, s in items if o in keep]
+    assert sorted(zip(got["p"].to_pylist(), got["o"].to_pylist(), got["s"].to_pylist())) == sorted(exp)
+    if out_cols:
+        assert set(got["rk"].to_pylist()) <= {1, 2}
