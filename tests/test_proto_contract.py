@@ -240,8 +240,9 @@ def test_planner_rejects_what_is_outside_the_path_with_a_message():
     L.auron_b200_explain.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_int64]
     L.auron_b200_last_error.restype = C.c_char_p
     src = P.ffi_reader(T, "in")
-    window = P.f_bytes(22, P.f_bytes(1, src))                                     # PhysicalPlanNode{window}: not on the path
-    for plan, needle in [(window, ""), (b"\x0a\x03abc", ""), (P.filter_(src, []), "predicate")]:
+    generate = P.f_bytes(23, P.f_bytes(1, src))                                   # PhysicalPlanNode{generate}: not on the path
+    lead = P.window(src, [P.window_expr("l", pa.int64(), "LEAD", [P.col("a")])], [], [])   # a window function that is not built
+    for plan, needle in [(generate, "not native"), (lead, "not native"), (b"\x0a\x03abc", ""), (P.filter_(src, []), "predicate")]:
         td = P.task_definition(plan) if plan != b"\x0a\x03abc" else plan
         assert L.auron_b200_explain(td, len(td), None, 0) == -1
         assert needle in L.auron_b200_last_error().decode().lower()
@@ -363,3 +364,22 @@ def test_expand_and_partitioned_scan_decode_on_the_cpu():
     assert {("FileScanExecConf", "partition_schema"), ("PartitionedFile", "partition_values"), ("ParquetScanExecNode", "pruning_predicates")} <= seen
     d = _explain(scan)["plan"]
     assert d["op"] == "ParquetExec" and [f[0] for f in d["schema"]] == ["y", "day", "region", "x"]      # projection order over [file columns..., partition columns...]
+
+
+def test_window_node_decodes_on_the_cpu():
+    # WindowExecNode / WindowExprNode / WindowGroupLimit (auron.proto:566-591): bytes checked against the reference schema, then the
+    # planner's operator (planner.rs:604-760)
+    src = P.sort(P.ffi_reader(T, "in"), [P.sort_expr(P.col("a")), P.sort_expr(P.col("b"))])
+    w = P.window(src, [P.window_expr("rk", pa.int32(), "RANK"), P.window_expr("sb", pa.int64(), "SUM", [P.col("b")])], [P.col("a")], [P.sort_expr(P.col("b"))])
+    seen = set()
+    walk("PhysicalPlanNode", w, seen)
+    assert {("WindowExecNode", "window_expr"), ("WindowExecNode", "partition_spec"), ("WindowExecNode", "order_spec"), ("WindowExprNode", "return_type"),
+            ("WindowExprNode", "agg_func"), ("WindowExprNode", "children")} <= seen
+    d = _explain(w)["plan"]
+    assert d["op"] == "WindowExec" and d["functions"] == ["RANK AS rk", "SUM AS sb"] and d["partition_by"] == ["col(a)"] and d["order_by"] == ["col(b)"]
+    assert [f[0] for f in d["schema"]][-2:] == ["rk", "sb"] and d["output_window_cols"] is True and d["group_limit"] == -1
+    lim = P.window(src, [P.window_expr("rk", pa.int32(), "RANK")], [P.col("a")], [P.sort_expr(P.col("b"))], group_limit=3, output_window_cols=False)
+    walk("PhysicalPlanNode", lim, seen)
+    assert ("WindowGroupLimit", "k") in seen
+    d = _explain(lim)["plan"]
+    assert d["group_limit"] == 3 and d["output_window_cols"] is False and [f[0] for f in d["schema"]] == [f.name for f in T]
