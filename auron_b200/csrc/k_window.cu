@@ -200,6 +200,8 @@ Buf window_scan_f64(Ctx& ctx, const double* in, const uint8_t* flags, int64_t n,
     return seg_scan<double, WOP_MAX>(ctx, in, flags, n);
 }
 
+static unsigned wgrid(int64_t n) { return (unsigned)((n + 255) / 256); }
+
 // ---- element-wise helpers around the scans
 __global__ void __launch_bounds__(256) win_fill_i64(long long* out, int64_t n, long long v) {
     const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -249,8 +251,6 @@ __global__ void __launch_bounds__(256) win_le_mask(const int32_t* __restrict__ v
     const uint32_t w = __ballot_sync(FULL_MASK, i < n && v[i] <= k);
     if (lane_id() == 0 && i < n) mask[i >> 5] = w;
 }
-
-static unsigned wgrid(int64_t n) { return (unsigned)((n + 255) / 256); }
 
 ColumnPtr window_rank_column(Ctx& ctx, int func, const uint8_t* pflags, const uint8_t* oflags, int64_t n) {
     // func: 0 ROW_NUMBER, 1 RANK, 2 DENSE_RANK ; Int32 output like the reference's builders
@@ -348,6 +348,131 @@ ColumnPtr window_agg_column(Ctx& ctx, int fn, const ColumnPtr& arg, const DType&
         }
     }
     return out;
+}
+
+// ---- functions that look at the whole partition: PERCENT_RANK, CUME_DIST, LEAD, NTH_VALUE (window/processors/{percent_rank,cume_dist,
+// lead,nth_value}_processor.rs).  Everything is derived from per-row scans plus one scatter to the first row of a group:
+//   start[i]   first row of row i's partition            running max of (boundary ? i : 0)
+//   size       rows of the partition                     row number of the partition's last row, scattered to start, gathered back
+//   peer end   rows of the partition up to the end of the current peer group: the same with the order boundaries
+__global__ void __launch_bounds__(256) win_start_seed(const uint8_t* __restrict__ flags, int64_t n, long long* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) out[i] = flags[i] ? i : 0;
+}
+// rn of the last row of every group (flags mark group starts) -> at_start[start of the group]
+__global__ void __launch_bounds__(256) win_scatter_last(const long long* __restrict__ rn, const uint8_t* __restrict__ flags, const long long* __restrict__ start, int64_t n,
+                                                        long long* __restrict__ at_start) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n && (i == n - 1 || flags[i + 1])) at_start[start[i]] = rn[i];
+}
+__global__ void __launch_bounds__(256) win_percent_rank_kernel(const long long* __restrict__ rank, const long long* __restrict__ size_at, const long long* __restrict__ pstart, int64_t n,
+                                                               double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const long long size = size_at[pstart[i]];
+    out[i] = size <= 1 ? 0.0 : (double)(rank[i] - 1) / (double)(size - 1);
+}
+__global__ void __launch_bounds__(256) win_cume_dist_kernel(const long long* __restrict__ peer_at, const long long* __restrict__ ostart, const long long* __restrict__ size_at,
+                                                            const long long* __restrict__ pstart, int64_t n, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) out[i] = (double)peer_at[ostart[i]] / (double)size_at[pstart[i]];
+}
+// LEAD: row i + offset if it lies in the same partition, else the row's default, which sits at n + i of the concatenated (values, defaults) column
+__global__ void __launch_bounds__(256) win_lead_idx(const long long* __restrict__ pstart, int64_t n, int64_t offset, int32_t* __restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int64_t t = i + offset;
+    idx[i] = (t >= 0 && t < n && pstart[t] == pstart[i]) ? (int32_t)t : (int32_t)(n + i);
+}
+// NTH_VALUE: the row at which the running count reaches `nth` for the first time -> at_start; then -1 (NULL) until the count is there
+__global__ void __launch_bounds__(256) win_nth_scatter(const long long* __restrict__ cnt, const uint8_t* __restrict__ counts_here, const long long* __restrict__ pstart, int64_t n,
+                                                       long long nth, long long* __restrict__ at_start) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n && cnt[i] == nth && counts_here[i]) at_start[pstart[i]] = i;
+}
+__global__ void __launch_bounds__(256) win_nth_idx(const long long* __restrict__ cnt, const long long* __restrict__ pstart, const long long* __restrict__ at_start, int64_t n, long long nth,
+                                                   int32_t* __restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) idx[i] = cnt[i] >= nth ? (int32_t)at_start[pstart[i]] : -1;
+}
+__global__ void __launch_bounds__(256) win_valid_bytes(const uint8_t* __restrict__ valid, int64_t n, uint8_t* __restrict__ out, long long* __restrict__ as_i64) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const bool ok = !valid || bit_get(valid, i);
+    out[i] = ok ? 1 : 0;
+    as_i64[i] = ok ? 1 : 0;
+}
+
+struct WinFrame {   // per-row scans shared by the functions below
+    Buf first_only, pstart, rn, size_at;
+};
+static WinFrame win_frame(Ctx& ctx, const uint8_t* pflags, int64_t n) {
+    WinFrame f;
+    f.first_only = window_boundaries(ctx, {}, n, nullptr);   // a flag on row 0 only: turns the segmented scan into a plain one
+    Buf seed = dalloc(ctx, (size_t)n * 8);
+    win_start_seed<<<wgrid(n), 256, 0, ctx.stream>>>(pflags, n, P<long long>(seed));
+    LAUNCH_CHECK(ctx);
+    f.pstart = window_scan_i64(ctx, P<long long>(seed), P<uint8_t>(f.first_only), n, WOP_MAX);
+    win_fill_i64<<<wgrid(n), 256, 0, ctx.stream>>>(P<long long>(seed), n, 1);
+    LAUNCH_CHECK(ctx);
+    f.rn = window_scan_i64(ctx, P<long long>(seed), pflags, n, WOP_ADD);
+    f.size_at = dalloc(ctx, (size_t)n * 8);
+    win_scatter_last<<<wgrid(n), 256, 0, ctx.stream>>>(P<long long>(f.rn), pflags, P<long long>(f.pstart), n, P<long long>(f.size_at));
+    LAUNCH_CHECK(ctx);
+    return f;
+}
+ColumnPtr window_dist_column(Ctx& ctx, int func /* 6 PERCENT_RANK, 7 CUME_DIST */, const uint8_t* pflags, const uint8_t* oflags, int64_t n) {
+    auto col = make_column(ctx, DType(T_FLOAT64), n, false);
+    if (n == 0) return col;
+    WinFrame f = win_frame(ctx, pflags, n);
+    Buf tmp = dalloc(ctx, (size_t)n * 8);
+    if (func == 6) {
+        win_rank_seed<<<wgrid(n), 256, 0, ctx.stream>>>(P<long long>(f.rn), oflags, n, P<long long>(tmp));
+        LAUNCH_CHECK(ctx);
+        Buf rank = window_scan_i64(ctx, P<long long>(tmp), pflags, n, WOP_MAX);
+        win_percent_rank_kernel<<<wgrid(n), 256, 0, ctx.stream>>>(P<long long>(rank), P<long long>(f.size_at), P<long long>(f.pstart), n, P<double>(col->data));
+        LAUNCH_CHECK(ctx);
+    } else {
+        win_start_seed<<<wgrid(n), 256, 0, ctx.stream>>>(oflags, n, P<long long>(tmp));
+        LAUNCH_CHECK(ctx);
+        Buf ostart = window_scan_i64(ctx, P<long long>(tmp), P<uint8_t>(f.first_only), n, WOP_MAX);
+        Buf peer_at = dalloc(ctx, (size_t)n * 8);
+        win_scatter_last<<<wgrid(n), 256, 0, ctx.stream>>>(P<long long>(f.rn), oflags, P<long long>(ostart), n, P<long long>(peer_at));
+        LAUNCH_CHECK(ctx);
+        win_cume_dist_kernel<<<wgrid(n), 256, 0, ctx.stream>>>(P<long long>(peer_at), P<long long>(ostart), P<long long>(f.size_at), P<long long>(f.pstart), n, P<double>(col->data));
+        LAUNCH_CHECK(ctx);
+    }
+    return col;
+}
+// values and defaults have the same type and n rows each
+ColumnPtr window_lead_column(Ctx& ctx, const ColumnPtr& values, const ColumnPtr& defaults, int64_t offset, const uint8_t* pflags, int64_t n) {
+    if (n == 0) return values;
+    AURON_CHECK(2 * n < (int64_t)INT32_MAX, "LEAD over more than 2^30 rows in one task");
+    WinFrame f = win_frame(ctx, pflags, n);
+    Buf idx = dalloc(ctx, (size_t)n * 4);
+    win_lead_idx<<<wgrid(n), 256, 0, ctx.stream>>>(P<long long>(f.pstart), n, offset, P<int32_t>(idx));
+    LAUNCH_CHECK(ctx);
+    Batch both;
+    both.num_rows = 2 * n;
+    both.cols.push_back(concat_columns(ctx, {values, defaults}));
+    return take_batch(ctx, both, P<int32_t>(idx), n, false)->cols[0];
+}
+ColumnPtr window_nth_column(Ctx& ctx, const ColumnPtr& values, int64_t nth, bool ignore_nulls, const uint8_t* pflags, int64_t n) {
+    if (n == 0) return values;
+    WinFrame f = win_frame(ctx, pflags, n);
+    Buf counts_here = dalloc(ctx, (size_t)n), seed = dalloc(ctx, (size_t)n * 8);
+    win_valid_bytes<<<wgrid(n), 256, 0, ctx.stream>>>(ignore_nulls ? values->vbits() : nullptr, n, P<uint8_t>(counts_here), P<long long>(seed));
+    LAUNCH_CHECK(ctx);
+    Buf cnt = window_scan_i64(ctx, P<long long>(seed), pflags, n, WOP_ADD);
+    Buf at = dalloc(ctx, (size_t)n * 8), idx = dalloc(ctx, (size_t)n * 4);
+    win_nth_scatter<<<wgrid(n), 256, 0, ctx.stream>>>(P<long long>(cnt), P<uint8_t>(counts_here), P<long long>(f.pstart), n, nth, P<long long>(at));
+    LAUNCH_CHECK(ctx);
+    win_nth_idx<<<wgrid(n), 256, 0, ctx.stream>>>(P<long long>(cnt), P<long long>(f.pstart), P<long long>(at), n, nth, P<int32_t>(idx));
+    LAUNCH_CHECK(ctx);
+    Batch one;
+    one.num_rows = n;
+    one.cols.push_back(values);
+    return take_batch(ctx, one, P<int32_t>(idx), n, true)->cols[0];
 }
 
 Buf window_le_mask(Ctx& ctx, const ColumnPtr& rank_col, int32_t k) {

@@ -132,6 +132,9 @@ JoinPairs join_probe(Ctx& ctx, const JoinTable& t, const std::vector<ColumnPtr>&
 Buf window_boundaries(Ctx& ctx, const std::vector<ColumnPtr>& keys, int64_t n, const uint8_t* also);
 ColumnPtr window_rank_column(Ctx& ctx, int func /* 0 ROW_NUMBER, 1 RANK, 2 DENSE_RANK */, const uint8_t* pflags, const uint8_t* oflags, int64_t n);
 ColumnPtr window_agg_column(Ctx& ctx, int fn /* AggFunction: 0 MIN, 1 MAX, 2 SUM, 3 AVG, 4 COUNT */, const ColumnPtr& arg, const DType& out_type, const uint8_t* pflags, int64_t n);
+ColumnPtr window_dist_column(Ctx& ctx, int func /* 6 PERCENT_RANK, 7 CUME_DIST */, const uint8_t* pflags, const uint8_t* oflags, int64_t n);
+ColumnPtr window_lead_column(Ctx& ctx, const ColumnPtr& values, const ColumnPtr& defaults, int64_t offset, const uint8_t* pflags, int64_t n);
+ColumnPtr window_nth_column(Ctx& ctx, const ColumnPtr& values, int64_t nth, bool ignore_nulls, const uint8_t* pflags, int64_t n);
 Buf window_le_mask(Ctx& ctx, const ColumnPtr& rank_col, int32_t k);   // bit mask of rows with rank <= k (WindowGroupLimit)
 
 // ----------------------------------------------------------------------------- k_sort.cu

@@ -1088,7 +1088,12 @@ WindowExec::WindowExec(OperatorPtr input, std::vector<ExprPtr> part, std::vector
     AURON_CHECK(group_limit < 0 || funcs.size() == 1, "WindowGroupLimit expects exactly one rank-like window function (window_exec.rs:341-344)");
     for (auto& f : funcs) {
         if (f.is_agg) AURON_CHECK(f.func >= 0 && f.func <= 4, "window aggregate function #" + std::to_string(f.func) + " is not native in auron_b200 (MIN / MAX / SUM / AVG / COUNT are)");
-        else AURON_CHECK(f.func >= 0 && f.func <= 2, "window function #" + std::to_string(f.func) + " is not native in auron_b200 (ROW_NUMBER / RANK / DENSE_RANK are)");
+        else {
+            AURON_CHECK(f.func >= 0 && f.func <= 7, "window function #" + std::to_string(f.func) + " is not native in auron_b200");
+            auto int_literal = [&](size_t i) { return f.args.size() > i && f.args[i]->kind == E_LITERAL && !f.args[i]->lit.is_null && f.args[i]->lit.type.width() > 0 && f.args[i]->lit.type.width() <= 8; };
+            if (f.func == 3) AURON_CHECK(f.args.size() == 3 && int_literal(1), "LEAD expects input / literal integer offset / default children (lead_processor.rs:40-63)");
+            if (f.func == 4 || f.func == 5) AURON_CHECK(f.args.size() == 2 && int_literal(1) && f.args[1]->lit.i > 0, "NTH_VALUE expects input / positive literal offset children (nth_value_processor.rs:36-66)");
+        }
     }
     children.push_back(std::move(input));
 }
@@ -1098,7 +1103,7 @@ std::string WindowExec::describe() const {
     o += "],\"order_by\":[";
     for (size_t i = 0; i < order_exprs.size(); i++) o += (i ? "," : "") + json_quote(expr_to_string(*order_exprs[i]));
     o += "],\"functions\":[";
-    static const char* wf[] = {"ROW_NUMBER", "RANK", "DENSE_RANK"};
+    static const char* wf[] = {"ROW_NUMBER", "RANK", "DENSE_RANK", "LEAD", "NTH_VALUE", "NTH_VALUE_IGNORE_NULLS", "PERCENT_RANK", "CUME_DIST"};
     static const char* af[] = {"MIN", "MAX", "SUM", "AVG", "COUNT"};
     for (size_t i = 0; i < funcs.size(); i++) o += (i ? "," : "") + json_quote(std::string(funcs[i].is_agg ? af[funcs[i].func] : wf[funcs[i].func]) + " AS " + funcs[i].field.name);
     return o + "],\"group_limit\":" + std::to_string(group_limit) + ",\"output_window_cols\":" + (output_window_cols ? "true" : "false");
@@ -1126,9 +1131,20 @@ BatchPtr WindowExec::next(Task& t) {
     Buf oflags = window_boundaries(t.ctx, ok, n, P<uint8_t>(pflags));   // a new partition starts a new peer group
     std::vector<ColumnPtr> wcols;
     for (auto& f : funcs) {
-        if (!f.is_agg) {
+        if (!f.is_agg && f.func <= 2) {
             AURON_CHECK(f.field.type.id == T_INT32, "rank-like window functions return int32");
             wcols.push_back(window_rank_column(t.ctx, f.func, P<uint8_t>(pflags), P<uint8_t>(oflags), n));
+        } else if (!f.is_agg && (f.func == 6 || f.func == 7)) {
+            AURON_CHECK(f.field.type.id == T_FLOAT64, "PERCENT_RANK / CUME_DIST return float64");
+            wcols.push_back(window_dist_column(t.ctx, f.func, P<uint8_t>(pflags), P<uint8_t>(oflags), n));
+        } else if (!f.is_agg && f.func == 3) {   // LEAD(input, offset, default)
+            ColumnPtr vals = eval_to_column(t, f.args[0], is, *in);
+            ColumnPtr dflt = (f.args[2]->kind == E_LITERAL && f.args[2]->lit.is_null) ? make_null_column(t.ctx, vals->type, n) : eval_to_column(t, f.args[2], is, *in);
+            AURON_CHECK(dflt->type == vals->type, "LEAD: the default is " + dflt->type.str() + ", the input " + vals->type.str());
+            wcols.push_back(window_lead_column(t.ctx, vals, dflt, f.args[1]->lit.i, P<uint8_t>(pflags), n));
+        } else if (!f.is_agg) {                  // NTH_VALUE [IGNORE NULLS](input, n)
+            ColumnPtr vals = eval_to_column(t, f.args[0], is, *in);
+            wcols.push_back(window_nth_column(t.ctx, vals, f.args[1]->lit.i, f.func == 5, P<uint8_t>(pflags), n));
         } else {
             ColumnPtr arg;
             if (f.args.empty()) {   // COUNT(*)-like: every row counts

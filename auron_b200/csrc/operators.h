@@ -166,12 +166,13 @@ struct HashJoinExec : Operator {
 };
 
 // window_exec.rs:162-345 + window/processors/*.rs.  The input arrives sorted by (partition spec, order spec); every window function is a
-// segmented scan over the whole input (k_window.cu).  Built: ROW_NUMBER, RANK, DENSE_RANK, running SUM / COUNT / MIN / MAX / AVG over
-// integers, dates and floats, WindowGroupLimit (keep the rows with rank <= k) and output_window_cols = false.  Not built: LEAD,
-// NTH_VALUE, PERCENT_RANK, CUME_DIST, aggregates over decimals / strings (the planner rejects them by name).
+// segmented scan (+ one scatter / gather for the functions that look at the whole partition) over the whole input (k_window.cu).
+// Built: ROW_NUMBER, RANK, DENSE_RANK, PERCENT_RANK, CUME_DIST, LEAD, NTH_VALUE [IGNORE NULLS], running SUM / COUNT / MIN / MAX / AVG
+// over integers, dates and floats, WindowGroupLimit (keep the rows with rank <= k) and output_window_cols = false.  Not built:
+// aggregates over decimals / strings (rejected by name).
 struct WindowFuncSpec {
     bool is_agg = false;
-    int func = 0;                 // WindowFunction (ROW_NUMBER 0, RANK 1, DENSE_RANK 2) or AggFunction (MIN 0, MAX 1, SUM 2, AVG 3, COUNT 4)
+    int func = 0;                 // WindowFunction (auron.proto:128-137) or AggFunction (MIN 0, MAX 1, SUM 2, AVG 3, COUNT 4)
     std::vector<ExprPtr> args;
     Field field;
 };

@@ -288,3 +288,56 @@ def test_window_group_limit_keeps_the_top_ranks(out_cols):
     assert sorted(zip(got["p"].to_pylist(), got["o"].to_pylist(), got["s"].to_pylist())) == sorted(exp)
     if out_cols:
         assert set(got["rk"].to_pylist()) <= {1, 2}
+
+
+def test_window_functions_that_look_at_the_whole_partition():
+    # PERCENT_RANK, CUME_DIST, LEAD (positive / negative offset, NULL and non-NULL default, strings), NTH_VALUE [IGNORE NULLS]
+    # (window/processors/{percent_rank,cume_dist,lead,nth_value}_processor.rs restated in Python over the engine's own row order)
+    rng = np.random.default_rng(77)
+    n = 90_000
+    t = pa.table({"p": pa.array(rng.integers(0, 900, n), type=pa.int32(), mask=rng.random(n) < 0.01),
+                  "o": pa.array(rng.integers(0, 25, n), type=pa.int64(), mask=rng.random(n) < 0.03),
+                  "v": pa.array(rng.integers(-1000, 1000, n), type=pa.int64(), mask=rng.random(n) < 0.2),
+                  "s": pa.array([f"s{int(x)}" for x in rng.integers(0, 500, n)], mask=rng.random(n) < 0.1)})
+    src = P.sort(P.ffi_reader(t.schema, "t"), [P.sort_expr(P.col("p")), P.sort_expr(P.col("o"))])
+    I, L, F, S = pa.int32(), pa.int64(), pa.float64(), pa.string()
+    wex = [P.window_expr("pr", F, "PERCENT_RANK"), P.window_expr("cd", F, "CUME_DIST"),
+           P.window_expr("lead1", L, "LEAD", [P.col("v"), P.lit(1, I), P.lit(None, L)]),
+           P.window_expr("lag2", L, "LEAD", [P.col("v"), P.lit(-2, I), P.lit(-7, L)]),
+           P.window_expr("leads", S, "LEAD", [P.col("s"), P.lit(3, I), P.lit("none", S)]),
+           P.window_expr("nth3", L, "NTH_VALUE", [P.col("v"), P.lit(3, I)]),
+           P.window_expr("nth2nn", S, "NTH_VALUE_IGNORE_NULLS", [P.col("s"), P.lit(2, L)])]
+    got = run(P.window(src, wex, [P.col("p")], [P.sort_expr(P.col("o"))]), {"t": t}, chunk=40_000)
+    rows = list(zip(*[got[c].to_pylist() for c in ["p", "o", "v", "s"]]))
+    assert len(rows) == n
+    # partitions and peer groups in the output order
+    exp = []
+    i = 0
+    while i < n:
+        j = i
+        while j < n and rows[j][0] == rows[i][0]:
+            j += 1
+        part = rows[i:j]
+        size = len(part)
+        k = 0
+        rank = 1
+        while k < size:
+            m = k
+            while m < size and part[m][1] == part[k][1]:
+                m += 1
+            for q in range(k, m):
+                pr = 0.0 if size <= 1 else (rank - 1) / (size - 1)
+                cd = m / size
+                lead1 = part[q + 1][2] if q + 1 < size else None
+                lag2 = part[q - 2][2] if q - 2 >= 0 else -7
+                leads = part[q + 3][3] if q + 3 < size else "none"
+                nth3 = part[2][2] if q >= 2 else None
+                nn = [x[3] for x in part[:q + 1] if x[3] is not None]
+                nth2nn = nn[1] if len(nn) >= 2 else None
+                exp.append((pr, cd, lead1, lag2, leads, nth3, nth2nn))
+            rank += m - k
+            k = m
+        i = j
+    out = list(zip(*[got[c].to_pylist() for c in ["pr", "cd", "lead1", "lag2", "leads", "nth3", "nth2nn"]]))
+    for r, (g, e) in enumerate(zip(out, exp)):
+        assert abs(g[0] - e[0]) < 1e-12 and abs(g[1] - e[1]) < 1e-12 and g[2:] == e[2:], (r, rows[r], g, e)

@@ -241,7 +241,7 @@ def test_planner_rejects_what_is_outside_the_path_with_a_message():
     L.auron_b200_last_error.restype = C.c_char_p
     src = P.ffi_reader(T, "in")
     generate = P.f_bytes(23, P.f_bytes(1, src))                                   # PhysicalPlanNode{generate}: not on the path
-    lead = P.window(src, [P.window_expr("l", pa.int64(), "LEAD", [P.col("a")])], [], [])   # a window function that is not built
+    lead = P.window(src, [P.window_expr("l", pa.int32(), "FIRST", [P.col("a")])], [], [])   # a window aggregate that is not built
     for plan, needle in [(generate, "not native"), (lead, "not native"), (b"\x0a\x03abc", ""), (P.filter_(src, []), "predicate")]:
         td = P.task_definition(plan) if plan != b"\x0a\x03abc" else plan
         assert L.auron_b200_explain(td, len(td), None, 0) == -1
