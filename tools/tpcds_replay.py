@@ -7,7 +7,8 @@ row by row in result order -- doubles within 1e-6, everything else by its string
 No Spark / JVM exists in this image, so the plans are written here by hand in the shape Spark plans them (broadcast hash joins on
 the dimension tables, partial + final hash aggregate, TakeOrderedAndProject as sort-with-limit) and the expected results come from
 pandas over the very same tables.  Queries: q3, q42, q52, q55 (date_dim x store_sales x item star joins), q7 (four dimensions, AVG of
-an integer and of three decimals), q43 (CASE WHEN sums per weekday), q96 (three dimensions, global COUNT).
+an integer and of three decimals), q43 (CASE WHEN sums per weekday), q67 (the ranking core: RANK() OVER (PARTITION BY ... ORDER BY sum DESC)
+with a rank filter), q96 (three dimensions, global COUNT).
 
     python tools/tpcds_replay.py [--rows 2000000] [--dir /tmp/auron_tpcds] [--queries q3,q7]
 
@@ -263,7 +264,44 @@ def q96(q, fr):
     return plan, ["cnt"], [(len(m),)]
 
 
-QUERIES = {"q3": q3, "q7": q7, "q42": q42, "q43": q43, "q52": q52, "q55": q55, "q96": q96}
+def q67(q, fr):
+    # the ranking core of q67 / q70 (ROLLUP left out): the five best (brand, year) cells of every category by revenue
+    # select * from (select i_category, i_brand, d_year, sumsales, rank() over (partition by i_category order by sumsales desc) rk
+    #                from (select i_category, i_brand, d_year, sum(ss_ext_sales_price) sumsales from store_sales, date_dim, item
+    #                      where ss_sold_date_sk = d_date_sk and ss_item_sk = i_item_sk group by i_category, i_brand, d_year) where sumsales is not null)
+    # where rk <= 5 order by i_category, rk, i_brand, d_year limit 100
+    dd, ddf = q.dim("date_dim", ["d_date_sk", "d_year"], [], ["d_date_sk", "d_year"])
+    it, itf = q.dim("item", ["i_item_sk", "i_category", "i_brand"], [], ["i_item_sk", "i_category", "i_brand"])
+    ss, ssf = q.scan("store_sales", ["ss_sold_date_sk", "ss_item_sk", "ss_ext_sales_price"])
+    ss = P.filter_(ss, [P.is_not_null(P.col("ss_sold_date_sk"))])
+    j, f = q.bjoin(ss, ssf, dd, ddf, "ss_sold_date_sk", "d_date_sk")
+    j, f = q.bjoin(j, f, it, itf, "ss_item_sk", "i_item_sk")
+    keys = ["i_category", "i_brand", "d_year"]
+    types = {x.name: x.type for x in f}
+    proj = P.projection(j, [P.col(c) for c in keys + ["ss_ext_sales_price"]], keys + ["ss_ext_sales_price"], [types[c] for c in keys + ["ss_ext_sales_price"]])
+    agg = P.filter_(q.two_phase(proj, keys, [("SUM", "ss_ext_sales_price", pa.decimal128(17, 2), "sumsales")]), [P.is_not_null(P.col("sumsales"))])
+    order = [P.sort_expr(P.col("i_category"), True, True), P.sort_expr(P.col("sumsales"), False, False)]
+    win = P.window(P.sort(agg, order), [P.window_expr("rk", I, "RANK")], [P.col("i_category")], [P.sort_expr(P.col("sumsales"), False, False)])
+    top = P.filter_(win, [P.binary("LtEq", P.col("rk"), P.lit(5, I))])
+    cols = keys + ["sumsales", "rk"]
+    plan = P.sort(top, [P.sort_expr(P.col(c), True, True) for c in ["i_category", "rk", "i_brand", "d_year"]], limit=100)
+    m = fr["store_sales"].merge(fr["date_dim"], left_on="ss_sold_date_sk", right_on="d_date_sk").merge(fr["item"], left_on="ss_item_sk", right_on="i_item_sk")
+    cells = []
+    for key, g in m.groupby(keys, dropna=False):
+        sm = _sum_dec(g.ss_ext_sales_price)
+        if sm is not None:
+            cells.append(tuple(None if (isinstance(k, float) and np.isnan(k)) else (int(k) if isinstance(k, (np.integer, float)) else k) for k in key) + (sm,))
+    rows = []
+    for cat in {c[0] for c in cells}:
+        part = [c for c in cells if c[0] == cat]
+        for c in part:
+            rk = 1 + sum(1 for o in part if o[3] > c[3])
+            if rk <= 5:
+                rows.append(c + (rk,))
+    return plan, cols, _order(rows, [(0, True, True), (4, True, True), (1, True, True), (2, True, True)])[:100]
+
+
+QUERIES = {"q3": q3, "q7": q7, "q42": q42, "q43": q43, "q52": q52, "q55": q55, "q67": q67, "q96": q96}
 
 
 # ---------------------------------------------------------------------------------------------------------------- the comparator
