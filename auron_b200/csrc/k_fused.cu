@@ -10,10 +10,13 @@
 //                                 each with a checkpoint of the dictionary-index stream -- so tiles of columns whose pages
 //                                 do not line up are still short lists of segments
 //   dict    (tiny)                the filter's interval test is evaluated ONCE per dictionary entry -> 1 bit per entry
-//   fused   (one warp per tile)   predicate columns are unpacked to pass bits, the selection of the tile is built with
-//                                 ballots; tiles without a selected row stop here.  Then the key column is unpacked to
-//                                 accumulator slots and the argument columns to values, and the selected rows update the
-//                                 accumulators with L2 reductions (RED).
+//   staged  (persistent warps)    tiles whose columns are single segments of regular index streams (or PLAIN pages): the packed
+//                                 bytes of the tile go to shared memory with one bulk copy per column (cp.async.bulk + mbarrier);
+//                                 the predicate column is unpacked for the lane's rows, key and arguments only for the rows that
+//                                 pass; the selected rows update the accumulators with L2 reductions (RED).  See fz_staged_kernel.
+//   tile    (one warp per tile)   the tiles the staged kernel leaves on a work list (a page boundary inside the tile, RLE runs,
+//                                 PLAIN fallback pages): the general segment walk -- predicate columns to pass bits with ballots,
+//                                 key and argument columns to shared-memory planes, then the same row loop.
 //   merge   (per batch)           see below
 //
 // Aggregation in dictionary space: a dictionary-encoded group key is never looked up.  A row's slot is its dictionary
@@ -22,8 +25,10 @@
 // the batch one thread per dictionary entry folds its accumulators into the direct table at key - kmin.  PLAIN key pages
 // address the direct table straight away.
 //
-// Roofline: HBM-bound on the encoded bytes (the only DRAM traffic that scales with rows); the row loop is bound by the SM's
-// LSU issue rate for RED (1.29 cycles per lane per SM, B300_MICROARCH.md "Atomics").
+// Roofline: the only DRAM traffic that scales with rows is the encoded bytes (measured: 1.67 GB per SF100 pass against 1.44 GB
+// algorithmic), but the kernels are bound by unpacking variable-width bit streams, not by moving them: ~3,900 warp instructions
+// per 1024-row tile, 48 % of the issue slots (DESIGN.md section 6c has the history of what moved that number and what did not --
+// more loads in flight and fewer atomics did not).
 #include "device_utils.cuh"
 #include "kernels.h"
 #include "parquet_dev.h"

@@ -7,9 +7,14 @@
 //   1. plan   : footers (Thrift), row-group selection by file range, list of column chunks
 //   2. fetch  : HBM-resident file images are used in place; host files are pread by a thread pool into one pinned
 //               staging buffer and uploaded with a single async copy
-//   3. parse  : page headers of every chunk (Thrift) in parallel on host threads -> page / dictionary descriptors;
-//               SNAPPY / ZSTD / LZ4_RAW pages are decompressed here (UNCOMPRESSED pages are decoded in place)
-//   4. decode : k_parquet.cu, one scout + one decode launch per column
+//   3. parse  : page headers of every chunk (Thrift) in parallel on host threads -> page / dictionary descriptors and the list of
+//               device decompression jobs (SNAPPY: k_snappy.cu; large literal chains are split into stored-copy jobs here, tags
+//               only); ZSTD / LZ4_RAW pages are decompressed on the host cores, UNCOMPRESSED pages are decoded in place;
+//               delta-encoded string pages are rewritten as PLAIN, Hive partition columns become constant columns, row groups
+//               that the pruning predicates exclude by their statistics are skipped at plan time
+//   4. decode : k_parquet.cu, one scout launch for all columns + one decode launch per column -- or, when the plan above is
+//               Filter -> HashAggregate of the supported shape, next_fused(): the batch goes through k_fused.cu instead and no
+//               column is materialised (three batches in flight on their own stream pairs, see next_fused)
 #include <dlfcn.h>
 #include <fcntl.h>
 #include <unistd.h>
