@@ -833,9 +833,53 @@ struct ParquetScanExec : Operator, FusedScanSource {
     // same L1 / LSU pipes and for HBM, so overlapping them conserves the total; the mode stays opt-in (AURON_SCAN_LANES=1).
     static constexpr int kLanes = 3;
     std::vector<std::unique_ptr<Ctx>> lanes;
+    std::vector<int> lane_priority;
     bool use_lanes = getenv("AURON_SCAN_LANES") != nullptr;
+    // Lane contexts (a stream + its staged-upload arena) outlive the scan that used them: every task is a new ParquetScanExec, and six
+    // stream creations / destructions per task are host time inside a 5.6 ms step; idle lanes wait in a process-wide pool instead
+    // (which also keeps the stream-ordered allocator's per-stream caches warm).
+    struct LanePool {
+        std::mutex mu;
+        struct Idle {
+            std::unique_ptr<Ctx> ctx;
+            int device, priority;
+        };
+        std::vector<Idle> idle;
+        std::unique_ptr<Ctx> take(int device, int priority) {
+            {
+                std::lock_guard<std::mutex> g(mu);
+                for (size_t i = 0; i < idle.size(); i++)
+                    if (idle[i].device == device && idle[i].priority == priority) {
+                        std::unique_ptr<Ctx> c = std::move(idle[i].ctx);
+                        idle.erase(idle.begin() + (long)i);
+                        return c;
+                    }
+            }
+            return std::unique_ptr<Ctx>(new Ctx(device, priority));
+        }
+        void give(std::unique_ptr<Ctx> c, int priority) {
+            if (!c || !c->stream) return;
+            try {
+                c->sync();   // idle by now (the scan has retired its batches); also recycles the lane's staged-upload arena
+            } catch (...) {
+                return;      // (called from a destructor: a stream in an error state is simply not kept)
+            }
+            c->prof.clear();
+            c->kernel_launches = 0;
+            std::lock_guard<std::mutex> g(mu);
+            if (idle.size() < 24) idle.push_back(Idle{std::move(c), 0, priority}), idle.back().device = idle.back().ctx->device;
+        }
+    };
+    static LanePool& lane_pool() {
+        static LanePool* p = new LanePool();   // (never destroyed: streams must not be torn down after the CUDA runtime at process exit)
+        return *p;
+    }
     Ctx& lane(Task& t, int i, int priority = 0) {
-        while ((int)lanes.size() <= i) lanes.emplace_back(new Ctx(t.ctx.device, priority));
+        while ((int)lanes.size() <= i) {
+            lanes.push_back(lane_pool().take(t.ctx.device, priority));
+            lanes.back()->profile = t.ctx.profile;
+            lane_priority.push_back(priority);
+        }
         return *lanes[(size_t)i];
     }
     static void chain(cudaStream_t from, cudaStream_t to) {   // work queued on `to` from here on runs after everything queued on `from` so far
@@ -1253,6 +1297,8 @@ struct ParquetScanExec : Operator, FusedScanSource {
         }
         inflight.clear();
         stop();
+        for (size_t i = 0; i < lanes.size(); i++) lane_pool().give(std::move(lanes[i]), lane_priority[i]);
+        lanes.clear();
         if (copy_stream) {
             cudaStreamSynchronize(copy_stream);
             cudaStreamDestroy(copy_stream);
