@@ -79,6 +79,12 @@ std::string describe(const char* path) {
             // engine's own block decoder as a check of sizes
             auto chunk = read_range(f, cm.start_offset(), cm.total_compressed);
             int64_t pos = 0, values = 0, pages = 0, dict_pages = 0, unc = 0, snappy_checked = 0;
+            // the scan's host-side helpers, exercised here on the CPU: the tag walk that splits a Snappy body into a head and stored
+            // literal pieces (checked against the decompressed body), and the decoders of the DELTA encodings (count + wrapping sum of
+            // the integers, count + byte total + FNV-1a of the PLAIN transcription of the strings)
+            int64_t split_pages = 0, split_head_out = 0, split_stored = 0, delta_pages = 0, delta_values = 0, delta_bytes = 0;
+            uint64_t delta_sum = 0, delta_fnv = 1469598103934665603ull;
+            const int max_def = (c + 1 < md.schema.size() && md.schema[c + 1].repetition == 1) ? 1 : 0;   // flat schemas: leaf c is element c + 1
             std::string encodings;
             while (pos < cm.total_compressed) {
                 pq::PageHeader h = pq::parse_page_header(chunk.data() + pos, (size_t)(cm.total_compressed - pos));
@@ -93,16 +99,71 @@ std::string describe(const char* path) {
                 }
                 unc += h.uncompressed_size + h.header_len;
                 const int lvl = h.type == pq::PAGE_DATA_V2 ? h.def_bytes + h.rep_bytes : 0;
+                std::vector<uint8_t> out;   // uncompressed body behind the v2 level bytes (SNAPPY and UNCOMPRESSED chunks)
+                bool have_body = false;
                 if (cm.codec == pq::CODEC_SNAPPY && !(h.type == pq::PAGE_DATA_V2 && !h.v2_compressed) && h.uncompressed_size > lvl) {
-                    std::vector<uint8_t> out((size_t)(h.uncompressed_size - lvl) + 8);
+                    out.resize((size_t)(h.uncompressed_size - lvl) + 8);
                     pq::snappy_decompress(body + lvl, (size_t)(h.compressed_size - lvl), out.data(), (size_t)(h.uncompressed_size - lvl));
                     snappy_checked++;
+                    have_body = true;
+                    std::vector<pq::LitPiece> pieces;
+                    int64_t head_in = 0, head_out = 0;
+                    const int64_t body_out = h.uncompressed_size - lvl;
+                    if (pq::snappy_split(body + lvl, h.compressed_size - lvl, body_out, 4096, &head_in, &head_out, &pieces) && !pieces.empty()) {
+                        int64_t at = head_out;
+                        for (auto& pc : pieces) {   // the literals behind the last back reference must be the tail of the body, byte for byte
+                            AURON_CHECK(at + pc.len <= body_out && memcmp(out.data() + at, body + lvl + pc.src_off, (size_t)pc.len) == 0, "snappy_split: a literal piece does not match the decompressed body");
+                            at += pc.len;
+                        }
+                        AURON_CHECK(at == body_out, "snappy_split: the pieces do not end at the end of the body");
+                        split_pages++;
+                        split_head_out += head_out;
+                        split_stored += body_out - head_out;
+                    }
+                } else if ((cm.codec == pq::CODEC_UNCOMPRESSED || (h.type == pq::PAGE_DATA_V2 && !h.v2_compressed)) && h.uncompressed_size > lvl) {
+                    out.assign(body + lvl, body + h.compressed_size);
+                    out.resize(out.size() + 8);
+                    have_body = true;
+                }
+                const bool delta = h.encoding == pq::ENC_DELTA_BINARY_PACKED || h.encoding == pq::ENC_DELTA_LENGTH_BYTE_ARRAY || h.encoding == pq::ENC_DELTA_BYTE_ARRAY;
+                if (have_body && delta && (h.type == pq::PAGE_DATA || h.type == pq::PAGE_DATA_V2)) {
+                    size_t vo = 0;   // value section inside `out`
+                    if (h.type == pq::PAGE_DATA && max_def > 0) {
+                        uint32_t dl = 0;
+                        memcpy(&dl, out.data(), 4);
+                        vo = 4 + (size_t)dl;
+                    }
+                    const size_t vlen = (size_t)(h.uncompressed_size - lvl) - vo;
+                    if (h.encoding == pq::ENC_DELTA_BINARY_PACKED) {
+                        std::vector<int64_t> vals;
+                        size_t dp = 0;
+                        pq::delta_binary_decode(out.data() + vo, vlen, dp, vals);
+                        delta_values += (int64_t)vals.size();
+                        for (int64_t v : vals) delta_sum += (uint64_t)(cm.type == pq::PT_INT32 ? (int64_t)(int32_t)v : v);
+                    } else {
+                        int32_t nv = 0;
+                        const std::vector<uint8_t> plain = pq::delta_strings_to_plain(out.data() + vo, vlen, h.encoding == pq::ENC_DELTA_BYTE_ARRAY, &nv);
+                        delta_values += nv;
+                        delta_bytes += (int64_t)plain.size() - 4 * (int64_t)nv;
+                        size_t q = 0;
+                        for (int32_t k = 0; k < nv; k++) {   // FNV-1a over the value bytes, a 0xFF between values
+                            uint32_t len;
+                            memcpy(&len, plain.data() + q, 4);
+                            q += 4;
+                            for (uint32_t b = 0; b < len; b++) delta_fnv = (delta_fnv ^ plain[q + b]) * 1099511628211ull;
+                            delta_fnv = (delta_fnv ^ 0xFFu) * 1099511628211ull;
+                            q += len;
+                        }
+                    }
+                    delta_pages++;
                 }
                 pos += h.header_len + h.compressed_size;
             }
             AURON_CHECK(pos == cm.total_compressed, "page headers do not tile the column chunk");
             o << ",\"data_pages\":" << pages << ",\"dictionary_pages\":" << dict_pages << ",\"page_values\":" << values << ",\"pages_uncompressed\":" << unc
-              << ",\"snappy_pages_decompressed\":" << snappy_checked << ",\"page_encodings\":[" << encodings << "]}";
+              << ",\"snappy_pages_decompressed\":" << snappy_checked << ",\"snappy_split_pages\":" << split_pages << ",\"snappy_split_head_bytes\":" << split_head_out
+              << ",\"snappy_split_stored_bytes\":" << split_stored << ",\"delta_pages\":" << delta_pages << ",\"delta_values\":" << delta_values << ",\"delta_sum\":\""
+              << delta_sum << "\",\"delta_string_bytes\":" << delta_bytes << ",\"delta_fnv\":\"" << delta_fnv << "\",\"page_encodings\":[" << encodings << "]}";
         }
         o << "]}";
     }

@@ -61,5 +61,17 @@ PageHeader parse_page_header(const uint8_t* buf, size_t len);
 // raw snappy block decompression (format description: snappy framing-less block format)
 void snappy_decompress(const uint8_t* in, size_t in_len, uint8_t* out, size_t out_len);
 
+// ---- host helpers of the scan (scan_parquet.cc), here so that auron_b200_parquet_describe can exercise them on the CPU
+struct LitPiece {
+    int64_t src_off, len;
+};
+// Walks the elements of a raw Snappy block by their tags only.  True when the block is well formed within `max_tokens` elements; then
+// [0, *head_in) / [0, *head_out) are the compressed / uncompressed bytes up to and including the last back reference and `pieces` the
+// literals behind it (offsets into p).
+bool snappy_split(const uint8_t* p, int64_t n, int64_t unc, int max_tokens, int64_t* head_in, int64_t* head_out, std::vector<LitPiece>* pieces);
+// one DELTA_BINARY_PACKED stream at p[pos...] -> values; pos ends behind the stream
+void delta_binary_decode(const uint8_t* p, size_t n, size_t& pos, std::vector<int64_t>& out);
+// value section of a DELTA_LENGTH_BYTE_ARRAY (`front_coded` false) or DELTA_BYTE_ARRAY page -> PLAIN ([u32 length][bytes] ...)
+std::vector<uint8_t> delta_strings_to_plain(const uint8_t* p, size_t n, bool front_coded, int32_t* n_values);
 }  // namespace pq
 }  // namespace auron

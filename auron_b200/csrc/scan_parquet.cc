@@ -457,154 +457,14 @@ struct ParquetScanExec : Operator, FusedScanSource {
     }
     // `p[0, n)` is a Snappy block of `unc` bytes made only of literals (incompressible data: one literal per 64 KB fragment of
     // the compressor): fills their (offset in p, length) and returns true; at most `max_pieces`
-    struct LitPiece {
-        int64_t src_off, len;
-    };
-    static bool snappy_literal_chain(const uint8_t* p, int64_t n, int64_t unc, size_t max_pieces, std::vector<LitPiece>* pieces) {
-        int64_t i = 0, out = 0;
-        uint64_t v = 0;
-        for (int shift = 0;; shift += 7) {
-            if (i >= n || shift > 28) return false;
-            const uint8_t b = p[i++];
-            v |= (uint64_t)(b & 0x7f) << shift;
-            if (!(b & 0x80)) break;
-        }
-        if ((int64_t)v != unc || unc <= 0) return false;
-        pieces->clear();
-        while (i < n) {
-            const uint8_t tag = p[i++];
-            if (tag & 3) return false;   // a back reference
-            int64_t len = (tag >> 2) + 1;
-            if (len > 60) {
-                const int nb = (int)len - 60;
-                if (i + nb > n) return false;
-                uint32_t w = 0;
-                for (int k = 0; k < nb; k++) w |= (uint32_t)p[i + k] << (8 * k);
-                i += nb;
-                len = (int64_t)w + 1;
-            }
-            if (len > n - i || len > unc - out || pieces->size() >= max_pieces) return false;
-            pieces->push_back(LitPiece{i, len});
-            i += len;
-            out += len;
-        }
-        return out == unc;
-    }
-    // Walk the elements of a raw Snappy block without decoding it (tags only).  True when the block is well formed up to
-    // `max_tokens` elements; then [0, *head_in) / [0, *head_out) are the compressed / uncompressed bytes up to and including the
-    // last back reference, and `pieces` are the literals after it (nothing refers back into them or reads them again).
+    using LitPiece = pq::LitPiece;
+    // (the tag walk of a Snappy block and the host decoders of the delta string encodings live in parquet_meta.cc, where
+    // auron_b200_parquet_describe exercises them on the CPU)
     static bool snappy_split(const uint8_t* p, int64_t n, int64_t unc, int max_tokens, int64_t* head_in, int64_t* head_out, std::vector<LitPiece>* pieces) {
-        int64_t i = 0, out = 0;
-        uint64_t v = 0;
-        for (int shift = 0;; shift += 7) {
-            if (i >= n || shift > 28) return false;
-            const uint8_t b = p[i++];
-            v |= (uint64_t)(b & 0x7f) << shift;
-            if (!(b & 0x80)) break;
-        }
-        if ((int64_t)v != unc || unc <= 0) return false;
-        pieces->clear();
-        *head_in = i;
-        *head_out = 0;
-        for (int tok = 0; i < n; tok++) {
-            if (tok >= max_tokens) return false;
-            const uint8_t tag = p[i++];
-            if ((tag & 3) == 0) {
-                int64_t len = (tag >> 2) + 1;
-                if (len > 60) {
-                    const int nb = (int)len - 60;
-                    if (i + nb > n) return false;
-                    uint32_t w = 0;
-                    for (int k = 0; k < nb; k++) w |= (uint32_t)p[i + k] << (8 * k);
-                    i += nb;
-                    len = (int64_t)w + 1;
-                }
-                if (len > n - i || len > unc - out) return false;
-                pieces->push_back(LitPiece{i, len});
-                i += len;
-                out += len;
-            } else {
-                const int64_t len = (tag & 3) == 1 ? 4 + ((tag >> 2) & 7) : (tag >> 2) + 1;
-                i += (tag & 3) == 1 ? 1 : (tag & 3) == 2 ? 2 : 4;
-                if (i > n || len > unc - out) return false;
-                out += len;
-                pieces->clear();        // literals before a back reference belong to the head
-                *head_in = i;
-                *head_out = out;
-            }
-        }
-        return out == unc;
+        return pq::snappy_split(p, n, unc, max_tokens, head_in, head_out, pieces);
     }
-    // ---- DELTA_LENGTH_BYTE_ARRAY / DELTA_BYTE_ARRAY string pages are rewritten as PLAIN on the host (each value of the second
-    // depends on the bytes of the one before it; both are rare next to dictionary and PLAIN pages)
-    static bool delta_varint(const uint8_t* p, size_t n, size_t& pos, uint64_t& v) {
-        v = 0;
-        for (int shift = 0; shift < 70; shift += 7) {
-            if (pos >= n) return false;
-            const uint8_t b = p[pos++];
-            v |= (uint64_t)(b & 0x7f) << shift;
-            if (!(b & 0x80)) return true;
-        }
-        return false;
-    }
-    // one DELTA_BINARY_PACKED stream at p[pos...] -> values; pos ends behind the stream
-    static void delta_binary_decode(const uint8_t* p, size_t n, size_t& pos, std::vector<int64_t>& out) {
-        uint64_t bs = 0, nm = 0, total = 0, fv = 0;
-        AURON_CHECK(delta_varint(p, n, pos, bs) && delta_varint(p, n, pos, nm) && delta_varint(p, n, pos, total) && delta_varint(p, n, pos, fv), "corrupt DELTA_BINARY_PACKED header");
-        AURON_CHECK(nm > 0 && nm <= 512 && bs > 0 && bs <= (1u << 20) && bs % nm == 0 && (bs / nm) % 8 == 0 && total <= (1ull << 31), "corrupt DELTA_BINARY_PACKED header");
-        const size_t per_mini = (size_t)(bs / nm);
-        out.clear();
-        out.reserve((size_t)total);
-        uint64_t last = (fv >> 1) ^ (0 - (fv & 1));
-        if (total) out.push_back((int64_t)last);
-        while (out.size() < total) {
-            uint64_t md = 0;
-            AURON_CHECK(delta_varint(p, n, pos, md) && pos + nm <= n, "corrupt DELTA_BINARY_PACKED block");
-            const uint64_t min_delta = (md >> 1) ^ (0 - (md & 1));
-            const uint8_t* widths = p + pos;
-            pos += (size_t)nm;
-            for (size_t m = 0; m < nm && out.size() < total; m++) {
-                const unsigned bw = widths[m];
-                const size_t bytes = per_mini * bw / 8;
-                AURON_CHECK(bw <= 64 && pos + bytes <= n, "corrupt DELTA_BINARY_PACKED miniblock");
-                for (size_t i = 0; i < per_mini && out.size() < total; i++) {
-                    uint64_t d = 0;
-                    const size_t bit = i * bw;
-                    for (unsigned k = 0; k < bw; k++) {
-                        const size_t b = bit + k;
-                        d |= (uint64_t)((p[pos + (b >> 3)] >> (b & 7)) & 1) << k;
-                    }
-                    last += min_delta + d;
-                    out.push_back((int64_t)last);
-                }
-                pos += bytes;
-            }
-        }
-    }
-    // value section of a DELTA_LENGTH_BYTE_ARRAY (`front_coded` false) or DELTA_BYTE_ARRAY page -> PLAIN ([u32 length][bytes] ...)
     static std::vector<uint8_t> delta_strings_to_plain(const uint8_t* p, size_t n, bool front_coded, int32_t* n_values) {
-        size_t pos = 0;
-        std::vector<int64_t> prefix, lens;
-        if (front_coded) delta_binary_decode(p, n, pos, prefix);
-        delta_binary_decode(p, n, pos, lens);
-        AURON_CHECK(!front_coded || prefix.size() == lens.size(), "corrupt DELTA_BYTE_ARRAY page");
-        std::vector<uint8_t> out;
-        size_t prev_at = 0, prev_len = 0;
-        for (size_t i = 0; i < lens.size(); i++) {
-            const int64_t pl = front_coded ? prefix[i] : 0, sl = lens[i];
-            AURON_CHECK(pl >= 0 && sl >= 0 && (size_t)pl <= prev_len && (size_t)sl <= n - pos && pl + sl <= INT32_MAX, "corrupt delta-encoded string page");
-            const uint32_t len = (uint32_t)(pl + sl);
-            const size_t at = out.size();
-            out.resize(at + 4 + len);
-            memcpy(out.data() + at, &len, 4);
-            if (pl) memmove(out.data() + at + 4, out.data() + prev_at + 4, (size_t)pl);
-            memcpy(out.data() + at + 4 + pl, p + pos, (size_t)sl);
-            pos += (size_t)sl;
-            prev_at = at;
-            prev_len = len;
-        }
-        *n_values = (int32_t)lens.size();
-        return out;
+        return pq::delta_strings_to_plain(p, n, front_coded, n_values);
     }
     static bool gpu_snappy() {
         return getenv("AURON_HOST_SNAPPY") == nullptr;   // AURON_HOST_SNAPPY=1: decompress on the host cores instead

@@ -303,3 +303,86 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cc", ".cu", ".h", ".cuh")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in src and "auron_oracle" not in src, f
+
+
+def _describe(path):
+    import ctypes as C
+    import json
+    L = runtime.lib()
+    L.auron_b200_parquet_describe.restype = C.c_int64
+    L.auron_b200_parquet_describe.argtypes = [C.c_char_p, C.c_char_p, C.c_int64]
+    buf = C.create_string_buffer(8 << 20)
+    assert L.auron_b200_parquet_describe(path.encode(), buf, len(buf)) > 0, buf.value
+    return json.loads(buf.value.decode())
+
+
+@pytest.mark.parametrize("compression", ["NONE", "SNAPPY"])
+@pytest.mark.parametrize("version", ["1.0", "2.0"])
+def test_delta_decoders_of_the_scan_against_arrow_on_the_cpu(tmp_path, compression, version):
+    # the host decoders the scan uses for DELTA_LENGTH_BYTE_ARRAY / DELTA_BYTE_ARRAY pages (rewritten as PLAIN before upload) and the
+    # host restatement of DELTA_BINARY_PACKED (the device kernel walks the same block structure): every value of every page, checked
+    # through count, wrapping sum (integers) and byte total + FNV-1a (strings) against the columns as Arrow C++ reads them back
+    import numpy as np
+    import pyarrow.parquet as pq
+    rng = np.random.default_rng(5)
+    n = 70_001
+    t = pa.table({"sorted32": pa.array(np.sort(rng.integers(-2**31, 2**31 - 1, n)).astype(np.int32), mask=rng.random(n) < 0.03),
+                  "noise64": pa.array(rng.integers(-2**63, 2**63 - 1, n, dtype=np.int64), mask=rng.random(n) < 0.02),
+                  "req64": pa.array(np.cumsum(rng.integers(0, 1000, n)).astype(np.int64)),
+                  "dl": pa.array([f"w{int(i) * 37 % 1013}" for i in rng.integers(0, 10**6, n)], mask=rng.random(n) < 0.05),
+                  "db": pa.array(sorted(f"key-{int(x):09d}" for x in rng.integers(0, 10**9, n)))},
+                 schema=pa.schema([("sorted32", pa.int32()), ("noise64", pa.int64()), pa.field("req64", pa.int64(), nullable=False), ("dl", pa.string()), ("db", pa.string())]))
+    enc = {"sorted32": "DELTA_BINARY_PACKED", "noise64": "DELTA_BINARY_PACKED", "req64": "DELTA_BINARY_PACKED", "dl": "DELTA_LENGTH_BYTE_ARRAY", "db": "DELTA_BYTE_ARRAY"}
+    path = str(tmp_path / "delta.parquet")
+    pq.write_table(t, path, compression=compression, use_dictionary=False, column_encoding=enc, data_page_version=version, row_group_size=30_000, data_page_size=32 * 1024)
+    d = _describe(path)
+    back = pq.read_table(path)
+    got = {name: [0, 0, 0, 1469598103934665603, 0] for name in t.column_names}     # values, sum, bytes, fnv, pages
+    for rg in d["row_groups"]:
+        for cm in rg["columns"]:
+            g = got[cm["path"]]
+            g[0] += cm["delta_values"]
+            g[1] = (g[1] + int(cm["delta_sum"])) % 2**64
+            g[2] += cm["delta_string_bytes"]
+            g[4] += cm["delta_pages"]
+            assert cm["delta_pages"] == cm["data_pages"] >= 1
+    for name in ("sorted32", "noise64", "req64"):
+        col = back[name].combine_chunks()
+        vals = col.drop_null().to_numpy(zero_copy_only=False).astype(np.int64)
+        assert got[name][0] == len(vals) and got[name][1] == int(vals.astype(np.uint64).sum(dtype=np.uint64)), name
+    for name in ("dl", "db"):
+        vals = [v.encode() for v in back[name].to_pylist() if v is not None]
+        assert got[name][0] == len(vals) and got[name][2] == sum(len(v) for v in vals), name
+    # the per-chunk FNV values chain per column only inside one chunk: check them chunk by chunk
+    for g_i, rg in enumerate(d["row_groups"]):
+        lo = sum(x["num_rows"] for x in d["row_groups"][:g_i])
+        for cm in rg["columns"]:
+            if cm["path"] not in ("dl", "db"):
+                continue
+            h = 1469598103934665603
+            for v in back[cm["path"]].slice(lo, rg["num_rows"]).to_pylist():
+                if v is None:
+                    continue
+                for b in v.encode():
+                    h = ((h ^ b) * 1099511628211) % 2**64
+                h = ((h ^ 0xFF) * 1099511628211) % 2**64
+            assert int(cm["delta_fnv"]) == h, cm["path"]
+
+
+def test_snappy_bodies_are_split_into_head_and_literal_pieces_on_the_cpu(tmp_path):
+    # pq::snappy_split (the tag walk the scan uses to turn the literal chain behind the last back reference of a page body into
+    # independent stored-copy jobs): auron_b200_parquet_describe checks every split against the fully decompressed body; here the
+    # shapes -- incompressible 1 MB pages split (a short head for the level bytes), compressible pages do not
+    import numpy as np
+    import pyarrow.parquet as pq
+    rng = np.random.default_rng(8)
+    n = 600_000
+    t = pa.table({"noise": pa.array(rng.integers(-2**31, 2**31 - 1, n).astype(np.int32), mask=rng.random(n) < 0.05),
+                  "runs": pa.array(np.repeat(rng.integers(0, 50, n // 1000 + 1), 1000)[:n].astype(np.int32))})
+    path = str(tmp_path / "split.parquet")
+    pq.write_table(t, path, compression="SNAPPY", use_dictionary=False, row_group_size=n, write_page_index=False)
+    d = _describe(path)
+    noise, runs = d["row_groups"][0]["columns"]
+    assert noise["snappy_split_pages"] == noise["data_pages"] >= 1
+    assert noise["snappy_split_stored_bytes"] > 0.95 * 4 * n * 0.95 and noise["snappy_split_head_bytes"] < 0.05 * 4 * n
+    assert runs["snappy_split_pages"] == 0 or runs["snappy_split_stored_bytes"] < 0.2 * 4 * n
