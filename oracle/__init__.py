@@ -261,6 +261,76 @@ def sort_table_canonical(t: pa.Table) -> pa.Table:
     return t.take(idx)
 
 
+def window_functions(rows, partition_of, order_of, specs):
+    """WindowExec's processors restated row by row (datafusion-ext-plans/src/window/processors/*.rs) over `rows` that are already in
+    window order.  partition_of(row) / order_of(row) give the partition / order key; specs = [(function, argument getter or None, extra)]:
+      ROW_NUMBER (row_number_processor.rs:37-66), RANK / DENSE_RANK (rank_processor.rs:47-80),
+      SUM / COUNT / MIN / MAX / AVG: the accumulator after every row (agg_processor.rs:49-93),
+      PERCENT_RANK (percent_rank_processor.rs:40-86), CUME_DIST (cume_dist_processor.rs:40-81),
+      LEAD with extra = (offset, default getter) (lead_processor.rs:38-109), NTH_VALUE / NTH_VALUE_IGNORE_NULLS with extra = n
+      (nth_value_processor.rs:82-120).
+    Returns one tuple per row."""
+    n = len(rows)
+    out = [[None] * len(specs) for _ in range(n)]
+    i = 0
+    while i < n:
+        j = i
+        while j < n and partition_of(rows[j]) == partition_of(rows[i]):
+            j += 1
+        part = rows[i:j]
+        size = len(part)
+        rank = dense = 0
+        equals = 1
+        acc = [dict(s=None, c=0, mn=None, mx=None, nth=None, seen=0) for _ in specs]
+        k = 0
+        peer_end = 0
+        for q, row in enumerate(part):
+            if q == 0 or order_of(row) != order_of(part[q - 1]):
+                rank += equals if q else 1
+                dense += 1
+                equals = 1
+                peer_end = q
+                while peer_end < size and order_of(part[peer_end]) == order_of(row):
+                    peer_end += 1
+            else:
+                equals += 1
+            for c, (fn, arg, extra) in enumerate(specs):
+                a = acc[c]
+                v = arg(row) if arg else None
+                if fn == "ROW_NUMBER":
+                    r = q + 1
+                elif fn == "RANK":
+                    r = rank
+                elif fn == "DENSE_RANK":
+                    r = dense
+                elif fn == "PERCENT_RANK":
+                    r = 0.0 if size <= 1 else (rank - 1) / (size - 1)
+                elif fn == "CUME_DIST":
+                    r = peer_end / size
+                elif fn == "LEAD":
+                    off, dflt = extra
+                    t = q + off
+                    r = arg(part[t]) if 0 <= t < size else dflt(row)
+                elif fn in ("NTH_VALUE", "NTH_VALUE_IGNORE_NULLS"):
+                    if a["nth"] is None and (fn == "NTH_VALUE" or v is not None):
+                        a["seen"] += 1
+                        if a["seen"] == extra:
+                            a["nth"] = (v,)
+                    r = a["nth"][0] if a["nth"] is not None else None
+                else:
+                    if fn == "COUNT" and arg is None:
+                        a["c"] += 1
+                    elif v is not None:
+                        a["s"] = v if a["s"] is None else a["s"] + v
+                        a["c"] += 1
+                        a["mn"] = v if a["mn"] is None else min(a["mn"], v)
+                        a["mx"] = v if a["mx"] is None else max(a["mx"], v)
+                    r = {"SUM": a["s"], "COUNT": a["c"], "MIN": a["mn"], "MAX": a["mx"], "AVG": None if a["c"] == 0 or a["s"] is None else a["s"] / a["c"]}[fn]
+                out[i + q][c] = r
+        i = j
+    return [tuple(r) for r in out]
+
+
 # ---------------------------------------------------------------- expression functions (E4 / rounding)
 def spark_round(value, scale: int, kind: str, in_scale: int = 0, half_even: bool = False):
     """spark_round / spark_bround on ONE column value (array branch: datafusion-ext-functions/src/spark_round.rs:62-132,

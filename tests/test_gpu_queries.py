@@ -10,6 +10,7 @@ import pyarrow as pa
 import pyarrow.parquet as pq
 import pytest
 
+import oracle
 from auron_b200 import proto as P
 from auron_b200 import runtime
 from helpers import run
@@ -200,39 +201,6 @@ def test_expand_rollup_aggregate():
     assert got.schema.field(2).type == pa.int64()
 
 
-def _window_reference(rows, funcs):
-    """The reference's processors restated row by row (window/processors/*.rs): rows = [(p, o, v, f)], already in window order"""
-    out = []
-    cur_p = object()
-    for p, o, v, f in rows:
-        if p != cur_p or isinstance(cur_p, object) and cur_p.__class__ is object:
-            cur_p, cur_o = p, object()
-            rn = rank = dense = 0
-            equals = 1
-            sv = cv = mn = mx = sf = cf = None
-            cv = cf = 0
-        rn += 1
-        if o == cur_o and rn > 1:
-            equals += 1
-        else:
-            rank += equals if rn > 1 else 1
-            dense += 1
-            equals = 1
-            cur_o = o
-        if v is not None:
-            sv = v if sv is None else sv + v
-            cv += 1
-            mn = v if mn is None else min(mn, v)
-            mx = v if mx is None else max(mx, v)
-        if f is not None:
-            sf = f if sf is None else sf + f
-            cf += 1
-        vals = {"ROW_NUMBER": rn, "RANK": rank, "DENSE_RANK": dense, "SUM_v": sv, "COUNT_v": cv, "MIN_v": mn, "MAX_v": mx,
-                "AVG_v": None if cv == 0 else sv / cv, "SUM_f": sf}
-        out.append(tuple(vals[k] for k in funcs))
-    return out
-
-
 @pytest.mark.parametrize("n,n_parts", [(5_000, 40), (300_000, 7), (120_000, 30_000)])
 def test_window_functions_over_sorted_partitions(n, n_parts):
     # WindowExec (window_exec.rs:162-345): input sorted by (partition, order); ROW_NUMBER / RANK / DENSE_RANK and running SUM / COUNT /
@@ -255,7 +223,10 @@ def test_window_functions_over_sorted_partitions(n, n_parts):
     assert sorted(rows, key=repr) == sorted(zip(*[t[c].to_pylist() for c in ["p", "o", "v", "f"]]), key=repr)          # same rows
     keys = [(r[0] is not None, r[0] if r[0] is not None else 0, r[1] is not None, r[1] if r[1] is not None else 0) for r in rows]
     assert keys == sorted(keys)                                                                                       # in window order
-    exp = _window_reference(rows, ["ROW_NUMBER", "RANK", "DENSE_RANK", "SUM_v", "COUNT_v", "MIN_v", "MAX_v", "AVG_v", "SUM_f"])
+    v_of, f_of = (lambda r: r[2]), (lambda r: r[3])
+    exp = oracle.window_functions(rows, lambda r: r[0], lambda r: r[1],
+                                  [("ROW_NUMBER", None, None), ("RANK", None, None), ("DENSE_RANK", None, None), ("SUM", v_of, None), ("COUNT", v_of, None),
+                                   ("MIN", v_of, None), ("MAX", v_of, None), ("AVG", v_of, None), ("SUM", f_of, None)])
     out = list(zip(*[got[c].to_pylist() for c in ["rn", "rk", "dr", "sv", "cv", "mn", "mx", "av", "sf"]]))
     for i, (g, e) in enumerate(zip(out, exp)):
         assert g[:7] == e[:7], (i, rows[i], g, e)
@@ -310,34 +281,10 @@ def test_window_functions_that_look_at_the_whole_partition():
     got = run(P.window(src, wex, [P.col("p")], [P.sort_expr(P.col("o"))]), {"t": t}, chunk=40_000)
     rows = list(zip(*[got[c].to_pylist() for c in ["p", "o", "v", "s"]]))
     assert len(rows) == n
-    # partitions and peer groups in the output order
-    exp = []
-    i = 0
-    while i < n:
-        j = i
-        while j < n and rows[j][0] == rows[i][0]:
-            j += 1
-        part = rows[i:j]
-        size = len(part)
-        k = 0
-        rank = 1
-        while k < size:
-            m = k
-            while m < size and part[m][1] == part[k][1]:
-                m += 1
-            for q in range(k, m):
-                pr = 0.0 if size <= 1 else (rank - 1) / (size - 1)
-                cd = m / size
-                lead1 = part[q + 1][2] if q + 1 < size else None
-                lag2 = part[q - 2][2] if q - 2 >= 0 else -7
-                leads = part[q + 3][3] if q + 3 < size else "none"
-                nth3 = part[2][2] if q >= 2 else None
-                nn = [x[3] for x in part[:q + 1] if x[3] is not None]
-                nth2nn = nn[1] if len(nn) >= 2 else None
-                exp.append((pr, cd, lead1, lag2, leads, nth3, nth2nn))
-            rank += m - k
-            k = m
-        i = j
+    v_of, s_of = (lambda r: r[2]), (lambda r: r[3])
+    exp = oracle.window_functions(rows, lambda r: r[0], lambda r: r[1],
+                                  [("PERCENT_RANK", None, None), ("CUME_DIST", None, None), ("LEAD", v_of, (1, lambda r: None)), ("LEAD", v_of, (-2, lambda r: -7)),
+                                   ("LEAD", s_of, (3, lambda r: "none")), ("NTH_VALUE", v_of, 3), ("NTH_VALUE_IGNORE_NULLS", s_of, 2)])
     out = list(zip(*[got[c].to_pylist() for c in ["pr", "cd", "lead1", "lag2", "leads", "nth3", "nth2nn"]]))
     for r, (g, e) in enumerate(zip(out, exp)):
         assert abs(g[0] - e[0]) < 1e-12 and abs(g[1] - e[1]) < 1e-12 and g[2:] == e[2:], (r, rows[r], g, e)
