@@ -112,7 +112,14 @@ def _plans():
              P.range_repartition([P.sort_expr(P.col("a"))], 3, [([10, 20], I)])]
     writers = [P.shuffle_writer(src, p, "/tmp/d", "/tmp/i") for p in parts]
     misc = [P.limit(src, 5, 1), P.rename_columns(src, [f"c{i}" for i in range(len(T))]), P.union([src, src], T), P.ipc_reader(T, "blocks")]
-    return [proj, agg, agg_f, sort, scan] + joins + writers + misc
+    # nodes added in round 2 (appended: the positions above are used by index)
+    expand = P.expand(src, pa.schema([("a", L), ("g", L)]), [[P.col("a"), P.lit(0, L)], [P.lit(None, L), P.lit(1, L)]])
+    window = P.window(P.sort(src, [P.sort_expr(P.col("a")), P.sort_expr(P.col("b"))]),
+                      [P.window_expr("rk", I, "RANK"), P.window_expr("sb", L, "SUM", [P.col("b")]), P.window_expr("ld", L, "LEAD", [P.col("b"), P.lit(1, I), P.lit(None, L)]),
+                       P.window_expr("nv", S, "NTH_VALUE_IGNORE_NULLS", [P.col("s"), P.lit(2, I)]), P.window_expr("cd", pa.float64(), "CUME_DIST")],
+                      [P.col("a")], [P.sort_expr(P.col("b"))])
+    limited = P.window(src, [P.window_expr("rk", I, "DENSE_RANK")], [P.col("a")], [P.sort_expr(P.col("b"), False, False)], group_limit=2, output_window_cols=False)
+    return [proj, agg, agg_f, sort, scan] + joins + writers + misc + [expand, window, limited, P.ipc_writer(src, "consumer")]
 
 
 def test_every_encoded_plan_is_a_well_formed_reference_message():
@@ -124,7 +131,7 @@ def test_every_encoded_plan_is_a_well_formed_reference_message():
     # the walk really went through the messages of the path (a vacuous pass would not)
     nodes = {f for m, f in seen if m == "PhysicalPlanNode"}
     assert nodes == {"ffi_reader", "ipc_reader", "filter", "projection", "agg", "sort", "parquet_scan", "hash_join", "sort_merge_join", "broadcast_join",
-                     "shuffle_writer", "limit", "rename_columns", "union"}
+                     "shuffle_writer", "limit", "rename_columns", "union", "expand", "window", "ipc_writer"}
     exprs = {f for m, f in seen if m == "PhysicalExprNode"}
     assert {"column", "literal", "bound_reference", "binary_expr", "agg_expr", "is_null_expr", "is_not_null_expr", "not_expr", "case_", "cast",
             "try_cast", "sort", "negative", "in_list", "scalar_function", "like_expr", "sc_and_expr", "sc_or_expr", "string_starts_with_expr",
