@@ -1526,6 +1526,9 @@ struct ParquetScanExec : Operator, FusedScanSource {
         if (use_lanes || getenv("AURON_DISABLE_FUSED_SCAN_AGG")) return false;
         auto col_ok = [&](int c) { return c >= 0 && c < (int)projection.size() && !is_part_col(projection[c]) && fused_type_ok(table_schema.fields[projection[c]].type); };
         if (!col_ok(spec.key_col)) return false;
+        // One predicate COLUMN (any number of conjuncts on it: they fold into one interval).  The kernels loop over predicate columns, but
+        // that loop has no GPU parity test yet; until it has one, conjunctions over several columns run operator by operator.
+        if (spec.pred_cols.size() > 1 && !getenv("AURON_FUSED_MULTI_PREDICATE")) return false;
         for (int c : spec.pred_cols)
             if (!col_ok(c)) return false;
         for (auto& a : spec.accs)

@@ -327,3 +327,11 @@ def test_fused_staged_tiles_match_the_tile_kernel(tmp_path, monkeypatch):
     p2 = _write(str(tmp_path / "b.parquet"), t, row_group_size=300_000, data_page_size=128 * 1024, use_dictionary=["item", "date", "qty"])
     got3, met3 = _check([p2], t, "item", [("date", "Gt", 2451500)], [("SUM", "dense"), ("COUNT", "qty")])
     assert sum(v for (op, name), v in met3.items() if name == "fused_staged_tiles") > 0, met3
+
+
+def test_predicates_on_several_columns_run_operator_by_operator(tmp_path):
+    # a conjunction over two columns is not fused (scan_parquet.cc can_fuse): the regular Filter -> HashAggregate path answers
+    rng = np.random.default_rng(13)
+    t = _store_sales(rng, 120_000)
+    p = _write(str(tmp_path / "a.parquet"), t, row_group_size=50_000)
+    _check([p], t, "item", DATE_PREDS + [("qty", "Gt", 40)], SUM_COUNT + [("COUNT*", None)], expect_fused=False)
