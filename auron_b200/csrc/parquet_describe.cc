@@ -120,29 +120,32 @@ std::string describe(const char* path) {
                         split_head_out += head_out;
                         split_stored += body_out - head_out;
                     }
-                } else if ((cm.codec == pq::CODEC_UNCOMPRESSED || (h.type == pq::PAGE_DATA_V2 && !h.v2_compressed)) && h.uncompressed_size > lvl) {
+                } else if ((cm.codec == pq::CODEC_UNCOMPRESSED || (h.type == pq::PAGE_DATA_V2 && !h.v2_compressed)) && h.uncompressed_size > lvl && h.compressed_size > lvl) {
                     out.assign(body + lvl, body + h.compressed_size);
                     out.resize(out.size() + 8);
                     have_body = true;
                 }
+                const size_t blen = have_body ? out.size() - 8 : 0;   // bytes of `out` that belong to the page (sizes in a damaged header are not trusted)
                 const bool delta = h.encoding == pq::ENC_DELTA_BINARY_PACKED || h.encoding == pq::ENC_DELTA_LENGTH_BYTE_ARRAY || h.encoding == pq::ENC_DELTA_BYTE_ARRAY;
                 if (have_body && delta && (h.type == pq::PAGE_DATA || h.type == pq::PAGE_DATA_V2)) {
                     size_t vo = 0;   // value section inside `out`
                     if (h.type == pq::PAGE_DATA && max_def > 0) {
+                        AURON_CHECK(blen >= 4, "corrupt parquet page");
                         uint32_t dl = 0;
                         memcpy(&dl, out.data(), 4);
                         vo = 4 + (size_t)dl;
                     }
-                    const size_t vlen = (size_t)(h.uncompressed_size - lvl) - vo;
+                    AURON_CHECK(vo <= blen && h.num_values >= 0, "corrupt parquet page levels");
+                    const size_t vlen = blen - vo;
                     if (h.encoding == pq::ENC_DELTA_BINARY_PACKED) {
                         std::vector<int64_t> vals;
                         size_t dp = 0;
-                        pq::delta_binary_decode(out.data() + vo, vlen, dp, vals);
+                        pq::delta_binary_decode(out.data() + vo, vlen, dp, vals, (size_t)h.num_values);
                         delta_values += (int64_t)vals.size();
                         for (int64_t v : vals) delta_sum += (uint64_t)(cm.type == pq::PT_INT32 ? (int64_t)(int32_t)v : v);
                     } else {
                         int32_t nv = 0;
-                        const std::vector<uint8_t> plain = pq::delta_strings_to_plain(out.data() + vo, vlen, h.encoding == pq::ENC_DELTA_BYTE_ARRAY, &nv);
+                        const std::vector<uint8_t> plain = pq::delta_strings_to_plain(out.data() + vo, vlen, h.encoding == pq::ENC_DELTA_BYTE_ARRAY, &nv, (size_t)h.num_values);
                         delta_values += nv;
                         delta_bytes += (int64_t)plain.size() - 4 * (int64_t)nv;
                         size_t q = 0;

@@ -413,10 +413,10 @@ static bool delta_varint(const uint8_t* p, size_t n, size_t& pos, uint64_t& v) {
     return false;
 }
 // one DELTA_BINARY_PACKED stream at p[pos...] -> values; pos ends behind the stream
-void delta_binary_decode(const uint8_t* p, size_t n, size_t& pos, std::vector<int64_t>& out) {
+void delta_binary_decode(const uint8_t* p, size_t n, size_t& pos, std::vector<int64_t>& out, size_t max_values) {
     uint64_t bs = 0, nm = 0, total = 0, fv = 0;
     AURON_CHECK(delta_varint(p, n, pos, bs) && delta_varint(p, n, pos, nm) && delta_varint(p, n, pos, total) && delta_varint(p, n, pos, fv), "corrupt DELTA_BINARY_PACKED header");
-    AURON_CHECK(nm > 0 && nm <= 512 && bs > 0 && bs <= (1u << 20) && bs % nm == 0 && (bs / nm) % 8 == 0 && total <= (1ull << 31), "corrupt DELTA_BINARY_PACKED header");
+    AURON_CHECK(nm > 0 && nm <= 512 && bs > 0 && bs <= (1u << 20) && bs % nm == 0 && (bs / nm) % 8 == 0 && total <= (uint64_t)max_values, "corrupt DELTA_BINARY_PACKED header");
     const size_t per_mini = (size_t)(bs / nm);
     out.clear();
     out.reserve((size_t)total);
@@ -447,17 +447,18 @@ void delta_binary_decode(const uint8_t* p, size_t n, size_t& pos, std::vector<in
     }
 }
 // value section of a DELTA_LENGTH_BYTE_ARRAY (`front_coded` false) or DELTA_BYTE_ARRAY page -> PLAIN ([u32 length][bytes] ...)
-std::vector<uint8_t> delta_strings_to_plain(const uint8_t* p, size_t n, bool front_coded, int32_t* n_values) {
+std::vector<uint8_t> delta_strings_to_plain(const uint8_t* p, size_t n, bool front_coded, int32_t* n_values, size_t max_values) {
     size_t pos = 0;
     std::vector<int64_t> prefix, lens;
-    if (front_coded) delta_binary_decode(p, n, pos, prefix);
-    delta_binary_decode(p, n, pos, lens);
+    if (front_coded) delta_binary_decode(p, n, pos, prefix, max_values);
+    delta_binary_decode(p, n, pos, lens, max_values);
     AURON_CHECK(!front_coded || prefix.size() == lens.size(), "corrupt DELTA_BYTE_ARRAY page");
     std::vector<uint8_t> out;
     size_t prev_at = 0, prev_len = 0;
     for (size_t i = 0; i < lens.size(); i++) {
         const int64_t pl = front_coded ? prefix[i] : 0, sl = lens[i];
-        AURON_CHECK(pl >= 0 && sl >= 0 && (size_t)pl <= prev_len && (size_t)sl <= n - pos && pl + sl <= INT32_MAX, "corrupt delta-encoded string page");
+        AURON_CHECK(pl >= 0 && sl >= 0 && (size_t)pl <= prev_len && pos <= n && (size_t)sl <= n - pos && pl + sl <= INT32_MAX && out.size() + 4 + (size_t)(pl + sl) <= (size_t)INT32_MAX,
+                    "corrupt delta-encoded string page");
         const uint32_t len = (uint32_t)(pl + sl);
         const size_t at = out.size();
         out.resize(at + 4 + len);

@@ -70,8 +70,9 @@ struct LitPiece {
 // literals behind it (offsets into p).
 bool snappy_split(const uint8_t* p, int64_t n, int64_t unc, int max_tokens, int64_t* head_in, int64_t* head_out, std::vector<LitPiece>* pieces);
 // one DELTA_BINARY_PACKED stream at p[pos...] -> values; pos ends behind the stream
-void delta_binary_decode(const uint8_t* p, size_t n, size_t& pos, std::vector<int64_t>& out);
+// (a stream may not announce more than `max_values` values: the page header's count -- zero-width miniblocks cost no input bytes)
+void delta_binary_decode(const uint8_t* p, size_t n, size_t& pos, std::vector<int64_t>& out, size_t max_values);
 // value section of a DELTA_LENGTH_BYTE_ARRAY (`front_coded` false) or DELTA_BYTE_ARRAY page -> PLAIN ([u32 length][bytes] ...)
-std::vector<uint8_t> delta_strings_to_plain(const uint8_t* p, size_t n, bool front_coded, int32_t* n_values);
+std::vector<uint8_t> delta_strings_to_plain(const uint8_t* p, size_t n, bool front_coded, int32_t* n_values, size_t max_values);
 }  // namespace pq
 }  // namespace auron

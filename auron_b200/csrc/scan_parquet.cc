@@ -463,8 +463,8 @@ struct ParquetScanExec : Operator, FusedScanSource {
     static bool snappy_split(const uint8_t* p, int64_t n, int64_t unc, int max_tokens, int64_t* head_in, int64_t* head_out, std::vector<LitPiece>* pieces) {
         return pq::snappy_split(p, n, unc, max_tokens, head_in, head_out, pieces);
     }
-    static std::vector<uint8_t> delta_strings_to_plain(const uint8_t* p, size_t n, bool front_coded, int32_t* n_values) {
-        return pq::delta_strings_to_plain(p, n, front_coded, n_values);
+    static std::vector<uint8_t> delta_strings_to_plain(const uint8_t* p, size_t n, bool front_coded, int32_t* n_values, size_t max_values) {
+        return pq::delta_strings_to_plain(p, n, front_coded, n_values, max_values);
     }
     static bool gpu_snappy() {
         return getenv("AURON_HOST_SNAPPY") == nullptr;   // AURON_HOST_SNAPPY=1: decompress on the host cores instead
@@ -621,7 +621,7 @@ struct ParquetScanExec : Operator, FusedScanSource {
             if (delta_strings) {   // (never on_device: the body is on the host, in the file image or in out.unc)
                 const std::vector<uint8_t> head(hp(0), hp(0) + o);
                 int32_t nn = 0;
-                const std::vector<uint8_t> plain = delta_strings_to_plain(hp(o + gap), (size_t)(total - o - gap), h.encoding == pq::ENC_DELTA_BYTE_ARRAY, &nn);
+                const std::vector<uint8_t> plain = delta_strings_to_plain(hp(o + gap), (size_t)(total - o - gap), h.encoding == pq::ENC_DELTA_BYTE_ARRAY, &nn, (size_t)h.num_values);
                 unc_off = (int64_t)out.unc.size();
                 out.unc.resize(out.unc.size() + head.size() + plain.size() + 8);
                 if (!head.empty()) memcpy(out.unc.data() + unc_off, head.data(), head.size());

@@ -164,6 +164,49 @@ def test_parquet_metadata_reader_survives_damaged_files(tmp_path):
     assert ok > 50 and bad > 50
 
 
+def test_delta_and_split_walkers_survive_damaged_page_bodies(tmp_path):
+    # the scan's host-side page walkers (DELTA_BINARY_PACKED / DELTA_LENGTH_BYTE_ARRAY / DELTA_BYTE_ARRAY decoders, the Snappy tag walk)
+    # on files whose PAGE BODIES are damaged: every length, offset and bit width comes from untrusted bytes, so the answer must be an
+    # error or a description -- never a crash, a hang or an allocation of the advertised size
+    import ctypes as C
+    import random
+    import numpy as np
+    import pyarrow.parquet as pq
+    rng = np.random.default_rng(2)
+    n = 30_000
+    t = pa.table({"a": pa.array(np.sort(rng.integers(-2**31, 2**31 - 1, n)).astype(np.int32), mask=rng.random(n) < 0.03),
+                  "b": pa.array(rng.integers(-2**63, 2**63 - 1, n, dtype=np.int64)),
+                  "dl": pa.array([f"w{int(i) % 977}" for i in rng.integers(0, 10**6, n)], mask=rng.random(n) < 0.05),
+                  "db": pa.array(sorted(f"key-{int(x):09d}" for x in rng.integers(0, 10**9, n))),
+                  "noise": pa.array(rng.integers(-2**31, 2**31 - 1, n).astype(np.int32), mask=rng.random(n) < 0.05)})
+    enc = {"a": "DELTA_BINARY_PACKED", "b": "DELTA_BINARY_PACKED", "dl": "DELTA_LENGTH_BYTE_ARRAY", "db": "DELTA_BYTE_ARRAY", "noise": "PLAIN"}
+    L = runtime.lib()
+    L.auron_b200_parquet_describe.restype = C.c_int64
+    L.auron_b200_parquet_describe.argtypes = [C.c_char_p, C.c_char_p, C.c_int64]
+    buf = C.create_string_buffer(1 << 22)
+    random.seed(7)
+    ok = bad = 0
+    for comp, ver in (("NONE", "1.0"), ("NONE", "2.0"), ("SNAPPY", "1.0"), ("SNAPPY", "2.0")):
+        src = str(tmp_path / f"{comp}{ver}.parquet")
+        pq.write_table(t, src, compression=comp, data_page_version=ver, use_dictionary=False, column_encoding=enc, row_group_size=n, data_page_size=256 * 1024)
+        raw = open(src, "rb").read()
+        md = pq.ParquetFile(src).metadata.row_group(0)
+        spans = [(md.column(c).data_page_offset, md.column(c).data_page_offset + md.column(c).total_compressed_size) for c in range(md.num_columns)]
+        mut = str(tmp_path / "mut.parquet")
+        for _ in range(250):
+            b = bytearray(raw)
+            for _ in range(random.randint(1, 3)):
+                lo, hi = random.choice(spans)
+                r = random.random()
+                pos = random.randint(lo, min(hi - 1, lo + 200)) if r < 0.5 else random.randint(lo, hi - 1)   # page / stream headers sit at the front
+                b[pos] = random.randint(0, 255)
+            open(mut, "wb").write(bytes(b))
+            rc = L.auron_b200_parquet_describe(mut.encode(), buf, len(buf))
+            ok += rc > 0
+            bad += rc < 0
+    assert ok > 50 and bad > 50
+
+
 def _jni_function_table():
     """JNINativeInterface_ in declaration order, generated from the structure of the JNI specification's "Interface Function
     Table" (4 reserved slots, then the functions; the Call*Method families come as plain / V / A triples per result type)."""
